@@ -1,0 +1,144 @@
+/* vitpose_b200 — C ABI of the B200-native ViTPose top-down inference hot path.
+ *
+ * The reference (MiraPurkrabek/ViTPose, a fork of mmpose 0.24) is 100 % Python and has no FFI: its
+ * extension points are the mmcv registry classes and a few free functions.  This header is the
+ * boundary a maintainer binds instead (ctypes stub in INTEGRATION.md); every entry point names the
+ * reference code it replaces.  Plain pointers and sizes only — no torch types.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless stated otherwise; the caller owns all memory,
+ *    including outputs and the workspace; the library never allocates device memory;
+ *  - calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream);
+ *  - return value 0 = ok; non-zero = error, message via vpb_last_error() (thread-local);
+ *  - "bf16" buffers are packed __nv_bfloat16; weights are [out_features, in_features] row-major,
+ *    i.e. exactly torch's nn.Linear layout cast to bf16.
+ */
+#ifndef VITPOSE_B200_H_
+#define VITPOSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPB_ABI_VERSION 1
+
+int vpb_abi_version(void);
+const char* vpb_last_error(void);
+
+/* ---- model description ---------------------------------------------------------------------
+ * Mirrors the `model = dict(...)` block of a ViTPose config
+ * (configs/body/2d_kpt_sview_rgb_img/topdown_heatmap/coco/ViTPose_base_coco_256x192.py:52-84). */
+typedef struct vpb_model_desc {
+  int32_t img_h, img_w;        /* 256, 192 */
+  int32_t embed_dim;           /* D */
+  int32_t depth;               /* number of Blocks */
+  int32_t num_heads;
+  int32_t mlp_hidden;          /* int(D * mlp_ratio) */
+  float ln_eps;                /* 1e-6, vit.py:212 */
+  int32_t has_last_norm;       /* ViT(last_norm=True) */
+  int32_t num_deconv;          /* classic decoder: 2; simple decoder: 0 */
+  int32_t deconv_channels[3];  /* num_deconv_filters */
+  int32_t upsample;            /* simple decoder: 4; classic: 0 */
+  int32_t final_kernel;        /* 1 (classic) or 3 (simple) */
+  int32_t num_keypoints;       /* out_channels */
+} vpb_model_desc;
+
+/* One transformer Block (vit.py:117-140). *_w are bf16, everything else fp32. */
+typedef struct vpb_block_weights {
+  const float* ln1_g; const float* ln1_b;
+  const void* qkv_w;  const float* qkv_b;    /* [3D, D], [3D]  (attn.qkv)  */
+  const void* proj_w; const float* proj_b;   /* [D, D], [D]    (attn.proj) */
+  const float* ln2_g; const float* ln2_b;
+  const void* fc1_w;  const float* fc1_b;    /* [4D, D], [4D]  (mlp.fc1)   */
+  const void* fc2_w;  const float* fc2_b;    /* [D, 4D], [D]   (mlp.fc2)   */
+} vpb_block_weights;
+
+/* Repacked weights (built once by the host side, vitpose_b200/weights.py):
+ *  patch_w  bf16 [D, 768]      = patch_embed.proj.weight.reshape(D, 3*16*16)
+ *  pos      fp32 [T, D]        = pos_embed[0, 1:] + pos_embed[0, :1]           (vit.py:320)
+ *  deconv_w bf16 [4][Cout][4*Cin]: per output parity (py,px) the 2x2 taps of the k4/s2/p1 transposed conv,
+ *           tap t=(ty,tx): ty=0 -> kh = (py==0 ? 1 : 2), ty=1 -> kh = (py==0 ? 3 : 0) (same for x);
+ *           column = t*Cin + ci, value = W[ci, co, kh, kw]
+ *  deconv_scale/shift fp32 [Cout]: BatchNorm2d(eval) folded: scale = g/sqrt(var+eps), shift = b - mean*scale
+ *  final_w  bf16 [K, Cin] (1x1) or [K][9*Cin] (3x3, column = (ky*3+kx)*Cin + ci);  final_b fp32 [K] */
+typedef struct vpb_weights {
+  const void* patch_w; const float* patch_b; const float* pos;
+  const vpb_block_weights* blocks;           /* HOST pointer to `depth` structs */
+  const float* last_g; const float* last_b;
+  const void* deconv_w[3]; const float* deconv_scale[3]; const float* deconv_shift[3];
+  const void* final_w; const float* final_b;
+} vpb_weights;
+
+/* Bytes of scratch `vpb_vitpose_forward` needs for `images` crops (count the flipped copies too). */
+size_t vpb_workspace_bytes(const vpb_model_desc* desc, int images);
+
+/* backbone + head for n crops (+ their horizontal flips when flip != 0):
+ *   img        fp32 [n, 3, img_h, img_w]  (NCHW, as the reference's `img` argument)
+ *   heatmaps   fp32 [(flip ? 2n : n), K, img_h/4, img_w/4]; rows [n, 2n) are the RAW outputs of the flipped
+ *              pass (not yet flipped back) — feed both halves to vpb_decode_heatmaps
+ *   features   optional bf16 [(flip ? 2n : n), T, D] token-major backbone output (NULL to skip)
+ * Replaces ViT.forward (vit.py:313-337), TopdownHeatmapSimpleHead.forward (simple_head.py:197-202) and the
+ * second, flipped pass of TopDown.forward_test (top_down.py:179-186). */
+int vpb_vitpose_forward(const vpb_model_desc* desc, const vpb_weights* w, const float* img, int n, int flip,
+                        void* workspace, size_t workspace_bytes, float* heatmaps, void* features, void* stream);
+
+/* decode modes = the branches of keypoints_from_heatmaps (top_down_eval.py:562-612) */
+enum { VPB_DECODE_NONE = 0, VPB_DECODE_DEFAULT = 1, VPB_DECODE_UNBIASED = 2, VPB_DECODE_UDP_DARK = 3 };
+
+/* flip_back + shift + average + argmax + refine + transform_preds, fused.
+ *   hm            fp32 [N,K,H,W]
+ *   hm_flipped    fp32 [N,K,H,W] raw heatmaps of the flipped pass, or NULL (no flip test)
+ *   flip_index    int32 [K] channel permutation of flip_back (post_transforms.py:138-141), or NULL
+ *   shift_heatmap test_cfg['shift_heatmap'] (simple_head.py:223-224)
+ *   mode/kernel   VPB_DECODE_*, test_cfg['modulate_kernel']
+ *   use_udp       selects the (W-1)/(H-1) scaling of transform_preds (post_transforms.py:183-188)
+ *   apply_transform 0 -> preds stay in heatmap pixels (host applies transform_preds itself)
+ *   center, scale fp32 [N,2]
+ *   preds         fp32 [N,K,2];  maxvals fp32 [N,K,1]
+ *   merged_out    optional fp32 [N,K,H,W]: the averaged heatmap (`output_heatmap` of forward_test)
+ *   argmax_out    optional int32 [N,K]: flat argmax index (bit-exact vs np.argmax)
+ * Replaces TopdownHeatmapSimpleHead.inference_model's host half (simple_head.py:217-226),
+ * top_down.py:187-188 and keypoints_from_heatmaps (top_down_eval.py:474-622, GaussianHeatmap branches). */
+int vpb_decode_heatmaps(const float* hm, const float* hm_flipped, const int32_t* flip_index, int shift_heatmap,
+                        int N, int K, int H, int W, int mode, int kernel, int use_udp, int apply_transform,
+                        const float* center, const float* scale, float* preds, float* maxvals, float* merged_out,
+                        int32_t* argmax_out, void* stream);
+
+/* flip_back (post_transforms.py:110-147, GaussianHeatmap) + optional shift_heatmap (simple_head.py:223-224):
+ * out[n,k,y,x] = in[n, flip_index[k], y, W-1-xs], xs = shift ? max(x-1,0) : x.  in/out fp32 [N,K,H,W]. */
+int vpb_flip_back(const float* in, const int32_t* flip_index, float* out, int N, int K, int H, int W, int shift,
+                  void* stream);
+/* transform_preds (post_transforms.py:150-194) in float32: coords/out fp32 [N,K,2], center/scale fp32 [N,2],
+ * heatmap size (W, H). */
+int vpb_transform_preds(const float* coords, const float* center, const float* scale, float* out, int N, int K,
+                        int W, int H, int use_udp, void* stream);
+
+/* ---- individual operators (used by the per-kernel parity tests and by vpb_vitpose_forward) ---- */
+enum {
+  VPB_EPI_BIAS_BF16 = 0,  /* out bf16 [M,ldo]  = A.B^T + bias                         (attn.qkv)            */
+  VPB_EPI_GELU_BF16 = 1,  /* out bf16 [M,ldo]  = gelu_erf(A.B^T + bias)               (mlp.fc1 + nn.GELU)   */
+  VPB_EPI_RESID_F32 = 2,  /* out fp32 [M,ldo]  = aux[M,ldo] + A.B^T + bias            (attn.proj / mlp.fc2 + residual) */
+  VPB_EPI_POS_F32 = 3,    /* out fp32 [M,ldo]  = A.B^T + bias + aux[row % period, N]  (patch embed + pos embed) */
+  VPB_EPI_NCHW_F32 = 4    /* out fp32 [M/period, N, period] = A.B^T + bias            (final 1x1 conv)      */
+};
+/* C = A[M,K] (bf16, row-major) x B[N,K]^T (bf16, row-major) on tcgen05 tensor cores. max_ctas <= 0: one per SM. */
+int vpb_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, void* out,
+                  int ldo, const float* aux, int period, int max_ctas, void* stream);
+int vpb_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int M, int D, float eps,
+                       void* stream);
+int vpb_im2col_patch16(const float* img, void* patches, int n, int H, int W, int flip, void* stream);
+int vpb_attention(const void* qkv, void* out, int n, int T, int heads, int head_dim, float scale, void* stream);
+int vpb_deconv4x4s2_bn_relu(const void* in, const void* wphase, const float* scale, const float* shift, void* out,
+                            int n, int h, int w, int cin, int cout, void* stream);
+int vpb_conv3x3_nchw(const void* in, const void* w9, const float* bias, float* out, int n, int h, int w, int cin,
+                     int cout, void* stream);
+int vpb_relu_upsample_nhwc(const void* in, void* out, int n, int h, int w, int C, int factor, void* stream);
+int vpb_tokens_to_nchw_f32(const void* tokens, float* out, int n, int T, int D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITPOSE_B200_H_ */

@@ -1,0 +1,143 @@
+"""Decode parity (-m gpu): the fused CUDA decode, called through the C ABI, against the oracle
+(oracle/decode_np.py) and against golden vectors produced by the unmodified reference.
+Bar: argmax indices and maxvals bit-exact; coordinates within 1e-3 px (float32 blur/log ulps)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode_np as O
+from oracle.make_golden import DECODE_MODES, adversarial_heatmaps
+from vitpose_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+COORD_TOL = 1e-3
+
+
+def _gpu_decode(hm, center, scale, mode_kw, hm_f=None, pairs=None, shift=False, want_merged=False):
+    from vitpose_b200 import ops
+    from vitpose_b200.engine import resolve_decode_mode
+    dev = torch.device('cuda:0')
+    mode = resolve_decode_mode(mode_kw.get('post_process', 'default'), False, mode_kw.get('use_udp', False))
+    K = hm.shape[1]
+    fi = None
+    if hm_f is not None:
+        fi = torch.from_numpy(O.flip_index(K, pairs).astype(np.int32)).to(dev)
+    r = ops.decode(torch.from_numpy(hm).to(dev), None if hm_f is None else torch.from_numpy(hm_f).to(dev), fi, shift,
+                   mode, mode_kw.get('kernel', 11), mode_kw.get('use_udp', False),
+                   torch.from_numpy(center.astype(np.float32)).to(dev),
+                   torch.from_numpy(scale.astype(np.float32)).to(dev), want_merged=want_merged, want_argmax=True)
+    torch.cuda.synchronize()
+    return {k: (v.cpu().numpy() if v is not None else None) for k, v in r.items()}
+
+
+def _compare(r, preds_ref, maxvals_ref, hm):
+    N, K, H, W = hm.shape
+    np.testing.assert_array_equal(r['argmax'], hm.reshape(N, K, -1).argmax(2).astype(np.int32))   # bit-exact
+    np.testing.assert_array_equal(r['maxvals'], maxvals_ref.astype(np.float32))                  # bit-exact
+    ok = np.isfinite(preds_ref)
+    assert np.array_equal(np.isfinite(r['preds']), ok)
+    np.testing.assert_allclose(r['preds'][ok], preds_ref[ok], atol=COORD_TOL, rtol=0)
+
+
+@pytest.mark.parametrize('mode', sorted(DECODE_MODES))
+def test_decode_vs_golden(golden_dir, mode):
+    g = np.load(os.path.join(golden_dir, 'decode_cases.npz'))
+    r = _gpu_decode(g['heatmaps'], g['center'], g['scale'], DECODE_MODES[mode])
+    _compare(r, g[f'preds_{mode}'], g[f'maxvals_{mode}'], g['heatmaps'])
+
+
+@pytest.mark.parametrize('shift', [0, 1])
+def test_flip_merge_vs_golden(golden_dir, shift):
+    g = np.load(os.path.join(golden_dir, 'decode_cases.npz'))
+    for mode in ('udp_dark', 'default'):
+        r = _gpu_decode(g['heatmaps'], g['center'], g['scale'], DECODE_MODES[mode], g['heatmaps_flipped_raw'],
+                        g['flip_pairs'].tolist(), bool(shift), want_merged=True)
+        np.testing.assert_array_equal(r['merged'], g[f'merged_shift{shift}'])                   # bit-exact average
+        ref = g[f'merged_shift{shift}_preds_{mode}']
+        ok = np.isfinite(ref)
+        np.testing.assert_allclose(r['preds'][ok], ref[ok], atol=COORD_TOL, rtol=0)
+
+
+def test_kat_through_cabi(golden_dir):
+    """The reference's own KATs (tests/test_evaluation/test_top_down_eval.py:29-89) through the CUDA path."""
+    g = np.load(os.path.join(golden_dir, 'kat.npz'))
+    r = _gpu_decode(g['heatmaps'], g['center'], g['scale'], dict(post_process='default'))
+    np.testing.assert_array_almost_equal(r['preds'], np.array([[[126, 126]]]), decimal=4)
+    np.testing.assert_array_almost_equal(r['maxvals'], np.array([[[2]]]), decimal=4)
+    r = _gpu_decode(g['heatmaps'], g['center'], g['scale'], dict(post_process='unbiased'))
+    np.testing.assert_array_almost_equal(r['preds'], np.array([[[126, 126]]]), decimal=4)
+    hm = np.ones((32, 17, 64, 64), dtype=np.float32)
+    hm[:, :, 31, 31] = 2
+    r = _gpu_decode(hm, g['udp_center'], g['udp_scale'], dict(use_udp=True))
+    np.testing.assert_array_almost_equal(r['preds'], np.tile([76, 76], (32, 17, 1)), decimal=0)
+    np.testing.assert_allclose(r['preds'], g['preds_udp'], atol=COORD_TOL)
+    np.testing.assert_array_almost_equal(r['maxvals'], np.tile([2], (32, 17, 1)), decimal=4)
+
+
+@pytest.mark.parametrize('seed,K', [(0, 17), (1, 133), (2, 5)])
+@pytest.mark.parametrize('mode', ['udp_dark', 'default', 'unbiased', 'none'])
+def test_decode_vs_oracle_random(seed, K, mode):
+    n = 6
+    hm = synthetic.gaussian_peak_heatmaps(n, K, seed)
+    hm[0, 0] = 0
+    hm[n - 1, K - 1] = -1.0
+    metas = synthetic.synthetic_metas(n, K, seed)
+    c = np.stack([m['center'] for m in metas])
+    s = np.stack([m['scale'] for m in metas])
+    with np.errstate(all='ignore'):
+        p, m = O.keypoints_from_heatmaps(hm, c, s, **DECODE_MODES[mode])
+    r = _gpu_decode(hm, c, s, DECODE_MODES[mode])
+    _compare(r, p, m, hm)
+
+
+@pytest.mark.parametrize('mode', ['udp_dark', 'default'])
+def test_decode_with_flip_vs_oracle(mode):
+    n, K = 5, 17
+    from vitpose_b200.configs import COCO17_FLIP_PAIRS
+    hm = synthetic.gaussian_peak_heatmaps(n, K, 3)
+    hm_f = synthetic.gaussian_peak_heatmaps(n, K, 4)
+    metas = synthetic.synthetic_metas(n, K, 3)
+    c = np.stack([m['center'] for m in metas])
+    s = np.stack([m['scale'] for m in metas])
+    for shift in (False, True):
+        merged = O.merge_flip(hm, hm_f, COCO17_FLIP_PAIRS, shift)
+        p, m = O.keypoints_from_heatmaps(merged, c, s, **DECODE_MODES[mode])
+        r = _gpu_decode(hm, c, s, DECODE_MODES[mode], hm_f, COCO17_FLIP_PAIRS, shift, want_merged=True)
+        np.testing.assert_array_equal(r['merged'], merged)
+        _compare(r, p, m, merged)
+
+
+def test_decode_full_size_properties():
+    """BASELINE size (256 crops x 17, and 64 x 133): properties that need no oracle run —
+    argmax == torch.argmax on the device-merged map, flip-merge involution, idempotent outputs."""
+    dev = torch.device('cuda:0')
+    from vitpose_b200 import ops, _lib
+    for n, K in ((256, 17), (64, 133)):
+        g = torch.Generator(device='cuda').manual_seed(n)
+        hm = torch.rand(n, K, 64, 48, device=dev, generator=g)
+        hm_f = torch.rand(n, K, 64, 48, device=dev, generator=g)
+        fi = torch.arange(K, device=dev, dtype=torch.int32)
+        c = torch.rand(n, 2, device=dev) * 100
+        s = torch.rand(n, 2, device=dev) + 0.5
+        r = ops.decode(hm, hm_f, fi, False, _lib.DECODE_UDP_DARK, 11, True, c, s, want_merged=True, want_argmax=True)
+        merged = (hm + hm_f.flip(3)) * 0.5
+        assert torch.equal(r['merged'], merged)
+        assert torch.equal(r['argmax'].long(), merged.reshape(n, K, -1).argmax(2))
+        assert torch.equal(r['maxvals'][..., 0], merged.reshape(n, K, -1).amax(2))
+        r2 = ops.decode(merged, None, None, False, _lib.DECODE_UDP_DARK, 11, True, c, s)
+        assert torch.equal(r['preds'], r2['preds'])           # fused merge == decode of the merged map
+        assert torch.isfinite(r['preds']).all()
+
+
+def test_decode_empty_and_errors():
+    from vitpose_b200 import ops, _lib
+    dev = torch.device('cuda:0')
+    r = ops.decode(torch.zeros(0, 17, 64, 48, device=dev), mode=_lib.DECODE_DEFAULT)
+    assert r['preds'].shape == (0, 17, 2)
+    with pytest.raises(_lib.VitposeLibError):
+        ops.decode(torch.zeros(1, 1, 64, 48, device=dev), mode=_lib.DECODE_UNBIASED, kernel=0)
+    with pytest.raises(_lib.VitposeLibError):
+        ops.decode(torch.zeros(1, 1, 64, 48), mode=_lib.DECODE_DEFAULT)          # CPU tensor: no fallback

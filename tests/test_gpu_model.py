@@ -1,0 +1,136 @@
+"""End-to-end parity (-m gpu): registry-built ``TopDown`` on the B200 path vs (a) golden outputs of the
+unmodified reference (tests/golden/model_*.npz) and (b) the torch-fp32 oracle on the same seeded weights.
+
+Tolerances (BASELINE.json north_star): heatmaps within 1e-2 max-abs in bf16 on heads scaled to realistic
+amplitude (std ~0.1; we also bound the error relative to the heatmap std), decoded coordinates within 0.5 px
+wherever the reference's own top-1/top-2 margin exceeds the measured heatmap error, and bit-exact argmax when
+decoding identical fp32 heatmaps (tests/test_gpu_decode.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode_np as O
+from oracle import vitpose_torch as VT
+from vitpose_b200 import configs, synthetic
+
+pytestmark = pytest.mark.gpu
+
+HEATMAP_ATOL = 1e-2
+
+
+def _build(cfg, sd):
+    import vitpose_b200 as V
+    model = V.build_posenet(cfg)
+    model.load_state_dict(sd, strict=True)
+    return model.cuda().eval()
+
+
+def _golden_model(golden_dir, name, decoder):
+    g = np.load(os.path.join(golden_dir, f'model_{name}.npz'))
+    sd = {k[2:]: torch.from_numpy(g[k].astype(np.float32) if g[k].dtype == np.float16 else g[k])
+          for k in g.files if k.startswith('w:')}
+    cfg = configs.tiny_model_cfg(5, decoder, depth=2 if decoder == 'classic' else 1)
+    img = torch.from_numpy(g['img'].astype(np.float32))
+    metas = [dict(center=g['center'][i], scale=g['scale'][i], image_file='', bbox_id=i, bbox_score=1.0,
+                  flip_pairs=g['flip_pairs'].tolist()) for i in range(img.shape[0])]
+    return g, sd, cfg, img, metas
+
+
+def _margin_ok(hm_ref, err):
+    """keypoints whose top-1 / top-2 (outside a 3x3 neighbourhood) margin exceeds 4x the heatmap error"""
+    N, K, H, W = hm_ref.shape
+    flat = hm_ref.reshape(N, K, -1)
+    idx = flat.argmax(2)
+    ok = np.zeros((N, K), dtype=bool)
+    for n in range(N):
+        for k in range(K):
+            y, x = divmod(int(idx[n, k]), W)
+            m = hm_ref[n, k].copy()
+            top = m[y, x]
+            m[max(0, y - 1):y + 2, max(0, x - 1):x + 2] = -np.inf
+            ok[n, k] = (top - m.max()) > 4 * err
+    return ok
+
+
+@pytest.mark.parametrize('name,decoder', [('tiny_classic', 'classic'), ('tiny_simple', 'simple')])
+def test_golden_tiny_model(golden_dir, name, decoder):
+    g, sd, cfg, img, metas = _golden_model(golden_dir, name, decoder)
+    for tag, tc in (('udp', configs.TEST_CFG_UDP), ('shift', configs.TEST_CFG_SHIFT),
+                    ('unbiased', dict(flip_test=True, post_process='unbiased', shift_heatmap=False,
+                                      modulate_kernel=11))):
+        model = _build(dict(cfg, test_cfg=dict(tc)), sd)
+        r = model(img=img.cuda(), img_metas=metas, return_loss=False, return_heatmap=True)
+        ref_hm = g[f'{tag}_heatmap']
+        err = np.abs(r['output_heatmap'] - ref_hm).max()
+        assert err < HEATMAP_ATOL, f'{name}/{tag}: heatmap max-abs err {err:.4g}'
+        assert err < 0.1 * ref_hm.std(), f'{name}/{tag}: err {err:.4g} vs heatmap std {ref_hm.std():.4g}'
+        assert r['preds'].shape == g[f'{tag}_preds'].shape and r['preds'].dtype == np.float32
+        np.testing.assert_allclose(r['boxes'], g[f'{tag}_boxes'], rtol=1e-6)
+        assert r['image_paths'] == ['', ''] and r['bbox_ids'] == [0, 1]
+        ok = _margin_ok(ref_hm, err)
+        d = np.abs(r['preds'][..., :2] - g[f'{tag}_preds'][..., :2]).max(-1)
+        # image-space px; one heatmap px is ~5 image px here, so 0.5 heatmap-px == 2.5 image-px; we hold 0.5 image-px
+        assert (d[ok] < 0.5).all(), f'{name}/{tag}: keypoint error {d[ok].max():.3f}px on confident keypoints'
+        np.testing.assert_allclose(r['preds'][..., 2], g[f'{tag}_preds'][..., 2], atol=HEATMAP_ATOL)
+
+
+def test_backbone_features_golden(golden_dir):
+    g, sd, cfg, img, metas = _golden_model(golden_dir, 'tiny_classic', 'classic')
+    model = _build(cfg, sd)
+    feat = model.backbone(img.cuda()).cpu().numpy()
+    ref = g['features']
+    assert feat.shape == ref.shape
+    err = np.abs(feat - ref).max()
+    assert err < 0.05 * max(1.0, np.abs(ref).max()), f'feature err {err:.4g} (ref absmax {np.abs(ref).max():.3g})'
+    hm = model.keypoint_head(model.backbone(img.cuda())).cpu().numpy()
+    assert np.abs(hm - g['heatmaps_noflip']).max() < HEATMAP_ATOL
+
+
+@pytest.mark.parametrize('name,n', [('S-classic-17', 4)])
+def test_small_config_vs_oracle(name, n):
+    """BASELINE configs[0] architecture (ViTPose-S classic, K=17), oracle on the host CPU."""
+    cfg = configs.baseline_model_cfg(name)
+    sd = synthetic.scaled_init_state_dict(cfg, 1)
+    img = synthetic.synthetic_crops(n, 1)
+    metas = synthetic.synthetic_metas(n, 17, 1)
+    ref = VT.forward_test(sd, img, metas, cfg, return_heatmap=True)
+    model = _build(cfg, sd)
+    r = model(img=img.cuda(), img_metas=metas, return_loss=False, return_heatmap=True)
+    err = np.abs(r['output_heatmap'] - ref['output_heatmap']).max()
+    std = ref['output_heatmap'].std()
+    assert err < HEATMAP_ATOL and err < 0.1 * std, f'heatmap err {err:.4g}, std {std:.4g}'
+    ok = _margin_ok(ref['output_heatmap'], err)
+    d = np.abs(r['preds'][..., :2] - ref['preds'][..., :2]).max(-1)
+    assert ok.mean() > 0.3
+    assert (d[ok] < 0.5).all()
+    # decode of the GPU's own averaged heatmap by the oracle: identical argmax / maxvals (bit-exact decode)
+    c = np.stack([m['center'] for m in metas])
+    s = np.stack([m['scale'] for m in metas])
+    p2, m2 = O.keypoints_from_heatmaps(r['output_heatmap'], c, s, post_process='default', use_udp=False)
+    np.testing.assert_array_equal(r['preds'][..., 2:3], m2)
+    np.testing.assert_allclose(r['preds'][..., :2], p2, atol=1e-3)
+
+
+def test_forward_test_contract():
+    cfg = configs.tiny_model_cfg(5)
+    sd = synthetic.scaled_init_state_dict(cfg, 2)
+    model = _build(cfg, sd)
+    img = synthetic.synthetic_crops(3, 2).cuda()
+    metas = synthetic.synthetic_metas(3, 5, 2)
+    r = model(img=img, img_metas=metas, return_loss=False)
+    assert set(r) == {'preds', 'boxes', 'image_paths', 'bbox_ids', 'output_heatmap'}
+    assert r['output_heatmap'] is None and r['preds'].shape == (3, 5, 3) and r['boxes'].shape == (3, 6)
+    with pytest.raises(AssertionError):
+        model.forward_test(img, metas[:2])
+    no_id = [{k: v for k, v in m.items() if k != 'bbox_id'} for m in metas]
+    with pytest.raises(AssertionError):
+        model.forward_test(img, no_id)
+    # no flip: single pass
+    model.test_cfg = dict(cfg['test_cfg'], flip_test=False)
+    r2 = model(img=img, img_metas=metas, return_loss=False, return_heatmap=True)
+    assert r2['output_heatmap'].shape == (3, 5, 64, 48)
+    # odd batch sizes and batch 1 (no bbox_id needed)
+    r1 = model.forward_test(img[:1], no_id[:1])
+    assert r1['bbox_ids'] is None and r1['preds'].shape == (1, 5, 3)

@@ -1,0 +1,181 @@
+"""Per-kernel parity (-m gpu): each sm_100a kernel, called through the C ABI, against a plain PyTorch
+fp32 evaluation of the same op on the same bf16-rounded operands."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+def _dev():
+    return torch.device('cuda:0')
+
+
+def _rand_bf16(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(BF16)
+
+
+def _report(name, got, ref, tol):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    err = (got - ref).abs()
+    m = err.max().item()
+    if not (m <= tol):
+        idx = np.unravel_index(int(err.argmax()), err.shape)
+        bad = (err > tol).float().mean().item()
+        rows_bad = (err > tol).any(dim=-1).nonzero().flatten()[:16].tolist() if err.ndim == 2 else None
+        raise AssertionError(f'{name}: max err {m:.4g} > {tol} at {idx} (got {got[idx].item():.5g}, '
+                             f'ref {ref[idx].item():.5g}); {bad * 100:.2f}% elements off; first bad rows {rows_bad}')
+    return m
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 256, 64), (128, 256, 768), (256, 128, 128), (384, 768, 768),
+                                   (1000, 384, 192), (192 * 8, 2304, 768), (192 * 6, 3072, 768),
+                                   (192 * 6, 768, 3072), (192 * 3, 1152, 384), (192 * 2, 3840, 1280),
+                                   (192 * 170, 768, 768)])
+def test_gemm_bias_bf16(M, N, K):
+    from vitpose_b200 import ops, _lib
+    a, b = _rand_bf16((M, K), 1), _rand_bf16((N, K), 2, 1.0 / math.sqrt(K))
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(3))
+    out = ops.gemm(a.to(_dev()), b.to(_dev()), _lib.EPI_BIAS_BF16, bias=bias.to(_dev()))
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t() + bias
+    _report(f'gemm {M}x{N}x{K}', out, ref, 0.03)
+
+
+def test_gemm_gelu_bf16():
+    from vitpose_b200 import ops, _lib
+    M, N, K = 192 * 4, 1024, 256
+    a, b = _rand_bf16((M, K), 4), _rand_bf16((N, K), 5, 2.0 / math.sqrt(K))
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(6)) * 0.5
+    out = ops.gemm(a.to(_dev()), b.to(_dev()), _lib.EPI_GELU_BF16, bias=bias.to(_dev()))
+    ref = F.gelu(a.float() @ b.float().t() + bias)
+    _report('gemm+gelu', out, ref, 0.03)
+
+
+def test_gemm_residual_f32_inplace():
+    from vitpose_b200 import ops, _lib
+    M, N, K = 192 * 5, 768, 768
+    a, b = _rand_bf16((M, K), 7), _rand_bf16((N, K), 8, 1.0 / math.sqrt(K))
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(9))
+    resid = torch.randn(M, N, generator=torch.Generator().manual_seed(10))
+    x = resid.clone().to(_dev())
+    ops.gemm(a.to(_dev()), b.to(_dev()), _lib.EPI_RESID_F32, bias=bias.to(_dev()), out=x, aux=x)
+    ref = resid + a.float() @ b.float().t() + bias
+    _report('gemm+residual', x, ref, 2e-3)
+
+
+def test_gemm_pos_f32():
+    from vitpose_b200 import ops, _lib
+    T, n, D, K = 192, 3, 384, 768
+    a, b = _rand_bf16((n * T, K), 11), _rand_bf16((D, K), 12, 1.0 / math.sqrt(K))
+    bias = torch.randn(D, generator=torch.Generator().manual_seed(13))
+    pos = torch.randn(T, D, generator=torch.Generator().manual_seed(14))
+    out = ops.gemm(a.to(_dev()), b.to(_dev()), _lib.EPI_POS_F32, bias=bias.to(_dev()), aux=pos.to(_dev()), period=T)
+    ref = (a.float() @ b.float().t() + bias).reshape(n, T, D) + pos
+    _report('gemm+pos', out.reshape(n, T, D), ref, 2e-3)
+
+
+@pytest.mark.parametrize('Kout,C', [(17, 256), (133, 256), (5, 64)])
+def test_gemm_nchw_heatmap(Kout, C):
+    from vitpose_b200 import ops, _lib
+    n, P = 3, 3072
+    a, b = _rand_bf16((n * P, C), 15), _rand_bf16((Kout, C), 16, 1.0 / math.sqrt(C))
+    bias = torch.randn(Kout, generator=torch.Generator().manual_seed(17))
+    out = ops.gemm(a.to(_dev()), b.to(_dev()), _lib.EPI_NCHW_F32, bias=bias.to(_dev()), period=P)
+    ref = (a.float() @ b.float().t() + bias).reshape(n, P, Kout).permute(0, 2, 1)
+    _report('gemm nchw', out, ref, 2e-3)
+
+
+@pytest.mark.parametrize('D', [128, 384, 768, 1024, 1280])
+def test_layernorm(D):
+    from vitpose_b200 import ops
+    M = 192 * 3 + 5
+    g = torch.Generator().manual_seed(D)
+    x = torch.randn(M, D, generator=g) * 3 + 0.5
+    gamma, beta = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    out = ops.layernorm(x.to(_dev()), gamma.to(_dev()), beta.to(_dev()), 1e-6)
+    ref = F.layer_norm(x, (D,), gamma, beta, 1e-6)
+    _report('layernorm', out, ref, 0.04)
+
+
+@pytest.mark.parametrize('flip', [False, True])
+def test_im2col(flip):
+    from vitpose_b200 import ops
+    n = 3
+    img = torch.randn(n, 3, 256, 192, generator=torch.Generator().manual_seed(21))
+    out = ops.im2col_patch16(img.to(_dev()), flip=flip).float().cpu()
+    src = torch.cat([img, img.flip(3)]) if flip else img
+    ref = F.unfold(src, kernel_size=16, stride=16, padding=2)          # [n, 768, 192]
+    ref = ref.transpose(1, 2).reshape(-1, 768).to(BF16).float()
+    assert out.shape == ref.shape
+    assert torch.equal(out, ref), f'im2col mismatch: {(out - ref).abs().max()}'
+
+
+@pytest.mark.parametrize('heads,hd', [(12, 64), (2, 64), (12, 32), (16, 80)])
+def test_attention(heads, hd):
+    from vitpose_b200 import ops
+    n, T = 3, 192
+    D = heads * hd
+    qkv = _rand_bf16((n, T, 3 * D), 30 + hd, 1.5)
+    out = ops.attention(qkv.to(_dev()), heads)
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().reshape(n, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    att = ((q * hd ** -0.5) @ k.transpose(-2, -1)).softmax(-1)
+    ref = (att @ v).transpose(1, 2).reshape(n, T, D)
+    _report(f'attention h{heads} d{hd}', out, ref, 0.03)
+
+
+@pytest.mark.parametrize('n,h,w,cin,cout', [(2, 16, 12, 128, 64), (4, 16, 12, 768, 256), (3, 32, 24, 256, 256),
+                                            (2, 32, 24, 64, 64)])
+def test_deconv(n, h, w, cin, cout):
+    from vitpose_b200 import ops
+    from vitpose_b200.engine import pack_deconv_weight, fold_bn
+    g = torch.Generator().manual_seed(cin + cout)
+    x = _rand_bf16((n, cin, h, w), 40)
+    wt = (torch.randn(cin, cout, 4, 4, generator=g) / math.sqrt(4 * cin)).to(BF16).float()
+    gamma, beta = 1 + 0.1 * torch.randn(cout, generator=g), 0.1 * torch.randn(cout, generator=g)
+    mean, var = 0.1 * torch.randn(cout, generator=g), 0.5 + torch.rand(cout, generator=g)
+    scale, shift = fold_bn(gamma, beta, mean, var)
+    out = ops.deconv4x4s2_bn_relu(x.permute(0, 2, 3, 1).contiguous().to(_dev()),
+                                  pack_deconv_weight(wt).to(_dev()), scale.to(_dev()), shift.to(_dev()))
+    ref = F.conv_transpose2d(x.float(), wt, None, stride=2, padding=1)
+    ref = F.relu(F.batch_norm(ref, mean, var, gamma, beta, False, 0.0, 1e-5))
+    _report('deconv', out.permute(0, 3, 1, 2), ref, 0.03)
+
+
+@pytest.mark.parametrize('cin,cout', [(128, 5), (1024, 17)])
+def test_conv3x3(cin, cout):
+    from vitpose_b200 import ops
+    n, h, w = 2, 64, 48
+    g = torch.Generator().manual_seed(cin)
+    x = _rand_bf16((n, cin, h, w), 50)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)).to(BF16).float()
+    bias = torch.randn(cout, generator=g)
+    w9 = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).to(BF16)
+    out = ops.conv3x3_nchw(x.permute(0, 2, 3, 1).contiguous().to(_dev()), w9.to(_dev()), bias.to(_dev()))
+    ref = F.conv2d(x.float(), wt, bias, padding=1)
+    _report('conv3x3', out, ref, 3e-3)
+
+
+def test_relu_upsample():
+    from vitpose_b200 import ops
+    n, h, w, C = 2, 16, 12, 128
+    x = _rand_bf16((n, C, h, w), 60)
+    out = ops.relu_upsample_nhwc(x.permute(0, 2, 3, 1).contiguous().to(_dev()), 4)
+    ref = F.interpolate(F.relu(x.float()), scale_factor=4, mode='bilinear', align_corners=False)
+    _report('relu_upsample', out.permute(0, 3, 1, 2), ref, 0.02)
+
+
+def test_tokens_to_nchw():
+    from vitpose_b200 import ops
+    n, T, D = 2, 192, 384
+    tok = _rand_bf16((n, T, D), 70)
+    out = ops.tokens_to_nchw(tok.to(_dev()), 16, 12).cpu()
+    ref = tok.float().permute(0, 2, 1).reshape(n, D, 16, 12)
+    assert torch.equal(out, ref)

@@ -1,0 +1,113 @@
+"""ctypes binding of include/vitpose_b200.h.  There is NO CPU fallback: every wrapper raises when the
+CUDA library is missing or when a call fails."""
+import ctypes
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libvitpose_b200.so')
+
+c_void_p, c_int, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+EPI_BIAS_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_POS_F32, EPI_NCHW_F32 = range(5)
+DECODE_NONE, DECODE_DEFAULT, DECODE_UNBIASED, DECODE_UDP_DARK = range(4)
+
+
+class ModelDesc(ctypes.Structure):
+    _fields_ = [('img_h', ctypes.c_int32), ('img_w', ctypes.c_int32), ('embed_dim', ctypes.c_int32),
+                ('depth', ctypes.c_int32), ('num_heads', ctypes.c_int32), ('mlp_hidden', ctypes.c_int32),
+                ('ln_eps', ctypes.c_float), ('has_last_norm', ctypes.c_int32), ('num_deconv', ctypes.c_int32),
+                ('deconv_channels', ctypes.c_int32 * 3), ('upsample', ctypes.c_int32),
+                ('final_kernel', ctypes.c_int32), ('num_keypoints', ctypes.c_int32)]
+
+
+class BlockWeights(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ('ln1_g', 'ln1_b', 'qkv_w', 'qkv_b', 'proj_w', 'proj_b',
+                                        'ln2_g', 'ln2_b', 'fc1_w', 'fc1_b', 'fc2_w', 'fc2_b')]
+
+
+class Weights(ctypes.Structure):
+    _fields_ = [('patch_w', c_void_p), ('patch_b', c_void_p), ('pos', c_void_p),
+                ('blocks', ctypes.POINTER(BlockWeights)), ('last_g', c_void_p), ('last_b', c_void_p),
+                ('deconv_w', c_void_p * 3), ('deconv_scale', c_void_p * 3), ('deconv_shift', c_void_p * 3),
+                ('final_w', c_void_p), ('final_b', c_void_p)]
+
+
+class VitposeLibError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_SIGS = {
+    'vpb_abi_version': (c_int, []),
+    'vpb_last_error': (ctypes.c_char_p, []),
+    'vpb_workspace_bytes': (c_size_t, [ctypes.POINTER(ModelDesc), c_int]),
+    'vpb_vitpose_forward': (c_int, [ctypes.POINTER(ModelDesc), ctypes.POINTER(Weights), c_void_p, c_int, c_int,
+                                    c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    'vpb_decode_heatmaps': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
+    'vpb_flip_back': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'vpb_transform_preds': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                    c_void_p]),
+    'vpb_gemm_bf16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                              c_int, c_int, c_void_p]),
+    'vpb_layernorm_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
+    'vpb_im2col_patch16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'vpb_attention': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    'vpb_deconv4x4s2_bn_relu': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                        c_int, c_int, c_void_p]),
+    'vpb_conv3x3_nchw': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p]),
+    'vpb_relu_upsample_nhwc': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'vpb_tokens_to_nchw_f32': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+def lib():
+    """Loads libvitpose_b200.so (in-tree).  Raises if it has not been built — no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VitposeLibError(
+            f'{LIB_PATH} is missing: build it with `python -m vitpose_b200.build` '
+            '(or __graft_entry__.build()). There is no CPU/eager fallback for this path.')
+    L = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    if L.vpb_abi_version() != 1:
+        raise VitposeLibError('ABI version mismatch between _lib.py and libvitpose_b200.so')
+    _lib = L
+    return L
+
+
+def check(code, what):
+    if code != 0:
+        msg = lib().vpb_last_error().decode('utf-8', 'replace')
+        raise VitposeLibError(f'{what} failed ({code}): {msg}')
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise VitposeLibError('the vitpose_b200 kernels need CUDA tensors (no CPU fallback)')
+    if not t.is_contiguous():
+        raise VitposeLibError('tensor must be contiguous')
+    return t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise VitposeLibError('vitpose_b200 runs only on a CUDA device (sm_100a); no CPU fallback exists')

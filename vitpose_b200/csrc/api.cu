@@ -1,0 +1,202 @@
+// extern "C" boundary (include/vitpose_b200.h) and the forward orchestration: the launch sequence that
+// replaces ViT.forward + TopdownHeatmapSimpleHead.forward for a batch of crops and their flips.
+#include "../../include/vitpose_b200.h"
+
+#include "gemm.cuh"
+#include "host_util.h"
+#include "ops.h"
+
+using namespace vpb;
+
+namespace {
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+  // offsets in bytes
+  size_t patches, x, xn, qkv, attn, hidden, head_a, head_b, total;
+};
+
+Workspace plan_workspace(const vpb_model_desc& d, int images) {
+  const size_t T = static_cast<size_t>(d.img_h / 16) * (d.img_w / 16);
+  const size_t rows = T * images;
+  const size_t D = d.embed_dim;
+  Workspace w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  // the im2col patches are dead once the patch-embed GEMM has run: they share the MLP hidden buffer
+  const size_t hidden_bytes = rows * static_cast<size_t>(d.mlp_hidden) * 2;
+  const size_t patch_bytes = rows * 768 * 2;
+  w.hidden = take(hidden_bytes > patch_bytes ? hidden_bytes : patch_bytes);
+  w.patches = w.hidden;
+  w.x = take(rows * D * 4);
+  w.xn = take(rows * D * 2);
+  w.qkv = take(rows * 3 * D * 2);
+  w.attn = take(rows * D * 2);
+  // head activations (NHWC bf16): classic = two deconv outputs, simple = the upsampled feature map
+  const size_t hp = static_cast<size_t>(d.img_h / 16), wp = static_cast<size_t>(d.img_w / 16);
+  size_t a = 0, b = 0;
+  if (d.num_deconv > 0) {
+    a = static_cast<size_t>(images) * (2 * hp) * (2 * wp) * d.deconv_channels[0] * 2;
+    if (d.num_deconv > 1) b = static_cast<size_t>(images) * (4 * hp) * (4 * wp) * d.deconv_channels[1] * 2;
+    if (d.num_deconv > 2) {
+      const size_t c = static_cast<size_t>(images) * (8 * hp) * (8 * wp) * d.deconv_channels[2] * 2;
+      a = a > c ? a : c;
+    }
+  } else if (d.upsample > 0) {
+    a = static_cast<size_t>(images) * (hp * d.upsample) * (wp * d.upsample) * D * 2;
+  }
+  w.head_a = take(a);
+  w.head_b = take(b);
+  w.total = off;
+  return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vpb_abi_version(void) { return VPB_ABI_VERSION; }
+const char* vpb_last_error(void) { return get_last_error(); }
+
+size_t vpb_workspace_bytes(const vpb_model_desc* desc, int images) {
+  if (!desc || images <= 0) return 0;
+  return plan_workspace(*desc, images).total;
+}
+
+int vpb_vitpose_forward(const vpb_model_desc* desc, const vpb_weights* w, const float* img, int n, int flip,
+                        void* workspace, size_t workspace_bytes, float* heatmaps, void* features, void* stream_) {
+  VPB_REQUIRE(desc && w && img && workspace, "forward: null argument");
+  VPB_REQUIRE(n > 0, "forward: n must be positive");
+  const vpb_model_desc& d = *desc;
+  VPB_REQUIRE(d.img_h % 16 == 0 && d.img_w % 16 == 0, "forward: image size must be a multiple of the 16-px patch");
+  VPB_REQUIRE(d.embed_dim % d.num_heads == 0, "forward: embed_dim %% num_heads != 0");
+  cudaStream_t stream = as_stream(stream_);
+  const int images = flip ? 2 * n : n;
+  const int hp = d.img_h / 16, wp = d.img_w / 16, T = hp * wp;
+  const int rows = images * T;
+  const int D = d.embed_dim, hd = D / d.num_heads;
+  const Workspace ws = plan_workspace(d, images);
+  VPB_REQUIRE(workspace_bytes >= ws.total, "forward: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+  VPB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "forward: workspace must be 1024-byte aligned");
+  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+  void* patches = base + ws.patches;
+  float* x = reinterpret_cast<float*>(base + ws.x);
+  void* xn = base + ws.xn;
+  void* qkv = base + ws.qkv;
+  void* attn = base + ws.attn;
+  void* hidden = base + ws.hidden;
+
+  // PatchEmbed (vit.py:159-165) + pos embed (vit.py:320)
+  if (int e = im2col_patch16(img, patches, n, d.img_h, d.img_w, flip, stream)) return e;
+  if (int e = gemm_bf16(patches, w->patch_w, rows, D, 768, EPI_POS_F32, w->patch_b, x, D, w->pos, T, 0, stream))
+    return e;
+
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  for (int l = 0; l < d.depth; ++l) {
+    const vpb_block_weights& b = w->blocks[l];
+    // x = x + proj(attn(LN1(x)))            (vit.py:138)
+    if (int e = layernorm_bf16(x, b.ln1_g, b.ln1_b, xn, rows, D, d.ln_eps, stream)) return e;
+    if (int e = gemm_bf16(xn, b.qkv_w, rows, 3 * D, D, EPI_BIAS_BF16, b.qkv_b, qkv, 3 * D, nullptr, 0, 0, stream))
+      return e;
+    if (int e = attention_fwd(qkv, attn, images, T, d.num_heads, hd, scale, 0, stream)) return e;
+    if (int e = gemm_bf16(attn, b.proj_w, rows, D, D, EPI_RESID_F32, b.proj_b, x, D, x, 0, 0, stream)) return e;
+    // x = x + fc2(gelu(fc1(LN2(x))))        (vit.py:139)
+    if (int e = layernorm_bf16(x, b.ln2_g, b.ln2_b, xn, rows, D, d.ln_eps, stream)) return e;
+    if (int e = gemm_bf16(xn, b.fc1_w, rows, d.mlp_hidden, D, EPI_GELU_BF16, b.fc1_b, hidden, d.mlp_hidden, nullptr,
+                          0, 0, stream))
+      return e;
+    if (int e = gemm_bf16(hidden, b.fc2_w, rows, D, d.mlp_hidden, EPI_RESID_F32, b.fc2_b, x, D, x, 0, 0, stream))
+      return e;
+  }
+  // last_norm (vit.py:328); token-major [images, T, D] == NHWC [images, hp, wp, D] for the head
+  void* feat = xn;
+  if (d.has_last_norm) {
+    if (int e = layernorm_bf16(x, w->last_g, w->last_b, xn, rows, D, d.ln_eps, stream)) return e;
+  } else {
+    set_last_error("forward: last_norm=False is not supported");
+    return -2;
+  }
+  if (features != nullptr)
+    VPB_CHECK_CUDA(cudaMemcpyAsync(features, feat, static_cast<size_t>(rows) * D * 2, cudaMemcpyDeviceToDevice, stream));
+  if (heatmaps == nullptr) return 0;
+
+  const int K = d.num_keypoints;
+  if (d.num_deconv > 0) {
+    VPB_REQUIRE(d.final_kernel == 1, "forward: classic decoder expects a 1x1 final conv");
+    const void* cur = feat;
+    int ch = D, h = hp, wd = wp;
+    void* bufs[2] = {base + ws.head_a, base + ws.head_b};
+    for (int i = 0; i < d.num_deconv; ++i) {
+      void* o = bufs[i & 1];
+      if (int e = deconv4x4s2_bn_relu(cur, w->deconv_w[i], w->deconv_scale[i], w->deconv_shift[i], o, images, h, wd,
+                                      ch, d.deconv_channels[i], 0, stream))
+        return e;
+      cur = o;
+      ch = d.deconv_channels[i];
+      h *= 2;
+      wd *= 2;
+    }
+    // final 1x1 conv (simple_head.py:132-139) as a GEMM over pixels with an NCHW fp32 epilogue
+    if (int e = gemm_bf16(cur, w->final_w, images * h * wd, K, ch, EPI_NCHW_F32, w->final_b, heatmaps, 0, nullptr,
+                          h * wd, 0, stream))
+      return e;
+  } else {
+    VPB_REQUIRE(d.final_kernel == 3 && d.upsample > 0, "forward: simple decoder expects upsample + 3x3 final conv");
+    void* up = base + ws.head_a;
+    if (int e = relu_upsample_bilinear_nhwc(feat, up, images, hp, wp, D, d.upsample, stream)) return e;
+    if (int e = conv3x3_nchw_out(up, w->final_w, w->final_b, heatmaps, images, hp * d.upsample, wp * d.upsample, D, K,
+                                 0, stream))
+      return e;
+  }
+  return 0;
+}
+
+int vpb_decode_heatmaps(const float* hm, const float* hm_flipped, const int32_t* flip_index, int shift_heatmap,
+                        int N, int K, int H, int W, int mode, int kernel, int use_udp, int apply_transform,
+                        const float* center, const float* scale, float* preds, float* maxvals, float* merged_out,
+                        int32_t* argmax_out, void* stream) {
+  return decode_heatmaps(hm, hm_flipped, flip_index, shift_heatmap, N, K, H, W, mode, kernel, use_udp,
+                         apply_transform, center, scale, preds, maxvals, merged_out, argmax_out, as_stream(stream));
+}
+
+int vpb_flip_back(const float* in, const int32_t* flip_index, float* out, int N, int K, int H, int W, int shift,
+                  void* stream) {
+  return flip_back(in, flip_index, out, N, K, H, W, shift, as_stream(stream));
+}
+int vpb_transform_preds(const float* coords, const float* center, const float* scale, float* out, int N, int K,
+                        int W, int H, int use_udp, void* stream) {
+  return transform_preds(coords, center, scale, out, N, K, W, H, use_udp, as_stream(stream));
+}
+
+int vpb_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, void* out,
+                  int ldo, const float* aux, int period, int max_ctas, void* stream) {
+  return gemm_bf16(A, B, M, N, K, epilogue, bias, out, ldo, aux, period, max_ctas, as_stream(stream));
+}
+int vpb_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int M, int D, float eps,
+                       void* stream) {
+  return layernorm_bf16(x, gamma, beta, y, M, D, eps, as_stream(stream));
+}
+int vpb_im2col_patch16(const float* img, void* patches, int n, int H, int W, int flip, void* stream) {
+  return im2col_patch16(img, patches, n, H, W, flip, as_stream(stream));
+}
+int vpb_attention(const void* qkv, void* out, int n, int T, int heads, int head_dim, float scale, void* stream) {
+  return attention_fwd(qkv, out, n, T, heads, head_dim, scale, 0, as_stream(stream));
+}
+int vpb_deconv4x4s2_bn_relu(const void* in, const void* wphase, const float* scale, const float* shift, void* out,
+                            int n, int h, int w, int cin, int cout, void* stream) {
+  return deconv4x4s2_bn_relu(in, wphase, scale, shift, out, n, h, w, cin, cout, 0, as_stream(stream));
+}
+int vpb_conv3x3_nchw(const void* in, const void* w9, const float* bias, float* out, int n, int h, int w, int cin,
+                     int cout, void* stream) {
+  return conv3x3_nchw_out(in, w9, bias, out, n, h, w, cin, cout, 0, as_stream(stream));
+}
+int vpb_relu_upsample_nhwc(const void* in, void* out, int n, int h, int w, int C, int factor, void* stream) {
+  return relu_upsample_bilinear_nhwc(in, out, n, h, w, C, factor, as_stream(stream));
+}
+int vpb_tokens_to_nchw_f32(const void* tokens, float* out, int n, int T, int D, void* stream) {
+  return tokens_to_nchw_f32(tokens, out, n, T, D, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,229 @@
+// Memory-bound helpers around the tensor-core kernels: patch im2col (+ test-time flip), LayerNorm,
+// token-major -> NCHW export, ReLU + bilinear upsample (simple decoder). All are single-pass, 8/16-byte
+// vectorised, one read and one write of each element.
+#include "host_util.h"
+#include "ops.h"
+#include "ptx.cuh"
+
+namespace vpb {
+
+// -------------------------------------------------------------------------------------------------
+// PatchEmbed as a GEMM operand (reference: Conv2d(3, D, 16, stride 16, padding 2), vit.py:157-165).
+// Row = (crop, patch_y, patch_x), column = c*256 + ky*16 + kx (the flattened conv weight order).
+// The flipped crops of the flip test (top_down.py:180, img.flip(3)) are generated here as extra rows, so
+// the flipped batch never exists in memory as an image.
+// One thread = one (row, c, ky) segment of 16 pixels: 64-byte read, 32-byte write.
+// -------------------------------------------------------------------------------------------------
+__global__ void im2col_patch16_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int n, int H,
+                                      int W, int Hp, int Wp, int total_segments) {
+  const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seg >= total_segments) return;
+  const int cky = seg % 48;                // c * 16 + ky
+  const int row = seg / 48;
+  const int c = cky >> 4, ky = cky & 15;
+  const int T = Hp * Wp;
+  const int im = row / T;
+  const int t = row - im * T;
+  const int pi = t / Wp, pj = t - pi * Wp;
+  const bool flipped = im >= n;
+  const int src_im = flipped ? im - n : im;
+  const int y = pi * 16 - 2 + ky;
+  float v[16];
+  if (y < 0 || y >= H) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  } else {
+    const float* rowp = img + (static_cast<size_t>(src_im * 3 + c) * H + y) * W;
+    // output kx = 0..15 reads x = x0 + kx (plain) or x = W-1-(x0+kx) (flipped), x0 = 16*pj - 2
+    const int x0 = pj * 16 - 2;
+    const int lo = flipped ? (W - 1 - (x0 + 15)) : x0;    // ascending source range [lo, lo+15], lo is even
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int x = lo + 2 * i;
+      float2 f = make_float2(0.f, 0.f);
+      if (x >= 0 && x + 1 < W) {
+        f = __ldg(reinterpret_cast<const float2*>(rowp + x));
+      } else {
+        if (x >= 0 && x < W) f.x = __ldg(rowp + x);
+        if (x + 1 >= 0 && x + 1 < W) f.y = __ldg(rowp + x + 1);
+      }
+      if (flipped) { v[15 - 2 * i] = f.x; v[14 - 2 * i] = f.y; }
+      else         { v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    }
+  }
+  uint4 w0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                        pack_bf16x2(v[6], v[7]));
+  uint4 w1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                        pack_bf16x2(v[14], v[15]));
+  uint4* o = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * 768 + cky * 16);
+  o[0] = w0;
+  o[1] = w1;
+}
+
+int im2col_patch16(const float* img, void* patches, int n, int H, int W, int flip, cudaStream_t stream) {
+  VPB_REQUIRE(n > 0 && H % 16 == 0 && W % 16 == 0 && W % 2 == 0, "im2col: bad shape n=%d H=%d W=%d", n, H, W);
+  VPB_REQUIRE((reinterpret_cast<uintptr_t>(img) & 7) == 0 && (reinterpret_cast<uintptr_t>(patches) & 15) == 0,
+              "im2col: misaligned pointers");
+  const int Hp = (H + 4 - 16) / 16 + 1, Wp = (W + 4 - 16) / 16 + 1;
+  const long long rows = static_cast<long long>(flip ? 2 * n : n) * Hp * Wp;
+  const long long total = rows * 48;
+  VPB_REQUIRE(total < (1ll << 31), "im2col: batch too large");
+  const int threads = 256;
+  im2col_patch16_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(
+      img, reinterpret_cast<__nv_bfloat16*>(patches), n, H, W, Hp, Wp, static_cast<int>(total));
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// LayerNorm (nn.LayerNorm(D, eps=1e-6), vit.py:125,133,212,242): one warp per token row, the row lives in
+// registers (NV float4 per lane), two-pass mean / variance in fp32, bf16 output feeding the next GEMM's
+// A operand. Reads M*D*4 bytes, writes M*D*2.
+// -------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                        int M, float eps) {
+  constexpr int D = NV * 128;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = xr[i * 32 + lane];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  const float mean = s * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+  const float rstd = 1.0f / sqrtf(q * (1.0f / D) + eps);
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+    const float o0 = (v[i].x - mean) * rstd * g.x + b.x;
+    const float o1 = (v[i].y - mean) * rstd * g.y + b.y;
+    const float o2 = (v[i].z - mean) * rstd * g.z + b.z;
+    const float o3 = (v[i].w - mean) * rstd * g.w + b.w;
+    yr[i * 32 + lane] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+  }
+}
+
+int layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int M, int D, float eps,
+                   cudaStream_t stream) {
+  VPB_REQUIRE(M > 0 && D > 0 && D % 128 == 0, "layernorm: D=%d must be a multiple of 128", D);
+  const int warps = 8;
+  dim3 grid((M + warps - 1) / warps), block(warps * 32);
+  __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
+  switch (D / 128) {
+#define VPB_LN_CASE(NV_) \
+  case NV_: layernorm_kernel<NV_><<<grid, block, 0, stream>>>(x, gamma, beta, yo, M, eps); break;
+    VPB_LN_CASE(1) VPB_LN_CASE(2) VPB_LN_CASE(3) VPB_LN_CASE(4) VPB_LN_CASE(5) VPB_LN_CASE(6) VPB_LN_CASE(8)
+    VPB_LN_CASE(10) VPB_LN_CASE(12) VPB_LN_CASE(16)
+#undef VPB_LN_CASE
+    default:
+      set_last_error("layernorm: unsupported D=%d", D);
+      return -2;
+  }
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// ViT.forward's final permute (vit.py:330): tokens [n, T, D] bf16 -> [n, D, T] fp32 through a padded
+// 32x32 shared-memory transpose. Only used when the backbone is called standalone; the fused path keeps
+// token-major (= NHWC) features for the head.
+// -------------------------------------------------------------------------------------------------
+__global__ void tokens_to_nchw_kernel(const __nv_bfloat16* __restrict__ tok, float* __restrict__ out, int T, int D) {
+  __shared__ float tile[32][33];
+  const int im = blockIdx.z;
+  const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, d = d0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < T && d < D) ? __bfloat162float(tok[(static_cast<size_t>(im) * T + t) * D + d]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int d = d0 + i, t = t0 + threadIdx.x;
+    if (t < T && d < D) out[(static_cast<size_t>(im) * D + d) * T + t] = tile[threadIdx.x][i];
+  }
+}
+
+int tokens_to_nchw_f32(const void* tokens, float* out, int n, int T, int D, cudaStream_t stream) {
+  VPB_REQUIRE(n > 0 && T > 0 && D > 0, "tokens_to_nchw: bad shape");
+  dim3 grid((T + 31) / 32, (D + 31) / 32, n), block(32, 8);
+  tokens_to_nchw_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(tokens), out, T, D);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Simple decoder input transform (topdown_heatmap_simple_head.py:278-287):
+// F.interpolate(relu(x), scale_factor=f, mode='bilinear', align_corners=False) on NHWC bf16.
+// src = (dst + 0.5) / f - 0.5 clamped at 0 (PyTorch's area_pixel_compute_source_index), neighbours clamped
+// to the last row/column. One thread = 8 channels of one output pixel (16-byte accesses).
+// -------------------------------------------------------------------------------------------------
+__global__ void relu_upsample_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int h,
+                                     int w, int C, int f, long long total_vec) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total_vec) return;
+  const int cv = C / 8;
+  const int c8 = static_cast<int>(idx % cv);
+  long long pix = idx / cv;
+  const int W2 = w * f, H2 = h * f;
+  const int ox = static_cast<int>(pix % W2);
+  pix /= W2;
+  const int oy = static_cast<int>(pix % H2);
+  const int im = static_cast<int>(pix / H2);
+  const float inv = 1.0f / f;
+  float sy = (oy + 0.5f) * inv - 0.5f, sx = (ox + 0.5f) * inv - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  sx = sx < 0.f ? 0.f : sx;
+  const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+  const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+  const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  auto ld = [&](int yy, int xx) {
+    return __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(im) * h + yy) * w + xx) * C) + c8);
+  };
+  const uint4 a = ld(y0, x0), b = ld(y0, x1), c = ld(y1, x0), d = ld(y1, x1);
+  const uint32_t* ap = &a.x; const uint32_t* bp = &b.x; const uint32_t* cp = &c.x; const uint32_t* dp = &d.x;
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ap + i));
+    const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(bp + i));
+    const float2 fc = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(cp + i));
+    const float2 fd = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dp + i));
+    const float r0 = hy * (hx * fmaxf(fa.x, 0.f) + lx * fmaxf(fb.x, 0.f)) +
+                     ly * (hx * fmaxf(fc.x, 0.f) + lx * fmaxf(fd.x, 0.f));
+    const float r1 = hy * (hx * fmaxf(fa.y, 0.f) + lx * fmaxf(fb.y, 0.f)) +
+                     ly * (hx * fmaxf(fc.y, 0.f) + lx * fmaxf(fd.y, 0.f));
+    o[i] = pack_bf16x2(r0, r1);
+  }
+  reinterpret_cast<uint4*>(out)[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+int relu_upsample_bilinear_nhwc(const void* in, void* out, int n, int h, int w, int C, int factor,
+                                cudaStream_t stream) {
+  VPB_REQUIRE(n > 0 && C % 8 == 0 && factor >= 1, "relu_upsample: bad shape n=%d C=%d factor=%d", n, C, factor);
+  const long long total = static_cast<long long>(n) * h * factor * w * factor * (C / 8);
+  const int threads = 256;
+  relu_upsample_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), h, w, C, factor, total);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vpb

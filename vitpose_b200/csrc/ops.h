@@ -1,0 +1,61 @@
+// Internal C++ launchers behind the C-ABI (include/vitpose_b200.h). Device pointers only; every call is
+// asynchronous on `stream`; return 0 on success, non-zero with vpb::get_last_error() set.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vpb {
+
+struct GemmParams;
+
+// ---- GEMM (gemm.cu) ----
+int gemm_pick_bn(int N, int epilogue);
+int make_gemm_maps(CUtensorMap* ta, CUtensorMap* tb, const void* A, const void* B, int M, int N, int K, int lda,
+                   int ldb, int bn);
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int bn, int epilogue,
+                int max_ctas, cudaStream_t stream);
+int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, void* out, int ldo,
+              const float* aux, int period, int max_ctas, cudaStream_t stream);
+
+// ---- elementwise / normalisation (elementwise.cu) ----
+// img fp32 [n,3,H,W] -> patches bf16 [(flip?2n:n) * Hp*Wp, 768]; rows [n*Hp*Wp, 2n*Hp*Wp) hold the
+// horizontally flipped crops (img.flip(3)) when flip != 0.
+int im2col_patch16(const float* img, void* patches, int n, int H, int W, int flip, cudaStream_t stream);
+// x fp32 [M, D] -> y bf16 [M, D], LayerNorm over D with affine (gamma, beta), eps
+int layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int M, int D, float eps,
+                   cudaStream_t stream);
+// tokens bf16 [n, T, D] -> fp32 NCHW [n, D, T]  (ViT.forward's permute for standalone backbone calls)
+int tokens_to_nchw_f32(const void* tokens, float* out, int n, int T, int D, cudaStream_t stream);
+// relu + bilinear x`factor` upsample (align_corners=False), bf16 NHWC [n,h,w,C] -> bf16 NHWC [n,h*f,w*f,C]
+int relu_upsample_bilinear_nhwc(const void* in, void* out, int n, int h, int w, int C, int factor,
+                                cudaStream_t stream);
+
+// ---- attention (attention.cu) ----
+// qkv bf16 [n, T, 3*heads*hd] (column order: which, head, d) -> out bf16 [n, T, heads*hd]
+int attention_fwd(const void* qkv, void* out, int n, int T, int heads, int hd, float scale, int max_ctas,
+                  cudaStream_t stream);
+
+// ---- deconv / conv implicit GEMMs (conv.cu) ----
+// ConvTranspose2d(k4,s2,p1,no bias) + folded BN + ReLU, NHWC bf16.
+//   in [n,h,w,Cin] -> out [n,2h,2w,Cout]; wphase bf16 [4 phases][Cout][4 taps * Cin] (see pack in python),
+//   scale/shift fp32 [Cout] applied as relu(acc * scale + shift)
+int deconv4x4s2_bn_relu(const void* in, const void* wphase, const float* scale, const float* shift, void* out,
+                        int n, int h, int w, int cin, int cout, int max_ctas, cudaStream_t stream);
+// Conv2d 3x3 pad 1 + bias, NHWC bf16 in [n,h,w,Cin], weights bf16 [Cout][9 taps * Cin] -> fp32 NCHW [n,Cout,h,w]
+int conv3x3_nchw_out(const void* in, const void* w9, const float* bias, float* out, int n, int h, int w, int cin,
+                     int cout, int max_ctas, cudaStream_t stream);
+
+// ---- decode (decode.cu) ----
+enum DecodeMode { DECODE_NONE = 0, DECODE_DEFAULT = 1, DECODE_UNBIASED = 2, DECODE_UDP_DARK = 3 };
+int decode_heatmaps(const float* hm, const float* hm_flipped, const int* flip_index, int shift_heatmap, int N, int K,
+                    int H, int W, int mode, int kernel, int use_udp, int apply_transform, const float* center,
+                    const float* scale, float* preds, float* maxvals, float* merged_out, int* argmax_out,
+                    cudaStream_t stream);
+
+int flip_back(const float* in, const int* perm, float* out, int N, int K, int H, int W, int shift,
+              cudaStream_t stream);
+int transform_preds(const float* coords, const float* center, const float* scale, float* out, int N, int K, int W,
+                    int H, int use_udp, cudaStream_t stream);
+
+}  // namespace vpb

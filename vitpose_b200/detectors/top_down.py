@@ -1,0 +1,125 @@
+"""``TopDown`` pose detector with the reference's registry name, constructor and ``forward`` /
+``forward_test`` contract (mmpose/models/detectors/top_down.py:23-218).
+
+``forward_test`` is the fused B200 path: one launch sequence runs the crops AND their horizontal flips
+through backbone + head (the flip is generated inside the im2col kernel), and one decode kernel does
+flip_back + shift + average + argmax + refinement + transform_preds on the device.  The only device->host
+copy is the [N,K,3] result (plus the averaged heatmap when ``return_heatmap=True``); the reference copies
+every heatmap twice and decodes in Python loops (simple_head.py:219,226; top_down_eval.py:598-617).
+"""
+import warnings
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import builder
+from ..builder import POSENETS
+from ..core.post_processing import flip_index_from_pairs
+from ..engine import decode_mode_from_cfg
+from ..heads.topdown_heatmap_simple_head import pack_results
+
+
+@POSENETS.register_module()
+class TopDown(nn.Module):
+
+    def __init__(self, backbone, neck=None, keypoint_head=None, train_cfg=None, test_cfg=None, pretrained=None,
+                 loss_pose=None):
+        super().__init__()
+        self.fp16_enabled = False
+        self.backbone = builder.build_backbone(backbone)
+        self.train_cfg = train_cfg
+        self.test_cfg = test_cfg if test_cfg is not None else {}
+        if neck is not None:
+            raise NotImplementedError('necks are not used by any ViTPose config')
+        if keypoint_head is not None:
+            keypoint_head = dict(keypoint_head)
+            keypoint_head['train_cfg'] = train_cfg
+            keypoint_head['test_cfg'] = test_cfg
+            if 'loss_keypoint' not in keypoint_head and loss_pose is not None:
+                warnings.warn('`loss_pose` for TopDown is deprecated, use `loss_keypoint` for heads instead. See '
+                              'https://github.com/open-mmlab/mmpose/pull/382 for more information.',
+                              DeprecationWarning)
+                keypoint_head['loss_keypoint'] = loss_pose
+            self.keypoint_head = builder.build_head(keypoint_head)
+        self.init_weights(pretrained=pretrained)
+
+    @property
+    def with_neck(self):
+        return hasattr(self, 'neck')
+
+    @property
+    def with_keypoint(self):
+        return hasattr(self, 'keypoint_head')
+
+    def init_weights(self, pretrained=None):
+        self.backbone.init_weights(pretrained)
+        if self.with_keypoint:
+            self.keypoint_head.init_weights()
+
+    def forward(self, img, target=None, target_weight=None, img_metas=None, return_loss=True,
+                return_heatmap=False, **kwargs):
+        """return_loss=True is the training entry of the reference (top_down.py:138-139); the training step is
+        a later milestone here, so only the inference branch is served."""
+        if return_loss:
+            raise NotImplementedError('forward_train (training step) is not part of the inference hot path yet')
+        return self.forward_test(img, img_metas, return_heatmap=return_heatmap, **kwargs)
+
+    def _engine(self):
+        return self.backbone.engine(self.keypoint_head if self.with_keypoint else None)
+
+    @torch.no_grad()
+    def forward_test(self, img, img_metas, return_heatmap=False, **kwargs):
+        """Same checks, same result dict as top_down.py:163-200."""
+        assert img.size(0) == len(img_metas)
+        batch_size, _, img_height, img_width = img.shape
+        if batch_size > 1:
+            assert 'bbox_id' in img_metas[0]
+        test_cfg = self.test_cfg
+        eng = self._engine()
+        dev = eng.device
+        flip = bool(test_cfg.get('flip_test', True))
+        img = img.to(device=dev, dtype=torch.float32, non_blocking=True)
+        hm, _ = eng.forward_heatmaps(img, flip=flip)
+
+        result = {}
+        if not self.with_keypoint:
+            return result
+        K = hm.shape[1]
+        n = batch_size
+        c = np.zeros((n, 2), dtype=np.float32)
+        s = np.zeros((n, 2), dtype=np.float32)
+        score = np.ones(n)
+        image_paths = []
+        bbox_ids = [] if 'bbox_id' in img_metas[0] else None
+        for i in range(n):
+            c[i, :] = img_metas[i]['center']
+            s[i, :] = img_metas[i]['scale']
+            image_paths.append(img_metas[i]['image_file'])
+            if 'bbox_score' in img_metas[i]:
+                score[i] = np.array(img_metas[i]['bbox_score']).reshape(-1)
+            if bbox_ids is not None:
+                bbox_ids.append(img_metas[i]['bbox_id'])
+        cs = torch.from_numpy(np.concatenate([c, s], axis=1)).to(dev, non_blocking=True)
+        flip_index = None
+        if flip:
+            flip_index = torch.from_numpy(flip_index_from_pairs(K, img_metas[0]['flip_pairs'])).to(dev)
+        mode = decode_mode_from_cfg(test_cfg)
+        r = eng.decode(hm, n, flip, flip_index, bool(test_cfg.get('shift_heatmap', False)), mode,
+                       test_cfg.get('modulate_kernel', 11), bool(test_cfg.get('use_udp', False)),
+                       cs[:, 0:2].contiguous(), cs[:, 2:4].contiguous(), want_merged=return_heatmap)
+        packed = torch.cat([r['preds'], r['maxvals']], dim=2)          # [N,K,3] -> one D2H copy
+        packed = packed.cpu().numpy()
+        result.update(pack_results(packed[:, :, 0:2], packed[:, :, 2:3], c, s, score, image_paths, bbox_ids))
+        if return_heatmap:
+            output_heatmap = r['merged'].cpu().numpy() if flip else hm[:n].cpu().numpy()
+        else:
+            output_heatmap = None
+        result['output_heatmap'] = output_heatmap
+        return result
+
+    @torch.no_grad()
+    def forward_dummy(self, img):
+        """Heatmaps for FLOP counting tools (top_down.py:202-218)."""
+        hm, _ = self._engine().forward_heatmaps(img.float(), flip=False)
+        return hm
