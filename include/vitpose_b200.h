@@ -28,6 +28,15 @@ extern "C" {
 int vpb_abi_version(void);
 const char* vpb_last_error(void);
 
+/* Optional profiler: while enabled, every kernel launched by vpb_vitpose_forward / vpb_decode_heatmaps is
+ * bracketed by a CUDA-event pair on the launching stream. vpb_profile_get synchronises on record i and returns
+ * its tag (static string) and duration in milliseconds. vpb_launch_count = kernels launched by those two
+ * entry points since the library was loaded. */
+void vpb_profile_enable(int on);
+int vpb_profile_count(void);
+int vpb_profile_get(int i, const char** tag, float* ms);
+long long vpb_launch_count(void);
+
 /* ---- model description ---------------------------------------------------------------------
  * Mirrors the `model = dict(...)` block of a ViTPose config
  * (configs/body/2d_kpt_sview_rgb_img/topdown_heatmap/coco/ViTPose_base_coco_256x192.py:52-84). */

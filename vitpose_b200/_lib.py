@@ -43,6 +43,10 @@ _lib = None
 _SIGS = {
     'vpb_abi_version': (c_int, []),
     'vpb_last_error': (ctypes.c_char_p, []),
+    'vpb_profile_enable': (None, [c_int]),
+    'vpb_profile_count': (c_int, []),
+    'vpb_profile_get': (c_int, [c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_float)]),
+    'vpb_launch_count': (ctypes.c_longlong, []),
     'vpb_workspace_bytes': (c_size_t, [ctypes.POINTER(ModelDesc), c_int]),
     'vpb_vitpose_forward': (c_int, [ctypes.POINTER(ModelDesc), ctypes.POINTER(Weights), c_void_p, c_int, c_int,
                                     c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
@@ -91,6 +95,17 @@ def check(code, what):
     if code != 0:
         msg = lib().vpb_last_error().decode('utf-8', 'replace')
         raise VitposeLibError(f'{what} failed ({code}): {msg}')
+
+
+def profile_records():
+    """[(tag, ms)] of the launches recorded since vpb_profile_enable(1)."""
+    L = lib()
+    out = []
+    tag, ms = ctypes.c_char_p(), c_float()
+    for i in range(L.vpb_profile_count()):
+        check(L.vpb_profile_get(i, ctypes.byref(tag), ctypes.byref(ms)), 'vpb_profile_get')
+        out.append((tag.value.decode(), ms.value))
+    return out
 
 
 def ptr(t):

@@ -8,7 +8,36 @@
 
 using namespace vpb;
 
+#include <vector>
+
 namespace {
+
+// Optional per-launch profiler: CUDA-event pairs recorded on the launching stream around every kernel of the
+// forward / decode sequence, so bench.py can report per-kernel durations measured inside the timed step.
+struct ProfRecord { const char* tag; cudaEvent_t a, b; };
+struct Profiler {
+  bool on = false;
+  std::vector<ProfRecord> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  cudaEvent_t get() {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[used++];
+  }
+} g_prof;
+long long g_launches = 0;
+
+template <typename F>
+int prof_run(const char* tag, cudaStream_t stream, F&& f) {
+  ++g_launches;
+  if (!g_prof.on) return f();
+  ProfRecord r{tag, g_prof.get(), g_prof.get()};
+  cudaEventRecord(r.a, stream);
+  int e = f();
+  cudaEventRecord(r.b, stream);
+  g_prof.recs.push_back(r);
+  return e;
+}
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -60,6 +89,22 @@ extern "C" {
 int vpb_abi_version(void) { return VPB_ABI_VERSION; }
 const char* vpb_last_error(void) { return get_last_error(); }
 
+void vpb_profile_enable(int on) {
+  g_prof.on = on != 0;
+  g_prof.recs.clear();
+  g_prof.used = 0;
+}
+int vpb_profile_count(void) { return static_cast<int>(g_prof.recs.size()); }
+int vpb_profile_get(int i, const char** tag, float* ms) {
+  if (i < 0 || i >= static_cast<int>(g_prof.recs.size())) return -2;
+  const ProfRecord& r = g_prof.recs[i];
+  VPB_CHECK_CUDA(cudaEventSynchronize(r.b));
+  VPB_CHECK_CUDA(cudaEventElapsedTime(ms, r.a, r.b));
+  *tag = r.tag;
+  return 0;
+}
+long long vpb_launch_count(void) { return g_launches; }
+
 size_t vpb_workspace_bytes(const vpb_model_desc* desc, int images) {
   if (!desc || images <= 0) return 0;
   return plan_workspace(*desc, images).total;
@@ -89,31 +134,31 @@ int vpb_vitpose_forward(const vpb_model_desc* desc, const vpb_weights* w, const 
   void* hidden = base + ws.hidden;
 
   // PatchEmbed (vit.py:159-165) + pos embed (vit.py:320)
-  if (int e = im2col_patch16(img, patches, n, d.img_h, d.img_w, flip, stream)) return e;
-  if (int e = gemm_bf16(patches, w->patch_w, rows, D, 768, EPI_POS_F32, w->patch_b, x, D, w->pos, T, 0, stream))
+  if (int e = prof_run("im2col", stream, [&] { return im2col_patch16(img, patches, n, d.img_h, d.img_w, flip, stream); })) return e;
+  if (int e = prof_run("gemm_patch", stream, [&] { return gemm_bf16(patches, w->patch_w, rows, D, 768, EPI_POS_F32, w->patch_b, x, D, w->pos, T, 0, stream); }))
     return e;
 
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   for (int l = 0; l < d.depth; ++l) {
     const vpb_block_weights& b = w->blocks[l];
     // x = x + proj(attn(LN1(x)))            (vit.py:138)
-    if (int e = layernorm_bf16(x, b.ln1_g, b.ln1_b, xn, rows, D, d.ln_eps, stream)) return e;
-    if (int e = gemm_bf16(xn, b.qkv_w, rows, 3 * D, D, EPI_BIAS_BF16, b.qkv_b, qkv, 3 * D, nullptr, 0, 0, stream))
+    if (int e = prof_run("layernorm", stream, [&] { return layernorm_bf16(x, b.ln1_g, b.ln1_b, xn, rows, D, d.ln_eps, stream); })) return e;
+    if (int e = prof_run("gemm_qkv", stream, [&] { return gemm_bf16(xn, b.qkv_w, rows, 3 * D, D, EPI_BIAS_BF16, b.qkv_b, qkv, 3 * D, nullptr, 0, 0, stream); }))
       return e;
-    if (int e = attention_fwd(qkv, attn, images, T, d.num_heads, hd, scale, 0, stream)) return e;
-    if (int e = gemm_bf16(attn, b.proj_w, rows, D, D, EPI_RESID_F32, b.proj_b, x, D, x, 0, 0, stream)) return e;
+    if (int e = prof_run("attention", stream, [&] { return attention_fwd(qkv, attn, images, T, d.num_heads, hd, scale, 0, stream); })) return e;
+    if (int e = prof_run("gemm_proj", stream, [&] { return gemm_bf16(attn, b.proj_w, rows, D, D, EPI_RESID_F32, b.proj_b, x, D, x, 0, 0, stream); })) return e;
     // x = x + fc2(gelu(fc1(LN2(x))))        (vit.py:139)
-    if (int e = layernorm_bf16(x, b.ln2_g, b.ln2_b, xn, rows, D, d.ln_eps, stream)) return e;
-    if (int e = gemm_bf16(xn, b.fc1_w, rows, d.mlp_hidden, D, EPI_GELU_BF16, b.fc1_b, hidden, d.mlp_hidden, nullptr,
-                          0, 0, stream))
+    if (int e = prof_run("layernorm", stream, [&] { return layernorm_bf16(x, b.ln2_g, b.ln2_b, xn, rows, D, d.ln_eps, stream); })) return e;
+    if (int e = prof_run("gemm_fc1", stream, [&] { return gemm_bf16(xn, b.fc1_w, rows, d.mlp_hidden, D, EPI_GELU_BF16, b.fc1_b, hidden, d.mlp_hidden, nullptr,
+                          0, 0, stream); }))
       return e;
-    if (int e = gemm_bf16(hidden, b.fc2_w, rows, D, d.mlp_hidden, EPI_RESID_F32, b.fc2_b, x, D, x, 0, 0, stream))
+    if (int e = prof_run("gemm_fc2", stream, [&] { return gemm_bf16(hidden, b.fc2_w, rows, D, d.mlp_hidden, EPI_RESID_F32, b.fc2_b, x, D, x, 0, 0, stream); }))
       return e;
   }
   // last_norm (vit.py:328); token-major [images, T, D] == NHWC [images, hp, wp, D] for the head
   void* feat = xn;
   if (d.has_last_norm) {
-    if (int e = layernorm_bf16(x, w->last_g, w->last_b, xn, rows, D, d.ln_eps, stream)) return e;
+    if (int e = prof_run("layernorm", stream, [&] { return layernorm_bf16(x, w->last_g, w->last_b, xn, rows, D, d.ln_eps, stream); })) return e;
   } else {
     set_last_error("forward: last_norm=False is not supported");
     return -2;
@@ -130,8 +175,8 @@ int vpb_vitpose_forward(const vpb_model_desc* desc, const vpb_weights* w, const 
     void* bufs[2] = {base + ws.head_a, base + ws.head_b};
     for (int i = 0; i < d.num_deconv; ++i) {
       void* o = bufs[i & 1];
-      if (int e = deconv4x4s2_bn_relu(cur, w->deconv_w[i], w->deconv_scale[i], w->deconv_shift[i], o, images, h, wd,
-                                      ch, d.deconv_channels[i], 0, stream))
+      if (int e = prof_run("deconv", stream, [&] { return deconv4x4s2_bn_relu(cur, w->deconv_w[i], w->deconv_scale[i], w->deconv_shift[i], o, images, h, wd,
+                                      ch, d.deconv_channels[i], 0, stream); }))
         return e;
       cur = o;
       ch = d.deconv_channels[i];
@@ -139,15 +184,15 @@ int vpb_vitpose_forward(const vpb_model_desc* desc, const vpb_weights* w, const 
       wd *= 2;
     }
     // final 1x1 conv (simple_head.py:132-139) as a GEMM over pixels with an NCHW fp32 epilogue
-    if (int e = gemm_bf16(cur, w->final_w, images * h * wd, K, ch, EPI_NCHW_F32, w->final_b, heatmaps, 0, nullptr,
-                          h * wd, 0, stream))
+    if (int e = prof_run("final_conv1x1", stream, [&] { return gemm_bf16(cur, w->final_w, images * h * wd, K, ch, EPI_NCHW_F32, w->final_b, heatmaps, 0, nullptr,
+                          h * wd, 0, stream); }))
       return e;
   } else {
     VPB_REQUIRE(d.final_kernel == 3 && d.upsample > 0, "forward: simple decoder expects upsample + 3x3 final conv");
     void* up = base + ws.head_a;
-    if (int e = relu_upsample_bilinear_nhwc(feat, up, images, hp, wp, D, d.upsample, stream)) return e;
-    if (int e = conv3x3_nchw_out(up, w->final_w, w->final_b, heatmaps, images, hp * d.upsample, wp * d.upsample, D, K,
-                                 0, stream))
+    if (int e = prof_run("relu_upsample", stream, [&] { return relu_upsample_bilinear_nhwc(feat, up, images, hp, wp, D, d.upsample, stream); })) return e;
+    if (int e = prof_run("final_conv3x3", stream, [&] { return conv3x3_nchw_out(up, w->final_w, w->final_b, heatmaps, images, hp * d.upsample, wp * d.upsample, D, K,
+                                 0, stream); }))
       return e;
   }
   return 0;
@@ -157,8 +202,11 @@ int vpb_decode_heatmaps(const float* hm, const float* hm_flipped, const int32_t*
                         int N, int K, int H, int W, int mode, int kernel, int use_udp, int apply_transform,
                         const float* center, const float* scale, float* preds, float* maxvals, float* merged_out,
                         int32_t* argmax_out, void* stream) {
-  return decode_heatmaps(hm, hm_flipped, flip_index, shift_heatmap, N, K, H, W, mode, kernel, use_udp,
-                         apply_transform, center, scale, preds, maxvals, merged_out, argmax_out, as_stream(stream));
+  cudaStream_t st = as_stream(stream);
+  return prof_run("decode", st, [&] {
+    return decode_heatmaps(hm, hm_flipped, flip_index, shift_heatmap, N, K, H, W, mode, kernel, use_udp,
+                           apply_transform, center, scale, preds, maxvals, merged_out, argmax_out, st);
+  });
 }
 
 int vpb_flip_back(const float* in, const int32_t* flip_index, float* out, int N, int K, int H, int W, int shift,

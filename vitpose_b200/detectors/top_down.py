@@ -97,7 +97,7 @@ class TopDown(nn.Module):
             s[i, :] = img_metas[i]['scale']
             image_paths.append(img_metas[i]['image_file'])
             if 'bbox_score' in img_metas[i]:
-                score[i] = np.array(img_metas[i]['bbox_score']).reshape(-1)
+                score[i] = np.array(img_metas[i]['bbox_score']).reshape(-1)[0]
             if bbox_ids is not None:
                 bbox_ids.append(img_metas[i]['bbox_id'])
         cs = torch.from_numpy(np.concatenate([c, s], axis=1)).to(dev, non_blocking=True)
