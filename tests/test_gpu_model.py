@@ -38,32 +38,20 @@ def _golden_model(golden_dir, name, decoder):
     return g, sd, cfg, img, metas
 
 
-def _margin_ok(hm_ref, err):
-    """keypoints whose top-1 / top-2 (outside a 3x3 neighbourhood) margin exceeds 4x the heatmap error and whose
-    3x3 peak is curved enough (second differences > 8x the error) for a Taylor/quarter refinement to be
-    well-conditioned — random-weight heatmaps are mostly flat noise, where the REFERENCE itself is unstable"""
-    N, K, H, W = hm_ref.shape
-    flat = hm_ref.reshape(N, K, -1)
-    idx = flat.argmax(2)
-    ok = np.zeros((N, K), dtype=bool)
-    for n in range(N):
-        for k in range(K):
-            y, x = divmod(int(idx[n, k]), W)
-            m = hm_ref[n, k].copy()
-            top = m[y, x]
-            m[max(0, y - 1):y + 2, max(0, x - 1):x + 2] = -np.inf
-            ok[n, k] = (top - m.max()) > 4 * err
-            if 2 <= y < H - 2 and 2 <= x < W - 2:
-                h = hm_ref[n, k]
-                cxx = 2 * h[y, x] - h[y, x - 1] - h[y, x + 1]
-                cyy = 2 * h[y, x] - h[y - 1, x] - h[y + 1, x]
-                ok[n, k] &= min(cxx, cyy) > 8 * err
-                # the quarter-offset takes sign(h[x+1] - h[x-1]): only meaningful when |difference| > error
-                gx = abs(h[y, x + 1] - h[y, x - 1])
-                gy = abs(h[y + 1, x] - h[y - 1, x])
-                ok[n, k] &= min(gx, gy) > 4 * err
-            else:
-                ok[n, k] = False
+def _stable_keypoints(hm_ref, err, center, scale, decode_kw):
+    """Keypoints on which the REFERENCE decode itself is stable under a perturbation of the size of the measured
+    heatmap error: decode(hm_ref) vs decode(hm_ref +- err * noise) move by < 0.15 px.  Random-weight heatmaps are
+    mostly flat noise, where argmax / Taylor refinement of the reference is ill-conditioned; end-to-end
+    coordinates are compared only where the reference is well-posed (decode parity on IDENTICAL heatmaps is
+    tested separately and holds everywhere)."""
+    base, _ = O.keypoints_from_heatmaps(hm_ref, center, scale, **decode_kw)
+    ok = np.isfinite(base).all(-1)
+    rng = np.random.RandomState(0)
+    for _ in range(3):
+        noise = rng.uniform(-1, 1, size=hm_ref.shape).astype(np.float32) * np.float32(2 * err)
+        with np.errstate(all='ignore'):
+            p, _ = O.keypoints_from_heatmaps(hm_ref + noise, center, scale, **decode_kw)
+        ok &= np.abs(p - base).max(-1) < 0.15
     return ok
 
 
@@ -82,7 +70,8 @@ def test_golden_tiny_model(golden_dir, name, decoder):
         assert r['preds'].shape == g[f'{tag}_preds'].shape and r['preds'].dtype == np.float32
         np.testing.assert_allclose(r['boxes'], g[f'{tag}_boxes'], rtol=1e-6)
         assert r['image_paths'] == ['', ''] and r['bbox_ids'] == [0, 1]
-        ok = _margin_ok(ref_hm, err)
+        kw = dict(post_process=tc.get('post_process', 'default'), kernel=11, use_udp=tc.get('use_udp', False))
+        ok = _stable_keypoints(ref_hm, err, g['center'], g['scale'], kw)
         d = np.abs(r['preds'][..., :2] - g[f'{tag}_preds'][..., :2]).max(-1)
         # image-space px; one heatmap px is ~5 image px here, so 0.5 heatmap-px == 2.5 image-px; we hold 0.5 image-px
         assert (d[ok] < 0.5).all(), f'{name}/{tag}: keypoint error {d[ok].max():.3f}px on confident keypoints'
@@ -114,13 +103,13 @@ def test_small_config_vs_oracle(name, n):
     err = np.abs(r['output_heatmap'] - ref['output_heatmap']).max()
     std = ref['output_heatmap'].std()
     assert err < HEATMAP_ATOL and err < 0.1 * std, f'heatmap err {err:.4g}, std {std:.4g}'
-    ok = _margin_ok(ref['output_heatmap'], err)
+    c = np.stack([m['center'] for m in metas])
+    s = np.stack([m['scale'] for m in metas])
+    ok = _stable_keypoints(ref['output_heatmap'], err, c, s, dict(post_process='default', use_udp=False))
     d = np.abs(r['preds'][..., :2] - ref['preds'][..., :2]).max(-1)
     assert ok.sum() >= 1
     assert (d[ok] < 0.5).all()
     # decode of the GPU's own averaged heatmap by the oracle: identical argmax / maxvals (bit-exact decode)
-    c = np.stack([m['center'] for m in metas])
-    s = np.stack([m['scale'] for m in metas])
     p2, m2 = O.keypoints_from_heatmaps(r['output_heatmap'], c, s, post_process='default', use_udp=False)
     np.testing.assert_array_equal(r['preds'][..., 2:3], m2)
     np.testing.assert_allclose(r['preds'][..., :2], p2, atol=1e-3)

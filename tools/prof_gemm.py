@@ -1,0 +1,30 @@
+"""Small driver for ncu captures of single kernels (GEMM fc1/qkv/proj shapes of ViTPose-B at 128 crops)."""
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vitpose_b200 import _lib, ops  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else 'fc1'
+dev = torch.device('cuda:0')
+M, D = 128 * 2 * 192, 768
+BF16 = torch.bfloat16
+shapes = {'fc1': (4 * D, D, _lib.EPI_GELU_BF16), 'qkv': (3 * D, D, _lib.EPI_BIAS_BF16),
+          'proj': (D, D, _lib.EPI_RESID_F32), 'fc2': (D, 4 * D, _lib.EPI_RESID_F32)}
+if which == 'attn':
+    qkv = torch.randn(256, 192, 3 * D, device=dev).to(BF16)
+    for _ in range(3):
+        ops.attention(qkv, 12)
+else:
+    N, K, epi = shapes[which]
+    A = torch.randn(M, K, device=dev).to(BF16)
+    B = (torch.randn(N, K, device=dev) / math.sqrt(K)).to(BF16)
+    bias = torch.randn(N, device=dev)
+    out = torch.randn(M, N, device=dev) if epi == _lib.EPI_RESID_F32 else torch.empty(M, N, device=dev, dtype=BF16)
+    for _ in range(3):
+        ops.gemm(A, B, epi, bias=bias, out=out, aux=out if epi == _lib.EPI_RESID_F32 else None)
+torch.cuda.synchronize()
+print('done', which)

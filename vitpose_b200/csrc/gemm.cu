@@ -5,9 +5,8 @@
 namespace vpb {
 
 template <int BN, int EPI>
-static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int max_ctas,
-                            cudaStream_t stream) {
-  constexpr int smem = gemm_num_stages(BN) * gemm_stage_bytes(BN) + 1024;
+static int launch_gemm_inst(const GemmMaps& maps, const GemmParams& p, int max_ctas, cudaStream_t stream) {
+  constexpr int smem = gemm_smem_bytes(BN, EPI);
   static bool configured = false;
   auto kern = gemm_bf16_tn_kernel<BN, EPI>;
   if (!configured) {
@@ -19,7 +18,7 @@ static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const 
   int grid = m_tiles * n_tiles;
   int cap = max_ctas > 0 ? max_ctas : sm_count();
   if (grid > cap) grid = cap;
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(maps.a, maps.b, maps.out, maps.aux, p);
   VPB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -32,23 +31,32 @@ int gemm_pick_bn(int N, int epilogue) {
   return (N % 256) > 128 || N > 1024 ? 256 : 128;
 }
 
-int make_gemm_maps(CUtensorMap* ta, CUtensorMap* tb, const void* A, const void* B, int M, int N, int K, int lda,
-                   int ldb, int bn) {
+int make_gemm_maps(GemmMaps* maps, const void* A, const void* B, int M, int N, int K, int lda, int ldb, int bn,
+                   int epilogue, void* out, int ldo, const float* aux) {
   uint64_t dims_a[2] = {(uint64_t)K, (uint64_t)M};
   uint64_t str_a[1] = {(uint64_t)lda * 2};
   uint32_t box_a[2] = {GEMM_BK, GEMM_BM};
-  if (make_tma_desc(ta, TMA_BF16, A, 2, dims_a, str_a, box_a, TMA_SWIZZLE_128B)) return -1;
+  if (make_tma_desc(&maps->a, TMA_BF16, A, 2, dims_a, str_a, box_a, TMA_SWIZZLE_128B)) return -1;
   uint64_t dims_b[2] = {(uint64_t)K, (uint64_t)N};
   uint64_t str_b[1] = {(uint64_t)ldb * 2};
   uint32_t box_b[2] = {GEMM_BK, (uint32_t)bn};
-  if (make_tma_desc(tb, TMA_BF16, B, 2, dims_b, str_b, box_b, TMA_SWIZZLE_128B)) return -1;
+  if (make_tma_desc(&maps->b, TMA_BF16, B, 2, dims_b, str_b, box_b, TMA_SWIZZLE_128B)) return -1;
+  maps->out = maps->a;   // placeholders for the epilogues that store directly
+  maps->aux = maps->a;
+  if (gemm_epi_staged(epilogue)) {
+    const bool f32 = epilogue == EPI_RESID_F32;
+    uint64_t dims_o[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t str_o[1] = {(uint64_t)ldo * (f32 ? 4 : 2)};
+    uint32_t box_o[2] = {f32 ? 32u : 64u, GEMM_BM};
+    if (make_tma_desc(&maps->out, f32 ? TMA_F32 : TMA_BF16, out, 2, dims_o, str_o, box_o, TMA_SWIZZLE_128B)) return -1;
+    if (f32 && make_tma_desc(&maps->aux, TMA_F32, aux, 2, dims_o, str_o, box_o, TMA_SWIZZLE_128B)) return -1;
+  }
   return 0;
 }
 
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int bn, int epilogue,
-                int max_ctas, cudaStream_t stream) {
+int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue, int max_ctas, cudaStream_t stream) {
 #define VPB_GEMM_CASE(BN_, EPI_) \
-  if (bn == BN_ && epilogue == EPI_) return launch_gemm_inst<BN_, EPI_>(ta, tb, p, max_ctas, stream);
+  if (bn == BN_ && epilogue == EPI_) return launch_gemm_inst<BN_, EPI_>(maps, p, max_ctas, stream);
   VPB_GEMM_CASE(256, EPI_BIAS_BF16)
   VPB_GEMM_CASE(128, EPI_BIAS_BF16)
   VPB_GEMM_CASE(64, EPI_BIAS_BF16)
@@ -78,12 +86,14 @@ int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, c
   if (epilogue != EPI_NCHW_F32)
     VPB_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "gemm: out must be 16B aligned, ldo%%8==0");
   if (epilogue == EPI_RESID_F32 || epilogue == EPI_POS_F32) VPB_REQUIRE(aux != nullptr, "gemm: aux is null");
+  if (epilogue == EPI_RESID_F32)
+    VPB_REQUIRE((reinterpret_cast<uintptr_t>(aux) & 15) == 0, "gemm: residual must be 16-byte aligned");
   if (epilogue == EPI_POS_F32 || epilogue == EPI_NCHW_F32) VPB_REQUIRE(period > 0, "gemm: period must be > 0");
   const int bn = gemm_pick_bn(N, epilogue);
-  CUtensorMap ta, tb;
-  if (make_gemm_maps(&ta, &tb, A, B, M, N, K, K, K, bn)) return -1;
+  GemmMaps maps;
+  if (make_gemm_maps(&maps, A, B, M, N, K, K, K, bn, epilogue, out, ldo, aux)) return -1;
   GemmParams p{M, N, K, bias, out, ldo, aux, period};
-  return launch_gemm(ta, tb, p, bn, epilogue, max_ctas, stream);
+  return launch_gemm(maps, p, bn, epilogue, max_ctas, stream);
 }
 
 }  // namespace vpb

@@ -1,7 +1,10 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a: C[M,N] = A[M,K] * B[N,K]^T with fused epilogues.
 //   warp 0     : TMA producer (A and B tiles, 128B-swizzled, K-major) through a STAGES-deep mbarrier ring
 //   warp 1     : tcgen05.mma issuer (one elected lane), accumulators double-buffered in TMEM
-//   warps 2..5 : epilogue (tcgen05.ld -> bias / GELU / residual / pos-embed / NCHW heatmap store)
+//   warps 2..5 : epilogue. tcgen05.ld -> bias / GELU / residual in registers -> 128B-swizzled staging tile in
+//                shared memory -> TMA store (coalesced, clipped at the tensor edge by hardware). The fp32
+//                residual tile is prefetched with TMA loads into a second staging ring. TMEM is released as soon
+//                as the last chunk of a tile is in registers, so the next tile's MMAs overlap the epilogue.
 // One CTA per SM, tiles 128 x BN, walked N-fastest so CTAs running together share the A panel in L2.
 #pragma once
 #include <cuda.h>
@@ -15,7 +18,6 @@ enum GemmEpilogue {
   EPI_RESID_F32 = 2,   // out fp32 [M, ldo]      = aux[M, ldo] + acc + bias        (residual stream, may alias out)
   EPI_POS_F32 = 3,     // out fp32 [M, ldo]      = acc + bias + aux[(row % period), N] (patch embed + pos embed)
   EPI_NCHW_F32 = 4,    // out fp32 [M/period, N, period] = acc + bias             (final conv -> heatmaps)
-  EPI_RELU_BF16 = 5,   // out bf16 [M, ldo]      = relu(acc * scale[n] + bias[n])  (unused by linear layers)
 };
 
 struct GemmParams {
@@ -30,37 +32,74 @@ struct GemmParams {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_STAGING_BYTES = GEMM_BM * 128;   // one [128 rows x 128 B] TMA-store box
 
+__host__ __device__ constexpr bool gemm_epi_staged(int epi) {
+  return epi == EPI_BIAS_BF16 || epi == EPI_GELU_BF16 || epi == EPI_RESID_F32;
+}
 __host__ __device__ constexpr int gemm_tmem_cols(int bn) {
   return 2 * bn <= 32 ? 32 : 2 * bn <= 64 ? 64 : 2 * bn <= 128 ? 128 : 2 * bn <= 256 ? 256 : 512;
 }
 __host__ __device__ constexpr int gemm_stage_bytes(int bn) { return GEMM_BM * 128 + bn * 128; }
-__host__ __device__ constexpr int gemm_num_stages(int bn) {
-  // keep the ring under ~192 KB so the rest of shared memory is free for the epilogue
-  return (196608 / gemm_stage_bytes(bn)) > 8 ? 8 : (196608 / gemm_stage_bytes(bn));
+// shared memory for the epilogue: 2 output staging boxes (+ 2 residual boxes)
+__host__ __device__ constexpr int gemm_epi_smem(int epi) {
+  return !gemm_epi_staged(epi) ? 0 : (epi == EPI_RESID_F32 ? 4 : 2) * GEMM_STAGING_BYTES;
+}
+__host__ __device__ constexpr int gemm_num_stages(int bn, int epi) {
+  // 227 KB usable, minus 1 KB alignment slack and ~1 KB of static shared memory
+  return ((230400 - gemm_epi_smem(epi)) / gemm_stage_bytes(bn)) > 8
+             ? 8
+             : ((230400 - gemm_epi_smem(epi)) / gemm_stage_bytes(bn));
+}
+__host__ __device__ constexpr int gemm_smem_bytes(int bn, int epi) {
+  return gemm_num_stages(bn, epi) * gemm_stage_bytes(bn) + gemm_epi_smem(epi) + 1024;
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (nn.GELU default) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. float
+// rounding level): erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p z), z >= 0.
+// ~17 issue slots per element instead of ~40 for erff(): the fc1 epilogue must stay under the tile's MMA time.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = fast_ex2(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-poly, e, 1.0f);          // erf(|x|/sqrt2) in [0, 1]
+  const float half_x = 0.5f * x;
+  return fmaf(half_x, copysignf(erf_abs, x), half_x);  // 0.5 x (1 + erf(x/sqrt2))
+}
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux,
                     const GemmParams p) {
-  constexpr int STAGES = gemm_num_stages(BN);
+  constexpr int STAGES = gemm_num_stages(BN, EPI);
   constexpr int A_BYTES = GEMM_BM * 128;
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = gemm_tmem_cols(BN);
   constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM, BN);
+  constexpr bool STAGED = gemm_epi_staged(EPI);
+  constexpr int CHUNK = (EPI == EPI_RESID_F32) ? 32 : 64;     // columns per 128-byte staging row
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
+  static_assert(!STAGED || BN % CHUNK == 0, "staged epilogue needs BN to be a multiple of the chunk width");
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_out = smem + STAGES * STAGE_BYTES;                 // 2 x [128 x 128 B]
+  uint8_t* s_res = s_out + 2 * GEMM_STAGING_BYTES;              // 2 x [128 x 128 B] (EPI_RESID_F32 only)
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
   __shared__ uint64_t tfull_bar[2];
   __shared__ uint64_t tempty_bar[2];
+  __shared__ uint64_t res_bar[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_bias[BN];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -77,10 +116,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 4);
+      mbar_init(&res_bar[s], 1);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (STAGED) tma_prefetch_desc(&tma_out);
+    if (EPI == EPI_RESID_F32) tma_prefetch_desc(&tma_aux);
   }
   if (warp == 1) tmem_alloc(&tmem_slot, TMEM_COLS);
   tc_fence_before();
@@ -136,83 +178,143 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   } else {
     const int quad = warp & 3;             // TMEM lane quadrant this warp may read
+    const int etid = threadIdx.x - 64;     // 0..127 among the epilogue threads
+    const int r = quad * 32 + lane;        // row inside the tile == TMEM lane
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t chunk_seq = 0;                // running chunk counter: staging buffer = chunk_seq & 1
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles;
       const int n_blk = tile % n_tiles;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const int row = m_blk * GEMM_BM + quad * 32 + lane;
-      const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+
+      if constexpr (STAGED) {
+        constexpr int NCHUNK = BN / CHUNK;
+        // bias of this n-tile -> smem (all readers of the previous tile's bias are past its last barrier)
+        for (int i = etid; i < BN; i += 128) {
+          const int col = n_blk * BN + i;
+          s_bias[i] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+        }
+        if (EPI == EPI_RESID_F32 && etid == 0) {             // prefetch the first residual chunk of the tile
+          mbar_arrive_expect_tx(&res_bar[chunk_seq & 1], GEMM_STAGING_BYTES);
+          tma_load_2d(s_res + (chunk_seq & 1) * GEMM_STAGING_BYTES, &tma_aux, &res_bar[chunk_seq & 1],
+                      n_blk * BN, m_blk * GEMM_BM);
+        }
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(t_row + c * 16, r);
-        tmem_ld_wait();
-        const int col0 = n_blk * BN + c * 16;
-        if (row_ok && col0 < p.N) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          const int ncols = min(16, p.N - col0);
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
+        for (int c = 0; c < NCHUNK; ++c, ++chunk_seq) {
+          const uint32_t buf = chunk_seq & 1;
+          uint32_t v[CHUNK];
+          if constexpr (CHUNK == 64) {
+            tmem_ld_32x32b_x32(t_row + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            tmem_ld_32x32b_x32(t_row + c * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          } else {
+            tmem_ld_32x32b_x32(t_row + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
           }
-          if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_RELU_BF16) {
-            if constexpr (EPI == EPI_GELU_BF16) {
+          if (EPI == EPI_RESID_F32 && etid == 0 && c + 1 < NCHUNK) {   // prefetch the next residual chunk
+            // its buffer was last read two chunks ago; every thread is past that chunk's second barrier
+            mbar_arrive_expect_tx(&res_bar[buf ^ 1], GEMM_STAGING_BYTES);
+            tma_load_2d(s_res + (buf ^ 1) * GEMM_STAGING_BYTES, &tma_aux, &res_bar[buf ^ 1],
+                        n_blk * BN + (c + 1) * CHUNK, m_blk * GEMM_BM);
+          }
+          tmem_ld_wait();
+          if (c == NCHUNK - 1) {            // whole accumulator is in registers: hand TMEM back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          // the TMA store that last read staging buffer `buf` (two chunks ago) must have finished reading it
+          if (etid == 0) tma_store_wait_read<1>();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          uint8_t* srow = s_out + buf * GEMM_STAGING_BYTES + r * 128;
+          const float* bias_c = s_bias + c * CHUNK;
+          if constexpr (EPI == EPI_RESID_F32) {
+            mbar_wait(&res_bar[buf], (chunk_seq >> 1) & 1);
+            const uint8_t* rrow = s_res + buf * GEMM_STAGING_BYTES + r * 128;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+            for (int u = 0; u < 8; ++u) {
+              const int pu = (u ^ (r & 7)) * 16;
+              float4 x = *reinterpret_cast<const float4*>(rrow + pu);
+              x.x += __uint_as_float(v[4 * u + 0]) + bias_c[4 * u + 0];
+              x.y += __uint_as_float(v[4 * u + 1]) + bias_c[4 * u + 1];
+              x.z += __uint_as_float(v[4 * u + 2]) + bias_c[4 * u + 2];
+              x.w += __uint_as_float(v[4 * u + 3]) + bias_c[4 * u + 3];
+              *reinterpret_cast<float4*>(srow + pu) = x;
             }
-            if constexpr (EPI == EPI_RELU_BF16) {
+          } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
-            }
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
-            if (ncols == 16) {
-              uint4 w0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                    pack_bf16x2(v[6], v[7]));
-              uint4 w1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                                    pack_bf16x2(v[14], v[15]));
-              reinterpret_cast<uint4*>(o)[0] = w0;
-              reinterpret_cast<uint4*>(o)[1] = w1;
-            } else {
-              for (int j = 0; j < ncols; ++j) o[j] = __float2bfloat16_rn(v[j]);
-            }
-          } else if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32) {
-            const float* a = (EPI == EPI_RESID_F32)
-                                 ? p.aux + static_cast<size_t>(row) * p.ldo + col0
-                                 : p.aux + static_cast<size_t>(row % p.period) * p.N + col0;
-            float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
-            if (ncols == 16) {
+            for (int u = 0; u < 8; ++u) {
+              float f[8];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float4 x = reinterpret_cast<const float4*>(a)[j];
-                x.x += v[4 * j + 0]; x.y += v[4 * j + 1]; x.z += v[4 * j + 2]; x.w += v[4 * j + 3];
-                reinterpret_cast<float4*>(o)[j] = x;
+              for (int j = 0; j < 8; ++j) {
+                f[j] = __uint_as_float(v[8 * u + j]) + bias_c[8 * u + j];
+                if constexpr (EPI == EPI_GELU_BF16) f[j] = gelu_erf(f[j]);
               }
-            } else {
-              for (int j = 0; j < ncols; ++j) o[j] = a[j] + v[j];
+              *reinterpret_cast<uint4*>(srow + ((u ^ (r & 7)) * 16)) =
+                  make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                             pack_bf16x2(f[6], f[7]));
             }
-          } else if constexpr (EPI == EPI_NCHW_F32) {
-            const int img = row / p.period;
-            const int pix = row - img * p.period;
-            float* o = reinterpret_cast<float*>(p.out) + (static_cast<size_t>(img) * p.N + col0) * p.period + pix;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < ncols) o[static_cast<size_t>(j) * p.period] = v[j];   // lanes = consecutive pixels: coalesced
+          }
+          fence_proxy_async_smem();         // generic-proxy smem writes -> visible to the TMA store
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (etid == 0) {
+            tma_store_2d(&tma_out, s_out + buf * GEMM_STAGING_BYTES, n_blk * BN + c * CHUNK, m_blk * GEMM_BM);
+            tma_store_commit();
           }
         }
+      } else {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const int row = m_blk * GEMM_BM + r;
+        const bool row_ok = row < p.M;
+#pragma unroll 1
+        for (int c = 0; c < BN / 16; ++c) {
+          uint32_t rr[16];
+          tmem_ld_32x32b_x16(t_row + c * 16, rr);
+          tmem_ld_wait();
+          const int col0 = n_blk * BN + c * 16;
+          if (row_ok && col0 < p.N) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+            const int ncols = min(16, p.N - col0);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
+            }
+            if constexpr (EPI == EPI_POS_F32) {
+              const float* a = p.aux + static_cast<size_t>(row % p.period) * p.N + col0;
+              float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
+              if (ncols == 16) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float4 x = reinterpret_cast<const float4*>(a)[j];
+                  x.x += v[4 * j + 0]; x.y += v[4 * j + 1]; x.z += v[4 * j + 2]; x.w += v[4 * j + 3];
+                  reinterpret_cast<float4*>(o)[j] = x;
+                }
+              } else {
+                for (int j = 0; j < ncols; ++j) o[j] = a[j] + v[j];
+              }
+            } else {   // EPI_NCHW_F32
+              const int img = row / p.period;
+              const int pix = row - img * p.period;
+              float* o = reinterpret_cast<float*>(p.out) + (static_cast<size_t>(img) * p.N + col0) * p.period + pix;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < ncols) o[static_cast<size_t>(j) * p.period] = v[j];   // lanes = consecutive pixels
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (STAGED && etid == 0) tma_store_wait_all<0>();   // all output bytes committed before the CTA exits
   }
   tc_fence_before();
   __syncthreads();

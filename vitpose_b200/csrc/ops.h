@@ -10,11 +10,11 @@ namespace vpb {
 struct GemmParams;
 
 // ---- GEMM (gemm.cu) ----
+struct GemmMaps { CUtensorMap a, b, out, aux; };
 int gemm_pick_bn(int N, int epilogue);
-int make_gemm_maps(CUtensorMap* ta, CUtensorMap* tb, const void* A, const void* B, int M, int N, int K, int lda,
-                   int ldb, int bn);
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int bn, int epilogue,
-                int max_ctas, cudaStream_t stream);
+int make_gemm_maps(GemmMaps* maps, const void* A, const void* B, int M, int N, int K, int lda, int ldb, int bn,
+                   int epilogue, void* out, int ldo, const float* aux);
+int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue, int max_ctas, cudaStream_t stream);
 int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, void* out, int ldo,
               const float* aux, int period, int max_ctas, cudaStream_t stream);
 
