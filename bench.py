@@ -160,16 +160,14 @@ def main():
     center = torch.from_numpy(np.stack([m['center'] for m in metas])).to(dev)
     scale = torch.from_numpy(np.stack([m['scale'] for m in metas])).to(dev)
     mode = decode_mode_from_cfg(test_cfg)
-    gather_buf = [torch.empty(n, K, 3, device=dev) for _ in range(world)] if world > 1 else None
+    from vitpose_b200 import parallel
 
     def device_step(i):
         hm, _ = eng.forward_heatmaps(dev_img[i & 1], flip=True)
         r = eng.decode(hm, n, True, flip_index, bool(test_cfg.get('shift_heatmap', False)), mode,
                        test_cfg.get('modulate_kernel', 11), bool(test_cfg.get('use_udp', False)), center, scale)
         out = torch.cat([r['preds'], r['maxvals']], dim=2)
-        if world > 1:
-            dist.all_gather(gather_buf, out)          # the path's only collective: final result gather
-        return out
+        return parallel.gather_contiguous(out)        # the path's only collective: final result gather
 
     def barrier():
         if world > 1:

@@ -1,0 +1,59 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes shard a crop list and gather results in dataset order,
+reproducing DistributedSampler + collect_results_gpu semantics (mmpose/apis/test.py:168-173,195-223)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vitpose_b200 import parallel
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_total, K, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        # "model": result for crop i is a deterministic function of i
+        def fake_result(i):
+            return torch.full((K, 3), float(i)) + torch.arange(K * 3).reshape(K, 3) * 1e-3
+
+        idx = parallel.strided_shard(n_total, rank, world)
+        local = torch.stack([fake_result(i) for i in idx])
+        full = parallel.gather_strided(local, n_total)
+        lo, hi = parallel.contiguous_shard(n_total, rank, world)
+        local_c = torch.stack([fake_result(i) for i in range(lo, hi)]) if hi > lo else torch.zeros(0, K, 3)
+        counts = [parallel.contiguous_shard(n_total, r, world)[1] - parallel.contiguous_shard(n_total, r, world)[0]
+                  for r in range(world)]
+        full_c = parallel.gather_contiguous(local_c, counts)
+        torch.save(dict(full=full, full_c=full_c, idx=idx), os.path.join(out_dir, f'r{rank}.pt'))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_total', [7, 8, 1])
+def test_shard_and_gather_world2(tmp_path, n_total):
+    world, K = 2, 5
+    mp.spawn(_worker, args=(world, _free_port(), n_total, K, str(tmp_path)), nprocs=world, join=True)
+    expect = torch.stack([torch.full((K, 3), float(i)) + torch.arange(K * 3).reshape(K, 3) * 1e-3
+                          for i in range(n_total)])
+    for r in range(world):
+        d = torch.load(os.path.join(str(tmp_path), f'r{r}.pt'))
+        assert torch.equal(d['full'], expect)          # every rank holds the ordered, truncated result
+        assert torch.equal(d['full_c'], expect)
+    # the reference's split: pad by wrapping, rank::world
+    assert parallel.strided_shard(7, 0, 2) == [0, 2, 4, 6] and parallel.strided_shard(7, 1, 2) == [1, 3, 5, 0]
+
+
+def test_single_process_passthrough():
+    x = torch.arange(12.).reshape(4, 3)
+    assert torch.equal(parallel.gather_strided(x, 3), x[:3])
+    assert torch.equal(parallel.gather_contiguous(x), x)
+    assert parallel.contiguous_shard(10, 1, 4) == (2, 5)

@@ -18,7 +18,7 @@ static int launch_gemm_inst(const GemmMaps& maps, const GemmParams& p, int max_c
   int grid = m_tiles * n_tiles;
   int cap = max_ctas > 0 ? max_ctas : sm_count();
   if (grid > cap) grid = cap;
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(maps.a, maps.b, maps.out, maps.aux, p);
+  kern<<<grid, gemm_threads(EPI), smem, stream>>>(maps.a, maps.b, maps.out, maps.aux, p);
   VPB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -31,7 +31,10 @@ struct GemmParams {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;   // 64 bf16 = one 128-byte swizzle row
-constexpr int GEMM_THREADS = 192;
+// bf16 epilogues (bias / GELU) are instruction-heavy: two epilogue warpgroups (8 warps, 2 per scheduler) split
+// the column chunks of a tile; the fp32 residual epilogue is memory-heavy and keeps one warpgroup.
+__host__ __device__ constexpr int gemm_epi_groups(int epi) { return (epi == 0 || epi == 1) ? 2 : 1; }
+__host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 128 * gemm_epi_groups(epi); }
 constexpr int GEMM_STAGING_BYTES = GEMM_BM * 128;   // one [128 rows x 128 B] TMA-store box
 
 __host__ __device__ constexpr bool gemm_epi_staged(int epi) {
@@ -72,8 +75,29 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(half_x, copysignf(erf_abs, x), half_x);  // 0.5 x (1 + erf(x/sqrt2))
 }
 
+// Same formula on two elements at once with Blackwell's packed fp32 pipe (FFMA2/FMUL2/FADD2): the FMA-pipe
+// instruction count per element halves; the two MUFU ops (rcp, ex2) per element stay scalar.
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 z = __fmul2_rn(ax, make_float2(0.70710678118654752f, 0.70710678118654752f));
+  const float2 den = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
+  const float2 t = make_float2(fast_rcp(den.x), fast_rcp(den.y));
+  float2 poly = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+  poly = __ffma2_rn(poly, t, make_float2(1.421413741f, 1.421413741f));
+  poly = __ffma2_rn(poly, t, make_float2(-0.284496736f, -0.284496736f));
+  poly = __ffma2_rn(poly, t, make_float2(0.254829592f, 0.254829592f));
+  poly = __fmul2_rn(poly, t);
+  const float2 zz = __fmul2_rn(__fmul2_rn(z, make_float2(-1.4426950408889634f, -1.4426950408889634f)), z);
+  const float2 e = make_float2(fast_ex2(zz.x), fast_ex2(zz.y));
+  const float2 npe = __fmul2_rn(poly, e);
+  const float2 erf_abs = make_float2(1.0f - npe.x, 1.0f - npe.y);
+  const float2 half_x = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  const float2 erf_s = make_float2(copysignf(erf_abs.x, x.x), copysignf(erf_abs.y, x.y));
+  return __ffma2_rn(half_x, erf_s, half_x);
+}
+
 template <int BN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux,
                     const GemmParams p) {
@@ -85,6 +109,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM, BN);
   constexpr bool STAGED = gemm_epi_staged(EPI);
   constexpr int CHUNK = (EPI == EPI_RESID_F32) ? 32 : 64;     // columns per 128-byte staging row
+  constexpr int GROUPS = gemm_epi_groups(EPI);                // epilogue warpgroups
+  constexpr int OUT_BUFS = GROUPS == 2 ? 1 : 2;               // staging boxes per group (2 boxes in total)
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
   static_assert(!STAGED || BN % CHUNK == 0, "staged epilogue needs BN to be a multiple of the chunk width");
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
@@ -99,7 +125,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   __shared__ uint64_t tempty_bar[2];
   __shared__ uint64_t res_bar[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_bias[BN];
+  constexpr int BIAS_PER_GROUP = (BN / CHUNK + GROUPS - 1) / GROUPS * CHUNK;   // columns a group's chunks cover
+  __shared__ __align__(16) float s_bias[GROUPS][STAGED ? BIAS_PER_GROUP : 1];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -115,7 +142,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 4 * GROUPS);
       mbar_init(&res_bar[s], 1);
     }
     fence_mbar_init();
@@ -178,11 +205,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   } else {
     const int quad = warp & 3;             // TMEM lane quadrant this warp may read
-    const int etid = threadIdx.x - 64;     // 0..127 among the epilogue threads
+    const int grp = (warp - 2) >> 2;       // epilogue warpgroup
+    const int etid = threadIdx.x - 64 - 128 * grp;   // 0..127 inside the warpgroup
     const int r = quad * 32 + lane;        // row inside the tile == TMEM lane
+    const int bar_id = 1 + grp;            // named barrier of this warpgroup
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t chunk_seq = 0;                // running chunk counter: staging buffer = chunk_seq & 1
+    uint32_t chunk_seq = 0;                // running chunk counter of this group: staging buffer = chunk_seq & 1
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles;
       const int n_blk = tile % n_tiles;
@@ -191,9 +220,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       if constexpr (STAGED) {
         constexpr int NCHUNK = BN / CHUNK;
         // bias of this n-tile -> smem (all readers of the previous tile's bias are past its last barrier)
-        for (int i = etid; i < BN; i += 128) {
-          const int col = n_blk * BN + i;
-          s_bias[i] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+        // (each group keeps only the columns of its own chunks: local chunk lc <-> tile chunk lc*GROUPS + grp)
+        for (int i = etid; i < BIAS_PER_GROUP; i += 128) {
+          const int col = n_blk * BN + ((i / CHUNK) * GROUPS + grp) * CHUNK + (i % CHUNK);
+          s_bias[grp][i] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
         }
         if (EPI == EPI_RESID_F32 && etid == 0) {             // prefetch the first residual chunk of the tile
           mbar_arrive_expect_tx(&res_bar[chunk_seq & 1], GEMM_STAGING_BYTES);
@@ -202,9 +232,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
+        if (grp >= NCHUNK) {                // narrow tile: this group has no chunk, just release TMEM
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
 #pragma unroll 1
-        for (int c = 0; c < NCHUNK; ++c, ++chunk_seq) {
-          const uint32_t buf = chunk_seq & 1;
+        for (int c = grp; c < NCHUNK; c += GROUPS, ++chunk_seq) {
+          const uint32_t buf = OUT_BUFS == 1 ? grp : (chunk_seq & 1);
           uint32_t v[CHUNK];
           if constexpr (CHUNK == 64) {
             tmem_ld_32x32b_x32(t_row + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -212,23 +247,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           } else {
             tmem_ld_32x32b_x32(t_row + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
           }
-          if (EPI == EPI_RESID_F32 && etid == 0 && c + 1 < NCHUNK) {   // prefetch the next residual chunk
+          if (EPI == EPI_RESID_F32 && etid == 0 && c + 1 < NCHUNK) {   // prefetch the next residual chunk (GROUPS == 1)
             // its buffer was last read two chunks ago; every thread is past that chunk's second barrier
             mbar_arrive_expect_tx(&res_bar[buf ^ 1], GEMM_STAGING_BYTES);
             tma_load_2d(s_res + (buf ^ 1) * GEMM_STAGING_BYTES, &tma_aux, &res_bar[buf ^ 1],
                         n_blk * BN + (c + 1) * CHUNK, m_blk * GEMM_BM);
           }
           tmem_ld_wait();
-          if (c == NCHUNK - 1) {            // whole accumulator is in registers: hand TMEM back to the MMA warp
+          if (c + GROUPS >= NCHUNK) {       // this group's last chunk is in registers: hand TMEM back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           }
           // the TMA store that last read staging buffer `buf` (two chunks ago) must have finished reading it
-          if (etid == 0) tma_store_wait_read<1>();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (etid == 0) tma_store_wait_read<OUT_BUFS - 1>();
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           uint8_t* srow = s_out + buf * GEMM_STAGING_BYTES + r * 128;
-          const float* bias_c = s_bias + c * CHUNK;
+          const float* bias_c = &s_bias[grp][(c / GROUPS) * CHUNK];
           if constexpr (EPI == EPI_RESID_F32) {
             mbar_wait(&res_bar[buf], (chunk_seq >> 1) & 1);
             const uint8_t* rrow = s_res + buf * GEMM_STAGING_BYTES + r * 128;
@@ -245,19 +280,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           } else {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              float f[8];
+              uint32_t w[4];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                f[j] = __uint_as_float(v[8 * u + j]) + bias_c[8 * u + j];
-                if constexpr (EPI == EPI_GELU_BF16) f[j] = gelu_erf(f[j]);
+              for (int j = 0; j < 4; ++j) {
+                const float2 b2 = *reinterpret_cast<const float2*>(bias_c + 8 * u + 2 * j);
+                float2 f = __fadd2_rn(make_float2(__uint_as_float(v[8 * u + 2 * j]),
+                                                  __uint_as_float(v[8 * u + 2 * j + 1])), b2);
+                if constexpr (EPI == EPI_GELU_BF16) f = gelu_erf2(f);
+                w[j] = pack_bf16x2(f.x, f.y);
               }
-              *reinterpret_cast<uint4*>(srow + ((u ^ (r & 7)) * 16)) =
-                  make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                             pack_bf16x2(f[6], f[7]));
+              *reinterpret_cast<uint4*>(srow + ((u ^ (r & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
           fence_proxy_async_smem();         // generic-proxy smem writes -> visible to the TMA store
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           if (etid == 0) {
             tma_store_2d(&tma_out, s_out + buf * GEMM_STAGING_BYTES, n_blk * BN + c * CHUNK, m_blk * GEMM_BM);
             tma_store_commit();
