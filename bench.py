@@ -140,6 +140,10 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    # NCCL prints its version banner on stdout at the first collective; keep stdout for the one JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
@@ -177,6 +181,9 @@ def main():
     for i in range(args.warmup):
         device_step(i)
     barrier()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     # ---- timed region (device-resident inputs) -------------------------------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
