@@ -88,11 +88,15 @@ size_t vpb_workspace_bytes(const vpb_model_desc* desc, int images);
  *   img        fp32 [n, 3, img_h, img_w]  (NCHW, as the reference's `img` argument)
  *   heatmaps   fp32 [(flip ? 2n : n), K, img_h/4, img_w/4]; rows [n, 2n) are the RAW outputs of the flipped
  *              pass (not yet flipped back) — feed both halves to vpb_decode_heatmaps
+ *   heatmaps_flipped  optional fp32 [n, K, img_h/4, img_w/4]: when non-NULL (and flip != 0) the flipped-pass maps
+ *              are written here instead and `heatmaps` only needs n maps (lets a caller that pipelines chunks of
+ *              a batch assemble contiguous [N,...] main / flipped tensors for one decode call)
  *   features   optional bf16 [(flip ? 2n : n), T, D] token-major backbone output (NULL to skip)
  * Replaces ViT.forward (vit.py:313-337), TopdownHeatmapSimpleHead.forward (simple_head.py:197-202) and the
  * second, flipped pass of TopDown.forward_test (top_down.py:179-186). */
 int vpb_vitpose_forward(const vpb_model_desc* desc, const vpb_weights* w, const float* img, int n, int flip,
-                        void* workspace, size_t workspace_bytes, float* heatmaps, void* features, void* stream);
+                        void* workspace, size_t workspace_bytes, float* heatmaps, float* heatmaps_flipped,
+                        void* features, void* stream);
 
 /* decode modes = the branches of keypoints_from_heatmaps (top_down_eval.py:562-612) */
 enum { VPB_DECODE_NONE = 0, VPB_DECODE_DEFAULT = 1, VPB_DECODE_UNBIASED = 2, VPB_DECODE_UDP_DARK = 3 };

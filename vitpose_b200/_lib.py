@@ -49,7 +49,7 @@ _SIGS = {
     'vpb_launch_count': (ctypes.c_longlong, []),
     'vpb_workspace_bytes': (c_size_t, [ctypes.POINTER(ModelDesc), c_int]),
     'vpb_vitpose_forward': (c_int, [ctypes.POINTER(ModelDesc), ctypes.POINTER(Weights), c_void_p, c_int, c_int,
-                                    c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+                                    c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     'vpb_decode_heatmaps': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),

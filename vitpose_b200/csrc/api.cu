@@ -111,7 +111,8 @@ size_t vpb_workspace_bytes(const vpb_model_desc* desc, int images) {
 }
 
 int vpb_vitpose_forward(const vpb_model_desc* desc, const vpb_weights* w, const float* img, int n, int flip,
-                        void* workspace, size_t workspace_bytes, float* heatmaps, void* features, void* stream_) {
+                        void* workspace, size_t workspace_bytes, float* heatmaps, float* heatmaps_flipped,
+                        void* features, void* stream_) {
   VPB_REQUIRE(desc && w && img && workspace, "forward: null argument");
   VPB_REQUIRE(n > 0, "forward: n must be positive");
   const vpb_model_desc& d = *desc;
@@ -168,6 +169,7 @@ int vpb_vitpose_forward(const vpb_model_desc* desc, const vpb_weights* w, const 
   if (heatmaps == nullptr) return 0;
 
   const int K = d.num_keypoints;
+  const bool split = flip && heatmaps_flipped != nullptr;   // flipped-pass maps go to their own buffer
   if (d.num_deconv > 0) {
     VPB_REQUIRE(d.final_kernel == 1, "forward: classic decoder expects a 1x1 final conv");
     const void* cur = feat;
@@ -184,16 +186,30 @@ int vpb_vitpose_forward(const vpb_model_desc* desc, const vpb_weights* w, const 
       wd *= 2;
     }
     // final 1x1 conv (simple_head.py:132-139) as a GEMM over pixels with an NCHW fp32 epilogue
-    if (int e = prof_run("final_conv1x1", stream, [&] { return gemm_bf16(cur, w->final_w, images * h * wd, K, ch, EPI_NCHW_F32, w->final_b, heatmaps, 0, nullptr,
-                          h * wd, 0, stream); }))
-      return e;
+    // (two launches when the flipped pass goes to its own buffer)
+    const int parts = split ? 2 : 1, per = images / parts;
+    for (int part = 0; part < parts; ++part) {
+      const void* a = static_cast<const uint8_t*>(cur) + static_cast<size_t>(part) * per * h * wd * ch * 2;
+      float* o = part == 0 ? heatmaps : heatmaps_flipped;
+      if (int e = prof_run("final_conv1x1", stream, [&] {
+            return gemm_bf16(a, w->final_w, per * h * wd, K, ch, EPI_NCHW_F32, w->final_b, o, 0, nullptr, h * wd, 0, stream);
+          }))
+        return e;
+    }
   } else {
     VPB_REQUIRE(d.final_kernel == 3 && d.upsample > 0, "forward: simple decoder expects upsample + 3x3 final conv");
     void* up = base + ws.head_a;
     if (int e = prof_run("relu_upsample", stream, [&] { return relu_upsample_bilinear_nhwc(feat, up, images, hp, wp, D, d.upsample, stream); })) return e;
-    if (int e = prof_run("final_conv3x3", stream, [&] { return conv3x3_nchw_out(up, w->final_w, w->final_b, heatmaps, images, hp * d.upsample, wp * d.upsample, D, K,
-                                 0, stream); }))
-      return e;
+    const int parts = split ? 2 : 1, per = images / parts;
+    const int h = hp * d.upsample, wd = wp * d.upsample;
+    for (int part = 0; part < parts; ++part) {
+      const void* a = static_cast<const uint8_t*>(up) + static_cast<size_t>(part) * per * h * wd * D * 2;
+      float* o = part == 0 ? heatmaps : heatmaps_flipped;
+      if (int e = prof_run("final_conv3x3", stream, [&] {
+            return conv3x3_nchw_out(a, w->final_w, w->final_b, o, per, h, wd, D, K, 0, stream);
+          }))
+        return e;
+    }
   }
   return 0;
 }

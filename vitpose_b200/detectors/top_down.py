@@ -27,6 +27,8 @@ class TopDown(nn.Module):
                  loss_pose=None):
         super().__init__()
         self.fp16_enabled = False
+        self.host_chunk = 64          # crops per H2D chunk when forward_test is fed host tensors
+        self._copy_stream = None
         self.backbone = builder.build_backbone(backbone)
         self.train_cfg = train_cfg
         self.test_cfg = test_cfg if test_cfg is not None else {}
@@ -79,14 +81,38 @@ class TopDown(nn.Module):
         eng = self._engine()
         dev = eng.device
         flip = bool(test_cfg.get('flip_test', True))
-        img = img.to(device=dev, dtype=torch.float32, non_blocking=True)
-        hm, _ = eng.forward_heatmaps(img, flip=flip)
-
         result = {}
         if not self.with_keypoint:
             return result
-        K = hm.shape[1]
         n = batch_size
+        K = eng.desc.num_keypoints
+        H4, W4 = eng.heatmap_size
+        chunk = self.host_chunk
+        if (not img.is_cuda) and img.dtype == torch.float32 and n > chunk:
+            # Host crops: copy chunk i+1 on a side stream while chunk i runs through the network, writing every
+            # chunk's maps into contiguous [N,...] main / flipped buffers so ONE decode sees the whole batch.
+            hm_main = torch.empty(n, K, H4, W4, device=dev, dtype=torch.float32)
+            hm_flip = torch.empty(n, K, H4, W4, device=dev, dtype=torch.float32) if flip else None
+            main_stream = torch.cuda.current_stream(dev)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(dev)
+            staged = []
+            for lo in range(0, n, chunk):
+                with torch.cuda.stream(self._copy_stream):
+                    d = img[lo:lo + chunk].to(dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                staged.append((lo, d, ev))
+            for lo, d, ev in staged:
+                main_stream.wait_event(ev)
+                d.record_stream(main_stream)
+                eng.forward_into(d, flip, hm_main[lo:lo + d.shape[0]],
+                                 hm_flip[lo:lo + d.shape[0]] if flip else None)
+            hm = (hm_main, hm_flip)
+        else:
+            img = img.to(device=dev, dtype=torch.float32, non_blocking=True)
+            hm_all, _ = eng.forward_heatmaps(img, flip=flip)
+            hm = (hm_all[:n], hm_all[n:2 * n] if flip else None)
         c = np.zeros((n, 2), dtype=np.float32)
         s = np.zeros((n, 2), dtype=np.float32)
         score = np.ones(n)
@@ -105,14 +131,15 @@ class TopDown(nn.Module):
         if flip:
             flip_index = torch.from_numpy(flip_index_from_pairs(K, img_metas[0]['flip_pairs'])).to(dev)
         mode = decode_mode_from_cfg(test_cfg)
-        r = eng.decode(hm, n, flip, flip_index, bool(test_cfg.get('shift_heatmap', False)), mode,
+        from .. import ops
+        r = ops.decode(hm[0], hm[1], flip_index, bool(test_cfg.get('shift_heatmap', False)), mode,
                        test_cfg.get('modulate_kernel', 11), bool(test_cfg.get('use_udp', False)),
-                       cs[:, 0:2].contiguous(), cs[:, 2:4].contiguous(), want_merged=return_heatmap)
+                       cs[:, 0:2].contiguous(), cs[:, 2:4].contiguous(), want_merged=return_heatmap and flip)
         packed = torch.cat([r['preds'], r['maxvals']], dim=2)          # [N,K,3] -> one D2H copy
         packed = packed.cpu().numpy()
         result.update(pack_results(packed[:, :, 0:2], packed[:, :, 2:3], c, s, score, image_paths, bbox_ids))
         if return_heatmap:
-            output_heatmap = r['merged'].cpu().numpy() if flip else hm[:n].cpu().numpy()
+            output_heatmap = r['merged'].cpu().numpy() if flip else hm[0].cpu().numpy()
         else:
             output_heatmap = None
         result['output_heatmap'] = output_heatmap

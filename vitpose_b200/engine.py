@@ -168,6 +168,17 @@ class VitPoseEngine:
         return self.desc.img_h // 16, self.desc.img_w // 16
 
     # ---- network -----------------------------------------------------------------------------------
+    def forward_into(self, img, flip, out_main, out_flip):
+        """Like forward_heatmaps, but writes the main-pass maps into ``out_main`` [n,K,h,w] and the raw
+        flipped-pass maps into ``out_flip`` [n,K,h,w] (slices of larger, contiguous batch buffers)."""
+        img = img.contiguous()
+        n = img.shape[0]
+        images = 2 * n if flip else n
+        ws_ptr, ws_bytes = self._workspace(images)
+        check(lib().vpb_vitpose_forward(ctypes.byref(self.desc), ctypes.byref(self.weights.struct), ptr(img), n,
+                                        int(flip), ws_ptr, ws_bytes, ptr(out_main), ptr(out_flip) if flip else None,
+                                        None, stream_ptr()), 'vpb_vitpose_forward')
+
     def forward_heatmaps(self, img, flip=False, want_features=False, want_heatmaps=True):
         """img fp32 CUDA [n,3,H,W] -> raw heatmaps fp32 [(2n|n), K, H/4, W/4] (+ bf16 token features)."""
         if img.dtype != torch.float32 or not img.is_cuda:
@@ -185,7 +196,7 @@ class VitPoseEngine:
         feat = (torch.empty(images, hp * wp, self.desc.embed_dim, device=self.device, dtype=BF16)
                 if want_features else None)
         check(lib().vpb_vitpose_forward(ctypes.byref(self.desc), ctypes.byref(self.weights.struct), ptr(img), n,
-                                        int(flip), ws_ptr, ws_bytes, ptr(hm), ptr(feat), stream_ptr()),
+                                        int(flip), ws_ptr, ws_bytes, ptr(hm), None, ptr(feat), stream_ptr()),
               'vpb_vitpose_forward')
         return hm, feat
 
