@@ -14,6 +14,8 @@
 // The scores never touch HBM (the eager reference materialises [N, h, 192, 192] fp32 per block).
 // Head dims that are not a multiple of 64 (32 for ViT-S, 80 for ViT-H) are loaded as 64-column boxes; the MMA
 // reads only the first hd columns / K-steps of them.
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "ops.h"
 #include "ptx.cuh"
@@ -28,6 +30,7 @@ struct AttnParams {
   int ldo;              // heads * hd
   float scale_log2e;    // scale * log2(e)
   __nv_bfloat16* out;
+  int dbg;              // profiling aid (VPB_ATT_DEBUG): 1 skip softmax math, 2 skip P.V MMAs, 4 skip S MMAs, 8 skip K/V loads
 };
 
 // Tn = T rounded up to 64 (P chunks); all sizes in bytes
@@ -184,6 +187,268 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
   if (warp == 0) tmem_dealloc(tmem_s, 256);
 }
 
+// -------------------------------------------------------------------------------------------------------------
+// Persistent, pipelined variant for head_dim 32 / 64 and T = 192 (ViT-S/B/L): one CTA per SM walks the
+// (crop, head, q-tile) units.
+//   warp 0     : TMA producer with two independent rings — {Q,K} tiles (dead as soon as S = Q.K^T has been issued and
+//                completed) and V tiles (needed until P.V) — so loads run several units ahead of their use
+//   warp 1     : MMA issuer: S(i+2) is issued right after softmax(i) has read its scores, P.V(i) when P(i) is ready
+//   warps 2..9 : 256 softmax threads, thread (row, half) owns half of the key columns of one query row: a score row is
+//                read from TMEM exactly once and stays in registers; halves exchange row max / sum through smem.
+//                softmax(i+1) runs before the epilogue of unit i, overlapping the exp work with P.V(i).
+// TMEM: S0 | S1 | O0 | O1 (2T + 2HD <= 512 columns). P (bf16) has its own smem tile, reused every unit once P.V of
+// the previous unit has completed. No per-unit TMEM allocation, barrier init or CTA launch; exp2 runs only for query
+// rows that exist (q-tile 1 of a 192-token sequence is half empty).
+// -------------------------------------------------------------------------------------------------------------
+constexpr int ATT2_THREADS = 320;
+constexpr int ATT2_QK_DEPTH = 2;
+constexpr int ATT2_V_DEPTH = 3;
+
+template <int HD, int T_>
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                            const AttnParams p, const int num_units) {
+  static_assert(HD <= 64 && HD % 32 == 0, "persistent attention handles head_dim 32 / 64");
+  static_assert(T_ % 64 == 0 && 2 * T_ + 2 * HD <= 512, "each softmax thread owns T/2 keys; S0,S1,O0,O1 must fit TMEM");
+  constexpr int T = T_;
+  constexpr int Q_BYTES = ATT_BM * 128, KV_BYTES = T * 128;
+  constexpr int P_BYTES = (T / 64) * ATT_BM * 128;
+  constexpr int QK_BYTES = Q_BYTES + KV_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_p = smem;
+  uint8_t* s_qk = smem + P_BYTES;
+  uint8_t* s_v = s_qk + ATT2_QK_DEPTH * QK_BYTES;
+  __shared__ uint64_t qk_full[ATT2_QK_DEPTH], qk_free[ATT2_QK_DEPTH], v_full[ATT2_V_DEPTH], v_free[ATT2_V_DEPTH];
+  __shared__ uint64_t s_full[2], o_full[2], o_free[2], p_full;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_max[2][ATT_BM], s_sum[2][ATT_BM];   // [column half][row], exchanged between the two halves
+
+  const int q_tiles = (T + ATT_BM - 1) / ATT_BM;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_local = num_units > static_cast<int>(blockIdx.x)
+                          ? (num_units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                static_cast<int>(gridDim.x)
+                          : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ATT2_QK_DEPTH; ++s) { mbar_init(&qk_full[s], 1); mbar_init(&qk_free[s], 1); }
+    for (int s = 0; s < ATT2_V_DEPTH; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_free[s], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&o_full[b], 1);
+      mbar_init(&o_free[b], 256);
+    }
+    mbar_init(&p_full, 256);
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < n_local; ++i) {
+        const int unit = blockIdx.x + i * gridDim.x;
+        const int qt = unit % q_tiles;
+        const int head = (unit / q_tiles) % p.heads;
+        const int crop = (unit / q_tiles) / p.heads;
+        const int sq = i % ATT2_QK_DEPTH, sv = i % ATT2_V_DEPTH;
+        mbar_wait(&qk_free[sq], ((i / ATT2_QK_DEPTH) & 1) ^ 1);
+        mbar_arrive_expect_tx(&qk_full[sq], QK_BYTES);
+        tma_load_3d(s_qk + sq * QK_BYTES, &tm_q, &qk_full[sq], head * HD, qt * ATT_BM, crop);
+        tma_load_3d(s_qk + sq * QK_BYTES + Q_BYTES, &tm_kv, &qk_full[sq], p.heads * HD + head * HD, 0, crop);
+        mbar_wait(&v_free[sv], ((i / ATT2_V_DEPTH) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[sv], KV_BYTES);
+        tma_load_3d(s_v + sv * KV_BYTES, &tm_kv, &v_full[sv], 2 * p.heads * HD + head * HD, 0, crop);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, T);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BM, HD, 0, 1);
+      auto issue_s = [&](int i) {
+        const int sq = i % ATT2_QK_DEPTH, b = i & 1;
+        mbar_wait(&qk_full[sq], (i / ATT2_QK_DEPTH) & 1);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(s_qk + sq * QK_BYTES), ka = qa + Q_BYTES;
+        if (!(p.dbg & 4)) {
+#pragma unroll
+          for (int ks = 0; ks < HD / 16; ++ks)
+            umma_bf16_ss(tmem_base + b * T, umma_desc_k_sw128(qa + ks * 32), umma_desc_k_sw128(ka + ks * 32), idesc_s,
+                         ks != 0);
+        }
+        umma_commit(&s_full[b]);
+        umma_commit(&qk_free[sq]);      // Q/K tiles are dead once S has been computed
+      };
+      // S_b may be overwritten once softmax(i-2) has read it, which p_full(i-2) implies
+      if (n_local > 0) issue_s(0);
+      if (n_local > 1) issue_s(1);
+      for (int i = 0; i < n_local; ++i) {
+        const int sv = i % ATT2_V_DEPTH, b = i & 1;
+        mbar_wait(&p_full, i & 1);                         // P(i) in smem, S_b read
+        mbar_wait(&o_free[b], ((i >> 1) & 1) ^ 1);         // O_b drained by the epilogue of unit i-2
+        mbar_wait(&v_full[sv], (i / ATT2_V_DEPTH) & 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + 2 * T + b * HD;
+        const uint32_t pa = smem_u32(s_p), va = smem_u32(s_v + sv * KV_BYTES);
+        for (int ks = 0; ks < ((p.dbg & 2) ? 0 : T / 16); ++ks) {
+          umma_bf16_ss(d, umma_desc_k_sw128(pa + (ks / 4) * (ATT_BM * 128) + (ks % 4) * 32),
+                       umma_desc_mn_sw128(va + ks * 2048, KV_BYTES), idesc_o, ks != 0);
+        }
+        umma_commit(&o_full[b]);
+        umma_commit(&v_free[sv]);
+        if (i + 2 < n_local) issue_s(i + 2);
+      }
+    }
+  } else {
+    constexpr int KH = T_ / 2;                      // keys per thread
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+
+    // softmax in two parts: (1) TMEM load, row max, exchange between the two column halves; (2) exp2, bf16 P, row sum.
+    // (Measured: running the previous unit's epilogue between the parts is slower — 0.133 vs 0.108 ms — the score
+    // registers stay live across it.)
+    uint32_t v[KH];
+    float mx_row = 0.f;
+    auto softmax_load_max = [&](int i) {
+      const int unit = blockIdx.x + i * gridDim.x;
+      const int qt = unit % q_tiles;
+      const int b = i & 1;
+      const bool warp_live = (qt * ATT_BM + quad * 32 < T) && !(p.dbg & 1);   // warps past the sequence end skip the math
+      mbar_wait(&s_full[b], (i >> 1) & 1);
+      tc_fence_after();
+      float mx = -INFINITY;
+      if (warp_live) {
+#pragma unroll
+        for (int c = 0; c < KH; c += 32)
+          tmem_ld_32x32b_x32(lane_base + b * T_ + half * KH + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < KH; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+        s_max[half][r] = mx;
+      }
+      tc_fence_before();            // our tcgen05.ld of S_b are complete (ordered before the p_full arrive below)
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");   // only the two warps that share these rows
+      if (warp_live) mx = fmaxf(mx, s_max[half ^ 1][r]);
+      mx_row = mx;
+    };
+    auto softmax_exp = [&](int i) -> float {
+      const int unit = blockIdx.x + i * gridDim.x;
+      const int qt = unit % q_tiles;
+      const bool warp_live = (qt * ATT_BM + quad * 32 < T) && !(p.dbg & 1);
+      // the single P tile is free once P.V of the previous unit has completed (its epilogue has just waited for it)
+      if (i > 0) mbar_wait(&o_full[(i - 1) & 1], ((i - 1) >> 1) & 1);
+      float sum = 0.f;
+      if (warp_live) {
+        const float mx = mx_row;
+        const float2 sc = make_float2(p.scale_log2e, p.scale_log2e);
+        const float2 nm = make_float2(-mx * p.scale_log2e, -mx * p.scale_log2e);
+        float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int g = 0; g < KH / 8; ++g) {            // 8 keys = one 16-byte unit of the swizzled P tile
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 a = __ffma2_rn(make_float2(__uint_as_float(v[8 * g + 2 * j]),
+                                                    __uint_as_float(v[8 * g + 2 * j + 1])), sc, nm);
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(fast_ex2(a.x), fast_ex2(a.y));
+            sum2 = __fadd2_rn(sum2, __bfloat1622float2(b2));      // sum what the tensor core will see
+            pk[j] = *reinterpret_cast<const uint32_t*>(&b2);
+          }
+          const int col0 = half * KH + 8 * g;
+          uint8_t* dst = s_p + (col0 / 64) * (ATT_BM * 128) + r * 128 + ((((col0 % 64) / 8) ^ (r & 7)) * 16);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        sum = sum2.x + sum2.y;
+        s_sum[half][r] = sum;
+      }
+      fence_proxy_async_smem();     // P (generic-proxy writes) visible to the tensor core
+      mbar_arrive(&p_full);
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+      return warp_live ? 1.0f / (sum + s_sum[half ^ 1][r]) : 0.f;
+    };
+
+    auto epilogue = [&](int i, float inv) {
+      const int unit = blockIdx.x + i * gridDim.x;
+      const int qt = unit % q_tiles;
+      const int head = (unit / q_tiles) % p.heads;
+      const int crop = (unit / q_tiles) / p.heads;
+      const int b = i & 1;
+      const int token = qt * ATT_BM + r;
+      const bool warp_live = (qt * ATT_BM + quad * 32 < T) && !(p.dbg & 1);
+      mbar_wait(&o_full[b], (i >> 1) & 1);
+      tc_fence_after();
+      if (warp_live) {
+        constexpr int OC = HD / 2;                    // output columns per thread
+        __nv_bfloat16* orow = p.out + (static_cast<size_t>(crop) * T + token) * p.ldo + head * HD + half * OC;
+#pragma unroll
+        for (int c = 0; c < OC; c += 16) {
+          uint32_t o[16];
+          tmem_ld_32x32b_x16(lane_base + 2 * T_ + b * HD + half * OC + c, o);
+          tmem_ld_wait();
+          if (token < T) {
+            uint32_t w8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              w8[j] = pack_bf16x2(__uint_as_float(o[2 * j]) * inv, __uint_as_float(o[2 * j + 1]) * inv);
+            reinterpret_cast<uint4*>(orow + c)[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+            reinterpret_cast<uint4*>(orow + c)[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&o_free[b]);
+    };
+
+    float inv_cur = 0.f;
+    if (n_local > 0) {
+      softmax_load_max(0);
+      inv_cur = softmax_exp(0);
+    }
+    for (int i = 0; i < n_local; ++i) {
+      // softmax of the next unit first: its exp work overlaps P.V of unit i, whose result the epilogue then drains
+      float inv_next = 0.f;
+      if (i + 1 < n_local) {
+        softmax_load_max(i + 1);
+        inv_next = softmax_exp(i + 1);
+      }
+      epilogue(i, inv_cur);
+      inv_cur = inv_next;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int HD, int T_>
+static int launch_attention_persistent(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p,
+                                       int max_ctas, cudaStream_t stream) {
+  constexpr int smem = (T_ / 64) * ATT_BM * 128 + ATT2_QK_DEPTH * (ATT_BM * 128 + T_ * 128) +
+                       ATT2_V_DEPTH * T_ * 128 + 1024;
+  static_assert(smem <= 227 * 1024 - 6 * 1024, "persistent attention tiles do not fit shared memory");
+  auto kern = attention_persistent_kernel<HD, T_>;
+  static bool configured = false;
+  if (!configured) {
+    VPB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int q_tiles = (T_ + ATT_BM - 1) / ATT_BM;
+  const int units = p.n * p.heads * q_tiles;
+  int grid = max_ctas > 0 ? max_ctas : sm_count();
+  if (grid > units) grid = units;
+  kern<<<grid, ATT2_THREADS, smem, stream>>>(tq, tkv, p, units);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int HD>
 static int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p, int smem,
                             cudaStream_t stream) {
@@ -217,11 +482,21 @@ int attention_fwd(const void* qkv, void* out, int n, int T, int heads, int hd, f
   p.n = n; p.T = T; p.heads = heads; p.hd = hd; p.ldo = heads * hd;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  {
+    const char* e = getenv("VPB_ATT_DEBUG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   const int nb = att_boxes(hd);
   const int qk = nb * (ATT_BM * 128 + T * 128);
   const int pb = ((T + 63) / 64) * ATT_BM * 128;
   const int region0 = ((qk > pb ? qk : pb) + 1023) & ~1023;
   const int smem = region0 + nb * T * 128 + 1024;
+  if (max_ctas >= 0) {   // max_ctas < 0 selects the per-unit kernel (kept for head_dim > 64 and for A/B tests)
+    int rc = 1;
+    if (hd == 32 && T == 192) rc = launch_attention_persistent<32, 192>(tq, tkv, p, max_ctas, stream);
+    if (hd == 64 && T == 192) rc = launch_attention_persistent<64, 192>(tq, tkv, p, max_ctas, stream);
+    if (rc <= 0) return rc;
+  }
   switch (hd) {
     case 32: return launch_attention<32>(tq, tkv, p, smem, stream);
     case 64: return launch_attention<64>(tq, tkv, p, smem, stream);
