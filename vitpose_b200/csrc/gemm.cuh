@@ -34,7 +34,10 @@ constexpr int GEMM_BK = 64;   // 64 bf16 = one 128-byte swizzle row
 // bf16 epilogues (bias / GELU) are instruction-heavy: two epilogue warpgroups (8 warps, 2 per scheduler) split
 // the column chunks of a tile; the fp32 residual epilogue is memory-heavy and keeps one warpgroup.
 __host__ __device__ constexpr int gemm_epi_groups(int epi) { return (epi == 0 || epi == 1) ? 2 : 1; }
-__host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 128 * gemm_epi_groups(epi); }
+// EPI_RESID_F32 adds warp 6: a TMA producer that streams the fp32 residual tile through a ring of in-place
+// staging slots, running ahead of the epilogue (and of the MMAs) by up to GEMM_RES_SLOTS chunks.
+__host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 128 * gemm_epi_groups(epi) + (epi == 2 ? 32 : 0); }
+constexpr int GEMM_RES_SLOTS = 4;
 constexpr int GEMM_STAGING_BYTES = GEMM_BM * 128;   // one [128 rows x 128 B] TMA-store box
 
 __host__ __device__ constexpr bool gemm_epi_staged(int epi) {
@@ -43,19 +46,20 @@ __host__ __device__ constexpr bool gemm_epi_staged(int epi) {
 __host__ __device__ constexpr int gemm_tmem_cols(int bn) {
   return 2 * bn <= 32 ? 32 : 2 * bn <= 64 ? 64 : 2 * bn <= 128 ? 128 : 2 * bn <= 256 ? 256 : 512;
 }
-__host__ __device__ constexpr int gemm_stage_bytes(int bn) { return GEMM_BM * 128 + bn * 128; }
-// shared memory for the epilogue: 2 output staging boxes (+ 2 residual boxes)
+// per-CTA bytes of one pipeline stage; with CTA pairs (cg = 2) each CTA stages its 128 A rows and HALF of the B tile
+__host__ __device__ constexpr int gemm_stage_bytes(int bn, int cg = 1) { return GEMM_BM * 128 + bn * 128 / cg; }
+// shared memory for the epilogue: one staging box per bf16 epilogue group, or the 4-slot residual ring
 __host__ __device__ constexpr int gemm_epi_smem(int epi) {
   return !gemm_epi_staged(epi) ? 0 : (epi == EPI_RESID_F32 ? 4 : 2) * GEMM_STAGING_BYTES;
 }
-__host__ __device__ constexpr int gemm_num_stages(int bn, int epi) {
+__host__ __device__ constexpr int gemm_num_stages(int bn, int epi, int cg = 1) {
   // 227 KB usable, minus 1 KB alignment slack and ~1 KB of static shared memory
-  return ((230400 - gemm_epi_smem(epi)) / gemm_stage_bytes(bn)) > 8
+  return ((230400 - gemm_epi_smem(epi)) / gemm_stage_bytes(bn, cg)) > 8
              ? 8
-             : ((230400 - gemm_epi_smem(epi)) / gemm_stage_bytes(bn));
+             : ((230400 - gemm_epi_smem(epi)) / gemm_stage_bytes(bn, cg));
 }
-__host__ __device__ constexpr int gemm_smem_bytes(int bn, int epi) {
-  return gemm_num_stages(bn, epi) * gemm_stage_bytes(bn) + gemm_epi_smem(epi) + 1024;
+__host__ __device__ constexpr int gemm_smem_bytes(int bn, int epi, int cg = 1) {
+  return gemm_num_stages(bn, epi, cg) * gemm_stage_bytes(bn, cg) + gemm_epi_smem(epi) + 1024;
 }
 
 // Exact-erf GELU (nn.GELU default) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. float
@@ -96,44 +100,51 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   return __ffma2_rn(half_x, erf_s, half_x);
 }
 
-template <int BN, int EPI>
+// CG = 1: one CTA per 128 x BN tile. CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile —
+// each CTA stages its own 128 A rows and half of the B tile, the leader CTA issues M=256 MMAs that read both halves,
+// so per-SM shared-memory traffic per MAC drops by a third (1-CTA 128x256 tiles are smem-bandwidth bound:
+// 96 B/clk of operand reads + 96 B/clk of TMA writes against 128 B/clk).
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux,
                     const GemmParams p) {
-  constexpr int STAGES = gemm_num_stages(BN, EPI);
+  constexpr int STAGES = gemm_num_stages(BN, EPI, CG);
   constexpr int A_BYTES = GEMM_BM * 128;
-  constexpr int B_BYTES = BN * 128;
+  constexpr int B_BYTES = BN * 128 / CG;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = gemm_tmem_cols(BN);
-  constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM, BN);
+  constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM * CG, BN);
+  static_assert(CG == 1 || (CG == 2 && BN % 32 == 0), "CTA pairs split the B tile in two halves");
   constexpr bool STAGED = gemm_epi_staged(EPI);
   constexpr int CHUNK = (EPI == EPI_RESID_F32) ? 32 : 64;     // columns per 128-byte staging row
   constexpr int GROUPS = gemm_epi_groups(EPI);                // epilogue warpgroups
-  constexpr int OUT_BUFS = GROUPS == 2 ? 1 : 2;               // staging boxes per group (2 boxes in total)
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
   static_assert(!STAGED || BN % CHUNK == 0, "staged epilogue needs BN to be a multiple of the chunk width");
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_out = smem + STAGES * STAGE_BYTES;                 // 2 x [128 x 128 B]
-  uint8_t* s_res = s_out + 2 * GEMM_STAGING_BYTES;              // 2 x [128 x 128 B] (EPI_RESID_F32 only)
+  // staging boxes of [128 rows x 128 B]: one per epilogue group (bf16), or the in-place residual ring (fp32)
+  uint8_t* s_out = smem + STAGES * STAGE_BYTES;
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
   __shared__ uint64_t tfull_bar[2];
   __shared__ uint64_t tempty_bar[2];
-  __shared__ uint64_t res_bar[2];
+  __shared__ uint64_t res_full[GEMM_RES_SLOTS];
+  __shared__ uint64_t res_empty[GEMM_RES_SLOTS];
   __shared__ uint32_t tmem_slot;
   constexpr int BIAS_PER_GROUP = (BN / CHUNK + GROUPS - 1) / GROUPS * CHUNK;   // columns a group's chunks cover
   __shared__ __align__(16) float s_bias[GROUPS][STAGED ? BIAS_PER_GROUP : 1];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int m_tiles = (p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);   // (pairs of) 128-row blocks
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int cta_rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;     // both CTAs of a pair walk the same tiles
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -142,8 +153,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4 * GROUPS);
-      mbar_init(&res_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4 * GROUPS * CG);   // the leader's barrier also collects the peer's epilogue warps
+    }
+    for (int s = 0; s < GEMM_RES_SLOTS; ++s) {
+      mbar_init(&res_full[s], 1);
+      mbar_init(&res_empty[s], 1);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tma_a);
@@ -151,9 +165,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (STAGED) tma_prefetch_desc(&tma_out);
     if (EPI == EPI_RESID_F32) tma_prefetch_desc(&tma_aux);
   }
-  if (warp == 1) tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_pair(&tmem_slot, TMEM_COLS);
+    else tmem_alloc(&tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // peer barriers initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
@@ -161,27 +179,35 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m_blk = (tile / n_tiles) * CG + cta_rank;
         const int n_blk = tile % n_tiles;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(sa, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
-          tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+          if constexpr (CG == 2) {
+            // both CTAs' bytes are credited to the LEADER's barrier, which the MMA issuer waits on
+            const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            tma_load_2d_pair(sa, &tma_a, leader_full, kb * GEMM_BK, m_blk * GEMM_BM);
+            tma_load_2d_pair(sb, &tma_b, leader_full, kb * GEMM_BK, n_blk * BN + cta_rank * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {      // with CTA pairs only the leader issues MMAs (for both CTAs)
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -192,15 +218,39 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
-            umma_bf16_ss(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), IDESC,
-                         (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CG == 2)
+              umma_bf16_ss_pair(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), IDESC,
+                                (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16_ss(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), IDESC,
+                           (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);   // frees this smem stage once the MMAs above have read it
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+          if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage], 3);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);       // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (CG == 2) umma_commit_pair(&tfull_bar[acc], 3);
+        else umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (EPI == EPI_RESID_F32 && warp == 6) {
+    // residual producer: chunk c of tile (m_blk, n_blk) = fp32 [128 rows x 32 cols] -> ring slot (in-place staging)
+    if (lane == 0) {
+      uint32_t seq = 0;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m_blk = (tile / n_tiles) * CG + cta_rank;
+        const int n_blk = tile % n_tiles;
+        for (int c = 0; c < BN / 32; ++c, ++seq) {
+          const uint32_t slot = seq % GEMM_RES_SLOTS;
+          mbar_wait(&res_empty[slot], ((seq / GEMM_RES_SLOTS) & 1) ^ 1);
+          mbar_arrive_expect_tx(&res_full[slot], GEMM_STAGING_BYTES);
+          tma_load_2d(s_out + slot * GEMM_STAGING_BYTES, &tma_aux, &res_full[slot], n_blk * BN + c * 32,
+                      m_blk * GEMM_BM);
+        }
       }
     }
   } else {
@@ -209,11 +259,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int etid = threadIdx.x - 64 - 128 * grp;   // 0..127 inside the warpgroup
     const int r = quad * 32 + lane;        // row inside the tile == TMEM lane
     const int bar_id = 1 + grp;            // named barrier of this warpgroup
+    auto arrive_tempty = [&](int a) {      // TMEM buffer drained: tell the MMA issuer (in the pair's leader CTA)
+      if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[a]), 0));
+      else mbar_arrive(&tempty_bar[a]);
+    };
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t chunk_seq = 0;                // running chunk counter of this group: staging buffer = chunk_seq & 1
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / n_tiles;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int m_blk = (tile / n_tiles) * CG + cta_rank;
       const int n_blk = tile % n_tiles;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
 
@@ -225,21 +279,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           const int col = n_blk * BN + ((i / CHUNK) * GROUPS + grp) * CHUNK + (i % CHUNK);
           s_bias[grp][i] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
         }
-        if (EPI == EPI_RESID_F32 && etid == 0) {             // prefetch the first residual chunk of the tile
-          mbar_arrive_expect_tx(&res_bar[chunk_seq & 1], GEMM_STAGING_BYTES);
-          tma_load_2d(s_res + (chunk_seq & 1) * GEMM_STAGING_BYTES, &tma_aux, &res_bar[chunk_seq & 1],
-                      n_blk * BN, m_blk * GEMM_BM);
-        }
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         if (grp >= NCHUNK) {                // narrow tile: this group has no chunk, just release TMEM
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) arrive_tempty(acc);
         }
 #pragma unroll 1
         for (int c = grp; c < NCHUNK; c += GROUPS, ++chunk_seq) {
-          const uint32_t buf = OUT_BUFS == 1 ? grp : (chunk_seq & 1);
+          // staging slot: bf16 epilogues own one box per group; the residual epilogue walks the in-place ring
+          const uint32_t buf = EPI == EPI_RESID_F32 ? (chunk_seq % GEMM_RES_SLOTS) : static_cast<uint32_t>(grp);
           uint32_t v[CHUNK];
           if constexpr (CHUNK == 64) {
             tmem_ld_32x32b_x32(t_row + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -247,30 +297,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           } else {
             tmem_ld_32x32b_x32(t_row + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
           }
-          if (EPI == EPI_RESID_F32 && etid == 0 && c + 1 < NCHUNK) {   // prefetch the next residual chunk (GROUPS == 1)
-            // its buffer was last read two chunks ago; every thread is past that chunk's second barrier
-            mbar_arrive_expect_tx(&res_bar[buf ^ 1], GEMM_STAGING_BYTES);
-            tma_load_2d(s_res + (buf ^ 1) * GEMM_STAGING_BYTES, &tma_aux, &res_bar[buf ^ 1],
-                        n_blk * BN + (c + 1) * CHUNK, m_blk * GEMM_BM);
-          }
           tmem_ld_wait();
           if (c + GROUPS >= NCHUNK) {       // this group's last chunk is in registers: hand TMEM back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) arrive_tempty(acc);
           }
-          // the TMA store that last read staging buffer `buf` (two chunks ago) must have finished reading it
-          if (etid == 0) tma_store_wait_read<OUT_BUFS - 1>();
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           uint8_t* srow = s_out + buf * GEMM_STAGING_BYTES + r * 128;
           const float* bias_c = &s_bias[grp][(c / GROUPS) * CHUNK];
+          if constexpr (EPI != EPI_RESID_F32) {
+            // the TMA store that last read this group's staging box must have finished reading it
+            if (etid == 0) tma_store_wait_read<0>();
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          }
           if constexpr (EPI == EPI_RESID_F32) {
-            mbar_wait(&res_bar[buf], (chunk_seq >> 1) & 1);
-            const uint8_t* rrow = s_res + buf * GEMM_STAGING_BYTES + r * 128;
+            // residual chunk landed in the slot (TMA, issued by warp 6 well ahead); update it in place: every thread
+            // reads and writes only its own 128-byte row, so no barrier is needed before the math
+            mbar_wait(&res_full[buf], (chunk_seq / GEMM_RES_SLOTS) & 1);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const int pu = (u ^ (r & 7)) * 16;
-              float4 x = *reinterpret_cast<const float4*>(rrow + pu);
+              float4 x = *reinterpret_cast<const float4*>(srow + pu);
               x.x += __uint_as_float(v[4 * u + 0]) + bias_c[4 * u + 0];
               x.y += __uint_as_float(v[4 * u + 1]) + bias_c[4 * u + 1];
               x.z += __uint_as_float(v[4 * u + 2]) + bias_c[4 * u + 2];
@@ -297,6 +344,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (etid == 0) {
             tma_store_2d(&tma_out, s_out + buf * GEMM_STAGING_BYTES, n_blk * BN + c * CHUNK, m_blk * GEMM_BM);
             tma_store_commit();
+            if constexpr (EPI == EPI_RESID_F32) {
+              // hand the previous chunk's slot back to the residual producer once its store has read it
+              if (chunk_seq > 0) {
+                tma_store_wait_read<1>();
+                mbar_arrive(&res_empty[(chunk_seq - 1) % GEMM_RES_SLOTS]);
+              }
+            }
           }
         }
       } else {
@@ -345,7 +399,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) arrive_tempty(acc);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -354,7 +408,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if constexpr (CG == 2) cluster_sync_all();   // the peer may still be reading our smem / signalling our barriers
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 }  // namespace vpb
