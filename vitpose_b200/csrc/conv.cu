@@ -55,6 +55,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   __shared__ uint64_t empty_bar[STAGES];
   __shared__ uint64_t tfull_bar, tempty_bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_ss[2][2][BN];                 // [item parity][scale | shift][channel of the n-tile]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cin_chunks = p.cin / 64;
@@ -142,13 +143,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     }
   } else {
     const int quad = warp & 3;
+    const int etid = threadIdx.x - 64;
     uint32_t acc_ph = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       int st, phase, nt;
       decode_item(item, st, phase, nt);
       const int n0 = (st / p.tiles_y) * p.n_box;
       const int y0 = (st % p.tiles_y) * p.h_box;
       const int py = phase >> 1, px = phase & 1;
+      // per-channel scale / shift (folded BN) or bias of this n-tile -> smem, double-buffered by item parity
+      float* sc = s_ss[it & 1][0];
+      float* sh = s_ss[it & 1][1];
+      for (int i = etid; i < BN; i += 128) {
+        const int co = nt * BN + i;
+        sc[i] = (p.scale != nullptr && co < p.cout) ? __ldg(p.scale + co) : 1.0f;
+        sh[i] = (p.shift != nullptr && co < p.cout) ? __ldg(p.shift + co) : 0.0f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(&tfull_bar, acc_ph);
       tc_fence_after();
 #pragma unroll 1
@@ -160,40 +172,57 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         const int img = n0 + nn, iy = y0 + yy;
         const bool ok = img < p.n && iy < p.h;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + sub * BN;
+        if constexpr (MODE == MODE_DECONV && BN % 32 == 0) {
+          const int oy = 2 * iy + py, ox = 2 * xx + px;
+          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                ((static_cast<size_t>(img) * (2 * p.h) + oy) * (2 * p.w) + ox) * p.cout + nt * BN;
 #pragma unroll 1
-        for (int c = 0; c < BN / 16; ++c) {
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(t_row + c * 16, r);
-          tmem_ld_wait();
-          const int co0 = nt * BN + c * 16;
-          if (!ok || co0 >= p.cout) continue;
-          const int ncols = min(16, p.cout - co0);
-          float v[16];
+          for (int c = 0; c < BN; c += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + c, r);
+            tmem_ld_wait();
+            if (!ok || nt * BN + c >= p.cout) continue;
+            uint32_t w[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          if (MODE == MODE_DECONV) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < ncols) v[j] = fmaxf(fmaf(v[j], __ldg(p.scale + co0 + j), __ldg(p.shift + co0 + j)), 0.f);
-            const int oy = 2 * iy + py, ox = 2 * xx + px;
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                               ((static_cast<size_t>(img) * (2 * p.h) + oy) * (2 * p.w) + ox) * p.cout + co0;
-            if (ncols == 16) {
-              reinterpret_cast<uint4*>(o)[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                          pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-              reinterpret_cast<uint4*>(o)[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
-                                                          pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-            } else {
-              for (int j = 0; j < ncols; ++j) o[j] = __float2bfloat16_rn(v[j]);
+            for (int j = 0; j < 16; ++j) {
+              const float a = fmaxf(fmaf(__uint_as_float(r[2 * j]), sc[c + 2 * j], sh[c + 2 * j]), 0.f);
+              const float b = fmaxf(fmaf(__uint_as_float(r[2 * j + 1]), sc[c + 2 * j + 1], sh[c + 2 * j + 1]), 0.f);
+              w[j] = pack_bf16x2(a, b);
             }
-          } else {
-            // fp32 NCHW heatmaps: lanes hold consecutive pixels -> 128-byte coalesced stores per channel
-            float* o = reinterpret_cast<float*>(p.out) +
-                       ((static_cast<size_t>(img) * p.cout + co0) * p.h + iy) * p.w + xx;
-            const size_t plane = static_cast<size_t>(p.h) * p.w;
+            if (nt * BN + c + 32 <= p.cout) {          // 64 contiguous bytes per pixel
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < ncols) o[j * plane] = v[j] + __ldg(p.shift + co0 + j);
+              for (int u = 0; u < 4; ++u)
+                reinterpret_cast<uint4*>(orow + c)[u] = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+            } else {
+              for (int j = 0; j < p.cout - (nt * BN + c); ++j)
+                orow[c + j] = __float2bfloat16_rn(fmaxf(fmaf(__uint_as_float(r[j]), sc[c + j], sh[c + j]), 0.f));
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < BN / 16; ++c) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(t_row + c * 16, r);
+            tmem_ld_wait();
+            const int co0 = nt * BN + c * 16;
+            if (!ok || co0 >= p.cout) continue;
+            const int ncols = min(16, p.cout - co0);
+            if (MODE == MODE_DECONV) {
+              const int oy = 2 * iy + py, ox = 2 * xx + px;
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                 ((static_cast<size_t>(img) * (2 * p.h) + oy) * (2 * p.w) + ox) * p.cout + co0;
+              for (int j = 0; j < ncols; ++j)
+                o[j] = __float2bfloat16_rn(
+                    fmaxf(fmaf(__uint_as_float(r[j]), sc[c * 16 + j], sh[c * 16 + j]), 0.f));
+            } else {
+              // fp32 NCHW heatmaps: lanes hold consecutive pixels -> 128-byte coalesced stores per channel
+              float* o = reinterpret_cast<float*>(p.out) +
+                         ((static_cast<size_t>(img) * p.cout + co0) * p.h + iy) * p.w + xx;
+              const size_t plane = static_cast<size_t>(p.h) * p.w;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < ncols) o[j * plane] = __uint_as_float(r[j]) + sh[c * 16 + j];
+            }
           }
         }
       }
