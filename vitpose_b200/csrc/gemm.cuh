@@ -305,11 +305,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
           uint8_t* srow = s_out + buf * GEMM_STAGING_BYTES + r * 128;
           const float* bias_c = &s_bias[grp][(c / GROUPS) * CHUNK];
-          if constexpr (EPI != EPI_RESID_F32) {
-            // the TMA store that last read this group's staging box must have finished reading it
-            if (etid == 0) tma_store_wait_read<0>();
-            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-          }
           if constexpr (EPI == EPI_RESID_F32) {
             // residual chunk landed in the slot (TMA, issued by warp 6 well ahead); update it in place: every thread
             // reads and writes only its own 128-byte row, so no barrier is needed before the math
@@ -325,19 +320,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               *reinterpret_cast<float4*>(srow + pu) = x;
             }
           } else {
+            // all the math first, into packed registers (overwriting v) ...
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              uint32_t w[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 b2 = *reinterpret_cast<const float2*>(bias_c + 8 * u + 2 * j);
-                float2 f = __fadd2_rn(make_float2(__uint_as_float(v[8 * u + 2 * j]),
-                                                  __uint_as_float(v[8 * u + 2 * j + 1])), b2);
-                if constexpr (EPI == EPI_GELU_BF16) f = gelu_erf2(f);
-                w[j] = pack_bf16x2(f.x, f.y);
-              }
-              *reinterpret_cast<uint4*>(srow + ((u ^ (r & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int j = 0; j < CHUNK / 2; ++j) {
+              const float2 b2 = *reinterpret_cast<const float2*>(bias_c + 2 * j);
+              float2 f = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), b2);
+              if constexpr (EPI == EPI_GELU_BF16) f = gelu_erf2(f);
+              v[j] = pack_bf16x2(f.x, f.y);
             }
+            // ... then wait until the TMA store that last read this group's staging box has finished reading it
+            // (that latency is now hidden behind the math), and write the row
+            if (etid == 0) tma_store_wait_read<0>();
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              *reinterpret_cast<uint4*>(srow + ((u ^ (r & 7)) * 16)) =
+                  make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
           }
           fence_proxy_async_smem();         // generic-proxy smem writes -> visible to the TMA store
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
