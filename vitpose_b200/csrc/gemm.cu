@@ -63,7 +63,7 @@ int gemm_pick_bn(int N, int epilogue) {
 }
 
 int make_gemm_maps(GemmMaps* maps, const void* A, const void* B, int M, int N, int K, int lda, int ldb, int bn,
-                   int epilogue, void* out, int ldo, const float* aux, int cg) {
+                   int epilogue, void* out, int ldo, const float* aux, int cg, int period) {
   uint64_t dims_a[2] = {(uint64_t)K, (uint64_t)M};
   uint64_t str_a[1] = {(uint64_t)lda * 2};
   uint32_t box_a[2] = {GEMM_BK, GEMM_BM};
@@ -75,12 +75,20 @@ int make_gemm_maps(GemmMaps* maps, const void* A, const void* B, int M, int N, i
   maps->out = maps->a;   // placeholders for the epilogues that store directly
   maps->aux = maps->a;
   if (gemm_epi_staged(epilogue)) {
-    const bool f32 = epilogue == EPI_RESID_F32;
+    const bool f32 = gemm_epi_adds_tile(epilogue);
     uint64_t dims_o[2] = {(uint64_t)N, (uint64_t)M};
     uint64_t str_o[1] = {(uint64_t)ldo * (f32 ? 4 : 2)};
     uint32_t box_o[2] = {f32 ? 32u : 64u, GEMM_BM};
     if (make_tma_desc(&maps->out, f32 ? TMA_F32 : TMA_BF16, out, 2, dims_o, str_o, box_o, TMA_SWIZZLE_128B)) return -1;
-    if (f32 && make_tma_desc(&maps->aux, TMA_F32, aux, 2, dims_o, str_o, box_o, TMA_SWIZZLE_128B)) return -1;
+    if (epilogue == EPI_RESID_F32 &&
+        make_tma_desc(&maps->aux, TMA_F32, aux, 2, dims_o, str_o, box_o, TMA_SWIZZLE_128B))
+      return -1;
+    if (epilogue == EPI_POSTMA_F32) {   // positional table [period, N] fp32, fetched as 64-row boxes
+      uint64_t dims_p[2] = {(uint64_t)N, (uint64_t)period};
+      uint64_t str_p[1] = {(uint64_t)N * 4};
+      uint32_t box_p[2] = {32u, 64u};
+      if (make_tma_desc(&maps->aux, TMA_F32, aux, 2, dims_p, str_p, box_p, TMA_SWIZZLE_128B)) return -1;
+    }
   }
   return 0;
 }
@@ -91,6 +99,7 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue,
     if (bn == 256 && epilogue == EPI_BIAS_BF16) return launch_gemm_inst<256, EPI_BIAS_BF16, 2>(maps, p, max_ctas, stream);
     if (bn == 256 && epilogue == EPI_GELU_BF16) return launch_gemm_inst<256, EPI_GELU_BF16, 2>(maps, p, max_ctas, stream);
     if (bn == 256 && epilogue == EPI_RESID_F32) return launch_gemm_inst<256, EPI_RESID_F32, 2>(maps, p, max_ctas, stream);
+    if (bn == 256 && epilogue == EPI_POSTMA_F32) return launch_gemm_inst<256, EPI_POSTMA_F32, 2>(maps, p, max_ctas, stream);
     set_last_error("gemm: no CTA-pair kernel instance for BN=%d epilogue=%d", bn, epilogue);
     return -2;
   }
@@ -105,6 +114,9 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue,
   VPB_GEMM_CASE(256, EPI_RESID_F32)
   VPB_GEMM_CASE(128, EPI_RESID_F32)
   VPB_GEMM_CASE(64, EPI_RESID_F32)
+  VPB_GEMM_CASE(256, EPI_POSTMA_F32)
+  VPB_GEMM_CASE(128, EPI_POSTMA_F32)
+  VPB_GEMM_CASE(64, EPI_POSTMA_F32)
   VPB_GEMM_CASE(256, EPI_POS_F32)
   VPB_GEMM_CASE(128, EPI_POS_F32)
   VPB_GEMM_CASE(64, EPI_POS_F32)
@@ -128,10 +140,13 @@ int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, c
   if (epilogue == EPI_RESID_F32)
     VPB_REQUIRE((reinterpret_cast<uintptr_t>(aux) & 15) == 0, "gemm: residual must be 16-byte aligned");
   if (epilogue == EPI_POS_F32 || epilogue == EPI_NCHW_F32) VPB_REQUIRE(period > 0, "gemm: period must be > 0");
+  // patch embed + pos embed: stream the positional rows with TMA when a period is a whole number of 64-row boxes
+  if (epilogue == EPI_POS_F32 && period % 64 == 0 && ldo == N && (reinterpret_cast<uintptr_t>(aux) & 15) == 0)
+    epilogue = EPI_POSTMA_F32;
   const int bn = gemm_pick_bn(N, epilogue);
   const int cg = gemm_pick_cg(M, bn, epilogue, K);
   GemmMaps maps;
-  if (make_gemm_maps(&maps, A, B, M, N, K, K, K, bn, epilogue, out, ldo, aux, cg)) return -1;
+  if (make_gemm_maps(&maps, A, B, M, N, K, K, K, bn, epilogue, out, ldo, aux, cg, period)) return -1;
   GemmParams p{M, N, K, bias, out, ldo, aux, period};
   return launch_gemm(maps, p, bn, epilogue, cg, max_ctas, stream);
 }

@@ -18,7 +18,10 @@ enum GemmEpilogue {
   EPI_RESID_F32 = 2,   // out fp32 [M, ldo]      = aux[M, ldo] + acc + bias        (residual stream, may alias out)
   EPI_POS_F32 = 3,     // out fp32 [M, ldo]      = acc + bias + aux[(row % period), N] (patch embed + pos embed)
   EPI_NCHW_F32 = 4,    // out fp32 [M/period, N, period] = acc + bias             (final conv -> heatmaps)
+  EPI_POSTMA_F32 = 5,  // as EPI_POS_F32 with the positional rows streamed by TMA (needs period % 64 == 0); internal
 };
+// epilogues that add an fp32 tile fetched by the residual-producer warp and store fp32 through the in-place ring
+__host__ __device__ constexpr bool gemm_epi_adds_tile(int epi) { return epi == EPI_RESID_F32 || epi == EPI_POSTMA_F32; }
 
 struct GemmParams {
   int M, N, K;
@@ -36,12 +39,14 @@ constexpr int GEMM_BK = 64;   // 64 bf16 = one 128-byte swizzle row
 __host__ __device__ constexpr int gemm_epi_groups(int epi) { return (epi == 0 || epi == 1) ? 2 : 1; }
 // EPI_RESID_F32 adds warp 6: a TMA producer that streams the fp32 residual tile through a ring of in-place
 // staging slots, running ahead of the epilogue (and of the MMAs) by up to GEMM_RES_SLOTS chunks.
-__host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 128 * gemm_epi_groups(epi) + (epi == 2 ? 32 : 0); }
+__host__ __device__ constexpr int gemm_threads(int epi) {
+  return 64 + 128 * gemm_epi_groups(epi) + ((epi == 2 || epi == 5) ? 32 : 0);
+}
 constexpr int GEMM_RES_SLOTS = 4;
 constexpr int GEMM_STAGING_BYTES = GEMM_BM * 128;   // one [128 rows x 128 B] TMA-store box
 
 __host__ __device__ constexpr bool gemm_epi_staged(int epi) {
-  return epi == EPI_BIAS_BF16 || epi == EPI_GELU_BF16 || epi == EPI_RESID_F32;
+  return epi == EPI_BIAS_BF16 || epi == EPI_GELU_BF16 || epi == EPI_RESID_F32 || epi == EPI_POSTMA_F32;
 }
 __host__ __device__ constexpr int gemm_tmem_cols(int bn) {
   return 2 * bn <= 32 ? 32 : 2 * bn <= 64 ? 64 : 2 * bn <= 128 ? 128 : 2 * bn <= 256 ? 256 : 512;
@@ -50,7 +55,7 @@ __host__ __device__ constexpr int gemm_tmem_cols(int bn) {
 __host__ __device__ constexpr int gemm_stage_bytes(int bn, int cg = 1) { return GEMM_BM * 128 + bn * 128 / cg; }
 // shared memory for the epilogue: one staging box per bf16 epilogue group, or the 4-slot residual ring
 __host__ __device__ constexpr int gemm_epi_smem(int epi) {
-  return !gemm_epi_staged(epi) ? 0 : (epi == EPI_RESID_F32 ? 4 : 2) * GEMM_STAGING_BYTES;
+  return !gemm_epi_staged(epi) ? 0 : (gemm_epi_adds_tile(epi) ? 4 : 2) * GEMM_STAGING_BYTES;
 }
 __host__ __device__ constexpr int gemm_num_stages(int bn, int epi, int cg = 1) {
   // 227 KB usable, minus 1 KB alignment slack and ~1 KB of static shared memory
@@ -117,7 +122,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM * CG, BN);
   static_assert(CG == 1 || (CG == 2 && BN % 32 == 0), "CTA pairs split the B tile in two halves");
   constexpr bool STAGED = gemm_epi_staged(EPI);
-  constexpr int CHUNK = (EPI == EPI_RESID_F32) ? 32 : 64;     // columns per 128-byte staging row
+  constexpr int CHUNK = (gemm_epi_adds_tile(EPI)) ? 32 : 64;     // columns per 128-byte staging row
   constexpr int GROUPS = gemm_epi_groups(EPI);                // epilogue warpgroups
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
   static_assert(!STAGED || BN % CHUNK == 0, "staged epilogue needs BN to be a multiple of the chunk width");
@@ -163,7 +168,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     if (STAGED) tma_prefetch_desc(&tma_out);
-    if (EPI == EPI_RESID_F32) tma_prefetch_desc(&tma_aux);
+    if (gemm_epi_adds_tile(EPI)) tma_prefetch_desc(&tma_aux);
   }
   if (warp == 1) {
     if constexpr (CG == 2) tmem_alloc_pair(&tmem_slot, TMEM_COLS);
@@ -237,7 +242,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (EPI == EPI_RESID_F32 && warp == 6) {
+  } else if (gemm_epi_adds_tile(EPI) && warp == 6) {
     // residual producer: chunk c of tile (m_blk, n_blk) = fp32 [128 rows x 32 cols] -> ring slot (in-place staging)
     if (lane == 0) {
       uint32_t seq = 0;
@@ -248,8 +253,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           const uint32_t slot = seq % GEMM_RES_SLOTS;
           mbar_wait(&res_empty[slot], ((seq / GEMM_RES_SLOTS) & 1) ^ 1);
           mbar_arrive_expect_tx(&res_full[slot], GEMM_STAGING_BYTES);
-          tma_load_2d(s_out + slot * GEMM_STAGING_BYTES, &tma_aux, &res_full[slot], n_blk * BN + c * 32,
-                      m_blk * GEMM_BM);
+          if constexpr (EPI == EPI_POSTMA_F32) {
+            // positional table rows (token = row % period): two 64-row boxes, each inside one period (period % 64 == 0)
+            const int t0 = (m_blk * GEMM_BM) % p.period, t1 = (m_blk * GEMM_BM + 64) % p.period;
+            tma_load_2d(s_out + slot * GEMM_STAGING_BYTES, &tma_aux, &res_full[slot], n_blk * BN + c * 32, t0);
+            tma_load_2d(s_out + slot * GEMM_STAGING_BYTES + 64 * 128, &tma_aux, &res_full[slot], n_blk * BN + c * 32,
+                        t1);
+          } else {
+            tma_load_2d(s_out + slot * GEMM_STAGING_BYTES, &tma_aux, &res_full[slot], n_blk * BN + c * 32,
+                        m_blk * GEMM_BM);
+          }
         }
       }
     }
@@ -289,7 +302,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll 1
         for (int c = grp; c < NCHUNK; c += GROUPS, ++chunk_seq) {
           // staging slot: bf16 epilogues own one box per group; the residual epilogue walks the in-place ring
-          const uint32_t buf = EPI == EPI_RESID_F32 ? (chunk_seq % GEMM_RES_SLOTS) : static_cast<uint32_t>(grp);
+          const uint32_t buf = gemm_epi_adds_tile(EPI) ? (chunk_seq % GEMM_RES_SLOTS) : static_cast<uint32_t>(grp);
           uint32_t v[CHUNK];
           if constexpr (CHUNK == 64) {
             tmem_ld_32x32b_x32(t_row + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -305,7 +318,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
           uint8_t* srow = s_out + buf * GEMM_STAGING_BYTES + r * 128;
           const float* bias_c = &s_bias[grp][(c / GROUPS) * CHUNK];
-          if constexpr (EPI == EPI_RESID_F32) {
+          if constexpr (gemm_epi_adds_tile(EPI)) {
             // residual chunk landed in the slot (TMA, issued by warp 6 well ahead); update it in place: every thread
             // reads and writes only its own 128-byte row, so no barrier is needed before the math
             mbar_wait(&res_full[buf], (chunk_seq / GEMM_RES_SLOTS) & 1);
@@ -342,7 +355,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (etid == 0) {
             tma_store_2d(&tma_out, s_out + buf * GEMM_STAGING_BYTES, n_blk * BN + c * CHUNK, m_blk * GEMM_BM);
             tma_store_commit();
-            if constexpr (EPI == EPI_RESID_F32) {
+            if constexpr (gemm_epi_adds_tile(EPI)) {
               // hand the previous chunk's slot back to the residual producer once its store has read it
               if (chunk_seq > 0) {
                 tma_store_wait_read<1>();

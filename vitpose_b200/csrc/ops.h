@@ -14,7 +14,7 @@ struct GemmMaps { CUtensorMap a, b, out, aux; };
 int gemm_pick_bn(int N, int epilogue);
 int gemm_pick_cg(int M, int bn, int epilogue, int K);
 int make_gemm_maps(GemmMaps* maps, const void* A, const void* B, int M, int N, int K, int lda, int ldb, int bn,
-                   int epilogue, void* out, int ldo, const float* aux, int cg);
+                   int epilogue, void* out, int ldo, const float* aux, int cg, int period);
 int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue, int cg, int max_ctas,
                 cudaStream_t stream);
 int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, void* out, int ldo,

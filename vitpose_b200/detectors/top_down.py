@@ -97,12 +97,18 @@ class TopDown(nn.Module):
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(dev)
             staged = []
-            for lo in range(0, n, chunk):
+            # geometric chunk schedule (32, 64, 128, ...): a small first chunk starts the GPU early, later chunks
+            # grow because their copies are hidden behind the compute of the chunks before them
+            lo, size = 0, max(1, chunk // 2)
+            while lo < n:
+                size = min(size, n - lo)
                 with torch.cuda.stream(self._copy_stream):
-                    d = img[lo:lo + chunk].to(dev, non_blocking=True)
+                    d = img[lo:lo + size].to(dev, non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(self._copy_stream)
                 staged.append((lo, d, ev))
+                lo += size
+                size *= 2
             for lo, d, ev in staged:
                 main_stream.wait_event(ev)
                 d.record_stream(main_stream)
