@@ -151,6 +151,21 @@ int vpb_conv3x3_nchw(const void* in, const void* w9, const float* bias, float* o
 int vpb_relu_upsample_nhwc(const void* in, void* out, int n, int h, int w, int C, int factor, void* stream);
 int vpb_tokens_to_nchw_f32(const void* tokens, float* out, int n, int T, int D, void* stream);
 
+/* ---- training-step operators (the network backward is not part of this library yet) ----
+ * JointsMSELoss.forward (mmpose/models/losses/mse_loss.py:24-45): loss[0] = loss_weight / K * sum_k mean_{n,hw}
+ * ((output - target) * target_weight[n,k])^2; target_weight may be NULL (use_target_weight=False);
+ * grad_output (optional, same shape as output) receives d loss / d output. */
+int vpb_joints_mse_loss(const float* output, const float* target, const float* target_weight, int N, int K, int HW,
+                        float loss_weight, float* loss, float* grad_output, void* stream);
+/* adds sum(grad^2) to *sq_norm_accum (zero it once per step; sqrt = clip_grad_norm_'s total norm) */
+int vpb_grad_sq_norm_accumulate(const float* grad, long long n, float* sq_norm_accum, void* stream);
+/* torch.optim.AdamW update of one tensor with its group's lr / weight_decay (layer decay:
+ * mmcv_custom/layer_decay_optimizer_constructor.py:6-78); when sq_norm != NULL gradients are scaled by
+ * min(1, max_norm / (sqrt(*sq_norm) + 1e-6)) first (grad_clip=dict(max_norm=1.)). */
+int vpb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int step, const float* sq_norm,
+                   float max_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

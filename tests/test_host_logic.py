@@ -180,8 +180,9 @@ def test_flip_index_matches_pairwise_swap():
     assert perm[1] == 2 and perm[2] == 1 and perm[0] == 0 and perm[91] == 112
 
 
-def test_joints_mse_loss_matches_golden(golden_dir):
+def test_joints_mse_loss_has_no_cpu_path(golden_dir):
     g = np.load(os.path.join(golden_dir, 'loss_kat.npz'))
     loss = V.build_loss(dict(type='JointsMSELoss', use_target_weight=True))
     o, t, w = (torch.from_numpy(g[k]) for k in ('output', 'target', 'weight'))
-    np.testing.assert_allclose(loss(o, t, w).numpy(), g['loss_weighted'], rtol=1e-6)
+    with pytest.raises(_lib.VitposeLibError):
+        loss(o, t, w)          # value parity vs the golden KATs is checked on the GPU (tests/test_training_ops.py)

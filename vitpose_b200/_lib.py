@@ -56,6 +56,11 @@ _SIGS = {
     'vpb_flip_back': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'vpb_transform_preds': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p]),
+    'vpb_joints_mse_loss': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                                    c_void_p]),
+    'vpb_grad_sq_norm_accumulate': (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p]),
+    'vpb_adamw_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_float, c_float, c_float,
+                               c_float, c_float, c_int, c_void_p, c_float, c_void_p]),
     'vpb_gemm_bf16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                               c_int, c_int, c_void_p]),
     'vpb_layernorm_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),

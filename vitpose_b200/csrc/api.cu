@@ -263,4 +263,18 @@ int vpb_tokens_to_nchw_f32(const void* tokens, float* out, int n, int T, int D, 
   return tokens_to_nchw_f32(tokens, out, n, T, D, as_stream(stream));
 }
 
+int vpb_joints_mse_loss(const float* output, const float* target, const float* target_weight, int N, int K, int HW,
+                        float loss_weight, float* loss, float* grad_output, void* stream) {
+  return joints_mse_loss(output, target, target_weight, N, K, HW, loss_weight, loss, grad_output, as_stream(stream));
+}
+int vpb_grad_sq_norm_accumulate(const float* grad, long long n, float* sq_norm_accum, void* stream) {
+  return grad_sq_norm_accumulate(grad, n, sq_norm_accum, as_stream(stream));
+}
+int vpb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int step, const float* sq_norm,
+                   float max_norm, void* stream) {
+  return adamw_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, sq_norm, max_norm,
+                    as_stream(stream));
+}
+
 }  // extern "C"

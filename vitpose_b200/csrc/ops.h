@@ -60,4 +60,12 @@ int flip_back(const float* in, const int* perm, float* out, int N, int K, int H,
 int transform_preds(const float* coords, const float* center, const float* scale, float* out, int N, int K, int W,
                     int H, int use_udp, cudaStream_t stream);
 
+// ---- training-step operators (train_ops.cu) ----
+int joints_mse_loss(const float* output, const float* target, const float* target_weight, int N, int K, int HW,
+                    float loss_weight, float* loss, float* grad_output, cudaStream_t stream);
+int grad_sq_norm_accumulate(const float* grad, long long n, float* sq_norm_accum, cudaStream_t stream);
+int adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int step, const float* sq_norm, float max_norm,
+               cudaStream_t stream);
+
 }  // namespace vpb

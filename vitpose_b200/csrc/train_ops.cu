@@ -1,0 +1,121 @@
+// Training-step operators of the ViTPose-B training config: the pieces that do not need the
+// network backward — heatmap loss (+ its gradient), global gradient norm, and the AdamW update with per-group
+// lr / weight decay (layer decay). All are single-pass, vectorised, HBM-bound kernels.
+//   JointsMSELoss.forward      mmpose/models/losses/mse_loss.py:24-45
+//   clip_grad_norm_(max_norm)  mmcv OptimizerHook (grad_clip=dict(max_norm=1.), ViTPose_base_coco_256x192.py:30)
+//   AdamW step                 torch.optim.AdamW as configured at ViTPose_base_coco_256x192.py:16-28
+#include "host_util.h"
+#include "ops.h"
+
+namespace vpb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// loss = loss_weight / (K * N * HW) * sum_{n,k,hw} ((o - t) * w[n,k])^2 ; grad_o = 2 * c * w^2 * (o - t)
+__global__ void joints_mse_kernel(const float* __restrict__ out, const float* __restrict__ tgt,
+                                  const float* __restrict__ w, float* __restrict__ loss, float* __restrict__ grad,
+                                  int HW, long long total, float coef) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  float acc = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const float wk = w ? w[i / HW] : 1.0f;
+    const float d = (out[i] - tgt[i]) * wk;
+    acc = fmaf(d, d, acc);
+    if (grad) grad[i] = 2.0f * coef * wk * d;
+  }
+  acc = warp_sum(acc);
+  __shared__ float s[32];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(loss, v * coef);
+  }
+}
+
+int joints_mse_loss(const float* output, const float* target, const float* target_weight, int N, int K, int HW,
+                    float loss_weight, float* loss, float* grad_output, cudaStream_t stream) {
+  VPB_REQUIRE(N > 0 && K > 0 && HW > 0, "joints_mse: bad shape");
+  const long long total = static_cast<long long>(N) * K * HW;
+  VPB_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), stream));
+  const float coef = loss_weight / (static_cast<float>(K) * static_cast<float>(N) * static_cast<float>(HW));
+  int blocks = static_cast<int>((total + 255) / 256);
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  joints_mse_kernel<<<blocks, 256, 0, stream>>>(output, target, target_weight, loss, grad_output, HW, total, coef);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void sq_norm_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  float acc = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    acc = fmaf(g[i], g[i], acc);
+  acc = warp_sum(acc);
+  __shared__ float s[32];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+
+// accumulates sum(g^2) into *sq_norm_accum (caller zeroes it once per step, calls per tensor, takes sqrt)
+int grad_sq_norm_accumulate(const float* grad, long long n, float* sq_norm_accum, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  int blocks = static_cast<int>((n + 255) / 256);
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  sq_norm_kernel<<<blocks, 256, 0, stream>>>(grad, n, sq_norm_accum);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// torch.optim.AdamW (decoupled weight decay, bias correction), gradient pre-scaled by clip coefficient
+// min(1, max_norm / (sqrt(*sq_norm) + 1e-6)) when sq_norm != null.
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
+                             float wd, float bc1, float bc2_sqrt, const float* __restrict__ sq_norm, float max_norm) {
+  float gs = 1.0f;
+  if (sq_norm != nullptr) {
+    const float coef = max_norm / (sqrtf(*sq_norm) + 1e-6f);
+    gs = coef < 1.0f ? coef : 1.0f;
+  }
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i] * gs;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+int adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int step, const float* sq_norm, float max_norm,
+               cudaStream_t stream) {
+  if (n <= 0) return 0;
+  VPB_REQUIRE(step >= 1, "adamw: step must be >= 1");
+  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+  const float bc2_sqrt = sqrtf(1.0f - powf(beta2, static_cast<float>(step)));
+  int blocks = static_cast<int>((n + 255) / 256);
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  adamw_kernel<<<blocks, 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                                           bc1, bc2_sqrt, sq_norm, max_norm);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vpb
