@@ -151,6 +151,19 @@ int vpb_conv3x3_nchw(const void* in, const void* w9, const float* bias, float* o
 int vpb_relu_upsample_nhwc(const void* in, void* out, int n, int h, int w, int C, int factor, void* stream);
 int vpb_tokens_to_nchw_f32(const void* tokens, float* out, int n, int T, int D, void* stream);
 
+/* ---- preprocessing ----
+ * TopDownAffine + ToTensor + NormalizeTensor for n boxes (mmpose/datasets/pipelines/top_down_transform.py:295-364,
+ * shared_transform.py:21-65): out[i] = ((warpAffine_u8(src[i], M_i, (out_w,out_h), INTER_LINEAR) / 255) - mean) / std
+ * as fp32 NCHW, bit-identical to cv2.warpAffine on uint8 + torchvision to_tensor/normalize.
+ *   src_ptrs  device array [n] of device pointers to uint8 HWC (3-channel, dense) images
+ *   src_hw    device int32 [n,2] (height, width) of each source image
+ *   inv_mats  device float64 [n,6]: the INVERSE (dst->src) 2x3 affine map, i.e. cv::invertAffineTransform of the
+ *             matrix get_warp_matrix / get_affine_transform returns (computed by the host in double)
+ *   mean3/std3 HOST float[3] */
+int vpb_warp_affine_normalize(const unsigned char* const* src_ptrs, const int32_t* src_hw, const double* inv_mats,
+                              int n, int out_h, int out_w, const float* mean3, const float* std3, float* out,
+                              void* stream);
+
 /* ---- training-step operators (the network backward is not part of this library yet) ----
  * JointsMSELoss.forward (mmpose/models/losses/mse_loss.py:24-45): loss[0] = loss_weight / K * sum_k mean_{n,hw}
  * ((output - target) * target_weight[n,k])^2; target_weight may be NULL (use_target_weight=False);

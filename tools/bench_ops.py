@@ -98,3 +98,20 @@ def main():
 
 if __name__ == '__main__':
     main()
+
+
+def bench_preprocess(crops=256):
+    """HBM roofline of the fused warp+normalise kernel: bytes = fp32 crop written + source pixels touched."""
+    from vitpose_b200 import pipelines as PL
+    dev = torch.device('cuda:0')
+    img = torch.randint(0, 256, (1080, 1920, 3), device=dev, dtype=torch.uint8)
+    boxes = [(0, [100 + 5 * i, 80 + 2 * i, 300, 500]) for i in range(crops)]
+    ms = timeit(lambda: PL.preprocess_crops([img], boxes))
+    out_b = crops * 3 * 256 * 192 * 4
+    src_b = crops * int(300 * 1.25 * 500 * 1.25 * 3)        # box area read at most once from HBM (then L2)
+    print('preprocess', json.dumps(dict(ms=round(ms, 4), gbs=round((out_b + src_b) / ms / 1e6, 1), crops=crops,
+                                        note='includes host-side matrix maths + 3 small H2D copies')))
+
+
+if __name__ == '__main__' and os.environ.get('VPB_BENCH_PREPROCESS'):
+    bench_preprocess()

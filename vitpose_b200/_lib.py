@@ -56,6 +56,8 @@ _SIGS = {
     'vpb_flip_back': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'vpb_transform_preds': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p]),
+    'vpb_warp_affine_normalize': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                          ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p, c_void_p]),
     'vpb_joints_mse_loss': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                     c_void_p]),
     'vpb_grad_sq_norm_accumulate': (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p]),

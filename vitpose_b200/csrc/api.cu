@@ -277,4 +277,13 @@ int vpb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
                     as_stream(stream));
 }
 
+int vpb_warp_affine_normalize(const unsigned char* const* src_ptrs, const int32_t* src_hw, const double* inv_mats,
+                              int n, int out_h, int out_w, const float* mean3, const float* std3, float* out,
+                              void* stream) {
+  cudaStream_t st = as_stream(stream);
+  return prof_run("warp_affine_normalize", st, [&] {
+    return warp_affine_normalize(src_ptrs, src_hw, inv_mats, n, out_h, out_w, mean3, std3, out, st);
+  });
+}
+
 }  // extern "C"

@@ -60,6 +60,11 @@ int flip_back(const float* in, const int* perm, float* out, int N, int K, int H,
 int transform_preds(const float* coords, const float* center, const float* scale, float* out, int N, int K, int W,
                     int H, int use_udp, cudaStream_t stream);
 
+// ---- preprocessing (preprocess.cu) ----
+int warp_affine_normalize(const unsigned char* const* src_ptrs, const int* src_hw, const double* inv_mats, int n,
+                          int out_h, int out_w, const float* mean3, const float* std3, float* out,
+                          cudaStream_t stream);
+
 // ---- training-step operators (train_ops.cu) ----
 int joints_mse_loss(const float* output, const float* target, const float* target_weight, int N, int K, int HW,
                     float loss_weight, float* loss, float* grad_output, cudaStream_t stream);
