@@ -226,8 +226,8 @@ def main():
             by_tag.setdefault(tag, []).append(v)
         bb = cfg['backbone']
         D, hidden, rows = bb['embed_dim'], int(bb['embed_dim'] * bb['mlp_ratio']), 2 * n * 192
-        flops = {'gemm_qkv': 2.0 * rows * 3 * D * D, 'gemm_proj': 2.0 * rows * D * D,
-                 'gemm_fc1': 2.0 * rows * hidden * D, 'gemm_fc2': 2.0 * rows * hidden * D}
+        flops = {'gemm_qkv': 2.0 * rows * 3 * D * D, 'gemm_proj_ln': 2.0 * rows * D * D,
+                 'gemm_fc1': 2.0 * rows * hidden * D, 'gemm_fc2_ln': 2.0 * rows * hidden * D}
         dom = 'gemm_fc1'
         dom_ms = float(np.mean(by_tag[dom]))
         achieved = flops[dom] / dom_ms / 1e9

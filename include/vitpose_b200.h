@@ -140,6 +140,18 @@ enum {
 /* C = A[M,K] (bf16, row-major) x B[N,K]^T (bf16, row-major) on tcgen05 tensor cores. max_ctas <= 0: one per SM. */
 int vpb_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, void* out,
                   int ldo, const float* aux, int period, int max_ctas, void* stream);
+/* Residual-stream GEMM with the following LayerNorm fused into its epilogue:
+ *   out fp32 [M,N] = (epilogue == VPB_EPI_RESID_F32 ? aux[M,N] : aux[row % period, N]) + A.B^T + bias
+ *   xn  bf16 [M,N] = LayerNorm(out row, eps) * gamma + beta
+ * i.e. `x = x + attn.proj(..)` / `x = x + mlp.fc2(..)` / patch embed + pos embed together with the norm1 / norm2 /
+ * last_norm that consumes the result (vit.py:137-140, :320, :328). The CTAs that own the column tiles of one
+ * 128-row block exchange per-row (mean, M2) through `scratch` (vpb_gemm_layernorm_scratch_bytes(M, N) bytes,
+ * 16-byte aligned, contents don't care), so the rows are normalised while they are still in tensor memory.
+ * out may alias aux (in-place residual update). */
+size_t vpb_gemm_layernorm_scratch_bytes(int M, int N);
+int vpb_gemm_bf16_layernorm(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias,
+                            float* out, const float* aux, int period, const float* gamma, const float* beta, float eps,
+                            void* xn, void* scratch, size_t scratch_bytes, void* stream);
 int vpb_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int M, int D, float eps,
                        void* stream);
 int vpb_im2col_patch16(const float* img, void* patches, int n, int H, int W, int flip, void* stream);

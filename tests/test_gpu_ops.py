@@ -95,6 +95,46 @@ def test_gemm_nchw_heatmap(Kout, C):
     _report('gemm nchw', out, ref, 2e-3, bf16_out=False)
 
 
+@pytest.mark.parametrize('M,D,K,offset', [
+    (192 * 3, 128, 128, 0.0), (192 * 5, 384, 384, 0.5), (192 * 7, 768, 768, 0.0), (192 * 40, 768, 3072, 3.0),
+    (192 * 200, 768, 768, 0.5), (192 * 200, 768, 3072, 0.0), (192 * 33, 1024, 1024, 0.0), (192 * 64, 1280, 5120, 1.0),
+    (192, 768, 768, 0.0)])
+def test_gemm_residual_layernorm_fused(M, D, K, offset):
+    """x = x + a @ w^T + bias (fp32, in place) and xn = LayerNorm(x) * gamma + beta from ONE kernel, against the
+    two-step fp32 reference; row means up to 3 sigma to exercise the (mean, M2) merge across column tiles."""
+    from vitpose_b200 import ops, _lib
+    g = torch.Generator().manual_seed(M + D)
+    a, w = _rand_bf16((M, K), 31), _rand_bf16((D, K), 32, 1.0 / math.sqrt(K))
+    bias = torch.randn(D, generator=g)
+    resid = torch.randn(M, D, generator=g) * 2 + offset * 2
+    gamma, beta = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    x = resid.clone().to(_dev())
+    out, xn = ops.gemm_layernorm(a.to(_dev()), w.to(_dev()), _lib.EPI_RESID_F32, bias.to(_dev()), x,
+                                 gamma.to(_dev()), beta.to(_dev()), 1e-6, out=x)
+    torch.cuda.synchronize()
+    assert out.data_ptr() == x.data_ptr()
+    if M * D * K <= 192 * 64 * 1280 * 5120:
+        ref = resid.to(_dev()) + a.to(_dev()).float() @ w.to(_dev()).float().t() + bias.to(_dev())
+        _report('gemm+residual (ln variant)', x, ref.cpu(), 2e-3, bf16_out=False)
+    # LayerNorm of the kernel's own fp32 rows isolates the normalisation from GEMM rounding
+    ref_n = F.layer_norm(x.cpu(), (D,), gamma, beta, 1e-6)
+    _report('fused layernorm', xn, ref_n, 0.04)
+
+
+def test_gemm_pos_layernorm_fused():
+    from vitpose_b200 import ops, _lib
+    T, n, D, K = 192, 9, 768, 768
+    g = torch.Generator().manual_seed(5)
+    a, b = _rand_bf16((n * T, K), 11), _rand_bf16((D, K), 12, 1.0 / math.sqrt(K))
+    bias, pos = torch.randn(D, generator=g), torch.randn(T, D, generator=g)
+    gamma, beta = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    out, xn = ops.gemm_layernorm(a.to(_dev()), b.to(_dev()), _lib.EPI_POS_F32, bias.to(_dev()), pos.to(_dev()),
+                                 gamma.to(_dev()), beta.to(_dev()), 1e-6, period=T)
+    ref = (a.float() @ b.float().t() + bias).reshape(n, T, D) + pos
+    _report('gemm+pos (ln variant)', out.reshape(n, T, D), ref, 2e-3, bf16_out=False)
+    _report('fused layernorm', xn, F.layer_norm(out.cpu(), (D,), gamma, beta, 1e-6), 0.04)
+
+
 @pytest.mark.parametrize('D', [128, 384, 768, 1024, 1280])
 def test_layernorm(D):
     from vitpose_b200 import ops

@@ -55,6 +55,14 @@ def main():
         res[name]['cublas_ms'] = ref_ms
         res[name]['cublas_tflops'] = 2.0 * M * N * K / ref_ms / 1e9
         del A, B, out
+    for name, K in (('proj_ln', D), ('fc2_ln', 4 * D)):      # residual GEMM + fused LayerNorm (one kernel)
+        A = torch.randn(M, K, device=dev).to(BF16)
+        B = (torch.randn(D, K, device=dev) / math.sqrt(K)).to(BF16)
+        bias, gm, bt = torch.randn(D, device=dev), torch.ones(D, device=dev), torch.zeros(D, device=dev)
+        out = torch.randn(M, D, device=dev)
+        ms = timeit(lambda: ops.gemm_layernorm(A, B, _lib.EPI_RESID_F32, bias, out, gm, bt, out=out))
+        res[name] = dict(ms=ms, tflops=2.0 * M * D * K / ms / 1e9)
+        del A, B, out
     qkv = torch.randn(a.crops * 2, 192, 3 * D, device=dev).to(BF16)
     ms = timeit(lambda: ops.attention(qkv, heads))
     fl = 4.0 * a.crops * 2 * 192 * 192 * D
@@ -91,7 +99,7 @@ def main():
         res[nm] = dict(ms=ms, gbs=n2 * 17 * 3072 * 4 / ms / 1e6)
     for k, v in res.items():
         print(k, json.dumps({kk: round(vv, 4) for kk, vv in v.items()}))
-    per_layer = res['qkv']['ms'] + res['proj']['ms'] + res['fc1']['ms'] + res['fc2']['ms'] + res['attention']['ms'] + 2 * res['layernorm']['ms']
+    per_layer = res['qkv']['ms'] + res['proj_ln']['ms'] + res['fc1']['ms'] + res['fc2_ln']['ms'] + res['attention']['ms']
     total = depth * per_layer + res['deconv1']['ms'] + res['deconv2']['ms'] + res['final1x1']['ms'] + res['im2col']['ms'] + res['decode_udp']['ms']
     print('est step ms', round(total, 3), 'crops/s', round(a.crops / total * 1e3, 1))
 

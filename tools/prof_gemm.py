@@ -18,6 +18,14 @@ if which == 'attn':
     qkv = torch.randn(256, 192, 3 * D, device=dev).to(BF16)
     for _ in range(3):
         ops.attention(qkv, 12)
+elif which in ('proj_ln', 'fc2_ln'):
+    K = D if which == 'proj_ln' else 4 * D
+    A = torch.randn(M, K, device=dev).to(BF16)
+    B = (torch.randn(D, K, device=dev) / math.sqrt(K)).to(BF16)
+    bias, gm, bt = torch.randn(D, device=dev), torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    out = torch.randn(M, D, device=dev)
+    for _ in range(3):
+        ops.gemm_layernorm(A, B, _lib.EPI_RESID_F32, bias, out, gm, bt, out=out)
 else:
     N, K, epi = shapes[which]
     A = torch.randn(M, K, device=dev).to(BF16)

@@ -65,6 +65,9 @@ _SIGS = {
                                c_float, c_float, c_int, c_void_p, c_float, c_void_p]),
     'vpb_gemm_bf16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                               c_int, c_int, c_void_p]),
+    'vpb_gemm_layernorm_scratch_bytes': (c_size_t, [c_int, c_int]),
+    'vpb_gemm_bf16_layernorm': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                        c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     'vpb_layernorm_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     'vpb_im2col_patch16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'vpb_attention': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),

@@ -44,7 +44,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
   // offsets in bytes
-  size_t patches, x, xn, qkv, attn, hidden, head_a, head_b, total;
+  size_t patches, x, xn, qkv, attn, hidden, head_a, head_b, ln_scratch, total;
 };
 
 Workspace plan_workspace(const vpb_model_desc& d, int images) {
@@ -78,6 +78,8 @@ Workspace plan_workspace(const vpb_model_desc& d, int images) {
   }
   w.head_a = take(a);
   w.head_b = take(b);
+  // per-row LayerNorm partial statistics + arrival counters of the residual GEMMs with the fused LayerNorm
+  w.ln_scratch = take(gemm_ln_scratch_bytes(static_cast<int>(rows), static_cast<int>(D)));
   w.total = off;
   return w;
 }
@@ -134,36 +136,48 @@ int vpb_vitpose_forward(const vpb_model_desc* desc, const vpb_weights* w, const 
   void* attn = base + ws.attn;
   void* hidden = base + ws.hidden;
 
-  // PatchEmbed (vit.py:159-165) + pos embed (vit.py:320)
+  // The LayerNorm that follows every update of the residual stream (norm1 / norm2 of the next sub-block,
+  // vit.py:138-139, and last_norm, vit.py:328) is produced by the epilogue of the GEMM that writes the stream.
+  VPB_REQUIRE(d.has_last_norm, "forward: last_norm=False is not supported");
+  VPB_REQUIRE(d.depth > 0, "forward: depth must be positive");
+  void* ln_scratch = base + ws.ln_scratch;
+  if (int e = gemm_ln_scratch_init(ln_scratch, rows, D, stream)) return e;
+  unsigned epoch = 0;
+
+  // PatchEmbed (vit.py:159-165) + pos embed (vit.py:320) + blocks[0].norm1
   if (int e = prof_run("im2col", stream, [&] { return im2col_patch16(img, patches, n, d.img_h, d.img_w, flip, stream); })) return e;
-  if (int e = prof_run("gemm_patch", stream, [&] { return gemm_bf16(patches, w->patch_w, rows, D, 768, EPI_POS_F32, w->patch_b, x, D, w->pos, T, 0, stream); }))
+  if (int e = prof_run("gemm_patch_ln", stream, [&] {
+        return gemm_bf16_ln(patches, w->patch_w, rows, D, 768, EPI_POS_F32, w->patch_b, x, w->pos, T, w->blocks[0].ln1_g,
+                            w->blocks[0].ln1_b, d.ln_eps, xn, ln_scratch, ++epoch, 0, stream);
+      }))
     return e;
 
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   for (int l = 0; l < d.depth; ++l) {
     const vpb_block_weights& b = w->blocks[l];
-    // x = x + proj(attn(LN1(x)))            (vit.py:138)
-    if (int e = prof_run("layernorm", stream, [&] { return layernorm_bf16(x, b.ln1_g, b.ln1_b, xn, rows, D, d.ln_eps, stream); })) return e;
+    // x = x + proj(attn(LN1(x)))            (vit.py:138), then LN2(x) for the MLP
     if (int e = prof_run("gemm_qkv", stream, [&] { return gemm_bf16(xn, b.qkv_w, rows, 3 * D, D, EPI_BIAS_BF16, b.qkv_b, qkv, 3 * D, nullptr, 0, 0, stream); }))
       return e;
     if (int e = prof_run("attention", stream, [&] { return attention_fwd(qkv, attn, images, T, d.num_heads, hd, scale, 0, stream); })) return e;
-    if (int e = prof_run("gemm_proj", stream, [&] { return gemm_bf16(attn, b.proj_w, rows, D, D, EPI_RESID_F32, b.proj_b, x, D, x, 0, 0, stream); })) return e;
-    // x = x + fc2(gelu(fc1(LN2(x))))        (vit.py:139)
-    if (int e = prof_run("layernorm", stream, [&] { return layernorm_bf16(x, b.ln2_g, b.ln2_b, xn, rows, D, d.ln_eps, stream); })) return e;
+    if (int e = prof_run("gemm_proj_ln", stream, [&] {
+          return gemm_bf16_ln(attn, b.proj_w, rows, D, D, EPI_RESID_F32, b.proj_b, x, x, 0, b.ln2_g, b.ln2_b, d.ln_eps, xn,
+                              ln_scratch, ++epoch, 0, stream);
+        }))
+      return e;
+    // x = x + fc2(gelu(fc1(LN2(x))))        (vit.py:139), then the next block's LN1 (or last_norm, vit.py:328)
     if (int e = prof_run("gemm_fc1", stream, [&] { return gemm_bf16(xn, b.fc1_w, rows, d.mlp_hidden, D, EPI_GELU_BF16, b.fc1_b, hidden, d.mlp_hidden, nullptr,
                           0, 0, stream); }))
       return e;
-    if (int e = prof_run("gemm_fc2", stream, [&] { return gemm_bf16(hidden, b.fc2_w, rows, D, d.mlp_hidden, EPI_RESID_F32, b.fc2_b, x, D, x, 0, 0, stream); }))
+    const float* ng = l + 1 < d.depth ? w->blocks[l + 1].ln1_g : w->last_g;
+    const float* nb = l + 1 < d.depth ? w->blocks[l + 1].ln1_b : w->last_b;
+    if (int e = prof_run("gemm_fc2_ln", stream, [&] {
+          return gemm_bf16_ln(hidden, b.fc2_w, rows, D, d.mlp_hidden, EPI_RESID_F32, b.fc2_b, x, x, 0, ng, nb, d.ln_eps, xn,
+                              ln_scratch, ++epoch, 0, stream);
+        }))
       return e;
   }
-  // last_norm (vit.py:328); token-major [images, T, D] == NHWC [images, hp, wp, D] for the head
+  // token-major [images, T, D] == NHWC [images, hp, wp, D] for the head
   void* feat = xn;
-  if (d.has_last_norm) {
-    if (int e = prof_run("layernorm", stream, [&] { return layernorm_bf16(x, w->last_g, w->last_b, xn, rows, D, d.ln_eps, stream); })) return e;
-  } else {
-    set_last_error("forward: last_norm=False is not supported");
-    return -2;
-  }
   if (features != nullptr)
     VPB_CHECK_CUDA(cudaMemcpyAsync(features, feat, static_cast<size_t>(rows) * D * 2, cudaMemcpyDeviceToDevice, stream));
   if (heatmaps == nullptr) return 0;
@@ -238,6 +252,17 @@ int vpb_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogu
                   int ldo, const float* aux, int period, int max_ctas, void* stream) {
   return gemm_bf16(A, B, M, N, K, epilogue, bias, out, ldo, aux, period, max_ctas, as_stream(stream));
 }
+int vpb_gemm_bf16_layernorm(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias,
+                            float* out, const float* aux, int period, const float* gamma, const float* beta, float eps,
+                            void* xn, void* scratch, size_t scratch_bytes, void* stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  VPB_REQUIRE(M > 0 && N > 0, "gemm+layernorm: empty problem");
+  VPB_REQUIRE(scratch != nullptr && scratch_bytes >= gemm_ln_scratch_bytes(M, N),
+              "gemm+layernorm: scratch too small (%zu < %zu)", scratch_bytes, gemm_ln_scratch_bytes(M, N));
+  if (int e = gemm_ln_scratch_init(scratch, M, N, stream)) return e;
+  return gemm_bf16_ln(A, B, M, N, K, epilogue, bias, out, aux, period, gamma, beta, eps, xn, scratch, 1u, 0, stream);
+}
+size_t vpb_gemm_layernorm_scratch_bytes(int M, int N) { return M > 0 && N > 0 ? gemm_ln_scratch_bytes(M, N) : 0; }
 int vpb_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int M, int D, float eps,
                        void* stream) {
   return layernorm_bf16(x, gamma, beta, y, M, D, eps, as_stream(stream));

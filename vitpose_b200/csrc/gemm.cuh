@@ -19,9 +19,23 @@ enum GemmEpilogue {
   EPI_POS_F32 = 3,     // out fp32 [M, ldo]      = acc + bias + aux[(row % period), N] (patch embed + pos embed)
   EPI_NCHW_F32 = 4,    // out fp32 [M/period, N, period] = acc + bias             (final conv -> heatmaps)
   EPI_POSTMA_F32 = 5,  // as EPI_POS_F32 with the positional rows streamed by TMA (needs period % 64 == 0); internal
+  // EPI_RESID_F32 / EPI_POSTMA_F32 that ALSO write LayerNorm(out row) * gamma + beta as bf16 [M, N] (N % BN == 0):
+  // the LayerNorm that follows every residual update (vit.py:138-139, 328) fused into the producing GEMM.
+  EPI_RESID_LN_F32 = 6,
+  EPI_POSTMA_LN_F32 = 7,
+  // the same for short-K GEMMs (attn.proj, patch embed), where the epilogue and not the MMA loop sets the pace:
+  // 3 operand stages, a deep residual ring, and the normalise pass on its own warpgroup (see gemm_ln_split)
+  EPI_RESID_LNS_F32 = 8,
+  EPI_POSTMA_LNS_F32 = 9,
 };
+__host__ __device__ constexpr bool gemm_epi_ln(int epi) { return epi >= EPI_RESID_LN_F32 && epi <= EPI_POSTMA_LNS_F32; }
+__host__ __device__ constexpr bool gemm_epi_pos(int epi) {
+  return epi == EPI_POSTMA_F32 || epi == EPI_POSTMA_LN_F32 || epi == EPI_POSTMA_LNS_F32;
+}
 // epilogues that add an fp32 tile fetched by the residual-producer warp and store fp32 through the in-place ring
-__host__ __device__ constexpr bool gemm_epi_adds_tile(int epi) { return epi == EPI_RESID_F32 || epi == EPI_POSTMA_F32; }
+__host__ __device__ constexpr bool gemm_epi_adds_tile(int epi) {
+  return epi == EPI_RESID_F32 || epi == EPI_POSTMA_F32 || gemm_epi_ln(epi);
+}
 
 struct GemmParams {
   int M, N, K;
@@ -30,6 +44,16 @@ struct GemmParams {
   int ldo;             // leading dimension of out / aux in elements
   const float* aux;    // residual or positional table
   int period;          // tokens per crop (EPI_POS) / pixels per crop (EPI_NCHW)
+  // fused LayerNorm (EPI_*_LN_F32): affine parameters [N] and the per-row partial statistics (mean, M2 of a tile's
+  // BN columns, one 8-byte word each) that the CTAs owning the n-tiles of one row block exchange through global
+  // memory. Launch e of a sequence writes region e & 1 and tags its words with bit (e >> 1) & 1 in the sign of M2,
+  // so a reader can tell them from the words launch e - 2 left there (see gemm_ln_scratch_init).
+  const float* ln_gamma;
+  const float* ln_beta;
+  unsigned long long* ln_part;   // two regions of [row blocks * 128, n_tiles] words, used alternately by launches
+  size_t ln_region;              // words per region
+  unsigned ln_epoch;
+  float ln_eps;
 };
 
 constexpr int GEMM_BM = 128;
@@ -39,32 +63,48 @@ constexpr int GEMM_BK = 64;   // 64 bf16 = one 128-byte swizzle row
 __host__ __device__ constexpr int gemm_epi_groups(int epi) { return (epi == 0 || epi == 1) ? 2 : 1; }
 // EPI_RESID_F32 adds warp 6: a TMA producer that streams the fp32 residual tile through a ring of in-place
 // staging slots, running ahead of the epilogue (and of the MMAs) by up to GEMM_RES_SLOTS chunks.
+// The short-K LayerNorm variants run TWO such epilogue warpgroups (warps 2..5 and 7..10), each with its own
+// residual ring and producer warp (6 and 11), on alternating tiles: with one warp per scheduler the epilogue of a
+// tile is a latency-bound instruction stream several times longer than the tile's MMA loop.
+__host__ __device__ constexpr bool gemm_ln_split(int epi) { return epi == EPI_RESID_LNS_F32 || epi == EPI_POSTMA_LNS_F32; }
 __host__ __device__ constexpr int gemm_threads(int epi) {
-  return 64 + 128 * gemm_epi_groups(epi) + ((epi == 2 || epi == 5) ? 32 : 0);
+  return 64 + 128 * gemm_epi_groups(epi) + (gemm_epi_adds_tile(epi) ? 32 : 0) + (gemm_ln_split(epi) ? 160 : 0);
 }
-constexpr int GEMM_RES_SLOTS = 4;
+constexpr int GEMM_RES_SLOTS = 4;   // upper bound (barrier arrays)
 constexpr int GEMM_STAGING_BYTES = GEMM_BM * 128;   // one [128 rows x 128 B] TMA-store box
 
 __host__ __device__ constexpr bool gemm_epi_staged(int epi) {
-  return epi == EPI_BIAS_BF16 || epi == EPI_GELU_BF16 || epi == EPI_RESID_F32 || epi == EPI_POSTMA_F32;
+  return epi == EPI_BIAS_BF16 || epi == EPI_GELU_BF16 || gemm_epi_adds_tile(epi);
 }
 __host__ __device__ constexpr int gemm_tmem_cols(int bn) {
   return 2 * bn <= 32 ? 32 : 2 * bn <= 64 ? 64 : 2 * bn <= 128 ? 128 : 2 * bn <= 256 ? 256 : 512;
 }
 // per-CTA bytes of one pipeline stage; with CTA pairs (cg = 2) each CTA stages its 128 A rows and HALF of the B tile
 __host__ __device__ constexpr int gemm_stage_bytes(int bn, int cg = 1) { return GEMM_BM * 128 + bn * 128 / cg; }
-// shared memory for the epilogue: one staging box per bf16 epilogue group, or the 4-slot residual ring
-__host__ __device__ constexpr int gemm_epi_smem(int epi) {
-  return !gemm_epi_staged(epi) ? 0 : (gemm_epi_adds_tile(epi) ? 4 : 2) * GEMM_STAGING_BYTES;
+// Slots of an in-place residual ring. The MMA-bound LayerNorm variant gives one up to keep its operand stages; the
+// short-K variants run 3 operand stages and split the rest of shared memory between their two rings.
+__host__ __device__ constexpr int gemm_res_slots(int bn, int epi, int cg) {
+  if (!gemm_ln_split(epi)) return gemm_epi_ln(epi) ? 3 : 4;
+  const int n = (230400 - 3 * gemm_stage_bytes(bn, cg) - 4096) / (2 * GEMM_STAGING_BYTES);
+  return n > GEMM_RES_SLOTS ? GEMM_RES_SLOTS : n;
+}
+// shared memory for the epilogue: one staging box per bf16 epilogue group, or the residual ring (+ gamma/beta)
+__host__ __device__ constexpr int gemm_epi_smem(int bn, int epi, int cg) {
+  return !gemm_epi_staged(epi) ? 0
+         : !gemm_epi_adds_tile(epi)
+             ? 2 * GEMM_STAGING_BYTES
+             : (gemm_ln_split(epi) ? 2 : 1) * (gemm_res_slots(bn, epi, cg) * GEMM_STAGING_BYTES +
+                                               (gemm_epi_ln(epi) ? 2048 : 0));
 }
 __host__ __device__ constexpr int gemm_num_stages(int bn, int epi, int cg = 1) {
   // 227 KB usable, minus 1 KB alignment slack and ~1 KB of static shared memory
-  return ((230400 - gemm_epi_smem(epi)) / gemm_stage_bytes(bn, cg)) > 8
+  return gemm_ln_split(epi) ? 3
+         : ((230400 - gemm_epi_smem(bn, epi, cg)) / gemm_stage_bytes(bn, cg)) > 8
              ? 8
-             : ((230400 - gemm_epi_smem(epi)) / gemm_stage_bytes(bn, cg));
+             : ((230400 - gemm_epi_smem(bn, epi, cg)) / gemm_stage_bytes(bn, cg));
 }
 __host__ __device__ constexpr int gemm_smem_bytes(int bn, int epi, int cg = 1) {
-  return gemm_num_stages(bn, epi, cg) * gemm_stage_bytes(bn, cg) + gemm_epi_smem(epi) + 1024;
+  return gemm_num_stages(bn, epi, cg) * gemm_stage_bytes(bn, cg) + gemm_epi_smem(bn, epi, cg) + 1024;
 }
 
 // Exact-erf GELU (nn.GELU default) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. float
@@ -105,6 +145,52 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   return __ffma2_rn(half_x, erf_s, half_x);
 }
 
+// Fused-LayerNorm statistics exchange: one 8-byte word per (row, n-tile) = {mean, M2 | tag << 31}; 8-byte accesses
+// are single-copy atomic, so the word carries its own validity (the tag of this launch) — no fence, flag or barrier.
+__device__ __forceinline__ void ln_publish_stats(const GemmParams& p, int m_blk, int r, int n_tiles, int n_blk,
+                                                 float mean, float m2) {
+  unsigned long long* part = p.ln_part + static_cast<size_t>(p.ln_epoch & 1u) * p.ln_region +
+                             (static_cast<size_t>(m_blk) * GEMM_BM + r) * n_tiles;
+  const uint32_t tag = ((p.ln_epoch >> 1) & 1u) << 31;
+  st_relaxed_gpu_u64(part + n_blk,
+                     (static_cast<unsigned long long>(__float_as_uint(fabsf(m2)) | tag) << 32) | __float_as_uint(mean));
+}
+// mean / rstd of row r over all N columns from the per-tile words (spins until every n-tile of the row has arrived;
+// all CTAs of the persistent grid are resident, siblings run in the same step of the tile loop)
+template <int BN>
+__device__ __forceinline__ void ln_row_stats(const GemmParams& p, int m_blk, int r, int n_tiles, float& mu,
+                                             float& rstd) {
+  const unsigned long long* part = p.ln_part + static_cast<size_t>(p.ln_epoch & 1u) * p.ln_region +
+                                   (static_cast<size_t>(m_blk) * GEMM_BM + r) * n_tiles;
+  const uint32_t tag = ((p.ln_epoch >> 1) & 1u) << 31;
+  float pm[10], pq[10];           // n_tiles <= 10 (checked on the host)
+  mu = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 10; ++j) {
+    if (j < n_tiles) {
+      unsigned long long w = ld_relaxed_gpu_u64(part + j);
+      uint32_t spins = 0;
+      while ((static_cast<uint32_t>(w >> 32) & 0x80000000u) != tag) {
+        if (++spins > (1u << 24)) __trap();   // a sibling CTA never arrived: fail loudly instead of hanging
+        w = ld_relaxed_gpu_u64(part + j);
+      }
+      pm[j] = __uint_as_float(static_cast<uint32_t>(w));
+      pq[j] = __uint_as_float(static_cast<uint32_t>(w >> 32) & 0x7fffffffu);
+      mu += pm[j];
+    }
+  }
+  mu /= static_cast<float>(n_tiles);
+  float var = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 10; ++j) {
+    if (j < n_tiles) {
+      const float dm = pm[j] - mu;
+      var += pq[j] + static_cast<float>(BN) * dm * dm;
+    }
+  }
+  rstd = rsqrtf(var / static_cast<float>(p.N) + p.ln_eps);
+}
+
 // CG = 1: one CTA per 128 x BN tile. CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile —
 // each CTA stages its own 128 A rows and half of the B tile, the leader CTA issues M=256 MMAs that read both halves,
 // so per-SM shared-memory traffic per MAC drops by a third (1-CTA 128x256 tiles are smem-bandwidth bound:
@@ -113,7 +199,7 @@ template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tma_ln, const GemmParams p) {
   constexpr int STAGES = gemm_num_stages(BN, EPI, CG);
   constexpr int A_BYTES = GEMM_BM * 128;
   constexpr int B_BYTES = BN * 128 / CG;
@@ -124,6 +210,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   constexpr bool STAGED = gemm_epi_staged(EPI);
   constexpr int CHUNK = (gemm_epi_adds_tile(EPI)) ? 32 : 64;     // columns per 128-byte staging row
   constexpr int GROUPS = gemm_epi_groups(EPI);                // epilogue warpgroups
+  constexpr bool LN = gemm_epi_ln(EPI);                       // fused LayerNorm of the updated residual rows
+  constexpr int RES_SLOTS = gemm_res_slots(BN, EPI, CG);
+  constexpr bool LN_SPLIT = gemm_ln_split(EPI);               // two epilogue warpgroups on alternating tiles
+  constexpr int TG = LN_SPLIT ? 2 : 1;                        // tile groups (epilogue warpgroup + ring + producer)
+  static_assert(RES_SLOTS >= 2, "residual ring too small");
+  static_assert(!LN || BN % 64 == 0, "the fused LayerNorm stores 64-column bf16 boxes");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
   static_assert(!STAGED || BN % CHUNK == 0, "staged epilogue needs BN to be a multiple of the chunk width");
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
@@ -132,15 +224,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // staging boxes of [128 rows x 128 B]: one per epilogue group (bf16), or the in-place residual ring (fp32)
   uint8_t* s_out = smem + STAGES * STAGE_BYTES;
+  constexpr int RING_BYTES = RES_SLOTS * GEMM_STAGING_BYTES;  // per tile group
+  float* s_affine = reinterpret_cast<float*>(s_out + TG * RING_BYTES);   // LN only, per tile group: gamma[BN] beta[BN]
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
   __shared__ uint64_t tfull_bar[2];
   __shared__ uint64_t tempty_bar[2];
-  __shared__ uint64_t res_full[GEMM_RES_SLOTS];
-  __shared__ uint64_t res_empty[GEMM_RES_SLOTS];
+  __shared__ uint64_t res_full[2][GEMM_RES_SLOTS];
+  __shared__ uint64_t res_empty[2][GEMM_RES_SLOTS];
   __shared__ uint32_t tmem_slot;
   constexpr int BIAS_PER_GROUP = (BN / CHUNK + GROUPS - 1) / GROUPS * CHUNK;   // columns a group's chunks cover
-  __shared__ __align__(16) float s_bias[GROUPS][STAGED ? BIAS_PER_GROUP : 1];
+  __shared__ __align__(16) float s_bias[LN_SPLIT ? 2 : GROUPS][STAGED ? BIAS_PER_GROUP : 1];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -161,14 +255,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_init(&tempty_bar[s], 4 * GROUPS * CG);   // the leader's barrier also collects the peer's epilogue warps
     }
     for (int s = 0; s < GEMM_RES_SLOTS; ++s) {
-      mbar_init(&res_full[s], 1);
-      mbar_init(&res_empty[s], 1);
+      mbar_init(&res_full[0][s], 1);
+      mbar_init(&res_empty[0][s], 1);
+      mbar_init(&res_full[1][s], 1);
+      mbar_init(&res_empty[1][s], 1);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     if (STAGED) tma_prefetch_desc(&tma_out);
     if (gemm_epi_adds_tile(EPI)) tma_prefetch_desc(&tma_aux);
+    if (LN) tma_prefetch_desc(&tma_ln);
   }
   if (warp == 1) {
     if constexpr (CG == 2) tmem_alloc_pair(&tmem_slot, TMEM_COLS);
@@ -242,67 +339,224 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (gemm_epi_adds_tile(EPI) && warp == 6) {
-    // residual producer: chunk c of tile (m_blk, n_blk) = fp32 [128 rows x 32 cols] -> ring slot (in-place staging)
+  } else if (gemm_epi_adds_tile(EPI) && (warp == 6 || (LN_SPLIT && warp == 11))) {
+    // residual producer of tile group tg: chunk c of tile (m_blk, n_blk) = fp32 [128 rows x 32 cols] -> ring slot
+    // (in-place staging)
     if (lane == 0) {
+      const int tg = warp == 11 ? 1 : 0;
+      uint8_t* ring = s_out + tg * RING_BYTES;
       uint32_t seq = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      for (int tile = tile0 + tg * tile_step; tile < num_tiles; tile += tile_step * TG) {
         const int m_blk = (tile / n_tiles) * CG + cta_rank;
         const int n_blk = tile % n_tiles;
         for (int c = 0; c < BN / 32; ++c, ++seq) {
-          const uint32_t slot = seq % GEMM_RES_SLOTS;
-          mbar_wait(&res_empty[slot], ((seq / GEMM_RES_SLOTS) & 1) ^ 1);
-          mbar_arrive_expect_tx(&res_full[slot], GEMM_STAGING_BYTES);
-          if constexpr (EPI == EPI_POSTMA_F32) {
+          const uint32_t slot = seq % RES_SLOTS;
+          mbar_wait(&res_empty[tg][slot], ((seq / RES_SLOTS) & 1) ^ 1);
+          mbar_arrive_expect_tx(&res_full[tg][slot], GEMM_STAGING_BYTES);
+          if constexpr (gemm_epi_pos(EPI)) {
             // positional table rows (token = row % period): two 64-row boxes, each inside one period (period % 64 == 0)
             const int t0 = (m_blk * GEMM_BM) % p.period, t1 = (m_blk * GEMM_BM + 64) % p.period;
-            tma_load_2d(s_out + slot * GEMM_STAGING_BYTES, &tma_aux, &res_full[slot], n_blk * BN + c * 32, t0);
-            tma_load_2d(s_out + slot * GEMM_STAGING_BYTES + 64 * 128, &tma_aux, &res_full[slot], n_blk * BN + c * 32,
-                        t1);
+            tma_load_2d(ring + slot * GEMM_STAGING_BYTES, &tma_aux, &res_full[tg][slot], n_blk * BN + c * 32, t0);
+            tma_load_2d(ring + slot * GEMM_STAGING_BYTES + 64 * 128, &tma_aux, &res_full[tg][slot],
+                        n_blk * BN + c * 32, t1);
           } else {
-            tma_load_2d(s_out + slot * GEMM_STAGING_BYTES, &tma_aux, &res_full[slot], n_blk * BN + c * 32,
+            tma_load_2d(ring + slot * GEMM_STAGING_BYTES, &tma_aux, &res_full[tg][slot], n_blk * BN + c * 32,
                         m_blk * GEMM_BM);
+          }
+        }
+        if constexpr (LN) {
+          // the normalised bf16 boxes of the tile go through the same ring: grant empty slots, nothing to load
+          for (int c = 0; c < BN / 64; ++c, ++seq) {
+            const uint32_t slot = seq % RES_SLOTS;
+            mbar_wait(&res_empty[tg][slot], ((seq / RES_SLOTS) & 1) ^ 1);
+            mbar_arrive(&res_full[tg][slot]);
           }
         }
       }
     }
   } else {
     const int quad = warp & 3;             // TMEM lane quadrant this warp may read
-    const int grp = (warp - 2) >> 2;       // epilogue warpgroup
-    const int etid = threadIdx.x - 64 - 128 * grp;   // 0..127 inside the warpgroup
+    // epilogue warpgroup: bf16 epilogues split the column chunks of every tile between two groups (cgrp), the
+    // short-K LayerNorm epilogue gives every other tile to each of its two groups
+    const int grp = LN_SPLIT ? (warp >= 7 ? 1 : 0) : ((warp - 2) >> 2);
+    const int cgrp = LN_SPLIT ? 0 : grp;
+    const int etid = LN_SPLIT ? static_cast<int>(threadIdx.x) - (grp ? 224 : 64)
+                              : static_cast<int>(threadIdx.x) - 64 - 128 * grp;   // 0..127 inside the warpgroup
+    uint8_t* ring = s_out + (LN_SPLIT ? grp : 0) * RING_BYTES;
+    uint64_t* rfull = res_full[LN_SPLIT ? grp : 0];
+    uint64_t* rempty = res_empty[LN_SPLIT ? grp : 0];
+    float* s_gamma = s_affine + (LN_SPLIT ? grp : 0) * 2 * BN;
+    float* s_beta = s_gamma + BN;
     const int r = quad * 32 + lane;        // row inside the tile == TMEM lane
     const int bar_id = 1 + grp;            // named barrier of this warpgroup
     auto arrive_tempty = [&](int a) {      // TMEM buffer drained: tell the MMA issuer (in the pair's leader CTA)
       if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[a]), 0));
       else mbar_arrive(&tempty_bar[a]);
     };
-    int acc = 0;
+    int acc = LN_SPLIT ? grp : 0;          // tile group g always finds its tiles in TMEM buffer g
     uint32_t acc_phase = 0;
     uint32_t chunk_seq = 0;                // running chunk counter of this group: staging buffer = chunk_seq & 1
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+    int const_n_blk = -1;                  // n-tile whose bias / gamma / beta columns are in shared memory
+    for (int tile = tile0 + (LN_SPLIT ? grp : 0) * tile_step; tile < num_tiles; tile += tile_step * TG) {
       const int m_blk = (tile / n_tiles) * CG + cta_rank;
       const int n_blk = tile % n_tiles;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
 
       if constexpr (STAGED) {
         constexpr int NCHUNK = BN / CHUNK;
-        // bias of this n-tile -> smem (all readers of the previous tile's bias are past its last barrier)
+        // bias (and LayerNorm affine) columns of this n-tile -> smem, only when the n-tile changes (it never does when
+        // the grid is a whole number of row blocks). All readers of the previous values are past a barrier.
         // (each group keeps only the columns of its own chunks: local chunk lc <-> tile chunk lc*GROUPS + grp)
-        for (int i = etid; i < BIAS_PER_GROUP; i += 128) {
-          const int col = n_blk * BN + ((i / CHUNK) * GROUPS + grp) * CHUNK + (i % CHUNK);
-          s_bias[grp][i] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+        if (n_blk != const_n_blk) {
+          const_n_blk = n_blk;
+          for (int i = etid; i < BIAS_PER_GROUP; i += 128) {
+            const int col = n_blk * BN + ((i / CHUNK) * GROUPS + cgrp) * CHUNK + (i % CHUNK);
+            s_bias[grp][i] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+          }
+          if constexpr (LN) {
+            for (int i = etid; i < BN; i += 128) {
+              s_gamma[i] = __ldg(p.ln_gamma + n_blk * BN + i);
+              s_beta[i] = __ldg(p.ln_beta + n_blk * BN + i);
+            }
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // constants visible to the whole group
         }
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-        if (grp >= NCHUNK) {                // narrow tile: this group has no chunk, just release TMEM
+        if (cgrp >= NCHUNK) {               // narrow tile: this group has no chunk, just release TMEM
           tc_fence_before();
           __syncwarp();
           if (lane == 0) arrive_tempty(acc);
         }
+        if constexpr (LN) {
+          // ---- pass 1: x' = residual + acc + bias. Stored as fp32 through the in-place ring exactly like
+          // EPI_RESID_F32, written back into the TMEM accumulator for pass 2, and reduced to a running (mean, M2)
+          // of this row over the tile's BN columns (two-pass inside a 32-column chunk, Chan's update across chunks).
+          float mean = 0.0f, m2 = 0.0f;
+          // one 32-column chunk (its accumulator values already in v)
+          auto pass1_chunk = [&](uint32_t(&v)[32], int c) {
+            const uint32_t buf = chunk_seq % RES_SLOTS;
+            const uint32_t srow = smem_u32(ring) + buf * GEMM_STAGING_BYTES + r * 128;
+            const float4* bias4 = reinterpret_cast<const float4*>(&s_bias[grp][c * 32]);
+            mbar_wait(&rfull[buf], (chunk_seq / RES_SLOTS) & 1);
+            float2 s0 = make_float2(0.0f, 0.0f), s1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const uint32_t pu = srow + ((u ^ (r & 7)) * 16);
+              const float4 x = lds_f4(pu);
+              const float4 bb = bias4[u];
+              // residual + (acc + bias), as the unfused epilogue; packed fp32 adds are IEEE per lane
+              const float2 lo = __fadd2_rn(make_float2(x.x, x.y),
+                                           __fadd2_rn(make_float2(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1])),
+                                                      make_float2(bb.x, bb.y)));
+              const float2 hi = __fadd2_rn(make_float2(x.z, x.w),
+                                           __fadd2_rn(make_float2(__uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3])),
+                                                      make_float2(bb.z, bb.w)));
+              sts_f4(pu, make_float4(lo.x, lo.y, hi.x, hi.y));
+              v[4 * u + 0] = __float_as_uint(lo.x);
+              v[4 * u + 1] = __float_as_uint(lo.y);
+              v[4 * u + 2] = __float_as_uint(hi.x);
+              v[4 * u + 3] = __float_as_uint(hi.y);
+              s0 = __fadd2_rn(s0, lo);
+              s1 = __fadd2_rn(s1, hi);
+            }
+            tmem_st_32x32b_x32(t_row + c * 32, v);
+            // the slot is complete: publish it to the async proxy and let thread 0 store it while the others go on
+            fence_proxy_async_smem();
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (etid == 0) {
+              tma_store_2d(&tma_out, ring + buf * GEMM_STAGING_BYTES, n_blk * BN + c * 32, m_blk * GEMM_BM);
+              tma_store_commit();
+              if (chunk_seq > 0) {
+                tma_store_wait_read<1>();
+                mbar_arrive(&rempty[(chunk_seq - 1) % RES_SLOTS]);
+              }
+            }
+            const float2 ss = __fadd2_rn(s0, s1);
+            const float mc = (ss.x + ss.y) * (1.0f / 32.0f);
+            const float2 nmc = make_float2(-mc, -mc);
+            float2 q0 = make_float2(0.0f, 0.0f), q1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float2 d0 = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), nmc);
+              const float2 d1 = __fadd2_rn(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), nmc);
+              q0 = __ffma2_rn(d0, d0, q0);
+              q1 = __ffma2_rn(d1, d1, q1);
+            }
+            const float2 qq = __fadd2_rn(q0, q1);
+            const float delta = mc - mean;
+            const float wgt = 1.0f / static_cast<float>(c + 1);          // n_b / (n_a + n_b), n_a = 32 c, n_b = 32
+            mean = fmaf(delta, wgt, mean);
+            m2 += (qq.x + qq.y) + delta * delta * (32.0f * static_cast<float>(c) * wgt);
+            ++chunk_seq;
+          };
+          {
+            // two register sets: the TMEM load of the next chunk is in flight while this one is processed
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32b_x32(t_row, va);
 #pragma unroll 1
-        for (int c = grp; c < NCHUNK; c += GROUPS, ++chunk_seq) {
+            for (int c = 0; c < NCHUNK; c += 2) {
+              tmem_ld_wait();
+              tmem_ld_32x32b_x32(t_row + (c + 1) * 32, vb);
+              pass1_chunk(va, c);
+              tmem_ld_wait();
+              if (c + 2 < NCHUNK) tmem_ld_32x32b_x32(t_row + (c + 2) * 32, va);
+              pass1_chunk(vb, c + 1);
+            }
+          }
+          tmem_st_wait();
+          // ---- publish (mean, M2) for the CTAs that own the other n-tiles of this row block (and for pass 2)
+          ln_publish_stats(p, m_blk, r, n_tiles, n_blk, mean, m2);
+          float mu, rstd;
+          ln_row_stats<BN>(p, m_blk, r, n_tiles, mu, rstd);
+          const float nmr = -mu * rstd;
+          // ---- pass 2: normalise the rows kept in TMEM, bf16 boxes of 64 columns through the same ring
+#pragma unroll 1
+          for (int c = 0; c < BN / 64; ++c, ++chunk_seq) {
+            const uint32_t buf = chunk_seq % RES_SLOTS;
+            uint32_t v[64];
+            tmem_ld_32x32b_x32(t_row + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            tmem_ld_32x32b_x32(t_row + c * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+            tmem_ld_wait();
+            if (c == BN / 64 - 1) {               // the tile has left TMEM: hand the buffer back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) arrive_tempty(acc);
+            }
+            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c * 64);
+            const float4* b4 = reinterpret_cast<const float4*>(s_beta + c * 64);
+            const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(nmr, nmr);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float4 gg = g4[j], bb = b4[j];
+              const float2 y0 = __ffma2_rn(
+                  __ffma2_rn(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), rs2, nm2),
+                  make_float2(gg.x, gg.y), make_float2(bb.x, bb.y));
+              const float2 y1 = __ffma2_rn(
+                  __ffma2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), rs2, nm2),
+                  make_float2(gg.z, gg.w), make_float2(bb.z, bb.w));
+              v[2 * j] = pack_bf16x2(y0.x, y0.y);
+              v[2 * j + 1] = pack_bf16x2(y1.x, y1.y);
+            }
+            const uint32_t srow = smem_u32(ring) + buf * GEMM_STAGING_BYTES + r * 128;
+            mbar_wait(&rfull[buf], (chunk_seq / RES_SLOTS) & 1);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              sts_u4(srow + ((u ^ (r & 7)) * 16), v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+            fence_proxy_async_smem();
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (etid == 0) {
+              tma_store_2d(&tma_ln, ring + buf * GEMM_STAGING_BYTES, n_blk * BN + c * 64, m_blk * GEMM_BM);
+              tma_store_commit();
+              tma_store_wait_read<1>();
+              mbar_arrive(&rempty[(chunk_seq - 1) % RES_SLOTS]);
+            }
+          }
+        } else {
+#pragma unroll 1
+        for (int c = cgrp; c < NCHUNK; c += GROUPS, ++chunk_seq) {
           // staging slot: bf16 epilogues own one box per group; the residual epilogue walks the in-place ring
-          const uint32_t buf = gemm_epi_adds_tile(EPI) ? (chunk_seq % GEMM_RES_SLOTS) : static_cast<uint32_t>(grp);
+          const uint32_t buf = gemm_epi_adds_tile(EPI) ? (chunk_seq % RES_SLOTS) : static_cast<uint32_t>(grp);
           uint32_t v[CHUNK];
           if constexpr (CHUNK == 64) {
             tmem_ld_32x32b_x32(t_row + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -316,21 +570,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             __syncwarp();
             if (lane == 0) arrive_tempty(acc);
           }
-          uint8_t* srow = s_out + buf * GEMM_STAGING_BYTES + r * 128;
+          const uint32_t srow = smem_u32(ring) + buf * GEMM_STAGING_BYTES + r * 128;
           const float* bias_c = &s_bias[grp][(c / GROUPS) * CHUNK];
           if constexpr (gemm_epi_adds_tile(EPI)) {
             // residual chunk landed in the slot (TMA, issued by warp 6 well ahead); update it in place: every thread
             // reads and writes only its own 128-byte row, so no barrier is needed before the math
-            mbar_wait(&res_full[buf], (chunk_seq / GEMM_RES_SLOTS) & 1);
+            mbar_wait(&rfull[buf], (chunk_seq / RES_SLOTS) & 1);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              const int pu = (u ^ (r & 7)) * 16;
-              float4 x = *reinterpret_cast<const float4*>(srow + pu);
+              const uint32_t pu = srow + ((u ^ (r & 7)) * 16);
+              float4 x = lds_f4(pu);
               x.x += __uint_as_float(v[4 * u + 0]) + bias_c[4 * u + 0];
               x.y += __uint_as_float(v[4 * u + 1]) + bias_c[4 * u + 1];
               x.z += __uint_as_float(v[4 * u + 2]) + bias_c[4 * u + 2];
               x.w += __uint_as_float(v[4 * u + 3]) + bias_c[4 * u + 3];
-              *reinterpret_cast<float4*>(srow + pu) = x;
+              sts_f4(pu, x);
             }
           } else {
             // all the math first, into packed registers (overwriting v) ...
@@ -347,22 +601,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-              *reinterpret_cast<uint4*>(srow + ((u ^ (r & 7)) * 16)) =
-                  make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+              sts_u4(srow + ((u ^ (r & 7)) * 16), v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
           }
           fence_proxy_async_smem();         // generic-proxy smem writes -> visible to the TMA store
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           if (etid == 0) {
-            tma_store_2d(&tma_out, s_out + buf * GEMM_STAGING_BYTES, n_blk * BN + c * CHUNK, m_blk * GEMM_BM);
+            tma_store_2d(&tma_out, ring + buf * GEMM_STAGING_BYTES, n_blk * BN + c * CHUNK, m_blk * GEMM_BM);
             tma_store_commit();
             if constexpr (gemm_epi_adds_tile(EPI)) {
               // hand the previous chunk's slot back to the residual producer once its store has read it
               if (chunk_seq > 0) {
                 tma_store_wait_read<1>();
-                mbar_arrive(&res_empty[(chunk_seq - 1) % GEMM_RES_SLOTS]);
+                mbar_arrive(&rempty[(chunk_seq - 1) % RES_SLOTS]);
               }
             }
           }
+        }
         }
       } else {
         mbar_wait(&tfull_bar[acc], acc_phase);
@@ -412,8 +666,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         __syncwarp();
         if (lane == 0) arrive_tempty(acc);
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if constexpr (LN_SPLIT) {
+        acc_phase ^= 1;                     // the same buffer again, two tiles later
+      } else {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
     }
     if (STAGED && etid == 0) tma_store_wait_all<0>();   // all output bytes committed before the CTA exits
   }

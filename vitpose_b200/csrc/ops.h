@@ -10,7 +10,7 @@ namespace vpb {
 struct GemmParams;
 
 // ---- GEMM (gemm.cu) ----
-struct GemmMaps { CUtensorMap a, b, out, aux; };
+struct GemmMaps { CUtensorMap a, b, out, aux, ln; };
 int gemm_pick_bn(int N, int epilogue);
 int gemm_pick_cg(int M, int bn, int epilogue, int K);
 int make_gemm_maps(GemmMaps* maps, const void* A, const void* B, int M, int N, int K, int lda, int ldb, int bn,
@@ -19,6 +19,16 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue,
                 cudaStream_t stream);
 int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, void* out, int ldo,
               const float* aux, int period, int max_ctas, cudaStream_t stream);
+// Residual / patch-embed GEMM (epilogue EPI_RESID_F32 or EPI_POS_F32, out fp32 [M, N]) that also writes
+// xn = LayerNorm(out) * gamma + beta as bf16 [M, N] from the same kernel. `scratch` (gemm_ln_scratch_bytes(M, N)
+// bytes, 16-byte aligned) holds the per-row partial statistics the column tiles exchange; gemm_ln_scratch_init
+// prepares it for a sequence of stream-ordered calls numbered epoch = 1, 2, ... (same M, N).
+// Falls back to GEMM + layernorm_bf16 (two kernels) for shapes the fused kernel does not cover.
+size_t gemm_ln_scratch_bytes(int M, int N);
+int gemm_ln_scratch_init(void* scratch, int M, int N, cudaStream_t stream);
+int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, float* out,
+                 const float* aux, int period, const float* gamma, const float* beta, float eps, void* xn,
+                 void* scratch, unsigned epoch, int max_ctas, cudaStream_t stream);
 
 // ---- elementwise / normalisation (elementwise.cu) ----
 // img fp32 [n,3,H,W] -> patches bf16 [(flip?2n:n) * Hp*Wp, 768]; rows [n*Hp*Wp, 2n*Hp*Wp) hold the

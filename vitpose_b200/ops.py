@@ -38,6 +38,23 @@ def gemm(a, b, epilogue, bias=None, out=None, aux=None, period=0, max_ctas=0):
     return out
 
 
+def gemm_layernorm(a, b, epilogue, bias, aux, gamma, beta, eps=1e-6, period=0, out=None):
+    """Residual-stream GEMM + the LayerNorm that follows it, one kernel: returns (out fp32 [M,N], xn bf16 [M,N]).
+    `out` may be the residual tensor itself (in-place update, as the forward pass does)."""
+    _need(a, BF16, 'a'); _need(b, BF16, 'b'); _need(aux, torch.float32, 'aux')
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K and epilogue in (_lib.EPI_RESID_F32, _lib.EPI_POS_F32)
+    out = torch.empty(M, N, device=a.device, dtype=torch.float32) if out is None else out
+    xn = torch.empty(M, N, device=a.device, dtype=BF16)
+    nbytes = lib().vpb_gemm_layernorm_scratch_bytes(M, N)
+    scratch = torch.empty(nbytes, device=a.device, dtype=torch.uint8)
+    check(lib().vpb_gemm_bf16_layernorm(ptr(a), ptr(b), M, N, K, epilogue, ptr(bias), ptr(out), ptr(aux), period,
+                                        ptr(gamma), ptr(beta), float(eps), ptr(xn), ptr(scratch), nbytes,
+                                        stream_ptr()), 'vpb_gemm_bf16_layernorm')
+    return out, xn
+
+
 def layernorm(x, gamma, beta, eps=1e-6, out=None):
     _need(x, torch.float32, 'x')
     M, D = x.shape
