@@ -163,6 +163,51 @@ int vpb_conv3x3_nchw(const void* in, const void* w9, const float* bias, float* o
 int vpb_relu_upsample_nhwc(const void* in, void* out, int n, int h, int w, int C, int factor, void* stream);
 int vpb_tokens_to_nchw_f32(const void* tokens, float* out, int n, int T, int D, void* stream);
 
+/* ---- backward pass of the training step (`*_bwd`) ------------------------------------
+ * The reference trains through torch.autograd (mmcv runner: loss.backward(), optimizer.step()); these are the
+ * operators that replace the autograd nodes of the path's modules. The tensor-core work of the backward pass is
+ * vpb_gemm_bf16 itself on transposed operands:
+ *   dgrad  dX[M,K] = dY[M,N] . W[N,K]   = vpb_gemm_bf16(A = dY, B = W^T [K,N], VPB_EPI_BIAS_BF16 / _RESID_F32)
+ *   wgrad  dW[N,K] += dY^T . X          = vpb_gemm_bf16(A = dY^T [N,M], B = X^T [K,M], VPB_EPI_RESID_F32, aux = out = dW)
+ * All matrices row-major; bf16 unless stated; gradients of parameters are fp32 and ACCUMULATED into their buffers. */
+int vpb_transpose_bf16(const void* in, void* out, int R, int C, int batch, void* stream);   /* out[b][C,R] = in[b][R,C]^T */
+int vpb_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
+/* out[C] += sum over the R rows of in[R,C] (bf16, or fp32 when is_f32): bias / pos-embed gradients */
+int vpb_colsum_accumulate(const void* in, int is_f32, int R, int C, float* out, void* stream);
+/* nn.GELU (exact erf, vit.py:71-76): out = gelu(pre); dpre = dh * gelu'(pre) */
+int vpb_gelu_fwd_bf16(const void* pre, void* out, long long n, void* stream);
+int vpb_gelu_bwd_bf16(const void* pre, const void* dh, void* dpre, long long n, void* stream);
+/* nn.LayerNorm backward (vit.py:125,133,328): x fp32 [M,D] (the saved input), dy bf16 [M,D];
+ * dx_accum fp32 [M,D] += dL/dx (the residual stream's gradient), dgamma / dbeta fp32 [D] += */
+int vpb_layernorm_bwd(const float* x, const float* gamma, const void* dy, float* dx_accum, float* dgamma,
+                      float* dbeta, int M, int D, float eps, void* stream);
+/* Attention.forward backward (vit.py:99-115): qkv [n,T,3*heads*hd] and out [n,T,heads*hd] saved by the forward
+ * pass, dout = dL/dout -> dqkv [n,T,3*heads*hd]. T = 192, head_dim = 64 (ViTPose-B, the training configuration). */
+int vpb_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, int n, int T, int heads,
+                      int head_dim, float scale, void* stream);
+/* ConvTranspose2d(k4,s2,p1,bias=False) without BatchNorm / ReLU (training forward; ones / zeros: fp32 [cout]) */
+int vpb_deconv4x4s2_raw(const void* in, const void* wphase, void* out, int n, int h, int w, int cin, int cout,
+                        const float* ones, const float* zeros, void* stream);
+/* nn.BatchNorm2d in training mode on NHWC rows [rows, C] (simple_head.py:324-333): batch mean / rstd (biased
+ * variance), running statistics updated with `momentum` and the unbiased variance (NULL to skip);
+ * scratch = 2*C floats. Then act = relu(bn(raw)), and its backward (dgamma / dbeta fp32 [C] +=). */
+int vpb_bn_train_stats(const void* raw, long long rows, int C, float eps, float momentum, float* sum_sumsq_scratch,
+                       float* mean, float* rstd, float* running_mean, float* running_var, void* stream);
+int vpb_bn_relu_fwd(const void* raw, void* act, const float* mean, const float* rstd, const float* gamma,
+                    const float* beta, long long rows, int C, void* stream);
+int vpb_bn_relu_bwd(const void* raw, const void* dact, void* draw, const float* mean, const float* rstd,
+                    const float* gamma, const float* beta, float* dgamma, float* dbeta, long long rows, int C,
+                    void* stream);
+/* dL/dheatmaps fp32 [n,K,P] -> bf16 rows [n*P, Kp] (zero padded to Kp >= K): operand of the final conv's GEMMs */
+int vpb_nchw_f32_to_rows_bf16(const float* in, void* out, int n, int K, int P, int Kp, void* stream);
+/* Operand gathers for the backward of the 4-phase transposed convolution (layouts in csrc/train_bwd.cu):
+ *   gather_x : x [n,h,w,cin]   -> [4 phases][n*h*w, 4*cin]   (wgrad: dWp[ph] = phase_dy[ph]^T . gather_x[ph])
+ *   phase_dy : dy [n,2h,2w,cout] -> [4 phases][n*h*w, cout]
+ *   gather_dy: dy [n,2h,2w,cout] -> [n*h*w, 16*cout]          (dgrad: dx = gather_dy . W2g^T) */
+int vpb_deconv_gather_x(const void* x, void* out, int n, int h, int w, int cin, void* stream);
+int vpb_deconv_gather_dy(const void* dy, void* out, int n, int h, int w, int cout, void* stream);
+int vpb_deconv_phase_dy(const void* dy, void* out, int n, int h, int w, int cout, void* stream);
+
 /* ---- preprocessing ----
  * TopDownAffine + ToTensor + NormalizeTensor for n boxes (mmpose/datasets/pipelines/top_down_transform.py:295-364,
  * shared_transform.py:21-65): out[i] = ((warpAffine_u8(src[i], M_i, (out_w,out_h), INTER_LINEAR) / 255) - mean) / std

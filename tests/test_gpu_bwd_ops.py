@@ -1,0 +1,160 @@
+"""Backward-pass operators (-m gpu) against torch.autograd of the same op in fp32 (on bf16-rounded operands).
+These are the autograd nodes of the training-step configuration: Linear dgrad / wgrad as
+GEMMs on transposed operands, GELU, LayerNorm, attention, BatchNorm(train)+ReLU and the transposed convolution."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF16 = torch.bfloat16
+
+
+def _dev():
+    return torch.device('cuda:0')
+
+
+def _rand(shape, seed, scale=1.0, dtype=BF16):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(_dev())
+
+
+def _close(name, got, ref, rel):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-12
+    rms = ((got - ref).pow(2).mean().sqrt() / (ref.pow(2).mean().sqrt() + 1e-12)).item()
+    assert err <= rel * scale and rms <= rel, f'{name}: max err {err:.4g} (ref absmax {scale:.4g}), rel rms {rms:.4g}'
+
+
+def test_transpose_and_cast():
+    from vitpose_b200 import ops
+    x = _rand((3, 200, 136), 1)
+    out = ops.transpose(x, batch=3)
+    assert torch.equal(out, x.transpose(1, 2).contiguous())
+    y = _rand((770, 64), 2)
+    assert torch.equal(ops.transpose(y), y.t().contiguous())
+    f = _rand((1000, 12), 3, dtype=torch.float32)
+    assert torch.equal(ops.cast_bf16(f), f.to(BF16))
+
+
+@pytest.mark.parametrize('R,C,f32', [(12288, 768, False), (1000, 2304, False), (64, 36864, True), (577, 18, False)])
+def test_colsum(R, C, f32):
+    from vitpose_b200 import ops
+    x = _rand((R, C), 4, dtype=torch.float32 if f32 else BF16)
+    out = torch.ones(C, device=_dev())
+    ops.colsum_accumulate(x, out)
+    _close('colsum', out, 1 + x.float().sum(0), 2e-4)
+
+
+def test_gelu_fwd_bwd():
+    from vitpose_b200 import ops
+    pre = _rand((192 * 4, 1024), 5, 1.5)
+    dh = _rand((192 * 4, 1024), 6)
+    x = pre.float().requires_grad_(True)
+    y = F.gelu(x)
+    y.backward(dh.float())
+    _close('gelu fwd', ops.gelu_fwd(pre), y.detach(), 1e-2)
+    _close('gelu bwd', ops.gelu_bwd(pre, dh), x.grad, 1e-2)
+
+
+@pytest.mark.parametrize('D', [128, 768])
+def test_layernorm_bwd(D):
+    from vitpose_b200 import ops
+    M = 192 * 7 + 3
+    x = _rand((M, D), 7, 2.0, torch.float32) + 0.3
+    gamma, dy = _rand((D,), 8, dtype=torch.float32), _rand((M, D), 9)
+    dx0 = _rand((M, D), 10, dtype=torch.float32)
+    xr, gr, br = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), torch.zeros(D, device=_dev(), requires_grad=True)
+    F.layer_norm(xr, (D,), gr, br, 1e-6).backward(dy.float())
+    dx = dx0.clone()
+    dg, db = torch.zeros(D, device=_dev()), torch.zeros(D, device=_dev())
+    ops.layernorm_bwd(x, gamma, dy, dx, dg, db, 1e-6)
+    _close('ln dx', dx - dx0, xr.grad, 2e-3)
+    _close('ln dgamma', dg, gr.grad, 2e-3)
+    _close('ln dbeta', db, br.grad, 2e-3)
+
+
+@pytest.mark.parametrize('n,heads', [(2, 2), (3, 12)])
+def test_attention_bwd(n, heads):
+    from vitpose_b200 import ops
+    T, hd = 192, 64
+    D = heads * hd
+    qkv = _rand((n, T, 3 * D), 11, 1.0)
+    dout = _rand((n, T, D), 12, 1.0)
+    out = ops.attention(qkv, heads)
+    x = qkv.float().requires_grad_(True)
+    q, k, v = x.reshape(n, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    a = ((q * hd ** -0.5) @ k.transpose(-2, -1)).softmax(-1)
+    o = (a @ v).transpose(1, 2).reshape(n, T, D)
+    o.backward(dout.float())
+    _close('attention fwd', out, o.detach(), 2e-2)
+    dqkv = ops.attention_bwd(qkv, out, dout, heads)
+    g = x.grad.reshape(n, T, 3, D)
+    d = dqkv.reshape(n, T, 3, D)
+    for i, nm in enumerate('qkv'):
+        _close(f'attention d{nm}', d[:, :, i], g[:, :, i], 3e-2)
+
+
+def test_linear_dgrad_wgrad_as_gemms():
+    """dX = dY W and dW += dY^T X through the forward GEMM kernel on transposed operands."""
+    from vitpose_b200 import ops, _lib
+    M, N, K = 192 * 16, 768, 3072
+    x, w, dy = _rand((M, K), 13), _rand((N, K), 14, 1 / math.sqrt(K)), _rand((M, N), 15)
+    dx = ops.gemm(dy, ops.transpose(w), _lib.EPI_BIAS_BF16)
+    _close('dgrad', dx, dy.float() @ w.float(), 1e-2)
+    dw = torch.ones(N, K, device=_dev())
+    ops.gemm(ops.transpose(dy), ops.transpose(x), _lib.EPI_RESID_F32, out=dw, aux=dw)
+    _close('wgrad', dw, 1 + dy.float().t() @ x.float(), 2e-3)
+
+
+def test_bn_train_relu_fwd_bwd():
+    from vitpose_b200 import ops
+    n, h, w, C = 4, 32, 24, 256
+    raw = _rand((n, h, w, C), 16, 2.0) + 0.5
+    dact = _rand((n, h, w, C), 17)
+    gamma, beta = _rand((C,), 18, dtype=torch.float32), _rand((C,), 19, 0.5, torch.float32)
+    rm, rv = torch.zeros(C, device=_dev()), torch.ones(C, device=_dev())
+    x = raw.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    g, b = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    y = F.relu(F.batch_norm(x, rm_ref, rv_ref, g, b, True, 0.1, 1e-5))
+    y.backward(dact.float().permute(0, 3, 1, 2))
+    mean, rstd = ops.bn_train_stats(raw, 1e-5, 0.1, rm, rv)
+    _close('bn running_mean', rm, rm_ref, 1e-3)
+    _close('bn running_var', rv, rv_ref, 1e-3)
+    act = ops.bn_relu_fwd(raw, mean, rstd, gamma, beta)
+    _close('bn+relu fwd', act, y.detach().permute(0, 2, 3, 1), 1e-2)
+    dg, db = torch.zeros(C, device=_dev()), torch.zeros(C, device=_dev())
+    draw = ops.bn_relu_bwd(raw, dact, mean, rstd, gamma, beta, dg, db)
+    _close('bn dgamma', dg, g.grad, 5e-3)
+    _close('bn dbeta', db, b.grad, 5e-3)
+    _close('bn+relu bwd', draw, x.grad.permute(0, 2, 3, 1), 2e-2)
+
+
+@pytest.mark.parametrize('n,h,w,cin,cout', [(2, 16, 12, 128, 64), (3, 32, 24, 256, 256)])
+def test_deconv_fwd_bwd(n, h, w, cin, cout):
+    """ConvTranspose2d(k4,s2,p1): raw forward, dgrad and wgrad (in the packed 4-phase layout) as gathers + GEMMs."""
+    from vitpose_b200 import ops, _lib
+    from vitpose_b200.engine import pack_deconv_weight, pack_deconv_weight_dgrad
+    x = _rand((n, h, w, cin), 20)
+    wt = _rand((cin, cout, 4, 4), 21, 0.05)
+    dy = _rand((n, 2 * h, 2 * w, cout), 22)
+    xr, wr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True), wt.float().requires_grad_(True)
+    y = F.conv_transpose2d(xr, wr, None, stride=2, padding=1)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    wp = pack_deconv_weight(wt)
+    raw = ops.deconv4x4s2_raw(x, wp)
+    _close('deconv raw', raw, y.detach().permute(0, 2, 3, 1), 1e-2)
+    # dgrad: [pixels, 16*cout] x W2g[cin, 16*cout]^T
+    dx = ops.gemm(ops.deconv_gather_dy(dy), pack_deconv_weight_dgrad(wp), _lib.EPI_BIAS_BF16)
+    _close('deconv dgrad', dx.reshape(n, h, w, cin), xr.grad.permute(0, 2, 3, 1), 1e-2)
+    # wgrad per phase: dWp[ph] [cout, 4*cin] = phase_dy[ph]^T . gather_x[ph]
+    a = ops.transpose(ops.deconv_phase_dy(dy), batch=4)        # [4, cout, pixels]
+    b = ops.transpose(ops.deconv_gather_x(x), batch=4)         # [4, 4*cin, pixels]
+    dwp = torch.zeros(4, cout, 4 * cin, device=_dev())
+    for ph in range(4):
+        ops.gemm(a[ph], b[ph], _lib.EPI_RESID_F32, out=dwp[ph], aux=dwp[ph])
+    ref = pack_deconv_weight(wr.grad)          # same re-layout applied to the reference gradient (fp32 in, bf16 out)
+    _close('deconv wgrad', dwp, ref, 1e-2)

@@ -56,6 +56,27 @@ _SIGS = {
     'vpb_flip_back': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'vpb_transform_preds': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p]),
+    'vpb_transpose_bf16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'vpb_cast_f32_bf16': (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p]),
+    'vpb_colsum_accumulate': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'vpb_gelu_fwd_bf16': (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p]),
+    'vpb_gelu_bwd_bf16': (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p]),
+    'vpb_layernorm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+                                  c_void_p]),
+    'vpb_attention_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                  c_void_p]),
+    'vpb_deconv4x4s2_raw': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                    c_void_p, c_void_p]),
+    'vpb_bn_train_stats': (c_int, [c_void_p, ctypes.c_longlong, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p]),
+    'vpb_bn_relu_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int,
+                                c_void_p]),
+    'vpb_bn_relu_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, ctypes.c_longlong, c_int, c_void_p]),
+    'vpb_nchw_f32_to_rows_bf16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'vpb_deconv_gather_x': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'vpb_deconv_gather_dy': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'vpb_deconv_phase_dy': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'vpb_warp_affine_normalize': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                           ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p, c_void_p]),
     'vpb_joints_mse_loss': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,

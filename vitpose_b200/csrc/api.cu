@@ -302,6 +302,70 @@ int vpb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
                     as_stream(stream));
 }
 
+// ---- backward-pass operators of the training step ----
+int vpb_transpose_bf16(const void* in, void* out, int R, int C, int batch, void* stream) {
+  return transpose_bf16(in, out, R, C, batch, as_stream(stream));
+}
+int vpb_cast_f32_bf16(const float* in, void* out, long long n, void* stream) {
+  return cast_f32_bf16(in, out, n, as_stream(stream));
+}
+int vpb_colsum_accumulate(const void* in, int is_f32, int R, int C, float* out, void* stream) {
+  return colsum_accumulate(in, is_f32, R, C, out, as_stream(stream));
+}
+int vpb_gelu_fwd_bf16(const void* pre, void* out, long long n, void* stream) {
+  return gelu_fwd_bf16(pre, out, n, as_stream(stream));
+}
+int vpb_gelu_bwd_bf16(const void* pre, const void* dh, void* dpre, long long n, void* stream) {
+  return gelu_bwd_bf16(pre, dh, dpre, n, as_stream(stream));
+}
+int vpb_layernorm_bwd(const float* x, const float* gamma, const void* dy, float* dx_accum, float* dgamma,
+                      float* dbeta, int M, int D, float eps, void* stream) {
+  return layernorm_bwd(x, gamma, dy, dx_accum, dgamma, dbeta, M, D, eps, as_stream(stream));
+}
+int vpb_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, int n, int T, int heads,
+                      int head_dim, float scale, void* stream) {
+  return attention_bwd(qkv, out, dout, dqkv, n, T, heads, head_dim, scale, as_stream(stream));
+}
+int vpb_deconv4x4s2_raw(const void* in, const void* wphase, void* out, int n, int h, int w, int cin, int cout,
+                        const float* ones, const float* zeros, void* stream) {
+  return deconv4x4s2_affine(in, wphase, ones, zeros, out, n, h, w, cin, cout, 0, 0, as_stream(stream));
+}
+int vpb_bn_train_stats(const void* raw, long long rows, int C, float eps, float momentum, float* sum_sumsq_scratch,
+                       float* mean, float* rstd, float* running_mean, float* running_var, void* stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  VPB_REQUIRE(rows > 0 && rows < (1ll << 31) && C > 0, "bn_train_stats: bad shape");
+  VPB_CHECK_CUDA(cudaMemsetAsync(sum_sumsq_scratch, 0, sizeof(float) * 2 * C, stream));
+  if (int e = colsum_sq_accumulate(raw, static_cast<int>(rows), C, sum_sumsq_scratch, sum_sumsq_scratch + C, stream))
+    return e;
+  return bn_finalize(sum_sumsq_scratch, sum_sumsq_scratch + C, mean, rstd, running_mean, running_var, C, rows, eps,
+                     momentum, stream);
+}
+int vpb_bn_relu_fwd(const void* raw, void* act, const float* mean, const float* rstd, const float* gamma,
+                    const float* beta, long long rows, int C, void* stream) {
+  return bn_relu_fwd(raw, act, mean, rstd, gamma, beta, rows, C, as_stream(stream));
+}
+int vpb_bn_relu_bwd(const void* raw, const void* dact, void* draw, const float* mean, const float* rstd,
+                    const float* gamma, const float* beta, float* dgamma, float* dbeta, long long rows, int C,
+                    void* stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  VPB_REQUIRE(rows > 0 && rows < (1ll << 31), "bn_relu_bwd: bad shape");
+  if (int e = bn_relu_bwd_reduce(raw, dact, mean, rstd, gamma, beta, static_cast<int>(rows), C, dbeta, dgamma, stream))
+    return e;
+  return bn_relu_bwd(raw, dact, draw, mean, rstd, gamma, beta, dbeta, dgamma, rows, C, stream);
+}
+int vpb_nchw_f32_to_rows_bf16(const float* in, void* out, int n, int K, int P, int Kp, void* stream) {
+  return nchw_f32_to_rows_bf16(in, out, n, K, P, Kp, as_stream(stream));
+}
+int vpb_deconv_gather_x(const void* x, void* out, int n, int h, int w, int cin, void* stream) {
+  return deconv_gather_x(x, out, n, h, w, cin, as_stream(stream));
+}
+int vpb_deconv_gather_dy(const void* dy, void* out, int n, int h, int w, int cout, void* stream) {
+  return deconv_gather_dy(dy, out, n, h, w, cout, as_stream(stream));
+}
+int vpb_deconv_phase_dy(const void* dy, void* out, int n, int h, int w, int cout, void* stream) {
+  return deconv_phase_dy(dy, out, n, h, w, cout, as_stream(stream));
+}
+
 int vpb_warp_affine_normalize(const unsigned char* const* src_ptrs, const int32_t* src_hw, const double* inv_mats,
                               int n, int out_h, int out_w, const float* mean3, const float* std3, float* out,
                               void* stream) {

@@ -32,6 +32,7 @@ struct ConvParams {
   int n_tiles;                   // ceil(cout / BN)
   const float* scale;            // [cout] (deconv: folded BN scale)
   const float* shift;            // [cout] (deconv: folded BN shift; conv3: bias)
+  float floor;                   // deconv: 0 = ReLU, -inf = no activation (training: BatchNorm needs the raw output)
   void* out;
 };
 
@@ -185,8 +186,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
             uint32_t w[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float a = fmaxf(fmaf(__uint_as_float(r[2 * j]), sc[c + 2 * j], sh[c + 2 * j]), 0.f);
-              const float b = fmaxf(fmaf(__uint_as_float(r[2 * j + 1]), sc[c + 2 * j + 1], sh[c + 2 * j + 1]), 0.f);
+              const float a = fmaxf(fmaf(__uint_as_float(r[2 * j]), sc[c + 2 * j], sh[c + 2 * j]), p.floor);
+              const float b = fmaxf(fmaf(__uint_as_float(r[2 * j + 1]), sc[c + 2 * j + 1], sh[c + 2 * j + 1]), p.floor);
               w[j] = pack_bf16x2(a, b);
             }
             if (nt * BN + c + 32 <= p.cout) {          // 64 contiguous bytes per pixel
@@ -195,7 +196,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
                 reinterpret_cast<uint4*>(orow + c)[u] = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
             } else {
               for (int j = 0; j < p.cout - (nt * BN + c); ++j)
-                orow[c + j] = __float2bfloat16_rn(fmaxf(fmaf(__uint_as_float(r[j]), sc[c + j], sh[c + j]), 0.f));
+                orow[c + j] = __float2bfloat16_rn(fmaxf(fmaf(__uint_as_float(r[j]), sc[c + j], sh[c + j]), p.floor));
             }
           }
         } else {
@@ -213,7 +214,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
                                  ((static_cast<size_t>(img) * (2 * p.h) + oy) * (2 * p.w) + ox) * p.cout + co0;
               for (int j = 0; j < ncols; ++j)
                 o[j] = __float2bfloat16_rn(
-                    fmaxf(fmaf(__uint_as_float(r[j]), sc[c * 16 + j], sh[c * 16 + j]), 0.f));
+                    fmaxf(fmaf(__uint_as_float(r[j]), sc[c * 16 + j], sh[c * 16 + j]), p.floor));
             } else {
               // fp32 NCHW heatmaps: lanes hold consecutive pixels -> 128-byte coalesced stores per channel
               float* o = reinterpret_cast<float*>(p.out) +
@@ -286,10 +287,16 @@ static int launch_conv(const void* in, const void* wts, ConvParams& p, int k_tot
 
 int deconv4x4s2_bn_relu(const void* in, const void* wphase, const float* scale, const float* shift, void* out,
                         int n, int h, int w, int cin, int cout, int max_ctas, cudaStream_t stream) {
+  return deconv4x4s2_affine(in, wphase, scale, shift, out, n, h, w, cin, cout, 1, max_ctas, stream);
+}
+
+int deconv4x4s2_affine(const void* in, const void* wphase, const float* scale, const float* shift, void* out, int n,
+                       int h, int w, int cin, int cout, int relu, int max_ctas, cudaStream_t stream) {
   VPB_REQUIRE(n > 0 && cin % 64 == 0 && cout % 8 == 0, "deconv: need Cin %% 64 == 0, Cout %% 8 == 0 (Cin=%d Cout=%d)",
               cin, cout);
   ConvParams p{};
   p.n = n; p.h = h; p.w = w; p.cin = cin; p.cout = cout; p.scale = scale; p.shift = shift; p.out = out;
+  p.floor = relu ? 0.f : -INFINITY;
   VPB_REQUIRE(pick_boxes(n, h, w, p) == 0, "deconv: %dx%d input does not tile into 384-pixel TMA boxes", h, w);
   if (cout % 128 == 0 || cout > 64) return launch_conv<128, MODE_DECONV>(in, wphase, p, 4 * cin, 4 * cout, max_ctas, stream);
   return launch_conv<64, MODE_DECONV>(in, wphase, p, 4 * cin, 4 * cout, max_ctas, stream);

@@ -52,6 +52,9 @@ int attention_fwd(const void* qkv, void* out, int n, int T, int heads, int hd, f
 // ConvTranspose2d(k4,s2,p1,no bias) + folded BN + ReLU, NHWC bf16.
 //   in [n,h,w,Cin] -> out [n,2h,2w,Cout]; wphase bf16 [4 phases][Cout][4 taps * Cin] (see pack in python),
 //   scale/shift fp32 [Cout] applied as relu(acc * scale + shift)
+// relu = 0: affine output without the activation (training forward: raw conv output for BatchNorm statistics)
+int deconv4x4s2_affine(const void* in, const void* wphase, const float* scale, const float* shift, void* out, int n,
+                       int h, int w, int cin, int cout, int relu, int max_ctas, cudaStream_t stream);
 int deconv4x4s2_bn_relu(const void* in, const void* wphase, const float* scale, const float* shift, void* out,
                         int n, int h, int w, int cin, int cout, int max_ctas, cudaStream_t stream);
 // Conv2d 3x3 pad 1 + bias, NHWC bf16 in [n,h,w,Cin], weights bf16 [Cout][9 taps * Cin] -> fp32 NCHW [n,Cout,h,w]
@@ -82,5 +85,29 @@ int grad_sq_norm_accumulate(const float* grad, long long n, float* sq_norm_accum
 int adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                float beta2, float eps, float weight_decay, int step, const float* sq_norm, float max_norm,
                cudaStream_t stream);
+
+// ---- backward pass of the training step (train_bwd.cu, attention_bwd.cu) ----
+int transpose_bf16(const void* in, void* out, int R, int C, int batch, cudaStream_t stream);
+int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream);
+int colsum_accumulate(const void* in, int is_f32, int R, int C, float* out, cudaStream_t stream);
+int colsum_sq_accumulate(const void* in, int R, int C, float* sum, float* sumsq, cudaStream_t stream);
+int gelu_fwd_bf16(const void* pre, void* out, long long n, cudaStream_t stream);
+int gelu_bwd_bf16(const void* pre, const void* dh, void* dpre, long long n, cudaStream_t stream);
+int layernorm_bwd(const float* x, const float* gamma, const void* dy, float* dx_accum, float* dgamma, float* dbeta,
+                  int M, int D, float eps, cudaStream_t stream);
+int bn_finalize(const float* sum, const float* sumsq, float* mean, float* rstd, float* running_mean, float* running_var,
+                int C, long long rows, float eps, float momentum, cudaStream_t stream);
+int bn_relu_fwd(const void* raw, void* act, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                long long rows, int C, cudaStream_t stream);
+int bn_relu_bwd_reduce(const void* raw, const void* dact, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, int R, int C, float* dbeta, float* dgamma, cudaStream_t stream);
+int bn_relu_bwd(const void* raw, const void* dact, void* draw, const float* mean, const float* rstd, const float* gamma,
+                const float* beta, const float* dbeta, const float* dgamma, long long rows, int C, cudaStream_t stream);
+int nchw_f32_to_rows_bf16(const float* in, void* out, int n, int K, int P, int Kp, cudaStream_t stream);
+int deconv_gather_x(const void* x, void* out, int n, int h, int w, int cin, cudaStream_t stream);
+int deconv_gather_dy(const void* dy, void* out, int n, int h, int w, int cout, cudaStream_t stream);
+int deconv_phase_dy(const void* dy, void* out, int n, int h, int w, int cout, cudaStream_t stream);
+int attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, int n, int T, int heads, int hd,
+                  float scale, cudaStream_t stream);
 
 }  // namespace vpb

@@ -1,0 +1,558 @@
+// Backward-pass kernels of the ViTPose-B training step: everything around the tensor-core
+// GEMMs, which are the forward kernel itself (gemm.cuh) applied to transposed operands:
+//   dgrad  dX[M,K] = dY[M,N] . W[N,K]      = gemm(A = dY,   B = W^T [K,N])
+//   wgrad  dW[N,K] = dY^T . X              = gemm(A = dY^T [N,M], B = X^T [K,M]), fp32, accumulating (EPI_RESID_F32)
+// so the pieces here are layout changes (transpose, casts, gathers for the transposed convolutions), column
+// reductions (bias / LayerNorm / BatchNorm parameter gradients, BatchNorm statistics) and the element-wise
+// derivatives (GELU, LayerNorm, BatchNorm + ReLU). All of them are HBM-bound.
+#include <cuda_bf16.h>
+
+#include "host_util.h"
+#include "ops.h"
+#include "ptx.cuh"
+
+namespace vpb {
+
+// -------------------------------------------------------------------------------------------------
+// out[C, R] = in[R, C]^T (bf16), 64 x 64 tiles through padded shared memory; R, C even.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in,
+                                                             __nv_bfloat16* __restrict__ out, int R, int C,
+                                                             long long in_batch_stride, long long out_batch_stride) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  in += static_cast<size_t>(blockIdx.z) * in_batch_stride;
+  out += static_cast<size_t>(blockIdx.z) * out_batch_stride;
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int i = ty; i < 64; i += 8) {
+    const int r = r0 + i, c = c0 + 2 * tx;
+    __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
+    if (r < R && c < C) v = *reinterpret_cast<const __nv_bfloat162*>(in + static_cast<size_t>(r) * C + c);
+    tile[i][2 * tx] = v.x;
+    tile[i][2 * tx + 1] = v.y;
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 8) {
+    const int c = c0 + i, r = r0 + 2 * tx;
+    if (c < C && r < R) {
+      __nv_bfloat162 v;
+      v.x = tile[2 * tx][i];
+      v.y = tile[2 * tx + 1][i];
+      *reinterpret_cast<__nv_bfloat162*>(out + static_cast<size_t>(c) * R + r) = v;
+    }
+  }
+}
+
+int transpose_bf16(const void* in, void* out, int R, int C, int batch, cudaStream_t stream) {
+  VPB_REQUIRE(R > 0 && C > 0 && batch > 0 && R % 2 == 0 && C % 2 == 0, "transpose: R=%d C=%d must be even", R, C);
+  dim3 grid((C + 63) / 64, (R + 63) / 64, batch);
+  transpose_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+                                                  reinterpret_cast<__nv_bfloat16*>(out), R, C,
+                                                  static_cast<long long>(R) * C, static_cast<long long>(R) * C);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// fp32 -> bf16 cast (master weights -> GEMM operands, fp32 gradient stream -> GEMM operand)
+// -------------------------------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long long n4) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = in[i];
+  out[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream) {
+  VPB_REQUIRE(n > 0 && n % 4 == 0, "cast: n=%lld must be a positive multiple of 4", n);
+  VPB_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 ||
+                  ((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0),
+              "cast: unaligned buffers");
+  const long long n4 = n / 4;
+  cast_f32_bf16_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(out), n4);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Column reductions over a row-major [R, C] matrix, accumulated (atomicAdd) into fp32 [C] vectors.
+//   COLSUM_BF16 / COLSUM_F32 : out0 += sum_r a              (bias gradients, pos-embed gradient)
+//   COLSUM_SQ_BF16           : out0 += sum a, out1 += sum a^2   (BatchNorm batch statistics)
+//   COLSUM_BNBWD             : with dy' = b * (bn(a) > 0), xhat = (a - mean) * rstd:
+//                              out0 += sum dy', out1 += sum dy' * xhat   (BatchNorm + ReLU backward reductions)
+// Block = 32 x 8 threads: 64 columns, `rows_per_block` rows.
+// -------------------------------------------------------------------------------------------------
+enum ColsumMode { COLSUM_BF16 = 0, COLSUM_F32 = 1, COLSUM_SQ_BF16 = 2, COLSUM_BNBWD = 3 };
+
+struct ColsumArgs {
+  const void* a;
+  const void* b;            // COLSUM_BNBWD: upstream gradient (bf16)
+  const float* mean;        // COLSUM_BNBWD: per column
+  const float* rstd;
+  const float* gamma;
+  const float* beta;
+  float* out0;
+  float* out1;
+  int R, C, rows_per_block;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) colsum_kernel(const ColsumArgs p) {
+  __shared__ float red[2][8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + 2 * tx;
+  const int r_begin = blockIdx.y * p.rows_per_block;
+  const int r_end = min(p.R, r_begin + p.rows_per_block);
+  float s0x = 0.f, s0y = 0.f, s1x = 0.f, s1y = 0.f;
+  if (c < p.C) {
+    float mx = 0.f, my = 0.f, rx = 0.f, ry = 0.f, gx = 0.f, gy = 0.f, bx = 0.f, by = 0.f;
+    if (MODE == COLSUM_BNBWD) {
+      mx = p.mean[c]; my = p.mean[c + 1];
+      rx = p.rstd[c]; ry = p.rstd[c + 1];
+      gx = p.gamma[c]; gy = p.gamma[c + 1];
+      bx = p.beta[c]; by = p.beta[c + 1];
+    }
+    for (int r = r_begin + ty; r < r_end; r += 8) {
+      const size_t off = static_cast<size_t>(r) * p.C + c;
+      float ax, ay;
+      if (MODE == COLSUM_F32) {
+        const float2 v = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(p.a) + off);
+        ax = v.x; ay = v.y;
+      } else {
+        const float2 v = __bfloat1622float2(
+            *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(p.a) + off));
+        ax = v.x; ay = v.y;
+      }
+      if (MODE == COLSUM_BF16 || MODE == COLSUM_F32) {
+        s0x += ax; s0y += ay;
+      } else if (MODE == COLSUM_SQ_BF16) {
+        s0x += ax; s0y += ay;
+        s1x = fmaf(ax, ax, s1x); s1y = fmaf(ay, ay, s1y);
+      } else {
+        const float2 d = __bfloat1622float2(
+            *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(p.b) + off));
+        const float hx = (ax - mx) * rx, hy = (ay - my) * ry;
+        const float dx = fmaf(hx, gx, bx) > 0.f ? d.x : 0.f;
+        const float dy = fmaf(hy, gy, by) > 0.f ? d.y : 0.f;
+        s0x += dx; s0y += dy;
+        s1x = fmaf(dx, hx, s1x); s1y = fmaf(dy, hy, s1y);
+      }
+    }
+  }
+  red[0][ty][2 * tx] = s0x; red[0][ty][2 * tx + 1] = s0y;
+  red[1][ty][2 * tx] = s1x; red[1][ty][2 * tx + 1] = s1y;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, col = threadIdx.x & 63;
+    if (which == 1 && (MODE == COLSUM_BF16 || MODE == COLSUM_F32)) return;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[which][i][col];
+    const int cc = blockIdx.x * 64 + col;
+    if (cc < p.C) atomicAdd((which ? p.out1 : p.out0) + cc, s);
+  }
+}
+
+static int launch_colsum(int mode, const ColsumArgs& a, cudaStream_t stream) {
+  VPB_REQUIRE(a.R > 0 && a.C > 0 && a.C % 2 == 0, "colsum: C=%d must be even", a.C);
+  ColsumArgs p = a;
+  // enough blocks to fill the machine, rows per block a multiple of 8
+  const int col_blocks = (p.C + 63) / 64;
+  int row_blocks = (4 * sm_count() + col_blocks - 1) / col_blocks;
+  if (row_blocks < 1) row_blocks = 1;
+  p.rows_per_block = ((p.R + row_blocks - 1) / row_blocks + 7) / 8 * 8;
+  row_blocks = (p.R + p.rows_per_block - 1) / p.rows_per_block;
+  dim3 grid(col_blocks, row_blocks);
+  switch (mode) {
+    case COLSUM_BF16: colsum_kernel<COLSUM_BF16><<<grid, 256, 0, stream>>>(p); break;
+    case COLSUM_F32: colsum_kernel<COLSUM_F32><<<grid, 256, 0, stream>>>(p); break;
+    case COLSUM_SQ_BF16: colsum_kernel<COLSUM_SQ_BF16><<<grid, 256, 0, stream>>>(p); break;
+    default: colsum_kernel<COLSUM_BNBWD><<<grid, 256, 0, stream>>>(p); break;
+  }
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int colsum_accumulate(const void* in, int is_f32, int R, int C, float* out, cudaStream_t stream) {
+  ColsumArgs a{in, nullptr, nullptr, nullptr, nullptr, nullptr, out, nullptr, R, C, 0};
+  return launch_colsum(is_f32 ? COLSUM_F32 : COLSUM_BF16, a, stream);
+}
+int colsum_sq_accumulate(const void* in, int R, int C, float* sum, float* sumsq, cudaStream_t stream) {
+  ColsumArgs a{in, nullptr, nullptr, nullptr, nullptr, nullptr, sum, sumsq, R, C, 0};
+  return launch_colsum(COLSUM_SQ_BF16, a, stream);
+}
+int bn_relu_bwd_reduce(const void* raw, const void* dact, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, int R, int C, float* dbeta, float* dgamma, cudaStream_t stream) {
+  ColsumArgs a{raw, dact, mean, rstd, gamma, beta, dbeta, dgamma, R, C, 0};
+  return launch_colsum(COLSUM_BNBWD, a, stream);
+}
+
+// -------------------------------------------------------------------------------------------------
+// GELU (exact erf, nn.GELU default): forward on the stored pre-activation and its derivative
+//   d/dx [x Phi(x)] = Phi(x) + x phi(x)
+// -------------------------------------------------------------------------------------------------
+__global__ void gelu_fwd_kernel(const uint4* __restrict__ pre, uint4* __restrict__ out, long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 v = pre[i];
+  uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+    const float a = 0.5f * f.x * (1.0f + erff(f.x * 0.70710678118654752f));
+    const float b = 0.5f * f.y * (1.0f + erff(f.y * 0.70710678118654752f));
+    w[j] = pack_bf16x2(a, b);
+  }
+  out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+__global__ void gelu_bwd_kernel(const uint4* __restrict__ pre, const uint4* __restrict__ dh, uint4* __restrict__ out,
+                                long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 v = pre[i], g = dh[i];
+  uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+    const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[j]));
+    const float da = 0.5f * (1.0f + erff(x.x * 0.70710678118654752f)) + x.x * 0.3989422804014327f * __expf(-0.5f * x.x * x.x);
+    const float db = 0.5f * (1.0f + erff(x.y * 0.70710678118654752f)) + x.y * 0.3989422804014327f * __expf(-0.5f * x.y * x.y);
+    w[j] = pack_bf16x2(d.x * da, d.y * db);
+  }
+  out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+int gelu_fwd_bf16(const void* pre, void* out, long long n, cudaStream_t stream) {
+  VPB_REQUIRE(n > 0 && n % 8 == 0, "gelu: n=%lld must be a multiple of 8", n);
+  const long long n8 = n / 8;
+  gelu_fwd_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(pre), reinterpret_cast<uint4*>(out), n8);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int gelu_bwd_bf16(const void* pre, const void* dh, void* dpre, long long n, cudaStream_t stream) {
+  VPB_REQUIRE(n > 0 && n % 8 == 0, "gelu: n=%lld must be a multiple of 8", n);
+  const long long n8 = n / 8;
+  gelu_bwd_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(pre), reinterpret_cast<const uint4*>(dh), reinterpret_cast<uint4*>(dpre), n8);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// LayerNorm backward. y = xhat * gamma + beta, xhat = (x - mean) * rstd. With g = dy * gamma:
+//   dx = rstd * (g - mean_D(g) - xhat * mean_D(g * xhat)),  dgamma = sum_rows dy * xhat,  dbeta = sum_rows dy
+// One warp per row (row in registers, statistics recomputed from the saved fp32 x); dx is ADDED to dx_accum
+// (the gradient already flowing through the residual connection); dgamma / dbeta are accumulated per warp over
+// `rows_per_warp` rows in registers and then added atomically.
+// -------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            const __nv_bfloat16* __restrict__ dy,
+                                                            float* __restrict__ dx_accum, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int M, float eps,
+                                                            int rows_per_warp) {
+  constexpr int D = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int row0 = warp_global * rows_per_warp;
+  float4 gm[NV], dg[NV], db[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    gm[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int row = row0; row < min(M, row0 + rows_per_warp); ++row) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+    const uint2* dr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(row) * D);
+    float4 v[NV], d[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i] = xr[i * 32 + lane];
+      const uint2 raw = dr[i * 32 + lane];
+      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+      d[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    const float mean = s * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+    const float rstd = 1.0f / sqrtf(q * (1.0f / D) + eps);
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;        // xhat
+      db[i].x += d[i].x; db[i].y += d[i].y; db[i].z += d[i].z; db[i].w += d[i].w;
+      dg[i].x = fmaf(d[i].x, v[i].x, dg[i].x); dg[i].y = fmaf(d[i].y, v[i].y, dg[i].y);
+      dg[i].z = fmaf(d[i].z, v[i].z, dg[i].z); dg[i].w = fmaf(d[i].w, v[i].w, dg[i].w);
+      d[i].x *= gm[i].x; d[i].y *= gm[i].y; d[i].z *= gm[i].z; d[i].w *= gm[i].w;   // g = dy * gamma
+      c1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+      c2 += (d[i].x * v[i].x + d[i].y * v[i].y) + (d[i].z * v[i].z + d[i].w * v[i].w);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      c1 += __shfl_xor_sync(0xffffffffu, c1, off);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, off);
+    }
+    c1 *= (1.0f / D);
+    c2 *= (1.0f / D);
+    float4* o = reinterpret_cast<float4*>(dx_accum + static_cast<size_t>(row) * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 a = o[i * 32 + lane];
+      a.x += rstd * (d[i].x - c1 - v[i].x * c2);
+      a.y += rstd * (d[i].y - c1 - v[i].y * c2);
+      a.z += rstd * (d[i].z - c1 - v[i].z * c2);
+      a.w += rstd * (d[i].w - c1 - v[i].w * c2);
+      o[i * 32 + lane] = a;
+    }
+  }
+  if (row0 < M) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      atomicAdd(dgamma + c + 0, dg[i].x); atomicAdd(dgamma + c + 1, dg[i].y);
+      atomicAdd(dgamma + c + 2, dg[i].z); atomicAdd(dgamma + c + 3, dg[i].w);
+      atomicAdd(dbeta + c + 0, db[i].x); atomicAdd(dbeta + c + 1, db[i].y);
+      atomicAdd(dbeta + c + 2, db[i].z); atomicAdd(dbeta + c + 3, db[i].w);
+    }
+  }
+}
+
+int layernorm_bwd(const float* x, const float* gamma, const void* dy, float* dx_accum, float* dgamma, float* dbeta,
+                  int M, int D, float eps, cudaStream_t stream) {
+  VPB_REQUIRE(M > 0 && D > 0 && D % 128 == 0, "layernorm_bwd: D=%d must be a multiple of 128", D);
+  const int warps = 8;
+  int rows_per_warp = (M + 8 * sm_count() * warps - 1) / (8 * sm_count() * warps);
+  if (rows_per_warp < 1) rows_per_warp = 1;
+  const int total_warps = (M + rows_per_warp - 1) / rows_per_warp;
+  dim3 grid((total_warps + warps - 1) / warps), block(warps * 32);
+  const __nv_bfloat16* d = reinterpret_cast<const __nv_bfloat16*>(dy);
+  switch (D / 128) {
+#define VPB_LNB_CASE(NV_)                                                                                          \
+  case NV_:                                                                                                        \
+    layernorm_bwd_kernel<NV_><<<grid, block, 0, stream>>>(x, gamma, d, dx_accum, dgamma, dbeta, M, eps, rows_per_warp); \
+    break;
+    VPB_LNB_CASE(1) VPB_LNB_CASE(2) VPB_LNB_CASE(3) VPB_LNB_CASE(4) VPB_LNB_CASE(6) VPB_LNB_CASE(8) VPB_LNB_CASE(10)
+#undef VPB_LNB_CASE
+    default:
+      set_last_error("layernorm_bwd: unsupported D=%d", D);
+      return -2;
+  }
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// BatchNorm2d in training mode + ReLU on NHWC bf16 rows [R = n*h*w, C]:
+//   forward  act = relu((raw - mean) * rstd * gamma + beta)              (mean / rstd from colsum_sq_accumulate)
+//   backward draw = gamma * rstd * (dy' - dbeta/R - xhat * dgamma/R),  dy' = dact * (act > 0)
+// -------------------------------------------------------------------------------------------------
+__global__ void bn_relu_fwd_kernel(const uint4* __restrict__ raw, uint4* __restrict__ act, const float* __restrict__ mean,
+                                   const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, long long n8, int C) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const int c0 = static_cast<int>((i * 8) % C);
+  const uint4 v = raw[i];
+  uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+    const int c = c0 + 2 * j;
+    const float a = fmaxf(fmaf((f.x - mean[c]) * rstd[c], gamma[c], beta[c]), 0.f);
+    const float b = fmaxf(fmaf((f.y - mean[c + 1]) * rstd[c + 1], gamma[c + 1], beta[c + 1]), 0.f);
+    w[j] = pack_bf16x2(a, b);
+  }
+  act[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+__global__ void bn_relu_bwd_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ dact, uint4* __restrict__ draw,
+                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ dbeta, const float* __restrict__ dgamma, float inv_rows,
+                                   long long n8, int C) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const int c0 = static_cast<int>((i * 8) % C);
+  const uint4 v = raw[i], g = dact[i];
+  uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+    const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[j]));
+    float o[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int c = c0 + 2 * j + k;
+      const float xh = ((k ? f.y : f.x) - mean[c]) * rstd[c];
+      const float dyp = fmaf(xh, gamma[c], beta[c]) > 0.f ? (k ? d.y : d.x) : 0.f;
+      o[k] = gamma[c] * rstd[c] * (dyp - dbeta[c] * inv_rows - xh * dgamma[c] * inv_rows);
+    }
+    w[j] = pack_bf16x2(o[0], o[1]);
+  }
+  draw[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+int bn_relu_fwd(const void* raw, void* act, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                long long rows, int C, cudaStream_t stream) {
+  VPB_REQUIRE(rows > 0 && C > 0 && C % 8 == 0, "bn_relu: C=%d must be a multiple of 8", C);
+  const long long n8 = rows * C / 8;
+  bn_relu_fwd_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(raw), reinterpret_cast<uint4*>(act), mean, rstd, gamma, beta, n8, C);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int bn_relu_bwd(const void* raw, const void* dact, void* draw, const float* mean, const float* rstd, const float* gamma,
+                const float* beta, const float* dbeta, const float* dgamma, long long rows, int C, cudaStream_t stream) {
+  VPB_REQUIRE(rows > 0 && C > 0 && C % 8 == 0, "bn_relu: C=%d must be a multiple of 8", C);
+  const long long n8 = rows * C / 8;
+  bn_relu_bwd_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(raw), reinterpret_cast<const uint4*>(dact), reinterpret_cast<uint4*>(draw), mean,
+      rstd, gamma, beta, dbeta, dgamma, 1.0f / static_cast<float>(rows), n8, C);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+// mean / rstd (and the running statistics update of nn.BatchNorm2d: momentum, unbiased variance) from the sums
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, int C, float rows, float eps, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float m = sum[c] / rows;
+  const float var = fmaxf(sumsq[c] / rows - m * m, 0.f);
+  mean[c] = m;
+  rstd[c] = 1.0f / sqrtf(var + eps);
+  if (running_mean != nullptr) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * rows / fmaxf(rows - 1.f, 1.f);
+  }
+}
+int bn_finalize(const float* sum, const float* sumsq, float* mean, float* rstd, float* running_mean, float* running_var,
+                int C, long long rows, float eps, float momentum, cudaStream_t stream) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sum, sumsq, mean, rstd, running_mean, running_var, C,
+                                                         static_cast<float>(rows), eps, momentum);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Heatmap gradient fp32 NCHW [n, K, P] -> bf16 pixel-major [n*P, Kp] (Kp >= K, zero padded): the A operand of the
+// final 1x1 conv's dgrad / (after a transpose) wgrad GEMMs.
+// -------------------------------------------------------------------------------------------------
+__global__ void nchw_to_rows_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int K, int P, int Kp) {
+  __shared__ float tile[32][33];
+  const int im = blockIdx.z;
+  const int p0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, pp = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && pp < P) ? in[(static_cast<size_t>(im) * K + k) * P + pp] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int pp = p0 + i, k = k0 + threadIdx.x;
+    if (pp < P && k < Kp) out[(static_cast<size_t>(im) * P + pp) * Kp + k] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+int nchw_f32_to_rows_bf16(const float* in, void* out, int n, int K, int P, int Kp, cudaStream_t stream) {
+  VPB_REQUIRE(n > 0 && K > 0 && P > 0 && Kp >= K, "nchw_to_rows: bad shape");
+  dim3 grid((P + 31) / 32, (Kp + 31) / 32, n), block(32, 8);
+  nchw_to_rows_kernel<<<grid, block, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out), K, P, Kp);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Gathers for the backward of ConvTranspose2d(k4, s2, p1) in its 4-phase form (engine.pack_deconv_weight):
+//   forward  Y[n, 2i+py, 2j+px, :] = sum_t X[n, i+dy(py,ty), j+dx(px,tx), :] . Wp[ph][:, t*Cin : (t+1)*Cin]^T
+//   with d(p, 0) = 0, d(0, 1) = -1, d(1, 1) = +1.
+// deconv_gather_x   : Xcol[ph][pix, t*Cin + ci] = X[n, i+dy, j+dx, ci]   (zero outside)   -> wgrad B operand (transposed later)
+// deconv_gather_dy  : G[pix, (ph*4+t)*Cout + co] = dY[n, 2(i-dy)+py, 2(j-dx)+px, co] (zero when (i-dy, j-dx) is outside)
+//                     -> dgrad A operand, against W2g[ci, (ph*4+t)*Cout + co] = Wp[ph][co][t*Cin+ci]
+// deconv_phase_dy   : Yp[ph][pix, co] = dY[n, 2i+py, 2j+px, co]                          -> wgrad A operand (transposed later)
+// One thread = 8 channels (16 bytes).
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int deconv_shift(int parity, int tap) { return tap == 0 ? 0 : (parity == 0 ? -1 : 1); }
+
+__global__ void deconv_gather_x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int h, int w, int cin8,
+                                       long long pixels, long long total) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % cin8);
+  long long rest = idx / cin8;
+  const int t = static_cast<int>(rest % 4);
+  rest /= 4;
+  const long long pix = rest % pixels;
+  const int ph = static_cast<int>(rest / pixels);
+  const int j = static_cast<int>(pix % w), i = static_cast<int>((pix / w) % h);
+  const long long im = pix / (static_cast<long long>(w) * h);
+  const int ii = i + deconv_shift(ph >> 1, t >> 1), jj = j + deconv_shift(ph & 1, t & 1);
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (ii >= 0 && ii < h && jj >= 0 && jj < w) v = x[((im * h + ii) * w + jj) * cin8 + c8];
+  out[idx] = v;
+}
+__global__ void deconv_gather_dy_kernel(const uint4* __restrict__ dy, uint4* __restrict__ out, int h, int w, int cout8,
+                                        long long total) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % cout8);
+  long long rest = idx / cout8;
+  const int pt = static_cast<int>(rest % 16);
+  const long long pix = rest / 16;
+  const int ph = pt >> 2, t = pt & 3;
+  const int j = static_cast<int>(pix % w), i = static_cast<int>((pix / w) % h);
+  const long long im = pix / (static_cast<long long>(w) * h);
+  const int ii = i - deconv_shift(ph >> 1, t >> 1), jj = j - deconv_shift(ph & 1, t & 1);
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (ii >= 0 && ii < h && jj >= 0 && jj < w)
+    v = dy[((im * 2 * h + 2 * ii + (ph >> 1)) * 2 * w + 2 * jj + (ph & 1)) * cout8 + c8];
+  out[idx] = v;
+}
+__global__ void deconv_phase_dy_kernel(const uint4* __restrict__ dy, uint4* __restrict__ out, int h, int w, int cout8,
+                                       long long pixels, long long total) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % cout8);
+  long long rest = idx / cout8;
+  const long long pix = rest % pixels;
+  const int ph = static_cast<int>(rest / pixels);
+  const int j = static_cast<int>(pix % w), i = static_cast<int>((pix / w) % h);
+  const long long im = pix / (static_cast<long long>(w) * h);
+  out[idx] = dy[((im * 2 * h + 2 * i + (ph >> 1)) * 2 * w + 2 * j + (ph & 1)) * cout8 + c8];
+}
+int deconv_gather_x(const void* x, void* out, int n, int h, int w, int cin, cudaStream_t stream) {
+  VPB_REQUIRE(n > 0 && h > 0 && w > 0 && cin % 8 == 0, "deconv_gather_x: bad shape");
+  const long long pixels = static_cast<long long>(n) * h * w, total = 4 * pixels * 4 * (cin / 8);
+  deconv_gather_x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), h, w, cin / 8, pixels, total);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int deconv_gather_dy(const void* dy, void* out, int n, int h, int w, int cout, cudaStream_t stream) {
+  VPB_REQUIRE(n > 0 && h > 0 && w > 0 && cout % 8 == 0, "deconv_gather_dy: bad shape");
+  const long long total = static_cast<long long>(n) * h * w * 16 * (cout / 8);
+  deconv_gather_dy_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(out), h, w, cout / 8, total);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int deconv_phase_dy(const void* dy, void* out, int n, int h, int w, int cout, cudaStream_t stream) {
+  VPB_REQUIRE(n > 0 && h > 0 && w > 0 && cout % 8 == 0, "deconv_phase_dy: bad shape");
+  const long long pixels = static_cast<long long>(n) * h * w, total = 4 * pixels * (cout / 8);
+  deconv_phase_dy_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(out), h, w, cout / 8, pixels, total);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vpb

@@ -63,6 +63,31 @@ def pack_deconv_weight(w):
     return out.to(BF16).contiguous()
 
 
+def pack_deconv_weight_dgrad(wp):
+    """Packed deconv weight [4 phases, Cout, 4 taps * Cin] -> [Cin, 16 * Cout] with column (ph*4 + t)*Cout + co:
+    the B operand of the transposed convolution's input gradient as one GEMM over the 16 (phase, tap) shifted
+    copies of dY (vpb_deconv_gather_dy)."""
+    _, cout, c4 = wp.shape
+    cin = c4 // 4
+    return wp.reshape(4, cout, 4, cin).permute(3, 0, 2, 1).reshape(cin, 16 * cout).contiguous()
+
+
+def unpack_deconv_weight(wp, dtype=torch.float32):
+    """Inverse of pack_deconv_weight: [4, Cout, 4*Cin] -> ConvTranspose2d layout [Cin, Cout, 4, 4]."""
+    _, cout, c4 = wp.shape
+    cin = c4 // 4
+    w = torch.empty(cin, cout, 4, 4, dtype=dtype, device=wp.device)
+    for py in range(2):
+        for px in range(2):
+            for ty in range(2):
+                for tx in range(2):
+                    kh = (1 if py == 0 else 2) if ty == 0 else (3 if py == 0 else 0)
+                    kw = (1 if px == 0 else 2) if tx == 0 else (3 if px == 0 else 0)
+                    t = ty * 2 + tx
+                    w[:, :, kh, kw] = wp[py * 2 + px, :, t * cin:(t + 1) * cin].t().to(dtype)
+    return w
+
+
 def fold_bn(g, b, mean, var, eps=1e-5):
     scale = g / torch.sqrt(var + eps)
     return scale.float().contiguous(), (b - mean * scale).float().contiguous()

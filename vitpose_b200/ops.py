@@ -159,3 +159,135 @@ def transform_preds(coords, center, scale, heatmap_wh, use_udp=False):
     check(lib().vpb_transform_preds(ptr(coords), ptr(center), ptr(scale), ptr(out), N, K, int(heatmap_wh[0]),
                                     int(heatmap_wh[1]), int(bool(use_udp)), stream_ptr()), 'vpb_transform_preds')
     return out
+
+
+# ---- backward-pass operators of the training step (include/vitpose_b200.h, "backward pass") ----
+def transpose(x, batch=1):
+    """bf16 [batch, R, C] (or [R, C]) -> [batch, C, R]."""
+    _need(x, BF16, 'x')
+    R, C = x.shape[-2:]
+    out = torch.empty(*x.shape[:-2], C, R, device=x.device, dtype=BF16)
+    check(lib().vpb_transpose_bf16(ptr(x), ptr(out), R, C, batch, stream_ptr()), 'vpb_transpose_bf16')
+    return out
+
+
+def cast_bf16(x):
+    _need(x, torch.float32, 'x')
+    out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    check(lib().vpb_cast_f32_bf16(ptr(x), ptr(out), x.numel(), stream_ptr()), 'vpb_cast_f32_bf16')
+    return out
+
+
+def colsum_accumulate(x, out):
+    """out[C] (fp32) += column sums of x [R, C] (bf16 or fp32)."""
+    assert x.is_contiguous() and out.dtype == torch.float32
+    R, C = x.shape
+    check(lib().vpb_colsum_accumulate(ptr(x), int(x.dtype == torch.float32), R, C, ptr(out), stream_ptr()),
+          'vpb_colsum_accumulate')
+    return out
+
+
+def gelu_fwd(pre):
+    _need(pre, BF16, 'pre')
+    out = torch.empty_like(pre)
+    check(lib().vpb_gelu_fwd_bf16(ptr(pre), ptr(out), pre.numel(), stream_ptr()), 'vpb_gelu_fwd_bf16')
+    return out
+
+
+def gelu_bwd(pre, dh):
+    _need(pre, BF16, 'pre'); _need(dh, BF16, 'dh')
+    out = torch.empty_like(pre)
+    check(lib().vpb_gelu_bwd_bf16(ptr(pre), ptr(dh), ptr(out), pre.numel(), stream_ptr()), 'vpb_gelu_bwd_bf16')
+    return out
+
+
+def layernorm_bwd(x, gamma, dy, dx_accum, dgamma, dbeta, eps=1e-6):
+    _need(x, torch.float32, 'x'); _need(dy, BF16, 'dy'); _need(dx_accum, torch.float32, 'dx_accum')
+    M, D = x.shape
+    check(lib().vpb_layernorm_bwd(ptr(x), ptr(gamma), ptr(dy), ptr(dx_accum), ptr(dgamma), ptr(dbeta), M, D,
+                                  float(eps), stream_ptr()), 'vpb_layernorm_bwd')
+
+
+def attention_bwd(qkv, out, dout, heads, scale=None):
+    """qkv bf16 [n,T,3*heads*hd], out / dout bf16 [n,T,heads*hd] -> dqkv bf16 [n,T,3*heads*hd]."""
+    _need(qkv, BF16, 'qkv'); _need(out, BF16, 'out'); _need(dout, BF16, 'dout')
+    n, T, three = qkv.shape
+    hd = three // 3 // heads
+    scale = hd ** -0.5 if scale is None else scale
+    dqkv = torch.empty_like(qkv)
+    check(lib().vpb_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(dqkv), n, T, heads, hd, float(scale),
+                                  stream_ptr()), 'vpb_attention_bwd')
+    return dqkv
+
+
+def deconv4x4s2_raw(x, wphase):
+    """ConvTranspose2d(k4,s2,p1) alone: x bf16 [n,h,w,cin] -> bf16 [n,2h,2w,cout]."""
+    _need(x, BF16, 'x'); _need(wphase, BF16, 'wphase')
+    n, h, w, cin = x.shape
+    cout = wphase.shape[1]
+    out = torch.empty(n, 2 * h, 2 * w, cout, device=x.device, dtype=BF16)
+    ones = torch.ones(cout, device=x.device)
+    zeros = torch.zeros(cout, device=x.device)
+    check(lib().vpb_deconv4x4s2_raw(ptr(x), ptr(wphase), ptr(out), n, h, w, cin, cout, ptr(ones), ptr(zeros),
+                                    stream_ptr()), 'vpb_deconv4x4s2_raw')
+    return out
+
+
+def bn_train_stats(raw, eps=1e-5, momentum=0.1, running_mean=None, running_var=None):
+    """raw bf16 [..., C] -> (mean, rstd) fp32 [C] of the batch; updates the running statistics in place."""
+    _need(raw, BF16, 'raw')
+    C = raw.shape[-1]
+    rows = raw.numel() // C
+    scratch = torch.empty(2 * C, device=raw.device)
+    mean, rstd = torch.empty(C, device=raw.device), torch.empty(C, device=raw.device)
+    check(lib().vpb_bn_train_stats(ptr(raw), rows, C, float(eps), float(momentum), ptr(scratch), ptr(mean), ptr(rstd),
+                                   ptr(running_mean), ptr(running_var), stream_ptr()), 'vpb_bn_train_stats')
+    return mean, rstd
+
+
+def bn_relu_fwd(raw, mean, rstd, gamma, beta):
+    C = raw.shape[-1]
+    act = torch.empty_like(raw)
+    check(lib().vpb_bn_relu_fwd(ptr(raw), ptr(act), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), raw.numel() // C, C,
+                                stream_ptr()), 'vpb_bn_relu_fwd')
+    return act
+
+
+def bn_relu_bwd(raw, dact, mean, rstd, gamma, beta, dgamma, dbeta):
+    C = raw.shape[-1]
+    draw = torch.empty_like(raw)
+    check(lib().vpb_bn_relu_bwd(ptr(raw), ptr(dact), ptr(draw), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta),
+                                ptr(dgamma), ptr(dbeta), raw.numel() // C, C, stream_ptr()), 'vpb_bn_relu_bwd')
+    return draw
+
+
+def nchw_to_rows(x, Kp):
+    """fp32 [n, K, P] -> bf16 [n*P, Kp] (zero padded columns)."""
+    _need(x, torch.float32, 'x')
+    n, K, P = x.shape
+    out = torch.empty(n * P, Kp, device=x.device, dtype=BF16)
+    check(lib().vpb_nchw_f32_to_rows_bf16(ptr(x), ptr(out), n, K, P, Kp, stream_ptr()), 'vpb_nchw_f32_to_rows_bf16')
+    return out
+
+
+def deconv_gather_x(x):
+    n, h, w, cin = x.shape
+    out = torch.empty(4, n * h * w, 4 * cin, device=x.device, dtype=BF16)
+    check(lib().vpb_deconv_gather_x(ptr(x), ptr(out), n, h, w, cin, stream_ptr()), 'vpb_deconv_gather_x')
+    return out
+
+
+def deconv_gather_dy(dy):
+    n, h2, w2, cout = dy.shape
+    h, w = h2 // 2, w2 // 2
+    out = torch.empty(n * h * w, 16 * cout, device=dy.device, dtype=BF16)
+    check(lib().vpb_deconv_gather_dy(ptr(dy), ptr(out), n, h, w, cout, stream_ptr()), 'vpb_deconv_gather_dy')
+    return out
+
+
+def deconv_phase_dy(dy):
+    n, h2, w2, cout = dy.shape
+    h, w = h2 // 2, w2 // 2
+    out = torch.empty(4, n * h * w, cout, device=dy.device, dtype=BF16)
+    check(lib().vpb_deconv_phase_dy(ptr(dy), ptr(out), n, h, w, cout, stream_ptr()), 'vpb_deconv_phase_dy')
+    return out
