@@ -1,0 +1,113 @@
+"""Training step (-m gpu): TopDown.forward_train -> loss.backward() on the B200 path against
+torch.autograd over the fp32 oracle (functional restatement of the reference modules, BatchNorm in training mode),
+on the same weights and batch; then the layer-decay AdamW update.  Tolerances are bf16-level: GEMM operands and the
+activation gradients between operators are bf16 on the GPU path, everything else fp32."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vitpose_torch as VT
+from vitpose_b200 import configs, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _targets(n, K, seed):
+    g = torch.Generator().manual_seed(seed)
+    ys, xs = torch.meshgrid(torch.arange(64.), torch.arange(48.), indexing='ij')
+    cx = torch.rand(n, K, generator=g) * 47
+    cy = torch.rand(n, K, generator=g) * 63
+    t = torch.exp(-((xs - cx[..., None, None]) ** 2 + (ys - cy[..., None, None]) ** 2) / (2 * 2.0 ** 2))
+    w = (torch.rand(n, K, 1, generator=g) > 0.2).float()
+    return t.contiguous(), w
+
+
+def _rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize('name,n,depth', [('tiny', 4, 2), ('B-classic-17', 3, 2), ('B-classic-17', 2, 12)])
+def test_forward_train_backward_vs_oracle(name, n, depth):
+    import vitpose_b200 as V
+    if name == 'tiny':
+        cfg = configs.tiny_model_cfg(5)
+    else:
+        cfg = configs.baseline_model_cfg(name)
+    cfg['backbone'].update(depth=depth, drop_path_rate=0.0)
+    K = cfg['keypoint_head']['out_channels']
+    sd = synthetic.scaled_init_state_dict(cfg, 7)
+    img = synthetic.synthetic_crops(n, 7)
+    target, tw = _targets(n, K, 7)
+    ref_sd = {k: v.clone() for k, v in sd.items()}
+    loss_ref, hm_ref, g_ref = VT.train_loss_and_grads(ref_sd, img, target, tw, cfg)
+
+    model = V.build_posenet(cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    losses = model(img=img.cuda(), target=target.cuda(), target_weight=tw.cuda(), img_metas=None, return_loss=True)
+    assert set(losses) >= {'heatmap_loss'}
+    loss = losses['heatmap_loss']
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) <= 2e-2 * abs(loss_ref.item()), (loss.item(), loss_ref.item())
+    # BatchNorm running statistics were updated as nn.BatchNorm2d(train) does
+    for i in (1, 4):
+        for b in ('running_mean', 'running_var'):
+            k = f'keypoint_head.deconv_layers.{i}.{b}'
+            assert _rel(model.state_dict()[k].cpu(), ref_sd[k]) < 2e-2, k
+    worst = {}
+    for nm, p in model.named_parameters():
+        assert p.grad is not None, f'{nm}: no gradient'
+        gr, rf = p.grad.cpu(), g_ref[nm]
+        assert gr.shape == rf.shape and torch.isfinite(gr).all(), nm
+        if rf.norm() < 1e-12:
+            continue
+        worst[nm] = (_rel(gr, rf), _cos(gr, rf))
+    # Upstream of the first ReLU everything is a linear function of bf16-rounded operands: tight.
+    for nm in ('keypoint_head.final_layer.weight', 'keypoint_head.final_layer.bias',
+               'keypoint_head.deconv_layers.4.weight', 'keypoint_head.deconv_layers.4.bias'):
+        assert worst[nm][0] < 0.02, (nm, worst[nm])
+    # Below a ReLU the comparison is statistical: the GPU path keeps the conv outputs in bf16, so ~0.4 % of the
+    # BatchNorm+ReLU units that sit within rounding distance of zero take the other branch than in the fp32 oracle,
+    # and a gradient field with a fraction f of its entries toggled is off by ~sqrt(f) (~6 %) in L2 -- on
+    # random-init weights that noise is not averaged out by the weight-gradient sums. Direction and norm must agree.
+    bad = {k: v for k, v in worst.items() if v[0] > 0.15 or v[1] < 0.99}
+    top = sorted(worst.items(), key=lambda kv: -kv[1][0])[:5]
+    assert not bad, f'gradient mismatch (rel err, cosine): {bad}; worst five: {top}'
+    # whole-model gradient: direction and norm
+    flat = torch.cat([p.grad.flatten().cpu() for _, p in model.named_parameters()])
+    flat_ref = torch.cat([g_ref[nm].flatten() for nm, _ in model.named_parameters()])
+    assert _cos(flat, flat_ref) > 0.998 and abs(float(flat.norm() / flat_ref.norm()) - 1) < 0.02
+
+
+def test_train_step_with_layer_decay_adamw_decreases_loss():
+    import vitpose_b200 as V
+    from vitpose_b200.optim import LayerDecayOptimizerConstructor
+    cfg = configs.tiny_model_cfg(5)
+    cfg['backbone'].update(drop_path_rate=0.0)
+    sd = synthetic.scaled_init_state_dict(cfg, 3)
+    model = V.build_posenet(cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    opt = LayerDecayOptimizerConstructor(dict(type='AdamW', lr=2e-3, betas=(0.9, 0.999), weight_decay=0.1),
+                                         dict(num_layers=2, layer_decay_rate=0.75))(model)
+    n = 4
+    img = synthetic.synthetic_crops(n, 3).cuda()
+    target, tw = _targets(n, 5, 3)
+    batch = dict(img=img, target=target.cuda(), target_weight=tw.cuda(), img_metas=None)
+    hist = []
+    for _ in range(6):
+        out = model.train_step(batch, opt)
+        assert set(out) == {'loss', 'log_vars', 'num_samples'} and out['num_samples'] == n
+        opt.zero_grad()
+        out['loss'].backward()
+        norm = opt.step(max_norm=1.0)
+        assert torch.isfinite(norm)
+        hist.append(out['loss'].item())
+    assert hist[-1] < hist[0], hist

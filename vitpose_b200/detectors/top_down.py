@@ -61,11 +61,44 @@ class TopDown(nn.Module):
 
     def forward(self, img, target=None, target_weight=None, img_metas=None, return_loss=True,
                 return_heatmap=False, **kwargs):
-        """return_loss=True is the training entry of the reference (top_down.py:138-139); the training step is
-        a later milestone here, so only the inference branch is served."""
+        """Dispatch of top_down.py:138-141."""
         if return_loss:
-            raise NotImplementedError('forward_train (training step) is not part of the inference hot path yet')
+            return self.forward_train(img, target, target_weight, img_metas, **kwargs)
         return self.forward_test(img, img_metas, return_heatmap=return_heatmap, **kwargs)
+
+    def forward_train(self, img, target, target_weight, img_metas=None, **kwargs):
+        """top_down.py:143-161: heatmaps of the batch, then the head's loss. The network is one autograd node whose
+        backward is the hand-written CUDA backward pass (vitpose_b200/training.py), so ``loss.backward()`` fills
+        ``.grad`` of every parameter exactly as in the reference's training loop."""
+        from ..training import network_heatmaps_train
+        output = network_heatmaps_train(self, img)
+        losses = dict()
+        if self.with_keypoint:
+            losses.update(self.keypoint_head.get_loss(output, target, target_weight))
+        return losses
+
+    @staticmethod
+    def _parse_losses(losses):
+        """mmpose/models/detectors/base.py:54-86 (single process: no all_reduce of the logged values)."""
+        log_vars = {}
+        for name, value in losses.items():
+            if isinstance(value, torch.Tensor):
+                log_vars[name] = value.mean()
+            elif isinstance(value, float):
+                log_vars[name] = value
+            elif isinstance(value, list):
+                log_vars[name] = sum(v.mean() for v in value)
+            else:
+                raise TypeError(f'{name} is not a tensor or list of tensors or float')
+        loss = sum(v for k, v in log_vars.items() if 'loss' in k)
+        log_vars['loss'] = loss
+        return loss, log_vars
+
+    def train_step(self, data_batch, optimizer=None, **kwargs):
+        """base.py:88-119: forward + loss parsing; the caller (runner hook) does backward() and optimizer.step()."""
+        losses = self.forward(**data_batch)
+        loss, log_vars = self._parse_losses(losses)
+        return dict(loss=loss, log_vars=log_vars, num_samples=len(next(iter(data_batch.values()))))
 
     def _engine(self):
         return self.backbone.engine(self.keypoint_head if self.with_keypoint else None)

@@ -1,0 +1,220 @@
+"""Training step of the ViTPose top-down path: ``TopDown.forward_train`` ->
+``loss.backward()`` -> layer-decay AdamW, with every tensor operation in libvitpose_b200.so.
+
+The reference trains through torch.autograd over eager modules (mmpose/models/detectors/top_down.py:143-161 for
+``forward_train``; ViT.forward vit.py:313-337; TopdownHeatmapSimpleHead.forward simple_head.py:197-202; BatchNorm2d in
+training mode inside the deconv stack, simple_head.py:324-333).  Here the whole network is ONE autograd node,
+:class:`_NetworkFn`: its forward launches the training variant of the forward pass (activations kept, BatchNorm on
+batch statistics, GELU unfused so the pre-activation survives), its backward launches the hand-written backward
+pass and returns the gradient of every parameter, so ``loss.backward()`` / ``optimizer.step()`` of an unmodified
+mmcv-style training loop work as before.  Python here only sequences C-ABI calls (the reference's runner is
+Python too); there is no eager fallback.
+
+Numerics: GEMM operands and the activation gradients between operators are bf16, the residual stream, its
+gradient, all parameter gradients, LayerNorm / BatchNorm statistics and the optimizer state are fp32.
+"""
+import torch
+
+from . import _lib, ops
+from .engine import pack_deconv_weight, pack_deconv_weight_dgrad, unpack_deconv_weight
+
+BF16 = torch.bfloat16
+EPI_BIAS, EPI_RESID, EPI_POS, EPI_NCHW = _lib.EPI_BIAS_BF16, _lib.EPI_RESID_F32, _lib.EPI_POS_F32, _lib.EPI_NCHW_F32
+
+
+def _wgrad(dy_t, x_t, out):
+    """out [N, K] fp32 += dY^T X, given dY^T [N, M] and X^T [K, M] (the forward GEMM, contraction over the M rows)."""
+    ops.gemm(dy_t, x_t, EPI_RESID, out=out, aux=out)
+
+
+class _Linear:
+    """bf16 operand copies of one nn.Linear: W [out, in] for the forward, W^T [in, out] for the input gradient."""
+
+    def __init__(self, lin):
+        self.w = ops.cast_bf16(lin.weight.detach().reshape(lin.weight.shape[0], -1).contiguous())
+        self.wt = ops.transpose(self.w)
+        self.b = lin.bias.detach() if lin.bias is not None else None
+
+
+def _param_list(model):
+    """(name, parameter) in a fixed order: the inputs of the autograd node."""
+    return [(n, p) for n, p in model.named_parameters()]
+
+
+class _NetworkFn(torch.autograd.Function):
+    """img [N,3,H,W] fp32 (+ every parameter of backbone and head) -> heatmaps [N,K,H/4,W/4] fp32."""
+
+    @staticmethod
+    def forward(ctx, model, img, *params):
+        bb, head = model.backbone, model.keypoint_head
+        if not img.is_cuda:
+            raise _lib.VitposeLibError('forward_train needs CUDA tensors (vitpose_b200 has no CPU path)')
+        if head.num_deconv_layers != 2 or head.final_conv_kernel != 1:
+            raise NotImplementedError('the training step is built for the classic decoder (2 deconv layers, 1x1 conv)')
+        img = img.contiguous().float()
+        n = img.shape[0]
+        D, heads, depth = bb.embed_dim, bb.num_heads, bb.depth
+        hp, wp = bb.patch_embed.patch_shape
+        T, M = hp * wp, n * hp * wp
+        s = {}                                           # saved activations / operands for the backward pass
+        # ---- operands from the current fp32 master parameters
+        pe = _Linear(bb.patch_embed.proj)
+        pos = bb.pos_embed.detach()
+        pos_tok = (pos[0, 1:] + pos[0, :1]).contiguous()
+        blocks = []
+        for blk in bb.blocks:
+            blocks.append(dict(qkv=_Linear(blk.attn.qkv), proj=_Linear(blk.attn.proj), fc1=_Linear(blk.mlp.fc1),
+                               fc2=_Linear(blk.mlp.fc2)))
+        # ---- ViT (vit.py:313-332); DropPath with rate 0 / eval is the identity
+        if bb.drop_path_rate > 0 and bb.training:
+            raise NotImplementedError('drop_path_rate > 0 is not implemented in the training step')
+        patches = ops.im2col_patch16(img, flip=False)
+        b0 = bb.blocks[0]
+        x, xn = ops.gemm_layernorm(patches, pe.w, EPI_POS, pe.b, pos_tok, b0.norm1.weight.detach(),
+                                   b0.norm1.bias.detach(), 1e-6, period=T)
+        acts = []
+        for l, blk in enumerate(bb.blocks):
+            w = blocks[l]
+            a = dict(x_in=x, xn1=xn)
+            qkv = ops.gemm(xn, w['qkv'].w, EPI_BIAS, bias=w['qkv'].b)
+            attn = ops.attention(qkv.view(n, T, 3 * D), heads).view(M, D)
+            x_mid, xn2 = ops.gemm_layernorm(attn, w['proj'].w, EPI_RESID, w['proj'].b, x, blk.norm2.weight.detach(),
+                                            blk.norm2.bias.detach(), 1e-6)
+            pre = ops.gemm(xn2, w['fc1'].w, EPI_BIAS, bias=w['fc1'].b)
+            h = ops.gelu_fwd(pre)
+            nxt = bb.blocks[l + 1].norm1 if l + 1 < depth else bb.last_norm
+            x, xn = ops.gemm_layernorm(h, w['fc2'].w, EPI_RESID, w['fc2'].b, x_mid, nxt.weight.detach(),
+                                       nxt.bias.detach(), 1e-6)
+            a.update(qkv=qkv, attn=attn, x_mid=x_mid, xn2=xn2, pre=pre, h=h)
+            acts.append(a)
+        s.update(patches=patches, acts=acts, x_final=x, blocks=blocks, pe=pe)
+        # ---- head (simple_head.py:197-202), BatchNorm2d in training mode
+        feat = xn.view(n, hp, wp, D)
+        cur, hs = feat, []
+        for i in range(2):
+            dw = head.deconv_layers[3 * i].weight.detach()
+            bn = head.deconv_layers[3 * i + 1]
+            wp_ = pack_deconv_weight(dw)
+            raw = ops.deconv4x4s2_raw(cur, wp_)
+            if bn.training:
+                mean, rstd = ops.bn_train_stats(raw, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
+                bn.num_batches_tracked += 1
+            else:
+                mean, rstd = bn.running_mean.detach().clone(), torch.rsqrt(bn.running_var.detach() + bn.eps)
+            act = ops.bn_relu_fwd(raw, mean, rstd, bn.weight.detach(), bn.bias.detach())
+            hs.append(dict(x=cur, wp=wp_, raw=raw, mean=mean, rstd=rstd, bn=bn, frozen_stats=not bn.training))
+            cur = act
+        fl = head.final_layer
+        K = fl.weight.shape[0]
+        wf = ops.cast_bf16(fl.weight.detach().reshape(K, -1).contiguous())
+        P = cur.shape[1] * cur.shape[2]
+        hm = ops.gemm(cur.view(n * P, -1), wf, EPI_NCHW, bias=fl.bias.detach(), period=P)
+        s.update(head=hs, act_last=cur, wf=wf, K=K, P=P, n=n, T=T, M=M, D=D, heads=heads, hw=(hp, wp))
+        ctx.s, ctx.model, ctx.names = s, model, [nm for nm, _ in _param_list(model)]
+        return hm.view(n, K, cur.shape[1], cur.shape[2])
+
+    @staticmethod
+    def backward(ctx, dhm):
+        s, model = ctx.s, ctx.model
+        bb, head = model.backbone, model.keypoint_head
+        n, T, M, D, heads, K, P = s['n'], s['T'], s['M'], s['D'], s['heads'], s['K'], s['P']
+        dev = dhm.device
+        g = {}                                           # parameter name -> fp32 gradient
+
+        def zeros(*shape):
+            return torch.zeros(*shape, device=dev, dtype=torch.float32)
+
+        # ---- final 1x1 conv: rows = pixels, columns = keypoints (zero padded to a multiple of 8)
+        Kp = (K + 7) // 8 * 8
+        dy = ops.nchw_to_rows(dhm.contiguous().float().view(n, K, P), Kp)                # [n*P, Kp]
+        act = s['act_last'].view(n * P, -1)
+        C = act.shape[1]
+        dwf = zeros(Kp, C)
+        _wgrad(ops.transpose(dy), ops.transpose(act), dwf)
+        dbf = zeros(Kp)
+        ops.colsum_accumulate(dy, dbf)
+        g['keypoint_head.final_layer.weight'] = dwf[:K].reshape(K, C, 1, 1)
+        g['keypoint_head.final_layer.bias'] = dbf[:K]
+        wf_pad = torch.zeros(Kp, C, device=dev, dtype=BF16)
+        wf_pad[:K] = s['wf']
+        dact = ops.gemm(dy, ops.transpose(wf_pad), EPI_BIAS)                             # [n*P, C]
+        # ---- [ConvTranspose2d -> BatchNorm2d(train) -> ReLU] x 2, last to first
+        for i in (1, 0):
+            hsi = s['head'][i]
+            bn, raw, xin, wp_ = hsi['bn'], hsi['raw'], hsi['x'], hsi['wp']
+            cout = raw.shape[-1]
+            dgam, dbet = zeros(cout), zeros(cout)
+            if hsi['frozen_stats']:
+                raise NotImplementedError('BatchNorm in eval mode inside forward_train is not implemented')
+            draw = ops.bn_relu_bwd(raw, dact.view(raw.shape), hsi['mean'], hsi['rstd'], bn.weight.detach(),
+                                   bn.bias.detach(), dgam, dbet)
+            g[f'keypoint_head.deconv_layers.{3 * i + 1}.weight'] = dgam
+            g[f'keypoint_head.deconv_layers.{3 * i + 1}.bias'] = dbet
+            a_t = ops.transpose(ops.deconv_phase_dy(draw), batch=4)                      # [4, cout, pixels]
+            b_t = ops.transpose(ops.deconv_gather_x(xin), batch=4)                       # [4, 4*cin, pixels]
+            dwp = zeros(4, cout, wp_.shape[2])
+            for ph in range(4):
+                _wgrad(a_t[ph], b_t[ph], dwp[ph])
+            g[f'keypoint_head.deconv_layers.{3 * i}.weight'] = unpack_deconv_weight(dwp)
+            del a_t, b_t
+            dact = ops.gemm(ops.deconv_gather_dy(draw), pack_deconv_weight_dgrad(wp_), EPI_BIAS)   # [pixels_in, cin]
+        # ---- last_norm, then the blocks in reverse
+        dx = zeros(M, D)
+        ln = bb.last_norm
+        dg_, db_ = zeros(D), zeros(D)
+        ops.layernorm_bwd(s['x_final'], ln.weight.detach(), dact, dx, dg_, db_, 1e-6)
+        g['backbone.last_norm.weight'], g['backbone.last_norm.bias'] = dg_, db_
+
+        def linear_bwd(name, lin, dy_bf16, x_bf16, want_dx=True):
+            """gradients of y = x W^T + b given dy: dW, db into g[...]; returns dx (bf16)."""
+            dw, dbias = zeros(*lin.w.shape), zeros(lin.w.shape[0])
+            _wgrad(ops.transpose(dy_bf16), ops.transpose(x_bf16), dw)
+            ops.colsum_accumulate(dy_bf16, dbias)
+            g[name + '.weight'], g[name + '.bias'] = dw, dbias
+            return ops.gemm(dy_bf16, lin.wt, EPI_BIAS) if want_dx else None
+
+        for l in range(len(bb.blocks) - 1, -1, -1):
+            a, w, blk = s['acts'][l], s['blocks'][l], bb.blocks[l]
+            pfx = f'backbone.blocks.{l}.'
+            # x_out = x_mid + fc2(gelu(fc1(norm2(x_mid))))            (vit.py:139)
+            dyb = ops.cast_bf16(dx)
+            dh = linear_bwd(pfx + 'mlp.fc2', w['fc2'], dyb, a['h'])
+            dpre = ops.gelu_bwd(a['pre'], dh)
+            dxn2 = linear_bwd(pfx + 'mlp.fc1', w['fc1'], dpre, a['xn2'])
+            dg_, db_ = zeros(D), zeros(D)
+            ops.layernorm_bwd(a['x_mid'], blk.norm2.weight.detach(), dxn2, dx, dg_, db_, 1e-6)
+            g[pfx + 'norm2.weight'], g[pfx + 'norm2.bias'] = dg_, db_
+            # x_mid = x_in + proj(attention(qkv(norm1(x_in))))        (vit.py:138)
+            dyb = ops.cast_bf16(dx)
+            dattn = linear_bwd(pfx + 'attn.proj', w['proj'], dyb, a['attn'])
+            dqkv = ops.attention_bwd(a['qkv'].view(n, T, 3 * D), a['attn'].view(n, T, D), dattn.view(n, T, D), heads)
+            dxn1 = linear_bwd(pfx + 'attn.qkv', w['qkv'], dqkv.view(M, 3 * D), a['xn1'])
+            dg_, db_ = zeros(D), zeros(D)
+            ops.layernorm_bwd(a['x_in'], blk.norm1.weight.detach(), dxn1, dx, dg_, db_, 1e-6)
+            g[pfx + 'norm1.weight'], g[pfx + 'norm1.bias'] = dg_, db_
+            s['acts'][l] = None                               # activations of this block are dead
+        # ---- patch embed (vit.py:159-165) + pos embed (vit.py:320)
+        dyb = ops.cast_bf16(dx)
+        linear_bwd('backbone.patch_embed.proj', s['pe'], dyb, s['patches'], want_dx=False)
+        g['backbone.patch_embed.proj.weight'] = g['backbone.patch_embed.proj.weight'].view(
+            bb.patch_embed.proj.weight.shape)
+        dpos_tok = zeros(T * D)
+        ops.colsum_accumulate(dx.view(n, T * D), dpos_tok)                 # sum over the crops
+        dcls = zeros(D)
+        ops.colsum_accumulate(dpos_tok.view(T, D), dcls)                   # the cls slot is added to every token
+        dpos = torch.empty(1, T + 1, D, device=dev, dtype=torch.float32)
+        dpos[0, 0] = dcls
+        dpos[0, 1:] = dpos_tok.view(T, D)
+        g['backbone.pos_embed'] = dpos
+        ctx.s = None
+        grads = []
+        for nm, p in _param_list(model):
+            gr = g.get(nm) if p.requires_grad else None
+            grads.append(gr.reshape(p.shape) if gr is not None else None)
+        return (None, None, *grads)
+
+
+def network_heatmaps_train(model, img):
+    """Differentiable forward of backbone + head for ``TopDown.forward_train``."""
+    params = [p for _, p in _param_list(model)]
+    return _NetworkFn.apply(model, img, *params)
