@@ -112,6 +112,120 @@ def run_reference(args, cfg, K):
     print(json.dumps(line))
 
 
+TRAIN_METRIC = 'crops/sec ViTPose-B training step (forward_train + backward + grad all-reduce + layer-decay AdamW) 256x192'
+
+
+def run_train(args, cfg, K):
+    """BASELINE.json configs[4]: one step = TopDown.forward_train -> loss.backward() -> gradient all-reduce (NCCL,
+    N > 1) -> grad-norm clip + layer-decay AdamW, per-GPU batch fixed (weak scaling)."""
+    import torch.distributed as dist
+    import vitpose_b200 as V
+    from vitpose_b200 import _lib, parallel
+    from vitpose_b200.optim import LayerDecayOptimizerConstructor
+
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    n = args.crops
+    cfg['backbone']['drop_path_rate'] = 0.0
+    sd = synthetic.scaled_init_state_dict(cfg, 0)
+    model = V.build_posenet(cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    params = [p for p in model.parameters()]
+    opt = LayerDecayOptimizerConstructor(dict(type='AdamW', lr=5e-4, betas=(0.9, 0.999), weight_decay=0.1),
+                                         dict(num_layers=cfg['backbone']['depth'], layer_decay_rate=0.75))(model)
+    g = torch.Generator().manual_seed(rank)
+
+    def make_batch(seed):
+        img = synthetic.synthetic_crops(n, seed=seed)
+        ys, xs = torch.meshgrid(torch.arange(64.), torch.arange(48.), indexing='ij')
+        cx, cy = torch.rand(n, K, generator=g) * 47, torch.rand(n, K, generator=g) * 63
+        tgt = torch.exp(-((xs - cx[..., None, None]) ** 2 + (ys - cy[..., None, None]) ** 2) / 8.0)
+        return img.pin_memory(), tgt.contiguous().pin_memory(), torch.ones(n, K, 1).pin_memory()
+
+    host = [make_batch(rank * 7 + i) for i in range(2)]
+    devb = [tuple(t.to(dev) for t in h) for h in host]
+
+    def step(batch):
+        out = model.train_step(dict(img=batch[0], target=batch[1], target_weight=batch[2], img_metas=None), opt)
+        opt.zero_grad(set_to_none=True)
+        out['loss'].backward()
+        parallel.allreduce_gradients(params)
+        opt.step(max_norm=1.0)
+        return out['loss']
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(devb[i & 1])
+    barrier()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    calls0 = _lib.ABI_CALLS[0]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        loss = step(devb[i & 1])
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    calls = _lib.ABI_CALLS[0] - calls0
+    clocks = sampler.stop() if rank == 0 else None
+    # end to end: pinned host batch -> device every step, loss value back on the host
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        hb = host[i & 1]
+        loss = step(tuple(t.to(dev, non_blocking=True) for t in hb))
+        loss_host = loss.item()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+    if rank == 0:
+        pk = peaks()
+        total = n * world
+        value = total / (ms / 1e3)
+        gf = GFLOP_PER_CROP[args.workload] * 3          # forward + dgrad + wgrad
+        tf = value * gf / 1e3 / world
+        line = dict(metric=TRAIN_METRIC, value=value, unit='crops/s', n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='bf16', data='synthetic',
+                    config=dict(workload=args.workload + '-train', crops_per_gpu=n, global_crops=total,
+                                optimizer='AdamW lr 5e-4 wd 0.1, layer decay 0.75, grad clip 1.0', drop_path=0.0,
+                                parallelism=f'dp{world}', collective='gradient all-reduce (NCCL)' if world > 1 else None,
+                                l2='activations per step >> 126 MB L2; inputs ping-pong between two buffers'),
+                    roofline=dict(bound='tensor', kernel='whole training step (3 x forward GEMM FLOPs)', achieved=tf,
+                                  peak=pk['tf_sustained'], unit='TFLOP/s', frac=tf / pk['tf_sustained'], traffic=None,
+                                  peak_source=f"{pk['source']} sustained bf16"),
+                    clocks=clocks, gpu_launches=int(calls), final_loss=loss_host,
+                    e2e=dict(value=total / (e2e_ms / 1e3), unit='crops/s',
+                             h2d_bytes_per_step=int(sum(t.numel() * 4 for t in host[0])), d2h_bytes_per_step=4,
+                             ms_per_step=e2e_ms, api='TopDown.train_step + loss.backward() + LayerDecayAdamW.step'))
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -121,6 +235,7 @@ def main():
     ap.add_argument('--workload', default='B-classic-17', choices=sorted(configs.BASELINE_CONFIGS))
     ap.add_argument('--crops', type=int, default=0, help='crops per GPU per step (default: BASELINE batch)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--train', action='store_true', help='measure the training step (BASELINE configs[4]) instead')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.crops <= 0:
@@ -129,6 +244,11 @@ def main():
     K = cfg['keypoint_head']['out_channels']
     if args.impl == 'reference':
         run_reference(args, cfg, K)
+        return
+    if args.train:
+        if args.crops == DEFAULT_CROPS[args.workload]:
+            args.crops = 64                      # per-GPU batch of the upstream training logs
+        run_train(args, cfg, K)
         return
 
     import torch.distributed as dist

@@ -135,7 +135,9 @@ enum {
   VPB_EPI_GELU_BF16 = 1,  /* out bf16 [M,ldo]  = gelu_erf(A.B^T + bias)               (mlp.fc1 + nn.GELU)   */
   VPB_EPI_RESID_F32 = 2,  /* out fp32 [M,ldo]  = aux[M,ldo] + A.B^T + bias            (attn.proj / mlp.fc2 + residual) */
   VPB_EPI_POS_F32 = 3,    /* out fp32 [M,ldo]  = A.B^T + bias + aux[row % period, N]  (patch embed + pos embed) */
-  VPB_EPI_NCHW_F32 = 4    /* out fp32 [M/period, N, period] = A.B^T + bias            (final 1x1 conv)      */
+  VPB_EPI_NCHW_F32 = 4,   /* out fp32 [M/period, N, period] = A.B^T + bias            (final 1x1 conv)      */
+  VPB_EPI_ACCUM_F32 = 10  /* out fp32 [M,ldo] += A.B^T, K split over CTAs (atomic adds; bias must be NULL): weight
+                             gradients dW += dY^T X, where M x N is small and K is every token of the batch    */
 };
 /* C = A[M,K] (bf16, row-major) x B[N,K]^T (bf16, row-major) on tcgen05 tensor cores. max_ctas <= 0: one per SM. */
 int vpb_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, void* out,
@@ -168,7 +170,7 @@ int vpb_tokens_to_nchw_f32(const void* tokens, float* out, int n, int T, int D, 
  * operators that replace the autograd nodes of the path's modules. The tensor-core work of the backward pass is
  * vpb_gemm_bf16 itself on transposed operands:
  *   dgrad  dX[M,K] = dY[M,N] . W[N,K]   = vpb_gemm_bf16(A = dY, B = W^T [K,N], VPB_EPI_BIAS_BF16 / _RESID_F32)
- *   wgrad  dW[N,K] += dY^T . X          = vpb_gemm_bf16(A = dY^T [N,M], B = X^T [K,M], VPB_EPI_RESID_F32, aux = out = dW)
+ *   wgrad  dW[N,K] += dY^T . X          = vpb_gemm_bf16(A = dY^T [N,M], B = X^T [K,M], VPB_EPI_ACCUM_F32, out = dW)
  * All matrices row-major; bf16 unless stated; gradients of parameters are fp32 and ACCUMULATED into their buffers. */
 int vpb_transpose_bf16(const void* in, void* out, int R, int C, int batch, void* stream);   /* out[b][C,R] = in[b][R,C]^T */
 int vpb_cast_f32_bf16(const float* in, void* out, long long n, void* stream);

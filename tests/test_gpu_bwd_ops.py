@@ -107,6 +107,12 @@ def test_linear_dgrad_wgrad_as_gemms():
     dw = torch.ones(N, K, device=_dev())
     ops.gemm(ops.transpose(dy), ops.transpose(x), _lib.EPI_RESID_F32, out=dw, aux=dw)
     _close('wgrad', dw, 1 + dy.float().t() @ x.float(), 2e-3)
+    # split-K accumulation (the form the training step uses), incl. a narrow output and a ragged K split
+    for (n_, k_, m_) in ((N, K, M), (24, 256, 192 * 13), (256, 1024, 192 * 37)):
+        x2, dy2 = _rand((m_, k_), 16), _rand((m_, n_), 17)
+        dw2 = torch.ones(n_, k_, device=_dev())
+        ops.gemm(ops.transpose(dy2), ops.transpose(x2), _lib.EPI_ACCUM_F32, out=dw2)
+        _close(f'wgrad split-K {n_}x{k_}x{m_}', dw2, 1 + dy2.float().t() @ x2.float(), 2e-3)
 
 
 def test_bn_train_relu_fwd_bwd():
@@ -155,6 +161,6 @@ def test_deconv_fwd_bwd(n, h, w, cin, cout):
     b = ops.transpose(ops.deconv_gather_x(x), batch=4)         # [4, 4*cin, pixels]
     dwp = torch.zeros(4, cout, 4 * cin, device=_dev())
     for ph in range(4):
-        ops.gemm(a[ph], b[ph], _lib.EPI_RESID_F32, out=dwp[ph], aux=dwp[ph])
+        ops.gemm(a[ph], b[ph], _lib.EPI_ACCUM_F32, out=dwp[ph])
     ref = pack_deconv_weight(wr.grad)          # same re-layout applied to the reference gradient (fp32 in, bf16 out)
     _close('deconv wgrad', dwp, ref, 1e-2)

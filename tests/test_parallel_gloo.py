@@ -57,3 +57,37 @@ def test_single_process_passthrough():
     assert torch.equal(parallel.gather_strided(x, 3), x[:3])
     assert torch.equal(parallel.gather_contiguous(x), x)
     assert parallel.contiguous_shard(10, 1, 4) == (2, 5)
+
+
+def _grad_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)                               # identical replicas
+        params = [torch.nn.Parameter(torch.randn(s)) for s in [(5, 7), (3,), (2, 2, 2), (11,)]]
+        g = torch.Generator().manual_seed(100 + rank)      # rank-specific gradients
+        for p in params:
+            p.grad = torch.randn(p.shape, generator=g)
+        params[1].grad = None if False else params[1].grad
+        ncoll = parallel.allreduce_gradients(params, bucket_bytes=100)   # tiny buckets: several collectives
+        torch.save(dict(grads=[p.grad.clone() for p in params], ncoll=ncoll), os.path.join(out_dir, f'g{rank}.pt'))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_gradients_world2(tmp_path):
+    world = 2
+    mp.spawn(_grad_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    shapes = [(5, 7), (3,), (2, 2, 2), (11,)]
+    expect = []
+    for shp in shapes:
+        expect.append(torch.zeros(shp))
+    for r in range(world):
+        g = torch.Generator().manual_seed(100 + r)
+        for i, shp in enumerate(shapes):
+            expect[i] += torch.randn(shp, generator=g) / world
+    for r in range(world):
+        d = torch.load(os.path.join(str(tmp_path), f'g{r}.pt'))
+        assert d['ncoll'] >= 2
+        for got, exp in zip(d['grads'], expect):
+            assert torch.allclose(got, exp, atol=1e-6)

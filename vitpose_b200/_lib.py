@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, 'libvitpose_b200.so')
 c_void_p, c_int, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
 
 EPI_BIAS_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_POS_F32, EPI_NCHW_F32 = range(5)
+EPI_ACCUM_F32 = 10
 DECODE_NONE, DECODE_DEFAULT, DECODE_UNBIASED, DECODE_UDP_DARK = range(4)
 
 
@@ -122,7 +123,11 @@ def lib():
     return L
 
 
+ABI_CALLS = [0]     # C-ABI calls that returned through check() (each launches at least one kernel)
+
+
 def check(code, what):
+    ABI_CALLS[0] += 1
     if code != 0:
         msg = lib().vpb_last_error().decode('utf-8', 'replace')
         raise VitposeLibError(f'{what} failed ({code}): {msg}')

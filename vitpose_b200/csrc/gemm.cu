@@ -17,7 +17,7 @@ static int launch_gemm_inst(const GemmMaps& maps, const GemmParams& p, int max_c
   }
   const int m_tiles = (p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
   const int n_tiles = (p.N + BN - 1) / BN;
-  int grid = m_tiles * n_tiles * CG;
+  int grid = m_tiles * n_tiles * CG * p.ksplit;
   int cap = max_ctas > 0 ? max_ctas : sm_count();
   cap -= cap % CG;
   if (cap < CG) cap = CG;
@@ -140,6 +140,9 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue,
   VPB_GEMM_CASE(256, EPI_POSTMA_LNS_F32)
   VPB_GEMM_CASE(128, EPI_POSTMA_LNS_F32)
   VPB_GEMM_CASE(64, EPI_POSTMA_LNS_F32)
+  VPB_GEMM_CASE(256, EPI_ACCUM_F32)
+  VPB_GEMM_CASE(128, EPI_ACCUM_F32)
+  VPB_GEMM_CASE(64, EPI_ACCUM_F32)
   VPB_GEMM_CASE(256, EPI_POS_F32)
   VPB_GEMM_CASE(128, EPI_POS_F32)
   VPB_GEMM_CASE(64, EPI_POS_F32)
@@ -170,7 +173,18 @@ int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, c
   const int cg = gemm_pick_cg(M, bn, epilogue, K);
   GemmMaps maps;
   if (make_gemm_maps(&maps, A, B, M, N, K, K, K, bn, epilogue, out, ldo, aux, cg, period)) return -1;
-  GemmParams p{M, N, K, bias, out, ldo, aux, period, nullptr, nullptr, nullptr, 0, 0u, 0.0f};
+  GemmParams p{M, N, K, bias, out, ldo, aux, period, 1, nullptr, nullptr, nullptr, 0, 0u, 0.0f};
+  if (epilogue == EPI_ACCUM_F32) {
+    VPB_REQUIRE(bias == nullptr && ldo % 4 == 0, "gemm: the accumulating epilogue takes no bias and needs ldo %% 4 == 0");
+    // about two waves of CTAs, at least 8 K blocks (512 rows of the contraction) per split, every split non-empty
+    const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + bn - 1) / bn);
+    const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+    int want = (2 * sm_count() + tiles - 1) / tiles;
+    if (want > k_blocks / 8) want = k_blocks / 8;
+    if (want < 1) want = 1;
+    const int kb_per = (k_blocks + want - 1) / want;
+    p.ksplit = (k_blocks + kb_per - 1) / kb_per;
+  }
   return launch_gemm(maps, p, bn, epilogue, cg, max_ctas, stream);
 }
 
@@ -232,7 +246,7 @@ int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue
   uint32_t box_o[2] = {64u, GEMM_BM};
   if (make_tma_desc(&maps.ln, TMA_BF16, xn, 2, dims_o, str_o, box_o, TMA_SWIZZLE_128B)) return -1;
   VPB_REQUIRE(N / bn <= 10, "gemm+layernorm: at most 10 column tiles per row (N=%d)", N);
-  GemmParams p{M, N, K, bias, out, N, aux, period, gamma, beta, reinterpret_cast<unsigned long long*>(scratch),
+  GemmParams p{M, N, K, bias, out, N, aux, period, 1, gamma, beta, reinterpret_cast<unsigned long long*>(scratch),
                ln_region_words(M, N), epoch, eps};
   return launch_gemm(maps, p, bn, epi, cg, max_ctas, stream);
 }

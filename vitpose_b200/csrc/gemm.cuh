@@ -27,6 +27,9 @@ enum GemmEpilogue {
   // 3 operand stages, a deep residual ring, and the normalise pass on its own warpgroup (see gemm_ln_split)
   EPI_RESID_LNS_F32 = 8,
   EPI_POSTMA_LNS_F32 = 9,
+  // out fp32 [M, ldo] += A.B^T with the K range of every tile split over `ksplit` CTAs that accumulate with vector
+  // atomics: weight gradients (small M x N, K = all tokens of the batch) would otherwise occupy a few SMs
+  EPI_ACCUM_F32 = 10,
 };
 __host__ __device__ constexpr bool gemm_epi_ln(int epi) { return epi >= EPI_RESID_LN_F32 && epi <= EPI_POSTMA_LNS_F32; }
 __host__ __device__ constexpr bool gemm_epi_pos(int epi) {
@@ -44,6 +47,7 @@ struct GemmParams {
   int ldo;             // leading dimension of out / aux in elements
   const float* aux;    // residual or positional table
   int period;          // tokens per crop (EPI_POS) / pixels per crop (EPI_NCHW)
+  int ksplit;          // EPI_ACCUM_F32: CTAs per output tile (>= 1); 1 for every other epilogue
   // fused LayerNorm (EPI_*_LN_F32): affine parameters [N] and the per-row partial statistics (mean, M2 of a tile's
   // BN columns, one 8-byte word each) that the CTAs owning the n-tiles of one row block exchange through global
   // memory. Launch e of a sequence writes region e & 1 and tags its words with bit (e >> 1) & 1 in the sign of M2,
@@ -240,8 +244,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int lane = threadIdx.x & 31;
   const int m_tiles = (p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);   // (pairs of) 128-row blocks
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
+  const int num_tiles = m_tiles * n_tiles * p.ksplit;
   const int k_blocks = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int kb_per = (k_blocks + p.ksplit - 1) / p.ksplit;   // K blocks per split (the host makes every split non-empty)
   const int cta_rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
   const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;     // both CTAs of a pair walk the same tiles
 
@@ -282,9 +287,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int m_blk = (tile / n_tiles) * CG + cta_rank;
-        const int n_blk = tile % n_tiles;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int m_blk = ((tile / p.ksplit) / n_tiles) * CG + cta_rank;
+        const int n_blk = (tile / p.ksplit) % n_tiles;
+        const int kb0 = (tile % p.ksplit) * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
@@ -313,7 +319,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int kb0 = (tile % p.ksplit) * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
@@ -322,10 +329,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             if constexpr (CG == 2)
               umma_bf16_ss_pair(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), IDESC,
-                                (kb | k) != 0 ? 1u : 0u);
+                                (kb > kb0 || k != 0) ? 1u : 0u);
             else
               umma_bf16_ss(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), IDESC,
-                           (kb | k) != 0 ? 1u : 0u);
+                           (kb > kb0 || k != 0) ? 1u : 0u);
           }
           // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
           if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage], 3);
@@ -347,8 +354,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint8_t* ring = s_out + tg * RING_BYTES;
       uint32_t seq = 0;
       for (int tile = tile0 + tg * tile_step; tile < num_tiles; tile += tile_step * TG) {
-        const int m_blk = (tile / n_tiles) * CG + cta_rank;
-        const int n_blk = tile % n_tiles;
+        const int m_blk = ((tile / p.ksplit) / n_tiles) * CG + cta_rank;
+        const int n_blk = (tile / p.ksplit) % n_tiles;
         for (int c = 0; c < BN / 32; ++c, ++seq) {
           const uint32_t slot = seq % RES_SLOTS;
           mbar_wait(&res_empty[tg][slot], ((seq / RES_SLOTS) & 1) ^ 1);
@@ -398,8 +405,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint32_t chunk_seq = 0;                // running chunk counter of this group: staging buffer = chunk_seq & 1
     int const_n_blk = -1;                  // n-tile whose bias / gamma / beta columns are in shared memory
     for (int tile = tile0 + (LN_SPLIT ? grp : 0) * tile_step; tile < num_tiles; tile += tile_step * TG) {
-      const int m_blk = (tile / n_tiles) * CG + cta_rank;
-      const int n_blk = tile % n_tiles;
+      const int m_blk = ((tile / p.ksplit) / n_tiles) * CG + cta_rank;
+      const int n_blk = (tile / p.ksplit) % n_tiles;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
 
       if constexpr (STAGED) {
@@ -639,7 +646,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               for (int j = 0; j < 16; ++j)
                 if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
             }
-            if constexpr (EPI == EPI_POS_F32) {
+            if constexpr (EPI == EPI_ACCUM_F32) {
+              float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
+              if (ncols == 16) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * j), "f"(v[4 * j]),
+                               "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                               : "memory");
+              } else {
+                for (int j = 0; j < ncols; ++j) atomicAdd(o + j, v[j]);
+              }
+            } else if constexpr (EPI == EPI_POS_F32) {
               const float* a = p.aux + static_cast<size_t>(row % p.period) * p.N + col0;
               float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
               if (ncols == 16) {

@@ -318,15 +318,32 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       o[i * 32 + lane] = a;
     }
   }
-  if (row0 < M) {
+  // block-level reduction of the per-warp dgamma / dbeta partials, then one atomic per column per block
+  __shared__ float red[2][D];
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int w = 0; w < nwarps; ++w) {
+    if (warp == w) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      atomicAdd(dgamma + c + 0, dg[i].x); atomicAdd(dgamma + c + 1, dg[i].y);
-      atomicAdd(dgamma + c + 2, dg[i].z); atomicAdd(dgamma + c + 3, dg[i].w);
-      atomicAdd(dbeta + c + 0, db[i].x); atomicAdd(dbeta + c + 1, db[i].y);
-      atomicAdd(dbeta + c + 2, db[i].z); atomicAdd(dbeta + c + 3, db[i].w);
+      for (int i = 0; i < NV; ++i) {
+        float4* rg = reinterpret_cast<float4*>(&red[0][0]) + i * 32 + lane;
+        float4* rb = reinterpret_cast<float4*>(&red[1][0]) + i * 32 + lane;
+        if (w == 0) {
+          *rg = dg[i];
+          *rb = db[i];
+        } else {
+          float4 a = *rg, c = *rb;
+          a.x += dg[i].x; a.y += dg[i].y; a.z += dg[i].z; a.w += dg[i].w;
+          c.x += db[i].x; c.y += db[i].y; c.z += db[i].z; c.w += db[i].w;
+          *rg = a;
+          *rb = c;
+        }
+      }
     }
+    __syncthreads();
+  }
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    atomicAdd(dgamma + c, red[0][c]);
+    atomicAdd(dbeta + c, red[1][c]);
   }
 }
 
@@ -334,7 +351,9 @@ int layernorm_bwd(const float* x, const float* gamma, const void* dy, float* dx_
                   int M, int D, float eps, cudaStream_t stream) {
   VPB_REQUIRE(M > 0 && D > 0 && D % 128 == 0, "layernorm_bwd: D=%d must be a multiple of 128", D);
   const int warps = 8;
-  int rows_per_warp = (M + 8 * sm_count() * warps - 1) / (8 * sm_count() * warps);
+  // two blocks per SM: enough warps to stream at HBM speed, few enough blocks that the parameter-gradient atomics
+  // (one per column per block) stay negligible
+  int rows_per_warp = (M + 2 * sm_count() * warps - 1) / (2 * sm_count() * warps);
   if (rows_per_warp < 1) rows_per_warp = 1;
   const int total_warps = (M + rows_per_warp - 1) / rows_per_warp;
   dim3 grid((total_warps + warps - 1) / warps), block(warps * 32);

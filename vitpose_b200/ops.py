@@ -27,6 +27,9 @@ def gemm(a, b, epilogue, bias=None, out=None, aux=None, period=0, max_ctas=0):
     elif epilogue in (_lib.EPI_RESID_F32, _lib.EPI_POS_F32):
         out = torch.empty(M, N, device=a.device, dtype=torch.float32) if out is None else out
         ldo = out.stride(0)
+    elif epilogue == _lib.EPI_ACCUM_F32:
+        assert out is not None and out.dtype == torch.float32 and bias is None, 'accumulates into an existing fp32 out'
+        ldo = out.stride(0)
     elif epilogue == _lib.EPI_NCHW_F32:
         assert M % period == 0
         out = torch.empty(M // period, N, period, device=a.device, dtype=torch.float32) if out is None else out

@@ -11,6 +11,10 @@ no data-path collective. The only exchange is the gather of per-crop results at 
   ``all_gather`` instead of two all_gathers of pickled, max-padded byte blobs;
 * ``gather_contiguous`` — concatenation in rank order.
 
+Training: the one real exchange step of the path is the gradient all-reduce —
+``allreduce_gradients`` averages ``.grad`` of the replicated parameters over the ranks in a few large flat
+buckets (what mmcv's DDP wrapper does for the reference, one NCCL all-reduce per bucket over NVLink/NVSwitch).
+
 Works with any torch.distributed backend: NCCL over NVLink on the B200 box, gloo in the CPU tests.
 """
 import torch
@@ -69,3 +73,32 @@ def gather_contiguous(local, counts=None):
     pad[:local.shape[0]] = local
     parts = _all_gather_equal(pad)
     return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+def allreduce_gradients(params, bucket_bytes=256 << 20):
+    """Average ``p.grad`` over all ranks, in place. Gradients are packed into flat fp32 buckets of about
+    ``bucket_bytes`` (parameter order), each reduced with one all_reduce(SUM) and scaled by 1/world.
+    Every rank must pass the same parameters in the same order. Returns the number of collectives issued."""
+    rank, world = world_info()
+    grads = [p.grad for p in params if p.grad is not None]
+    if world == 1 or not grads:
+        return 0
+    buckets, cur, size = [], [], 0
+    for g in grads:
+        nbytes = g.numel() * g.element_size()
+        if cur and size + nbytes > bucket_bytes:
+            buckets.append(cur)
+            cur, size = [], 0
+        cur.append(g)
+        size += nbytes
+    if cur:
+        buckets.append(cur)
+    for b in buckets:
+        flat = torch.cat([g.reshape(-1) for g in b])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(world)
+        off = 0
+        for g in b:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+    return len(buckets)

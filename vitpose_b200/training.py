@@ -23,8 +23,9 @@ EPI_BIAS, EPI_RESID, EPI_POS, EPI_NCHW = _lib.EPI_BIAS_BF16, _lib.EPI_RESID_F32,
 
 
 def _wgrad(dy_t, x_t, out):
-    """out [N, K] fp32 += dY^T X, given dY^T [N, M] and X^T [K, M] (the forward GEMM, contraction over the M rows)."""
-    ops.gemm(dy_t, x_t, EPI_RESID, out=out, aux=out)
+    """out [N, K] fp32 += dY^T X, given dY^T [N, M] and X^T [K, M]: the forward GEMM kernel with the contraction
+    (all M token rows of the batch) split over CTAs, because N x K alone is only a handful of tiles."""
+    ops.gemm(dy_t, x_t, _lib.EPI_ACCUM_F32, out=out)
 
 
 class _Linear:
