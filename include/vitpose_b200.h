@@ -238,6 +238,16 @@ int vpb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
                    float beta1, float beta2, float eps, float weight_decay, int step, const float* sq_norm,
                    float max_norm, void* stream);
 
+/* Multi-tensor form: one call updates every parameter (and computes the clip norm first when sq_norm != NULL).
+ * entries: DEVICE array of n descriptors; chunk_start: DEVICE int[n+1], prefix sum of ceil(n_i / 4096);
+ * total_chunks = chunk_start[n]. `step` is the per-tensor AdamW step count (>= 1) for the bias correction. */
+typedef struct vpb_tensor_entry {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+  long long n; float lr; float weight_decay; int32_t step; int32_t pad_;
+} vpb_tensor_entry;
+int vpb_adamw_multi(const vpb_tensor_entry* entries, const int32_t* chunk_start, int n, int total_chunks, float beta1,
+                    float beta2, float eps, float* sq_norm, float max_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

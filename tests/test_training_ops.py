@@ -95,7 +95,9 @@ def test_joints_mse_loss_kats_and_grad(golden_dir):
 
 
 @pytest.mark.gpu
-def test_layer_decay_adamw_matches_torch():
+@pytest.mark.parametrize('multi', [True, False])
+def test_layer_decay_adamw_matches_torch(multi):
+    """multi: one vpb_adamw_multi launch for all tensors; else the per-tensor vpb_adamw_step path."""
     dev = torch.device('cuda:0')
     torch.manual_seed(0)
     cfg = configs.tiny_model_cfg(5, depth=2)
@@ -113,7 +115,7 @@ def test_layer_decay_adamw_matches_torch():
         for p1, p2 in zip(m1.parameters(), m2.parameters()):
             gr = torch.randn(p1.shape, device=dev, generator=gen) * 0.05
             p1.grad, p2.grad = gr.clone(), gr.clone()
-        total = opt1.step(max_norm=1.0)
+        total = opt1.step(max_norm=1.0) if multi else opt1.step_per_tensor(max_norm=1.0)
         ref_total = torch.nn.utils.clip_grad_norm_(m2.parameters(), 1.0)
         opt2.step()
         assert abs(total.item() - ref_total.item()) / ref_total.item() < 1e-4

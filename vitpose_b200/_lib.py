@@ -85,6 +85,8 @@ _SIGS = {
     'vpb_grad_sq_norm_accumulate': (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p]),
     'vpb_adamw_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_float, c_float, c_float,
                                c_float, c_float, c_int, c_void_p, c_float, c_void_p]),
+    'vpb_adamw_multi': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_void_p, c_float,
+                                c_void_p]),
     'vpb_gemm_bf16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                               c_int, c_int, c_void_p]),
     'vpb_gemm_layernorm_scratch_bytes': (c_size_t, [c_int, c_int]),

@@ -302,6 +302,11 @@ int vpb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
                     as_stream(stream));
 }
 
+int vpb_adamw_multi(const vpb_tensor_entry* entries, const int32_t* chunk_start, int n, int total_chunks, float beta1,
+                    float beta2, float eps, float* sq_norm, float max_norm, void* stream) {
+  return adamw_multi(entries, chunk_start, n, total_chunks, beta1, beta2, eps, sq_norm, max_norm, as_stream(stream));
+}
+
 // ---- backward-pass operators of the training step ----
 int vpb_transpose_bf16(const void* in, void* out, int R, int C, int batch, void* stream) {
   return transpose_bf16(in, out, R, C, batch, as_stream(stream));

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+struct vpb_tensor_entry;
+
 namespace vpb {
 
 struct GemmParams;
@@ -109,5 +111,8 @@ int deconv_gather_dy(const void* dy, void* out, int n, int h, int w, int cout, c
 int deconv_phase_dy(const void* dy, void* out, int n, int h, int w, int cout, cudaStream_t stream);
 int attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, int n, int T, int heads, int hd,
                   float scale, cudaStream_t stream);
+
+int adamw_multi(const vpb_tensor_entry* entries, const int* chunk_start, int n, int total_chunks, float beta1,
+                float beta2, float eps, float* sq_norm, float max_norm, cudaStream_t stream);
 
 }  // namespace vpb

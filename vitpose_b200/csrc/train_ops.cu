@@ -4,6 +4,7 @@
 //   JointsMSELoss.forward      mmpose/models/losses/mse_loss.py:24-45
 //   clip_grad_norm_(max_norm)  mmcv OptimizerHook (grad_clip=dict(max_norm=1.), ViTPose_base_coco_256x192.py:30)
 //   AdamW step                 torch.optim.AdamW as configured at ViTPose_base_coco_256x192.py:16-28
+#include "../../include/vitpose_b200.h"
 #include "host_util.h"
 #include "ops.h"
 
@@ -114,6 +115,83 @@ int adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_s
   if (blocks > cap) blocks = cap;
   adamw_kernel<<<blocks, 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
                                            bc1, bc2_sqrt, sq_norm, max_norm);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- multi-tensor forms: one launch for every parameter of the model -----------------------------------------
+// `entries` (device) describes the tensors; `chunk_start` (device, n+1 ints) is the prefix sum of their chunk counts
+// (a chunk = MT_CHUNK elements = one CTA). A CTA finds its tensor by binary search over chunk_start.
+constexpr int MT_CHUNK = 256 * 16;
+
+__device__ __forceinline__ int mt_find(const int* __restrict__ chunk_start, int n, int chunk) {
+  int lo = 0, hi = n;                       // chunk_start[lo] <= chunk < chunk_start[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (chunk_start[mid] <= chunk) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) sq_norm_multi_kernel(const vpb_tensor_entry* __restrict__ entries,
+                                                            const int* __restrict__ chunk_start, int n,
+                                                            float* __restrict__ out) {
+  const int t = mt_find(chunk_start, n, blockIdx.x);
+  const vpb_tensor_entry e = entries[t];
+  const long long base = static_cast<long long>(blockIdx.x - chunk_start[t]) * MT_CHUNK;
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < MT_CHUNK; k += 256) {
+    const long long i = base + k;
+    if (i < e.n) acc = fmaf(e.grad[i], e.grad[i], acc);
+  }
+  acc = warp_sum(acc);
+  __shared__ float s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < 8 ? s[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const vpb_tensor_entry* __restrict__ entries,
+                                                          const int* __restrict__ chunk_start, int n, float beta1,
+                                                          float beta2, float eps, const float* __restrict__ sq_norm,
+                                                          float max_norm) {
+  const int t = mt_find(chunk_start, n, blockIdx.x);
+  const vpb_tensor_entry e = entries[t];
+  float gs = 1.0f;
+  if (sq_norm != nullptr) {
+    const float coef = max_norm / (sqrtf(*sq_norm) + 1e-6f);
+    gs = coef < 1.0f ? coef : 1.0f;
+  }
+  const float bc1 = 1.0f - powf(beta1, static_cast<float>(e.step));
+  const float bc2_sqrt = sqrtf(1.0f - powf(beta2, static_cast<float>(e.step)));
+  const long long base = static_cast<long long>(blockIdx.x - chunk_start[t]) * MT_CHUNK;
+  for (int k = threadIdx.x; k < MT_CHUNK; k += 256) {
+    const long long i = base + k;
+    if (i >= e.n) break;
+    const float gi = e.grad[i] * gs;
+    const float pi = e.param[i] * (1.0f - e.lr * e.weight_decay);
+    const float mi = beta1 * e.exp_avg[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * e.exp_avg_sq[i] + (1.0f - beta2) * gi * gi;
+    e.exp_avg[i] = mi;
+    e.exp_avg_sq[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    e.param[i] = pi - (e.lr / bc1) * (mi / denom);
+  }
+}
+
+int adamw_multi(const vpb_tensor_entry* entries, const int* chunk_start, int n, int total_chunks, float beta1,
+                float beta2, float eps, float* sq_norm, float max_norm, cudaStream_t stream) {
+  VPB_REQUIRE(n > 0 && total_chunks > 0 && entries && chunk_start, "adamw_multi: empty table");
+  if (sq_norm != nullptr) {
+    VPB_CHECK_CUDA(cudaMemsetAsync(sq_norm, 0, sizeof(float), stream));
+    sq_norm_multi_kernel<<<total_chunks, 256, 0, stream>>>(entries, chunk_start, n, sq_norm);
+    VPB_CHECK_CUDA(cudaGetLastError());
+  }
+  adamw_multi_kernel<<<total_chunks, 256, 0, stream>>>(entries, chunk_start, n, beta1, beta2, eps, sq_norm, max_norm);
   VPB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -79,8 +79,59 @@ class LayerDecayAdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._sq_norm = None
 
+    _ENTRY = [('param', '<u8'), ('grad', '<u8'), ('exp_avg', '<u8'), ('exp_avg_sq', '<u8'), ('n', '<i8'),
+              ('lr', '<f4'), ('weight_decay', '<f4'), ('step', '<i4'), ('pad', '<i4')]     # vpb_tensor_entry
+    _CHUNK = 4096
+
     @torch.no_grad()
     def step(self, max_norm=None):
+        """One multi-tensor launch for the clip norm and one for the update (vpb_adamw_multi): the descriptor table
+        (pointers, sizes, per-group lr / weight decay, step counts) is rebuilt on the host and uploaded each call
+        because autograd hands out fresh gradient tensors every step."""
+        import numpy as np
+        L = lib()
+        items = [(g, p) for g in self.param_groups for p in g['params'] if p.grad is not None]
+        if not items:
+            return None
+        dev = items[0][1].device
+        if dev.type != 'cuda':
+            raise _lib.VitposeLibError('LayerDecayAdamW runs on CUDA parameters only (no CPU fallback)')
+        b1, b2 = self.param_groups[0]['betas']
+        eps = self.param_groups[0]['eps']
+        if any(g['betas'] != (b1, b2) or g['eps'] != eps for g in self.param_groups):
+            raise NotImplementedError('per-group betas / eps')
+        table = np.zeros(len(items), dtype=self._ENTRY)
+        starts = np.zeros(len(items) + 1, dtype=np.int32)
+        keep = []
+        for i, (group, p) in enumerate(items):
+            st = self.state[p]
+            if not st:
+                st['step'] = 0
+                st['exp_avg'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            st['step'] += 1
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            if g.dtype != torch.float32 or p.dtype != torch.float32 or not p.is_contiguous():
+                raise _lib.VitposeLibError('LayerDecayAdamW expects contiguous fp32 parameters and gradients')
+            keep.append(g)
+            table[i] = (p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(), p.numel(),
+                        group['lr'], group['weight_decay'], st['step'], 0)
+            starts[i + 1] = starts[i] + (p.numel() + self._CHUNK - 1) // self._CHUNK
+        d_table = torch.from_numpy(table.view(np.uint8)).to(dev)
+        d_starts = torch.from_numpy(starts).to(dev)
+        sq = None
+        if max_norm is not None:
+            if self._sq_norm is None or self._sq_norm.device != dev:
+                self._sq_norm = torch.zeros(1, device=dev, dtype=torch.float32)
+            sq = self._sq_norm
+        check(L.vpb_adamw_multi(ptr(d_table), ptr(d_starts), len(items), int(starts[-1]), float(b1), float(b2),
+                                float(eps), ptr(sq), float(max_norm) if max_norm is not None else 0.0, stream_ptr()),
+              'vpb_adamw_multi')
+        return torch.sqrt(sq[0]) if sq is not None else None
+
+    @torch.no_grad()
+    def step_per_tensor(self, max_norm=None):
+        """The same update with one vpb_grad_sq_norm_accumulate + vpb_adamw_step call per tensor."""
         L = lib()
         params = [p for g in self.param_groups for p in g['params'] if p.grad is not None]
         if not params:
