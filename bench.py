@@ -157,8 +157,7 @@ def run_train(args, cfg, K):
     def step(batch):
         out = model.train_step(dict(img=batch[0], target=batch[1], target_weight=batch[2], img_metas=None), opt)
         opt.zero_grad(set_to_none=True)
-        out['loss'].backward()
-        parallel.allreduce_gradients(params)
+        out['loss'].backward()          # N > 1: the gradient all-reduce (NCCL) is issued inside, overlapped
         opt.step(max_norm=1.0)
         return out['loss']
 

@@ -192,14 +192,15 @@ int vpb_deconv4x4s2_raw(const void* in, const void* wphase, void* out, int n, in
                         const float* ones, const float* zeros, void* stream);
 /* nn.BatchNorm2d in training mode on NHWC rows [rows, C] (simple_head.py:324-333): batch mean / rstd (biased
  * variance), running statistics updated with `momentum` and the unbiased variance (NULL to skip);
- * scratch = 2*C floats. Then act = relu(bn(raw)), and its backward (dgamma / dbeta fp32 [C] +=). */
+ * scratch = 4*C floats (2*C fp64 accumulators, 8-byte aligned: the unordered atomic sums stay reproducible to the last
+ * fp32 bit). Then act = relu(bn(raw)), and its backward (dgamma / dbeta fp32 [C] +=). */
 int vpb_bn_train_stats(const void* raw, long long rows, int C, float eps, float momentum, float* sum_sumsq_scratch,
                        float* mean, float* rstd, float* running_mean, float* running_var, void* stream);
 int vpb_bn_relu_fwd(const void* raw, void* act, const float* mean, const float* rstd, const float* gamma,
                     const float* beta, long long rows, int C, void* stream);
 int vpb_bn_relu_bwd(const void* raw, const void* dact, void* draw, const float* mean, const float* rstd,
-                    const float* gamma, const float* beta, float* dgamma, float* dbeta, long long rows, int C,
-                    void* stream);
+                    const float* gamma, const float* beta, float* dgamma, float* dbeta, float* scratch /* 6*C floats */,
+                    long long rows, int C, void* stream);
 /* dL/dheatmaps fp32 [n,K,P] -> bf16 rows [n*P, Kp] (zero padded to Kp >= K): operand of the final conv's GEMMs */
 int vpb_nchw_f32_to_rows_bf16(const float* in, void* out, int n, int K, int P, int Kp, void* stream);
 /* Operand gathers for the backward of the 4-phase transposed convolution (layouts in csrc/train_bwd.cu):
@@ -240,7 +241,9 @@ int vpb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
 
 /* Multi-tensor form: one call updates every parameter (and computes the clip norm first when sq_norm != NULL).
  * entries: DEVICE array of n descriptors; chunk_start: DEVICE int[n+1], prefix sum of ceil(n_i / 4096);
- * total_chunks = chunk_start[n]. `step` is the per-tensor AdamW step count (>= 1) for the bias correction. */
+ * total_chunks = chunk_start[n]. `step` is the per-tensor AdamW step count (>= 1) for the bias correction.
+ * sq_norm: NULL (no clipping) or DEVICE float[1 + total_chunks]: [0] receives sum(grad^2), the rest is scratch for the
+ * per-chunk partials, which are added in a fixed order so that all data-parallel replicas clip identically. */
 typedef struct vpb_tensor_entry {
   float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
   long long n; float lr; float weight_decay; int32_t step; int32_t pad_;

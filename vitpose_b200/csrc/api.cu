@@ -339,24 +339,28 @@ int vpb_bn_train_stats(const void* raw, long long rows, int C, float eps, float 
                        float* mean, float* rstd, float* running_mean, float* running_var, void* stream_) {
   cudaStream_t stream = as_stream(stream_);
   VPB_REQUIRE(rows > 0 && rows < (1ll << 31) && C > 0, "bn_train_stats: bad shape");
-  VPB_CHECK_CUDA(cudaMemsetAsync(sum_sumsq_scratch, 0, sizeof(float) * 2 * C, stream));
-  if (int e = colsum_sq_accumulate(raw, static_cast<int>(rows), C, sum_sumsq_scratch, sum_sumsq_scratch + C, stream))
-    return e;
-  return bn_finalize(sum_sumsq_scratch, sum_sumsq_scratch + C, mean, rstd, running_mean, running_var, C, rows, eps,
-                     momentum, stream);
+  VPB_REQUIRE((reinterpret_cast<uintptr_t>(sum_sumsq_scratch) & 7) == 0, "bn_train_stats: scratch must be 8-byte aligned");
+  double* acc = reinterpret_cast<double*>(sum_sumsq_scratch);     // 2*C fp64 accumulators
+  VPB_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, stream));
+  if (int e = colsum_sq_accumulate(raw, static_cast<int>(rows), C, acc, acc + C, stream)) return e;
+  return bn_finalize(acc, acc + C, mean, rstd, running_mean, running_var, C, rows, eps, momentum, stream);
 }
 int vpb_bn_relu_fwd(const void* raw, void* act, const float* mean, const float* rstd, const float* gamma,
                     const float* beta, long long rows, int C, void* stream) {
   return bn_relu_fwd(raw, act, mean, rstd, gamma, beta, rows, C, as_stream(stream));
 }
 int vpb_bn_relu_bwd(const void* raw, const void* dact, void* draw, const float* mean, const float* rstd,
-                    const float* gamma, const float* beta, float* dgamma, float* dbeta, long long rows, int C,
-                    void* stream_) {
+                    const float* gamma, const float* beta, float* dgamma, float* dbeta, float* scratch, long long rows,
+                    int C, void* stream_) {
   cudaStream_t stream = as_stream(stream_);
   VPB_REQUIRE(rows > 0 && rows < (1ll << 31), "bn_relu_bwd: bad shape");
-  if (int e = bn_relu_bwd_reduce(raw, dact, mean, rstd, gamma, beta, static_cast<int>(rows), C, dbeta, dgamma, stream))
+  VPB_REQUIRE(scratch != nullptr && (reinterpret_cast<uintptr_t>(scratch) & 7) == 0, "bn_relu_bwd: scratch (6*C floats, 8-byte aligned)");
+  double* acc = reinterpret_cast<double*>(scratch);          // 2*C fp64 accumulators
+  float* sums = scratch + 4 * C;                             // 2*C fp32: this layer's sum dy', sum dy' * xhat
+  if (int e = bn_relu_bwd_reduce(raw, dact, mean, rstd, gamma, beta, static_cast<int>(rows), C, acc, sums, dbeta, dgamma,
+                                 stream))
     return e;
-  return bn_relu_bwd(raw, dact, draw, mean, rstd, gamma, beta, dbeta, dgamma, rows, C, stream);
+  return bn_relu_bwd(raw, dact, draw, mean, rstd, gamma, beta, sums, sums + C, rows, C, stream);
 }
 int vpb_nchw_f32_to_rows_bf16(const float* in, void* out, int n, int K, int P, int Kp, void* stream) {
   return nchw_f32_to_rows_bf16(in, out, n, K, P, Kp, as_stream(stream));

@@ -92,17 +92,18 @@ int adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_s
 int transpose_bf16(const void* in, void* out, int R, int C, int batch, cudaStream_t stream);
 int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream);
 int colsum_accumulate(const void* in, int is_f32, int R, int C, float* out, cudaStream_t stream);
-int colsum_sq_accumulate(const void* in, int R, int C, float* sum, float* sumsq, cudaStream_t stream);
+int colsum_sq_accumulate(const void* in, int R, int C, double* sum, double* sumsq, cudaStream_t stream);
 int gelu_fwd_bf16(const void* pre, void* out, long long n, cudaStream_t stream);
 int gelu_bwd_bf16(const void* pre, const void* dh, void* dpre, long long n, cudaStream_t stream);
 int layernorm_bwd(const float* x, const float* gamma, const void* dy, float* dx_accum, float* dgamma, float* dbeta,
                   int M, int D, float eps, cudaStream_t stream);
-int bn_finalize(const float* sum, const float* sumsq, float* mean, float* rstd, float* running_mean, float* running_var,
+int bn_finalize(const double* sum, const double* sumsq, float* mean, float* rstd, float* running_mean, float* running_var,
                 int C, long long rows, float eps, float momentum, cudaStream_t stream);
 int bn_relu_fwd(const void* raw, void* act, const float* mean, const float* rstd, const float* gamma, const float* beta,
                 long long rows, int C, cudaStream_t stream);
 int bn_relu_bwd_reduce(const void* raw, const void* dact, const float* mean, const float* rstd, const float* gamma,
-                       const float* beta, int R, int C, float* dbeta, float* dgamma, cudaStream_t stream);
+                       const float* beta, int R, int C, double* acc, float* sums_f, float* dbeta, float* dgamma,
+                       cudaStream_t stream);
 int bn_relu_bwd(const void* raw, const void* dact, void* draw, const float* mean, const float* rstd, const float* gamma,
                 const float* beta, const float* dbeta, const float* dgamma, long long rows, int C, cudaStream_t stream);
 int nchw_f32_to_rows_bf16(const float* in, void* out, int n, int K, int P, int Kp, cudaStream_t stream);

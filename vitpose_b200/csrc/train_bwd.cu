@@ -149,7 +149,13 @@ __global__ void __launch_bounds__(256) colsum_kernel(const ColsumArgs p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += red[which][i][col];
     const int cc = blockIdx.x * 64 + col;
-    if (cc < p.C) atomicAdd((which ? p.out1 : p.out0) + cc, s);
+    if (cc < p.C) {
+      // BatchNorm statistics feed the activations: accumulate them in fp64 so that the (unordered) atomic sum is
+      // reproducible to the last fp32 bit; parameter gradients take plain fp32 atomics
+      if (MODE == COLSUM_SQ_BF16 || MODE == COLSUM_BNBWD)
+        atomicAdd(reinterpret_cast<double*>(which ? p.out1 : p.out0) + cc, static_cast<double>(s));
+      else atomicAdd((which ? p.out1 : p.out0) + cc, s);
+    }
   }
 }
 
@@ -177,14 +183,33 @@ int colsum_accumulate(const void* in, int is_f32, int R, int C, float* out, cuda
   ColsumArgs a{in, nullptr, nullptr, nullptr, nullptr, nullptr, out, nullptr, R, C, 0};
   return launch_colsum(is_f32 ? COLSUM_F32 : COLSUM_BF16, a, stream);
 }
-int colsum_sq_accumulate(const void* in, int R, int C, float* sum, float* sumsq, cudaStream_t stream) {
-  ColsumArgs a{in, nullptr, nullptr, nullptr, nullptr, nullptr, sum, sumsq, R, C, 0};
+int colsum_sq_accumulate(const void* in, int R, int C, double* sum, double* sumsq, cudaStream_t stream) {
+  ColsumArgs a{in, nullptr, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<float*>(sum),
+               reinterpret_cast<float*>(sumsq), R, C, 0};
   return launch_colsum(COLSUM_SQ_BF16, a, stream);
 }
+// sums of this layer into fp64 accumulators `acc` (2*C, zeroed here), then sums_f[0..C) = sum dy', sums_f[C..2C) =
+// sum dy' * xhat as fp32 (what bn_relu_bwd_kernel consumes) and dbeta / dgamma += them
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ acc, float* __restrict__ sums_f,
+                                       float* __restrict__ dbeta, float* __restrict__ dgamma, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float a = static_cast<float>(acc[c]), b = static_cast<float>(acc[C + c]);
+  sums_f[c] = a;
+  sums_f[C + c] = b;
+  dbeta[c] += a;
+  dgamma[c] += b;
+}
 int bn_relu_bwd_reduce(const void* raw, const void* dact, const float* mean, const float* rstd, const float* gamma,
-                       const float* beta, int R, int C, float* dbeta, float* dgamma, cudaStream_t stream) {
-  ColsumArgs a{raw, dact, mean, rstd, gamma, beta, dbeta, dgamma, R, C, 0};
-  return launch_colsum(COLSUM_BNBWD, a, stream);
+                       const float* beta, int R, int C, double* acc, float* sums_f, float* dbeta, float* dgamma,
+                       cudaStream_t stream) {
+  VPB_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, stream));
+  ColsumArgs a{raw, dact, mean, rstd, gamma, beta, reinterpret_cast<float*>(acc), reinterpret_cast<float*>(acc + C),
+               R, C, 0};
+  if (int e = launch_colsum(COLSUM_BNBWD, a, stream)) return e;
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(acc, sums_f, dbeta, dgamma, C);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -443,13 +468,13 @@ int bn_relu_bwd(const void* raw, const void* dact, void* draw, const float* mean
   return 0;
 }
 // mean / rstd (and the running statistics update of nn.BatchNorm2d: momentum, unbiased variance) from the sums
-__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, float* __restrict__ mean,
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, float* __restrict__ mean,
                                    float* __restrict__ rstd, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, int C, float rows, float eps, float momentum) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float m = sum[c] / rows;
-  const float var = fmaxf(sumsq[c] / rows - m * m, 0.f);
+  const float m = static_cast<float>(sum[c] / rows);
+  const float var = fmaxf(static_cast<float>(sumsq[c] / rows - (sum[c] / rows) * (sum[c] / rows)), 0.f);
   mean[c] = m;
   rstd[c] = 1.0f / sqrtf(var + eps);
   if (running_mean != nullptr) {
@@ -457,7 +482,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * rows / fmaxf(rows - 1.f, 1.f);
   }
 }
-int bn_finalize(const float* sum, const float* sumsq, float* mean, float* rstd, float* running_mean, float* running_var,
+int bn_finalize(const double* sum, const double* sumsq, float* mean, float* rstd, float* running_mean, float* running_var,
                 int C, long long rows, float eps, float momentum, cudaStream_t stream) {
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sum, sumsq, mean, rstd, running_mean, running_var, C,
                                                          static_cast<float>(rows), eps, momentum);

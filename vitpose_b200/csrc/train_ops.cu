@@ -151,8 +151,22 @@ __global__ void __launch_bounds__(256) sq_norm_multi_kernel(const vpb_tensor_ent
   if (threadIdx.x < 32) {
     float v = threadIdx.x < 8 ? s[threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) atomicAdd(out, v);
+    if (threadIdx.x == 0) out[blockIdx.x] = v;          // per-chunk partial: no atomics, fixed order below
   }
+}
+// sum of the per-chunk partials in a fixed order (one CTA): every replica gets the same clip coefficient bit for bit
+__global__ void __launch_bounds__(1024) sq_norm_finish_kernel(const float* __restrict__ partial, int n,
+                                                              float* __restrict__ out) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) acc += static_cast<double>(partial[i]);
+  __shared__ double s[1024];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) {
+    if (threadIdx.x < w) s[threadIdx.x] += s[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = static_cast<float>(s[0]);
 }
 
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const vpb_tensor_entry* __restrict__ entries,
@@ -186,9 +200,10 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const vpb_tensor_entry
 int adamw_multi(const vpb_tensor_entry* entries, const int* chunk_start, int n, int total_chunks, float beta1,
                 float beta2, float eps, float* sq_norm, float max_norm, cudaStream_t stream) {
   VPB_REQUIRE(n > 0 && total_chunks > 0 && entries && chunk_start, "adamw_multi: empty table");
-  if (sq_norm != nullptr) {
-    VPB_CHECK_CUDA(cudaMemsetAsync(sq_norm, 0, sizeof(float), stream));
-    sq_norm_multi_kernel<<<total_chunks, 256, 0, stream>>>(entries, chunk_start, n, sq_norm);
+  if (sq_norm != nullptr) {      // sq_norm[0] = result, sq_norm[1 .. total_chunks] = per-chunk partials
+    sq_norm_multi_kernel<<<total_chunks, 256, 0, stream>>>(entries, chunk_start, n, sq_norm + 1);
+    VPB_CHECK_CUDA(cudaGetLastError());
+    sq_norm_finish_kernel<<<1, 1024, 0, stream>>>(sq_norm + 1, total_chunks, sq_norm);
     VPB_CHECK_CUDA(cudaGetLastError());
   }
   adamw_multi_kernel<<<total_chunks, 256, 0, stream>>>(entries, chunk_start, n, beta1, beta2, eps, sq_norm, max_norm);

@@ -72,11 +72,11 @@ def pack_deconv_weight_dgrad(wp):
     return wp.reshape(4, cout, 4, cin).permute(3, 0, 2, 1).reshape(cin, 16 * cout).contiguous()
 
 
-def unpack_deconv_weight(wp, dtype=torch.float32):
+def unpack_deconv_weight(wp, dtype=torch.float32, out=None):
     """Inverse of pack_deconv_weight: [4, Cout, 4*Cin] -> ConvTranspose2d layout [Cin, Cout, 4, 4]."""
     _, cout, c4 = wp.shape
     cin = c4 // 4
-    w = torch.empty(cin, cout, 4, 4, dtype=dtype, device=wp.device)
+    w = torch.empty(cin, cout, 4, 4, dtype=dtype, device=wp.device) if out is None else out
     for py in range(2):
         for px in range(2):
             for ty in range(2):

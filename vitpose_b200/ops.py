@@ -241,7 +241,7 @@ def bn_train_stats(raw, eps=1e-5, momentum=0.1, running_mean=None, running_var=N
     _need(raw, BF16, 'raw')
     C = raw.shape[-1]
     rows = raw.numel() // C
-    scratch = torch.empty(2 * C, device=raw.device)
+    scratch = torch.empty(4 * C, device=raw.device)
     mean, rstd = torch.empty(C, device=raw.device), torch.empty(C, device=raw.device)
     check(lib().vpb_bn_train_stats(ptr(raw), rows, C, float(eps), float(momentum), ptr(scratch), ptr(mean), ptr(rstd),
                                    ptr(running_mean), ptr(running_var), stream_ptr()), 'vpb_bn_train_stats')
@@ -259,8 +259,10 @@ def bn_relu_fwd(raw, mean, rstd, gamma, beta):
 def bn_relu_bwd(raw, dact, mean, rstd, gamma, beta, dgamma, dbeta):
     C = raw.shape[-1]
     draw = torch.empty_like(raw)
+    scratch = torch.empty(6 * C, device=raw.device)
     check(lib().vpb_bn_relu_bwd(ptr(raw), ptr(dact), ptr(draw), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta),
-                                ptr(dgamma), ptr(dbeta), raw.numel() // C, C, stream_ptr()), 'vpb_bn_relu_bwd')
+                                ptr(dgamma), ptr(dbeta), ptr(scratch), raw.numel() // C, C, stream_ptr()),
+          'vpb_bn_relu_bwd')
     return draw
 
 

@@ -121,8 +121,9 @@ class LayerDecayAdamW(torch.optim.Optimizer):
         d_starts = torch.from_numpy(starts).to(dev)
         sq = None
         if max_norm is not None:
-            if self._sq_norm is None or self._sq_norm.device != dev:
-                self._sq_norm = torch.zeros(1, device=dev, dtype=torch.float32)
+            need = 1 + int(starts[-1])
+            if self._sq_norm is None or self._sq_norm.device != dev or self._sq_norm.numel() < need:
+                self._sq_norm = torch.zeros(need, device=dev, dtype=torch.float32)
             sq = self._sq_norm
         check(L.vpb_adamw_multi(ptr(d_table), ptr(d_starts), len(items), int(starts[-1]), float(b1), float(b2),
                                 float(eps), ptr(sq), float(max_norm) if max_norm is not None else 0.0, stream_ptr()),

@@ -122,8 +122,11 @@ class _NetworkFn(torch.autograd.Function):
         dev = dhm.device
         g = {}                                           # parameter name -> fp32 gradient
 
-        # every gradient buffer starts at zero (the kernels accumulate): one memset of one arena instead of ~270 fills
-        cap = sum((p.numel() + 63) // 64 * 64 for _, p in _param_list(model)) * 2 + M * D + (1 << 20)
+        # Every parameter gradient lives in ONE zero-initialised arena, in the order the backward pass produces
+        # them: one memset instead of ~270 fills, and with N > 1 ranks the arena is all-reduced (NCCL) in a few
+        # large segments that are issued as soon as they are complete, so the exchange overlaps the rest of the
+        # backward pass; when backward() returns the gradients are already averaged (what the DDP wrapper does).
+        cap = sum((p.numel() + 63) // 64 * 64 for _, p in _param_list(model)) + (1 << 20)
         arena = torch.zeros(cap, device=dev, dtype=torch.float32)
         used = [0]
 
@@ -132,10 +135,27 @@ class _NetworkFn(torch.autograd.Function):
             for d in shape:
                 numel *= d
             if used[0] + numel > cap:
-                return torch.zeros(*shape, device=dev, dtype=torch.float32)
+                raise RuntimeError('gradient arena exhausted')
             t = arena[used[0]:used[0] + numel].view(*shape)
             used[0] += (numel + 63) // 64 * 64
             return t
+
+        def scratch_zeros(*shape):                       # zero-initialised buffers that are not parameter gradients
+            return torch.zeros(*shape, device=dev, dtype=torch.float32)
+
+        world = 1
+        if getattr(model, 'allreduce_in_backward', True) and torch.distributed.is_available() \
+                and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()
+        pending, sent = [], [0]
+
+        def exchange(final=False):
+            """all-reduce the arena segment completed since the last call (at least 32 MB unless final)."""
+            if world == 1 or used[0] == sent[0] or (not final and (used[0] - sent[0]) * 4 < (32 << 20)):
+                return
+            seg = arena[sent[0]:used[0]]
+            pending.append(torch.distributed.all_reduce(seg, op=torch.distributed.ReduceOp.SUM, async_op=True))
+            sent[0] = used[0]
 
         # ---- final 1x1 conv: rows = pixels, columns = keypoints (zero padded to a multiple of 8)
         Kp = (K + 7) // 8 * 8
@@ -165,14 +185,16 @@ class _NetworkFn(torch.autograd.Function):
             g[f'keypoint_head.deconv_layers.{3 * i + 1}.bias'] = dbet
             a_t = ops.transpose(ops.deconv_phase_dy(draw), batch=4)                      # [4, cout, pixels]
             b_t = ops.transpose(ops.deconv_gather_x(xin), batch=4)                       # [4, 4*cin, pixels]
-            dwp = zeros(4, cout, wp_.shape[2])
+            dwp = scratch_zeros(4, cout, wp_.shape[2])
             for ph in range(4):
                 _wgrad(a_t[ph], b_t[ph], dwp[ph])
-            g[f'keypoint_head.deconv_layers.{3 * i}.weight'] = unpack_deconv_weight(dwp)
+            g[f'keypoint_head.deconv_layers.{3 * i}.weight'] = unpack_deconv_weight(
+                dwp, out=zeros(wp_.shape[2] // 4, cout, 4, 4))
             del a_t, b_t
             dact = ops.gemm(ops.deconv_gather_dy(draw), pack_deconv_weight_dgrad(wp_), EPI_BIAS)   # [pixels_in, cin]
         # ---- last_norm, then the blocks in reverse
-        dx = zeros(M, D)
+        exchange()
+        dx = scratch_zeros(M, D)
         ln = bb.last_norm
         dg_, db_ = zeros(D), zeros(D)
         ops.layernorm_bwd(s['x_final'], ln.weight.detach(), dact, dx, dg_, db_, 1e-6)
@@ -206,20 +228,23 @@ class _NetworkFn(torch.autograd.Function):
             ops.layernorm_bwd(a['x_in'], blk.norm1.weight.detach(), dxn1, dx, dg_, db_, 1e-6)
             g[pfx + 'norm1.weight'], g[pfx + 'norm1.bias'] = dg_, db_
             s['acts'][l] = None                               # activations of this block are dead
+            exchange()
         # ---- patch embed (vit.py:159-165) + pos embed (vit.py:320)
         dyb = ops.cast_bf16(dx)
         linear_bwd('backbone.patch_embed.proj', s['pe'], dyb, s['patches'], want_dx=False)
         g['backbone.patch_embed.proj.weight'] = g['backbone.patch_embed.proj.weight'].view(
             bb.patch_embed.proj.weight.shape)
-        dpos_tok = zeros(T * D)
+        dpos = zeros(1, T + 1, D)                                          # [cls slot | tokens], contiguous
+        dpos_tok = dpos[0, 1:].reshape(T * D)
         ops.colsum_accumulate(dx.view(n, T * D), dpos_tok)                 # sum over the crops
-        dcls = zeros(D)
-        ops.colsum_accumulate(dpos_tok.view(T, D), dcls)                   # the cls slot is added to every token
-        dpos = torch.empty(1, T + 1, D, device=dev, dtype=torch.float32)
-        dpos[0, 0] = dcls
-        dpos[0, 1:] = dpos_tok.view(T, D)
+        ops.colsum_accumulate(dpos[0, 1:], dpos[0, 0])                     # the cls slot is added to every token
         g['backbone.pos_embed'] = dpos
         ctx.s = None
+        exchange(final=True)
+        for h in pending:
+            h.wait()
+        if world > 1:
+            arena[:used[0]].mul_(1.0 / world)
         grads = []
         for nm, p in _param_list(model):
             gr = g.get(nm) if p.requires_grad else None
