@@ -134,7 +134,7 @@ def run_train(args, cfg, K):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     n = args.crops
-    cfg['backbone']['drop_path_rate'] = 0.0
+    drop = float(cfg['backbone'].get('drop_path_rate', 0.0))      # the config's stochastic depth (ViTPose-B: 0.3)
     sd = synthetic.scaled_init_state_dict(cfg, 0)
     model = V.build_posenet(cfg)
     model.load_state_dict(sd, strict=True)
@@ -209,7 +209,7 @@ def run_train(args, cfg, K):
                     warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype='bf16', data='synthetic',
                     config=dict(workload=args.workload + '-train', crops_per_gpu=n, global_crops=total,
-                                optimizer='AdamW lr 5e-4 wd 0.1, layer decay 0.75, grad clip 1.0', drop_path=0.0,
+                                optimizer='AdamW lr 5e-4 wd 0.1, layer decay 0.75, grad clip 1.0', drop_path=drop,
                                 parallelism=f'dp{world}', collective='gradient all-reduce (NCCL)' if world > 1 else None,
                                 l2='activations per step >> 126 MB L2; inputs ping-pong between two buffers'),
                     roofline=dict(bound='tensor', kernel='whole training step (3 x forward GEMM FLOPs)', achieved=tf,

@@ -149,11 +149,15 @@ int vpb_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogu
  * last_norm that consumes the result (vit.py:137-140, :320, :328). The CTAs that own the column tiles of one
  * 128-row block exchange per-row (mean, M2) through `scratch` (vpb_gemm_layernorm_scratch_bytes(M, N) bytes,
  * 16-byte aligned, contents don't care), so the rows are normalised while they are still in tensor memory.
- * out may alias aux (in-place residual update). */
+ * out may alias aux (in-place residual update).
+ * row_scale (optional fp32 [ceil(M / rows_per_scale)], VPB_EPI_RESID_F32 only): the GEMM branch of rows
+ * [i*rows_per_scale, (i+1)*rows_per_scale) is multiplied by row_scale[i] before the residual add — stochastic depth,
+ * `x + drop_path(branch)` with row_scale = mask / keep_prob per crop (vit.py:48-56,138-139). */
 size_t vpb_gemm_layernorm_scratch_bytes(int M, int N);
 int vpb_gemm_bf16_layernorm(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias,
                             float* out, const float* aux, int period, const float* gamma, const float* beta, float eps,
-                            void* xn, void* scratch, size_t scratch_bytes, void* stream);
+                            void* xn, void* scratch, size_t scratch_bytes, const float* row_scale, int rows_per_scale,
+                            void* stream);
 int vpb_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int M, int D, float eps,
                        void* stream);
 int vpb_im2col_patch16(const float* img, void* patches, int n, int H, int W, int flip, void* stream);
@@ -173,7 +177,9 @@ int vpb_tokens_to_nchw_f32(const void* tokens, float* out, int n, int T, int D, 
  *   wgrad  dW[N,K] += dY^T . X          = vpb_gemm_bf16(A = dY^T [N,M], B = X^T [K,M], VPB_EPI_ACCUM_F32, out = dW)
  * All matrices row-major; bf16 unless stated; gradients of parameters are fp32 and ACCUMULATED into their buffers. */
 int vpb_transpose_bf16(const void* in, void* out, int R, int C, int batch, void* stream);   /* out[b][C,R] = in[b][R,C]^T */
-int vpb_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
+/* out = bf16(in), optionally times row_scale[(i / row_len) / rows_per_scale] (gradient of a stochastic-depth branch) */
+int vpb_cast_f32_bf16(const float* in, void* out, long long n, const float* row_scale, int row_len,
+                      int rows_per_scale, void* stream);
 /* out[C] += sum over the R rows of in[R,C] (bf16, or fp32 when is_f32): bias / pos-embed gradients */
 int vpb_colsum_accumulate(const void* in, int is_f32, int R, int C, float* out, void* stream);
 /* nn.GELU (exact erf, vit.py:71-76): out = gelu(pre); dpre = dh * gelu'(pre) */
@@ -238,6 +244,14 @@ int vpb_grad_sq_norm_accumulate(const float* grad, long long n, float* sq_norm_a
 int vpb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int step, const float* sq_norm,
                    float max_norm, void* stream);
+
+/* pose_pck_accuracy's arithmetic (mmpose/core/evaluation/top_down_eval.py:8-60,133-215), the `acc_pose` value of
+ * TopdownHeatmapSimpleHead.get_accuracy (simple_head.py:170-195): pred / gt fp32 [N,K,2] are the arg-max coordinates
+ * of the output and target heatmaps (vpb_decode_heatmaps with VPB_DECODE_NONE, no transform), weight fp32 [N,K]
+ * (> 0 = visible). norm0 / norm1 divide x / y (the reference passes (H, W)). acc fp32 [K] (-1 = no visible sample),
+ * avg fp32 [1], cnt int32 [1]. */
+int vpb_pose_pck_accuracy(const float* pred, const float* gt, const float* weight, int N, int K, float norm0,
+                          float norm1, float thr, float* acc, float* avg, int32_t* cnt, void* stream);
 
 /* Multi-tensor form: one call updates every parameter (and computes the clip norm first when sq_norm != NULL).
  * entries: DEVICE array of n descriptors; chunk_start: DEVICE int[n+1], prefix sum of ceil(n_i / 4096);

@@ -141,3 +141,36 @@ def test_decode_empty_and_errors():
         ops.decode(torch.zeros(1, 1, 64, 48, device=dev), mode=_lib.DECODE_UNBIASED, kernel=0)
     with pytest.raises(_lib.VitposeLibError):
         ops.decode(torch.zeros(1, 1, 64, 48), mode=_lib.DECODE_DEFAULT)          # CPU tensor: no fallback
+
+
+def test_pose_pck_accuracy_matches_oracle():
+    """acc_pose of forward_train (simple_head.py:170-195): device arg-max + PCK arithmetic vs the oracle, incl. the
+    reference KAT (tests/test_evaluation/test_top_down_eval.py:11-26), invisible keypoints and empty maps."""
+    import vitpose_b200 as V
+    from vitpose_b200.core.evaluation.top_down_eval import pose_pck_accuracy
+    output = np.zeros((1, 5, 64, 64), dtype=np.float32)
+    target = np.zeros((1, 5, 64, 64), dtype=np.float32)
+    mask = np.array([[True, True, False, False, False]])
+    output[0, 0, 20, 20] = 1
+    target[0, 0, 10, 10] = 1
+    output[0, 1, 30, 30] = 1
+    target[0, 1, 30, 30] = 1
+    acc, avg_acc, cnt = pose_pck_accuracy(output, target, mask)
+    np.testing.assert_array_almost_equal(acc, np.array([0, 1, -1, -1, -1]), decimal=4)
+    assert abs(avg_acc - 0.5) < 1e-4 and cnt == 2
+    rng = np.random.RandomState(5)
+    N, K = 33, 17
+    target = np.zeros((N, K, 64, 48), dtype=np.float32)
+    output = rng.randn(N, K, 64, 48).astype(np.float32) * 0.05
+    for n in range(N):
+        for k in range(K):
+            y, x = rng.randint(64), rng.randint(48)
+            target[n, k, y, x] = 1
+            output[n, k, np.clip(y + rng.randint(-4, 5), 0, 63), np.clip(x + rng.randint(-4, 5), 0, 47)] += 1
+    target[0, 3] = 0
+    mask = rng.rand(N, K) > 0.25
+    mask[:, 5] = False
+    a0, v0, c0 = O.pose_pck_accuracy(output, target, mask)
+    a1, v1, c1 = pose_pck_accuracy(output, target, mask)
+    np.testing.assert_allclose(a1, a0, rtol=0, atol=1e-7)
+    assert abs(v1 - v0) < 1e-6 and c1 == c0

@@ -32,8 +32,10 @@ def _cos(a, b):
     return float((a @ b) / (a.norm() * b.norm() + 1e-30))
 
 
-@pytest.mark.parametrize('name,n,depth', [('tiny', 4, 2), ('B-classic-17', 3, 2), ('B-classic-17', 2, 12)])
-def test_forward_train_backward_vs_oracle(name, n, depth):
+@pytest.mark.parametrize('name,n,depth,drop', [('tiny', 4, 2, 0.0), ('B-classic-17', 3, 2, 0.0),
+                                               ('B-classic-17', 2, 12, 0.0), ('B-classic-17', 6, 3, 0.3)])
+def test_forward_train_backward_vs_oracle(name, n, depth, drop):
+    """drop > 0: stochastic depth with the SAME per-crop masks injected into both implementations."""
     import vitpose_b200 as V
     if name == 'tiny':
         cfg = configs.tiny_model_cfg(5)
@@ -45,11 +47,22 @@ def test_forward_train_backward_vs_oracle(name, n, depth):
     img = synthetic.synthetic_crops(n, 7)
     target, tw = _targets(n, K, 7)
     ref_sd = {k: v.clone() for k, v in sd.items()}
-    loss_ref, hm_ref, g_ref = VT.train_loss_and_grads(ref_sd, img, target, tw, cfg)
+    scales = None
+    if drop > 0:
+        gen = torch.Generator().manual_seed(11)
+        scales = []
+        for p in torch.linspace(0, drop, depth).tolist():
+            keep = 1.0 - p
+            scales.append(tuple(torch.floor(keep + torch.rand(n, generator=gen)) / keep for _ in range(2)))
+        assert any((s == 0).any() for pair in scales for s in pair), 'the masks must drop something'
+    loss_ref, hm_ref, g_ref = VT.train_loss_and_grads(ref_sd, img, target, tw, cfg, drop_scales=scales)
 
+    cfg['backbone']['drop_path_rate'] = drop
     model = V.build_posenet(cfg)
     model.load_state_dict(sd, strict=True)
     model = model.cuda().train()
+    if scales is not None:
+        model.backbone._drop_path_scales = [tuple(s.float().cuda().contiguous() for s in pair) for pair in scales]
     losses = model(img=img.cuda(), target=target.cuda(), target_weight=tw.cuda(), img_metas=None, return_loss=True)
     assert set(losses) >= {'heatmap_loss'}
     loss = losses['heatmap_loss']
@@ -111,3 +124,21 @@ def test_train_step_with_layer_decay_adamw_decreases_loss():
         assert torch.isfinite(norm)
         hist.append(out['loss'].item())
     assert hist[-1] < hist[0], hist
+
+
+def test_drop_path_random_masks_follow_the_schedule():
+    """Without injected masks the factors are 0 or 1/keep_prob with keep_prob = 1 - linspace(0, rate, depth)[i]."""
+    from types import SimpleNamespace
+    from vitpose_b200.training import drop_path_scales
+    bb = SimpleNamespace(drop_path_rate=0.3, depth=4, training=True)
+    sc = drop_path_scales(bb, 4096, torch.device('cuda:0'))
+    assert sc[0] == (None, None)
+    for i, p in enumerate(torch.linspace(0, 0.3, 4).tolist()):
+        if i == 0:
+            continue
+        for s in sc[i]:
+            vals = torch.unique(s).cpu()
+            assert torch.allclose(vals, torch.tensor([0.0, 1.0 / (1.0 - p)]), atol=1e-6)
+            assert abs(float((s == 0).float().mean()) - p) < 0.03
+    bb.training = False
+    assert all(pair == (None, None) for pair in drop_path_scales(bb, 8, torch.device('cuda:0')))

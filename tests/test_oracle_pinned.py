@@ -148,6 +148,43 @@ def test_golden_loss(golden_dir):
     np.testing.assert_allclose(VT.joints_mse_loss(o, t, None, False).numpy(), g['loss_unweighted'], rtol=1e-6)
 
 
+def test_kat_pose_pck_accuracy():
+    """tests/test_evaluation/test_top_down_eval.py:11-26."""
+    output = np.zeros((1, 5, 64, 64), dtype=np.float32)
+    target = np.zeros((1, 5, 64, 64), dtype=np.float32)
+    mask = np.array([[True, True, False, False, False]])
+    output[0, 0, 20, 20] = 1
+    target[0, 0, 10, 10] = 1
+    output[0, 1, 30, 30] = 1
+    target[0, 1, 30, 30] = 1
+    acc, avg_acc, cnt = O.pose_pck_accuracy(output, target, mask)
+    np.testing.assert_array_almost_equal(acc, np.array([0, 1, -1, -1, -1]), decimal=4)
+    assert abs(avg_acc - 0.5) < 1e-4 and abs(cnt - 2) < 1e-4
+
+
+@pytest.mark.reference
+def test_live_reference_pose_pck_accuracy():
+    from oracle import ref_loader
+    ref = ref_loader.load_reference()
+    rng = np.random.RandomState(3)
+    N, K = 9, 17
+    target = np.zeros((N, K, 64, 48), dtype=np.float32)
+    output = rng.randn(N, K, 64, 48).astype(np.float32) * 0.05
+    for n in range(N):
+        for k in range(K):
+            y, x = rng.randint(64), rng.randint(48)
+            target[n, k, y, x] = 1
+            oy, ox = np.clip(y + rng.randint(-4, 5), 0, 63), np.clip(x + rng.randint(-4, 5), 0, 47)
+            output[n, k, oy, ox] += 1
+    target[0, 3] = 0                      # a map whose maximum is <= 0 decodes to (-1, -1)
+    mask = rng.rand(N, K) > 0.25
+    mask[:, 5] = False                    # a keypoint that is never visible
+    a0, v0, c0 = ref.pose_pck_accuracy(output, target, mask.copy())
+    a1, v1, c1 = O.pose_pck_accuracy(output, target, mask.copy())
+    np.testing.assert_array_equal(a0, a1)
+    assert v0 == v1 and c0 == c1
+
+
 def test_gaussian_taps_match_cv2():
     cv2 = pytest.importorskip('cv2')
     for k in (1, 3, 5, 7, 9, 11, 17):

@@ -58,7 +58,7 @@ _SIGS = {
     'vpb_transform_preds': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p]),
     'vpb_transpose_bf16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    'vpb_cast_f32_bf16': (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p]),
+    'vpb_cast_f32_bf16': (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_int, c_int, c_void_p]),
     'vpb_colsum_accumulate': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'vpb_gelu_fwd_bf16': (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p]),
     'vpb_gelu_bwd_bf16': (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p]),
@@ -87,11 +87,14 @@ _SIGS = {
                                c_float, c_float, c_int, c_void_p, c_float, c_void_p]),
     'vpb_adamw_multi': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_void_p, c_float,
                                 c_void_p]),
+    'vpb_pose_pck_accuracy': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
     'vpb_gemm_bf16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                               c_int, c_int, c_void_p]),
     'vpb_gemm_layernorm_scratch_bytes': (c_size_t, [c_int, c_int]),
     'vpb_gemm_bf16_layernorm': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                                        c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                        c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_int,
+                                        c_void_p]),
     'vpb_layernorm_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     'vpb_im2col_patch16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'vpb_attention': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),

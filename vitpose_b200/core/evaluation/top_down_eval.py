@@ -89,3 +89,23 @@ def keypoints_from_heatmaps(heatmaps,
     preds = r['preds'].cpu().numpy()
     maxvals = r['maxvals'].cpu().numpy()
     return preds, maxvals
+
+
+def pose_pck_accuracy(output, target, mask, thr=0.05, normalize=None):
+    """PCK accuracy from heatmaps with the reference's signature (top_down_eval.py:133-178): NumPy in, NumPy out;
+    arg-max and the distance / threshold arithmetic run on the GPU (vpb_decode_heatmaps + vpb_pose_pck_accuracy).
+    ``normalize`` (np.ndarray[N,2]) must be the same for every sample (the reference's default is [[H, W]] * N)."""
+    N, K, H, W = output.shape
+    if K == 0:
+        return None, 0, 0
+    _lib.require_cuda()
+    norm = None
+    if normalize is not None:
+        normalize = np.asarray(normalize)
+        assert (normalize == normalize[:1]).all(), 'per-sample normalisation factors are not implemented'
+        norm = (normalize[0, 0], normalize[0, 1])
+    o = torch.from_numpy(np.ascontiguousarray(output, dtype=np.float32)).cuda()
+    t = torch.from_numpy(np.ascontiguousarray(target, dtype=np.float32)).cuda()
+    w = torch.from_numpy(np.ascontiguousarray(mask).astype(np.float32)).cuda()
+    acc, avg, cnt = ops.pose_pck_accuracy(o, t, w, thr, norm)
+    return acc.cpu().numpy(), float(avg.item()), int(cnt.item())

@@ -254,13 +254,15 @@ int vpb_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogu
 }
 int vpb_gemm_bf16_layernorm(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias,
                             float* out, const float* aux, int period, const float* gamma, const float* beta, float eps,
-                            void* xn, void* scratch, size_t scratch_bytes, void* stream_) {
+                            void* xn, void* scratch, size_t scratch_bytes, const float* row_scale, int rows_per_scale,
+                            void* stream_) {
   cudaStream_t stream = as_stream(stream_);
   VPB_REQUIRE(M > 0 && N > 0, "gemm+layernorm: empty problem");
   VPB_REQUIRE(scratch != nullptr && scratch_bytes >= gemm_ln_scratch_bytes(M, N),
               "gemm+layernorm: scratch too small (%zu < %zu)", scratch_bytes, gemm_ln_scratch_bytes(M, N));
   if (int e = gemm_ln_scratch_init(scratch, M, N, stream)) return e;
-  return gemm_bf16_ln(A, B, M, N, K, epilogue, bias, out, aux, period, gamma, beta, eps, xn, scratch, 1u, 0, stream);
+  return gemm_bf16_ln(A, B, M, N, K, epilogue, bias, out, aux, period, gamma, beta, eps, xn, scratch, 1u, 0, stream,
+                      row_scale, rows_per_scale);
 }
 size_t vpb_gemm_layernorm_scratch_bytes(int M, int N) { return M > 0 && N > 0 ? gemm_ln_scratch_bytes(M, N) : 0; }
 int vpb_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int M, int D, float eps,
@@ -307,12 +309,18 @@ int vpb_adamw_multi(const vpb_tensor_entry* entries, const int32_t* chunk_start,
   return adamw_multi(entries, chunk_start, n, total_chunks, beta1, beta2, eps, sq_norm, max_norm, as_stream(stream));
 }
 
+int vpb_pose_pck_accuracy(const float* pred, const float* gt, const float* weight, int N, int K, float norm0,
+                          float norm1, float thr, float* acc, float* avg, int32_t* cnt, void* stream) {
+  return pose_pck_accuracy(pred, gt, weight, N, K, norm0, norm1, thr, acc, avg, cnt, as_stream(stream));
+}
+
 // ---- backward-pass operators of the training step ----
 int vpb_transpose_bf16(const void* in, void* out, int R, int C, int batch, void* stream) {
   return transpose_bf16(in, out, R, C, batch, as_stream(stream));
 }
-int vpb_cast_f32_bf16(const float* in, void* out, long long n, void* stream) {
-  return cast_f32_bf16(in, out, n, as_stream(stream));
+int vpb_cast_f32_bf16(const float* in, void* out, long long n, const float* row_scale, int row_len,
+                      int rows_per_scale, void* stream) {
+  return cast_f32_bf16(in, out, n, as_stream(stream), row_scale, row_len, rows_per_scale);
 }
 int vpb_colsum_accumulate(const void* in, int is_f32, int R, int C, float* out, void* stream) {
   return colsum_accumulate(in, is_f32, R, C, out, as_stream(stream));

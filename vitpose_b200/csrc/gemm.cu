@@ -173,7 +173,7 @@ int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, c
   const int cg = gemm_pick_cg(M, bn, epilogue, K);
   GemmMaps maps;
   if (make_gemm_maps(&maps, A, B, M, N, K, K, K, bn, epilogue, out, ldo, aux, cg, period)) return -1;
-  GemmParams p{M, N, K, bias, out, ldo, aux, period, 1, nullptr, nullptr, nullptr, 0, 0u, 0.0f};
+  GemmParams p{M, N, K, bias, out, ldo, aux, period, 1, nullptr, 1, nullptr, nullptr, nullptr, 0, 0u, 0.0f};
   if (epilogue == EPI_ACCUM_F32) {
     VPB_REQUIRE(bias == nullptr && ldo % 4 == 0, "gemm: the accumulating epilogue takes no bias and needs ldo %% 4 == 0");
     // about two waves of CTAs, at least 8 K blocks (512 rows of the contraction) per split, every split non-empty
@@ -208,7 +208,10 @@ int gemm_ln_scratch_init(void* scratch, int M, int N, cudaStream_t stream) {
 
 int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, float* out,
                  const float* aux, int period, const float* gamma, const float* beta, float eps, void* xn,
-                 void* scratch, unsigned epoch, int max_ctas, cudaStream_t stream) {
+                 void* scratch, unsigned epoch, int max_ctas, cudaStream_t stream, const float* row_scale,
+                 int rows_per_scale) {
+  VPB_REQUIRE(row_scale == nullptr || (rows_per_scale > 0 && epilogue == EPI_RESID_F32),
+              "gemm+layernorm: row_scale needs rows_per_scale > 0 and the residual epilogue");
   VPB_REQUIRE(epilogue == EPI_RESID_F32 || epilogue == EPI_POS_F32, "gemm+layernorm: epilogue %d has no fused form",
               epilogue);
   VPB_REQUIRE(gamma && beta && xn && out && aux, "gemm+layernorm: null argument");
@@ -222,6 +225,10 @@ int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue
   const bool fused = !disabled && bn != 0 && pos_ok && scratch != nullptr && epoch > 0 && K % 8 == 0 && N % 8 == 0 &&
                      ((reinterpret_cast<uintptr_t>(aux) | reinterpret_cast<uintptr_t>(out) |
                        reinterpret_cast<uintptr_t>(xn) | reinterpret_cast<uintptr_t>(scratch)) & 15) == 0;
+  if (!fused && row_scale != nullptr) {
+    set_last_error("gemm+layernorm: row_scale is only implemented in the fused kernel (N=%d K=%d)", N, K);
+    return -2;
+  }
   if (!fused) {   // two kernels (still on the GPU): shapes the fused epilogue does not cover
     if (int e = gemm_bf16(A, B, M, N, K, epilogue, bias, out, N, aux, period, max_ctas, stream)) return e;
     return layernorm_bf16(out, gamma, beta, xn, M, N, eps, stream);
@@ -246,7 +253,8 @@ int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue
   uint32_t box_o[2] = {64u, GEMM_BM};
   if (make_tma_desc(&maps.ln, TMA_BF16, xn, 2, dims_o, str_o, box_o, TMA_SWIZZLE_128B)) return -1;
   VPB_REQUIRE(N / bn <= 10, "gemm+layernorm: at most 10 column tiles per row (N=%d)", N);
-  GemmParams p{M, N, K, bias, out, N, aux, period, 1, gamma, beta, reinterpret_cast<unsigned long long*>(scratch),
+  GemmParams p{M, N, K, bias, out, N, aux, period, 1, row_scale, rows_per_scale > 0 ? rows_per_scale : 1, gamma, beta,
+               reinterpret_cast<unsigned long long*>(scratch),
                ln_region_words(M, N), epoch, eps};
   return launch_gemm(maps, p, bn, epi, cg, max_ctas, stream);
 }

@@ -48,6 +48,10 @@ struct GemmParams {
   const float* aux;    // residual or positional table
   int period;          // tokens per crop (EPI_POS) / pixels per crop (EPI_NCHW)
   int ksplit;          // EPI_ACCUM_F32: CTAs per output tile (>= 1); 1 for every other epilogue
+  // residual epilogues: out = aux + row_scale[row / scale_period] * (acc + bias); null = 1. Stochastic depth
+  // (DropPath, vit.py:48-56,138-139): the branch of crop i is multiplied by mask_i / keep_prob.
+  const float* row_scale;
+  int scale_period;
   // fused LayerNorm (EPI_*_LN_F32): affine parameters [N] and the per-row partial statistics (mean, M2 of a tile's
   // BN columns, one 8-byte word each) that the CTAs owning the n-tiles of one row block exchange through global
   // memory. Launch e of a sequence writes region e & 1 and tags its words with bit (e >> 1) & 1 in the sign of M2,
@@ -408,6 +412,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const int m_blk = ((tile / p.ksplit) / n_tiles) * CG + cta_rank;
       const int n_blk = (tile / p.ksplit) % n_tiles;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+      float rs = 1.0f;                     // per-row scale of the branch (stochastic depth), rows past M clamp
+      if (gemm_epi_adds_tile(EPI) && p.row_scale != nullptr)
+        rs = __ldg(p.row_scale + min(m_blk * GEMM_BM + r, p.M - 1) / p.scale_period);
+      const float2 rs2 = make_float2(rs, rs);
+      (void)rs2;
 
       if constexpr (STAGED) {
         constexpr int NCHUNK = BN / CHUNK;
@@ -453,12 +462,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               const float4 x = lds_f4(pu);
               const float4 bb = bias4[u];
               // residual + (acc + bias), as the unfused epilogue; packed fp32 adds are IEEE per lane
-              const float2 lo = __fadd2_rn(make_float2(x.x, x.y),
+              const float2 lo = __ffma2_rn(rs2,
                                            __fadd2_rn(make_float2(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1])),
-                                                      make_float2(bb.x, bb.y)));
-              const float2 hi = __fadd2_rn(make_float2(x.z, x.w),
+                                                      make_float2(bb.x, bb.y)),
+                                           make_float2(x.x, x.y));
+              const float2 hi = __ffma2_rn(rs2,
                                            __fadd2_rn(make_float2(__uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3])),
-                                                      make_float2(bb.z, bb.w)));
+                                                      make_float2(bb.z, bb.w)),
+                                           make_float2(x.z, x.w));
               sts_f4(pu, make_float4(lo.x, lo.y, hi.x, hi.y));
               v[4 * u + 0] = __float_as_uint(lo.x);
               v[4 * u + 1] = __float_as_uint(lo.y);
@@ -587,10 +598,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             for (int u = 0; u < 8; ++u) {
               const uint32_t pu = srow + ((u ^ (r & 7)) * 16);
               float4 x = lds_f4(pu);
-              x.x += __uint_as_float(v[4 * u + 0]) + bias_c[4 * u + 0];
-              x.y += __uint_as_float(v[4 * u + 1]) + bias_c[4 * u + 1];
-              x.z += __uint_as_float(v[4 * u + 2]) + bias_c[4 * u + 2];
-              x.w += __uint_as_float(v[4 * u + 3]) + bias_c[4 * u + 3];
+              // fmaf(1, t, x) == x + t exactly, so the unscaled path keeps its rounding
+              x.x = fmaf(rs, __uint_as_float(v[4 * u + 0]) + bias_c[4 * u + 0], x.x);
+              x.y = fmaf(rs, __uint_as_float(v[4 * u + 1]) + bias_c[4 * u + 1], x.y);
+              x.z = fmaf(rs, __uint_as_float(v[4 * u + 2]) + bias_c[4 * u + 2], x.z);
+              x.w = fmaf(rs, __uint_as_float(v[4 * u + 3]) + bias_c[4 * u + 3], x.w);
               sts_f4(pu, x);
             }
           } else {

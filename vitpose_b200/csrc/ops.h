@@ -30,7 +30,8 @@ size_t gemm_ln_scratch_bytes(int M, int N);
 int gemm_ln_scratch_init(void* scratch, int M, int N, cudaStream_t stream);
 int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, float* out,
                  const float* aux, int period, const float* gamma, const float* beta, float eps, void* xn,
-                 void* scratch, unsigned epoch, int max_ctas, cudaStream_t stream);
+                 void* scratch, unsigned epoch, int max_ctas, cudaStream_t stream, const float* row_scale = nullptr,
+                 int rows_per_scale = 0);
 
 // ---- elementwise / normalisation (elementwise.cu) ----
 // img fp32 [n,3,H,W] -> patches bf16 [(flip?2n:n) * Hp*Wp, 768]; rows [n*Hp*Wp, 2n*Hp*Wp) hold the
@@ -90,7 +91,8 @@ int adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_s
 
 // ---- backward pass of the training step (train_bwd.cu, attention_bwd.cu) ----
 int transpose_bf16(const void* in, void* out, int R, int C, int batch, cudaStream_t stream);
-int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream);
+int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream, const float* row_scale = nullptr,
+                  int row_len = 0, int rows_per_scale = 0);
 int colsum_accumulate(const void* in, int is_f32, int R, int C, float* out, cudaStream_t stream);
 int colsum_sq_accumulate(const void* in, int R, int C, double* sum, double* sumsq, cudaStream_t stream);
 int gelu_fwd_bf16(const void* pre, void* out, long long n, cudaStream_t stream);
@@ -115,5 +117,8 @@ int attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv
 
 int adamw_multi(const vpb_tensor_entry* entries, const int* chunk_start, int n, int total_chunks, float beta1,
                 float beta2, float eps, float* sq_norm, float max_norm, cudaStream_t stream);
+
+int pose_pck_accuracy(const float* pred, const float* gt, const float* weight, int N, int K, float norm0, float norm1,
+                      float thr, float* acc, float* avg, int* cnt, cudaStream_t stream);
 
 }  // namespace vpb

@@ -56,20 +56,28 @@ int transpose_bf16(const void* in, void* out, int R, int C, int batch, cudaStrea
 // -------------------------------------------------------------------------------------------------
 // fp32 -> bf16 cast (master weights -> GEMM operands, fp32 gradient stream -> GEMM operand)
 // -------------------------------------------------------------------------------------------------
-__global__ void cast_f32_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long long n4) {
+__global__ void cast_f32_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long long n4,
+                                     const float* __restrict__ row_scale, int row_len4, int rows_per_scale) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
-  const float4 v = in[i];
+  float4 v = in[i];
+  if (row_scale != nullptr) {        // gradient of a stochastic-depth branch: times mask_i / keep_prob of the crop
+    const float s = __ldg(row_scale + (i / row_len4) / rows_per_scale);
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+  }
   out[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
 }
-int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream) {
+int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream, const float* row_scale, int row_len,
+                  int rows_per_scale) {
   VPB_REQUIRE(n > 0 && n % 4 == 0, "cast: n=%lld must be a positive multiple of 4", n);
-  VPB_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 ||
-                  ((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0),
+  VPB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0,
               "cast: unaligned buffers");
+  VPB_REQUIRE(row_scale == nullptr || (row_len > 0 && row_len % 4 == 0 && rows_per_scale > 0),
+              "cast: row_scale needs row_len %% 4 == 0 and rows_per_scale > 0");
   const long long n4 = n / 4;
   cast_f32_bf16_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(out), n4);
+      reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(out), n4, row_scale, row_len > 0 ? row_len / 4 : 1,
+      rows_per_scale > 0 ? rows_per_scale : 1);
   VPB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

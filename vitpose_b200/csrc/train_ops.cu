@@ -211,4 +211,49 @@ int adamw_multi(const vpb_tensor_entry* entries, const int* chunk_start, int n, 
   return 0;
 }
 
+// ---- training-time accuracy: pose_pck_accuracy (mmpose/core/evaluation/top_down_eval.py:133-215) -------------
+// pred / gt: arg-max coordinates [N,K,2] of output and target heatmaps (-1 where the map's maximum is <= 0);
+// distances are normalised by (norm0, norm1) = (H, W) applied to (x, y) exactly as the reference does, computed in
+// fp64 and stored as fp32 before the `< thr` test (NumPy stores them into a float32 array).
+__global__ void pck_accuracy_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                    const float* __restrict__ weight, int N, int K, double norm0, double norm1,
+                                    double thr, float* __restrict__ acc, float* __restrict__ avg, int* __restrict__ cnt) {
+  __shared__ double s_sum;
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) { s_sum = 0.0; s_cnt = 0; }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    int valid = 0, hit = 0;
+    for (int n = 0; n < N; ++n) {
+      const size_t i = static_cast<size_t>(n) * K + k;
+      if (!(weight[i] > 0.f)) continue;
+      const double dx = (static_cast<double>(pred[2 * i]) - static_cast<double>(gt[2 * i])) / norm0;
+      const double dy = (static_cast<double>(pred[2 * i + 1]) - static_cast<double>(gt[2 * i + 1])) / norm1;
+      const float d = static_cast<float>(sqrt(dx * dx + dy * dy));
+      ++valid;
+      if (static_cast<double>(d) < thr) ++hit;
+    }
+    const double a = valid > 0 ? static_cast<double>(hit) / valid : -1.0;
+    acc[k] = static_cast<float>(a);
+    if (valid > 0) {
+      atomicAdd(&s_sum, a);
+      atomicAdd(&s_cnt, 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *avg = s_cnt > 0 ? static_cast<float>(s_sum / s_cnt) : 0.f;
+    *cnt = s_cnt;
+  }
+}
+
+int pose_pck_accuracy(const float* pred, const float* gt, const float* weight, int N, int K, float norm0, float norm1,
+                      float thr, float* acc, float* avg, int* cnt, cudaStream_t stream) {
+  VPB_REQUIRE(N > 0 && K > 0 && norm0 > 0 && norm1 > 0, "pck_accuracy: bad shape");
+  pck_accuracy_kernel<<<1, 256, 0, stream>>>(pred, gt, weight, N, K, norm0, norm1, static_cast<double>(thr), acc, avg,
+                                             cnt);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace vpb

@@ -75,6 +75,7 @@ class TopDown(nn.Module):
         losses = dict()
         if self.with_keypoint:
             losses.update(self.keypoint_head.get_loss(output, target, target_weight))
+            losses.update(self.keypoint_head.get_accuracy(output, target, target_weight))
         return losses
 
     @staticmethod

@@ -203,7 +203,16 @@ class TopdownHeatmapSimpleHead(TopdownHeatmapBaseHead):
         return losses
 
     def get_accuracy(self, output, target, target_weight):
-        raise NotImplementedError('pose_pck_accuracy (training-time metric) is outside the inference hot path')
+        """simple_head.py:170-195. The reference copies both heatmap batches to the host every iteration and returns
+        a Python float; here arg-max and the PCK arithmetic stay on the device and ``acc_pose`` is a 0-dim CUDA tensor
+        (``_parse_losses`` and loggers call ``.mean()`` / ``.item()`` on it when they need the number)."""
+        from .. import ops
+        accuracy = dict()
+        if self.target_type == 'GaussianHeatmap':
+            _, avg_acc, _ = ops.pose_pck_accuracy(output.detach().float().contiguous(), target.float().contiguous(),
+                                                  target_weight.detach().squeeze(-1))
+            accuracy['acc_pose'] = avg_acc[0]
+        return accuracy
 
     # ---- execution --------------------------------------------------------------------------------------
     def _packed_weights(self, device):

@@ -41,7 +41,8 @@ def gemm(a, b, epilogue, bias=None, out=None, aux=None, period=0, max_ctas=0):
     return out
 
 
-def gemm_layernorm(a, b, epilogue, bias, aux, gamma, beta, eps=1e-6, period=0, out=None):
+def gemm_layernorm(a, b, epilogue, bias, aux, gamma, beta, eps=1e-6, period=0, out=None, row_scale=None,
+                   rows_per_scale=0):
     """Residual-stream GEMM + the LayerNorm that follows it, one kernel: returns (out fp32 [M,N], xn bf16 [M,N]).
     `out` may be the residual tensor itself (in-place update, as the forward pass does)."""
     _need(a, BF16, 'a'); _need(b, BF16, 'b'); _need(aux, torch.float32, 'aux')
@@ -54,7 +55,7 @@ def gemm_layernorm(a, b, epilogue, bias, aux, gamma, beta, eps=1e-6, period=0, o
     scratch = torch.empty(nbytes, device=a.device, dtype=torch.uint8)
     check(lib().vpb_gemm_bf16_layernorm(ptr(a), ptr(b), M, N, K, epilogue, ptr(bias), ptr(out), ptr(aux), period,
                                         ptr(gamma), ptr(beta), float(eps), ptr(xn), ptr(scratch), nbytes,
-                                        stream_ptr()), 'vpb_gemm_bf16_layernorm')
+                                        ptr(row_scale), int(rows_per_scale), stream_ptr()), 'vpb_gemm_bf16_layernorm')
     return out, xn
 
 
@@ -174,10 +175,13 @@ def transpose(x, batch=1):
     return out
 
 
-def cast_bf16(x):
+def cast_bf16(x, row_scale=None, rows_per_scale=0):
+    """fp32 -> bf16; with row_scale (fp32 [rows / rows_per_scale]) rows of the 2-D x are scaled first."""
     _need(x, torch.float32, 'x')
     out = torch.empty(x.shape, device=x.device, dtype=BF16)
-    check(lib().vpb_cast_f32_bf16(ptr(x), ptr(out), x.numel(), stream_ptr()), 'vpb_cast_f32_bf16')
+    row_len = x.shape[-1] if row_scale is not None else 0
+    check(lib().vpb_cast_f32_bf16(ptr(x), ptr(out), x.numel(), ptr(row_scale), int(row_len), int(rows_per_scale),
+                                  stream_ptr()), 'vpb_cast_f32_bf16')
     return out
 
 
@@ -296,3 +300,21 @@ def deconv_phase_dy(dy):
     out = torch.empty(4, n * h * w, cout, device=dy.device, dtype=BF16)
     check(lib().vpb_deconv_phase_dy(ptr(dy), ptr(out), n, h, w, cout, stream_ptr()), 'vpb_deconv_phase_dy')
     return out
+
+
+def pose_pck_accuracy(output, target, weight, thr=0.05, normalize=None):
+    """Device-side pose_pck_accuracy: output / target fp32 CUDA [N,K,H,W], weight fp32 CUDA [N,K] (> 0 = visible).
+    Returns (acc [K], avg_acc [1], cnt [1] int32) as CUDA tensors (no host synchronisation)."""
+    _need(output, torch.float32, 'output'); _need(target, torch.float32, 'target')
+    N, K, H, W = output.shape
+    n0, n1 = (float(H), float(W)) if normalize is None else (float(normalize[0]), float(normalize[1]))
+    pred = decode(output, mode=_lib.DECODE_NONE)['preds']
+    gt = decode(target, mode=_lib.DECODE_NONE)['preds']
+    dev = output.device
+    acc = torch.empty(K, device=dev, dtype=torch.float32)
+    avg = torch.empty(1, device=dev, dtype=torch.float32)
+    cnt = torch.empty(1, device=dev, dtype=torch.int32)
+    w = weight.reshape(N, K).float().contiguous()
+    check(lib().vpb_pose_pck_accuracy(ptr(pred), ptr(gt), ptr(w), N, K, n0, n1, float(thr), ptr(acc), ptr(avg),
+                                      ptr(cnt), stream_ptr()), 'vpb_pose_pck_accuracy')
+    return acc, avg, cnt

@@ -37,6 +37,25 @@ class _Linear:
         self.b = lin.bias.detach() if lin.bias is not None else None
 
 
+def drop_path_scales(bb, n, device):
+    """[(s_attn, s_mlp)] per block: fp32 [n] factors mask / keep_prob of timm's drop_path (per-sample Bernoulli), or
+    (None, None) where the branch is always kept. ``bb._drop_path_scales`` (same structure) overrides the random
+    draw — the parity tests inject the masks the oracle uses."""
+    forced = getattr(bb, '_drop_path_scales', None)
+    if forced is not None:
+        return forced
+    rates = torch.linspace(0, bb.drop_path_rate, bb.depth).tolist()
+    out = []
+    for p in rates:
+        if p <= 0.0 or not bb.training:
+            out.append((None, None))
+            continue
+        keep = 1.0 - p
+        pair = tuple(torch.floor(keep + torch.rand(n, device=device)).div_(keep).float().contiguous() for _ in range(2))
+        out.append(pair)
+    return out
+
+
 def _param_list(model):
     """(name, parameter) in a fixed order: the inputs of the autograd node."""
     return [(n, p) for n, p in model.named_parameters()]
@@ -66,9 +85,10 @@ class _NetworkFn(torch.autograd.Function):
         for blk in bb.blocks:
             blocks.append(dict(qkv=_Linear(blk.attn.qkv), proj=_Linear(blk.attn.proj), fc1=_Linear(blk.mlp.fc1),
                                fc2=_Linear(blk.mlp.fc2)))
-        # ---- ViT (vit.py:313-332); DropPath with rate 0 / eval is the identity
-        if bb.drop_path_rate > 0 and bb.training:
-            raise NotImplementedError('drop_path_rate > 0 is not implemented in the training step')
+        # ---- ViT (vit.py:313-332). Stochastic depth (DropPath, vit.py:48-56,132,138-139,233): block i drops the
+        # whole residual branch of a crop with probability linspace(0, drop_path_rate, depth)[i]; the surviving
+        # branches are divided by keep_prob. The per-crop factor goes into the residual GEMM epilogue.
+        scales = drop_path_scales(bb, n, img.device)
         patches = ops.im2col_patch16(img, flip=False)
         b0 = bb.blocks[0]
         x, xn = ops.gemm_layernorm(patches, pe.w, EPI_POS, pe.b, pos_tok, b0.norm1.weight.detach(),
@@ -79,14 +99,15 @@ class _NetworkFn(torch.autograd.Function):
             a = dict(x_in=x, xn1=xn)
             qkv = ops.gemm(xn, w['qkv'].w, EPI_BIAS, bias=w['qkv'].b)
             attn = ops.attention(qkv.view(n, T, 3 * D), heads).view(M, D)
+            s1, s2 = scales[l]
             x_mid, xn2 = ops.gemm_layernorm(attn, w['proj'].w, EPI_RESID, w['proj'].b, x, blk.norm2.weight.detach(),
-                                            blk.norm2.bias.detach(), 1e-6)
+                                            blk.norm2.bias.detach(), 1e-6, row_scale=s1, rows_per_scale=T)
             pre = ops.gemm(xn2, w['fc1'].w, EPI_BIAS, bias=w['fc1'].b)
             h = ops.gelu_fwd(pre)
             nxt = bb.blocks[l + 1].norm1 if l + 1 < depth else bb.last_norm
             x, xn = ops.gemm_layernorm(h, w['fc2'].w, EPI_RESID, w['fc2'].b, x_mid, nxt.weight.detach(),
-                                       nxt.bias.detach(), 1e-6)
-            a.update(qkv=qkv, attn=attn, x_mid=x_mid, xn2=xn2, pre=pre, h=h)
+                                       nxt.bias.detach(), 1e-6, row_scale=s2, rows_per_scale=T)
+            a.update(qkv=qkv, attn=attn, x_mid=x_mid, xn2=xn2, pre=pre, h=h, s1=s1, s2=s2)
             acts.append(a)
         s.update(patches=patches, acts=acts, x_final=x, blocks=blocks, pe=pe)
         # ---- head (simple_head.py:197-202), BatchNorm2d in training mode
@@ -212,7 +233,7 @@ class _NetworkFn(torch.autograd.Function):
             a, w, blk = s['acts'][l], s['blocks'][l], bb.blocks[l]
             pfx = f'backbone.blocks.{l}.'
             # x_out = x_mid + fc2(gelu(fc1(norm2(x_mid))))            (vit.py:139)
-            dyb = ops.cast_bf16(dx)
+            dyb = ops.cast_bf16(dx, a['s2'], T)                # gradient of the (possibly dropped / rescaled) branch
             dh = linear_bwd(pfx + 'mlp.fc2', w['fc2'], dyb, a['h'])
             dpre = ops.gelu_bwd(a['pre'], dh)
             dxn2 = linear_bwd(pfx + 'mlp.fc1', w['fc1'], dpre, a['xn2'])
@@ -220,7 +241,7 @@ class _NetworkFn(torch.autograd.Function):
             ops.layernorm_bwd(a['x_mid'], blk.norm2.weight.detach(), dxn2, dx, dg_, db_, 1e-6)
             g[pfx + 'norm2.weight'], g[pfx + 'norm2.bias'] = dg_, db_
             # x_mid = x_in + proj(attention(qkv(norm1(x_in))))        (vit.py:138)
-            dyb = ops.cast_bf16(dx)
+            dyb = ops.cast_bf16(dx, a['s1'], T)
             dattn = linear_bwd(pfx + 'attn.proj', w['proj'], dyb, a['attn'])
             dqkv = ops.attention_bwd(a['qkv'].view(n, T, 3 * D), a['attn'].view(n, T, D), dattn.view(n, T, D), heads)
             dxn1 = linear_bwd(pfx + 'attn.qkv', w['qkv'], dqkv.view(M, 3 * D), a['xn1'])
