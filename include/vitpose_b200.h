@@ -217,6 +217,21 @@ int vpb_deconv_gather_x(const void* x, void* out, int n, int h, int w, int cin, 
 int vpb_deconv_gather_dy(const void* dy, void* out, int n, int h, int w, int cout, void* stream);
 int vpb_deconv_phase_dy(const void* dy, void* out, int n, int h, int w, int cout, void* stream);
 
+/* ---- post-decode evaluation step ----
+ * Per-image rescoring + OKS NMS of the top-down COCO datasets (topdown_coco_dataset.py:476-503; oks_iou / oks_nms /
+ * soft_oks_nms, mmpose/core/post_processing/nms.py:51-207). The P poses are grouped by image: group g is rows
+ * [group_start[g], group_start[g+1]).
+ *   kpts        fp32 [P,K,3] (x, y, score);  areas fp64 [P];  box_scores fp64 [P]
+ *   var         fp64 [K] = (2 * sigma_k)^2
+ *   rescore     != 0: pose score = mean(joint scores > vis_thr) * box score; else box_scores are the pose scores
+ *   use_vis     != 0: only joints whose DETECTION score exceeds vis_thr enter the OKS (nms.py:80-82)
+ *   soft        0: oks_nms (keep while OKS <= thr); 1: soft_oks_nms (Gaussian rescoring, at most max_dets per image)
+ *   scores_out  fp64 [P] scores used;  keep int32 [P]: kept row indices of group g, in selection order, starting at
+ *               keep[group_start[g]];  keep_count int32 [G].  max_group = largest group size (<= 2048). */
+int vpb_oks_nms(const float* kpts, const double* areas, const double* box_scores, const int32_t* group_start, int G,
+                int K, int max_group, const double* var, double thr, int use_vis, double vis_thr, int rescore, int soft,
+                int max_dets, double* scores_out, int32_t* keep, int32_t* keep_count, void* stream);
+
 /* ---- preprocessing ----
  * TopDownAffine + ToTensor + NormalizeTensor for n boxes (mmpose/datasets/pipelines/top_down_transform.py:295-364,
  * shared_transform.py:21-65): out[i] = ((warpAffine_u8(src[i], M_i, (out_w,out_h), INTER_LINEAR) / 255) - mean) / std

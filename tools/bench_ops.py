@@ -104,8 +104,42 @@ def main():
     print('est step ms', round(total, 3), 'crops/s', round(a.crops / total * 1e3, 1))
 
 
+def bench_nms(images=5000, poses=20, K=17):
+    """Rescoring + OKS NMS of a COCO-val-sized evaluation (5000 images) in one launch, vs the NumPy oracle."""
+    import time
+    import numpy as np
+    from oracle import nms_np as O
+    from vitpose_b200.core.post_processing import oks_nms_batched
+    rng = np.random.RandomState(0)
+    P = images * poses
+    people = rng.rand(images, 5, K, 2).astype(np.float32) * 200
+    who = rng.randint(5, size=(images, poses))
+    kp = np.zeros((images, poses, K, 3), dtype=np.float32)
+    kp[..., :2] = people[np.arange(images)[:, None], who] + rng.randn(images, poses, K, 2).astype(np.float32) * 3
+    kp[..., 2] = rng.rand(images, poses, K)
+    kp = kp.reshape(P, K, 3)
+    areas, box = rng.rand(P) * 3e4 + 5e3, rng.rand(P).astype(np.float32)
+    starts = np.arange(images + 1, dtype=np.int32) * poses
+    oks_nms_batched(kp, areas, box, starts, 0.9, None, 0.2, rescore=True, rescore_vis_thr=0.2)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    keep, _ = oks_nms_batched(kp, areas, box, starts, 0.9, None, 0.2, rescore=True, rescore_vis_thr=0.2)
+    t_gpu = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for i in range(200):
+        lo = starts[i]
+        sc = O.rescore(kp[lo:lo + poses], box[lo:lo + poses], 0.2).astype(np.float64)
+        O.oks_nms(kp[lo:lo + poses].reshape(poses, -1), sc, areas[lo:lo + poses], 0.9, None, 0.2)
+    t_cpu = (time.perf_counter() - t0) / 200 * images
+    print('oks_nms', json.dumps(dict(images=images, poses=P, gpu_call_ms=round(t_gpu * 1e3, 2),
+                                     numpy_ms=round(t_cpu * 1e3, 1), kept=int(sum(len(k) for k in keep)))))
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'nms':
+        bench_nms()
+    else:
+        main()
 
 
 def bench_preprocess(crops=256):

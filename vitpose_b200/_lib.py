@@ -89,6 +89,8 @@ _SIGS = {
                                 c_void_p]),
     'vpb_pose_pck_accuracy': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_void_p,
                                       c_void_p, c_void_p, c_void_p]),
+    'vpb_oks_nms': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, ctypes.c_double,
+                            c_int, ctypes.c_double, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'vpb_gemm_bf16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                               c_int, c_int, c_void_p]),
     'vpb_gemm_layernorm_scratch_bytes': (c_size_t, [c_int, c_int]),

@@ -50,3 +50,72 @@ def transform_preds(coords, center, scale, output_size, use_udp=False):
     target = np.ones_like(coords)
     target[:, :2] = out
     return target
+
+
+# ---- post-decode evaluation step: OKS NMS (mmpose/core/post_processing/nms.py:51-207) ------------------------------
+COCO_SIGMAS = np.array([.26, .25, .25, .35, .35, .79, .79, .72, .72, .62, .62, 1.07, 1.07, .87, .87, .89, .89]) / 10.0
+
+
+def oks_nms_batched(kpts, areas, scores, group_start, thr, sigmas=None, vis_thr=None, soft=False, max_dets=20,
+                    rescore=False, rescore_vis_thr=None):
+    """All images of an evaluation at once: ``kpts`` [P,K,3], ``areas`` [P], ``scores`` [P] (box scores when
+    ``rescore``), ``group_start`` [G+1] (poses of image g are rows group_start[g]:group_start[g+1]).
+    Returns (list of G index arrays in selection order — global row indices —, the [P] scores used).
+    One CTA per image runs rescoring (topdown_coco_dataset.py:476-490) and oks_nms / soft_oks_nms on the GPU."""
+    _lib.require_cuda()
+    dev = torch.device('cuda')
+    kpts = np.ascontiguousarray(kpts, dtype=np.float32)
+    P, K, _ = kpts.shape
+    gs = np.ascontiguousarray(group_start, dtype=np.int32)
+    G = len(gs) - 1
+    if P == 0 or G <= 0:
+        return [np.zeros(0, dtype=np.intp) for _ in range(max(G, 0))], np.zeros(0)
+    sig = COCO_SIGMAS if sigmas is None else np.asarray(sigmas, dtype=np.float64)
+    assert len(sig) == K, 'one sigma per keypoint'
+    var = torch.from_numpy((sig * 2) ** 2).to(dev)
+    d_k = torch.from_numpy(kpts).to(dev)
+    d_a = torch.from_numpy(np.ascontiguousarray(areas, dtype=np.float64)).to(dev)
+    d_s = torch.from_numpy(np.ascontiguousarray(scores, dtype=np.float64)).to(dev)
+    d_g = torch.from_numpy(gs).to(dev)
+    out_s = torch.empty(P, device=dev, dtype=torch.float64)
+    keep = torch.empty(P, device=dev, dtype=torch.int32)
+    cnt = torch.empty(G, device=dev, dtype=torch.int32)
+    use_vis = vis_thr is not None
+    vt = float(vis_thr) if use_vis else (float(rescore_vis_thr) if rescore_vis_thr is not None else 0.0)
+    if rescore and rescore_vis_thr is not None and use_vis:
+        assert float(rescore_vis_thr) == float(vis_thr), 'one visibility threshold per call'
+    _lib.check(_lib.lib().vpb_oks_nms(_lib.ptr(d_k), _lib.ptr(d_a), _lib.ptr(d_s), _lib.ptr(d_g), G, K,
+                                      int(np.diff(gs).max()), _lib.ptr(var), float(thr), int(use_vis), vt,
+                                      int(bool(rescore)), int(bool(soft)), int(max_dets), _lib.ptr(out_s),
+                                      _lib.ptr(keep), _lib.ptr(cnt), _lib.stream_ptr()), 'vpb_oks_nms')
+    keep, cnt = keep.cpu().numpy(), cnt.cpu().numpy()
+    return [keep[gs[g]:gs[g] + cnt[g]].astype(np.intp) for g in range(G)], out_s.cpu().numpy()
+
+
+def _db_arrays(kpts_db, score_per_joint):
+    if score_per_joint:
+        scores = np.array([k['score'].mean() for k in kpts_db])
+    else:
+        scores = np.array([k['score'] for k in kpts_db])
+    kpts = np.array([np.asarray(k['keypoints']).reshape(-1, 3) for k in kpts_db])
+    areas = np.array([k['area'] for k in kpts_db])
+    return kpts, areas, scores
+
+
+def oks_nms(kpts_db, thr, sigmas=None, vis_thr=None, score_per_joint=False):
+    """Reference signature (nms.py:89-128): list of dicts with 'keypoints', 'score', 'area' -> indices to keep."""
+    if len(kpts_db) == 0:
+        return []
+    kpts, areas, scores = _db_arrays(kpts_db, score_per_joint)
+    keep, _ = oks_nms_batched(kpts, areas, scores, [0, len(kpts_db)], thr, sigmas, vis_thr)
+    return keep[0]
+
+
+def soft_oks_nms(kpts_db, thr, max_dets=20, sigmas=None, vis_thr=None, score_per_joint=False):
+    """Reference signature (nms.py:154-207)."""
+    if len(kpts_db) == 0:
+        return []
+    kpts, areas, scores = _db_arrays(kpts_db, score_per_joint)
+    keep, _ = oks_nms_batched(kpts, areas, scores, [0, len(kpts_db)], thr, sigmas, vis_thr, soft=True,
+                              max_dets=max_dets)
+    return keep[0]

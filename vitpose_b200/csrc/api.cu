@@ -314,6 +314,16 @@ int vpb_pose_pck_accuracy(const float* pred, const float* gt, const float* weigh
   return pose_pck_accuracy(pred, gt, weight, N, K, norm0, norm1, thr, acc, avg, cnt, as_stream(stream));
 }
 
+int vpb_oks_nms(const float* kpts, const double* areas, const double* box_scores, const int32_t* group_start, int G,
+                int K, int max_group, const double* var, double thr, int use_vis, double vis_thr, int rescore, int soft,
+                int max_dets, double* scores_out, int32_t* keep, int32_t* keep_count, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  return prof_run("oks_nms", st, [&] {
+    return oks_nms(kpts, areas, box_scores, group_start, G, K, max_group, var, thr, use_vis, vis_thr, rescore, soft,
+                   max_dets, scores_out, keep, keep_count, st);
+  });
+}
+
 // ---- backward-pass operators of the training step ----
 int vpb_transpose_bf16(const void* in, void* out, int R, int C, int batch, void* stream) {
   return transpose_bf16(in, out, R, C, batch, as_stream(stream));

@@ -121,4 +121,9 @@ int adamw_multi(const vpb_tensor_entry* entries, const int* chunk_start, int n, 
 int pose_pck_accuracy(const float* pred, const float* gt, const float* weight, int N, int K, float norm0, float norm1,
                       float thr, float* acc, float* avg, int* cnt, cudaStream_t stream);
 
+// ---- post-decode evaluation step (nms.cu) ----
+int oks_nms(const float* kpts, const double* areas, const double* box_scores, const int* group_start, int G, int K,
+            int max_group, const double* var, double thr, int use_vis, double vis_thr, int rescore, int soft,
+            int max_dets, double* scores_out, int* keep, int* keep_count, cudaStream_t stream);
+
 }  // namespace vpb
