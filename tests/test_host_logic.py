@@ -186,3 +186,35 @@ def test_joints_mse_loss_has_no_cpu_path(golden_dir):
     o, t, w = (torch.from_numpy(g[k]) for k in ('output', 'target', 'weight'))
     with pytest.raises(_lib.VitposeLibError):
         loss(o, t, w)          # value parity vs the golden KATs is checked on the GPU (tests/test_training_ops.py)
+
+
+def test_mae_checkpoint_adaptation(tmp_path):
+    """mmcv_custom/checkpoint.py:361-395: a 224x224 MAE ViT (14x14 patch kernel, 14x14 position grid + cls token,
+    `model` key, `module.` prefix) loaded into the 256x192 pose backbone: patch kernel zero-padded to 16x16, position
+    tokens bicubically resized to 16x12, cls slot kept."""
+    from vitpose_b200.checkpoint import adapt_state_dict, extract_state_dict
+    cfg = configs.tiny_model_cfg(5)
+    D = cfg['backbone']['embed_dim']
+    g = torch.Generator().manual_seed(0)
+    src = {'module.patch_embed.proj.weight': torch.randn(D, 3, 14, 14, generator=g),
+           'module.patch_embed.proj.bias': torch.randn(D, generator=g),
+           'module.pos_embed': torch.randn(1, 1 + 14 * 14, D, generator=g),
+           'module.blocks.0.norm1.weight': torch.randn(D, generator=g)}
+    path = os.path.join(str(tmp_path), 'mae.pth')
+    torch.save({'model': src}, path)
+    bb = V.build_backbone(dict(cfg['backbone'], patch_padding='pad'))
+    bb.init_weights(pretrained=path)
+    w = bb.patch_embed.proj.weight.detach()
+    assert torch.equal(w[:, :, 1:15, 1:15], src['module.patch_embed.proj.weight'])
+    assert float(w[:, :, 0].abs().max()) == 0 and float(w[:, :, 15].abs().max()) == 0
+    pe = src['module.pos_embed']
+    ref = F.interpolate(pe[:, 1:].reshape(1, 14, 14, D).permute(0, 3, 1, 2), size=(16, 12), mode='bicubic',
+                        align_corners=False).permute(0, 2, 3, 1).flatten(1, 2)
+    assert torch.equal(bb.pos_embed.detach()[:, :1], pe[:, :1])
+    assert torch.allclose(bb.pos_embed.detach()[:, 1:], ref)
+    assert torch.equal(bb.blocks[0].norm1.weight.detach(), src['module.blocks.0.norm1.weight'])
+    # resize modes and the ViTPose+ expert split
+    sd = extract_state_dict({'state_dict': {k[7:]: v for k, v in src.items()}})
+    bic = adapt_state_dict(sd, bb, 'bicubic')['patch_embed.proj.weight']
+    assert bic.shape[2:] == (16, 16) and torch.allclose(
+        bic, F.interpolate(sd['patch_embed.proj.weight'], size=(16, 16), mode='bicubic', align_corners=False))

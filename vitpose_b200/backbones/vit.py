@@ -105,10 +105,13 @@ class ViT(nn.Module):
     def init_weights(self, pretrained=None):
         """vit.py:286-304: trunc-normal(0.02) Linear weights, zero biases, LayerNorm 1/0."""
         if pretrained is not None:
-            ckpt = torch.load(pretrained, map_location='cpu')
-            sd = ckpt.get('state_dict', ckpt.get('model', ckpt))
+            # base_backbone.py:init_weights -> mmcv_custom load_checkpoint(self, pretrained, strict=False,
+            # patch_padding=self.patch_padding): MAE-pretrain adaptation of patch / position embeddings
+            from ..checkpoint import adapt_state_dict, extract_state_dict
+            sd = extract_state_dict(torch.load(pretrained, map_location='cpu'))
             sd = {k[len('backbone.'):] if k.startswith('backbone.') else k: v for k, v in sd.items()}
-            self.load_state_dict(sd, strict=False)
+            self.load_state_dict(adapt_state_dict(sd, self, self.patch_padding), strict=False)
+            self._engine = None
             return
         for m in self.modules():
             if isinstance(m, nn.Linear):
