@@ -142,6 +142,10 @@ enum {
 /* C = A[M,K] (bf16, row-major) x B[N,K]^T (bf16, row-major) on tcgen05 tensor cores. max_ctas <= 0: one per SM. */
 int vpb_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, void* out,
                   int ldo, const float* aux, int period, int max_ctas, void* stream);
+/* out fp32 [M,ldo] += At^T . Bt for ROW-MAJOR At bf16 [K,M] and Bt bf16 [K,N] (M, N multiples of 8): a weight
+ * gradient dW[N_out,K_in] += dY[tokens,N_out]^T . X[tokens,K_in] straight from dY and X — both tiles are consumed as
+ * MN-major tensor-core operands (no transposed copies), the contraction over the tokens is split over CTAs. */
+int vpb_gemm_bf16_atb_accum(const void* At, const void* Bt, int M, int N, int K, float* out, int ldo, void* stream);
 /* Residual-stream GEMM with the following LayerNorm fused into its epilogue:
  *   out fp32 [M,N] = (epilogue == VPB_EPI_RESID_F32 ? aux[M,N] : aux[row % period, N]) + A.B^T + bias
  *   xn  bf16 [M,N] = LayerNorm(out row, eps) * gamma + beta
@@ -174,7 +178,8 @@ int vpb_tokens_to_nchw_f32(const void* tokens, float* out, int n, int T, int D, 
  * operators that replace the autograd nodes of the path's modules. The tensor-core work of the backward pass is
  * vpb_gemm_bf16 itself on transposed operands:
  *   dgrad  dX[M,K] = dY[M,N] . W[N,K]   = vpb_gemm_bf16(A = dY, B = W^T [K,N], VPB_EPI_BIAS_BF16 / _RESID_F32)
- *   wgrad  dW[N,K] += dY^T . X          = vpb_gemm_bf16(A = dY^T [N,M], B = X^T [K,M], VPB_EPI_ACCUM_F32, out = dW)
+ *   wgrad  dW[N,K] += dY^T . X          = vpb_gemm_bf16_atb_accum(At = dY [M,N], Bt = X [M,K], out = dW)
+ *                                         (or vpb_gemm_bf16(dY^T, X^T, VPB_EPI_ACCUM_F32) on transposed copies)
  * All matrices row-major; bf16 unless stated; gradients of parameters are fp32 and ACCUMULATED into their buffers. */
 int vpb_transpose_bf16(const void* in, void* out, int R, int C, int batch, void* stream);   /* out[b][C,R] = in[b][R,C]^T */
 /* out = bf16(in), optionally times row_scale[(i / row_len) / rows_per_scale] (gradient of a stochastic-depth branch) */

@@ -113,6 +113,10 @@ def test_linear_dgrad_wgrad_as_gemms():
         dw2 = torch.ones(n_, k_, device=_dev())
         ops.gemm(ops.transpose(dy2), ops.transpose(x2), _lib.EPI_ACCUM_F32, out=dw2)
         _close(f'wgrad split-K {n_}x{k_}x{m_}', dw2, 1 + dy2.float().t() @ x2.float(), 2e-3)
+        # the same product straight from dY and X (MN-major operands, no transposed copies)
+        dw3 = torch.ones(n_, k_, device=_dev())
+        ops.gemm_atb_accum(dy2, x2, dw3)
+        _close(f'wgrad At.B {n_}x{k_}x{m_}', dw3, 1 + dy2.float().t() @ x2.float(), 2e-3)
 
 
 def test_bn_train_relu_fwd_bwd():

@@ -93,6 +93,7 @@ _SIGS = {
                             c_int, ctypes.c_double, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'vpb_gemm_bf16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                               c_int, c_int, c_void_p]),
+    'vpb_gemm_bf16_atb_accum': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     'vpb_gemm_layernorm_scratch_bytes': (c_size_t, [c_int, c_int]),
     'vpb_gemm_bf16_layernorm': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                         c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_int,

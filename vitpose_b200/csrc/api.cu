@@ -252,6 +252,9 @@ int vpb_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogu
                   int ldo, const float* aux, int period, int max_ctas, void* stream) {
   return gemm_bf16(A, B, M, N, K, epilogue, bias, out, ldo, aux, period, max_ctas, as_stream(stream));
 }
+int vpb_gemm_bf16_atb_accum(const void* At, const void* Bt, int M, int N, int K, float* out, int ldo, void* stream) {
+  return gemm_bf16_atb_accum(At, Bt, M, N, K, out, ldo, 0, as_stream(stream));
+}
 int vpb_gemm_bf16_layernorm(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias,
                             float* out, const float* aux, int period, const float* gamma, const float* beta, float eps,
                             void* xn, void* scratch, size_t scratch_bytes, const float* row_scale, int rows_per_scale,

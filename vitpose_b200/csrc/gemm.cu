@@ -6,11 +6,11 @@
 
 namespace vpb {
 
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, int OPM = 0>
 static int launch_gemm_inst(const GemmMaps& maps, const GemmParams& p, int max_ctas, cudaStream_t stream) {
   constexpr int smem = gemm_smem_bytes(BN, EPI, CG);
   static bool configured = false;
-  auto kern = gemm_bf16_tn_kernel<BN, EPI, CG>;
+  auto kern = gemm_bf16_tn_kernel<BN, EPI, CG, OPM>;
   if (!configured) {
     VPB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
@@ -257,6 +257,38 @@ int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue
                reinterpret_cast<unsigned long long*>(scratch),
                ln_region_words(M, N), epoch, eps};
   return launch_gemm(maps, p, bn, epi, cg, max_ctas, stream);
+}
+
+// ---- out[M, N] += At^T . Bt for row-major At [K, M], Bt [K, N] (weight gradients) ------------------------------
+int gemm_bf16_atb_accum(const void* At, const void* Bt, int M, int N, int K, float* out, int ldo, int max_ctas,
+                        cudaStream_t stream) {
+  VPB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  VPB_REQUIRE(M % 8 == 0 && N % 8 == 0, "gemm(At, Bt): M=%d and N=%d must be multiples of 8 (16-byte row pitch)", M, N);
+  VPB_REQUIRE(((reinterpret_cast<uintptr_t>(At) | reinterpret_cast<uintptr_t>(Bt) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+                  ldo % 4 == 0, "gemm(At, Bt): operands / out must be 16-byte aligned, ldo %% 4 == 0");
+  const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  GemmMaps maps;
+  uint64_t dims_a[2] = {(uint64_t)M, (uint64_t)K};
+  uint64_t str_a[1] = {(uint64_t)M * 2};
+  uint32_t box[2] = {64u, (uint32_t)GEMM_BK};
+  if (make_tma_desc(&maps.a, TMA_BF16, At, 2, dims_a, str_a, box, TMA_SWIZZLE_128B)) return -1;
+  uint64_t dims_b[2] = {(uint64_t)N, (uint64_t)K};
+  uint64_t str_b[1] = {(uint64_t)N * 2};
+  if (make_tma_desc(&maps.b, TMA_BF16, Bt, 2, dims_b, str_b, box, TMA_SWIZZLE_128B)) return -1;
+  maps.out = maps.a;
+  maps.aux = maps.a;
+  maps.ln = maps.a;
+  GemmParams p{M, N, K, nullptr, out, ldo, nullptr, 0, 1, nullptr, 1, nullptr, nullptr, nullptr, 0, 0u, 0.0f};
+  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + bn - 1) / bn);
+  const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  int want = (2 * sm_count() + tiles - 1) / tiles;
+  if (want > k_blocks / 8) want = k_blocks / 8;
+  if (want < 1) want = 1;
+  const int kb_per = (k_blocks + want - 1) / want;
+  p.ksplit = (k_blocks + kb_per - 1) / kb_per;
+  if (bn == 256) return launch_gemm_inst<256, EPI_ACCUM_F32, 1, 1>(maps, p, max_ctas, stream);
+  if (bn == 128) return launch_gemm_inst<128, EPI_ACCUM_F32, 1, 1>(maps, p, max_ctas, stream);
+  return launch_gemm_inst<64, EPI_ACCUM_F32, 1, 1>(maps, p, max_ctas, stream);
 }
 
 }  // namespace vpb

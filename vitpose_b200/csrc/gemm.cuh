@@ -203,7 +203,10 @@ __device__ __forceinline__ void ln_row_stats(const GemmParams& p, int m_blk, int
 // each CTA stages its own 128 A rows and half of the B tile, the leader CTA issues M=256 MMAs that read both halves,
 // so per-SM shared-memory traffic per MAC drops by a third (1-CTA 128x256 tiles are smem-bandwidth bound:
 // 96 B/clk of operand reads + 96 B/clk of TMA writes against 128 B/clk).
-template <int BN, int EPI, int CG>
+// OPM = 1: both operands are given TRANSPOSED, A^T [K, M] and B^T [K, N] row-major (what a weight gradient
+// dW = dY^T X has: the contraction runs over the rows of dY and X). Their tiles are TMA-loaded as [64 k-rows] x
+// [64-column chunks] and consumed as MN-major UMMA operands, so no transposed copies of the activations are made.
+template <int BN, int EPI, int CG, int OPM = 0>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux,
@@ -213,8 +216,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   constexpr int B_BYTES = BN * 128 / CG;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = gemm_tmem_cols(BN);
-  constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM * CG, BN);
+  constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM * CG, BN, OPM, OPM);
   static_assert(CG == 1 || (CG == 2 && BN % 32 == 0), "CTA pairs split the B tile in two halves");
+  static_assert(OPM == 0 || (CG == 1 && BN % 64 == 0), "MN-major operands: single-CTA tiles, 64-column chunks");
+  constexpr int OPM_CHUNK = GEMM_BK * 128;      // [64 k-rows][64 columns] bf16
   constexpr bool STAGED = gemm_epi_staged(EPI);
   constexpr int CHUNK = (gemm_epi_adds_tile(EPI)) ? 32 : 64;     // columns per 128-byte staging row
   constexpr int GROUPS = gemm_epi_groups(EPI);                // epilogue warpgroups
@@ -306,8 +311,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             tma_load_2d_pair(sb, &tma_b, leader_full, kb * GEMM_BK, n_blk * BN + cta_rank * (BN / 2));
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
-            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+            if constexpr (OPM == 1) {
+#pragma unroll
+              for (int c = 0; c < GEMM_BM / 64; ++c)
+                tma_load_2d(sa + c * OPM_CHUNK, &tma_a, &full_bar[stage], m_blk * GEMM_BM + c * 64, kb * GEMM_BK);
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c)
+                tma_load_2d(sb + c * OPM_CHUNK, &tma_b, &full_bar[stage], n_blk * BN + c * 64, kb * GEMM_BK);
+            } else {
+              tma_load_2d(sa, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+              tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -334,6 +348,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             if constexpr (CG == 2)
               umma_bf16_ss_pair(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), IDESC,
                                 (kb > kb0 || k != 0) ? 1u : 0u);
+            else if constexpr (OPM == 1)     // 16 k-rows = 2048 B per step; 64-column chunks OPM_CHUNK apart
+              umma_bf16_ss(d_tmem, umma_desc_mn_sw128(a_addr + k * 2048, OPM_CHUNK),
+                           umma_desc_mn_sw128(b_addr + k * 2048, OPM_CHUNK), IDESC, (kb > kb0 || k != 0) ? 1u : 0u);
             else
               umma_bf16_ss(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), IDESC,
                            (kb > kb0 || k != 0) ? 1u : 0u);

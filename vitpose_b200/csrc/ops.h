@@ -21,6 +21,10 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue,
                 cudaStream_t stream);
 int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, void* out, int ldo,
               const float* aux, int period, int max_ctas, cudaStream_t stream);
+// out[M, N] (fp32, leading dimension ldo) += At^T . Bt for ROW-MAJOR At [K, M], Bt [K, N]: the weight gradient
+// dW = dY^T X straight from dY and X (MN-major tensor-core operands, K split over CTAs, atomic accumulation)
+int gemm_bf16_atb_accum(const void* At, const void* Bt, int M, int N, int K, float* out, int ldo, int max_ctas,
+                        cudaStream_t stream);
 // Residual / patch-embed GEMM (epilogue EPI_RESID_F32 or EPI_POS_F32, out fp32 [M, N]) that also writes
 // xn = LayerNorm(out) * gamma + beta as bf16 [M, N] from the same kernel. `scratch` (gemm_ln_scratch_bytes(M, N)
 // bytes, 16-byte aligned) holds the per-row partial statistics the column tiles exchange; gemm_ln_scratch_init

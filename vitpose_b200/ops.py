@@ -41,6 +41,17 @@ def gemm(a, b, epilogue, bias=None, out=None, aux=None, period=0, max_ctas=0):
     return out
 
 
+def gemm_atb_accum(at, bt, out):
+    """out [M,N] fp32 += at^T @ bt for row-major bf16 at [K,M], bt [K,N] (weight gradient from dY and X)."""
+    _need(at, BF16, 'at'); _need(bt, BF16, 'bt'); _need(out, torch.float32, 'out')
+    K, M = at.shape
+    N = bt.shape[1]
+    assert bt.shape[0] == K and out.shape == (M, N)
+    check(lib().vpb_gemm_bf16_atb_accum(ptr(at), ptr(bt), M, N, K, ptr(out), out.stride(0), stream_ptr()),
+          'vpb_gemm_bf16_atb_accum')
+    return out
+
+
 def gemm_layernorm(a, b, epilogue, bias, aux, gamma, beta, eps=1e-6, period=0, out=None, row_scale=None,
                    rows_per_scale=0):
     """Residual-stream GEMM + the LayerNorm that follows it, one kernel: returns (out fp32 [M,N], xn bf16 [M,N]).

@@ -22,10 +22,11 @@ BF16 = torch.bfloat16
 EPI_BIAS, EPI_RESID, EPI_POS, EPI_NCHW = _lib.EPI_BIAS_BF16, _lib.EPI_RESID_F32, _lib.EPI_POS_F32, _lib.EPI_NCHW_F32
 
 
-def _wgrad(dy_t, x_t, out):
-    """out [N, K] fp32 += dY^T X, given dY^T [N, M] and X^T [K, M]: the forward GEMM kernel with the contraction
-    (all M token rows of the batch) split over CTAs, because N x K alone is only a handful of tiles."""
-    ops.gemm(dy_t, x_t, _lib.EPI_ACCUM_F32, out=out)
+def _wgrad(dy, x, out):
+    """out [N, K] fp32 += dY^T X from dY [M, N] and X [M, K] as they are (row-major): both tiles are consumed as
+    MN-major tensor-core operands and the contraction (all M token rows of the batch) is split over CTAs, because
+    N x K alone is only a handful of tiles."""
+    ops.gemm_atb_accum(dy, x, out)
 
 
 class _Linear:
@@ -184,7 +185,7 @@ class _NetworkFn(torch.autograd.Function):
         act = s['act_last'].view(n * P, -1)
         C = act.shape[1]
         dwf = zeros(Kp, C)
-        _wgrad(ops.transpose(dy), ops.transpose(act), dwf)
+        _wgrad(dy, act, dwf)
         dbf = zeros(Kp)
         ops.colsum_accumulate(dy, dbf)
         g['keypoint_head.final_layer.weight'] = dwf[:K].reshape(K, C, 1, 1)
@@ -204,8 +205,8 @@ class _NetworkFn(torch.autograd.Function):
                                    bn.bias.detach(), dgam, dbet)
             g[f'keypoint_head.deconv_layers.{3 * i + 1}.weight'] = dgam
             g[f'keypoint_head.deconv_layers.{3 * i + 1}.bias'] = dbet
-            a_t = ops.transpose(ops.deconv_phase_dy(draw), batch=4)                      # [4, cout, pixels]
-            b_t = ops.transpose(ops.deconv_gather_x(xin), batch=4)                       # [4, 4*cin, pixels]
+            a_t = ops.deconv_phase_dy(draw)                                             # [4, pixels, cout]
+            b_t = ops.deconv_gather_x(xin)                                               # [4, pixels, 4*cin]
             dwp = scratch_zeros(4, cout, wp_.shape[2])
             for ph in range(4):
                 _wgrad(a_t[ph], b_t[ph], dwp[ph])
@@ -224,7 +225,7 @@ class _NetworkFn(torch.autograd.Function):
         def linear_bwd(name, lin, dy_bf16, x_bf16, want_dx=True):
             """gradients of y = x W^T + b given dy: dW, db into g[...]; returns dx (bf16)."""
             dw, dbias = zeros(*lin.w.shape), zeros(lin.w.shape[0])
-            _wgrad(ops.transpose(dy_bf16), ops.transpose(x_bf16), dw)
+            _wgrad(dy_bf16, x_bf16, dw)
             ops.colsum_accumulate(dy_bf16, dbias)
             g[name + '.weight'], g[name + '.bias'] = dw, dbias
             return ops.gemm(dy_bf16, lin.wt, EPI_BIAS) if want_dx else None
