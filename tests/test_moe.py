@@ -1,0 +1,131 @@
+"""the ViTPose+ variant (ViTMoE backbone + TopDownMoE detector). Host logic on CPU; the B200
+path against the fp32 oracle (MoEMlp restated functionally) on a batch that MIXES dataset indices (-m gpu)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vitpose_torch as VT
+from vitpose_b200 import configs, synthetic
+
+
+def _moe_cfg(num_expert=3, part=32, depth=2):
+    cfg = configs.tiny_model_cfg(5, depth=depth)
+    cfg['type'] = 'TopDownMoE'
+    cfg['backbone'].update(type='ViTMoE', num_expert=num_expert, part_features=part, drop_path_rate=0.0)
+    cfg['associate_keypoint_head'] = [dict(cfg['keypoint_head'], out_channels=4),
+                                      dict(cfg['keypoint_head'], out_channels=6)]
+    return cfg
+
+
+def _randomise(model, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() > 1:
+                p.copy_(torch.randn(p.shape, generator=g) * (0.5 / np.sqrt(p[0].numel())))
+            elif n.endswith('.bias'):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+        for n, b in model.named_buffers():
+            if n.endswith('running_var'):
+                b.copy_(torch.rand(b.shape, generator=g) + 0.5)
+            elif n.endswith('running_mean'):
+                b.copy_(torch.randn(b.shape, generator=g) * 0.1)
+
+
+def test_moe_state_dict_layout_and_split():
+    import vitpose_b200 as V
+    from vitpose_b200.checkpoint import split_moe_state_dict
+    cfg = _moe_cfg()
+    model = V.build_posenet(cfg)
+    sd = model.state_dict()
+    D, part = cfg['backbone']['embed_dim'], 32
+    assert sd['backbone.blocks.0.mlp.fc2.weight'].shape == (D - part, 4 * D)
+    assert sd['backbone.blocks.1.mlp.experts.2.weight'].shape == (part, 4 * D)
+    assert sd['associate_keypoint_heads.1.final_layer.weight'].shape[0] == 6
+    _randomise(model, 0)
+    sd = model.state_dict()
+    # tools/model_split.py: per-dataset plain TopDown checkpoints
+    s0 = split_moe_state_dict(sd, 0)
+    assert not any('experts' in k or k.startswith('associate') for k in s0)
+    w = s0['backbone.blocks.1.mlp.fc2.weight']
+    assert w.shape == (D, 4 * D)
+    assert torch.equal(w[:D - part], sd['backbone.blocks.1.mlp.fc2.weight'])
+    assert torch.equal(w[D - part:], sd['backbone.blocks.1.mlp.experts.0.weight'])
+    s2 = split_moe_state_dict(sd, 2, num_keypoints=6)
+    assert torch.equal(s2['backbone.blocks.0.mlp.fc2.bias'][D - part:], sd['backbone.blocks.0.mlp.experts.2.bias'])
+    assert torch.equal(s2['keypoint_head.final_layer.weight'], sd['associate_keypoint_heads.1.final_layer.weight'][:6])
+    plain = configs.tiny_model_cfg(6, depth=2)
+    plain['backbone']['drop_path_rate'] = 0.0
+    V.build_posenet(plain).load_state_dict(s2, strict=True)     # loads into an ordinary ViT + head
+    # the backbone's per-dataset view is the same tensor
+    eff = model.backbone.effective_state_dict(2)
+    assert torch.equal(eff['blocks.0.mlp.fc2.weight'], s2['backbone.blocks.0.mlp.fc2.weight'])
+    with pytest.raises(IndexError):
+        model.backbone.effective_state_dict(3)
+
+
+@pytest.mark.reference
+def test_moe_state_dict_keys_equal_reference():
+    import importlib.util
+    import os
+    import sys
+    from oracle import ref_loader
+    ref_loader.load_reference()
+    path = '/root/reference/mmpose/models/backbones/vit_moe.py'
+    if not os.path.exists(path):
+        pytest.skip('reference tree not mounted')
+    spec = importlib.util.spec_from_file_location('mmpose.models.backbones.vit_moe', path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod
+    spec.loader.exec_module(mod)
+    import vitpose_b200 as V
+    kw = dict(img_size=(256, 192), patch_size=16, embed_dim=128, depth=2, num_heads=2, ratio=1, mlp_ratio=4,
+              qkv_bias=True, drop_path_rate=0.0, num_expert=3, part_features=32)
+    ref = mod.ViTMoE(**kw)
+    ours = V.build_backbone(dict(type='ViTMoE', **kw))
+    rs, os_ = ref.state_dict(), ours.state_dict()
+    assert list(rs) == list(os_)
+    for k in rs:
+        assert rs[k].shape == os_[k].shape, k
+    # and the reference module agrees with the oracle restatement on a mixed batch
+    ours.load_state_dict(rs)
+    img = synthetic.synthetic_crops(3, 1)
+    src = torch.tensor([2, 0, 1])
+    ref.eval()
+    with torch.no_grad():
+        f_ref = ref(img, src)
+        f_or = VT.vit_features({'backbone.' + k: v for k, v in rs.items()}, img, 2, 2, dataset_source=src)
+    assert torch.allclose(f_ref, f_or, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_topdown_moe_mixed_batch_vs_oracle():
+    import vitpose_b200 as V
+    cfg = _moe_cfg()
+    model = V.build_posenet(cfg)
+    _randomise(model, 1)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    n = 5
+    img = synthetic.synthetic_crops(n, 4)
+    metas = synthetic.synthetic_metas(n, 5, 4)
+    for m, d in zip(metas, [1, 0, 2, 1, 0]):
+        m['dataset_idx'] = d
+    ocfg = dict(cfg, backbone=dict(cfg['backbone']))
+    ref = VT.forward_test(sd, img, metas, ocfg, return_heatmap=True)
+    model = model.cuda().eval()
+    r = model(img=img.cuda(), img_metas=metas, return_loss=False, return_heatmap=True)
+    err = np.abs(r['output_heatmap'] - ref['output_heatmap']).max()
+    std = ref['output_heatmap'].std()
+    assert err < 1e-2 and err < 0.1 * std, f'heatmap err {err:.4g}, std {std:.4g}'
+    assert r['bbox_ids'] == ref['bbox_ids'] and r['image_paths'] == ref['image_paths']
+    np.testing.assert_allclose(r['boxes'], ref['boxes'], rtol=1e-6)
+    # a homogeneous batch goes through the single-engine path; the experts must actually matter
+    for m in metas:
+        m['dataset_idx'] = 2
+    r2 = model(img=img.cuda(), img_metas=metas, return_loss=False, return_heatmap=True)
+    ref2 = VT.forward_test(sd, img, metas, ocfg, return_heatmap=True)
+    assert np.abs(r2['output_heatmap'] - ref2['output_heatmap']).max() < 1e-2
+    assert np.abs(ref2['output_heatmap'] - ref['output_heatmap']).max() > 10 * err
+    feats = model.backbone(img.cuda(), torch.tensor([1, 0, 2, 1, 0]))
+    f_ref = VT.vit_features(sd, img, 2, 2, dataset_source=torch.tensor([1, 0, 2, 1, 0]))
+    assert (feats.cpu() - f_ref).abs().max() < 0.05 * max(1.0, float(f_ref.abs().max()))

@@ -1,3 +1,4 @@
 from .vit import ViT
+from .vit_moe import ViTMoE
 
-__all__ = ['ViT']
+__all__ = ['ViT', 'ViTMoE']

@@ -81,3 +81,31 @@ def load_checkpoint(model, filename, map_location='cpu', strict=False, patch_pad
     if strict and (missing or unexpected):
         raise RuntimeError(f'missing keys {missing}, unexpected keys {unexpected}')
     return checkpoint
+
+
+COCO_PLUS_DATASETS = ('coco', 'aic', 'mpii', 'ap10k', 'apt36k', 'wholebody')
+COCO_PLUS_KEYPOINTS = (17, 14, 16, 17, 17, 133)
+
+
+def split_moe_state_dict(state_dict, dataset_idx, num_keypoints=None):
+    """ViTPose+ multi-dataset state dict -> the plain ``TopDown`` / ``ViT`` state dict of one dataset, as the
+    reference's tools/model_split.py writes it: every ``mlp.fc2`` becomes ``cat(fc2, experts[dataset_idx])`` on the
+    output dimension (:36-40, :70-79); for ``dataset_idx`` > 0 the tensors of ``associate_keypoint_heads[idx-1]``
+    replace the main head's (:83-84) and the final layer is cut to the dataset's keypoint count (:86-87)."""
+    sd = dict(state_dict)
+    out = {}
+    for k, v in sd.items():
+        if 'mlp.experts' in k or k.startswith('associate_keypoint_heads.'):
+            continue
+        if 'mlp.fc2' in k:
+            v = torch.cat([v, sd[k.replace('fc2.', f'experts.{dataset_idx}.')]], dim=0)
+        out[k] = v
+    if dataset_idx > 0:
+        pre = f'associate_keypoint_heads.{dataset_idx - 1}.'
+        for k, v in sd.items():
+            if k.startswith(pre):
+                out['keypoint_head.' + k[len(pre):]] = v
+        nk = COCO_PLUS_KEYPOINTS[dataset_idx] if num_keypoints is None else num_keypoints
+        for k in ('keypoint_head.final_layer.weight', 'keypoint_head.final_layer.bias'):
+            out[k] = out[k][:nk]
+    return out

@@ -1,3 +1,4 @@
 from .top_down import TopDown
+from .top_down_moe import TopDownMoE
 
-__all__ = ['TopDown']
+__all__ = ['TopDown', 'TopDownMoE']
