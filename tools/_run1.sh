@@ -1,2 +1,2 @@
 cd /root/repo
-timeout 600 python -m pytest tests/test_moe.py -q -m gpu 2>&1 | tail -25 > gpurun_out/t_moe.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_bwd -c 2 -o gpurun_out/prof_attnbwd -f python tools/prof_gemm.py attn_bwd > gpurun_out/ncu_attnbwd.log 2>&1

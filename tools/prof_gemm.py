@@ -18,6 +18,24 @@ if which == 'attn':
     qkv = torch.randn(256, 192, 3 * D, device=dev).to(BF16)
     for _ in range(3):
         ops.attention(qkv, 12)
+elif which == 'attn_bwd':
+    qkv = torch.randn(64, 192, 3 * D, device=dev).to(BF16)
+    o = ops.attention(qkv, 12)
+    do = torch.randn(64, 192, D, device=dev).to(BF16)
+    for _ in range(3):
+        ops.attention_bwd(qkv, o, do, 12)
+elif which == 'wgrad':
+    dy = torch.randn(64 * 192, 4 * D, device=dev).to(BF16)
+    xx = torch.randn(64 * 192, D, device=dev).to(BF16)
+    dw = torch.zeros(4 * D, D, device=dev)
+    for _ in range(3):
+        ops.gemm_atb_accum(dy, xx, dw)
+elif which == 'decode':
+    hm = torch.rand(512, 17, 64, 48, device=dev)
+    fi = torch.arange(17, device=dev, dtype=torch.int32)
+    c, s_ = torch.rand(256, 2, device=dev), torch.rand(256, 2, device=dev)
+    for _ in range(3):
+        ops.decode(hm[:256], hm[256:], fi, False, _lib.DECODE_UDP_DARK, 11, True, c, s_)
 elif which in ('proj_ln', 'fc2_ln'):
     K = D if which == 'proj_ln' else 4 * D
     A = torch.randn(M, K, device=dev).to(BF16)
