@@ -174,6 +174,21 @@ def test_attention(heads, hd):
     _report(f'attention h{heads} d{hd}', out, ref, 0.03)
 
 
+@pytest.mark.parametrize('heads,hd,n', [(16, 80, 40), (12, 64, 40)])
+def test_attention_many_units_per_cta(heads, hd, n):
+    """Several (crop, head, q-tile) units per persistent CTA: exercises the tile rings and the single O accumulator of
+    the head_dim-80 variant (64-column SWIZZLE_128B box + 16-column SWIZZLE_32B box per operand)."""
+    from vitpose_b200 import ops
+    T, D = 192, heads * hd
+    qkv = _rand_bf16((n, T, 3 * D), 77 + hd, 1.5).to(_dev())
+    out = ops.attention(qkv, heads)
+    q, k, v = qkv.float().reshape(n, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    att = ((q * hd ** -0.5) @ k.transpose(-2, -1)).softmax(-1)
+    ref = (att @ v).transpose(1, 2).reshape(n, T, D)
+    _report(f'attention h{heads} d{hd} n{n}', out, ref.cpu(), 0.03)
+    assert torch.equal(out, ops.attention(qkv, heads))          # deterministic
+
+
 @pytest.mark.parametrize('n,h,w,cin,cout', [(2, 16, 12, 128, 64), (4, 16, 12, 768, 256), (3, 32, 24, 256, 256),
                                             (2, 32, 24, 64, 64)])
 def test_deconv(n, h, w, cin, cout):

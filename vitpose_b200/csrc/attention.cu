@@ -204,16 +204,24 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
 // softmax threads = 128 * NSPLIT: thread (row, part) owns T/NSPLIT key columns of one query row
 __host__ __device__ constexpr int att2_threads(int nsplit) { return 64 + 128 * nsplit; }
 constexpr int ATT2_QK_DEPTH = 2;
-constexpr int ATT2_V_DEPTH = 3;
+// head_dim 80 (ViT-H) = a 64-column SWIZZLE_128B box + a 16-column SWIZZLE_32B box per operand; its larger tiles
+// leave room for two V stages and one O accumulator
+__host__ __device__ constexpr int att2_v_depth(int hd) { return hd > 64 ? 2 : 3; }
+__host__ __device__ constexpr int att2_row_bytes(int hd) { return hd > 64 ? 160 : 128; }
 
 template <int HD, int T_, int NSPLIT>
 __global__ void __launch_bounds__(att2_threads(NSPLIT), 1)
 attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                            const __grid_constant__ CUtensorMap tm_qb, const __grid_constant__ CUtensorMap tm_kvb,
                             const AttnParams p, const int num_units) {
-  static_assert(HD <= 64 && HD % 32 == 0, "persistent attention handles head_dim 32 / 64");
-  static_assert(T_ % 64 == 0 && 2 * T_ + 2 * HD <= 512, "each softmax thread owns T/2 keys; S0,S1,O0,O1 must fit TMEM");
+  static_assert(HD == 32 || HD == 64 || HD == 80, "persistent attention handles head_dim 32 / 64 / 80");
+  constexpr bool WIDE = HD > 64;                    // second, 16-column box per operand (tm_qb / tm_kvb)
+  constexpr int OB = (2 * T_ + 2 * HD <= 512) ? 2 : 1;   // O accumulators that fit TMEM next to S0 | S1
+  static_assert(T_ % 64 == 0 && 2 * T_ + OB * HD <= 512, "each softmax thread owns T/2 keys; S0,S1,O must fit TMEM");
   constexpr int T = T_;
-  constexpr int Q_BYTES = ATT_BM * 128, KV_BYTES = T * 128;
+  constexpr int ATT2_V_DEPTH = att2_v_depth(HD);
+  constexpr int QA_BYTES = ATT_BM * 128, KVA_BYTES = T * 128;          // 64-column boxes
+  constexpr int Q_BYTES = ATT_BM * att2_row_bytes(HD), KV_BYTES = T * att2_row_bytes(HD);
   constexpr int P_BYTES = (T / 64) * ATT_BM * 128;
   constexpr int QK_BYTES = Q_BYTES + KV_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -225,7 +233,8 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
   __shared__ uint64_t s_full[2], o_full[2], o_free[2], p_full;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_max[NSPLIT][ATT_BM], s_sum[NSPLIT][ATT_BM];   // [column part][row], exchanged between the parts
-  static_assert(T_ % (8 * NSPLIT) == 0 && (T_ / NSPLIT) % 16 == 0 && (HD / NSPLIT) % 16 == 0, "unsupported column split");
+  static_assert(T_ % (8 * NSPLIT) == 0 && (T_ / NSPLIT) % 16 == 0 && (WIDE ? NSPLIT == 2 : (HD / NSPLIT) % 16 == 0),
+                "unsupported column split");
 
   const int q_tiles = (T + ATT_BM - 1) / ATT_BM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -246,6 +255,10 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
     fence_mbar_init();
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_kv);
+    if (WIDE) {
+      tma_prefetch_desc(&tm_qb);
+      tma_prefetch_desc(&tm_kvb);
+    }
   }
   if (warp == 1) tmem_alloc(&tmem_slot, 512);
   tc_fence_before();
@@ -278,16 +291,24 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
         mbar_arrive_expect_tx(&qk_full[sq], QK_BYTES);
         tma_load_3d(s_qk + sq * QK_BYTES, &tm_q, &qk_full[sq], head * HD, qt * ATT_BM, crop);
         tma_load_3d(s_qk + sq * QK_BYTES + Q_BYTES, &tm_kv, &qk_full[sq], p.heads * HD + head * HD, 0, crop);
+        if constexpr (WIDE) {     // columns [64, 80) of Q and K
+          tma_load_3d(s_qk + sq * QK_BYTES + QA_BYTES, &tm_qb, &qk_full[sq], head * HD + 64, qt * ATT_BM, crop);
+          tma_load_3d(s_qk + sq * QK_BYTES + Q_BYTES + KVA_BYTES, &tm_kvb, &qk_full[sq], p.heads * HD + head * HD + 64,
+                      0, crop);
+        }
         timed_wait(&v_free[sv], ((i / ATT2_V_DEPTH) & 1) ^ 1, 1);
         mbar_arrive_expect_tx(&v_full[sv], KV_BYTES);
         tma_load_3d(s_v + sv * KV_BYTES, &tm_kv, &v_full[sv], 2 * p.heads * HD + head * HD, 0, crop);
+        if constexpr (WIDE)
+          tma_load_3d(s_v + sv * KV_BYTES + KVA_BYTES, &tm_kvb, &v_full[sv], 2 * p.heads * HD + head * HD + 64, 0, crop);
       }
       if (timing) { p.dbg_buf[0] = t_wait[0]; p.dbg_buf[1] = t_wait[1]; }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, T);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BM, HD, 0, 1);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BM, WIDE ? 64 : HD, 0, 1);
+      constexpr uint32_t idesc_o16 = umma_idesc_bf16(ATT_BM, 16, 0, 1);      // WIDE: output columns [64, 80)
       auto issue_s = [&](int i) {
         const int sq = i % ATT2_QK_DEPTH, b = i & 1;
         timed_wait(&qk_full[sq], (i / ATT2_QK_DEPTH) & 1, 0);
@@ -295,9 +316,11 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
         const uint32_t qa = smem_u32(s_qk + sq * QK_BYTES), ka = qa + Q_BYTES;
         if (!(p.dbg & 4)) {
 #pragma unroll
-          for (int ks = 0; ks < HD / 16; ++ks)
+          for (int ks = 0; ks < (WIDE ? 4 : HD / 16); ++ks)
             umma_bf16_ss(tmem_base + b * T, umma_desc_k_sw128(qa + ks * 32), umma_desc_k_sw128(ka + ks * 32), idesc_s,
                          ks != 0);
+          if constexpr (WIDE)       // fifth K step: the 16-column SWIZZLE_32B boxes
+            umma_bf16_ss(tmem_base + b * T, umma_desc_k_sw32(qa + QA_BYTES), umma_desc_k_sw32(ka + KVA_BYTES), idesc_s, 1u);
         }
         umma_commit(&s_full[b]);
         umma_commit(&qk_free[sq]);      // Q/K tiles are dead once S has been computed
@@ -306,16 +329,18 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
       if (n_local > 0) issue_s(0);
       if (n_local > 1) issue_s(1);
       for (int i = 0; i < n_local; ++i) {
-        const int sv = i % ATT2_V_DEPTH, b = i & 1;
-        timed_wait(&p_full, i & 1, 1);                     // P(i) in smem, S_b read
-        timed_wait(&o_free[b], ((i >> 1) & 1) ^ 1, 2);     // O_b drained by the epilogue of unit i-2
+        const int sv = i % ATT2_V_DEPTH, b = i % OB;
+        timed_wait(&p_full, i & 1, 1);                     // P(i) in smem, S read
+        timed_wait(&o_free[b], ((i / OB) & 1) ^ 1, 2);     // O_b drained by the epilogue of unit i - OB
         timed_wait(&v_full[sv], (i / ATT2_V_DEPTH) & 1, 3);
         tc_fence_after();
         const uint32_t d = tmem_base + 2 * T + b * HD;
         const uint32_t pa = smem_u32(s_p), va = smem_u32(s_v + sv * KV_BYTES);
         for (int ks = 0; ks < ((p.dbg & 2) ? 0 : T / 16); ++ks) {
-          umma_bf16_ss(d, umma_desc_k_sw128(pa + (ks / 4) * (ATT_BM * 128) + (ks % 4) * 32),
-                       umma_desc_mn_sw128(va + ks * 2048, KV_BYTES), idesc_o, ks != 0);
+          const uint64_t pd = umma_desc_k_sw128(pa + (ks / 4) * (ATT_BM * 128) + (ks % 4) * 32);
+          umma_bf16_ss(d, pd, umma_desc_mn_sw128(va + ks * 2048, KVA_BYTES), idesc_o, ks != 0);
+          if constexpr (WIDE)       // 16 keys x 32 B per K step in the SWIZZLE_32B box
+            umma_bf16_ss(d + 64, pd, umma_desc_mn_sw32(va + KVA_BYTES + ks * 512), idesc_o16, ks != 0);
         }
         umma_commit(&o_full[b]);
         umma_commit(&v_free[sv]);
@@ -385,7 +410,7 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
       }
       // ... and only then wait for the single P tile: it is free once P.V of the previous unit has completed, and that
       // MMA ran while the exponentials above were being computed
-      if (i > 0) timed_wait(&o_full[(i - 1) & 1], ((i - 1) >> 1) & 1, 1);
+      if (i > 0) timed_wait(&o_full[(i - 1) % OB], ((i - 1) / OB) & 1, 1);
       if (warp_live) {
 #pragma unroll
         for (int g = 0; g < KH / 8; ++g) {            // 8 keys = one 16-byte unit of the swizzled P tile
@@ -409,18 +434,21 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
       const int qt = unit % q_tiles;
       const int head = (unit / q_tiles) % p.heads;
       const int crop = (unit / q_tiles) / p.heads;
-      const int b = i & 1;
+      const int b = i % OB;
       const int token = qt * ATT_BM + r;
       const bool warp_live = (qt * ATT_BM + quad * 32 < T) && !(p.dbg & 1);
-      timed_wait(&o_full[b], (i >> 1) & 1, 2);
+      timed_wait(&o_full[b], (i / OB) & 1, 2);
       tc_fence_after();
       if (warp_live) {
-        constexpr int OC = HD / NSPLIT;               // output columns per thread
-        __nv_bfloat16* orow = p.out + (static_cast<size_t>(crop) * T + token) * p.ldo + head * HD + half * OC;
-#pragma unroll
-        for (int c = 0; c < OC; c += 16) {
+        // output columns per thread: an even split, or 48 + 32 for head_dim 80
+        constexpr int OC0 = WIDE ? 48 : HD / NSPLIT;
+        const int oc_begin = half * OC0;
+        const int oc = WIDE ? (half == 0 ? 48 : HD - 48) : OC0;
+        __nv_bfloat16* orow = p.out + (static_cast<size_t>(crop) * T + token) * p.ldo + head * HD + oc_begin;
+#pragma unroll 1
+        for (int c = 0; c < oc; c += 16) {
           uint32_t o[16];
-          tmem_ld_32x32b_x16(lane_base + 2 * T_ + b * HD + half * OC + c, o);
+          tmem_ld_32x32b_x16(lane_base + 2 * T_ + b * HD + oc_begin + c, o);
           tmem_ld_wait();
           if (token < T) {
             uint32_t w8[8];
@@ -463,10 +491,11 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
 }
 
 template <int HD, int T_, int NSPLIT>
-static int launch_attention_persistent(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p,
-                                       int max_ctas, cudaStream_t stream) {
-  constexpr int smem = (T_ / 64) * ATT_BM * 128 + ATT2_QK_DEPTH * (ATT_BM * 128 + T_ * 128) +
-                       ATT2_V_DEPTH * T_ * 128 + 1024;
+static int launch_attention_persistent(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& tqb,
+                                       const CUtensorMap& tkvb, const AttnParams& p, int max_ctas,
+                                       cudaStream_t stream) {
+  constexpr int smem = (T_ / 64) * ATT_BM * 128 + ATT2_QK_DEPTH * (ATT_BM + T_) * att2_row_bytes(HD) +
+                       att2_v_depth(HD) * T_ * att2_row_bytes(HD) + 1024;
   static_assert(smem <= 227 * 1024 - 6 * 1024, "persistent attention tiles do not fit shared memory");
   auto kern = attention_persistent_kernel<HD, T_, NSPLIT>;
   static bool configured = false;
@@ -478,7 +507,7 @@ static int launch_attention_persistent(const CUtensorMap& tq, const CUtensorMap&
   const int units = p.n * p.heads * q_tiles;
   int grid = max_ctas > 0 ? max_ctas : sm_count();
   if (grid > units) grid = units;
-  kern<<<grid, att2_threads(NSPLIT), smem, stream>>>(tq, tkv, p, units);
+  kern<<<grid, att2_threads(NSPLIT), smem, stream>>>(tq, tkv, tqb, tkvb, p, units);
   VPB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -540,11 +569,19 @@ int attention_fwd(const void* qkv, void* out, int n, int T, int heads, int hd, f
   const int smem = region0 + nb * T * 128 + 1024;
   if (max_ctas >= 0) {   // max_ctas < 0 selects the per-unit kernel (kept for head_dim > 64 and for A/B tests)
     int rc = 1;
-    if (hd == 32 && T == 192) rc = launch_attention_persistent<32, 192, 2>(tq, tkv, p, max_ctas, stream);
+    if (hd == 32 && T == 192) rc = launch_attention_persistent<32, 192, 2>(tq, tkv, tq, tkv, p, max_ctas, stream);
     if (hd == 64 && T == 192) {
       // measured at 256 images x 12 heads: 2 column parts per row (8 softmax warps) 0.109 ms, 4 parts (16 warps) 0.134 ms
-      rc = (p.dbg & 16) ? launch_attention_persistent<64, 192, 4>(tq, tkv, p, max_ctas, stream)
-                        : launch_attention_persistent<64, 192, 2>(tq, tkv, p, max_ctas, stream);
+      rc = (p.dbg & 16) ? launch_attention_persistent<64, 192, 4>(tq, tkv, tq, tkv, p, max_ctas, stream)
+                        : launch_attention_persistent<64, 192, 2>(tq, tkv, tq, tkv, p, max_ctas, stream);
+    }
+    if (hd == 80 && T == 192 && !(p.dbg & 128)) {
+      // head_dim 80 (ViT-H): a second, 16-column SWIZZLE_32B box per operand
+      CUtensorMap tqb, tkvb;
+      uint32_t box_qb[3] = {16, ATT_BM, 1}, box_kvb[3] = {16, (uint32_t)T, 1};
+      if (make_tma_desc(&tqb, TMA_BF16, qkv, 3, dims, strides, box_qb, TMA_SWIZZLE_32B)) return -1;
+      if (make_tma_desc(&tkvb, TMA_BF16, qkv, 3, dims, strides, box_kvb, TMA_SWIZZLE_32B)) return -1;
+      rc = launch_attention_persistent<80, 192, 2>(tq, tkv, tqb, tkvb, p, max_ctas, stream);
     }
     if (rc <= 0) return rc;
   }
