@@ -194,10 +194,13 @@ int vpb_gelu_bwd_bf16(const void* pre, const void* dh, void* dpre, long long n, 
  * dx_accum fp32 [M,D] += dL/dx (the residual stream's gradient), dgamma / dbeta fp32 [D] += */
 int vpb_layernorm_bwd(const float* x, const float* gamma, const void* dy, float* dx_accum, float* dgamma,
                       float* dbeta, int M, int D, float eps, void* stream);
-/* Attention.forward backward (vit.py:99-115): qkv [n,T,3*heads*hd] and out [n,T,heads*hd] saved by the forward
- * pass, dout = dL/dout -> dqkv [n,T,3*heads*hd]. T = 192, head_dim = 64 (ViTPose-B, the training configuration). */
-int vpb_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, int n, int T, int heads,
-                      int head_dim, float scale, void* stream);
+/* Attention.forward (vit.py:99-115) that also returns lse fp32 [n, heads, T] = log2 sum_j exp2(s_ij * scale * log2 e),
+ * and its backward: qkv [n,T,3*heads*hd], out [n,T,heads*hd] and lse saved by the forward pass, dout = dL/dout ->
+ * dqkv [n,T,3*heads*hd]. Backward: T = 192, head_dim = 64 (ViTPose-B, the training configuration). */
+int vpb_attention_lse(const void* qkv, void* out, float* lse, int n, int T, int heads, int head_dim, float scale,
+                      void* stream);
+int vpb_attention_bwd(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, int n, int T,
+                      int heads, int head_dim, float scale, void* stream);
 /* ConvTranspose2d(k4,s2,p1,bias=False) without BatchNorm / ReLU (training forward; ones / zeros: fp32 [cout]) */
 int vpb_deconv4x4s2_raw(const void* in, const void* wphase, void* out, int n, int h, int w, int cin, int cout,
                         const float* ones, const float* zeros, void* stream);

@@ -83,14 +83,17 @@ def test_attention_bwd(n, heads):
     D = heads * hd
     qkv = _rand((n, T, 3 * D), 11, 1.0)
     dout = _rand((n, T, D), 12, 1.0)
-    out = ops.attention(qkv, heads)
+    out, lse = ops.attention_with_lse(qkv, heads)
+    assert torch.equal(out, ops.attention(qkv, heads))
     x = qkv.float().requires_grad_(True)
     q, k, v = x.reshape(n, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
     a = ((q * hd ** -0.5) @ k.transpose(-2, -1)).softmax(-1)
     o = (a @ v).transpose(1, 2).reshape(n, T, D)
     o.backward(dout.float())
     _close('attention fwd', out, o.detach(), 2e-2)
-    dqkv = ops.attention_bwd(qkv, out, dout, heads)
+    s_ref = ((q * hd ** -0.5) @ k.transpose(-2, -1)).detach()
+    _close('attention lse', lse, torch.logsumexp(s_ref, -1) * 1.4426950408889634, 1e-3)
+    dqkv = ops.attention_bwd(qkv, out, lse, dout, heads)
     g = x.grad.reshape(n, T, 3, D)
     d = dqkv.reshape(n, T, 3, D)
     for i, nm in enumerate('qkv'):

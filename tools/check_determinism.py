@@ -23,8 +23,8 @@ h = rnd(M, 4 * D); w2 = rnd(D, 4 * D, scale=1 / math.sqrt(4 * D))
 rep('gemm resid+ln (long K)', lambda: ops.gemm_layernorm(h, w2, _lib.EPI_RESID_F32, bt, res, gm, bt))
 qkv = rnd(64, 192, 3 * D)
 rep('attention fwd', lambda: ops.attention(qkv, 12))
-o = ops.attention(qkv, 12); do = rnd(64, 192, D)
-rep('attention bwd', lambda: ops.attention_bwd(qkv, o, do, 12))
+o, lse_ = ops.attention_with_lse(qkv, 12); do = rnd(64, 192, D)
+rep('attention bwd', lambda: ops.attention_bwd(qkv, o, lse_, do, 12))
 dy = rnd(M, D)
 def lnb():
     dx = torch.zeros(M, D, device=dev); dg = torch.zeros(D, device=dev); db = torch.zeros(D, device=dev)

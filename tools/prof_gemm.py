@@ -20,10 +20,10 @@ if which == 'attn':
         ops.attention(qkv, 12)
 elif which == 'attn_bwd':
     qkv = torch.randn(64, 192, 3 * D, device=dev).to(BF16)
-    o = ops.attention(qkv, 12)
+    o, lse_ = ops.attention_with_lse(qkv, 12)
     do = torch.randn(64, 192, D, device=dev).to(BF16)
     for _ in range(3):
-        ops.attention_bwd(qkv, o, do, 12)
+        ops.attention_bwd(qkv, o, lse_, do, 12)
 elif which == 'wgrad':
     dy = torch.randn(64 * 192, 4 * D, device=dev).to(BF16)
     xx = torch.randn(64 * 192, D, device=dev).to(BF16)

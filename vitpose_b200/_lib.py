@@ -64,8 +64,9 @@ _SIGS = {
     'vpb_gelu_bwd_bf16': (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p]),
     'vpb_layernorm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                   c_void_p]),
-    'vpb_attention_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
-                                  c_void_p]),
+    'vpb_attention_lse': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    'vpb_attention_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                  c_float, c_void_p]),
     'vpb_deconv4x4s2_raw': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                     c_void_p, c_void_p]),
     'vpb_bn_train_stats': (c_int, [c_void_p, ctypes.c_longlong, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,

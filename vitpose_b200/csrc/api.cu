@@ -348,9 +348,13 @@ int vpb_layernorm_bwd(const float* x, const float* gamma, const void* dy, float*
                       float* dbeta, int M, int D, float eps, void* stream) {
   return layernorm_bwd(x, gamma, dy, dx_accum, dgamma, dbeta, M, D, eps, as_stream(stream));
 }
-int vpb_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, int n, int T, int heads,
-                      int head_dim, float scale, void* stream) {
-  return attention_bwd(qkv, out, dout, dqkv, n, T, heads, head_dim, scale, as_stream(stream));
+int vpb_attention_lse(const void* qkv, void* out, float* lse, int n, int T, int heads, int head_dim, float scale,
+                      void* stream) {
+  return attention_fwd(qkv, out, n, T, heads, head_dim, scale, 0, as_stream(stream), lse);
+}
+int vpb_attention_bwd(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, int n, int T,
+                      int heads, int head_dim, float scale, void* stream) {
+  return attention_bwd(qkv, out, lse, dout, dqkv, n, T, heads, head_dim, scale, as_stream(stream));
 }
 int vpb_deconv4x4s2_raw(const void* in, const void* wphase, void* out, int n, int h, int w, int cin, int cout,
                         const float* ones, const float* zeros, void* stream) {

@@ -30,6 +30,7 @@ struct AttnParams {
   int ldo;              // heads * hd
   float scale_log2e;    // scale * log2(e)
   __nv_bfloat16* out;
+  float* lse;           // optional [n, heads, T]: log2(sum_j exp2(s_ij * scale * log2e)) per query row (for the backward pass)
   long long* dbg_buf;   // optional [16] cycle counters of CTA 0 (VPB_ATT_DEBUG & 32), see tools/att_debug.py
   int dbg;              // profiling aid (VPB_ATT_DEBUG): 1 skip softmax math, 2 skip P.V MMAs, 4 skip S MMAs, 8 skip K/V loads
 };
@@ -425,6 +426,12 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
       if (warp_live) {
 #pragma unroll
         for (int o = 1; o < NSPLIT; ++o) sum += s_sum[(half + o) % NSPLIT][r];
+        if (p.lse != nullptr && half == 0 && qt * ATT_BM + r < T) {
+          const int head = (unit / q_tiles) % p.heads;
+          const int crop = (unit / q_tiles) / p.heads;
+          p.lse[(static_cast<size_t>(crop) * p.heads + head) * T + qt * ATT_BM + r] =
+              fmaf(mx_row, p.scale_log2e, log2f(sum));
+        }
       }
       return warp_live ? 1.0f / sum : 0.f;
     };
@@ -527,7 +534,7 @@ static int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const
 }
 
 int attention_fwd(const void* qkv, void* out, int n, int T, int heads, int hd, float scale, int max_ctas,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, float* lse) {
   (void)max_ctas;
   VPB_REQUIRE(n > 0 && heads > 0, "attention: empty problem");
   VPB_REQUIRE(T % 16 == 0 && T >= 16 && T <= 256, "attention: T=%d must be a multiple of 16 in [16,256]", T);
@@ -545,6 +552,7 @@ int attention_fwd(const void* qkv, void* out, int n, int T, int heads, int hd, f
   p.n = n; p.T = T; p.heads = heads; p.hd = hd; p.ldo = heads * hd;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
   {
     const char* e = getenv("VPB_ATT_DEBUG");
     p.dbg = e ? atoi(e) : 0;
@@ -585,6 +593,7 @@ int attention_fwd(const void* qkv, void* out, int n, int T, int heads, int hd, f
     }
     if (rc <= 0) return rc;
   }
+  VPB_REQUIRE(lse == nullptr, "attention: the log-sum-exp output needs the persistent kernel (T=192, head_dim 32/64/80)");
   switch (hd) {
     case 32: return launch_attention<32>(tq, tkv, p, smem, stream);
     case 64: return launch_attention<64>(tq, tkv, p, smem, stream);

@@ -5,8 +5,9 @@
 //   dQ = scale * dS K,  dK = scale * dS^T Q
 // One CTA per (crop, head). Q, K, V, dO of the head are TMA-loaded once as 128B-swizzled [192 x 64] tiles; the
 // query rows are processed in two 128-row tiles (the second is half empty). Per tile:
-//   tcgen05.mma S  = Q_t K^T       -> TMEM [0,192)   ; 128 threads (one query row each) recompute the softmax and
-//                                                       write P (bf16) to smem
+//   tcgen05.mma S  = Q_t K^T       -> TMEM [0,192)   ; 256 threads ((query row, half of the keys) each) form
+//                                                       P = exp2(S * scale * log2e - lse) with the forward pass's
+//                                                       log-sum-exp in ONE pass and write it (bf16) to smem
 //   tcgen05.mma dP = dO_t V^T      -> same TMEM columns; the threads form dS = scale * P o (dP - delta) (bf16, smem)
 //   tcgen05.mma dQ_t = dS K        -> TMEM [192,256)  (K consumed as an MN-major operand)
 //   tcgen05.mma dK += dS^T Q_t, dV += P^T dO_t -> TMEM [256,512): A operands are the P / dS tiles read MN-major
@@ -21,7 +22,7 @@ namespace vpb {
 
 constexpr int AB_T = 192;
 constexpr int AB_HD = 64;
-constexpr int AB_THREADS = 160;                     // warp 0: TMA + MMA issue; warps 1..4: one query / key row per thread
+constexpr int AB_THREADS = 288;                     // warp 0: TMA + MMA issue; warps 1..8: (row, column half) per thread
 constexpr int AB_TILE = AB_T * 128;                 // [192 rows][128 B]
 constexpr int AB_CHUNK = 128 * 128;                 // [128 rows][64 keys] bf16
 constexpr int AB_SMEM = 4 * AB_TILE + 3 * AB_CHUNK + 4 * AB_CHUNK + 1024;   // Q K V dO | dS | P + one chunk of slack
@@ -31,6 +32,7 @@ struct AttnBwdParams {
   float scale, scale_log2e;
   const __nv_bfloat16* dO;    // [n, T, heads*64]
   const __nv_bfloat16* O;     // [n, T, heads*64] forward output
+  const float* lse;           // [n, heads, T] log2-sum-exp of the scaled scores, written by the forward kernel
   __nv_bfloat16* dqkv;        // [n, T, 3*heads*64]
 };
 
@@ -56,9 +58,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   if (threadIdx.x == 0) {
     mbar_init(&bar_load, 1);
     mbar_init(&bar_s, 1);
-    mbar_init(&bar_sdone, 128);
+    mbar_init(&bar_sdone, 256);
     mbar_init(&bar_dp, 1);
-    mbar_init(&bar_ds, 128);
+    mbar_init(&bar_ds, 256);
     mbar_init(&bar_mma, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tm_qkv);
@@ -129,13 +131,15 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     }
   } else {
     const int quad = warp & 3;
+    const int half = (warp - 1) >> 2;               // which half of the key columns (and of the output columns)
     const int r = quad * 32 + lane;                 // row inside a tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    constexpr int KH = AB_T / 2;                    // 96 keys per thread
     for (int t = 0; t < 2; ++t) {
       const int token = t * 128 + r;
       const bool valid = token < AB_T;
-      // delta = <dO_row, O_row>
-      float delta = 0.f;
+      // delta = <dO_row, O_row> (both halves compute it: 256 bytes per thread, no exchange needed)
+      float delta = 0.f, lse = 0.f;
       if (valid) {
         const size_t off = (static_cast<size_t>(crop) * AB_T + token) * ld_o + head * AB_HD;
         const uint4* a = reinterpret_cast<const uint4*>(p.dO + off);
@@ -151,37 +155,20 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
             delta = fmaf(fx.x, fy.x, fmaf(fx.y, fy.y, delta));
           }
         }
+        lse = __ldg(p.lse + (static_cast<size_t>(crop) * p.heads + head) * AB_T + token);
       }
       mbar_wait(&bar_s, t);
       tc_fence_after();
-      // softmax of this query row, recomputed: max, sum, then normalised probabilities (bf16) into shared memory
-      float mx = -INFINITY;
-      for (int c = 0; c < AB_T; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_off + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-      }
-      const float mxs = mx * p.scale_log2e;
-      float sum = 0.f;
-      for (int c = 0; c < AB_T; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_off + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sum += exp2f(fmaf(__uint_as_float(v[j]), p.scale_log2e, -mxs));
-      }
-      const float inv = valid ? 1.0f / sum : 0.f;
-      for (int c = 0; c < AB_T; c += 32) {
+      // P = exp2(s * scale * log2e - lse), one pass over this thread's 96 keys
+      for (int c = half * KH; c < (half + 1) * KH; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_s + lane_off + c, v);
         tmem_ld_wait();
         uint32_t packed[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          const float e0 = valid ? exp2f(fmaf(__uint_as_float(v[j]), p.scale_log2e, -mxs)) * inv : 0.f;
-          const float e1 = valid ? exp2f(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, -mxs)) * inv : 0.f;
+          const float e0 = valid ? exp2f(fmaf(__uint_as_float(v[j]), p.scale_log2e, -lse)) : 0.f;
+          const float e1 = valid ? exp2f(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, -lse)) : 0.f;
           packed[j / 2] = pack_bf16x2(e0, e1);
         }
         const uint32_t row = smem_u32(s_p) + (c / 64) * AB_CHUNK + r * 128;
@@ -195,7 +182,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       mbar_wait(&bar_dp, t);
       tc_fence_after();
       // dS = scale * P o (dP - delta)
-      for (int c = 0; c < AB_T; c += 32) {
+      for (int c = half * KH; c < (half + 1) * KH; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_s + lane_off + c, v);
         tmem_ld_wait();
@@ -225,48 +212,43 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       mbar_arrive(&bar_ds);
       mbar_wait(&bar_mma, t);
       tc_fence_after();
-      // dQ rows of this tile
+      // dQ rows of this tile: 32 of the 64 columns per thread
       {
-        __nv_bfloat16* orow = p.dqkv + (static_cast<size_t>(crop) * AB_T + token) * ld_qkv + head * AB_HD;
+        __nv_bfloat16* orow = p.dqkv + (static_cast<size_t>(crop) * AB_T + token) * ld_qkv + head * AB_HD + half * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_dq + lane_off + half * 32, v);
+        tmem_ld_wait();
+        if (valid) {
 #pragma unroll
-        for (int c = 0; c < AB_HD; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_dq + lane_off + c, v);
-          tmem_ld_wait();
-          if (valid) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              reinterpret_cast<uint4*>(orow + c)[u] =
-                  make_uint4(pack_bf16x2(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
-                             pack_bf16x2(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
-                             pack_bf16x2(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
-                             pack_bf16x2(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
-          }
+          for (int u = 0; u < 4; ++u)
+            reinterpret_cast<uint4*>(orow)[u] =
+                make_uint4(pack_bf16x2(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
+                           pack_bf16x2(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
+                           pack_bf16x2(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
+                           pack_bf16x2(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
         }
       }
       tc_fence_before();
     }
-    // dK / dV rows (keys): key tile m, lane r <-> key m*128 + r
+    // dK / dV rows (keys): key tile m, lane r <-> key m*128 + r; half 0 stores dK, half 1 stores dV
     for (int m = 0; m < 2; ++m) {
       const int key = m * 128 + r;
-      for (int which = 0; which < 2; ++which) {
-        const uint32_t base = (which == 0 ? tmem_dk : tmem_dv) + m * AB_HD + lane_off;
-        __nv_bfloat16* orow =
-            p.dqkv + (static_cast<size_t>(crop) * AB_T + key) * ld_qkv + (1 + which) * ld_o + head * AB_HD;
+      const uint32_t base = (half == 0 ? tmem_dk : tmem_dv) + m * AB_HD + lane_off;
+      __nv_bfloat16* orow =
+          p.dqkv + (static_cast<size_t>(crop) * AB_T + key) * ld_qkv + (1 + half) * ld_o + head * AB_HD;
 #pragma unroll
-        for (int c = 0; c < AB_HD; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(base + c, v);
-          tmem_ld_wait();
-          if (key < AB_T) {
+      for (int c = 0; c < AB_HD; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(base + c, v);
+        tmem_ld_wait();
+        if (key < AB_T) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              reinterpret_cast<uint4*>(orow + c)[u] =
-                  make_uint4(pack_bf16x2(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
-                             pack_bf16x2(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
-                             pack_bf16x2(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
-                             pack_bf16x2(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
-          }
+          for (int u = 0; u < 4; ++u)
+            reinterpret_cast<uint4*>(orow + c)[u] =
+                make_uint4(pack_bf16x2(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
+                           pack_bf16x2(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
+                           pack_bf16x2(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
+                           pack_bf16x2(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
         }
       }
     }
@@ -276,9 +258,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   if (warp == 0) tmem_dealloc(tmem_s, 512);
 }
 
-int attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, int n, int T, int heads, int hd,
-                  float scale, cudaStream_t stream) {
-  VPB_REQUIRE(n > 0 && heads > 0, "attention_bwd: empty problem");
+int attention_bwd(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, int n, int T,
+                  int heads, int hd, float scale, cudaStream_t stream) {
+  VPB_REQUIRE(n > 0 && heads > 0 && lse != nullptr, "attention_bwd: empty problem / missing log-sum-exp");
   VPB_REQUIRE(T == AB_T && hd == AB_HD, "attention_bwd: built for T=%d, head_dim=%d (got T=%d, head_dim=%d)", AB_T,
               AB_HD, T, hd);
   const int ld_o = heads * hd, ld = 3 * ld_o;
@@ -294,6 +276,7 @@ int attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv
   p.n = n; p.heads = heads; p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
   p.dO = reinterpret_cast<const __nv_bfloat16*>(dout);
   p.O = reinterpret_cast<const __nv_bfloat16*>(out);
+  p.lse = lse;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   static bool configured = false;
   if (!configured) {

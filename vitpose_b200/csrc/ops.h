@@ -53,7 +53,7 @@ int relu_upsample_bilinear_nhwc(const void* in, void* out, int n, int h, int w, 
 // ---- attention (attention.cu) ----
 // qkv bf16 [n, T, 3*heads*hd] (column order: which, head, d) -> out bf16 [n, T, heads*hd]
 int attention_fwd(const void* qkv, void* out, int n, int T, int heads, int hd, float scale, int max_ctas,
-                  cudaStream_t stream);
+                  cudaStream_t stream, float* lse = nullptr);
 
 // ---- deconv / conv implicit GEMMs (conv.cu) ----
 // ConvTranspose2d(k4,s2,p1,no bias) + folded BN + ReLU, NHWC bf16.
@@ -116,8 +116,8 @@ int nchw_f32_to_rows_bf16(const float* in, void* out, int n, int K, int P, int K
 int deconv_gather_x(const void* x, void* out, int n, int h, int w, int cin, cudaStream_t stream);
 int deconv_gather_dy(const void* dy, void* out, int n, int h, int w, int cout, cudaStream_t stream);
 int deconv_phase_dy(const void* dy, void* out, int n, int h, int w, int cout, cudaStream_t stream);
-int attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, int n, int T, int heads, int hd,
-                  float scale, cudaStream_t stream);
+int attention_bwd(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, int n, int T,
+                  int heads, int hd, float scale, cudaStream_t stream);
 
 int adamw_multi(const vpb_tensor_entry* entries, const int* chunk_start, int n, int total_chunks, float beta1,
                 float beta2, float eps, float* sq_norm, float max_norm, cudaStream_t stream);

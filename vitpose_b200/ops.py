@@ -226,14 +226,27 @@ def layernorm_bwd(x, gamma, dy, dx_accum, dgamma, dbeta, eps=1e-6):
                                   float(eps), stream_ptr()), 'vpb_layernorm_bwd')
 
 
-def attention_bwd(qkv, out, dout, heads, scale=None):
-    """qkv bf16 [n,T,3*heads*hd], out / dout bf16 [n,T,heads*hd] -> dqkv bf16 [n,T,3*heads*hd]."""
-    _need(qkv, BF16, 'qkv'); _need(out, BF16, 'out'); _need(dout, BF16, 'dout')
+def attention_with_lse(qkv, heads, scale=None):
+    """Forward attention that also returns the per-row log-sum-exp (base 2) the backward pass consumes."""
+    _need(qkv, BF16, 'qkv')
+    n, T, three = qkv.shape
+    hd = three // 3 // heads
+    scale = hd ** -0.5 if scale is None else scale
+    out = torch.empty(n, T, heads * hd, device=qkv.device, dtype=BF16)
+    lse = torch.empty(n, heads, T, device=qkv.device, dtype=torch.float32)
+    check(lib().vpb_attention_lse(ptr(qkv), ptr(out), ptr(lse), n, T, heads, hd, float(scale), stream_ptr()),
+          'vpb_attention_lse')
+    return out, lse
+
+
+def attention_bwd(qkv, out, lse, dout, heads, scale=None):
+    """qkv bf16 [n,T,3*heads*hd], out / dout bf16 [n,T,heads*hd], lse fp32 [n,heads,T] -> dqkv bf16 [n,T,3*heads*hd]."""
+    _need(qkv, BF16, 'qkv'); _need(out, BF16, 'out'); _need(dout, BF16, 'dout'); _need(lse, torch.float32, 'lse')
     n, T, three = qkv.shape
     hd = three // 3 // heads
     scale = hd ** -0.5 if scale is None else scale
     dqkv = torch.empty_like(qkv)
-    check(lib().vpb_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(dqkv), n, T, heads, hd, float(scale),
+    check(lib().vpb_attention_bwd(ptr(qkv), ptr(out), ptr(lse), ptr(dout), ptr(dqkv), n, T, heads, hd, float(scale),
                                   stream_ptr()), 'vpb_attention_bwd')
     return dqkv
 

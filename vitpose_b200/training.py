@@ -99,7 +99,8 @@ class _NetworkFn(torch.autograd.Function):
             w = blocks[l]
             a = dict(x_in=x, xn1=xn)
             qkv = ops.gemm(xn, w['qkv'].w, EPI_BIAS, bias=w['qkv'].b)
-            attn = ops.attention(qkv.view(n, T, 3 * D), heads).view(M, D)
+            attn, lse = ops.attention_with_lse(qkv.view(n, T, 3 * D), heads)
+            attn = attn.view(M, D)
             s1, s2 = scales[l]
             x_mid, xn2 = ops.gemm_layernorm(attn, w['proj'].w, EPI_RESID, w['proj'].b, x, blk.norm2.weight.detach(),
                                             blk.norm2.bias.detach(), 1e-6, row_scale=s1, rows_per_scale=T)
@@ -108,7 +109,7 @@ class _NetworkFn(torch.autograd.Function):
             nxt = bb.blocks[l + 1].norm1 if l + 1 < depth else bb.last_norm
             x, xn = ops.gemm_layernorm(h, w['fc2'].w, EPI_RESID, w['fc2'].b, x_mid, nxt.weight.detach(),
                                        nxt.bias.detach(), 1e-6, row_scale=s2, rows_per_scale=T)
-            a.update(qkv=qkv, attn=attn, x_mid=x_mid, xn2=xn2, pre=pre, h=h, s1=s1, s2=s2)
+            a.update(qkv=qkv, attn=attn, lse=lse, x_mid=x_mid, xn2=xn2, pre=pre, h=h, s1=s1, s2=s2)
             acts.append(a)
         s.update(patches=patches, acts=acts, x_final=x, blocks=blocks, pe=pe)
         # ---- head (simple_head.py:197-202), BatchNorm2d in training mode
@@ -244,7 +245,8 @@ class _NetworkFn(torch.autograd.Function):
             # x_mid = x_in + proj(attention(qkv(norm1(x_in))))        (vit.py:138)
             dyb = ops.cast_bf16(dx, a['s1'], T)
             dattn = linear_bwd(pfx + 'attn.proj', w['proj'], dyb, a['attn'])
-            dqkv = ops.attention_bwd(a['qkv'].view(n, T, 3 * D), a['attn'].view(n, T, D), dattn.view(n, T, D), heads)
+            dqkv = ops.attention_bwd(a['qkv'].view(n, T, 3 * D), a['attn'].view(n, T, D), a['lse'],
+                                     dattn.view(n, T, D), heads)
             dxn1 = linear_bwd(pfx + 'attn.qkv', w['qkv'], dqkv.view(M, 3 * D), a['xn1'])
             dg_, db_ = zeros(D), zeros(D)
             ops.layernorm_bwd(a['x_in'], blk.norm1.weight.detach(), dxn1, dx, dg_, db_, 1e-6)
