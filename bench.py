@@ -353,8 +353,13 @@ def main():
         tgemm_ms = sum(float(np.sum(by_tag[k])) for k in flops) / args.steps
         tgemm_tf = sum(flops[k] * len(by_tag[k]) for k in flops) / args.steps / tgemm_ms / 1e9
         shares = {k: round(float(np.sum(v)) / args.steps / ms, 4) for k, v in by_tag.items()}
+        # DRAM bytes of one fc1 launch from the committed ncu --set full capture of this command (B workload, 256 crops)
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'r01_fc1_traffic.json')
+        if args.workload == 'B-classic-17' and n == 256 and os.path.exists(tpath):
+            traffic = json.load(open(tpath))['traffic_bytes']
         roofline = dict(bound='tensor', kernel='gemm_bf16_tn_kernel<256,GELU> (mlp.fc1)', achieved=achieved,
-                        peak=pk['tf_sustained'], unit='TFLOP/s', frac=achieved / pk['tf_sustained'], traffic=None,
+                        peak=pk['tf_sustained'], unit='TFLOP/s', frac=achieved / pk['tf_sustained'], traffic=traffic,
                         peak_source=f"{pk['source']} sustained bf16 (kernel timed inside a long step)",
                         transformer_gemms_tflops=tgemm_tf, transformer_gemms_frac=tgemm_tf / pk['tf_sustained'],
                         step_share_by_kernel=shares)

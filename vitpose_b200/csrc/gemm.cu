@@ -33,35 +33,16 @@ static int launch_gemm_inst(const GemmMaps& maps, const GemmParams& p, int max_c
   cfg.blockDim = dim3(gemm_threads(EPI));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  // (A cooperative launch would let the driver guarantee that the sibling CTAs of the fused-LayerNorm kernels are
+  // co-scheduled, but Nsight Compute cannot profile cooperative cluster launches; the grid is one CTA per SM, sized
+  // from the device, which gives the same guarantee on a GPU this process has to itself.)
+  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (gemm_epi_ln(EPI)) {
-    // the CTAs of a row block wait for each other: a cooperative launch makes the driver schedule the whole grid
-    // at once (or refuse the launch) instead of leaving resident CTAs spinning on siblings that cannot start
-    static int coop = -1;      // 1 supported, 0 refused once -> plain launches (the grid still fits: one CTA per SM)
-    if (coop != 0) {
-      attr[1].id = cudaLaunchAttributeCooperative;
-      attr[1].val.cooperative = 1;
-      cfg.numAttrs = 2;
-      const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps.a, maps.b, maps.out, maps.aux, maps.ln, p);
-      if (e == cudaSuccess) {
-        coop = 1;
-        return 0;
-      }
-      (void)cudaGetLastError();
-      if (coop == 1) {
-        set_last_error("gemm+layernorm: cooperative launch failed: %s", cudaGetErrorString(e));
-        return -1;
-      }
-      coop = 0;
-      cfg.numAttrs = 1;
-    }
-  }
   VPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps.a, maps.b, maps.out, maps.aux, maps.ln, p));
   return 0;
 }
