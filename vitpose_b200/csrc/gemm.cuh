@@ -244,7 +244,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   __shared__ uint64_t tfull_bar[2];
   __shared__ uint64_t tempty_bar[2];
   __shared__ uint64_t res_full[2][GEMM_RES_SLOTS];
-  __shared__ uint64_t res_empty[2][GEMM_RES_SLOTS];
+  __shared__ uint64_t res_ready[2][GEMM_RES_SLOTS];   // slot updated in place by the epilogue -> ring warp stores it
   __shared__ uint32_t tmem_slot;
   constexpr int BIAS_PER_GROUP = (BN / CHUNK + GROUPS - 1) / GROUPS * CHUNK;   // columns a group's chunks cover
   __shared__ __align__(16) float s_bias[LN_SPLIT ? 2 : GROUPS][STAGED ? BIAS_PER_GROUP : 1];
@@ -270,9 +270,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     for (int s = 0; s < GEMM_RES_SLOTS; ++s) {
       mbar_init(&res_full[0][s], 1);
-      mbar_init(&res_empty[0][s], 1);
+      mbar_init(&res_ready[0][s], 1);
       mbar_init(&res_full[1][s], 1);
-      mbar_init(&res_empty[1][s], 1);
+      mbar_init(&res_ready[1][s], 1);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tma_a);
@@ -368,39 +368,62 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
     }
   } else if (gemm_epi_adds_tile(EPI) && (warp == 6 || (LN_SPLIT && warp == 11))) {
-    // residual producer of tile group tg: chunk c of tile (m_blk, n_blk) = fp32 [128 rows x 32 cols] -> ring slot
-    // (in-place staging)
+    // Ring warp of tile group tg: owns BOTH ends of the in-place staging ring. It TMA-loads the fp32 residual (or
+    // positional) chunk c of tile (m_blk, n_blk) = [128 rows x 32 cols] into a slot, the epilogue threads update the
+    // slot in place and flag it ready, and this warp TMA-stores it and recycles the slot once the store has read it —
+    // so no epilogue thread ever waits for a store. With the fused LayerNorm the tile's bf16 boxes (64 columns) follow
+    // its fp32 chunks through the same slots (nothing to load for those).
     if (lane == 0) {
       const int tg = warp == 11 ? 1 : 0;
       uint8_t* ring = s_out + tg * RING_BYTES;
-      uint32_t seq = 0;
-      for (int tile = tile0 + tg * tile_step; tile < num_tiles; tile += tile_step * TG) {
+      constexpr int NX = BN / 32, NCH = NX + (LN ? BN / 64 : 0);     // chunks per tile
+      const int first_tile = tile0 + tg * tile_step, stride = tile_step * TG;
+      auto load = [&](int tile, int c, uint32_t slot) {
+        if (c >= NX) {                      // bf16 LayerNorm box: the slot only has to be free
+          mbar_arrive(&res_full[tg][slot]);
+          return;
+        }
         const int m_blk = ((tile / p.ksplit) / n_tiles) * CG + cta_rank;
         const int n_blk = (tile / p.ksplit) % n_tiles;
-        for (int c = 0; c < BN / 32; ++c, ++seq) {
-          const uint32_t slot = seq % RES_SLOTS;
-          mbar_wait(&res_empty[tg][slot], ((seq / RES_SLOTS) & 1) ^ 1);
-          mbar_arrive_expect_tx(&res_full[tg][slot], GEMM_STAGING_BYTES);
-          if constexpr (gemm_epi_pos(EPI)) {
-            // positional table rows (token = row % period): two 64-row boxes, each inside one period (period % 64 == 0)
-            const int t0 = (m_blk * GEMM_BM) % p.period, t1 = (m_blk * GEMM_BM + 64) % p.period;
-            tma_load_2d(ring + slot * GEMM_STAGING_BYTES, &tma_aux, &res_full[tg][slot], n_blk * BN + c * 32, t0);
-            tma_load_2d(ring + slot * GEMM_STAGING_BYTES + 64 * 128, &tma_aux, &res_full[tg][slot],
-                        n_blk * BN + c * 32, t1);
-          } else {
-            tma_load_2d(ring + slot * GEMM_STAGING_BYTES, &tma_aux, &res_full[tg][slot], n_blk * BN + c * 32,
-                        m_blk * GEMM_BM);
-          }
+        mbar_arrive_expect_tx(&res_full[tg][slot], GEMM_STAGING_BYTES);
+        if constexpr (gemm_epi_pos(EPI)) {
+          // positional table rows (token = row % period): two 64-row boxes, each inside one period (period % 64 == 0)
+          const int t0 = (m_blk * GEMM_BM) % p.period, t1 = (m_blk * GEMM_BM + 64) % p.period;
+          tma_load_2d(ring + slot * GEMM_STAGING_BYTES, &tma_aux, &res_full[tg][slot], n_blk * BN + c * 32, t0);
+          tma_load_2d(ring + slot * GEMM_STAGING_BYTES + 64 * 128, &tma_aux, &res_full[tg][slot], n_blk * BN + c * 32,
+                      t1);
+        } else {
+          tma_load_2d(ring + slot * GEMM_STAGING_BYTES, &tma_aux, &res_full[tg][slot], n_blk * BN + c * 32,
+                      m_blk * GEMM_BM);
         }
-        if constexpr (LN) {
-          // the normalised bf16 boxes of the tile go through the same ring: grant empty slots, nothing to load
-          for (int c = 0; c < BN / 64; ++c, ++seq) {
-            const uint32_t slot = seq % RES_SLOTS;
-            mbar_wait(&res_empty[tg][slot], ((seq / RES_SLOTS) & 1) ^ 1);
-            mbar_arrive(&res_full[tg][slot]);
-          }
+      };
+      int ld_tile = first_tile, ld_c = 0, st_tile = first_tile, st_c = 0;
+      uint32_t nld = 0, nst = 0;
+      auto load_next = [&](uint32_t slot) {
+        if (ld_tile >= num_tiles) return;
+        load(ld_tile, ld_c, slot);
+        ++nld;
+        if (++ld_c == NCH) { ld_c = 0; ld_tile += stride; }
+      };
+      for (int i = 0; i < RES_SLOTS; ++i) load_next(static_cast<uint32_t>(i));
+      while (st_tile < num_tiles) {
+        const uint32_t slot = nst % RES_SLOTS;
+        mbar_wait(&res_ready[tg][slot], (nst / RES_SLOTS) & 1);      // the epilogue has finished chunk nst in place
+        const int m_blk = ((st_tile / p.ksplit) / n_tiles) * CG + cta_rank;
+        const int n_blk = (st_tile / p.ksplit) % n_tiles;
+        if (st_c < NX)
+          tma_store_2d(&tma_out, ring + slot * GEMM_STAGING_BYTES, n_blk * BN + st_c * 32, m_blk * GEMM_BM);
+        else
+          tma_store_2d(&tma_ln, ring + slot * GEMM_STAGING_BYTES, n_blk * BN + (st_c - NX) * 64, m_blk * GEMM_BM);
+        tma_store_commit();
+        if (nst > 0) {                      // the previous store has read its slot: reuse it for the next load
+          tma_store_wait_read<1>();
+          load_next((nst - 1) % RES_SLOTS);
         }
+        ++nst;
+        if (++st_c == NCH) { st_c = 0; st_tile += stride; }
       }
+      tma_store_wait_all<0>();              // all output bytes committed before the CTA exits
     }
   } else {
     const int quad = warp & 3;             // TMEM lane quadrant this warp may read
@@ -412,7 +435,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                               : static_cast<int>(threadIdx.x) - 64 - 128 * grp;   // 0..127 inside the warpgroup
     uint8_t* ring = s_out + (LN_SPLIT ? grp : 0) * RING_BYTES;
     uint64_t* rfull = res_full[LN_SPLIT ? grp : 0];
-    uint64_t* rempty = res_empty[LN_SPLIT ? grp : 0];
+    uint64_t* rready = res_ready[LN_SPLIT ? grp : 0];
     float* s_gamma = s_affine + (LN_SPLIT ? grp : 0) * 2 * BN;
     float* s_beta = s_gamma + BN;
     const int r = quad * 32 + lane;        // row inside the tile == TMEM lane
@@ -499,14 +522,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             // the slot is complete: publish it to the async proxy and let thread 0 store it while the others go on
             fence_proxy_async_smem();
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-            if (etid == 0) {
-              tma_store_2d(&tma_out, ring + buf * GEMM_STAGING_BYTES, n_blk * BN + c * 32, m_blk * GEMM_BM);
-              tma_store_commit();
-              if (chunk_seq > 0) {
-                tma_store_wait_read<1>();
-                mbar_arrive(&rempty[(chunk_seq - 1) % RES_SLOTS]);
-              }
-            }
+            if (etid == 0) mbar_arrive(&rready[buf]);      // the ring warp stores the slot and recycles it
             const float2 ss = __fadd2_rn(s0, s1);
             const float mc = (ss.x + ss.y) * (1.0f / 32.0f);
             const float2 nmc = make_float2(-mc, -mc);
@@ -580,12 +596,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               sts_u4(srow + ((u ^ (r & 7)) * 16), v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
             fence_proxy_async_smem();
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-            if (etid == 0) {
-              tma_store_2d(&tma_ln, ring + buf * GEMM_STAGING_BYTES, n_blk * BN + c * 64, m_blk * GEMM_BM);
-              tma_store_commit();
-              tma_store_wait_read<1>();
-              mbar_arrive(&rempty[(chunk_seq - 1) % RES_SLOTS]);
-            }
+            if (etid == 0) mbar_arrive(&rready[buf]);
           }
         } else {
 #pragma unroll 1
@@ -642,14 +653,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           fence_proxy_async_smem();         // generic-proxy smem writes -> visible to the TMA store
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           if (etid == 0) {
-            tma_store_2d(&tma_out, ring + buf * GEMM_STAGING_BYTES, n_blk * BN + c * CHUNK, m_blk * GEMM_BM);
-            tma_store_commit();
             if constexpr (gemm_epi_adds_tile(EPI)) {
-              // hand the previous chunk's slot back to the residual producer once its store has read it
-              if (chunk_seq > 0) {
-                tma_store_wait_read<1>();
-                mbar_arrive(&rempty[(chunk_seq - 1) % RES_SLOTS]);
-              }
+              mbar_arrive(&rready[buf]);                   // the ring warp stores the slot and recycles it
+            } else {
+              tma_store_2d(&tma_out, ring + buf * GEMM_STAGING_BYTES, n_blk * BN + c * CHUNK, m_blk * GEMM_BM);
+              tma_store_commit();
             }
           }
         }
@@ -720,7 +728,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         if (acc == 0) acc_phase ^= 1;
       }
     }
-    if (STAGED && etid == 0) tma_store_wait_all<0>();   // all output bytes committed before the CTA exits
+    if (STAGED && !gemm_epi_adds_tile(EPI) && etid == 0) tma_store_wait_all<0>();   // output committed before exit
   }
   tc_fence_before();
   __syncthreads();
