@@ -42,17 +42,22 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms. The process is started before the warm-up (it needs
+    about a second to print its first line); ``mark()`` at both ends of the timed region selects the samples taken
+    DURING it (plus the one straddling each end, so that a region shorter than the sampling period still has data)."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.marks = index, [], None, []
+
+    def mark(self):
+        self.marks.append(len(self.rows))
 
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -65,12 +70,15 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
-        time.sleep(0.25)
+        time.sleep(0.12)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        rows = self.rows
+        if len(self.marks) >= 2:
+            rows = self.rows[max(0, self.marks[0] - 1):self.marks[-1] + 1]
+        sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == 'Active'})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i] == 'Active'})
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
                     reasons=reasons, samples=len(sm))
 
@@ -128,6 +136,9 @@ def run_train(args, cfg, K):
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     sys.stdout.flush()
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
@@ -172,17 +183,16 @@ def run_train(args, cfg, K):
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     os.close(saved_stdout)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     calls0 = _lib.ABI_CALLS[0]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     ev0.record()
     for i in range(args.steps):
         loss = step(devb[i & 1])
     ev1.record()
     barrier()
+    sampler.mark()
     ms = ev0.elapsed_time(ev1) / args.steps
     calls = _lib.ABI_CALLS[0] - calls0
     clocks = sampler.stop() if rank == 0 else None
@@ -259,6 +269,9 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    sampler = ClockSampler(local_rank)      # started now: nvidia-smi needs about a second before its first sample
+    if rank == 0:
+        sampler.start()
     # NCCL prints its version banner on stdout at the first collective; keep stdout for the one JSON line
     sys.stdout.flush()
     saved_stdout = os.dup(1)
@@ -304,19 +317,18 @@ def main():
     os.dup2(saved_stdout, 1)
     os.close(saved_stdout)
     # ---- timed region (device-resident inputs) -------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     L = _lib.lib()
     launches0 = L.vpb_launch_count()
     L.vpb_profile_enable(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     ev0.record()
     for i in range(args.steps):
         device_step(i)
     ev1.record()
     barrier()
+    sampler.mark()
     ms = ev0.elapsed_time(ev1) / args.steps
     records = _lib.profile_records()
     L.vpb_profile_enable(0)
