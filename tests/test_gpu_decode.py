@@ -132,6 +132,37 @@ def test_decode_full_size_properties():
         assert torch.isfinite(r['preds']).all()
 
 
+def test_decode_config4_full_size_vs_oracle_subset():
+    """BASELINE configs[3] decode size: 2048 crops x 133 keypoints (272 384 maps), shift_heatmap + quarter offset as
+    shipped. Whole batch: batch-split invariance (bitwise); a random subset of crops: against the oracle."""
+    from vitpose_b200 import ops, _lib
+    from vitpose_b200.configs import WHOLEBODY133_FLIP_PAIRS
+    from vitpose_b200.core.post_processing import flip_index_from_pairs
+    dev = torch.device('cuda:0')
+    n, K = 2048, 133
+    g = torch.Generator(device='cuda').manual_seed(4)
+    hm = torch.rand(n, K, 64, 48, device=dev, generator=g)
+    hm_f = torch.rand(n, K, 64, 48, device=dev, generator=g)
+    # a sharp peak per map so that the decode is well-posed
+    idx = torch.randint(0, 64 * 48, (n, K), device=dev, generator=g)
+    hm.view(n, K, -1).scatter_(2, idx[..., None], 3.0)
+    perm = flip_index_from_pairs(K, WHOLEBODY133_FLIP_PAIRS)
+    fi = torch.from_numpy(perm).to(dev)
+    c = torch.rand(n, 2, device=dev, generator=g) * 100 + 50
+    s = torch.rand(n, 2, device=dev, generator=g) + 0.5
+    full = ops.decode(hm, hm_f, fi, True, _lib.DECODE_DEFAULT, 11, False, c, s)
+    for lo, hi in ((0, 1024), (1024, 2048), (777, 779)):
+        part = ops.decode(hm[lo:hi].contiguous(), hm_f[lo:hi].contiguous(), fi, True, _lib.DECODE_DEFAULT, 11, False,
+                          c[lo:hi].contiguous(), s[lo:hi].contiguous())
+        assert torch.equal(part['preds'], full['preds'][lo:hi]) and torch.equal(part['maxvals'], full['maxvals'][lo:hi])
+    pick = np.random.RandomState(0).choice(n, 24, replace=False)
+    merged = O.merge_flip(hm[pick].cpu().numpy(), hm_f[pick].cpu().numpy(), WHOLEBODY133_FLIP_PAIRS, True)
+    p_ref, m_ref = O.keypoints_from_heatmaps(merged, c[pick].cpu().numpy(), s[pick].cpu().numpy(),
+                                             post_process='default', use_udp=False)
+    np.testing.assert_array_equal(full['maxvals'][pick].cpu().numpy(), m_ref)
+    np.testing.assert_allclose(full['preds'][pick].cpu().numpy(), p_ref, atol=1e-3)
+
+
 def test_decode_empty_and_errors():
     from vitpose_b200 import ops, _lib
     dev = torch.device('cuda:0')

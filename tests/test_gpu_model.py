@@ -199,3 +199,34 @@ def test_forward_test_contract():
     # odd batch sizes and batch 1 (no bbox_id needed)
     r1 = model.forward_test(img[:1], no_id[:1])
     assert r1['bbox_ids'] is None and r1['preds'].shape == (1, 5, 3)
+
+
+def test_config2_full_size_properties():
+    """BASELINE configs[1] at its full size (ViTPose-B, 256 crops, flip test, UDP-DARK) through properties that need
+    no oracle run: (1) batch-split invariance — the first 128 crops decoded alone give bit-identical results;
+    (2) mirror symmetry of the flip test — for horizontally flipped crops the averaged heatmap is exactly the
+    flipped-back heatmap of the originals ((a + b) * 0.5 is commutative), so arg-max columns mirror and channels swap;
+    (3) determinism — the same call twice is bit-identical."""
+    from vitpose_b200.core.post_processing import flip_index_from_pairs
+    cfg = configs.baseline_model_cfg('B-classic-17')
+    sd = synthetic.scaled_init_state_dict(cfg, 5)
+    n, K = 256, 17
+    img = synthetic.synthetic_crops(n, 5).cuda()
+    metas = synthetic.synthetic_metas(n, K, 5)
+    model = _build(cfg, sd)
+    r = model(img=img, img_metas=metas, return_loss=False, return_heatmap=True)
+    r_again = model(img=img, img_metas=metas, return_loss=False, return_heatmap=True)
+    assert np.array_equal(r['preds'], r_again['preds']) and np.array_equal(r['output_heatmap'], r_again['output_heatmap'])
+    half = model(img=img[:128].contiguous(), img_metas=metas[:128], return_loss=False, return_heatmap=True)
+    assert np.array_equal(half['output_heatmap'], r['output_heatmap'][:128])
+    assert np.array_equal(half['preds'], r['preds'][:128])
+    rf = model(img=img.flip(3).contiguous(), img_metas=metas, return_loss=False, return_heatmap=True)
+    perm = flip_index_from_pairs(K, metas[0]['flip_pairs'])
+    mirrored = r['output_heatmap'][:, perm][..., ::-1]
+    assert np.array_equal(rf['output_heatmap'], mirrored)
+    am = r['output_heatmap'].reshape(n, K, -1).argmax(2)
+    am_f = rf['output_heatmap'].reshape(n, K, -1).argmax(2)
+    y, x = am // 48, am % 48
+    # first-index tie-break can differ under mirroring only on exact ties; random-weight maps have none
+    assert np.array_equal(am_f // 48, y[:, perm]) and np.array_equal(am_f % 48, 47 - x[:, perm])
+    assert np.array_equal(rf['preds'][..., 2], r['preds'][:, perm, 2])
