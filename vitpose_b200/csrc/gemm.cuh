@@ -1,11 +1,16 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a: C[M,N] = A[M,K] * B[N,K]^T with fused epilogues.
-//   warp 0     : TMA producer (A and B tiles, 128B-swizzled, K-major) through a STAGES-deep mbarrier ring
-//   warp 1     : tcgen05.mma issuer (one elected lane), accumulators double-buffered in TMEM
-//   warps 2..5 : epilogue. tcgen05.ld -> bias / GELU / residual in registers -> 128B-swizzled staging tile in
-//                shared memory -> TMA store (coalesced, clipped at the tensor edge by hardware). The fp32
-//                residual tile is prefetched with TMA loads into a second staging ring. TMEM is released as soon
-//                as the last chunk of a tile is in registers, so the next tile's MMAs overlap the epilogue.
-// One CTA per SM, tiles 128 x BN, walked N-fastest so CTAs running together share the A panel in L2.
+//   warp 0      : TMA producer (A and B tiles, 128B-swizzled) through a STAGES-deep mbarrier ring
+//   warp 1      : tcgen05.mma issuer (one elected lane), accumulators double-buffered in TMEM
+//   warps 2..   : epilogue warpgroup(s). tcgen05.ld -> bias / GELU / residual (/ LayerNorm) in registers -> 128B-swizzled
+//                 staging tile in shared memory -> TMA store (coalesced, clipped at the tensor edge by hardware).
+//                 bf16 epilogues: two warpgroups split the column chunks of a tile; the short-K LayerNorm variant: two
+//                 warpgroups on alternating tiles; everything else: one warpgroup.
+//   warp 6 (11) : ring warp of the fp32 residual epilogues: TMA-loads the residual / positional chunk into a slot,
+//                 TMA-stores the slot once the epilogue has updated it in place, recycles it.
+// TMEM is released as soon as the last chunk of a tile has left it, so the next tile's MMAs overlap the epilogue.
+// One CTA (or CTA pair, cta_group::2) per SM, tiles 128 (256) x BN, walked N-fastest so CTAs running together share
+// the A panel in L2. Variants: EPI_ACCUM_F32 splits K over CTAs (weight gradients), OPM = 1 consumes transposed
+// operands as MN-major tiles, EPI_*_LN* fuse the LayerNorm that follows a residual update.
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"
@@ -69,8 +74,8 @@ constexpr int GEMM_BK = 64;   // 64 bf16 = one 128-byte swizzle row
 // bf16 epilogues (bias / GELU) are instruction-heavy: two epilogue warpgroups (8 warps, 2 per scheduler) split
 // the column chunks of a tile; the fp32 residual epilogue is memory-heavy and keeps one warpgroup.
 __host__ __device__ constexpr int gemm_epi_groups(int epi) { return (epi == 0 || epi == 1) ? 2 : 1; }
-// EPI_RESID_F32 adds warp 6: a TMA producer that streams the fp32 residual tile through a ring of in-place
-// staging slots, running ahead of the epilogue (and of the MMAs) by up to GEMM_RES_SLOTS chunks.
+// The fp32 residual epilogues add warp 6 (and 11): the ring warp that streams the residual tile through in-place
+// staging slots (loads ahead of the epilogue, stores behind it).
 // The short-K LayerNorm variants run TWO such epilogue warpgroups (warps 2..5 and 7..10), each with its own
 // residual ring and producer warp (6 and 11), on alternating tiles: with one warp per scheduler the epilogue of a
 // tile is a latency-bound instruction stream several times longer than the tile's MMA loop.
