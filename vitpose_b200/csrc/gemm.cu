@@ -243,6 +243,8 @@ int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue
   // tiles (needs the smaller operand stages of CTA pairs or of <=128-wide tiles to fit in shared memory).
   // measured (B200, M = 49152, K = N = 768): 0.117 ms, against 0.138 ms with one epilogue group (pairs or single
   // CTAs) and 0.153 ms with 128-wide tiles; 0.076 + 0.038 ms for the unfused GEMM + LayerNorm kernels
+  // (the split variant's 3 operand stages cost a long-K GEMM more than the second epilogue group gains: fc2 + LN
+  // 0.211 ms unsplit, 0.240 ms split at M = 49152)
   const bool short_k = K < 1536;
   int cg = gemm_pick_cg(M, bn, EPI_RESID_LNS_F32, K);
   const bool split = short_k && (bn <= 128 || cg == 2);
