@@ -14,6 +14,7 @@
 
 #include "host_util.h"
 #include "ops.h"
+#include "ptx.cuh"
 
 namespace vpb {
 
@@ -75,48 +76,85 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const DecodeParams 
   const int lane = tid & 31, warp = tid >> 5;
 
   // ---- 1. load (both passes), merge, optional store of the merged map -------------------------
+  // Each map is one contiguous HW*4-byte row in HBM: thread 0 fetches it (and its flipped partner) with a bulk
+  // asynchronous copy straight into shared memory — two instructions per CTA instead of ~12 LDG.128 per thread.
   const float* src = p.hm + static_cast<size_t>(map) * HW;
-  const bool vec = (HW % 4 == 0);
-  if (vec) {
-    for (int i = tid; i < HW / 4; i += DEC_THREADS)
-      reinterpret_cast<float4*>(s_map)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-  } else {
-    for (int i = tid; i < HW; i += DEC_THREADS) s_map[i] = __ldg(src + i);
-  }
+  const float* srcf = nullptr;
   if (p.hmf != nullptr) {
     const int ks = p.flip_index ? p.flip_index[k] : k;
-    const float* srcf = p.hmf + static_cast<size_t>(n * p.K + ks) * HW;
-    if (vec) {
-      for (int i = tid; i < HW / 4; i += DEC_THREADS)
-        reinterpret_cast<float4*>(s_aux)[i] = __ldg(reinterpret_cast<const float4*>(srcf) + i);
-    } else {
-      for (int i = tid; i < HW; i += DEC_THREADS) s_aux[i] = __ldg(srcf + i);
+    srcf = p.hmf + static_cast<size_t>(n * p.K + ks) * HW;
+  }
+  const bool bulk = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(srcf)) & 15) == 0;
+  if (bulk) {
+    __shared__ uint64_t bar;
+    if (tid == 0) {
+      mbar_init(&bar, 1);
+      fence_mbar_init();
     }
     __syncthreads();
-    for (int i = tid; i < HW; i += DEC_THREADS) {
-      const int y = i / W, x = i - y * W;
-      const int xs = p.shift ? (x > 0 ? x - 1 : 0) : x;
-      // (a + b) * 0.5 exactly as NumPy float32: one rounded add, then an exact halving
-      s_map[i] = __fmul_rn(__fadd_rn(s_map[i], s_aux[y * W + (W - 1 - xs)]), 0.5f);
+    if (tid == 0) {
+      const uint32_t bytes = static_cast<uint32_t>(HW) * 4u;
+      mbar_arrive_expect_tx(&bar, srcf ? 2 * bytes : bytes);
+      bulk_load_1d(s_map, src, bytes, &bar);
+      if (srcf) bulk_load_1d(s_aux, srcf, bytes, &bar);
     }
+    mbar_wait(&bar, 0);
+  } else {
+    for (int i = tid; i < HW; i += DEC_THREADS) s_map[i] = __ldg(src + i);
+    if (srcf)
+      for (int i = tid; i < HW; i += DEC_THREADS) s_aux[i] = __ldg(srcf + i);
+    __syncthreads();
   }
-  __syncthreads();
-  if (p.merged_out != nullptr) {
-    float* dst = p.merged_out + static_cast<size_t>(map) * HW;
-    if (vec) {
-      for (int i = tid; i < HW / 4; i += DEC_THREADS)
-        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_map)[i];
-    } else {
-      for (int i = tid; i < HW; i += DEC_THREADS) dst[i] = s_map[i];
-    }
-  }
-
-  // ---- 2. argmax, first index wins on ties (np.argmax) -----------------------------------------
+  // ---- 2. flip merge fused with the arg-max scan (first index wins on ties, np.argmax) -----------------------
+  // One pass over the map: 16-byte groups, the flipped partner read mirrored (components reversed), the merged
+  // values written back for the refinement stage, the running maximum kept in registers.
   float best = -INFINITY;
   int best_i = 0x7fffffff;
-  for (int i = tid; i < HW; i += DEC_THREADS) {
-    const float v = s_map[i];
+  auto consider = [&](float v, int i) {
     if (v > best || best_i == 0x7fffffff) { best = v; best_i = i; }   // increasing i: strict > keeps the first
+  };
+  if (HW % 4 == 0 && W % 4 == 0) {
+    const int W4 = W / 4;
+    float4* m4 = reinterpret_cast<float4*>(s_map);
+    const float4* a4 = reinterpret_cast<const float4*>(s_aux);
+    for (int g = tid; g < HW / 4; g += DEC_THREADS) {
+      float4 a = m4[g];
+      if (srcf != nullptr) {
+        const int y = g / W4, x4 = g - y * W4;
+        float4 b;
+        if (!p.shift) {
+          const float4 t = a4[y * W4 + (W4 - 1 - x4)];
+          b = make_float4(t.w, t.z, t.y, t.x);
+        } else {                       // out[x] = flipped[max(x - 1, 0)]: not 16-byte aligned, scalar reads
+          const float* row = s_aux + y * W;
+          const int x0 = 4 * x4;
+          b = make_float4(row[W - 1 - (x0 > 0 ? x0 - 1 : 0)], row[W - 1 - x0], row[W - 2 - x0], row[W - 3 - x0]);
+        }
+        // (a + b) * 0.5 exactly as NumPy float32: one rounded add, then an exact halving
+        a.x = __fmul_rn(__fadd_rn(a.x, b.x), 0.5f);
+        a.y = __fmul_rn(__fadd_rn(a.y, b.y), 0.5f);
+        a.z = __fmul_rn(__fadd_rn(a.z, b.z), 0.5f);
+        a.w = __fmul_rn(__fadd_rn(a.w, b.w), 0.5f);
+        m4[g] = a;
+      }
+      consider(a.x, 4 * g);
+      consider(a.y, 4 * g + 1);
+      consider(a.z, 4 * g + 2);
+      consider(a.w, 4 * g + 3);
+    }
+  } else {
+    if (srcf != nullptr) {
+      for (int y = warp; y < H; y += DEC_THREADS / 32) {
+        const float* arow = s_aux + y * W;
+        float* mrow = s_map + y * W;
+        for (int x = lane; x < W; x += 32) {
+          const int xs = p.shift ? (x > 0 ? x - 1 : 0) : x;
+          mrow[x] = __fmul_rn(__fadd_rn(mrow[x], arow[W - 1 - xs]), 0.5f);
+        }
+      }
+      __syncthreads();
+    }
+    for (int i = tid; i < HW; i += DEC_THREADS) consider(s_map[i], i);
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
@@ -126,6 +164,16 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const DecodeParams 
   }
   if (lane == 0) { s_red_v[warp] = best; s_red_i[warp] = best_i; }
   __syncthreads();
+  if (p.merged_out != nullptr) {       // every thread's merged values are in shared memory after the barrier above
+    float* dst = p.merged_out + static_cast<size_t>(map) * HW;
+    const bool vec = (HW % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    if (vec) {
+      for (int i = tid; i < HW / 4; i += DEC_THREADS)
+        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_map)[i];
+    } else {
+      for (int i = tid; i < HW; i += DEC_THREADS) dst[i] = s_map[i];
+    }
+  }
   best = s_red_v[0];
   best_i = s_red_i[0];
 #pragma unroll
