@@ -60,13 +60,14 @@ __device__ float merged_from_global(const DecodeParams& p, int map, int y, int x
 }
 
 __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const DecodeParams p) {
-  __shared__ __align__(16) float s_map[DEC_MAX_PIX];
-  __shared__ __align__(16) float s_aux[DEC_MAX_PIX];
+  // dynamic shared memory sized to the actual map (two 64x48 maps = 24 KB -> 8 CTAs per SM instead of 6):
+  // s_map = this map (merged in place), s_aux = the flipped partner / the row-blurred map (UNBIASED)
+  extern __shared__ __align__(16) float s_dyn[];
+  float* s_map = s_dyn;
+  float* s_aux = s_dyn + ((p.H * p.W + 3) & ~3);
   __shared__ float s_red_v[DEC_THREADS / 32];
   __shared__ int s_red_i[DEC_THREADS / 32];
   __shared__ float s_part[7 * 32];
-  __shared__ float s_pts[16];
-  __shared__ int s_pt_map[7], s_pt_y[7], s_pt_x[7];
 
   const int map = blockIdx.x;
   const int n = map / p.K;
@@ -192,68 +193,72 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const DecodeParams 
   const int ks = p.ksize, r = (ks - 1) / 2;
   if (p.mode == DECODE_UDP_DARK) {
     // Only 7 values of the blurred log-map are ever read: evaluate the separable blur there.
-    if (tid < 7) {
-      const int dxs[7] = {0, 1, -1, 0, 0, 1, -1};
-      const int dys[7] = {0, 0, 0, 1, -1, 1, -1};
-      int pm = map, py, px;
+    // stencil point `pt` of this map: (map, y, x) it reads (every thread derives its own; no broadcast needed)
+    auto stencil_point = [&](int pt, int& pm, int& py, int& px) {
+      const int dxs = (0x2424 >> (2 * pt)) & 3;    // dx = {0,1,-1,0,0,1,-1} as 2-bit codes (2 = -1)
+      const int dys = (0x2640 >> (2 * pt)) & 3;    // dy = {0,0,0,1,-1,1,-1}
+      pm = map;
       if (alive) {
-        px = clampi(ix + dxs[tid], 0, W - 1);
-        py = clampi(iy + dys[tid], 0, H - 1);
+        px = clampi(ix + (dxs == 2 ? -1 : dxs), 0, W - 1);
+        py = clampi(iy + (dys == 2 ? -1 : dys), 0, H - 1);
       } else {
         // coords = -1: the reference's flat gather underflows into the previous map's last padded row
         const int prev = (map + p.N * p.K - 1) % (p.N * p.K);
-        if (tid == 2 || tid == 6) { pm = prev; py = H - 1; px = W - 1; }
-        else if (tid == 4)        { pm = prev; py = H - 1; px = 0; }
-        else                      { py = 0; px = 0; }
+        if (pt == 2 || pt == 6) { pm = prev; py = H - 1; px = W - 1; }
+        else if (pt == 4)       { pm = prev; py = H - 1; px = 0; }
+        else                    { py = 0; px = 0; }
       }
-      s_pt_map[tid] = pm; s_pt_y[tid] = py; s_pt_x[tid] = px;
-    }
-    __syncthreads();
+    };
     for (int t = tid; t < 7 * ks; t += DEC_THREADS) {
       const int pt = t / ks, tr = t - pt * ks;
-      const int pm = s_pt_map[pt];
-      const int yy = reflect101(s_pt_y[pt] + tr - r, H);
+      int pm, py, px;
+      stencil_point(pt, pm, py, px);
+      const int yy = reflect101(py + tr - r, H);
       float acc = 0.0f;
       for (int tx = 0; tx < ks; ++tx) {
-        const int xx = reflect101(s_pt_x[pt] + tx - r, W);
+        const int xx = reflect101(px + tx - r, W);
         const float v = (pm == map) ? s_map[yy * W + xx] : merged_from_global(p, pm, yy, xx);
         acc = __fadd_rn(acc, __fmul_rn(p.taps[tx], v));
       }
       s_part[pt * 32 + tr] = acc;
     }
     __syncthreads();
-    if (tid < 7) {
-      float acc = 0.0f;
-      for (int tr = 0; tr < ks; ++tr) acc = __fadd_rn(acc, __fmul_rn(p.taps[tr], s_part[tid * 32 + tr]));
-      acc = fminf(fmaxf(acc, 0.001f), 50.0f);
-      s_pts[tid] = logf(acc);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      const float v0 = s_pts[0], xp = s_pts[1], xm = s_pts[2], yp = s_pts[3], ym = s_pts[4];
-      const float xpyp = s_pts[5], xmym = s_pts[6];
-      const float dx = __fmul_rn(0.5f, __fsub_rn(xp, xm));
-      const float dy = __fmul_rn(0.5f, __fsub_rn(yp, ym));
-      const float two_v0 = __fmul_rn(2.0f, v0);
-      const float dxx = __fadd_rn(__fsub_rn(xp, two_v0), xm);
-      const float dyy = __fadd_rn(__fsub_rn(yp, two_v0), ym);
-      float t = __fsub_rn(xpyp, xp);
-      t = __fsub_rn(t, yp);
-      t = __fadd_rn(t, v0);
-      t = __fadd_rn(t, v0);
-      t = __fsub_rn(t, xm);
-      t = __fsub_rn(t, ym);
-      t = __fadd_rn(t, xmym);
-      const float dxy = __fmul_rn(0.5f, t);
-      // float64 solve of (H + eps32 * I) delta = g, as np.linalg.inv on the float64-promoted Hessian
-      const double eps = 1.1920928955078125e-07;
-      const double a = static_cast<double>(dxx) + eps, b = static_cast<double>(dxy),
-                   d = static_cast<double>(dyy) + eps;
-      const double det = a * d - b * b;
-      const double ddx = (d * static_cast<double>(dx) - b * static_cast<double>(dy)) / det;
-      const double ddy = (a * static_cast<double>(dy) - b * static_cast<double>(dx)) / det;
-      cx = static_cast<float>(static_cast<double>(cx) - ddx);
-      cy = static_cast<float>(static_cast<double>(cy) - ddy);
+    if (warp == 0) {                      // column pass + log on lanes 0..6, gathered into lane 0 by shuffles
+      float lv = 0.0f;
+      if (lane < 7) {
+        float acc = 0.0f;
+        for (int tr = 0; tr < ks; ++tr) acc = __fadd_rn(acc, __fmul_rn(p.taps[tr], s_part[lane * 32 + tr]));
+        acc = fminf(fmaxf(acc, 0.001f), 50.0f);
+        lv = logf(acc);
+      }
+      const float v0 = __shfl_sync(0xffffffffu, lv, 0), xp = __shfl_sync(0xffffffffu, lv, 1),
+                  xm = __shfl_sync(0xffffffffu, lv, 2), yp = __shfl_sync(0xffffffffu, lv, 3),
+                  ym = __shfl_sync(0xffffffffu, lv, 4), xpyp = __shfl_sync(0xffffffffu, lv, 5),
+                  xmym = __shfl_sync(0xffffffffu, lv, 6);
+      if (lane == 0) {
+        const float dx = __fmul_rn(0.5f, __fsub_rn(xp, xm));
+        const float dy = __fmul_rn(0.5f, __fsub_rn(yp, ym));
+        const float two_v0 = __fmul_rn(2.0f, v0);
+        const float dxx = __fadd_rn(__fsub_rn(xp, two_v0), xm);
+        const float dyy = __fadd_rn(__fsub_rn(yp, two_v0), ym);
+        float t = __fsub_rn(xpyp, xp);
+        t = __fsub_rn(t, yp);
+        t = __fadd_rn(t, v0);
+        t = __fadd_rn(t, v0);
+        t = __fsub_rn(t, xm);
+        t = __fsub_rn(t, ym);
+        t = __fadd_rn(t, xmym);
+        const float dxy = __fmul_rn(0.5f, t);
+        // float64 solve of (H + eps32 * I) delta = g, as np.linalg.inv on the float64-promoted Hessian
+        const double eps = 1.1920928955078125e-07;
+        const double a = static_cast<double>(dxx) + eps, b = static_cast<double>(dxy),
+                     d = static_cast<double>(dyy) + eps;
+        const double det = a * d - b * b;
+        const double ddx = (d * static_cast<double>(dx) - b * static_cast<double>(dy)) / det;
+        const double ddy = (a * static_cast<double>(dy) - b * static_cast<double>(dx)) / det;
+        cx = static_cast<float>(static_cast<double>(cx) - ddx);
+        cy = static_cast<float>(static_cast<double>(cy) - ddy);
+      }
     }
   } else if (p.mode == DECODE_UNBIASED) {
     // full zero-bordered separable blur (the rescale needs the max of the blurred map)
@@ -433,7 +438,9 @@ int decode_heatmaps(const float* hm, const float* hm_flipped, const int* flip_in
   p.merged_out = merged_out; p.argmax_out = argmax_out;
   for (int i = 0; i < DEC_MAX_TAPS; ++i) p.taps[i] = 0.f;
   if (mode == DECODE_UNBIASED || mode == DECODE_UDP_DARK) gaussian_taps_host(p.ksize, p.taps);
-  decode_kernel<<<N * K, DEC_THREADS, 0, stream>>>(p);
+  const bool need_aux = hm_flipped != nullptr || mode == DECODE_UNBIASED;
+  const size_t smem = static_cast<size_t>((H * W + 3) & ~3) * sizeof(float) * (need_aux ? 2 : 1);
+  decode_kernel<<<N * K, DEC_THREADS, smem, stream>>>(p);
   VPB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
