@@ -93,6 +93,22 @@ def test_decode_vs_oracle_random(seed, K, mode):
     _compare(r, p, m, hm)
 
 
+@pytest.mark.parametrize('kernel,width,height', [(11, 48, 64), (11, 46, 61), (7, 48, 64), (11, 36, 44), (11, 64, 64)])
+def test_unbiased_blur_paths_vs_oracle(kernel, width, height):
+    """post_process='unbiased' runs a register-blocked 11-tap blur when W % 4 == 0 and a generic loop otherwise;
+    both must reproduce the oracle (cv2.GaussianBlur on the zero-bordered map) for ragged sizes and other kernels."""
+    n, K = 4, 9
+    hm = synthetic.gaussian_peak_heatmaps(n, K, 11, height=height, width=width)
+    metas = synthetic.synthetic_metas(n, K, 11)
+    c = np.stack([m['center'] for m in metas])
+    s = np.stack([m['scale'] for m in metas])
+    kw = dict(post_process='unbiased', kernel=kernel)
+    with np.errstate(all='ignore'):
+        p, m = O.keypoints_from_heatmaps(hm, c, s, **kw)
+    r = _gpu_decode(hm, c, s, kw)
+    _compare(r, p, m, hm)
+
+
 @pytest.mark.parametrize('mode', ['udp_dark', 'default'])
 def test_decode_with_flip_vs_oracle(mode):
     n, K = 5, 17

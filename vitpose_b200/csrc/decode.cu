@@ -262,28 +262,90 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const DecodeParams 
     }
   } else if (p.mode == DECODE_UNBIASED) {
     // full zero-bordered separable blur (the rescale needs the max of the blurred map)
-    for (int i = tid; i < HW; i += DEC_THREADS) {
-      const int y = i / W, x = i - y * W;
-      float acc = 0.0f;
-      for (int tx = 0; tx < ks; ++tx) {
-        const int xx = x + tx - r;
-        const float v = (xx >= 0 && xx < W) ? s_map[y * W + xx] : 0.0f;
-        acc = __fadd_rn(acc, __fmul_rn(p.taps[tx], v));
-      }
-      s_aux[i] = acc;
-    }
-    __syncthreads();
     float bmax = -INFINITY;
-    for (int i = tid; i < HW; i += DEC_THREADS) {
-      const int y = i / W, x = i - y * W;
-      float acc = 0.0f;
-      for (int ty = 0; ty < ks; ++ty) {
-        const int yy = y + ty - r;
-        const float v = (yy >= 0 && yy < H) ? s_aux[yy * W + x] : 0.0f;
-        acc = __fadd_rn(acc, __fmul_rn(p.taps[ty], v));
+    if (ks == 11 && W % 4 == 0) {
+      // Register-blocked 11-tap passes (the shipped kernel size). Same per-output summation order as the generic
+      // loop below (acc = 0; acc += tap[t] * v, t ascending, zeros outside the map), so results are bit-identical.
+      const int W4 = W / 4;
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* m4 = reinterpret_cast<const float4*>(s_map);
+      float4* a4 = reinterpret_cast<float4*>(s_aux);
+      // rows: one 4-pixel group per thread-iteration; its 14 inputs come from five 16-byte loads
+      for (int g = tid; g < H * W4; g += DEC_THREADS) {
+        const int y = g / W4, x4 = g - y * W4;
+        float in[20];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const int gx = x4 + q - 2;
+          const float4 v = (gx >= 0 && gx < W4) ? m4[y * W4 + gx] : zero4;
+          in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
+        }
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float acc = 0.0f;
+#pragma unroll
+          for (int tx = 0; tx < 11; ++tx) acc = __fadd_rn(acc, __fmul_rn(p.taps[tx], in[c + tx + 3]));
+          o[c] = acc;
+        }
+        a4[g] = make_float4(o[0], o[1], o[2], o[3]);
       }
-      s_map[i] = acc;            // the un-blurred map is no longer needed
-      bmax = fmaxf(bmax, acc);
+      __syncthreads();
+      // columns: one (4-pixel column group, 8-row segment) per thread, an 11-row window sliding down in registers
+      float4* o4 = reinterpret_cast<float4*>(s_map);
+      const int nseg = (H + 7) / 8;
+      for (int item = tid; item < W4 * nseg; item += DEC_THREADS) {
+        const int seg = item / W4, x4 = item - seg * W4;
+        const int y0 = seg * 8;
+        float4 win[11];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          const int yy = y0 + j - 5;
+          win[j + 1] = (yy >= 0 && yy < H) ? a4[yy * W4 + x4] : zero4;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int j = 0; j < 10; ++j) win[j] = win[j + 1];
+          const int yy = y0 + i + 5;
+          win[10] = (yy < H) ? a4[yy * W4 + x4] : zero4;
+          if (y0 + i < H) {
+            float4 acc = zero4;
+#pragma unroll
+            for (int ty = 0; ty < 11; ++ty) {
+              acc.x = __fadd_rn(acc.x, __fmul_rn(p.taps[ty], win[ty].x));
+              acc.y = __fadd_rn(acc.y, __fmul_rn(p.taps[ty], win[ty].y));
+              acc.z = __fadd_rn(acc.z, __fmul_rn(p.taps[ty], win[ty].z));
+              acc.w = __fadd_rn(acc.w, __fmul_rn(p.taps[ty], win[ty].w));
+            }
+            o4[(y0 + i) * W4 + x4] = acc;      // the un-blurred map is no longer needed
+            bmax = fmaxf(bmax, fmaxf(fmaxf(acc.x, acc.y), fmaxf(acc.z, acc.w)));
+          }
+        }
+      }
+    } else {
+      for (int i = tid; i < HW; i += DEC_THREADS) {
+        const int y = i / W, x = i - y * W;
+        float acc = 0.0f;
+        for (int tx = 0; tx < ks; ++tx) {
+          const int xx = x + tx - r;
+          const float v = (xx >= 0 && xx < W) ? s_map[y * W + xx] : 0.0f;
+          acc = __fadd_rn(acc, __fmul_rn(p.taps[tx], v));
+        }
+        s_aux[i] = acc;
+      }
+      __syncthreads();
+      for (int i = tid; i < HW; i += DEC_THREADS) {
+        const int y = i / W, x = i - y * W;
+        float acc = 0.0f;
+        for (int ty = 0; ty < ks; ++ty) {
+          const int yy = y + ty - r;
+          const float v = (yy >= 0 && yy < H) ? s_aux[yy * W + x] : 0.0f;
+          acc = __fadd_rn(acc, __fmul_rn(p.taps[ty], v));
+        }
+        s_map[i] = acc;            // the un-blurred map is no longer needed
+        bmax = fmaxf(bmax, acc);
+      }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, off));
