@@ -244,6 +244,13 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
                                 static_cast<int>(gridDim.x)
                           : 0;
 
+  // Query tile of the i-th unit of this CTA. With an even grid, unit % q_tiles would be the same for every i, i.e. a
+  // CTA would get only full (128-row) or only partial (64-row, half the softmax warps idle) tiles; rotating the tile
+  // index by i hands every CTA the same mix. The q_tiles units of one (crop, head) share i whenever the grid is a
+  // multiple of q_tiles, so the rotation is a bijection.
+  const bool rotate_qt = (gridDim.x % q_tiles) == 0;
+  auto unit_qt = [&](int unit, int i) { return rotate_qt ? (unit + i) % q_tiles : unit % q_tiles; };
+
   if (threadIdx.x == 0) {
     for (int s = 0; s < ATT2_QK_DEPTH; ++s) { mbar_init(&qk_full[s], 1); mbar_init(&qk_free[s], 1); }
     for (int s = 0; s < ATT2_V_DEPTH; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_free[s], 1); }
@@ -284,7 +291,7 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
     if (lane == 0) {
       for (int i = 0; i < n_local; ++i) {
         const int unit = blockIdx.x + i * gridDim.x;
-        const int qt = unit % q_tiles;
+        const int qt = unit_qt(unit, i);
         const int head = (unit / q_tiles) % p.heads;
         const int crop = (unit / q_tiles) / p.heads;
         const int sq = i % ATT2_QK_DEPTH, sv = i % ATT2_V_DEPTH;
@@ -363,7 +370,7 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
     float mx_row = 0.f;
     auto softmax_load_max = [&](int i) {
       const int unit = blockIdx.x + i * gridDim.x;
-      const int qt = unit % q_tiles;
+      const int qt = unit_qt(unit, i);
       const int b = i & 1;
       const bool warp_live = (qt * ATT_BM + quad * 32 < T) && !(p.dbg & 1);   // warps past the sequence end skip the math
       timed_wait(&s_full[b], (i >> 1) & 1, 0);
@@ -390,7 +397,7 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
     };
     auto softmax_exp = [&](int i) -> float {
       const int unit = blockIdx.x + i * gridDim.x;
-      const int qt = unit % q_tiles;
+      const int qt = unit_qt(unit, i);
       const bool warp_live = (qt * ATT_BM + quad * 32 < T) && !(p.dbg & 1);
       float sum = 0.f;
       if (warp_live) {
@@ -438,7 +445,7 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
 
     auto epilogue = [&](int i, float inv) {
       const int unit = blockIdx.x + i * gridDim.x;
-      const int qt = unit % q_tiles;
+      const int qt = unit_qt(unit, i);
       const int head = (unit / q_tiles) % p.heads;
       const int crop = (unit / q_tiles) / p.heads;
       const int b = i % OB;
@@ -495,6 +502,344 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Ping-pong persistent attention (T = 192). Same unit walk, TMA producer and MMA issuer as the kernel above, but
+//   * the probabilities never touch shared memory: a softmax thread owns one whole query row, reads its scores from
+//     TMEM in 32-column chunks (pass 1: row max; pass 2: exp2, bf16 pack, row sum) and writes the packed bf16 pairs
+//     back over the first half of the same score columns with tcgen05.st; P.V then takes its A operand from TMEM;
+//   * two softmax groups of 128 threads (warps 2-5 and 6-9) work on alternate units with their own S / P / O columns,
+//     so one group's exp2 phase (MUFU-bound) overlaps the other's TMEM loads, row max and output epilogue, and no
+//     barrier or shared-memory exchange between threads of a row is left.
+// TMEM: S0 | S1 | O0 | O1; for head_dim 80 (2T + 2*80 > 512) O_g lives in the upper, already-consumed half of S_g and
+// S(i+2) is issued only after the epilogue of unit i has drained it.
+// -------------------------------------------------------------------------------------------------------------
+constexpr int PP_QK_DEPTH = 2;
+__host__ __device__ constexpr int pp_v_depth(int hd) { return hd > 64 ? 2 : 3; }
+// output staging: 8 softmax warps x 32 rows, row pitch = HD * 2 + 16 bytes (conflict-free 16-byte row writes)
+__host__ __device__ constexpr int pp_stage_pitch(int hd) { return hd * 2 + 16; }
+__host__ __device__ constexpr int pp_stage_bytes(int hd) { return 8 * 32 * pp_stage_pitch(hd); }
+constexpr int PP_THREADS = 64 + 256;
+
+template <int HD, int T_>
+__global__ void __launch_bounds__(PP_THREADS, 1)
+attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                          const __grid_constant__ CUtensorMap tm_qb, const __grid_constant__ CUtensorMap tm_kvb,
+                          const AttnParams p, const int num_units) {
+  static_assert(HD == 32 || HD == 64 || HD == 80, "ping-pong attention handles head_dim 32 / 64 / 80");
+  constexpr bool WIDE = HD > 64;
+  constexpr int T = T_;
+  constexpr bool O_ALIAS = 2 * T + 2 * HD > 512;
+  static_assert(T % 32 == 0 && 2 * T <= 512 && (!O_ALIAS || T / 2 + HD <= T), "S0 | S1 (| O0 | O1) must fit TMEM");
+  constexpr int QA_BYTES = ATT_BM * 128, KVA_BYTES = T * 128;
+  constexpr int Q_BYTES = ATT_BM * att2_row_bytes(HD), KV_BYTES = T * att2_row_bytes(HD);
+  constexpr int QK_BYTES = Q_BYTES + KV_BYTES;
+  constexpr int PP_V_DEPTH = pp_v_depth(HD);
+  constexpr int PITCH = pp_stage_pitch(HD);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_qk = smem;
+  uint8_t* s_v = s_qk + PP_QK_DEPTH * QK_BYTES;
+  uint8_t* s_stage = s_v + PP_V_DEPTH * KV_BYTES;
+  __shared__ uint64_t qk_full[PP_QK_DEPTH], qk_free[PP_QK_DEPTH], v_full[PP_V_DEPTH], v_free[PP_V_DEPTH];
+  __shared__ uint64_t s_full[2], p_full[2], o_full[2], o_free[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int q_tiles = (T + ATT_BM - 1) / ATT_BM;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_local = num_units > static_cast<int>(blockIdx.x)
+                          ? (num_units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                static_cast<int>(gridDim.x)
+                          : 0;
+  // rotate the query tile with i so every CTA and both softmax groups get the same mix of full and partial tiles,
+  // the two groups holding one of each at any time (group g sees (i + 1) / 2 = g, g + 1, g + 2, ...)
+  const bool rotate_qt = (gridDim.x % q_tiles) == 0;
+  auto unit_qt = [&](int unit, int i) { return rotate_qt ? (unit + ((i + 1) >> 1)) % q_tiles : unit % q_tiles; };
+  // A partial last tile (64 live rows for T = 192) is placed alternately at the bottom (tile rows [0, 64), TMA zero
+  // fill above) and at the top (the box starts at token T - 128: rows [64, 128) are the live ones, rows [0, 64) repeat
+  // tokens of the full tile and are ignored), so that its softmax work alternates between warps 0-1 and 2-3 of a
+  // group, i.e. between the SM's sub-partition pairs, instead of always loading the same two MUFU pipes.
+  struct Placement { int q0, r_lo, r_hi; };
+  auto unit_rows = [&](int qt, int i) {
+    const int live = (T - qt * ATT_BM < ATT_BM) ? T - qt * ATT_BM : ATT_BM;
+    const bool high = live < ATT_BM && T >= ATT_BM && ((i >> 2) & 1);
+    Placement pl;
+    pl.q0 = high ? T - ATT_BM : qt * ATT_BM;
+    pl.r_lo = high ? ATT_BM - live : 0;
+    pl.r_hi = high ? ATT_BM : live;
+    return pl;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PP_QK_DEPTH; ++s) { mbar_init(&qk_full[s], 1); mbar_init(&qk_free[s], 1); }
+    for (int s = 0; s < PP_V_DEPTH; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_free[s], 1); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 128);
+      mbar_init(&o_full[g], 1);
+      mbar_init(&o_free[g], 128);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+    if (WIDE) {
+      tma_prefetch_desc(&tm_qb);
+      tma_prefetch_desc(&tm_kvb);
+    }
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  // cycle accounting (CTA 0 only, one thread per role), enabled with VPB_ATT_DEBUG & 32; printed by & 64
+  const bool timing = p.dbg_buf != nullptr && blockIdx.x == 0;
+  long long t_acc[6] = {0, 0, 0, 0, 0, 0};
+  auto timed_wait = [&](uint64_t* bar, uint32_t parity, int slot) {
+    if (timing) {
+      const long long t0 = clock64();
+      mbar_wait(bar, parity);
+      t_acc[slot] += clock64() - t0;
+    } else {
+      mbar_wait(bar, parity);
+    }
+  };
+  const long long t_start = clock64();
+  auto s_col = [&](int g) { return static_cast<uint32_t>(g * T); };
+  auto o_col = [&](int g) { return static_cast<uint32_t>(O_ALIAS ? g * T + T / 2 : 2 * T + g * HD); };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < n_local; ++i) {
+        const int unit = blockIdx.x + i * gridDim.x;
+        const int qt = unit_qt(unit, i);
+        const int head = (unit / q_tiles) % p.heads;
+        const int crop = (unit / q_tiles) / p.heads;
+        const int sq = i % PP_QK_DEPTH, sv = i % PP_V_DEPTH;
+        const int q0 = unit_rows(qt, i).q0;
+        timed_wait(&qk_free[sq], ((i / PP_QK_DEPTH) & 1) ^ 1, 0);
+        mbar_arrive_expect_tx(&qk_full[sq], QK_BYTES);
+        tma_load_3d(s_qk + sq * QK_BYTES, &tm_q, &qk_full[sq], head * HD, q0, crop);
+        tma_load_3d(s_qk + sq * QK_BYTES + Q_BYTES, &tm_kv, &qk_full[sq], p.heads * HD + head * HD, 0, crop);
+        if constexpr (WIDE) {     // columns [64, 80) of Q and K
+          tma_load_3d(s_qk + sq * QK_BYTES + QA_BYTES, &tm_qb, &qk_full[sq], head * HD + 64, q0, crop);
+          tma_load_3d(s_qk + sq * QK_BYTES + Q_BYTES + KVA_BYTES, &tm_kvb, &qk_full[sq], p.heads * HD + head * HD + 64,
+                      0, crop);
+        }
+        timed_wait(&v_free[sv], ((i / PP_V_DEPTH) & 1) ^ 1, 1);
+        mbar_arrive_expect_tx(&v_full[sv], KV_BYTES);
+        tma_load_3d(s_v + sv * KV_BYTES, &tm_kv, &v_full[sv], 2 * p.heads * HD + head * HD, 0, crop);
+        if constexpr (WIDE)
+          tma_load_3d(s_v + sv * KV_BYTES + KVA_BYTES, &tm_kvb, &v_full[sv], 2 * p.heads * HD + head * HD + 64, 0, crop);
+      }
+      if (timing) { p.dbg_buf[0] = t_acc[0]; p.dbg_buf[1] = t_acc[1]; }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, T);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BM, WIDE ? 64 : HD, 0, 1);
+      constexpr uint32_t idesc_o16 = umma_idesc_bf16(ATT_BM, 16, 0, 1);
+      auto issue_s = [&](int i) {
+        const int sq = i % PP_QK_DEPTH, g = i & 1;
+        // S_g: its scores were consumed before p_full(i-2) and P(i-2) was read by P.V(i-2), issued earlier by this
+        // thread; with O_g aliased into S_g the epilogue of unit i-2 must have drained it as well
+        if constexpr (O_ALIAS) timed_wait(&o_free[g], ((i >> 1) & 1) ^ 1, 2);
+        timed_wait(&qk_full[sq], (i / PP_QK_DEPTH) & 1, 0);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(s_qk + sq * QK_BYTES), ka = qa + Q_BYTES;
+        if (!(p.dbg & 4)) {
+#pragma unroll
+          for (int ks = 0; ks < (WIDE ? 4 : HD / 16); ++ks)
+            umma_bf16_ss(tmem_base + s_col(g), umma_desc_k_sw128(qa + ks * 32), umma_desc_k_sw128(ka + ks * 32),
+                         idesc_s, ks != 0);
+          if constexpr (WIDE)
+            umma_bf16_ss(tmem_base + s_col(g), umma_desc_k_sw32(qa + QA_BYTES), umma_desc_k_sw32(ka + KVA_BYTES),
+                         idesc_s, 1u);
+        }
+        umma_commit(&s_full[g]);
+        umma_commit(&qk_free[sq]);
+      };
+      if (n_local > 0) issue_s(0);
+      if (n_local > 1) issue_s(1);
+      for (int i = 0; i < n_local; ++i) {
+        const int sv = i % PP_V_DEPTH, g = i & 1;
+        timed_wait(&p_full[g], (i >> 1) & 1, 1);                               // P(i) in TMEM, S(i) consumed
+        if constexpr (!O_ALIAS) timed_wait(&o_free[g], ((i >> 1) & 1) ^ 1, 2);    // O_g drained by the epilogue of unit i-2
+        timed_wait(&v_full[sv], (i / PP_V_DEPTH) & 1, 3);
+        tc_fence_after();
+        const uint32_t d = tmem_base + o_col(g);
+        const uint32_t pa = tmem_base + s_col(g);
+        const uint32_t va = smem_u32(s_v + sv * KV_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < ((p.dbg & 2) ? 0 : T / 16); ++ks) {
+          umma_bf16_ts(d, pa + ks * 8, umma_desc_mn_sw128(va + ks * 2048, KVA_BYTES), idesc_o, ks != 0);
+          if constexpr (WIDE)
+            umma_bf16_ts(d + 64, pa + ks * 8, umma_desc_mn_sw32(va + KVA_BYTES + ks * 512), idesc_o16, ks != 0);
+        }
+        umma_commit(&o_full[g]);
+        umma_commit(&v_free[sv]);
+        if (i + 2 < n_local) issue_s(i + 2);
+      }
+      if (timing) { for (int k = 0; k < 4; ++k) p.dbg_buf[2 + k] = t_acc[k]; }
+    }
+  } else {
+    const int g = (warp - 2) >> 2;                  // softmax group: units i = g, g + 2, ...
+    const int quad = warp & 3;                      // TMEM lane quarter this warp may access
+    const int r = quad * 32 + lane;                 // query row inside the tile
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t S = lane_base + s_col(g), O = lane_base + o_col(g);
+    constexpr int NC = T / 32;
+
+    const long long t_loop = timing ? clock64() : 0;
+    long long t_body = 0;
+    for (int i = g; i < n_local; i += 2) {
+      const long long t_top = timing ? clock64() : 0;
+      const int unit = blockIdx.x + i * gridDim.x;
+      const int qt = unit_qt(unit, i);
+      const int head = (unit / q_tiles) % p.heads;
+      const int crop = (unit / q_tiles) / p.heads;
+      const Placement pl = unit_rows(qt, i);
+      const int token = pl.q0 + r;
+      const bool rows_here = quad * 32 < pl.r_hi && quad * 32 + 32 > pl.r_lo;
+      const bool warp_live = rows_here && !(p.dbg & 1);                         // warps without live rows skip the math
+      const bool row_live = r >= pl.r_lo && r < pl.r_hi;
+      const uint32_t ph = (i >> 1) & 1;
+      float inv = 0.f;
+      const bool tlive = timing && warp_live;      // counters: s_full wait, softmax math, o_full wait, epilogue
+      timed_wait(&s_full[g], ph, warp_live ? 0 : 4);
+      long long t_mark = tlive ? clock64() : 0;
+      tc_fence_after();
+      if (warp_live) {
+        uint32_t va[32], vb[32];
+        // pass 1: row maximum
+        float mx = -INFINITY;
+        tmem_ld_32x32b_x32(S, va);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          uint32_t(&cur)[32] = (c & 1) ? vb : va;
+          uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+          tmem_ld_wait();
+          if (c + 1 < NC) tmem_ld_32x32b_x32(S + 32 * (c + 1), nxt);
+          float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(cur[j + 2]), __uint_as_float(cur[j + 3])));
+          }
+          mx = fmaxf(mx, fmaxf(m0, m1));
+        }
+        // pass 2: p = exp2(s * scale*log2e - max'), bf16 pairs written back over columns [16c, 16c + 16) — always
+        // behind the columns still to be read
+        const float2 sc = make_float2(p.scale_log2e, p.scale_log2e);
+        const float2 nm = make_float2(-mx * p.scale_log2e, -mx * p.scale_log2e);
+        float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+        tmem_ld_32x32b_x32(S, va);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          uint32_t(&cur)[32] = (c & 1) ? vb : va;
+          uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+          tmem_ld_wait();
+          if (c + 1 < NC) tmem_ld_32x32b_x32(S + 32 * (c + 1), nxt);
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 a = __ffma2_rn(make_float2(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1])), sc, nm);
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(fast_ex2(a.x), fast_ex2(a.y));
+            if (j & 1) sum_b = __fadd2_rn(sum_b, __bfloat1622float2(b2));      // sum what the tensor core will see
+            else       sum_a = __fadd2_rn(sum_a, __bfloat1622float2(b2));
+            pk[j] = *reinterpret_cast<const uint32_t*>(&b2);
+          }
+          tmem_st_32x32b_x16(S + 16 * c, pk);
+        }
+        tmem_st_wait();
+        const float sum = (sum_a.x + sum_b.x) + (sum_a.y + sum_b.y);
+        inv = 1.0f / sum;
+        if (p.lse != nullptr && row_live)
+          p.lse[(static_cast<size_t>(crop) * p.heads + head) * T + token] = fmaf(mx, p.scale_log2e, log2f(sum));
+      }
+      tc_fence_before();            // our tcgen05.ld / st of S_g are complete and ordered before the arrive
+      mbar_arrive(&p_full[g]);
+      if (tlive) t_acc[1] += clock64() - t_mark;
+
+      // epilogue: O_g / row sum -> bf16, one whole output row (HD * 2 bytes, contiguous) per thread
+      timed_wait(&o_full[g], ph, warp_live ? 2 : 4);
+      t_mark = tlive ? clock64() : 0;
+      tc_fence_after();
+      if (warp_live) {
+        uint32_t o[HD];               // all loads in flight at once, one wait
+#pragma unroll
+        for (int c = 0; c < HD; c += 16) tmem_ld_32x32b_x16(O + c, *reinterpret_cast<uint32_t(*)[16]>(&o[c]));
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&o_free[g]);      // O_g is in registers: the next P.V (or S, when aliased) may overwrite it now
+        // A thread owns a row, but a row-per-thread store touches 32 different 128-byte lines with 16 bytes each per
+        // instruction (measured: 38 of 115 us). Stage the warp's 32 rows in shared memory and write them back with
+        // consecutive lanes on consecutive 16-byte pieces of a row: whole lines per instruction.
+        uint8_t* stage = s_stage + (warp - 2) * 32 * PITCH;
+#pragma unroll
+        for (int c = 0; c < HD; c += 8) {
+          uint32_t w4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            w4[j] = pack_bf16x2(__uint_as_float(o[c + 2 * j]) * inv, __uint_as_float(o[c + 2 * j + 1]) * inv);
+          *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 2) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+        __syncwarp();
+        if (!(p.dbg & 8)) {
+          constexpr int CH = HD / 8;          // 16-byte pieces per row
+          __nv_bfloat16* obase = p.out + (static_cast<size_t>(crop) * T + pl.q0 + quad * 32) * p.ldo + head * HD;
+#pragma unroll
+          for (int e = lane; e < 32 * CH; e += 32) {
+            const int row = e / CH, ch = e - row * CH;
+            const int rr = quad * 32 + row;
+            if (rr >= pl.r_lo && rr < pl.r_hi)
+              *reinterpret_cast<uint4*>(obase + static_cast<size_t>(row) * p.ldo + ch * 8) =
+                  *reinterpret_cast<const uint4*>(stage + row * PITCH + ch * 16);
+          }
+        }
+        __syncwarp();
+      } else {
+        tc_fence_before();
+        mbar_arrive(&o_free[g]);
+      }
+      if (tlive) { t_acc[3] += clock64() - t_mark; t_acc[5] += 1; }
+      if (timing) t_body += clock64() - t_top;
+    }
+    if (timing && threadIdx.x == 128) {
+      for (int k = 0; k < 4; ++k) p.dbg_buf[6 + k] = t_acc[k];
+      p.dbg_buf[10] = clock64() - t_start;
+      p.dbg_buf[11] = n_local;
+      p.dbg_buf[12] = t_acc[4];
+      p.dbg_buf[13] = t_acc[5];
+      p.dbg_buf[14] = t_loop - t_start;
+      p.dbg_buf[15] = t_body;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int HD, int T_>
+static int launch_attention_pingpong(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& tqb,
+                                     const CUtensorMap& tkvb, const AttnParams& p, int max_ctas, cudaStream_t stream) {
+  constexpr int smem = PP_QK_DEPTH * (ATT_BM + T_) * att2_row_bytes(HD) + pp_v_depth(HD) * T_ * att2_row_bytes(HD) +
+                       pp_stage_bytes(HD) + 1024;
+  static_assert(smem <= 227 * 1024 - 6 * 1024, "ping-pong attention tiles do not fit shared memory");
+  auto kern = attention_pingpong_kernel<HD, T_>;
+  static bool configured = false;
+  if (!configured) {
+    VPB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int q_tiles = (T_ + ATT_BM - 1) / ATT_BM;
+  const int units = p.n * p.heads * q_tiles;
+  int grid = max_ctas > 0 ? max_ctas : sm_count();
+  if (grid > units) grid = units;
+  kern<<<grid, PP_THREADS, smem, stream>>>(tq, tkv, tqb, tkvb, p, units);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 template <int HD, int T_, int NSPLIT>
@@ -564,10 +909,11 @@ int attention_fwd(const void* qkv, void* out, int n, int T, int heads, int hd, f
     if (p.dbg & 64) {   // print the counters of the previous launch
       cudaStreamSynchronize(stream);
       if (dbg_buf)
-        fprintf(stderr, "att waits (cycles, CTA0): producer qk_free %lld v_free %lld | mma qk_full %lld p_full %lld "
-                        "o_free %lld v_full %lld | softmax s_full %lld o_full(P) %lld o_full(epi) %lld | total %lld units %lld\n",
+        fprintf(stderr, "att cycles (CTA0): producer qk_free %lld v_free %lld | mma qk_full %lld p_full %lld o_free %lld "
+                        "v_full %lld | softmax thread 128, live units: s_full %lld math %lld o_full %lld epilogue %lld "
+                        "(%lld units), idle units %lld | total %lld, %lld units, loop entry at %lld, loop bodies %lld\n",
                 dbg_buf[0], dbg_buf[1], dbg_buf[2], dbg_buf[3], dbg_buf[4], dbg_buf[5], dbg_buf[6], dbg_buf[7],
-                dbg_buf[8], dbg_buf[9], dbg_buf[10]);
+                dbg_buf[8], dbg_buf[9], dbg_buf[13], dbg_buf[12], dbg_buf[10], dbg_buf[11], dbg_buf[14], dbg_buf[15]);
     }
   }
   const int nb = att_boxes(hd);
@@ -577,6 +923,20 @@ int attention_fwd(const void* qkv, void* out, int n, int T, int heads, int hd, f
   const int smem = region0 + nb * T * 128 + 1024;
   if (max_ctas >= 0) {   // max_ctas < 0 selects the per-unit kernel (kept for head_dim > 64 and for A/B tests)
     int rc = 1;
+    const bool pingpong = !(p.dbg & 256);     // VPB_ATT_DEBUG & 256: the single-group kernel (P through smem), for A/B
+    if (pingpong && hd == 32 && T == 192) rc = launch_attention_pingpong<32, 192>(tq, tkv, tq, tkv, p, max_ctas, stream);
+    if (pingpong && hd == 64 && T == 192) rc = launch_attention_pingpong<64, 192>(tq, tkv, tq, tkv, p, max_ctas, stream);
+    // head_dim 80: O_g has to alias the consumed half of S_g (2T + 2*80 > 512 TMEM columns), which serialises S(i+2)
+    // behind the epilogue of unit i; measured 50.5 us vs 47.7 us for the single-group kernel at 64 crops, so that
+    // kernel stays the default for ViT-H (VPB_ATT_DEBUG & 512 selects the ping-pong one)
+    if (pingpong && (p.dbg & 512) && hd == 80 && T == 192) {
+      CUtensorMap tqb, tkvb;
+      uint32_t box_qb[3] = {16, ATT_BM, 1}, box_kvb[3] = {16, (uint32_t)T, 1};
+      if (make_tma_desc(&tqb, TMA_BF16, qkv, 3, dims, strides, box_qb, TMA_SWIZZLE_32B)) return -1;
+      if (make_tma_desc(&tkvb, TMA_BF16, qkv, 3, dims, strides, box_kvb, TMA_SWIZZLE_32B)) return -1;
+      rc = launch_attention_pingpong<80, 192>(tq, tkv, tqb, tkvb, p, max_ctas, stream);
+    }
+    if (rc <= 0) return rc;
     if (hd == 32 && T == 192) rc = launch_attention_persistent<32, 192, 2>(tq, tkv, tq, tkv, p, max_ctas, stream);
     if (hd == 64 && T == 192) {
       // measured at 256 images x 12 heads: 2 column parts per row (8 softmax warps) 0.109 ms, 4 parts (16 warps) 0.134 ms
