@@ -212,45 +212,66 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       mbar_arrive(&bar_ds);
       mbar_wait(&bar_mma, t);
       tc_fence_after();
-      // dQ rows of this tile: 32 of the 64 columns per thread
+      // dQ rows of this tile: 32 of the 64 columns per thread. A row-per-thread global store would touch 32 lines
+      // with 16 bytes each per instruction, so the warp stages its 32 x 64-byte block in shared memory (the Q rows
+      // of tile 0, dead once bar_mma(0) has completed; 16-byte pieces XOR-swizzled: conflict-free both ways) and
+      // writes it back with four lanes per row.
       {
-        __nv_bfloat16* orow = p.dqkv + (static_cast<size_t>(crop) * AB_T + token) * ld_qkv + head * AB_HD + half * 32;
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_dq + lane_off + half * 32, v);
         tmem_ld_wait();
-        if (valid) {
+        uint8_t* stage = s_q + (warp - 1) * 2048;
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            reinterpret_cast<uint4*>(orow)[u] =
-                make_uint4(pack_bf16x2(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
-                           pack_bf16x2(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
-                           pack_bf16x2(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
-                           pack_bf16x2(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<uint4*>(stage + lane * 64 + ((u ^ ((lane >> 1) & 3)) * 16)) =
+              make_uint4(pack_bf16x2(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
+                         pack_bf16x2(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
+                         pack_bf16x2(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
+                         pack_bf16x2(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
+        __syncwarp();
+        __nv_bfloat16* obase = p.dqkv + (static_cast<size_t>(crop) * AB_T + t * 128 + quad * 32) * ld_qkv +
+                               head * AB_HD + half * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int row = 8 * j + (lane >> 2), ch = lane & 3;
+          if (t * 128 + quad * 32 + row < AB_T)
+            *reinterpret_cast<uint4*>(obase + static_cast<size_t>(row) * ld_qkv + ch * 8) =
+                *reinterpret_cast<const uint4*>(stage + row * 64 + ((ch ^ ((row >> 1) & 3)) * 16));
         }
+        __syncwarp();
       }
       tc_fence_before();
     }
-    // dK / dV rows (keys): key tile m, lane r <-> key m*128 + r; half 0 stores dK, half 1 stores dV
+    // dK / dV rows (keys): key tile m, lane r <-> key m*128 + r; half 0 stores dK, half 1 stores dV. Every operand tile
+    // is dead by now (all MMAs have completed): the warp stages its 32 x 128-byte block in the K/V/dO area (row pitch
+    // 144 bytes) and stores whole 128-byte lines, eight lanes per row.
     for (int m = 0; m < 2; ++m) {
-      const int key = m * 128 + r;
       const uint32_t base = (half == 0 ? tmem_dk : tmem_dv) + m * AB_HD + lane_off;
-      __nv_bfloat16* orow =
-          p.dqkv + (static_cast<size_t>(crop) * AB_T + key) * ld_qkv + (1 + half) * ld_o + head * AB_HD;
+      uint8_t* stage = s_k + (warp - 1) * (32 * 144);
 #pragma unroll
       for (int c = 0; c < AB_HD; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(base + c, v);
         tmem_ld_wait();
-        if (key < AB_T) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            reinterpret_cast<uint4*>(orow + c)[u] =
-                make_uint4(pack_bf16x2(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
-                           pack_bf16x2(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
-                           pack_bf16x2(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
-                           pack_bf16x2(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
-        }
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<uint4*>(stage + lane * 144 + c * 2 + u * 16) =
+              make_uint4(pack_bf16x2(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
+                         pack_bf16x2(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
+                         pack_bf16x2(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
+                         pack_bf16x2(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
       }
+      __syncwarp();
+      __nv_bfloat16* obase = p.dqkv + (static_cast<size_t>(crop) * AB_T + m * 128 + quad * 32) * ld_qkv +
+                             (1 + half) * ld_o + head * AB_HD;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int row = 4 * j + (lane >> 3), ch = lane & 7;
+        if (m * 128 + quad * 32 + row < AB_T)
+          *reinterpret_cast<uint4*>(obase + static_cast<size_t>(row) * ld_qkv + ch * 8) =
+              *reinterpret_cast<const uint4*>(stage + row * 144 + ch * 16);
+      }
+      __syncwarp();
     }
   }
   tc_fence_before();
