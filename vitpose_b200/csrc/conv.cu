@@ -57,6 +57,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   __shared__ uint64_t tfull_bar, tempty_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_ss[2][2][BN];                 // [item parity][scale | shift][channel of the n-tile]
+  __shared__ __align__(16) uint8_t s_ostage[4][32 * 64];   // per epilogue warp: 32 pixels x 64 bytes (deconv stores)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cin_chunks = p.cin / 64;
@@ -174,27 +175,47 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         const bool ok = img < p.n && iy < p.h;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + sub * BN;
         if constexpr (MODE == MODE_DECONV && BN % 32 == 0) {
+          // A thread owns a pixel, but pixel-per-thread stores put 16 bytes into 32 different lines per instruction.
+          // Each warp stages its 32 pixels x 32 channels in shared memory (16-byte pieces XOR-swizzled, conflict-free
+          // both ways) and writes them back with four lanes per pixel: 64 contiguous bytes, whole sectors.
           const int oy = 2 * iy + py, ox = 2 * xx + px;
-          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                ((static_cast<size_t>(img) * (2 * p.h) + oy) * (2 * p.w) + ox) * p.cout + nt * BN;
+          const long long my_off =
+              ok ? ((static_cast<long long>(img) * (2 * p.h) + oy) * (2 * p.w) + ox) * p.cout + nt * BN : -1;
+          long long poff[4];                        // output offsets of the pixels this lane writes back
+#pragma unroll
+          for (int j = 0; j < 4; ++j) poff[j] = __shfl_sync(0xffffffffu, my_off, 8 * j + (lane >> 2));
+          uint8_t* stage = s_ostage[quad];
+          __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out);
 #pragma unroll 1
           for (int c = 0; c < BN; c += 32) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_row + c, r);
             tmem_ld_wait();
-            if (!ok || nt * BN + c >= p.cout) continue;
-            uint32_t w[16];
+            if (nt * BN + c >= p.cout) continue;     // warp-uniform
+            if (nt * BN + c + 32 <= p.cout) {        // 64 contiguous bytes per pixel (warp-uniform)
+              uint32_t w[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float a = fmaxf(fmaf(__uint_as_float(r[2 * j]), sc[c + 2 * j], sh[c + 2 * j]), p.floor);
-              const float b = fmaxf(fmaf(__uint_as_float(r[2 * j + 1]), sc[c + 2 * j + 1], sh[c + 2 * j + 1]), p.floor);
-              w[j] = pack_bf16x2(a, b);
-            }
-            if (nt * BN + c + 32 <= p.cout) {          // 64 contiguous bytes per pixel
+              for (int j = 0; j < 16; ++j) {
+                const float a = fmaxf(fmaf(__uint_as_float(r[2 * j]), sc[c + 2 * j], sh[c + 2 * j]), p.floor);
+                const float b =
+                    fmaxf(fmaf(__uint_as_float(r[2 * j + 1]), sc[c + 2 * j + 1], sh[c + 2 * j + 1]), p.floor);
+                w[j] = pack_bf16x2(a, b);
+              }
 #pragma unroll
               for (int u = 0; u < 4; ++u)
-                reinterpret_cast<uint4*>(orow + c)[u] = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
-            } else {
+                *reinterpret_cast<uint4*>(stage + lane * 64 + ((u ^ ((lane >> 1) & 3)) * 16)) =
+                    make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int row = 8 * j + (lane >> 2), ch = lane & 3;
+                if (poff[j] >= 0)
+                  *reinterpret_cast<uint4*>(obase + poff[j] + c + ch * 8) =
+                      *reinterpret_cast<const uint4*>(stage + row * 64 + ((ch ^ ((row >> 1) & 3)) * 16));
+              }
+              __syncwarp();
+            } else if (ok) {
+              __nv_bfloat16* orow = obase + my_off;
               for (int j = 0; j < p.cout - (nt * BN + c); ++j)
                 orow[c + j] = __float2bfloat16_rn(fmaxf(fmaf(__uint_as_float(r[j]), sc[c + j], sh[c + j]), p.floor));
             }
