@@ -392,7 +392,7 @@ def main():
                              h2d_bytes_per_step=int(host[0].numel() * 4 + n * 16),
                              d2h_bytes_per_step=int(n * K * 3 * 4), ms_per_step=e2e_ms,
                              api='TopDown.forward_test(img=<pinned host fp32>, img_metas=...)'))
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # rank 0 at N = 1 only (other ranks would compete for the cores)
             threads = os.cpu_count() or 1
             rate, _ = oracle_crops_per_sec(cfg, sd, 4, K, threads, steps=1, warmup=1)
             ns = int(max(4, min(n, rate * 12)))
