@@ -691,6 +691,26 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     const uint32_t S = lane_base + s_col(g), O = lane_base + o_col(g);
     constexpr int NC = T / 32;
 
+    // The staged output block of a unit is written to global memory one unit later, while this group waits for the
+    // next P.V to complete (it has nothing else to do then), instead of at the end of its own epilogue.
+    uint8_t* const stage = s_stage + (warp - 2) * 32 * PITCH;
+    __nv_bfloat16* pend_base = nullptr;       // null: nothing pending
+    int pend_lo = 0, pend_hi = 0;
+    auto flush_pending = [&]() {
+      if (pend_base != nullptr && !(p.dbg & 8)) {
+        constexpr int CH = HD / 8;            // 16-byte pieces per row
+#pragma unroll
+        for (int e = lane; e < 32 * CH; e += 32) {
+          const int row = e / CH, ch = e - row * CH;
+          const int rr = quad * 32 + row;
+          if (rr >= pend_lo && rr < pend_hi)
+            *reinterpret_cast<uint4*>(pend_base + static_cast<size_t>(row) * p.ldo + ch * 8) =
+                *reinterpret_cast<const uint4*>(stage + row * PITCH + ch * 16);
+        }
+        __syncwarp();                         // the block may be overwritten by the next epilogue
+      }
+      pend_base = nullptr;
+    };
     const long long t_loop = timing ? clock64() : 0;
     long long t_body = 0;
     for (int i = g; i < n_local; i += 2) {
@@ -745,9 +765,12 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float2 a = __ffma2_rn(make_float2(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1])), sc, nm);
-            const __nv_bfloat162 b2 = __floats2bfloat162_rn(fast_ex2(a.x), fast_ex2(a.y));
-            if (j & 1) sum_b = __fadd2_rn(sum_b, __bfloat1622float2(b2));      // sum what the tensor core will see
-            else       sum_a = __fadd2_rn(sum_a, __bfloat1622float2(b2));
+            const float2 e = make_float2(fast_ex2(a.x), fast_ex2(a.y));
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(e.x, e.y);
+            // row sum of the unrounded values: two instructions per pair fewer than unpacking the bf16 pair again; the
+            // difference to the sum of the rounded ones is ~2^-9 / sqrt(T) relative, far below the bf16 output rounding
+            if (j & 1) sum_b = __fadd2_rn(sum_b, e);
+            else       sum_a = __fadd2_rn(sum_a, e);
             pk[j] = *reinterpret_cast<const uint32_t*>(&b2);
           }
           tmem_st_32x32b_x16(S + 16 * c, pk);
@@ -761,6 +784,7 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       tc_fence_before();            // our tcgen05.ld / st of S_g are complete and ordered before the arrive
       mbar_arrive(&p_full[g]);
       if (tlive) t_acc[1] += clock64() - t_mark;
+      flush_pending();              // previous unit's output rows, while P.V of this one runs
 
       // epilogue: O_g / row sum -> bf16, one whole output row (HD * 2 bytes, contiguous) per thread
       timed_wait(&o_full[g], ph, warp_live ? 2 : 4);
@@ -776,7 +800,6 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
         // A thread owns a row, but a row-per-thread store touches 32 different 128-byte lines with 16 bytes each per
         // instruction (measured: 38 of 115 us). Stage the warp's 32 rows in shared memory and write them back with
         // consecutive lanes on consecutive 16-byte pieces of a row: whole lines per instruction.
-        uint8_t* stage = s_stage + (warp - 2) * 32 * PITCH;
 #pragma unroll
         for (int c = 0; c < HD; c += 8) {
           uint32_t w4[4];
@@ -786,19 +809,9 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
           *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 2) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
         }
         __syncwarp();
-        if (!(p.dbg & 8)) {
-          constexpr int CH = HD / 8;          // 16-byte pieces per row
-          __nv_bfloat16* obase = p.out + (static_cast<size_t>(crop) * T + pl.q0 + quad * 32) * p.ldo + head * HD;
-#pragma unroll
-          for (int e = lane; e < 32 * CH; e += 32) {
-            const int row = e / CH, ch = e - row * CH;
-            const int rr = quad * 32 + row;
-            if (rr >= pl.r_lo && rr < pl.r_hi)
-              *reinterpret_cast<uint4*>(obase + static_cast<size_t>(row) * p.ldo + ch * 8) =
-                  *reinterpret_cast<const uint4*>(stage + row * PITCH + ch * 16);
-          }
-        }
-        __syncwarp();
+        pend_base = p.out + (static_cast<size_t>(crop) * T + pl.q0 + quad * 32) * p.ldo + head * HD;
+        pend_lo = pl.r_lo;
+        pend_hi = pl.r_hi;
       } else {
         tc_fence_before();
         mbar_arrive(&o_free[g]);
@@ -806,6 +819,7 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       if (tlive) { t_acc[3] += clock64() - t_mark; t_acc[5] += 1; }
       if (timing) t_body += clock64() - t_top;
     }
+    flush_pending();
     if (timing && threadIdx.x == 128) {
       for (int k = 0; k < 4; ++k) p.dbg_buf[6 + k] = t_acc[k];
       p.dbg_buf[10] = clock64() - t_start;
@@ -926,10 +940,10 @@ int attention_fwd(const void* qkv, void* out, int n, int T, int heads, int hd, f
     const bool pingpong = !(p.dbg & 256);     // VPB_ATT_DEBUG & 256: the single-group kernel (P through smem), for A/B
     if (pingpong && hd == 32 && T == 192) rc = launch_attention_pingpong<32, 192>(tq, tkv, tq, tkv, p, max_ctas, stream);
     if (pingpong && hd == 64 && T == 192) rc = launch_attention_pingpong<64, 192>(tq, tkv, tq, tkv, p, max_ctas, stream);
-    // head_dim 80: O_g has to alias the consumed half of S_g (2T + 2*80 > 512 TMEM columns), which serialises S(i+2)
-    // behind the epilogue of unit i; measured 50.5 us vs 47.7 us for the single-group kernel at 64 crops, so that
-    // kernel stays the default for ViT-H (VPB_ATT_DEBUG & 512 selects the ping-pong one)
-    if (pingpong && (p.dbg & 512) && hd == 80 && T == 192) {
+    // head_dim 80: O_g aliases the consumed half of S_g (2T + 2*80 > 512 TMEM columns), so S(i+2) is issued after the
+    // epilogue of unit i has loaded O_g into registers; still 65.6 us vs 85.8 us for the single-group kernel at 128
+    // image passes once the output stores were deferred
+    if (pingpong && hd == 80 && T == 192) {
       CUtensorMap tqb, tkvb;
       uint32_t box_qb[3] = {16, ATT_BM, 1}, box_kvb[3] = {16, (uint32_t)T, 1};
       if (make_tma_desc(&tqb, TMA_BF16, qkv, 3, dims, strides, box_qb, TMA_SWIZZLE_32B)) return -1;
