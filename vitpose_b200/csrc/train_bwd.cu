@@ -224,6 +224,21 @@ int bn_relu_bwd_reduce(const void* raw, const void* dact, const float* mean, con
 // GELU (exact erf, nn.GELU default): forward on the stored pre-activation and its derivative
 //   d/dx [x Phi(x)] = Phi(x) + x phi(x)
 // -------------------------------------------------------------------------------------------------
+// erf(x / sqrt 2) and exp(-x^2 / 2) from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, float rounding level), one rcp
+// and one ex2 instead of erff()'s ~40 instructions: with erff() these two kernels were instruction-bound (47 us of
+// issue time against 23 us of HBM time per layer). The exponential is also the Gaussian density of the derivative.
+__device__ __forceinline__ void erf_and_gauss(float x, float& erf_s, float& gauss) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  gauss = fast_ex2(-1.4426950408889634f * z * z);          // exp(-x^2 / 2)
+  erf_s = copysignf(fmaf(-poly, gauss, 1.0f), x);
+}
+
 __global__ void gelu_fwd_kernel(const uint4* __restrict__ pre, uint4* __restrict__ out, long long n8) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
@@ -232,9 +247,11 @@ __global__ void gelu_fwd_kernel(const uint4* __restrict__ pre, uint4* __restrict
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
-    const float a = 0.5f * f.x * (1.0f + erff(f.x * 0.70710678118654752f));
-    const float b = 0.5f * f.y * (1.0f + erff(f.y * 0.70710678118654752f));
-    w[j] = pack_bf16x2(a, b);
+    float ea, eb, ga, gb;
+    erf_and_gauss(f.x, ea, ga);
+    erf_and_gauss(f.y, eb, gb);
+    const float ha = 0.5f * f.x, hb = 0.5f * f.y;
+    w[j] = pack_bf16x2(fmaf(ha, ea, ha), fmaf(hb, eb, hb));
   }
   out[i] = make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -249,8 +266,11 @@ __global__ void gelu_bwd_kernel(const uint4* __restrict__ pre, const uint4* __re
   for (int j = 0; j < 4; ++j) {
     const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
     const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[j]));
-    const float da = 0.5f * (1.0f + erff(x.x * 0.70710678118654752f)) + x.x * 0.3989422804014327f * __expf(-0.5f * x.x * x.x);
-    const float db = 0.5f * (1.0f + erff(x.y * 0.70710678118654752f)) + x.y * 0.3989422804014327f * __expf(-0.5f * x.y * x.y);
+    float ea, eb, ga, gb;
+    erf_and_gauss(x.x, ea, ga);
+    erf_and_gauss(x.y, eb, gb);
+    const float da = fmaf(0.5f, ea, 0.5f) + x.x * 0.3989422804014327f * ga;   // Phi(x) + x phi(x)
+    const float db = fmaf(0.5f, eb, 0.5f) + x.y * 0.3989422804014327f * gb;
     w[j] = pack_bf16x2(d.x * da, d.y * db);
   }
   out[i] = make_uint4(w[0], w[1], w[2], w[3]);

@@ -140,9 +140,25 @@ __global__ void __launch_bounds__(256) sq_norm_multi_kernel(const vpb_tensor_ent
   const vpb_tensor_entry e = entries[t];
   const long long base = static_cast<long long>(blockIdx.x - chunk_start[t]) * MT_CHUNK;
   float acc = 0.f;
-  for (int k = threadIdx.x; k < MT_CHUNK; k += 256) {
-    const long long i = base + k;
-    if (i < e.n) acc = fmaf(e.grad[i], e.grad[i], acc);
+  if ((reinterpret_cast<uintptr_t>(e.grad) & 15) == 0) {      // 16-byte loads; a fixed order either way
+#pragma unroll
+    for (int j = 0; j < MT_CHUNK / 1024; ++j) {
+      const long long i = base + j * 1024 + threadIdx.x * 4;
+      if (i + 3 < e.n) {
+        const float4 g = *reinterpret_cast<const float4*>(e.grad + i);
+        acc = fmaf(g.x, g.x, acc);
+        acc = fmaf(g.y, g.y, acc);
+        acc = fmaf(g.z, g.z, acc);
+        acc = fmaf(g.w, g.w, acc);
+      } else {
+        for (long long q = i; q < e.n && q < i + 4; ++q) acc = fmaf(e.grad[q], e.grad[q], acc);
+      }
+    }
+  } else {
+    for (int k = threadIdx.x; k < MT_CHUNK; k += 256) {
+      const long long i = base + k;
+      if (i < e.n) acc = fmaf(e.grad[i], e.grad[i], acc);
+    }
   }
   acc = warp_sum(acc);
   __shared__ float s[8];
@@ -172,7 +188,7 @@ __global__ void __launch_bounds__(1024) sq_norm_finish_kernel(const float* __res
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const vpb_tensor_entry* __restrict__ entries,
                                                           const int* __restrict__ chunk_start, int n, float beta1,
                                                           float beta2, float eps, const float* __restrict__ sq_norm,
-                                                          float max_norm) {
+                                                          float max_norm, int allow_vec) {
   const int t = mt_find(chunk_start, n, blockIdx.x);
   const vpb_tensor_entry e = entries[t];
   float gs = 1.0f;
@@ -183,17 +199,44 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const vpb_tensor_entry
   const float bc1 = 1.0f - powf(beta1, static_cast<float>(e.step));
   const float bc2_sqrt = sqrtf(1.0f - powf(beta2, static_cast<float>(e.step)));
   const long long base = static_cast<long long>(blockIdx.x - chunk_start[t]) * MT_CHUNK;
-  for (int k = threadIdx.x; k < MT_CHUNK; k += 256) {
-    const long long i = base + k;
-    if (i >= e.n) break;
-    const float gi = e.grad[i] * gs;
-    const float pi = e.param[i] * (1.0f - e.lr * e.weight_decay);
-    const float mi = beta1 * e.exp_avg[i] + (1.0f - beta1) * gi;
-    const float vi = beta2 * e.exp_avg_sq[i] + (1.0f - beta2) * gi * gi;
-    e.exp_avg[i] = mi;
-    e.exp_avg_sq[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    e.param[i] = pi - (e.lr / bc1) * (mi / denom);
+  const float decay = 1.0f - e.lr * e.weight_decay, step_size = e.lr / bc1;
+  // one element, exactly the arithmetic of torch's single-tensor AdamW
+  auto update = [&](float g, float& pr, float& m, float& v) {
+    const float gi = g * gs;
+    const float pi = pr * decay;
+    m = beta1 * m + (1.0f - beta1) * gi;
+    v = beta2 * v + (1.0f - beta2) * gi * gi;
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    pr = pi - step_size * (m / denom);
+  };
+  const bool vec = allow_vec && ((reinterpret_cast<uintptr_t>(e.grad) | reinterpret_cast<uintptr_t>(e.param) |
+                     reinterpret_cast<uintptr_t>(e.exp_avg) | reinterpret_cast<uintptr_t>(e.exp_avg_sq)) & 15) == 0;
+  if (vec) {      // 16-byte accesses, four independent loads per array in flight per thread
+#pragma unroll
+    for (int j = 0; j < MT_CHUNK / 1024; ++j) {
+      const long long i = base + j * 1024 + threadIdx.x * 4;
+      if (i + 3 < e.n) {
+        const float4 g = *reinterpret_cast<const float4*>(e.grad + i);
+        float4 pr = *reinterpret_cast<const float4*>(e.param + i);
+        float4 m = *reinterpret_cast<const float4*>(e.exp_avg + i);
+        float4 v = *reinterpret_cast<const float4*>(e.exp_avg_sq + i);
+        update(g.x, pr.x, m.x, v.x);
+        update(g.y, pr.y, m.y, v.y);
+        update(g.z, pr.z, m.z, v.z);
+        update(g.w, pr.w, m.w, v.w);
+        *reinterpret_cast<float4*>(e.exp_avg + i) = m;
+        *reinterpret_cast<float4*>(e.exp_avg_sq + i) = v;
+        *reinterpret_cast<float4*>(e.param + i) = pr;
+      } else {
+        for (long long q = i; q < e.n && q < i + 4; ++q) update(e.grad[q], e.param[q], e.exp_avg[q], e.exp_avg_sq[q]);
+      }
+    }
+  } else {
+    for (int k = threadIdx.x; k < MT_CHUNK; k += 256) {
+      const long long i = base + k;
+      if (i >= e.n) break;
+      update(e.grad[i], e.param[i], e.exp_avg[i], e.exp_avg_sq[i]);
+    }
   }
 }
 
@@ -206,7 +249,9 @@ int adamw_multi(const vpb_tensor_entry* entries, const int* chunk_start, int n, 
     sq_norm_finish_kernel<<<1, 1024, 0, stream>>>(sq_norm + 1, total_chunks, sq_norm);
     VPB_CHECK_CUDA(cudaGetLastError());
   }
-  adamw_multi_kernel<<<total_chunks, 256, 0, stream>>>(entries, chunk_start, n, beta1, beta2, eps, sq_norm, max_norm);
+  static const int allow_vec = getenv("VPB_ADAMW_SCALAR") == nullptr;      // A/B switch for measurements
+  adamw_multi_kernel<<<total_chunks, 256, 0, stream>>>(entries, chunk_start, n, beta1, beta2, eps, sq_norm, max_norm,
+                                                       allow_vec);
   VPB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
