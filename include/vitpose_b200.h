@@ -288,6 +288,17 @@ typedef struct vpb_tensor_entry {
 int vpb_adamw_multi(const vpb_tensor_entry* entries, const int32_t* chunk_start, int n, int total_chunks, float beta1,
                     float beta2, float eps, float* sq_norm, float max_norm, void* stream);
 
+/* bf16 operand copies of all linear layers of the training step in one launch: for every entry, w[rows, cols] =
+ * bf16(src) and wt[cols, rows] = bf16(src)^T (round to nearest even). Replaces, per layer, the implicit fp32 -> bf16
+ * weight use of nn.Linear in the reference's autograd graph (mmpose/models/backbones/vit.py:79-85, 100-121: attn.qkv /
+ * attn.proj / mlp.fc1 / mlp.fc2; patch_embed.proj :143-165 as a [D, 3*16*16] matrix). `entries` and `tile_start`
+ * ([n + 1] prefix sums of ceil(rows/32) * ceil(cols/32)) live in device memory. */
+typedef struct vpb_cast_entry {
+  const float* src; void* w; void* wt; int32_t rows; int32_t cols;
+} vpb_cast_entry;
+int vpb_cast_transpose_multi(const vpb_cast_entry* entries, const int32_t* tile_start, int n, int total_tiles,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -171,3 +171,30 @@ def test_deconv_fwd_bwd(n, h, w, cin, cout):
         ops.gemm(a[ph], b[ph], _lib.EPI_ACCUM_F32, out=dwp[ph])
     ref = pack_deconv_weight(wr.grad)          # same re-layout applied to the reference gradient (fp32 in, bf16 out)
     _close('deconv wgrad', dwp, ref, 1e-2)
+
+
+def test_cast_transpose_multi_matches_per_layer_ops():
+    """One launch for the bf16 W / W^T copies of many layers == cast_bf16 + transpose per layer, bit for bit
+    (ragged shapes exercise partial 32 x 32 tiles)."""
+    import torch.nn as nn
+    from vitpose_b200 import ops
+    from vitpose_b200.training import _LinearBank
+    torch.manual_seed(0)
+    dev = torch.device('cuda:0')
+    layers = [nn.Linear(45, 70), nn.Linear(768, 96), nn.Linear(33, 31, bias=False), nn.Conv2d(3, 40, 16, 16),
+              nn.Linear(64, 2304)]
+    layers = [l.to(dev) for l in layers]
+    bank = _LinearBank(layers)
+    for rep in range(2):                       # second pass: weights updated in place, table reused
+        lins = bank.refresh()
+        torch.cuda.synchronize()
+        for l, lin in zip(layers, lins):
+            w_ref = l.weight.detach().reshape(l.weight.shape[0], -1).to(torch.bfloat16)   # round to nearest even
+            if w_ref.numel() % 4 == 0:
+                assert torch.equal(w_ref, ops.cast_bf16(l.weight.detach().reshape(l.weight.shape[0], -1).contiguous()))
+            assert torch.equal(lin.w, w_ref)
+            assert torch.equal(lin.wt, w_ref.t().contiguous())
+            assert lin.w.data_ptr() % 16 == 0 and lin.wt.data_ptr() % 16 == 0
+        with torch.no_grad():
+            for l in layers:
+                l.weight.mul_(1.5).add_(0.01)

@@ -88,6 +88,7 @@ _SIGS = {
                                c_float, c_float, c_int, c_void_p, c_float, c_void_p]),
     'vpb_adamw_multi': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_void_p, c_float,
                                 c_void_p]),
+    'vpb_cast_transpose_multi': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'vpb_pose_pck_accuracy': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_void_p,
                                       c_void_p, c_void_p, c_void_p]),
     'vpb_oks_nms': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, ctypes.c_double,

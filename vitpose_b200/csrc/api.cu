@@ -312,6 +312,12 @@ int vpb_adamw_multi(const vpb_tensor_entry* entries, const int32_t* chunk_start,
   return adamw_multi(entries, chunk_start, n, total_chunks, beta1, beta2, eps, sq_norm, max_norm, as_stream(stream));
 }
 
+int vpb_cast_transpose_multi(const vpb_cast_entry* entries, const int32_t* tile_start, int n, int total_tiles,
+                             void* stream) {
+  cudaStream_t st = as_stream(stream);
+  return prof_run("cast_transpose_multi", st, [&] { return cast_transpose_multi(entries, tile_start, n, total_tiles, st); });
+}
+
 int vpb_pose_pck_accuracy(const float* pred, const float* gt, const float* weight, int N, int K, float norm0,
                           float norm1, float thr, float* acc, float* avg, int32_t* cnt, void* stream) {
   return pose_pck_accuracy(pred, gt, weight, N, K, norm0, norm1, thr, acc, avg, cnt, as_stream(stream));

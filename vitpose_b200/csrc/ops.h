@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 struct vpb_tensor_entry;
+struct vpb_cast_entry;
 
 namespace vpb {
 
@@ -121,6 +122,8 @@ int attention_bwd(const void* qkv, const void* out, const float* lse, const void
 
 int adamw_multi(const vpb_tensor_entry* entries, const int* chunk_start, int n, int total_chunks, float beta1,
                 float beta2, float eps, float* sq_norm, float max_norm, cudaStream_t stream);
+int cast_transpose_multi(const vpb_cast_entry* entries, const int* tile_start, int n, int total_tiles,
+                         cudaStream_t stream);
 
 int pose_pck_accuracy(const float* pred, const float* gt, const float* weight, int N, int K, float norm0, float norm1,
                       float thr, float* acc, float* avg, int* cnt, cudaStream_t stream);

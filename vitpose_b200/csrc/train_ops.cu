@@ -4,6 +4,8 @@
 //   JointsMSELoss.forward      mmpose/models/losses/mse_loss.py:24-45
 //   clip_grad_norm_(max_norm)  mmcv OptimizerHook (grad_clip=dict(max_norm=1.), ViTPose_base_coco_256x192.py:30)
 //   AdamW step                 torch.optim.AdamW as configured at ViTPose_base_coco_256x192.py:16-28
+#include <cuda_bf16.h>
+
 #include "../../include/vitpose_b200.h"
 #include "host_util.h"
 #include "ops.h"
@@ -252,6 +254,50 @@ int adamw_multi(const vpb_tensor_entry* entries, const int* chunk_start, int n, 
   static const int allow_vec = getenv("VPB_ADAMW_SCALAR") == nullptr;      // A/B switch for measurements
   adamw_multi_kernel<<<total_chunks, 256, 0, stream>>>(entries, chunk_start, n, beta1, beta2, eps, sq_norm, max_norm,
                                                        allow_vec);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- bf16 operand copies of every linear layer in ONE launch -------------------------------------------------------
+// The training step needs W (bf16, [out, in]) for the forward GEMM and W^T (bf16, [in, out]) for the input-gradient GEMM
+// of each of its ~50 linear layers, refreshed from the fp32 master parameters after every optimizer step. One cast and
+// one transpose launch per layer were launch-latency-bound (125 launches, 0.82 ms per step for 0.5 GB of traffic).
+// One CTA = one 32 x 32 tile of one matrix: coalesced fp32 read, coalesced bf16 write of W, shared-memory transpose,
+// coalesced bf16 write of W^T. Rounding = __float2bfloat16_rn, identical to cast_f32_bf16 + transpose_bf16.
+__global__ void __launch_bounds__(256) cast_transpose_multi_kernel(const vpb_cast_entry* __restrict__ entries,
+                                                                   const int* __restrict__ tile_start, int n) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int t = mt_find(tile_start, n, blockIdx.x);
+  const vpb_cast_entry e = entries[t];
+  const int local = blockIdx.x - tile_start[t];
+  const int tiles_x = (e.cols + 31) / 32;
+  const int ty = local / tiles_x, tx = local - ty * tiles_x;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;          // 32 x 8 threads
+  __nv_bfloat16* w = reinterpret_cast<__nv_bfloat16*>(e.w);
+  __nv_bfloat16* wt = reinterpret_cast<__nv_bfloat16*>(e.wt);
+  const int x = tx * 32 + lx;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int y = ty * 32 + ly + 8 * j;
+    if (x < e.cols && y < e.rows) {
+      const __nv_bfloat16 v = __float2bfloat16_rn(e.src[static_cast<size_t>(y) * e.cols + x]);
+      w[static_cast<size_t>(y) * e.cols + x] = v;
+      tile[ly + 8 * j][lx] = v;
+    }
+  }
+  __syncthreads();
+  const int xt = ty * 32 + lx;                                      // row of W = column of W^T
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int yt = tx * 32 + ly + 8 * j;                            // column of W = row of W^T
+    if (xt < e.rows && yt < e.cols) wt[static_cast<size_t>(yt) * e.rows + xt] = tile[lx][ly + 8 * j];
+  }
+}
+
+int cast_transpose_multi(const vpb_cast_entry* entries, const int* tile_start, int n, int total_tiles,
+                         cudaStream_t stream) {
+  VPB_REQUIRE(n > 0 && total_tiles > 0 && entries && tile_start, "cast_transpose_multi: empty table");
+  cast_transpose_multi_kernel<<<total_tiles, 256, 0, stream>>>(entries, tile_start, n);
   VPB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -32,10 +32,69 @@ def _wgrad(dy, x, out):
 class _Linear:
     """bf16 operand copies of one nn.Linear: W [out, in] for the forward, W^T [in, out] for the input gradient."""
 
-    def __init__(self, lin):
-        self.w = ops.cast_bf16(lin.weight.detach().reshape(lin.weight.shape[0], -1).contiguous())
-        self.wt = ops.transpose(self.w)
+    def __init__(self, lin, w=None, wt=None):
+        if w is None:
+            w = ops.cast_bf16(lin.weight.detach().reshape(lin.weight.shape[0], -1).contiguous())
+            wt = ops.transpose(w)
+        self.w, self.wt = w, wt
         self.b = lin.bias.detach() if lin.bias is not None else None
+
+
+class _LinearBank:
+    """Persistent bf16 W / W^T buffers of a list of linear layers, refreshed from the fp32 master parameters by ONE
+    vpb_cast_transpose_multi launch per training step (one cast + one transpose launch per layer were launch-bound:
+    125 launches, 0.82 ms per step). The descriptor table is rebuilt only when a parameter's storage moves. The
+    buffers are shared by successive steps: a backward pass must run before the parameters it was recorded with are
+    updated (the reference's autograd raises a version-counter error in that situation)."""
+
+    _ENTRY = None
+
+    def __init__(self, layers):
+        import numpy as np
+        if _LinearBank._ENTRY is None:
+            _LinearBank._ENTRY = np.dtype([('src', np.uint64), ('w', np.uint64), ('wt', np.uint64),
+                                           ('rows', np.int32), ('cols', np.int32)], align=True)
+            assert _LinearBank._ENTRY.itemsize == 32
+        self.layers = list(layers)
+        dev = self.layers[0].weight.device
+        shapes = [(l.weight.shape[0], l.weight.numel() // l.weight.shape[0]) for l in self.layers]
+        total = sum(r * c for r, c in shapes)
+        self.arena = torch.empty(2 * total + 16 * len(shapes), device=dev, dtype=torch.bfloat16)
+        self.views, off = [], 0
+        for r, c in shapes:
+            w = self.arena[off:off + r * c].view(r, c)
+            off += (r * c + 7) // 8 * 8                     # 16-byte aligned operands (TMA)
+            wt = self.arena[off:off + r * c].view(c, r)
+            off += (r * c + 7) // 8 * 8
+            self.views.append((w, wt))
+        self.shapes = shapes
+        self._ptrs = None
+        self._table = self._starts = None
+        self._total_tiles = 0
+
+    def _build_table(self):
+        import numpy as np
+        table = np.zeros(len(self.layers), dtype=self._ENTRY)
+        starts = np.zeros(len(self.layers) + 1, dtype=np.int32)
+        for i, (l, (w, wt), (r, c)) in enumerate(zip(self.layers, self.views, self.shapes)):
+            if not l.weight.is_contiguous() or l.weight.dtype != torch.float32:
+                raise _lib.VitposeLibError('training expects contiguous fp32 master weights')
+            table[i] = (l.weight.data_ptr(), w.data_ptr(), wt.data_ptr(), r, c)
+            starts[i + 1] = starts[i] + ((r + 31) // 32) * ((c + 31) // 32)
+        dev = self.arena.device
+        self._table = torch.from_numpy(table.view(np.uint8)).to(dev)
+        self._starts = torch.from_numpy(starts).to(dev)
+        self._total_tiles = int(starts[-1])
+
+    def refresh(self):
+        ptrs = tuple(l.weight.data_ptr() for l in self.layers)
+        if ptrs != self._ptrs:
+            self._build_table()
+            self._ptrs = ptrs
+        _lib.check(_lib.lib().vpb_cast_transpose_multi(_lib.ptr(self._table), _lib.ptr(self._starts), len(self.layers),
+                                                       self._total_tiles, _lib.stream_ptr()),
+                   'vpb_cast_transpose_multi')
+        return [_Linear(l, w, wt) for l, (w, wt) in zip(self.layers, self.views)]
 
 
 def drop_path_scales(bb, n, device):
@@ -79,13 +138,20 @@ class _NetworkFn(torch.autograd.Function):
         T, M = hp * wp, n * hp * wp
         s = {}                                           # saved activations / operands for the backward pass
         # ---- operands from the current fp32 master parameters
-        pe = _Linear(bb.patch_embed.proj)
+        bank = getattr(model, '_vpb_linear_bank', None)
+        layers = [bb.patch_embed.proj] + [m for blk in bb.blocks
+                                          for m in (blk.attn.qkv, blk.attn.proj, blk.mlp.fc1, blk.mlp.fc2)]
+        if bank is None or bank.layers != layers or bank.arena.device != img.device:
+            bank = _LinearBank(layers)
+            model._vpb_linear_bank = bank
+        lins = bank.refresh()                            # one launch: bf16 W and W^T of every linear layer
+        pe = lins[0]
         pos = bb.pos_embed.detach()
         pos_tok = (pos[0, 1:] + pos[0, :1]).contiguous()
         blocks = []
-        for blk in bb.blocks:
-            blocks.append(dict(qkv=_Linear(blk.attn.qkv), proj=_Linear(blk.attn.proj), fc1=_Linear(blk.mlp.fc1),
-                               fc2=_Linear(blk.mlp.fc2)))
+        for i in range(len(bb.blocks)):
+            q, pr, f1, f2 = lins[1 + 4 * i:5 + 4 * i]
+            blocks.append(dict(qkv=q, proj=pr, fc1=f1, fc2=f2))
         # ---- ViT (vit.py:313-332). Stochastic depth (DropPath, vit.py:48-56,132,138-139,233): block i drops the
         # whole residual branch of a crop with probability linspace(0, drop_path_rate, depth)[i]; the surviving
         # branches are divided by keep_prob. The per-crop factor goes into the residual GEMM epilogue.
