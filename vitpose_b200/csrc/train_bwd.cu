@@ -431,6 +431,12 @@ int layernorm_bwd(const float* x, const float* gamma, const void* dy, float* dx_
 //   forward  act = relu((raw - mean) * rstd * gamma + beta)              (mean / rstd from colsum_sq_accumulate)
 //   backward draw = gamma * rstd * (dy' - dbeta/R - xhat * dgamma/R),  dy' = dact * (act > 0)
 // -------------------------------------------------------------------------------------------------
+// eight consecutive per-channel fp32 parameters (c0 is a multiple of 8: 32-byte aligned) with two 16-byte loads
+__device__ __forceinline__ void load8(const float* __restrict__ p, float (&o)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+  o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
 __global__ void bn_relu_fwd_kernel(const uint4* __restrict__ raw, uint4* __restrict__ act, const float* __restrict__ mean,
                                    const float* __restrict__ rstd, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, long long n8, int C) {
@@ -439,12 +445,17 @@ __global__ void bn_relu_fwd_kernel(const uint4* __restrict__ raw, uint4* __restr
   const int c0 = static_cast<int>((i * 8) % C);
   const uint4 v = raw[i];
   uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  float pm[8], pr[8], pg[8], pb[8];             // the 8 channels' parameters: two 16-byte loads per array
+  load8(mean + c0, pm);
+  load8(rstd + c0, pr);
+  load8(gamma + c0, pg);
+  load8(beta + c0, pb);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
-    const int c = c0 + 2 * j;
-    const float a = fmaxf(fmaf((f.x - mean[c]) * rstd[c], gamma[c], beta[c]), 0.f);
-    const float b = fmaxf(fmaf((f.y - mean[c + 1]) * rstd[c + 1], gamma[c + 1], beta[c + 1]), 0.f);
+    const int c = 2 * j;
+    const float a = fmaxf(fmaf((f.x - pm[c]) * pr[c], pg[c], pb[c]), 0.f);
+    const float b = fmaxf(fmaf((f.y - pm[c + 1]) * pr[c + 1], pg[c + 1], pb[c + 1]), 0.f);
     w[j] = pack_bf16x2(a, b);
   }
   act[i] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -460,6 +471,13 @@ __global__ void bn_relu_bwd_kernel(const uint4* __restrict__ raw, const uint4* _
   const uint4 v = raw[i], g = dact[i];
   uint32_t w[4] = {v.x, v.y, v.z, v.w};
   const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+  float pm[8], pr[8], pg[8], pb[8], pdb[8], pdg[8];
+  load8(mean + c0, pm);
+  load8(rstd + c0, pr);
+  load8(gamma + c0, pg);
+  load8(beta + c0, pb);
+  load8(dbeta + c0, pdb);
+  load8(dgamma + c0, pdg);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
@@ -467,10 +485,10 @@ __global__ void bn_relu_bwd_kernel(const uint4* __restrict__ raw, const uint4* _
     float o[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      const int c = c0 + 2 * j + k;
-      const float xh = ((k ? f.y : f.x) - mean[c]) * rstd[c];
-      const float dyp = fmaf(xh, gamma[c], beta[c]) > 0.f ? (k ? d.y : d.x) : 0.f;
-      o[k] = gamma[c] * rstd[c] * (dyp - dbeta[c] * inv_rows - xh * dgamma[c] * inv_rows);
+      const int c = 2 * j + k;
+      const float xh = ((k ? f.y : f.x) - pm[c]) * pr[c];
+      const float dyp = fmaf(xh, pg[c], pb[c]) > 0.f ? (k ? d.y : d.x) : 0.f;
+      o[k] = pg[c] * pr[c] * (dyp - pdb[c] * inv_rows - xh * pdg[c] * inv_rows);
     }
     w[j] = pack_bf16x2(o[0], o[1]);
   }
@@ -479,6 +497,8 @@ __global__ void bn_relu_bwd_kernel(const uint4* __restrict__ raw, const uint4* _
 int bn_relu_fwd(const void* raw, void* act, const float* mean, const float* rstd, const float* gamma, const float* beta,
                 long long rows, int C, cudaStream_t stream) {
   VPB_REQUIRE(rows > 0 && C > 0 && C % 8 == 0, "bn_relu: C=%d must be a multiple of 8", C);
+  VPB_REQUIRE(((reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(rstd) | reinterpret_cast<uintptr_t>(gamma) |
+                reinterpret_cast<uintptr_t>(beta)) & 15) == 0, "bn_relu: per-channel arrays must be 16-byte aligned");
   const long long n8 = rows * C / 8;
   bn_relu_fwd_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const uint4*>(raw), reinterpret_cast<uint4*>(act), mean, rstd, gamma, beta, n8, C);
@@ -488,6 +508,9 @@ int bn_relu_fwd(const void* raw, void* act, const float* mean, const float* rstd
 int bn_relu_bwd(const void* raw, const void* dact, void* draw, const float* mean, const float* rstd, const float* gamma,
                 const float* beta, const float* dbeta, const float* dgamma, long long rows, int C, cudaStream_t stream) {
   VPB_REQUIRE(rows > 0 && C > 0 && C % 8 == 0, "bn_relu: C=%d must be a multiple of 8", C);
+  VPB_REQUIRE(((reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(rstd) | reinterpret_cast<uintptr_t>(gamma) |
+                reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(dbeta) |
+                reinterpret_cast<uintptr_t>(dgamma)) & 15) == 0, "bn_relu: per-channel arrays must be 16-byte aligned");
   const long long n8 = rows * C / 8;
   bn_relu_bwd_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const uint4*>(raw), reinterpret_cast<const uint4*>(dact), reinterpret_cast<uint4*>(draw), mean,
