@@ -579,73 +579,95 @@ int nchw_f32_to_rows_bf16(const float* in, void* out, int n, int K, int P, int K
 // -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int deconv_shift(int parity, int tap) { return tap == 0 ? 0 : (parity == 0 ? -1 : 1); }
 
+// IdxT = unsigned when every index fits 32 bits (always, at the sizes of the training step): 64-bit divisions by
+// run-time values cost ~100 instructions each and made these copy kernels instruction-bound.
+template <typename IdxT>
 __global__ void deconv_gather_x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int h, int w, int cin8,
-                                       long long pixels, long long total) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+                                       long long pixels_, long long total) {
+  const IdxT idx = static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (static_cast<long long>(idx) >= total) return;
+  const IdxT pixels = static_cast<IdxT>(pixels_);
   const int c8 = static_cast<int>(idx % cin8);
-  long long rest = idx / cin8;
+  IdxT rest = idx / cin8;
   const int t = static_cast<int>(rest % 4);
   rest /= 4;
-  const long long pix = rest % pixels;
+  const IdxT pix = rest % pixels;
   const int ph = static_cast<int>(rest / pixels);
   const int j = static_cast<int>(pix % w), i = static_cast<int>((pix / w) % h);
-  const long long im = pix / (static_cast<long long>(w) * h);
+  const IdxT im = pix / (static_cast<IdxT>(w) * h);
   const int ii = i + deconv_shift(ph >> 1, t >> 1), jj = j + deconv_shift(ph & 1, t & 1);
   uint4 v = make_uint4(0, 0, 0, 0);
   if (ii >= 0 && ii < h && jj >= 0 && jj < w) v = x[((im * h + ii) * w + jj) * cin8 + c8];
   out[idx] = v;
 }
+template <typename IdxT>
 __global__ void deconv_gather_dy_kernel(const uint4* __restrict__ dy, uint4* __restrict__ out, int h, int w, int cout8,
                                         long long total) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+  const IdxT idx = static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (static_cast<long long>(idx) >= total) return;
   const int c8 = static_cast<int>(idx % cout8);
-  long long rest = idx / cout8;
+  IdxT rest = idx / cout8;
   const int pt = static_cast<int>(rest % 16);
-  const long long pix = rest / 16;
+  const IdxT pix = rest / 16;
   const int ph = pt >> 2, t = pt & 3;
   const int j = static_cast<int>(pix % w), i = static_cast<int>((pix / w) % h);
-  const long long im = pix / (static_cast<long long>(w) * h);
+  const IdxT im = pix / (static_cast<IdxT>(w) * h);
   const int ii = i - deconv_shift(ph >> 1, t >> 1), jj = j - deconv_shift(ph & 1, t & 1);
   uint4 v = make_uint4(0, 0, 0, 0);
   if (ii >= 0 && ii < h && jj >= 0 && jj < w)
     v = dy[((im * 2 * h + 2 * ii + (ph >> 1)) * 2 * w + 2 * jj + (ph & 1)) * cout8 + c8];
   out[idx] = v;
 }
+template <typename IdxT>
 __global__ void deconv_phase_dy_kernel(const uint4* __restrict__ dy, uint4* __restrict__ out, int h, int w, int cout8,
-                                       long long pixels, long long total) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+                                       long long pixels_, long long total) {
+  const IdxT idx = static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (static_cast<long long>(idx) >= total) return;
+  const IdxT pixels = static_cast<IdxT>(pixels_);
   const int c8 = static_cast<int>(idx % cout8);
-  long long rest = idx / cout8;
-  const long long pix = rest % pixels;
+  IdxT rest = idx / cout8;
+  const IdxT pix = rest % pixels;
   const int ph = static_cast<int>(rest / pixels);
   const int j = static_cast<int>(pix % w), i = static_cast<int>((pix / w) % h);
-  const long long im = pix / (static_cast<long long>(w) * h);
+  const IdxT im = pix / (static_cast<IdxT>(w) * h);
   out[idx] = dy[((im * 2 * h + 2 * i + (ph >> 1)) * 2 * w + 2 * j + (ph & 1)) * cout8 + c8];
 }
 int deconv_gather_x(const void* x, void* out, int n, int h, int w, int cin, cudaStream_t stream) {
   VPB_REQUIRE(n > 0 && h > 0 && w > 0 && cin % 8 == 0, "deconv_gather_x: bad shape");
   const long long pixels = static_cast<long long>(n) * h * w, total = 4 * pixels * 4 * (cin / 8);
-  deconv_gather_x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), h, w, cin / 8, pixels, total);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (total + 256 < (1ll << 31))           // the source index is < total / 16, the padded grid stays below 2^32
+    deconv_gather_x_kernel<unsigned><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
+                                                               reinterpret_cast<uint4*>(out), h, w, cin / 8, pixels, total);
+  else
+    deconv_gather_x_kernel<long long><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
+                                                                reinterpret_cast<uint4*>(out), h, w, cin / 8, pixels, total);
   VPB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int deconv_gather_dy(const void* dy, void* out, int n, int h, int w, int cout, cudaStream_t stream) {
   VPB_REQUIRE(n > 0 && h > 0 && w > 0 && cout % 8 == 0, "deconv_gather_dy: bad shape");
   const long long total = static_cast<long long>(n) * h * w * 16 * (cout / 8);
-  deconv_gather_dy_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(out), h, w, cout / 8, total);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (total + 256 < (1ll << 31))           // the source index is < total / 4
+    deconv_gather_dy_kernel<unsigned><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(dy),
+                                                                reinterpret_cast<uint4*>(out), h, w, cout / 8, total);
+  else
+    deconv_gather_dy_kernel<long long><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(dy),
+                                                                 reinterpret_cast<uint4*>(out), h, w, cout / 8, total);
   VPB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int deconv_phase_dy(const void* dy, void* out, int n, int h, int w, int cout, cudaStream_t stream) {
   VPB_REQUIRE(n > 0 && h > 0 && w > 0 && cout % 8 == 0, "deconv_phase_dy: bad shape");
   const long long pixels = static_cast<long long>(n) * h * w, total = 4 * pixels * (cout / 8);
-  deconv_phase_dy_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(out), h, w, cout / 8, pixels, total);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (total + 256 < (1ll << 31))           // source index = a permutation of [0, total)
+    deconv_phase_dy_kernel<unsigned><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(dy),
+                                                               reinterpret_cast<uint4*>(out), h, w, cout / 8, pixels, total);
+  else
+    deconv_phase_dy_kernel<long long><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(dy),
+                                                                reinterpret_cast<uint4*>(out), h, w, cout / 8, pixels, total);
   VPB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
