@@ -235,13 +235,16 @@ int tokens_to_nchw_f32(const void* tokens, float* out, int n, int T, int D, cuda
 // src = (dst + 0.5) / f - 0.5 clamped at 0 (PyTorch's area_pixel_compute_source_index), neighbours clamped
 // to the last row/column. One thread = 8 channels of one output pixel (16-byte accesses).
 // -------------------------------------------------------------------------------------------------
+// IdxT = unsigned when the output fits 32-bit indexing (64-bit divisions by run-time values cost ~100 instructions each
+// and outweighed the interpolation itself).
+template <typename IdxT>
 __global__ void relu_upsample_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int h,
                                      int w, int C, int f, long long total_vec) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total_vec) return;
+  const IdxT idx = static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (static_cast<long long>(idx) >= total_vec) return;
   const int cv = C / 8;
   const int c8 = static_cast<int>(idx % cv);
-  long long pix = idx / cv;
+  IdxT pix = idx / cv;
   const int W2 = w * f, H2 = h * f;
   const int ox = static_cast<int>(pix % W2);
   pix /= W2;
@@ -280,8 +283,13 @@ int relu_upsample_bilinear_nhwc(const void* in, void* out, int n, int h, int w, 
   VPB_REQUIRE(n > 0 && C % 8 == 0 && factor >= 1, "relu_upsample: bad shape n=%d C=%d factor=%d", n, C, factor);
   const long long total = static_cast<long long>(n) * h * factor * w * factor * (C / 8);
   const int threads = 256;
-  relu_upsample_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), h, w, C, factor, total);
+  const unsigned grid = static_cast<unsigned>((total + threads - 1) / threads);
+  if (total + threads < (1ll << 31))
+    relu_upsample_kernel<unsigned><<<grid, threads, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), h, w, C, factor, total);
+  else
+    relu_upsample_kernel<long long><<<grid, threads, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), h, w, C, factor, total);
   VPB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
