@@ -18,8 +18,42 @@ import types
 REF_ROOT = os.environ.get('VITPOSE_REFERENCE_ROOT', '/root/reference')
 
 
+# the reference files on the hot path (everything load_reference() executes), relative to the reference root
+REFERENCE_FILES = (
+    'mmpose/core/post_processing/post_transforms.py',
+    'mmpose/core/evaluation/top_down_eval.py',
+    'mmpose/models/builder.py',
+    'mmpose/models/utils/ops.py',
+    'mmpose/models/losses/mse_loss.py',
+    'mmpose/models/backbones/base_backbone.py',
+    'mmpose/models/backbones/vit.py',
+    'mmpose/models/heads/topdown_heatmap_base_head.py',
+    'mmpose/models/heads/topdown_heatmap_simple_head.py',
+    'mmpose/models/detectors/base.py',
+    'mmpose/models/detectors/top_down.py',
+)
+
+
 def available():
     return os.path.isfile(os.path.join(REF_ROOT, 'mmpose/models/backbones/vit.py'))
+
+
+def stage_reference(dst, src='/root/reference'):
+    """Copies the UNMODIFIED reference files of the hot path into ``dst`` (the git-ignored ``baseline/_ref``), so
+    that ``bench.py --impl reference`` can run the real reference on a GPU box, where /root/reference does not
+    exist. Called by ``__graft_entry__.build()`` in the authoring container. Returns the number of files copied."""
+    import shutil
+    n = 0
+    for rel in REFERENCE_FILES:
+        s = os.path.join(src, rel)
+        if not os.path.isfile(s):
+            return 0
+        d = os.path.join(dst, rel)
+        os.makedirs(os.path.dirname(d), exist_ok=True)
+        if not os.path.isfile(d) or os.path.getmtime(d) < os.path.getmtime(s):
+            shutil.copy2(s, d)
+        n += 1
+    return n
 
 
 class _Registry:

@@ -521,9 +521,16 @@ __host__ __device__ constexpr int pp_v_depth(int hd) { return hd > 64 ? 2 : 3; }
 __host__ __device__ constexpr int pp_stage_pitch(int hd) { return hd * 2 + 16; }
 __host__ __device__ constexpr int pp_stage_bytes(int hd) { return 8 * 32 * pp_stage_pitch(hd); }
 constexpr int PP_THREADS = 64 + 256;
+// EPIW: a third warpgroup (warps 10-13) drains O_g (tcgen05.ld, 1 / row sum, bf16, line-sized stores) for BOTH softmax
+// groups, so a softmax group goes from P(i) straight to the scores of unit i + 2: the per-group chain
+// softmax -> P.V -> epilogue (6900 cycles per unit, of which 3450 softmax) shrinks to softmax -> S(i+2).
+// EPIW layout: four warpgroups of 128 threads so that setmaxnreg can move registers between the roles:
+// warps 0-3 TMA / MMA (+ two idle warps), 4-7 and 8-11 the softmax groups, 12-15 the epilogue.
+__host__ __device__ constexpr int pp_threads(bool epiw) { return epiw ? 512 : PP_THREADS; }
+__host__ __device__ constexpr int pp_first_softmax_warp(bool epiw) { return epiw ? 4 : 2; }
 
-template <int HD, int T_>
-__global__ void __launch_bounds__(PP_THREADS, 1)
+template <int HD, int T_, bool EPIW>
+__global__ void __launch_bounds__(pp_threads(EPIW), 1)
 attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                           const __grid_constant__ CUtensorMap tm_qb, const __grid_constant__ CUtensorMap tm_kvb,
                           const AttnParams p, const int num_units) {
@@ -545,6 +552,7 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
   __shared__ uint64_t qk_full[PP_QK_DEPTH], qk_free[PP_QK_DEPTH], v_full[PP_V_DEPTH], v_free[PP_V_DEPTH];
   __shared__ uint64_t s_full[2], p_full[2], o_full[2], o_free[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_inv[2][2][EPIW ? ATT_BM : 1];   // EPIW: 1 / row sum of unit i at [i & 1][(i >> 1) & 1][row]
 
   const int q_tiles = (T + ATT_BM - 1) / ATT_BM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -593,24 +601,36 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  // cycle accounting (CTA 0 only, one thread per role), enabled with VPB_ATT_DEBUG & 32; printed by & 64
+  // cycle accounting (CTA 0 only, one thread per role), enabled with VPB_ATT_DEBUG & 32; printed by & 64.
+  // The counters are declared inside each role (PP_TIMING_STATE) so that they are not live across the
+  // setmaxnreg-limited branches of the other roles.
   const bool timing = p.dbg_buf != nullptr && blockIdx.x == 0;
-  long long t_acc[6] = {0, 0, 0, 0, 0, 0};
-  auto timed_wait = [&](uint64_t* bar, uint32_t parity, int slot) {
-    if (timing) {
-      const long long t0 = clock64();
-      mbar_wait(bar, parity);
-      t_acc[slot] += clock64() - t0;
-    } else {
-      mbar_wait(bar, parity);
-    }
-  };
-  const long long t_start = clock64();
+#define PP_TIMING_STATE                                                \
+  long long t_acc[6] = {0, 0, 0, 0, 0, 0};                             \
+  const long long t_start = timing ? clock64() : 0;                    \
+  (void)t_start;                                                       \
+  auto timed_wait = [&](uint64_t* bar, uint32_t parity, int slot) {    \
+    if (timing) {                                                      \
+      const long long t0 = clock64();                                  \
+      mbar_wait(bar, parity);                                          \
+      t_acc[slot] += clock64() - t0;                                   \
+    } else {                                                           \
+      mbar_wait(bar, parity);                                          \
+    }                                                                  \
+  }
   auto s_col = [&](int g) { return static_cast<uint32_t>(g * T); };
   auto o_col = [&](int g) { return static_cast<uint32_t>(O_ALIAS ? g * T + T / 2 : 2 * T + g * HD); };
 
+  constexpr int W0 = pp_first_softmax_warp(EPIW);
+  // EPIW: 512 threads start with 128 registers each; the softmax threads (two 32-column chunks of scores in flight
+  // plus the packed probabilities) get what the producer / issuer / idle warps and the epilogue do not need. Each
+  // setmaxnreg is the first instruction of its warpgroup's branch, so that the register allocation of the branch
+  // follows it.
+  if (warp < (EPIW ? 4 : 2)) {
+  if constexpr (EPIW) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     if (lane == 0) {
+      PP_TIMING_STATE;
       for (int i = 0; i < n_local; ++i) {
         const int unit = blockIdx.x + i * gridDim.x;
         const int qt = unit_qt(unit, i);
@@ -637,6 +657,7 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      PP_TIMING_STATE;
       constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, T);
       constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BM, WIDE ? 64 : HD, 0, 1);
       constexpr uint32_t idesc_o16 = umma_idesc_bf16(ATT_BM, 16, 0, 1);
@@ -683,8 +704,69 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       }
       if (timing) { for (int k = 0; k < 4; ++k) p.dbg_buf[2 + k] = t_acc[k]; }
     }
+  }
+  } else if (EPIW && warp >= 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    // ---- epilogue warpgroup: O_g of every unit (both groups, in unit order) -> out. o_free[g] is armed for these 128
+    // threads; the 1 / row sum of unit i was left in s_inv by the softmax thread of the same row before it arrived on
+    // p_full (arrive -> MMA thread's wait -> tcgen05.commit -> o_full orders the write before the read below), and is
+    // overwritten by softmax(i + 4) only after P.V(i + 2) was issued, i.e. after this thread's arrive on o_free.
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    uint8_t* const stage = s_stage + (warp - 12) * 32 * PITCH;
+    PP_TIMING_STATE;
+    for (int i = 0; i < n_local; ++i) {
+      const int g = i & 1;
+      const int unit = blockIdx.x + i * gridDim.x;
+      const int qt = unit_qt(unit, i);
+      const int head = (unit / q_tiles) % p.heads;
+      const int crop = (unit / q_tiles) / p.heads;
+      const Placement pl = unit_rows(qt, i);
+      const bool warp_live = quad * 32 < pl.r_hi && quad * 32 + 32 > pl.r_lo && !(p.dbg & 1);
+      timed_wait(&o_full[g], (i >> 1) & 1, 2);
+      tc_fence_after();
+      if (warp_live) {
+        uint32_t o[HD];
+#pragma unroll
+        for (int c = 0; c < HD; c += 16)
+          tmem_ld_32x32b_x16(lane_base + o_col(g) + c, *reinterpret_cast<uint32_t(*)[16]>(&o[c]));
+        const float inv = s_inv[g][(i >> 1) & 1][r];
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&o_free[g]);
+#pragma unroll
+        for (int c = 0; c < HD; c += 8) {
+          uint32_t w4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            w4[j] = pack_bf16x2(__uint_as_float(o[c + 2 * j]) * inv, __uint_as_float(o[c + 2 * j + 1]) * inv);
+          *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 2) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+        __syncwarp();
+        if (!(p.dbg & 8)) {
+          __nv_bfloat16* base = p.out + (static_cast<size_t>(crop) * T + pl.q0 + quad * 32) * p.ldo + head * HD;
+          constexpr int CH = HD / 8;
+#pragma unroll
+          for (int e = lane; e < 32 * CH; e += 32) {
+            const int row = e / CH, ch = e - row * CH;
+            const int rr = quad * 32 + row;
+            if (rr >= pl.r_lo && rr < pl.r_hi)
+              *reinterpret_cast<uint4*>(base + static_cast<size_t>(row) * p.ldo + ch * 8) =
+                  *reinterpret_cast<const uint4*>(stage + row * PITCH + ch * 16);
+          }
+        }
+        __syncwarp();                         // the staging block is rewritten by the next unit
+      } else {
+        tc_fence_before();
+        mbar_arrive(&o_free[g]);
+      }
+    }
+    if (timing && threadIdx.x == 384) { p.dbg_buf[8] = t_acc[2]; }
   } else {
-    const int g = (warp - 2) >> 2;                  // softmax group: units i = g, g + 2, ...
+    if constexpr (EPIW) asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+    PP_TIMING_STATE;
+    const int g = (warp - W0) >> 2;                 // softmax group: units i = g, g + 2, ...
     const int quad = warp & 3;                      // TMEM lane quarter this warp may access
     const int r = quad * 32 + lane;                 // query row inside the tile
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
@@ -693,7 +775,7 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
 
     // The staged output block of a unit is written to global memory one unit later, while this group waits for the
     // next P.V to complete (it has nothing else to do then), instead of at the end of its own epilogue.
-    uint8_t* const stage = s_stage + (warp - 2) * 32 * PITCH;
+    uint8_t* const stage = s_stage + (warp - W0) * 32 * PITCH;
     __nv_bfloat16* pend_base = nullptr;       // null: nothing pending
     int pend_lo = 0, pend_hi = 0;
     auto flush_pending = [&]() {
@@ -734,6 +816,8 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
         uint32_t va[32], vb[32];
         // pass 1: row maximum
         float mx = -INFINITY;
+        if (p.dbg & 1024) mx = 0.f;      // timing experiment (results invalid): no row-max pass over the scores
+        else {
         tmem_ld_32x32b_x32(S, va);
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -748,6 +832,7 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
             m1 = fmaxf(m1, fmaxf(__uint_as_float(cur[j + 2]), __uint_as_float(cur[j + 3])));
           }
           mx = fmaxf(mx, fmaxf(m0, m1));
+        }
         }
         // pass 2: p = exp2(s * scale*log2e - max'), bf16 pairs written back over columns [16c, 16c + 16) — always
         // behind the columns still to be read
@@ -778,12 +863,17 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
         tmem_st_wait();
         const float sum = (sum_a.x + sum_b.x) + (sum_a.y + sum_b.y);
         inv = 1.0f / sum;
+        if constexpr (EPIW) s_inv[g][ph][r] = inv;
         if (p.lse != nullptr && row_live)
           p.lse[(static_cast<size_t>(crop) * p.heads + head) * T + token] = fmaf(mx, p.scale_log2e, log2f(sum));
       }
       tc_fence_before();            // our tcgen05.ld / st of S_g are complete and ordered before the arrive
       mbar_arrive(&p_full[g]);
-      if (tlive) t_acc[1] += clock64() - t_mark;
+      if (tlive) { t_acc[1] += clock64() - t_mark; t_acc[5] += 1; }
+      if constexpr (EPIW) {         // the epilogue warpgroup takes O_g from here
+        if (timing) t_body += clock64() - t_top;
+        continue;
+      }
       flush_pending();              // previous unit's output rows, while P.V of this one runs
 
       // epilogue: O_g / row sum -> bf16, one whole output row (HD * 2 bytes, contiguous) per thread
@@ -816,12 +906,13 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
         tc_fence_before();
         mbar_arrive(&o_free[g]);
       }
-      if (tlive) { t_acc[3] += clock64() - t_mark; t_acc[5] += 1; }
+      if (tlive) { t_acc[3] += clock64() - t_mark; }
       if (timing) t_body += clock64() - t_top;
     }
     flush_pending();
-    if (timing && threadIdx.x == 128) {
-      for (int k = 0; k < 4; ++k) p.dbg_buf[6 + k] = t_acc[k];
+    if (timing && threadIdx.x == 32 * W0 + 64) {
+      for (int k = 0; k < 4; ++k)
+        if (!(EPIW && k == 2)) p.dbg_buf[6 + k] = t_acc[k];
       p.dbg_buf[10] = clock64() - t_start;
       p.dbg_buf[11] = n_local;
       p.dbg_buf[12] = t_acc[4];
@@ -835,13 +926,15 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-template <int HD, int T_>
+#undef PP_TIMING_STATE
+
+template <int HD, int T_, bool EPIW>
 static int launch_attention_pingpong(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& tqb,
                                      const CUtensorMap& tkvb, const AttnParams& p, int max_ctas, cudaStream_t stream) {
   constexpr int smem = PP_QK_DEPTH * (ATT_BM + T_) * att2_row_bytes(HD) + pp_v_depth(HD) * T_ * att2_row_bytes(HD) +
                        pp_stage_bytes(HD) + 1024;
   static_assert(smem <= 227 * 1024 - 6 * 1024, "ping-pong attention tiles do not fit shared memory");
-  auto kern = attention_pingpong_kernel<HD, T_>;
+  auto kern = attention_pingpong_kernel<HD, T_, EPIW>;
   static bool configured = false;
   if (!configured) {
     VPB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -851,7 +944,7 @@ static int launch_attention_pingpong(const CUtensorMap& tq, const CUtensorMap& t
   const int units = p.n * p.heads * q_tiles;
   int grid = max_ctas > 0 ? max_ctas : sm_count();
   if (grid > units) grid = units;
-  kern<<<grid, PP_THREADS, smem, stream>>>(tq, tkv, tqb, tkvb, p, units);
+  kern<<<grid, pp_threads(EPIW), smem, stream>>>(tq, tkv, tqb, tkvb, p, units);
   VPB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -938,8 +1031,16 @@ int attention_fwd(const void* qkv, void* out, int n, int T, int heads, int hd, f
   if (max_ctas >= 0) {   // max_ctas < 0 selects the per-unit kernel (kept for head_dim > 64 and for A/B tests)
     int rc = 1;
     const bool pingpong = !(p.dbg & 256);     // VPB_ATT_DEBUG & 256: the single-group kernel (P through smem), for A/B
-    if (pingpong && hd == 32 && T == 192) rc = launch_attention_pingpong<32, 192>(tq, tkv, tq, tkv, p, max_ctas, stream);
-    if (pingpong && hd == 64 && T == 192) rc = launch_attention_pingpong<64, 192>(tq, tkv, tq, tkv, p, max_ctas, stream);
+    // VPB_ATT_DEBUG & 512: a separate epilogue warpgroup drains O_g (A/B; measured slower for head_dim 64 / 80:
+    // 150.4 vs 139.0 us at 512 image passes — the kernel is bound by the two tcgen05.ld passes over the scores,
+    // not by the softmax -> P.V -> epilogue chain)
+    const bool epiw = (p.dbg & 512) != 0;
+    if (pingpong && hd == 32 && T == 192)
+      rc = epiw ? launch_attention_pingpong<32, 192, true>(tq, tkv, tq, tkv, p, max_ctas, stream)
+                : launch_attention_pingpong<32, 192, false>(tq, tkv, tq, tkv, p, max_ctas, stream);
+    if (pingpong && hd == 64 && T == 192)
+      rc = epiw ? launch_attention_pingpong<64, 192, true>(tq, tkv, tq, tkv, p, max_ctas, stream)
+                : launch_attention_pingpong<64, 192, false>(tq, tkv, tq, tkv, p, max_ctas, stream);
     // head_dim 80: O_g aliases the consumed half of S_g (2T + 2*80 > 512 TMEM columns), so S(i+2) is issued after the
     // epilogue of unit i has loaded O_g into registers; still 65.6 us vs 85.8 us for the single-group kernel at 128
     // image passes once the output stores were deferred
@@ -948,7 +1049,8 @@ int attention_fwd(const void* qkv, void* out, int n, int T, int heads, int hd, f
       uint32_t box_qb[3] = {16, ATT_BM, 1}, box_kvb[3] = {16, (uint32_t)T, 1};
       if (make_tma_desc(&tqb, TMA_BF16, qkv, 3, dims, strides, box_qb, TMA_SWIZZLE_32B)) return -1;
       if (make_tma_desc(&tkvb, TMA_BF16, qkv, 3, dims, strides, box_kvb, TMA_SWIZZLE_32B)) return -1;
-      rc = launch_attention_pingpong<80, 192>(tq, tkv, tqb, tkvb, p, max_ctas, stream);
+      rc = epiw ? launch_attention_pingpong<80, 192, true>(tq, tkv, tqb, tkvb, p, max_ctas, stream)
+                : launch_attention_pingpong<80, 192, false>(tq, tkv, tqb, tkvb, p, max_ctas, stream);
     }
     if (rc <= 0) return rc;
     if (hd == 32 && T == 192) rc = launch_attention_persistent<32, 192, 2>(tq, tkv, tq, tkv, p, max_ctas, stream);

@@ -47,6 +47,16 @@ static int launch_gemm_inst(const GemmMaps& maps, const GemmParams& p, int max_c
   return 0;
 }
 
+// Pipeline-depth switches of the residual GEMMs (GEMM_FLAG_*), VPB_GEMM_FLAGS=<int> overrides the default (A/B runs).
+static int gemm_flags() {
+  static int flags = -1;
+  if (flags < 0) {
+    const char* e = getenv("VPB_GEMM_FLAGS");
+    flags = e ? atoi(e) : GEMM_DEFAULT_FLAGS;
+  }
+  return flags;
+}
+
 // CTA pairs pay off on the large transformer GEMMs (full 256-wide N tiles, many tiles); everything else stays 1-CTA.
 // VPB_GEMM_CG=1 forces single-CTA tiles (A/B experiments).
 int gemm_pick_cg(int M, int bn, int epilogue, int K) {
@@ -177,6 +187,7 @@ int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, c
   GemmMaps maps;
   if (make_gemm_maps(&maps, A, B, M, N, K, K, K, bn, epilogue, out, ldo, aux, cg, period)) return -1;
   GemmParams p{M, N, K, bias, out, ldo, aux, period, 1, nullptr, 1, nullptr, nullptr, nullptr, 0, 0u, 0.0f};
+  p.flags = gemm_flags();
   if (epilogue == EPI_ACCUM_F32) {
     VPB_REQUIRE(bias == nullptr && ldo % 4 == 0, "gemm: the accumulating epilogue takes no bias and needs ldo %% 4 == 0");
     // about two waves of CTAs, at least 8 K blocks (512 rows of the contraction) per split, every split non-empty
@@ -261,6 +272,7 @@ int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue
   GemmParams p{M, N, K, bias, out, N, aux, period, 1, row_scale, rows_per_scale > 0 ? rows_per_scale : 1, gamma, beta,
                reinterpret_cast<unsigned long long*>(scratch),
                ln_region_words(M, N), epoch, eps};
+  p.flags = gemm_flags();
   return launch_gemm(maps, p, bn, epi, cg, max_ctas, stream);
 }
 

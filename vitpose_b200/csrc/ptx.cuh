@@ -85,6 +85,14 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, ui
       "r"(c2), "r"(c3)
       : "memory");
 }
+// fire-and-forget prefetch of a 2-D box into L2 (no shared memory, no barrier): deepens a TMA pipeline beyond what
+// fits in shared memory — the later cp.async.bulk.tensor of the same box is then an L2 hit
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 // 1-D bulk copy global -> shared (no tensor map): size and both addresses multiples of 16 bytes
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

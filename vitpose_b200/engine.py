@@ -186,18 +186,37 @@ class VitPoseEngine:
 
     @property
     def heatmap_size(self):
-        return self.desc.img_h // 4, self.desc.img_w // 4
+        """(H, W) of the maps vpb_vitpose_forward writes: the 16x16 token grid times 2 per transposed convolution
+        (classic decoder, simple_head.py:306-337) or times ``upsample`` (simple decoder, simple_head.py:269-287)."""
+        hp, wp = self.tokens_hw
+        d = self.desc
+        f = (1 << d.num_deconv) if d.num_deconv > 0 else (d.upsample if d.upsample > 0 else 1)
+        return hp * f, wp * f
 
     @property
     def tokens_hw(self):
         return self.desc.img_h // 16, self.desc.img_w // 16
 
     # ---- network -----------------------------------------------------------------------------------
+    def _check_crops(self, img):
+        """The kernels index the crop buffer from desc.img_h / img_w: a mis-sized batch must be an error, not a read
+        past the buffer."""
+        if img.dtype != torch.float32 or not img.is_cuda:
+            raise _lib.VitposeLibError('img must be a float32 CUDA tensor')
+        if img.dim() != 4 or tuple(img.shape[1:]) != (3, self.desc.img_h, self.desc.img_w):
+            raise ValueError(f'expected crops of shape [n,3,{self.desc.img_h},{self.desc.img_w}], got {tuple(img.shape)}')
+
     def forward_into(self, img, flip, out_main, out_flip):
         """Like forward_heatmaps, but writes the main-pass maps into ``out_main`` [n,K,h,w] and the raw
         flipped-pass maps into ``out_flip`` [n,K,h,w] (slices of larger, contiguous batch buffers)."""
+        self._check_crops(img)
         img = img.contiguous()
         n = img.shape[0]
+        H4, W4 = self.heatmap_size
+        want = (n, self.desc.num_keypoints, H4, W4)
+        for t in (out_main, out_flip) if flip else (out_main,):
+            if tuple(t.shape) != want or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f'heatmap buffer must be contiguous float32 {want}, got {tuple(t.shape)} {t.dtype}')
         images = 2 * n if flip else n
         ws_ptr, ws_bytes = self._workspace(images)
         check(lib().vpb_vitpose_forward(ctypes.byref(self.desc), ctypes.byref(self.weights.struct), ptr(img), n,
@@ -206,12 +225,9 @@ class VitPoseEngine:
 
     def forward_heatmaps(self, img, flip=False, want_features=False, want_heatmaps=True):
         """img fp32 CUDA [n,3,H,W] -> raw heatmaps fp32 [(2n|n), K, H/4, W/4] (+ bf16 token features)."""
-        if img.dtype != torch.float32 or not img.is_cuda:
-            raise _lib.VitposeLibError('img must be a float32 CUDA tensor')
+        self._check_crops(img)
         img = img.contiguous()
         n = img.shape[0]
-        if tuple(img.shape[1:]) != (3, self.desc.img_h, self.desc.img_w):
-            raise ValueError(f'expected crops of shape [n,3,{self.desc.img_h},{self.desc.img_w}], got {tuple(img.shape)}')
         images = 2 * n if flip else n
         ws_ptr, ws_bytes = self._workspace(images)
         H4, W4 = self.heatmap_size
