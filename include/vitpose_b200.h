@@ -65,7 +65,7 @@ typedef struct vpb_block_weights {
   const void* fc2_w;  const float* fc2_b;    /* [D, 4D], [D]   (mlp.fc2)   */
 } vpb_block_weights;
 
-/* Repacked weights (built once by the host side, vitpose_b200/weights.py):
+/* Repacked weights (built once by the host side, vitpose_b200/engine.py: PackedWeights):
  *  patch_w  bf16 [D, 768]      = patch_embed.proj.weight.reshape(D, 3*16*16)
  *  pos      fp32 [T, D]        = pos_embed[0, 1:] + pos_embed[0, :1]           (vit.py:320)
  *  deconv_w bf16 [4][Cout][4*Cin]: per output parity (py,px) the 2x2 taps of the k4/s2/p1 transposed conv,
@@ -231,7 +231,9 @@ int vpb_deconv_phase_dy(const void* dy, void* out, int n, int h, int w, int cout
  * [group_start[g], group_start[g+1]).
  *   kpts        fp32 [P,K,3] (x, y, score);  areas fp64 [P];  box_scores fp64 [P]
  *   var         fp64 [K] = (2 * sigma_k)^2
- *   rescore     != 0: pose score = mean(joint scores > vis_thr) * box score; else box_scores are the pose scores
+ *   rescore     bit 0: pose score = mean(joint scores > vis_thr) * box score; else box_scores are the pose scores.
+ *               bit 1: the areas are float32 values (TopDownCocoDataset.evaluate passes boxes[:, 4]): their pair sum
+ *               in the OKS denominator is rounded to float32 as NumPy does for float32 operands
  *   use_vis     != 0: only joints whose DETECTION score exceeds vis_thr enter the OKS (nms.py:80-82)
  *   soft        0: oks_nms (keep while OKS <= thr); 1: soft_oks_nms (Gaussian rescoring, at most max_dets per image)
  *   scores_out  fp64 [P] scores used;  keep int32 [P]: kept row indices of group g, in selection order, starting at
@@ -253,7 +255,9 @@ int vpb_warp_affine_normalize(const unsigned char* const* src_ptrs, const int32_
                               int n, int out_h, int out_w, const float* mean3, const float* std3, float* out,
                               void* stream);
 
-/* ---- training-step operators (the network backward is not part of this library yet) ----
+/* ---- training-step operators: loss, gradient norm, AdamW. The backward-pass operators of
+ * the network itself (attention / LayerNorm / GELU / BatchNorm backward, weight-gradient GEMMs) follow below;
+ * vitpose_b200/training.py sequences them into one autograd node. ----
  * JointsMSELoss.forward (mmpose/models/losses/mse_loss.py:24-45): loss[0] = loss_weight / K * sum_k mean_{n,hw}
  * ((output - target) * target_weight[n,k])^2; target_weight may be NULL (use_target_weight=False);
  * grad_output (optional, same shape as output) receives d loss / d output. */

@@ -142,3 +142,9 @@ def test_drop_path_random_masks_follow_the_schedule():
             assert abs(float((s == 0).float().mean()) - p) < 0.03
     bb.training = False
     assert all(pair == (None, None) for pair in drop_path_scales(bb, 8, torch.device('cuda:0')))
+    # frozen blocks are in eval mode (vit.py:249-259): their DropPath is the identity
+    import vitpose_b200 as V
+    vit = V.ViT(img_size=(256, 192), embed_dim=64, depth=4, num_heads=2, qkv_bias=True, drop_path_rate=0.3,
+                frozen_stages=2).train()
+    sc = drop_path_scales(vit, 16, torch.device('cuda:0'))
+    assert sc[1] == (None, None) and sc[2] == (None, None) and sc[3][0] is not None

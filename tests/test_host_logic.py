@@ -218,3 +218,52 @@ def test_mae_checkpoint_adaptation(tmp_path):
     bic = adapt_state_dict(sd, bb, 'bicubic')['patch_embed.proj.weight']
     assert bic.shape[2:] == (16, 16) and torch.allclose(
         bic, F.interpolate(sd['patch_embed.proj.weight'], size=(16, 16), mode='bicubic', align_corners=False))
+
+
+def _frozen_names(backbone):
+    return sorted(n for n, p in backbone.named_parameters() if not p.requires_grad)
+
+
+def test_freeze_stages_selection():
+    """vit.py:249-284: frozen_stages / freeze_attn / freeze_ffn set requires_grad=False on the same tensors as the
+    reference (including its loop from blocks[1]), survive .train(), and put frozen blocks in eval mode."""
+    kw = dict(img_size=(256, 192), embed_dim=64, depth=4, num_heads=2, qkv_bias=True)
+    bb = V.ViT(frozen_stages=2, **kw)
+    fr = _frozen_names(bb)
+    assert 'patch_embed.proj.weight' in fr and 'patch_embed.proj.bias' in fr
+    assert all(n.startswith(('patch_embed.', 'blocks.1.', 'blocks.2.')) for n in fr)
+    assert any(n.startswith('blocks.1.') for n in fr) and any(n.startswith('blocks.2.') for n in fr)
+    assert not any(n.startswith('blocks.0.') for n in fr)          # the reference's range(1, frozen_stages + 1)
+    bb.train()
+    assert _frozen_names(bb) == fr
+    assert not bb.blocks[1].training and not bb.blocks[2].training and bb.blocks[0].training and bb.blocks[3].training
+    bb = V.ViT(freeze_attn=True, **kw).train()
+    fr = _frozen_names(bb)
+    assert fr and all('.attn.' in n or '.norm1.' in n for n in fr) and len(fr) == 4 * 6
+    bb = V.ViT(freeze_ffn=True, **kw).train()
+    fr = _frozen_names(bb)
+    assert 'pos_embed' in fr and 'patch_embed.proj.weight' in fr
+    assert all(n == 'pos_embed' or n.startswith('patch_embed.') or '.mlp.' in n or '.norm2.' in n for n in fr)
+    assert _frozen_names(V.ViT(**kw)) == []
+    # the layer-decay constructor leaves frozen tensors out, as the reference does (constructor :35-36)
+    from vitpose_b200.optim import layer_decay_param_groups
+    cfg = configs.tiny_model_cfg(5)
+    cfg['backbone'].update(frozen_stages=1)
+    model = V.build_posenet(cfg)
+    names = [n for g in layer_decay_param_groups(model, 5e-4, 0.1, 2, 0.75) for n in g['param_names']]
+    assert not any(n.startswith(('backbone.patch_embed', 'backbone.blocks.1.')) for n in names)
+    assert any(n.startswith('backbone.blocks.0.') for n in names)
+
+
+@pytest.mark.reference
+def test_freeze_stages_equal_reference():
+    from oracle import ref_loader
+    ref = ref_loader.load_reference()
+    for kw in (dict(frozen_stages=2), dict(frozen_stages=0), dict(freeze_attn=True), dict(freeze_ffn=True),
+               dict(frozen_stages=1, freeze_ffn=True)):
+        args = dict(img_size=(256, 192), embed_dim=64, depth=4, num_heads=2, qkv_bias=True, **kw)
+        r, o = ref.ViT(**args), V.ViT(**args)
+        r.train()          # (the reference's override returns None)
+        o.train()
+        assert _frozen_names(r) == _frozen_names(o), kw
+        assert [b.training for b in r.blocks] == [b.training for b in o.blocks], kw

@@ -1,9 +1,10 @@
-"""Per-parameter gradient error of the training step vs the fp32 oracle (diagnostic script, not collected by pytest:
-    python tests/debug_train_grads.py B-classic-17 3 2)."""
+"""TEST INFRASTRUCTURE (diagnostic, uses the oracle as checker like tests/ do; never imported by the product path):
+per-parameter gradient error of the training step vs autograd over the fp32 oracle.
+    python tools/debug_train_grads.py B-classic-17 3 2"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
 from oracle import vitpose_torch as VT
 from vitpose_b200 import configs, synthetic
 import vitpose_b200 as V

@@ -6,7 +6,8 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libvitpose_b200.so')
+# VPB_LIB=<path>: an alternative build of the same library (same-box A/B of compile-time variants)
+LIB_PATH = os.environ.get('VPB_LIB') or os.path.join(HERE, 'libvitpose_b200.so')
 
 c_void_p, c_int, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
 

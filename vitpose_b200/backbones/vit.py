@@ -100,6 +100,37 @@ class ViT(nn.Module):
         nn.init.trunc_normal_(self.pos_embed, std=.02)
         self._engine = None
         self._engine_key = None
+        if use_checkpoint:
+            # activation checkpointing (vit.py:323-324) only trades memory for recompute; the training step here
+            # always keeps the activations it needs, so the flag changes nothing — say so instead of ignoring it
+            import warnings
+            warnings.warn('vitpose_b200: use_checkpoint=True has no effect (activations are kept; results identical)')
+        self._freeze_stages()
+
+    def _freeze_stages(self):
+        """vit.py:249-284, same selection rules (including the reference's loop ``range(1, frozen_stages + 1)``, which
+        leaves blocks[0] trainable): frozen tensors get ``requires_grad = False`` — the backward pass then skips their
+        weight gradients and the layer-decay optimizer leaves them out — and frozen blocks are put in eval mode, which
+        switches their stochastic depth off (``DropPath`` is a child of ``Block``)."""
+        def freeze(module):
+            module.eval()
+            for param in module.parameters():
+                param.requires_grad = False
+
+        if self.frozen_stages >= 0:
+            freeze(self.patch_embed)
+        for i in range(1, self.frozen_stages + 1):
+            freeze(self.blocks[i])
+        if self.freeze_attn:
+            for blk in self.blocks:
+                freeze(blk.attn)
+                freeze(blk.norm1)
+        if self.freeze_ffn:
+            self.pos_embed.requires_grad = False
+            freeze(self.patch_embed)
+            for blk in self.blocks:
+                freeze(blk.mlp)
+                freeze(blk.norm2)
 
     # ---- reference API ------------------------------------------------------------------------------
     def init_weights(self, pretrained=None):
@@ -160,5 +191,7 @@ class ViT(nn.Module):
         return self.forward_features(x)
 
     def train(self, mode=True):
+        """vit.py:338-341: frozen parts stay frozen (and in eval mode) whenever the mode is switched."""
         super().train(mode)
+        self._freeze_stages()
         return self

@@ -57,11 +57,12 @@ COCO_SIGMAS = np.array([.26, .25, .25, .35, .35, .79, .79, .72, .72, .62, .62, 1
 
 
 def oks_nms_batched(kpts, areas, scores, group_start, thr, sigmas=None, vis_thr=None, soft=False, max_dets=20,
-                    rescore=False, rescore_vis_thr=None):
+                    rescore=False, rescore_vis_thr=None, areas_float32=False):
     """All images of an evaluation at once: ``kpts`` [P,K,3], ``areas`` [P], ``scores`` [P] (box scores when
     ``rescore``), ``group_start`` [G+1] (poses of image g are rows group_start[g]:group_start[g+1]).
     Returns (list of G index arrays in selection order — global row indices —, the [P] scores used).
-    One CTA per image runs rescoring (topdown_coco_dataset.py:476-490) and oks_nms / soft_oks_nms on the GPU."""
+    One CTA per image runs rescoring (topdown_coco_dataset.py:476-490) and oks_nms / soft_oks_nms on the GPU.
+    ``areas_float32``: the areas are float32 values (the dataset path), whose pair sums NumPy rounds to float32."""
     _lib.require_cuda()
     dev = torch.device('cuda')
     kpts = np.ascontiguousarray(kpts, dtype=np.float32)
@@ -86,7 +87,8 @@ def oks_nms_batched(kpts, areas, scores, group_start, thr, sigmas=None, vis_thr=
         assert float(rescore_vis_thr) == float(vis_thr), 'one visibility threshold per call'
     _lib.check(_lib.lib().vpb_oks_nms(_lib.ptr(d_k), _lib.ptr(d_a), _lib.ptr(d_s), _lib.ptr(d_g), G, K,
                                       int(np.diff(gs).max()), _lib.ptr(var), float(thr), int(use_vis), vt,
-                                      int(bool(rescore)), int(bool(soft)), int(max_dets), _lib.ptr(out_s),
+                                      int(bool(rescore)) | (2 if areas_float32 else 0), int(bool(soft)),
+                                      int(max_dets), _lib.ptr(out_s),
                                       _lib.ptr(keep), _lib.ptr(cnt), _lib.stream_ptr()), 'vpb_oks_nms')
     keep, cnt = keep.cpu().numpy(), cnt.cpu().numpy()
     return [keep[gs[g]:gs[g] + cnt[g]].astype(np.intp) for g in range(G)], out_s.cpu().numpy()

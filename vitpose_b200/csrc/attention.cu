@@ -601,6 +601,8 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();                  // the set-up above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   // cycle accounting (CTA 0 only, one thread per role), enabled with VPB_ATT_DEBUG & 32; printed by & 64.
   // The counters are declared inside each role (PP_TIMING_STATE) so that they are not live across the
   // setmaxnreg-limited branches of the other roles.
@@ -944,8 +946,15 @@ static int launch_attention_pingpong(const CUtensorMap& tq, const CUtensorMap& t
   const int units = p.n * p.heads * q_tiles;
   int grid = max_ctas > 0 ? max_ctas : sm_count();
   if (grid > units) grid = units;
-  kern<<<grid, pp_threads(EPIW), smem, stream>>>(tq, tkv, tqb, tkvb, p, units);
-  VPB_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(pp_threads(EPIW));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_launch_attr(&attr[0]);
+  VPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tkv, tqb, tkvb, p, units));
   return 0;
 }
 

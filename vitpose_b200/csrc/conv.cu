@@ -77,6 +77,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();                  // the set-up above overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
   // item -> (super tile, phase, n tile); n tile fastest so co-running CTAs share the activation box in L2
   auto decode_item = [&](int item, int& st, int& phase, int& nt) {
@@ -301,8 +303,15 @@ static int launch_conv(const void* in, const void* wts, ConvParams& p, int k_tot
   int grid = p.super_tiles * (MODE == MODE_DECONV ? 4 : 1) * p.n_tiles;
   const int cap = max_ctas > 0 ? max_ctas : sm_count();
   if (grid > cap) grid = cap;
-  kern<<<grid, CV_THREADS, smem, stream>>>(tin, tw, p);
-  VPB_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(CV_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_launch_attr(&attr[0]);
+  VPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tin, tw, p));
   return 0;
 }
 

@@ -6,6 +6,8 @@
 
 namespace vpb {
 
+static long long* gemm_debug_buf(cudaStream_t stream, int bn, int epi);
+
 template <int BN, int EPI, int CG, int OPM = 0>
 static int launch_gemm_inst(const GemmMaps& maps, const GemmParams& p, int max_ctas, cudaStream_t stream) {
   constexpr int smem = gemm_smem_bytes(BN, EPI, CG);
@@ -28,6 +30,8 @@ static int launch_gemm_inst(const GemmMaps& maps, const GemmParams& p, int max_c
     cap -= cap % (n_tiles * CG);
   }
   if (grid > cap) grid = cap;
+  GemmParams pd = p;
+  pd.dbg = gemm_debug_buf(stream, BN, EPI);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(gemm_threads(EPI));
@@ -36,14 +40,14 @@ static int launch_gemm_inst(const GemmMaps& maps, const GemmParams& p, int max_c
   // (A cooperative launch would let the driver guarantee that the sibling CTAs of the fused-LayerNorm kernels are
   // co-scheduled, but Nsight Compute cannot profile cooperative cluster launches; the grid is one CTA per SM, sized
   // from the device, which gives the same guarantee on a GPU this process has to itself.)
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  VPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps.a, maps.b, maps.out, maps.aux, maps.ln, p));
+  cfg.numAttrs = 1 + pdl_launch_attr(&attr[1]);
+  VPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps.a, maps.b, maps.out, maps.aux, maps.ln, pd));
   return 0;
 }
 
@@ -55,6 +59,31 @@ static int gemm_flags() {
     flags = e ? atoi(e) : GEMM_DEFAULT_FLAGS;
   }
   return flags;
+}
+
+// VPB_GEMM_DEBUG=1: per-role wait-cycle counters of CTA 0 (managed memory); every launch prints the counters the
+// previous launch left (tools/gemm_time.py). Measured with them in round 2 (profiles/r02_summary.md): the MMA issuer
+// of the paired 256 x 256 GEMMs waits for operands 29 % (fc1) to 42 % (proj + LayerNorm, 3 stages) of the kernel.
+static long long* gemm_debug_buf(cudaStream_t stream, int bn, int epi) {
+  static int on = -1;
+  static long long* buf = nullptr;
+  if (on < 0) {
+    const char* e = getenv("VPB_GEMM_DEBUG");
+    on = e ? atoi(e) : 0;
+  }
+  if (!on) return nullptr;
+  if (buf == nullptr) {
+    if (cudaMallocManaged(&buf, 32 * sizeof(long long)) != cudaSuccess) return nullptr;
+    for (int i = 0; i < 32; ++i) buf[i] = 0;
+  } else {
+    cudaStreamSynchronize(stream);
+    fprintf(stderr, "gemm cycles (CTA0, prev launch -> now BN=%d epi=%d): producer wait_empty %lld total %lld | mma wait_tempty %lld "
+                    "wait_full %lld total %lld | ring0 wait_ready %lld wait_read %lld total %lld | epi0 wait_tfull %lld "
+                    "wait_rfull %lld sibling %lld wait_slot_p2 %lld total %lld tiles %lld | mma wait_full_B %lld\n",
+            bn, epi, buf[0], buf[1], buf[2], buf[3], buf[4], buf[5], buf[6], buf[7], buf[8], buf[9], buf[10], buf[11],
+            buf[12], buf[13], buf[14]);
+  }
+  return buf;
 }
 
 // CTA pairs pay off on the large transformer GEMMs (full 256-wide N tiles, many tiles); everything else stays 1-CTA.

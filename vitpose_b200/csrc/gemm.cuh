@@ -69,6 +69,8 @@ struct GemmParams {
   float ln_eps;
   // Pipeline-depth switches (gemm_flags(): VPB_GEMM_FLAGS overrides the default for A/B runs; results identical):
   int flags;
+  // optional [32] cycle counters of CTA 0 (VPB_GEMM_DEBUG=1, printed by the next launch), see gemm.cu
+  long long* dbg;
 };
 // ring warp: prefetch the residual chunk of this group's NEXT tile into L2 while chunk c of the current tile loads
 constexpr int GEMM_FLAG_PF_RESID = 1;
@@ -107,9 +109,13 @@ __host__ __device__ constexpr int gemm_tmem_cols(int bn) {
 __host__ __device__ constexpr int gemm_stage_bytes(int bn, int cg = 1) { return GEMM_BM * 128 + bn * 128 / cg; }
 // Slots of an in-place residual ring. The MMA-bound LayerNorm variant gives one up to keep its operand stages; the
 // short-K variants run 3 operand stages and split the rest of shared memory between their two rings.
+#ifndef VPB_SPLIT_STAGES
+#define VPB_SPLIT_STAGES 3
+#endif
+__host__ __device__ constexpr int gemm_split_stages(int bn, int cg) { return (cg == 2 && bn == 256) ? VPB_SPLIT_STAGES : 3; }
 __host__ __device__ constexpr int gemm_res_slots(int bn, int epi, int cg) {
   if (!gemm_ln_split(epi)) return gemm_epi_ln(epi) ? 3 : 4;
-  const int n = (230400 - 3 * gemm_stage_bytes(bn, cg) - 4096) / (2 * GEMM_STAGING_BYTES);
+  const int n = (230400 - gemm_split_stages(bn, cg) * gemm_stage_bytes(bn, cg) - 4096) / (2 * GEMM_STAGING_BYTES);
   return n > GEMM_RES_SLOTS ? GEMM_RES_SLOTS : n;
 }
 // shared memory for the epilogue: one staging box per bf16 epilogue group, or the residual ring (+ gamma/beta)
@@ -122,13 +128,37 @@ __host__ __device__ constexpr int gemm_epi_smem(int bn, int epi, int cg) {
 }
 __host__ __device__ constexpr int gemm_num_stages(int bn, int epi, int cg = 1) {
   // 227 KB usable, minus 1 KB alignment slack and ~1 KB of static shared memory
-  return gemm_ln_split(epi) ? 3
+  return gemm_ln_split(epi) ? gemm_split_stages(bn, cg)
          : ((230400 - gemm_epi_smem(bn, epi, cg)) / gemm_stage_bytes(bn, cg)) > 8
              ? 8
              : ((230400 - gemm_epi_smem(bn, epi, cg)) / gemm_stage_bytes(bn, cg));
 }
 __host__ __device__ constexpr int gemm_smem_bytes(int bn, int epi, int cg = 1) {
   return gemm_num_stages(bn, epi, cg) * gemm_stage_bytes(bn, cg) + gemm_epi_smem(bn, epi, cg) + 1024;
+}
+// Decoupled operand rings (CTA pairs, 256-wide tiles): the A tiles (activations, streamed from HBM: ~2 us under load)
+// and the B tiles (weights, L2-resident: a fraction of that) get rings of their own depth in the same shared memory,
+// few B stages and as many A stages as the rest holds, instead of STAGES x (A + B). The loads in flight are what
+// bounds these kernels (VPB_GEMM_DEBUG counters: the MMA issuer waits for operands 29 % (fc1) - 42 % (proj) of the
+// time with the producer waiting for free stages).
+// Measured (B200, M = 98304, one polling producer thread for both rings): SLOWER — fc1 411 -> 471 us, qkv 274 -> 325,
+// fc2 + LN 411 -> 481, proj + LN 205 -> 219: the B tiles stall the issuer as long as the A tiles do (their latency
+// under load is not shorter), and the polling thread is slower than two blocking waits. Kept switched off.
+#ifndef VPB_GEMM_DEC
+#define VPB_GEMM_DEC 0
+#endif
+#ifndef VPB_GEMM_SB
+#define VPB_GEMM_SB 3
+#endif
+__host__ __device__ constexpr bool gemm_decoupled(int bn, int cg, int opm) {
+  return VPB_GEMM_DEC != 0 && cg == 2 && bn == 256 && opm == 0;
+}
+__host__ __device__ constexpr int gemm_b_stages(int bn, int epi, int cg) {
+  return gemm_num_stages(bn, epi, cg) <= 3 ? 2 : VPB_GEMM_SB;
+}
+__host__ __device__ constexpr int gemm_a_stages(int bn, int epi, int cg) {
+  return (gemm_num_stages(bn, epi, cg) * gemm_stage_bytes(bn, cg) - gemm_b_stages(bn, epi, cg) * (bn * 128 / cg)) /
+         (GEMM_BM * 128);
 }
 
 // Exact-erf GELU (nn.GELU default) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. float
@@ -231,6 +261,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   constexpr int A_BYTES = GEMM_BM * 128;
   constexpr int B_BYTES = BN * 128 / CG;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr bool DEC = gemm_decoupled(BN, CG, OPM);
+  constexpr int SA = DEC ? gemm_a_stages(BN, EPI, CG) : STAGES;     // DEC: A ring [SA][A_BYTES] then B ring [SB][B_BYTES]
+  constexpr int SB = DEC ? gemm_b_stages(BN, EPI, CG) : 1;
+  static_assert(!DEC || (SA * A_BYTES + SB * B_BYTES <= STAGES * STAGE_BYTES && SA >= 2 && SB >= 2), "operand rings");
   constexpr int TMEM_COLS = gemm_tmem_cols(BN);
   constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM * CG, BN, OPM, OPM);
   static_assert(CG == 1 || (CG == 2 && BN % 32 == 0), "CTA pairs split the B tile in two halves");
@@ -255,8 +289,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint8_t* s_out = smem + STAGES * STAGE_BYTES;
   constexpr int RING_BYTES = RES_SLOTS * GEMM_STAGING_BYTES;  // per tile group
   float* s_affine = reinterpret_cast<float*>(s_out + TG * RING_BYTES);   // LN only, per tile group: gamma[BN] beta[BN]
-  __shared__ uint64_t full_bar[STAGES];
-  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t full_bar[SA];      // (A + B of a stage, or the A ring when DEC)
+  __shared__ uint64_t empty_bar[SA];
+  __shared__ uint64_t fullb_bar[SB];     // DEC: the B ring
+  __shared__ uint64_t emptyb_bar[SB];
   __shared__ uint64_t tfull_bar[2];
   __shared__ uint64_t tempty_bar[2];
   __shared__ uint64_t res_full[2][GEMM_RES_SLOTS];
@@ -276,9 +312,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;     // both CTAs of a pair walk the same tiles
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < SA; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(&fullb_bar[s], 1);
+      mbar_init(&emptyb_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -306,11 +346,58 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if constexpr (CG == 2) cluster_sync_all();   // peer barriers initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();                  // everything above overlapped the previous kernel's tail; its output is visible now
+  pdl_launch_dependents();
+  // cycle accounting of CTA 0 (one thread per role): time spent in each kind of wait, and the role's total
+  const bool timing = p.dbg != nullptr && blockIdx.x == 0;
+  auto twait = [&](uint64_t* bar, uint32_t parity, long long& acc) {
+    if (timing) {
+      const long long t0 = clock64();
+      mbar_wait(bar, parity);
+      acc += clock64() - t0;
+    } else {
+      mbar_wait(bar, parity);
+    }
+  };
+  const long long t_role = timing ? clock64() : 0;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long w_empty = 0;
+      if constexpr (DEC) {
+        // One thread feeds both rings: it polls (test_wait, non-blocking) the next free slot of each and issues
+        // whichever load can go, so a full B ring never holds back the A loads further ahead.
+        int ta = tile0, ka = 0, tb = tile0, kb_ = 0, sa_i = 0, sb_i = 0;
+        uint32_t pa = 0, pb = 0;
+        const uint8_t* b_ring = smem + SA * A_BYTES;
+        while (ta < num_tiles || tb < num_tiles) {
+          bool progressed = false;
+          if (ta < num_tiles && mbar_test_wait(&empty_bar[sa_i], pa ^ 1)) {
+            const int m_blk = (ta / n_tiles) * CG + cta_rank;
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[sa_i], 2 * A_BYTES);
+            tma_load_2d_pair(smem + sa_i * A_BYTES, &tma_a, mapa_shared(smem_u32(&full_bar[sa_i]), 0), ka * GEMM_BK,
+                             m_blk * GEMM_BM);
+            if (++sa_i == SA) { sa_i = 0; pa ^= 1; }
+            if (++ka == k_blocks) { ka = 0; ta += tile_step; }
+            progressed = true;
+          }
+          if (tb < num_tiles && mbar_test_wait(&emptyb_bar[sb_i], pb ^ 1)) {
+            const int n_blk = tb % n_tiles;
+            if (cta_rank == 0) mbar_arrive_expect_tx(&fullb_bar[sb_i], 2 * B_BYTES);
+            tma_load_2d_pair(const_cast<uint8_t*>(b_ring) + sb_i * B_BYTES, &tma_b,
+                             mapa_shared(smem_u32(&fullb_bar[sb_i]), 0), kb_ * GEMM_BK, n_blk * BN + cta_rank * (BN / 2));
+            if (++sb_i == SB) { sb_i = 0; pb ^= 1; }
+            if (++kb_ == k_blocks) { kb_ = 0; tb += tile_step; }
+            progressed = true;
+          }
+          if (!progressed) {
+            if (timing) w_empty += 64;
+            __nanosleep(32);
+          }
+        }
+      } else
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int m_blk = ((tile / p.ksplit) / n_tiles) * CG + cta_rank;
         const int n_blk = (tile / p.ksplit) % n_tiles;
@@ -323,7 +410,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int m_next = ((nt / p.ksplit) / n_tiles) * CG + cta_rank;
         for (int kb = kb0; kb < kb1; ++kb) {
           if (pf_a) tma_prefetch_l2_2d(&tma_a, kb * GEMM_BK, m_next * GEMM_BM);
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          twait(&empty_bar[stage], phase ^ 1, w_empty);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           if constexpr (CG == 2) {
@@ -349,6 +436,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (timing) { p.dbg[0] = w_empty; p.dbg[1] = clock64() - t_role; }
     }
   } else if (warp == 1) {
     if (lane == 0 && cta_rank == 0) {      // with CTA pairs only the leader issues MMAs (for both CTAs)
@@ -356,13 +444,33 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long w_tempty = 0, w_full = 0, w_fullb = 0;
+      int sb_i = 0;
+      uint32_t pb = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        twait(&tempty_bar[acc], acc_phase ^ 1, w_tempty);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
+        if constexpr (DEC) {
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            twait(&full_bar[stage], phase, w_full);
+            twait(&fullb_bar[sb_i], pb, w_fullb);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * A_BYTES);
+            const uint32_t b_addr = smem_u32(smem + SA * A_BYTES + sb_i * B_BYTES);
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k)
+              umma_bf16_ss_pair(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), IDESC,
+                                (kb > 0 || k != 0) ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage], 3);
+            umma_commit_pair(&emptyb_bar[sb_i], 3);
+            if (++stage == SA) { stage = 0; phase ^= 1; }
+            if (++sb_i == SB) { sb_i = 0; pb ^= 1; }
+          }
+        } else {
         const int kb0 = (tile % p.ksplit) * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          twait(&full_bar[stage], phase, w_full);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
@@ -383,12 +491,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        }
         // accumulator complete -> epilogue (of both CTAs)
         if constexpr (CG == 2) umma_commit_pair(&tfull_bar[acc], 3);
         else umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+      if (timing) { p.dbg[2] = w_tempty; p.dbg[3] = w_full; p.dbg[4] = clock64() - t_role; p.dbg[14] = w_fullb; }
     }
   } else if (gemm_epi_adds_tile(EPI) && (warp == 6 || (LN_SPLIT && warp == 11))) {
     // Ring warp of tile group tg: owns BOTH ends of the in-place staging ring. It TMA-loads the fp32 residual (or
@@ -428,6 +538,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       };
       int ld_tile = first_tile, ld_c = 0, st_tile = first_tile, st_c = 0;
       uint32_t nld = 0, nst = 0;
+      long long w_ready = 0, w_read = 0;
       auto load_next = [&](uint32_t slot) {
         if (ld_tile >= num_tiles) return;
         load(ld_tile, ld_c, slot);
@@ -437,7 +548,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       for (int i = 0; i < RES_SLOTS; ++i) load_next(static_cast<uint32_t>(i));
       while (st_tile < num_tiles) {
         const uint32_t slot = nst % RES_SLOTS;
-        mbar_wait(&res_ready[tg][slot], (nst / RES_SLOTS) & 1);      // the epilogue has finished chunk nst in place
+        twait(&res_ready[tg][slot], (nst / RES_SLOTS) & 1, w_ready);  // the epilogue has finished chunk nst in place
         const int m_blk = ((st_tile / p.ksplit) / n_tiles) * CG + cta_rank;
         const int n_blk = (st_tile / p.ksplit) % n_tiles;
         if (st_c < NX)
@@ -446,7 +557,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           tma_store_2d(&tma_ln, ring + slot * GEMM_STAGING_BYTES, n_blk * BN + (st_c - NX) * 64, m_blk * GEMM_BM);
         tma_store_commit();
         if (p.flags & GEMM_FLAG_WAIT0) {    // this store has read its slot (a few hundred cycles): reload it now
+          const long long t0 = timing ? clock64() : 0;
           tma_store_wait_read<0>();
+          if (timing) w_read += clock64() - t0;
           load_next(slot);
         } else if (nst > 0) {               // the previous store has read its slot: reuse it for the next load
           tma_store_wait_read<1>();
@@ -456,6 +569,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         if (++st_c == NCH) { st_c = 0; st_tile += stride; }
       }
       tma_store_wait_all<0>();              // all output bytes committed before the CTA exits
+      if (timing && tg == 0) { p.dbg[5] = w_ready; p.dbg[6] = w_read; p.dbg[7] = clock64() - t_role; }
     }
   } else {
     const int quad = warp & 3;             // TMEM lane quadrant this warp may read
@@ -480,6 +594,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint32_t acc_phase = 0;
     uint32_t chunk_seq = 0;                // running chunk counter of this group: staging buffer = chunk_seq & 1
     int const_n_blk = -1;                  // n-tile whose bias / gamma / beta columns are in shared memory
+    long long w_tfull = 0, w_rfull = 0, w_sib = 0, w_bar = 0, n_epi_tiles = 0;
     for (int tile = tile0 + (LN_SPLIT ? grp : 0) * tile_step; tile < num_tiles; tile += tile_step * TG) {
       const int m_blk = ((tile / p.ksplit) / n_tiles) * CG + cta_rank;
       const int n_blk = (tile / p.ksplit) % n_tiles;
@@ -509,7 +624,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // constants visible to the whole group
         }
-        mbar_wait(&tfull_bar[acc], acc_phase);
+        twait(&tfull_bar[acc], acc_phase, w_tfull);
+        ++n_epi_tiles;
         tc_fence_after();
         if (cgrp >= NCHUNK) {               // narrow tile: this group has no chunk, just release TMEM
           tc_fence_before();
@@ -526,7 +642,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             const uint32_t buf = chunk_seq % RES_SLOTS;
             const uint32_t srow = smem_u32(ring) + buf * GEMM_STAGING_BYTES + r * 128;
             const float4* bias4 = reinterpret_cast<const float4*>(&s_bias[grp][c * 32]);
-            mbar_wait(&rfull[buf], (chunk_seq / RES_SLOTS) & 1);
+            twait(&rfull[buf], (chunk_seq / RES_SLOTS) & 1, w_rfull);
             float2 s0 = make_float2(0.0f, 0.0f), s1 = make_float2(0.0f, 0.0f);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -591,7 +707,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           // ---- publish (mean, M2) for the CTAs that own the other n-tiles of this row block (and for pass 2)
           ln_publish_stats(p, m_blk, r, n_tiles, n_blk, mean, m2);
           float mu, rstd;
+          const long long t_sib = timing ? clock64() : 0;
           ln_row_stats<BN>(p, m_blk, r, n_tiles, mu, rstd);
+          if (timing) w_sib += clock64() - t_sib;
           const float nmr = -mu * rstd;
           // ---- pass 2: normalise the rows kept in TMEM, bf16 boxes of 64 columns through the same ring
 #pragma unroll 1
@@ -622,7 +740,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               v[2 * j + 1] = pack_bf16x2(y1.x, y1.y);
             }
             const uint32_t srow = smem_u32(ring) + buf * GEMM_STAGING_BYTES + r * 128;
-            mbar_wait(&rfull[buf], (chunk_seq / RES_SLOTS) & 1);
+            twait(&rfull[buf], (chunk_seq / RES_SLOTS) & 1, w_bar);
 #pragma unroll
             for (int u = 0; u < 8; ++u)
               sts_u4(srow + ((u ^ (r & 7)) * 16), v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
@@ -653,7 +771,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if constexpr (gemm_epi_adds_tile(EPI)) {
             // residual chunk landed in the slot (TMA, issued by warp 6 well ahead); update it in place: every thread
             // reads and writes only its own 128-byte row, so no barrier is needed before the math
-            mbar_wait(&rfull[buf], (chunk_seq / RES_SLOTS) & 1);
+            twait(&rfull[buf], (chunk_seq / RES_SLOTS) & 1, w_rfull);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const uint32_t pu = srow + ((u ^ (r & 7)) * 16);
@@ -761,6 +879,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
     }
     if (STAGED && !gemm_epi_adds_tile(EPI) && etid == 0) tma_store_wait_all<0>();   // output committed before exit
+    if (timing && etid == 0 && grp == 0) {
+      p.dbg[8] = w_tfull; p.dbg[9] = w_rfull; p.dbg[10] = w_sib; p.dbg[11] = w_bar;
+      p.dbg[12] = clock64() - t_role; p.dbg[13] = n_epi_tiles;
+    }
   }
   tc_fence_before();
   __syncthreads();

@@ -1,6 +1,7 @@
 #include "host_util.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace vpb {
@@ -64,6 +65,18 @@ int make_tma_desc(CUtensorMap* out, TmaDtype dtype, const void* base, int rank, 
     return -1;
   }
   return 0;
+}
+
+int pdl_launch_attr(cudaLaunchAttribute* attr) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("VPB_PDL");
+    on = e ? atoi(e) : 1;
+  }
+  if (!on) return 0;
+  attr->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr->val.programmaticStreamSerializationAllowed = 1;
+  return 1;
 }
 
 int sm_count() {

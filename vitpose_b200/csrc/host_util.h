@@ -37,4 +37,8 @@ int make_tma_desc(CUtensorMap* out, TmaDtype dtype, const void* base, int rank, 
 
 int sm_count();
 
+// Programmatic dependent launch for the kernels of the forward sequence (VPB_PDL=0 switches it off, A/B): fills
+// `attr` and returns 1 when enabled, else returns 0. Only kernels that call pdl_wait() may be launched with it.
+int pdl_launch_attr(cudaLaunchAttribute* attr);
+
 }  // namespace vpb

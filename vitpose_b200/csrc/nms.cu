@@ -39,10 +39,14 @@ __device__ __forceinline__ double np_pairwise_sum(const double* a, int n) {   //
 }
 
 __device__ float oks_pair(const float* __restrict__ g, const float* __restrict__ d, double a_g, double a_d,
-                          const double* __restrict__ var, int K, bool use_vis, double vis_thr) {
+                          const double* __restrict__ var, int K, bool use_vis, double vis_thr, bool area_f32 = false) {
   double e[NMS_MAX_K];
   int n = 0;
-  const double denom = (a_g + a_d) / 2 + 2.220446049250313e-16;     // np.spacing(1)
+  // (a_g + a_d) / 2 + np.spacing(1): with float32 areas (the dataset path hands over the float32 `boxes[:, 4]`) the
+  // sum and the halving are float32 operations, only np.spacing(1) widens the result
+  const double half = area_f32 ? static_cast<double>(__fmul_rn(__fadd_rn(static_cast<float>(a_g), static_cast<float>(a_d)), 0.5f))
+                               : (a_g + a_d) / 2;
+  const double denom = half + 2.220446049250313e-16;     // np.spacing(1)
   for (int k = 0; k < K; ++k) {
     if (use_vis && !(static_cast<double>(d[3 * k + 2]) > vis_thr)) continue;
     const float dx = __fsub_rn(d[3 * k], g[3 * k]), dy = __fsub_rn(d[3 * k + 1], g[3 * k + 1]);
@@ -82,7 +86,7 @@ __global__ void __launch_bounds__(NMS_THREADS) oks_nms_kernel(const NmsParams p)
   // ---- scores: rescoring = mean of the visible joint scores (fp32, joint order) times the box score
   for (int i = threadIdx.x; i < P; i += NMS_THREADS) {
     double s = p.box_scores[lo + i];
-    if (p.rescore) {
+    if (p.rescore & 1) {
       const float* kp = p.kpts + static_cast<size_t>(lo + i) * p.K * 3;
       float acc = 0.f;
       int cnt = 0;
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(NMS_THREADS) oks_nms_kernel(const NmsParams p)
           const int j = order[q];
           if (!alive[j]) continue;
           const float o = oks_pair(gk, p.kpts + static_cast<size_t>(lo + j) * p.K * 3, p.areas[lo + i],
-                                   p.areas[lo + j], p.var, p.K, p.use_vis != 0, p.vis_thr);
+                                   p.areas[lo + j], p.var, p.K, p.use_vis != 0, p.vis_thr, (p.rescore & 2) != 0);
           if (!(static_cast<double>(o) <= p.thr)) alive[j] = 0;
         }
       }
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(NMS_THREADS) oks_nms_kernel(const NmsParams p)
       for (int j = threadIdx.x; j < P; j += NMS_THREADS) {
         if (!alive[j]) continue;
         const float o = oks_pair(gk, p.kpts + static_cast<size_t>(lo + j) * p.K * 3, p.areas[lo + i], p.areas[lo + j],
-                                 p.var, p.K, p.use_vis != 0, p.vis_thr);
+                                 p.var, p.K, p.use_vis != 0, p.vis_thr, (p.rescore & 2) != 0);
         // scores * np.exp(-overlap**2 / thr): the exponent stays float32 (a Python float does not widen an array)
         const float t = __fdiv_rn(-__fmul_rn(o, o), static_cast<float>(p.thr));
         sc[j] = sc[j] * static_cast<double>(expf(t));

@@ -39,6 +39,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (a thread that watches two barriers)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: ~2^26 failed probes (each probe itself sleeps in hardware for a while) is seconds
 // of waiting — far beyond any legitimate stall here — then trap instead of hanging the box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -47,6 +59,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 26)) __trap();
   }
 }
+
+// ---- programmatic dependent launch -------------------------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still running: its CTAs are placed on SMs as the predecessor's CTAs exit and run their prologue (barrier
+// set-up, TMEM allocation, descriptor prefetch) there. pdl_wait() blocks until the predecessor has completed and its
+// memory is visible — it must precede every access to data the predecessor wrote; pdl_launch_dependents() lets the
+// successor of THIS kernel be scheduled once every CTA of this kernel has called it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- proxies / fences -----------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {

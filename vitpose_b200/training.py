@@ -110,7 +110,10 @@ def drop_path_scales(bb, n, device):
     # all 2 * depth Bernoulli draws in one shot (a handful of launches instead of ~8 per block)
     keep = (1.0 - rates).to(device=device, dtype=torch.float32).view(-1, 1, 1)
     masks = torch.floor(keep + torch.rand(bb.depth, 2, n, device=device)).div_(keep).contiguous()
-    return [(None, None) if p <= 0.0 else (masks[i, 0], masks[i, 1]) for i, p in enumerate(rates.tolist())]
+    # a frozen block is in eval mode (vit.py:257-259), where DropPath is the identity (vit.py:55-56)
+    blocks = getattr(bb, 'blocks', None)
+    frozen = [blocks is not None and not blocks[i].training for i in range(bb.depth)]
+    return [(None, None) if p <= 0.0 or frozen[i] else (masks[i, 0], masks[i, 1]) for i, p in enumerate(rates.tolist())]
 
 
 def _param_list(model):
@@ -286,12 +289,19 @@ class _NetworkFn(torch.autograd.Function):
         ops.layernorm_bwd(s['x_final'], ln.weight.detach(), dact, dx, dg_, db_, 1e-6)
         g['backbone.last_norm.weight'], g['backbone.last_norm.bias'] = dg_, db_
 
+        trainable = {nm for nm, p in _param_list(model) if p.requires_grad}
+
         def linear_bwd(name, lin, dy_bf16, x_bf16, want_dx=True):
-            """gradients of y = x W^T + b given dy: dW, db into g[...]; returns dx (bf16)."""
-            dw, dbias = zeros(*lin.w.shape), zeros(lin.w.shape[0])
-            _wgrad(dy_bf16, x_bf16, dw)
-            ops.colsum_accumulate(dy_bf16, dbias)
-            g[name + '.weight'], g[name + '.bias'] = dw, dbias
+            """gradients of y = x W^T + b given dy: dW, db into g[...]; returns dx (bf16). Frozen tensors
+            (``requires_grad = False``: frozen_stages / freeze_attn / freeze_ffn, vit.py:249-284) are skipped."""
+            if name + '.weight' in trainable:
+                dw = zeros(*lin.w.shape)
+                _wgrad(dy_bf16, x_bf16, dw)
+                g[name + '.weight'] = dw
+            if name + '.bias' in trainable:
+                dbias = zeros(lin.w.shape[0])
+                ops.colsum_accumulate(dy_bf16, dbias)
+                g[name + '.bias'] = dbias
             return ops.gemm(dy_bf16, lin.wt, EPI_BIAS) if want_dx else None
 
         for l in range(len(bb.blocks) - 1, -1, -1):
@@ -319,8 +329,9 @@ class _NetworkFn(torch.autograd.Function):
         # ---- patch embed (vit.py:159-165) + pos embed (vit.py:320)
         dyb = ops.cast_bf16(dx)
         linear_bwd('backbone.patch_embed.proj', s['pe'], dyb, s['patches'], want_dx=False)
-        g['backbone.patch_embed.proj.weight'] = g['backbone.patch_embed.proj.weight'].view(
-            bb.patch_embed.proj.weight.shape)
+        if 'backbone.patch_embed.proj.weight' in g:
+            g['backbone.patch_embed.proj.weight'] = g['backbone.patch_embed.proj.weight'].view(
+                bb.patch_embed.proj.weight.shape)
         dpos = zeros(1, T + 1, D)                                          # [cls slot | tokens], contiguous
         dpos_tok = dpos[0, 1:].reshape(T * D)
         ops.colsum_accumulate(dx.view(n, T * D), dpos_tok)                 # sum over the crops
