@@ -129,3 +129,37 @@ def test_topdown_moe_mixed_batch_vs_oracle():
     feats = model.backbone(img.cuda(), torch.tensor([1, 0, 2, 1, 0]))
     f_ref = VT.vit_features(sd, img, 2, 2, dataset_source=torch.tensor([1, 0, 2, 1, 0]))
     assert (feats.cpu() - f_ref).abs().max() < 0.05 * max(1.0, float(f_ref.abs().max()))
+
+
+def test_moe_loads_plain_vit_checkpoint(tmp_path):
+    """``TopDownMoE(pretrained=<MAE / plain ViT checkpoint>)`` — vit_moe.py:336 passes ``part_features`` to
+    load_checkpoint, which splits every fc2 [D, 4D] into the shared fc2 [D - part, 4D] and one copy of the last
+    ``part`` rows per expert (mmcv_custom/checkpoint.py:396-405)."""
+    import vitpose_b200 as V
+    plain_cfg = configs.tiny_model_cfg(5, depth=2)
+    plain_cfg['backbone']['img_size'] = (224, 224)        # MAE pretrain: square 14 x 14 position grid, resized on load
+    plain = V.build_backbone(plain_cfg['backbone'])
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for p in plain.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+    path = str(tmp_path / 'vit.pth')
+    torch.save(dict(state_dict={'backbone.' + k: v for k, v in plain.state_dict().items()}), path)
+    cfg = _moe_cfg(num_expert=3, part=32)
+    moe = V.build_backbone(cfg['backbone'])
+    moe.init_weights(pretrained=path)
+    D, part = cfg['backbone']['embed_dim'], 32
+    for i in range(2):
+        w, b = plain.state_dict()[f'blocks.{i}.mlp.fc2.weight'], plain.state_dict()[f'blocks.{i}.mlp.fc2.bias']
+        sd = moe.state_dict()
+        assert torch.equal(sd[f'blocks.{i}.mlp.fc2.weight'], w[:D - part])
+        assert torch.equal(sd[f'blocks.{i}.mlp.fc2.bias'], b[:D - part])
+        for e in range(3):
+            assert torch.equal(sd[f'blocks.{i}.mlp.experts.{e}.weight'], w[D - part:])
+            assert torch.equal(sd[f'blocks.{i}.mlp.experts.{e}.bias'], b[D - part:])
+        assert torch.equal(sd[f'blocks.{i}.attn.qkv.weight'], plain.state_dict()[f'blocks.{i}.attn.qkv.weight'])
+    # every dataset's effective FFN is then the plain ViT's
+    assert torch.equal(moe.effective_state_dict(1)['blocks.0.mlp.fc2.weight'], plain.state_dict()['blocks.0.mlp.fc2.weight'])
+    # freeze_ffn also freezes the expert FFNs that replace the plain ones
+    frozen = V.build_backbone(dict(cfg['backbone'], freeze_ffn=True))
+    assert not any(p.requires_grad for n, p in frozen.named_parameters() if '.mlp.' in n)

@@ -91,3 +91,37 @@ def test_allreduce_gradients_world2(tmp_path):
         assert d['ncoll'] >= 2
         for got, exp in zip(d['grads'], expect):
             assert torch.allclose(got, exp, atol=1e-6)
+
+
+def _log_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from vitpose_b200.detectors.top_down import TopDown
+        losses = dict(heatmap_loss=torch.tensor(1.0 + rank), acc_pose=torch.tensor(0.25 * (rank + 1)), extra=0.5,
+                      aux_loss=[torch.tensor([2.0 * rank, 2.0 * rank + 2.0])])
+        loss, log_vars = TopDown._parse_losses(TopDown, losses)
+        torch.save(dict(loss=loss, log_vars=log_vars), os.path.join(out_dir, f'l{rank}.pt'))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_parse_losses_averages_logged_values_over_ranks(tmp_path):
+    """mmpose/models/detectors/base.py:37-76: the returned loss is the LOCAL sum of the '*loss*' entries (backward runs
+    on it); the logged values are averaged over the ranks and handed out as Python floats."""
+    world = 2
+    mp.spawn(_log_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        d = torch.load(os.path.join(str(tmp_path), f'l{r}.pt'))
+        local_aux = 2.0 * r + 1.0
+        assert abs(float(d['loss']) - (1.0 + r + local_aux)) < 1e-6
+        lv = d['log_vars']
+        assert all(isinstance(v, float) for v in lv.values())
+        assert abs(lv['heatmap_loss'] - 1.5) < 1e-6 and abs(lv['acc_pose'] - 0.375) < 1e-6 and lv['extra'] == 0.5
+        assert abs(lv['aux_loss'] - 2.0) < 1e-6 and abs(lv['loss'] - 3.5) < 1e-6
+    # single process: same values, no collective
+    from vitpose_b200.detectors.top_down import TopDown
+    loss, lv = TopDown._parse_losses(TopDown, dict(heatmap_loss=torch.tensor(2.0), acc_pose=torch.tensor(0.5)))
+    assert float(loss) == 2.0 and lv == dict(heatmap_loss=2.0, acc_pose=0.5, loss=2.0)
+    with pytest.raises(TypeError):
+        TopDown._parse_losses(TopDown, dict(bad_loss='x'))

@@ -141,7 +141,9 @@ class ViT(nn.Module):
             from ..checkpoint import adapt_state_dict, extract_state_dict
             sd = extract_state_dict(torch.load(pretrained, map_location='cpu'))
             sd = {k[len('backbone.'):] if k.startswith('backbone.') else k: v for k, v in sd.items()}
-            self.load_state_dict(adapt_state_dict(sd, self, self.patch_padding), strict=False)
+            # ViTPose+ (vit_moe.py:336): part_features splits every MAE fc2 [D, 4D] into the shared fc2 and the experts
+            self.load_state_dict(adapt_state_dict(sd, self, self.patch_padding, getattr(self, 'part_features', None)),
+                                 strict=False)
             self._engine = None
             return
         for m in self.modules():

@@ -40,6 +40,7 @@ class ViTMoE(ViT):
         for blk in self.blocks:
             blk.mlp = _MoEMlp(num_expert, D, hidden, part_features)
         self._engines = {}
+        self._freeze_stages()            # the FFN modules were replaced after ViT.__init__ froze the old ones
         self.init_weights(None)
 
     def effective_state_dict(self, dataset_idx):

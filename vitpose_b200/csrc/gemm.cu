@@ -7,6 +7,7 @@
 namespace vpb {
 
 static long long* gemm_debug_buf(cudaStream_t stream, int bn, int epi);
+static bool gemm_cooperative();
 
 template <int BN, int EPI, int CG, int OPM = 0>
 static int launch_gemm_inst(const GemmMaps& maps, const GemmParams& p, int max_ctas, cudaStream_t stream) {
@@ -37,16 +38,24 @@ static int launch_gemm_inst(const GemmMaps& maps, const GemmParams& p, int max_c
   cfg.blockDim = dim3(gemm_threads(EPI));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  // (A cooperative launch would let the driver guarantee that the sibling CTAs of the fused-LayerNorm kernels are
-  // co-scheduled, but Nsight Compute cannot profile cooperative cluster launches; the grid is one CTA per SM, sized
-  // from the device, which gives the same guarantee on a GPU this process has to itself.)
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1 + pdl_launch_attr(&attr[1]);
+  if (gemm_epi_ln(EPI) && gemm_cooperative()) {
+    // The CTAs that own the column tiles of one row block spin on each other's LayerNorm statistics: they must all
+    // be resident. A cooperative launch makes the driver guarantee that (it places the whole grid at once, whatever
+    // else runs on the device — a second stream, NCCL's CTAs, MPS) or fail the launch loudly, instead of relying on
+    // the grid being sized to an otherwise idle GPU. VPB_COOP=0 launches normally (Nsight Compute cannot profile
+    // cooperative cluster launches).
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    cfg.numAttrs = 2;
+  } else {
+    cfg.numAttrs = 1 + pdl_launch_attr(&attr[1]);
+  }
   VPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps.a, maps.b, maps.out, maps.aux, maps.ln, pd));
   return 0;
 }
@@ -84,6 +93,15 @@ static long long* gemm_debug_buf(cudaStream_t stream, int bn, int epi) {
             buf[12], buf[13], buf[14]);
   }
   return buf;
+}
+
+static bool gemm_cooperative() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("VPB_COOP");
+    on = e ? atoi(e) : 1;
+  }
+  return on != 0;
 }
 
 // CTA pairs pay off on the large transformer GEMMs (full 256-wide N tiles, many tiles); everything else stays 1-CTA.

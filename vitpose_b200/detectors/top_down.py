@@ -78,9 +78,16 @@ class TopDown(nn.Module):
             losses.update(self.keypoint_head.get_accuracy(output, target, target_weight))
         return losses
 
-    @staticmethod
-    def _parse_losses(losses):
-        """mmpose/models/detectors/base.py:54-86 (single process: no all_reduce of the logged values)."""
+    # mmpose/models/detectors/base.py:66-74 turns every logged value into a Python float with one ``.item()`` (a
+    # device->host sync) and, when distributed, one all_reduce per value. Here the values are stacked, averaged over
+    # the ranks with ONE all_reduce (NCCL) and read back with ONE copy. ``log_vars_on_device = True`` skips the
+    # read-back and leaves 0-dim device tensors (no host sync in the step; not what an mmcv log buffer expects).
+    log_vars_on_device = False
+
+    def _parse_losses(self, losses):
+        """mmpose/models/detectors/base.py:37-76: ``loss`` = sum of the entries whose name contains 'loss';
+        ``log_vars`` = every entry (and the total), averaged over the ranks when torch.distributed is initialised."""
+        import torch.distributed as dist
         log_vars = {}
         for name, value in losses.items():
             if isinstance(value, torch.Tensor):
@@ -93,6 +100,19 @@ class TopDown(nn.Module):
                 raise TypeError(f'{name} is not a tensor or list of tensors or float')
         loss = sum(v for k, v in log_vars.items() if 'loss' in k)
         log_vars['loss'] = loss
+        names = [k for k, v in log_vars.items() if not isinstance(v, float)]
+        if names:
+            dev = next(v.device for v in (log_vars[k] for k in names))
+            packed = torch.stack([log_vars[k].detach().to(device=dev, dtype=torch.float32) for k in names])
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                packed = packed / dist.get_world_size()
+                dist.all_reduce(packed)
+            if self.log_vars_on_device:
+                for i, k in enumerate(names):
+                    log_vars[k] = packed[i]
+            else:
+                for k, v in zip(names, packed.tolist()):
+                    log_vars[k] = v
         return loss, log_vars
 
     def train_step(self, data_batch, optimizer=None, **kwargs):

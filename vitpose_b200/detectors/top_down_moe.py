@@ -52,8 +52,11 @@ class TopDownMoE(TopDown):
             idx = np.nonzero(src == d)[0]
             self._dataset_idx = d
             sel = torch.from_numpy(idx).to(img.device)
-            r = TopDown.forward_test(self, img.index_select(0, sel), [img_metas[i] for i in idx],
-                                     return_heatmap=return_heatmap, **kwargs)
+            # the reference flips the WHOLE batch back with img_metas[0]['flip_pairs'] (top_down_moe.py:229-232)
+            metas_d = [img_metas[i] for i in idx]
+            if 'flip_pairs' in img_metas[0]:
+                metas_d[0] = dict(metas_d[0], flip_pairs=img_metas[0]['flip_pairs'])
+            r = TopDown.forward_test(self, img.index_select(0, sel), metas_d, return_heatmap=return_heatmap, **kwargs)
             if merged is None:
                 merged = dict(preds=np.zeros((n,) + r['preds'].shape[1:], r['preds'].dtype),
                               boxes=np.zeros((n,) + r['boxes'].shape[1:], r['boxes'].dtype),

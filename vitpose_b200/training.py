@@ -13,6 +13,8 @@ Python too); there is no eager fallback.
 Numerics: GEMM operands and the activation gradients between operators are bf16, the residual stream, its
 gradient, all parameter gradients, LayerNorm / BatchNorm statistics and the optimizer state are fp32.
 """
+import os
+
 import torch
 
 from . import _lib, ops
@@ -114,6 +116,30 @@ def drop_path_scales(bb, n, device):
     blocks = getattr(bb, 'blocks', None)
     frozen = [blocks is not None and not blocks[i].training for i in range(bb.depth)]
     return [(None, None) if p <= 0.0 or frozen[i] else (masks[i, 0], masks[i, 1]) for i, p in enumerate(rates.tolist())]
+
+
+_GRAD_GROUPS = {}
+
+
+def gradient_process_group():
+    """(group, has_avg) for the gradient all-reduce. With the NCCL backend the exchange gets a communicator of its
+    own whose kernels are limited to ``VPB_NCCL_MAX_CTAS`` (default 8) CTAs through ``ncclConfig_t.maxCTAs``: the
+    all-reduce overlaps the persistent one-CTA-per-SM GEMMs of the backward pass, and NCCL's default channel count
+    takes more SMs away from them than the NVLink transfer needs (2 GPUs: 17.9 / 16.6 / 16.3 ms per step with 2 / 4 / 8
+    channels, 17.5 ms with the default). Other backends (gloo in the CPU tests) use the default group."""
+    dist = torch.distributed
+    key = dist.get_backend()
+    if key not in _GRAD_GROUPS:
+        group, has_avg = None, False
+        if key == 'nccl':
+            has_avg = True
+            max_ctas = int(os.environ.get('VPB_NCCL_MAX_CTAS', '8'))
+            if max_ctas > 0:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = max_ctas
+                group = dist.new_group(backend='nccl', pg_options=opts)     # collective: every rank gets here together
+        _GRAD_GROUPS[key] = (group, has_avg)
+    return _GRAD_GROUPS[key]
 
 
 def _param_list(model):
@@ -237,13 +263,26 @@ class _NetworkFn(torch.autograd.Function):
                 and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size()
         pending, sent = [], [0]
+        group, has_avg = gradient_process_group() if world > 1 else (None, False)
+        # optional bf16 exchange (VPB_GRAD_BF16=1 or model.grad_allreduce_dtype = torch.bfloat16): half the bytes on
+        # NVLink; the reference's DDP exchanges fp32, so fp32 stays the default
+        bf16_exchange = world > 1 and (getattr(model, 'grad_allreduce_dtype', None) == BF16 or
+                                       os.environ.get('VPB_GRAD_BF16', '0') == '1')
+        compressed = []
 
         def exchange(final=False):
-            """all-reduce the arena segment completed since the last call (at least 32 MB unless final)."""
+            """all-reduce (average) the arena segment completed since the last call (at least 32 MB unless final)."""
             if world == 1 or used[0] == sent[0] or (not final and (used[0] - sent[0]) * 4 < (32 << 20)):
                 return
+            dist = torch.distributed
             seg = arena[sent[0]:used[0]]
-            pending.append(torch.distributed.all_reduce(seg, op=torch.distributed.ReduceOp.SUM, async_op=True))
+            op = dist.ReduceOp.AVG if has_avg else dist.ReduceOp.SUM
+            if bf16_exchange:
+                half = seg.to(BF16)
+                compressed.append((seg, half))
+                pending.append(dist.all_reduce(half, op=op, group=group, async_op=True))
+            else:
+                pending.append(dist.all_reduce(seg, op=op, group=group, async_op=True))
             sent[0] = used[0]
 
         # ---- final 1x1 conv: rows = pixels, columns = keypoints (zero padded to a multiple of 8)
@@ -341,7 +380,9 @@ class _NetworkFn(torch.autograd.Function):
         exchange(final=True)
         for h in pending:
             h.wait()
-        if world > 1:
+        for seg, half in compressed:
+            seg.copy_(half)
+        if world > 1 and not has_avg:
             arena[:used[0]].mul_(1.0 / world)
         grads = []
         for nm, p in _param_list(model):
