@@ -8,6 +8,8 @@
 
 using namespace vpb;
 
+#include <stdlib.h>
+
 #include <vector>
 
 namespace {
@@ -212,6 +214,32 @@ int vpb_vitpose_forward(const vpb_model_desc* desc, const vpb_weights* w, const 
     }
   } else {
     VPB_REQUIRE(d.final_kernel == 3 && d.upsample > 0, "forward: simple decoder expects upsample + 3x3 final conv");
+    static int fused = -1;      // VPB_SIMPLE_FUSED=0: materialise the upsampled map and run the 3x3 implicit GEMM (A/B)
+    if (fused < 0) {
+      const char* e = getenv("VPB_SIMPLE_FUSED");
+      fused = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (fused && 9 * K <= 256 && (9 * T * (1 + d.upsample) + 2 * hp * d.upsample) * 4 <= 48 * 1024) {
+      // nine 1x1 convolutions on the token grid as ONE GEMM (final_w [K][9 * D] viewed as [9K, D]: row k * 9 + t),
+      // then the bilinear gather of the tap maps (elementwise.cu): the upsampled map is never materialised
+      void* r = base + ws.head_a;                                         // relu(features) bf16 [rows, D]
+      float* z = reinterpret_cast<float*>(base + ws.head_a + align_up(static_cast<size_t>(rows) * D * 2, 1024));
+      if (int e = prof_run("relu", stream, [&] { return relu_bf16(feat, r, static_cast<long long>(rows) * D, stream); })) return e;
+      if (int e = prof_run("simple_tap_gemm", stream, [&] {
+            return gemm_bf16(r, w->final_w, rows, 9 * K, D, EPI_NCHW_F32, nullptr, z, 0, nullptr, T, 0, stream);
+          }))
+        return e;
+      const int parts = split ? 2 : 1, per = images / parts;
+      for (int part = 0; part < parts; ++part) {
+        float* o = part == 0 ? heatmaps : heatmaps_flipped;
+        const float* zp = z + static_cast<size_t>(part) * per * 9 * K * T;
+        if (int e = prof_run("simple_gather", stream, [&] {
+              return simple_head_gather(zp, w->final_b, o, per, K, hp, wp, d.upsample, stream);
+            }))
+          return e;
+      }
+      return 0;
+    }
     void* up = base + ws.head_a;
     if (int e = prof_run("relu_upsample", stream, [&] { return relu_upsample_bilinear_nhwc(feat, up, images, hp, wp, D, d.upsample, stream); })) return e;
     const int parts = split ? 2 : 1, per = images / parts;

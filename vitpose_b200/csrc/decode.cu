@@ -19,7 +19,7 @@
 namespace vpb {
 
 constexpr int DEC_THREADS = 128;
-constexpr int DEC_MAX_PIX = 4096;   // 64x64 (the reference's KAT) >= 64x48
+constexpr int DEC_MAX_PIX = 16384;  // 128x96 (a three-deconv head) and the reference's 64x64 KAT; ViTPose maps are 64x48
 constexpr int DEC_MAX_TAPS = 31;
 
 struct DecodeParams {
@@ -502,6 +502,14 @@ int decode_heatmaps(const float* hm, const float* hm_flipped, const int* flip_in
   if (mode == DECODE_UNBIASED || mode == DECODE_UDP_DARK) gaussian_taps_host(p.ksize, p.taps);
   const bool need_aux = hm_flipped != nullptr || mode == DECODE_UNBIASED;
   const size_t smem = static_cast<size_t>((H * W + 3) & ~3) * sizeof(float) * (need_aux ? 2 : 1);
+  if (smem > 48 * 1024) {     // maps larger than 64 x 48 with a flipped partner: opt in to more dynamic shared memory
+    static bool configured = false;
+    if (!configured) {
+      VPB_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          2 * DEC_MAX_PIX * static_cast<int>(sizeof(float))));
+      configured = true;
+    }
+  }
   decode_kernel<<<N * K, DEC_THREADS, smem, stream>>>(p);
   VPB_CHECK_CUDA(cudaGetLastError());
   return 0;

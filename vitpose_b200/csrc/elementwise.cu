@@ -294,4 +294,117 @@ int relu_upsample_bilinear_nhwc(const void* in, void* out, int n, int h, int w, 
   return 0;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Simple decoder without the upsampled map. conv3x3(pad 1)(upsample_x4(relu(x))) is linear in r = relu(x) and the
+// bilinear upsample acts on every channel separately, so
+//   heatmap[k, Y, X] = bias[k] + sum_{tap t = (ky, kx)} [ (Y+ky-1, X+kx-1) inside the upsampled map ]
+//                                 * upsample(z_t[k])[Y+ky-1, X+kx-1],      z_t[k] = sum_c W[k, c, ky, kx] * r[c]
+// i.e. nine 1x1 convolutions on the 16 x 12 token grid (ONE GEMM with 9K output columns) followed by a gather that
+// interpolates the nine small maps. 16x fewer FLOPs than the convolution on the 64 x 48 map, the
+// [images, 64, 48, D] bf16 map (12.9 GB for ViTPose-L at 1024 crops + flips) is never written, and the interpolation
+// runs in fp32 instead of on a bf16-rounded map. (topdown_heatmap_simple_head.py:278-287 + final 3x3 conv :132-139)
+// -------------------------------------------------------------------------------------------------
+__global__ void relu_bf16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long long n_vec) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_vec) return;
+  uint4 v = __ldg(in + i);
+  uint32_t* w = &v.x;
+  const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(w + j);
+    x = __hmax2(x, zero);
+    w[j] = *reinterpret_cast<uint32_t*>(&x);
+  }
+  out[i] = v;
+}
+
+int relu_bf16(const void* in, void* out, long long n, cudaStream_t stream) {
+  VPB_REQUIRE(n > 0 && n % 8 == 0, "relu_bf16: element count %lld must be a positive multiple of 8", n);
+  const long long n_vec = n / 8;
+  relu_bf16_kernel<<<static_cast<unsigned>((n_vec + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), n_vec);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// z fp32 [images, K * 9, h * w] (column k * 9 + t of the tap GEMM, token-contiguous) -> out fp32 [images, K, h*f, w*f].
+// One CTA per (image, keypoint). The bilinear upsample is separable: the nine tap maps are first interpolated along x
+// into shared memory (u[t][i][xx], 9 x h x W values), then every output pixel needs 2 multiply-adds per tap with the
+// row weights of its three source rows (tables in shared memory) — ~40 instructions per pixel instead of ~250 with a
+// per-tap 2-D interpolation (1.06 -> see profiles/r02_summary.md for 1024 images x 17 keypoints).
+__global__ void __launch_bounds__(256) simple_head_gather_kernel(const float* __restrict__ z,
+                                                                  const float* __restrict__ bias, float* __restrict__ out,
+                                                                  int K, int h, int w, int f) {
+  extern __shared__ float s_dyn[];
+  const int img = blockIdx.x / K, k = blockIdx.x % K;
+  const int T = h * w, H = h * f, W = w * f;
+  float* s_z = s_dyn;                            // [9][h * w]
+  float* s_u = s_z + 9 * T;                      // [9][h][W]: tap maps interpolated along x
+  int* s_y0 = reinterpret_cast<int*>(s_u + 9 * h * W);   // [H]: upper source row (the lower one is min(y0 + 1, h - 1))
+  float* s_ly = reinterpret_cast<float*>(s_y0 + H);      // [H]: weight of the lower row
+  const float* src = z + (static_cast<size_t>(img) * K + k) * 9 * T;
+  for (int i = threadIdx.x; i < 9 * T; i += blockDim.x) s_z[i] = __ldg(src + i);
+  const float inv = 1.0f / f;
+  for (int y = threadIdx.x; y < H; y += blockDim.x) {
+    float sy = (y + 0.5f) * inv - 0.5f;          // PyTorch's area_pixel_compute_source_index (align_corners=False)
+    sy = sy < 0.f ? 0.f : sy;
+    const int y0 = static_cast<int>(sy);
+    s_y0[y] = y0;
+    s_ly[y] = sy - y0;
+  }
+  __syncthreads();
+  {
+    // (xx, ti) walked incrementally: no division by the run-time width in the loop
+    const int step_x = static_cast<int>(blockDim.x) % W, step_r = static_cast<int>(blockDim.x) / W;
+    int xx = static_cast<int>(threadIdx.x) % W, ti = static_cast<int>(threadIdx.x) / W;   // ti = t * h + i
+    for (int e = threadIdx.x; e < 9 * h * W; e += blockDim.x) {
+      float sx = (xx + 0.5f) * inv - 0.5f;
+      sx = sx < 0.f ? 0.f : sx;
+      const int x0 = static_cast<int>(sx), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+      const float lx = sx - x0;
+      const float* row = s_z + ti * w;
+      s_u[e] = (1.f - lx) * row[x0] + lx * row[x1];
+      xx += step_x;
+      ti += step_r;
+      if (xx >= W) { xx -= W; ++ti; }
+    }
+  }
+  __syncthreads();
+  const float b = bias != nullptr ? __ldg(bias + k) : 0.f;
+  float* o = out + (static_cast<size_t>(img) * K + k) * H * W;
+  const int step_x = static_cast<int>(blockDim.x) % W, step_y = static_cast<int>(blockDim.x) / W;
+  int X = static_cast<int>(threadIdx.x) % W, Y = static_cast<int>(threadIdx.x) / W;
+  for (int p = threadIdx.x; p < H * W; p += blockDim.x, X += step_x, Y += step_y) {
+    if (X >= W) { X -= W; ++Y; }
+    float acc = b;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = Y + ky - 1;
+      if (yy < 0 || yy >= H) continue;           // zero padding of the conv on the upsampled map
+      const int y0 = s_y0[yy], y1 = y0 + (y0 < h - 1 ? 1 : 0);
+      const float ly = s_ly[yy], hy = 1.f - ly;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = X + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        const float* u = s_u + (ky * 3 + kx) * h * W;
+        acc += hy * u[y0 * W + xx] + ly * u[y1 * W + xx];
+      }
+    }
+    o[p] = acc;
+  }
+}
+
+int simple_head_gather(const float* z, const float* bias, float* out, int images, int K, int h, int w, int factor,
+                       cudaStream_t stream) {
+  VPB_REQUIRE(images > 0 && K > 0 && factor >= 1, "simple_head_gather: bad shape");
+  const size_t smem = (static_cast<size_t>(9) * h * w + static_cast<size_t>(9) * h * w * factor + 2 * static_cast<size_t>(h) * factor) *
+                      sizeof(float);
+  VPB_REQUIRE(smem <= 48 * 1024, "simple_head_gather: token grid %d x %d (x%d) too large", h, w, factor);
+  simple_head_gather_kernel<<<static_cast<unsigned>(images) * K, 256, smem, stream>>>(z, bias, out, K, h, w, factor);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace vpb

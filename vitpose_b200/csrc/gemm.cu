@@ -123,6 +123,14 @@ int gemm_pick_cg(int M, int bn, int epilogue, int K) {
 int gemm_pick_bn(int N, int epilogue) {
   if (epilogue == EPI_NCHW_F32) return N <= 32 ? 32 : (N <= 144 ? 144 : 256);
   if (N % 256 == 0) return 256;
+  // wide but not a multiple of 256 (ViTPose-S qkv, N = 1152 = 4.5 tiles): a clipped last 256-wide tile on CTA pairs
+  // beats nine 128-wide single-CTA tiles (VPB_GEMM_WIDE=0 restores those, A/B)
+  static int wide = -1;
+  if (wide < 0) {
+    const char* e = getenv("VPB_GEMM_WIDE");
+    wide = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (wide && N >= 1024 && (N % 256) >= 128 && gemm_epi_staged(epilogue) && !gemm_epi_adds_tile(epilogue)) return 256;
   if (N % 128 == 0) return 128;
   if (N <= 64) return 64;
   return (N % 256) > 128 || N > 1024 ? 256 : 128;

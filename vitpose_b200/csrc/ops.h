@@ -51,6 +51,12 @@ int tokens_to_nchw_f32(const void* tokens, float* out, int n, int T, int D, cuda
 int relu_upsample_bilinear_nhwc(const void* in, void* out, int n, int h, int w, int C, int factor,
                                 cudaStream_t stream);
 
+// Simple decoder without the upsampled map (see elementwise.cu): relu on the bf16 features, then — after the tap GEMM
+// z = relu(x) . W9^T (fp32 [images, 9K, h*w]) — the bilinear gather of the nine tap maps + bias -> fp32 NCHW heatmaps
+int relu_bf16(const void* in, void* out, long long n, cudaStream_t stream);
+int simple_head_gather(const float* z, const float* bias, float* out, int images, int K, int h, int w, int factor,
+                       cudaStream_t stream);
+
 // ---- attention (attention.cu) ----
 // qkv bf16 [n, T, 3*heads*hd] (column order: which, head, d) -> out bf16 [n, T, heads*hd]
 int attention_fwd(const void* qkv, void* out, int n, int T, int heads, int hd, float scale, int max_ctas,

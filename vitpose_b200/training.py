@@ -122,18 +122,19 @@ _GRAD_GROUPS = {}
 
 
 def gradient_process_group():
-    """(group, has_avg) for the gradient all-reduce. With the NCCL backend the exchange gets a communicator of its
-    own whose kernels are limited to ``VPB_NCCL_MAX_CTAS`` (default 8) CTAs through ``ncclConfig_t.maxCTAs``: the
-    all-reduce overlaps the persistent one-CTA-per-SM GEMMs of the backward pass, and NCCL's default channel count
-    takes more SMs away from them than the NVLink transfer needs (2 GPUs: 17.9 / 16.6 / 16.3 ms per step with 2 / 4 / 8
-    channels, 17.5 ms with the default). Other backends (gloo in the CPU tests) use the default group."""
+    """(group, has_avg) for the gradient all-reduce. ``VPB_NCCL_MAX_CTAS=<n>`` gives the exchange an NCCL communicator
+    of its own whose kernels are limited to n CTAs (``ncclConfig_t.maxCTAs``), because the all-reduce overlaps the
+    persistent one-CTA-per-SM GEMMs of the backward pass. Measured in round 2 (2 GPUs, 64 crops per GPU, ReduceOp.AVG):
+    15.28 ms per step with NCCL's default CTA count, 15.79 ms with 8 CTAs (14.79 ms on one GPU) — the default is kept
+    (round 1, with a SUM + separate scaling pass: 17.5 ms default, 16.3 ms with 8 channels). Other backends (gloo in
+    the CPU tests) use the default group and SUM + scale."""
     dist = torch.distributed
     key = dist.get_backend()
     if key not in _GRAD_GROUPS:
         group, has_avg = None, False
         if key == 'nccl':
             has_avg = True
-            max_ctas = int(os.environ.get('VPB_NCCL_MAX_CTAS', '8'))
+            max_ctas = int(os.environ.get('VPB_NCCL_MAX_CTAS', '0'))
             if max_ctas > 0:
                 opts = dist.ProcessGroupNCCL.Options()
                 opts.config.max_ctas = max_ctas
