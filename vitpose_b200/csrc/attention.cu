@@ -517,20 +517,24 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
 // -------------------------------------------------------------------------------------------------------------
 constexpr int PP_QK_DEPTH = 2;
 __host__ __device__ constexpr int pp_v_depth(int hd) { return hd > 64 ? 2 : 3; }
-// output staging: 8 softmax warps x 32 rows, row pitch = HD * 2 + 16 bytes (conflict-free 16-byte row writes)
-__host__ __device__ constexpr int pp_stage_pitch(int hd) { return hd * 2 + 16; }
-__host__ __device__ constexpr int pp_stage_bytes(int hd) { return 8 * 32 * pp_stage_pitch(hd); }
+// output staging: one block of 32 rows per softmax warp; a warp stages HD / RS columns of its rows (row pitch = bytes of
+// those columns + 16: conflict-free 16-byte row writes)
+__host__ __device__ constexpr int pp_stage_pitch(int hd, int rs = 1) { return hd * 2 / rs + 16; }
+__host__ __device__ constexpr int pp_stage_bytes(int hd, int rs = 1) { return 8 * rs * 32 * pp_stage_pitch(hd, rs); }
 constexpr int PP_THREADS = 64 + 256;
-// EPIW: a third warpgroup (warps 10-13) drains O_g (tcgen05.ld, 1 / row sum, bf16, line-sized stores) for BOTH softmax
-// groups, so a softmax group goes from P(i) straight to the scores of unit i + 2: the per-group chain
-// softmax -> P.V -> epilogue (6900 cycles per unit, of which 3450 softmax) shrinks to softmax -> S(i+2).
-// EPIW layout: four warpgroups of 128 threads so that setmaxnreg can move registers between the roles:
-// warps 0-3 TMA / MMA (+ two idle warps), 4-7 and 8-11 the softmax groups, 12-15 the epilogue.
-__host__ __device__ constexpr int pp_threads(bool epiw) { return epiw ? 512 : PP_THREADS; }
-__host__ __device__ constexpr int pp_first_softmax_warp(bool epiw) { return epiw ? 4 : 2; }
+// RS = 2 ("row split", A/B variant, measured slower — see attention_fwd): TWO threads per query row in each softmax
+// group (8 warps per group; warps w and w + 4 of a group share a TMEM lane quarter and take keys [0, T/2) and
+// [T/2, T)), halving the per-thread work of the softmax and of the epilogue. The two threads of a row exchange their partial row maximum
+// and row sum through shared memory (one 64-thread named barrier per lane quarter, twice per unit); P of the second
+// half is written behind ITS OWN score columns ([T/2, T/2 + T/4)), so no thread overwrites scores another one still
+// reads, and P.V takes its K steps from the two pieces. Layout: warps 0-3 TMA / MMA / 2 idle (one warpgroup, so that
+// setmaxnreg can hand its registers to the sixteen softmax warps 4-19). (A separate epilogue warpgroup was tried first
+// in round 2 and dropped: 150.4 vs 139.0 us, profiles/r02_summary.md.)
+__host__ __device__ constexpr int pp_threads(int rs) { return rs == 2 ? 128 + 512 : PP_THREADS; }
+__host__ __device__ constexpr int pp_first_softmax_warp(int rs) { return rs == 2 ? 4 : 2; }
 
-template <int HD, int T_, bool EPIW>
-__global__ void __launch_bounds__(pp_threads(EPIW), 1)
+template <int HD, int T_, int RS>
+__global__ void __launch_bounds__(pp_threads(RS), 1)
 attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                           const __grid_constant__ CUtensorMap tm_qb, const __grid_constant__ CUtensorMap tm_kvb,
                           const AttnParams p, const int num_units) {
@@ -543,7 +547,8 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
   constexpr int Q_BYTES = ATT_BM * att2_row_bytes(HD), KV_BYTES = T * att2_row_bytes(HD);
   constexpr int QK_BYTES = Q_BYTES + KV_BYTES;
   constexpr int PP_V_DEPTH = pp_v_depth(HD);
-  constexpr int PITCH = pp_stage_pitch(HD);
+  constexpr int PITCH = pp_stage_pitch(HD, RS);
+  static_assert(RS == 1 || (RS == 2 && !O_ALIAS && T % 64 == 0 && HD % 32 == 0), "row split: head_dim 32 / 64 only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_qk = smem;
@@ -552,7 +557,8 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
   __shared__ uint64_t qk_full[PP_QK_DEPTH], qk_free[PP_QK_DEPTH], v_full[PP_V_DEPTH], v_free[PP_V_DEPTH];
   __shared__ uint64_t s_full[2], p_full[2], o_full[2], o_free[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_inv[2][2][EPIW ? ATT_BM : 1];   // EPIW: 1 / row sum of unit i at [i & 1][(i >> 1) & 1][row]
+  __shared__ float s_xmax[2][2][RS == 2 ? ATT_BM : 1];   // RS = 2: partial row maximum [group][key half][row]
+  __shared__ float s_xsum[2][2][RS == 2 ? ATT_BM : 1];   //         partial row sum
 
   const int q_tiles = (T + ATT_BM - 1) / ATT_BM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -584,9 +590,9 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     for (int s = 0; s < PP_V_DEPTH; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_free[s], 1); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
-      mbar_init(&p_full[g], 128);
+      mbar_init(&p_full[g], 128 * RS);
       mbar_init(&o_full[g], 1);
-      mbar_init(&o_free[g], 128);
+      mbar_init(&o_free[g], 128 * RS);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tm_q);
@@ -623,13 +629,12 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
   auto s_col = [&](int g) { return static_cast<uint32_t>(g * T); };
   auto o_col = [&](int g) { return static_cast<uint32_t>(O_ALIAS ? g * T + T / 2 : 2 * T + g * HD); };
 
-  constexpr int W0 = pp_first_softmax_warp(EPIW);
-  // EPIW: 512 threads start with 128 registers each; the softmax threads (two 32-column chunks of scores in flight
-  // plus the packed probabilities) get what the producer / issuer / idle warps and the epilogue do not need. Each
-  // setmaxnreg is the first instruction of its warpgroup's branch, so that the register allocation of the branch
-  // follows it.
-  if (warp < (EPIW ? 4 : 2)) {
-  if constexpr (EPIW) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  constexpr int W0 = pp_first_softmax_warp(RS);
+  // RS = 2: 640 threads start with 96 registers each; the softmax threads (two 32-column chunks of scores in flight plus
+  // the packed probabilities) get what the producer / issuer / idle warps do not need. Each setmaxnreg is the first
+  // instruction of its warpgroup's branch, so that the register allocation of the branch follows it.
+  if (warp < W0) {
+  if constexpr (RS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");   // 32 + 4 x 112 = 5 x 96: the CTA's own pool
   if (warp == 0) {
     if (lane == 0) {
       PP_TIMING_STATE;
@@ -696,9 +701,12 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
         const uint32_t va = smem_u32(s_v + sv * KV_BYTES);
 #pragma unroll
         for (int ks = 0; ks < ((p.dbg & 2) ? 0 : T / 16); ++ks) {
-          umma_bf16_ts(d, pa + ks * 8, umma_desc_mn_sw128(va + ks * 2048, KVA_BYTES), idesc_o, ks != 0);
+          // P (bf16 pairs, 8 columns per K = 16 step): one piece at column 0, or with RS = 2 one behind each half of the
+          // score columns (keys [0, T/2) at column 0, keys [T/2, T) at column T/2)
+          const uint32_t pcol = (RS == 2 && ks >= T / 32) ? T / 2 + (ks - T / 32) * 8 : ks * 8;
+          umma_bf16_ts(d, pa + pcol, umma_desc_mn_sw128(va + ks * 2048, KVA_BYTES), idesc_o, ks != 0);
           if constexpr (WIDE)
-            umma_bf16_ts(d + 64, pa + ks * 8, umma_desc_mn_sw32(va + KVA_BYTES + ks * 512), idesc_o16, ks != 0);
+            umma_bf16_ts(d + 64, pa + pcol, umma_desc_mn_sw32(va + KVA_BYTES + ks * 512), idesc_o16, ks != 0);
         }
         umma_commit(&o_full[g]);
         umma_commit(&v_free[sv]);
@@ -707,73 +715,19 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       if (timing) { for (int k = 0; k < 4; ++k) p.dbg_buf[2 + k] = t_acc[k]; }
     }
   }
-  } else if (EPIW && warp >= 12) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-    // ---- epilogue warpgroup: O_g of every unit (both groups, in unit order) -> out. o_free[g] is armed for these 128
-    // threads; the 1 / row sum of unit i was left in s_inv by the softmax thread of the same row before it arrived on
-    // p_full (arrive -> MMA thread's wait -> tcgen05.commit -> o_full orders the write before the read below), and is
-    // overwritten by softmax(i + 4) only after P.V(i + 2) was issued, i.e. after this thread's arrive on o_free.
-    const int quad = warp & 3;
-    const int r = quad * 32 + lane;
-    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    uint8_t* const stage = s_stage + (warp - 12) * 32 * PITCH;
-    PP_TIMING_STATE;
-    for (int i = 0; i < n_local; ++i) {
-      const int g = i & 1;
-      const int unit = blockIdx.x + i * gridDim.x;
-      const int qt = unit_qt(unit, i);
-      const int head = (unit / q_tiles) % p.heads;
-      const int crop = (unit / q_tiles) / p.heads;
-      const Placement pl = unit_rows(qt, i);
-      const bool warp_live = quad * 32 < pl.r_hi && quad * 32 + 32 > pl.r_lo && !(p.dbg & 1);
-      timed_wait(&o_full[g], (i >> 1) & 1, 2);
-      tc_fence_after();
-      if (warp_live) {
-        uint32_t o[HD];
-#pragma unroll
-        for (int c = 0; c < HD; c += 16)
-          tmem_ld_32x32b_x16(lane_base + o_col(g) + c, *reinterpret_cast<uint32_t(*)[16]>(&o[c]));
-        const float inv = s_inv[g][(i >> 1) & 1][r];
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&o_free[g]);
-#pragma unroll
-        for (int c = 0; c < HD; c += 8) {
-          uint32_t w4[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            w4[j] = pack_bf16x2(__uint_as_float(o[c + 2 * j]) * inv, __uint_as_float(o[c + 2 * j + 1]) * inv);
-          *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 2) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-        }
-        __syncwarp();
-        if (!(p.dbg & 8)) {
-          __nv_bfloat16* base = p.out + (static_cast<size_t>(crop) * T + pl.q0 + quad * 32) * p.ldo + head * HD;
-          constexpr int CH = HD / 8;
-#pragma unroll
-          for (int e = lane; e < 32 * CH; e += 32) {
-            const int row = e / CH, ch = e - row * CH;
-            const int rr = quad * 32 + row;
-            if (rr >= pl.r_lo && rr < pl.r_hi)
-              *reinterpret_cast<uint4*>(base + static_cast<size_t>(row) * p.ldo + ch * 8) =
-                  *reinterpret_cast<const uint4*>(stage + row * PITCH + ch * 16);
-          }
-        }
-        __syncwarp();                         // the staging block is rewritten by the next unit
-      } else {
-        tc_fence_before();
-        mbar_arrive(&o_free[g]);
-      }
-    }
-    if (timing && threadIdx.x == 384) { p.dbg_buf[8] = t_acc[2]; }
   } else {
-    if constexpr (EPIW) asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+    if constexpr (RS == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     PP_TIMING_STATE;
-    const int g = (warp - W0) >> 2;                 // softmax group: units i = g, g + 2, ...
+    const int g = (warp - W0) / (4 * RS);           // softmax group: units i = g, g + 2, ...
+    const int half = RS == 2 ? ((warp - W0) >> 2) & 1 : 0;   // RS = 2: which half of the keys / of the output columns
     const int quad = warp & 3;                      // TMEM lane quarter this warp may access
     const int r = quad * 32 + lane;                 // query row inside the tile
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const uint32_t S = lane_base + s_col(g), O = lane_base + o_col(g);
-    constexpr int NC = T / 32;
+    constexpr int NC = T / 32 / RS;                 // 32-column score chunks of this thread
+    constexpr int CB = T / RS;                      // RS = 2: the second thread of a row starts at score column T / 2
+    constexpr int OC = HD / RS;                     // output columns of this thread
+    const uint32_t S = lane_base + s_col(g) + half * CB, O = lane_base + o_col(g) + half * OC;
+    const int xbar = 1 + g * 4 + quad;              // RS = 2: named barrier of the two warps that share this lane quarter
 
     // The staged output block of a unit is written to global memory one unit later, while this group waits for the
     // next P.V to complete (it has nothing else to do then), instead of at the end of its own epilogue.
@@ -782,7 +736,7 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     int pend_lo = 0, pend_hi = 0;
     auto flush_pending = [&]() {
       if (pend_base != nullptr && !(p.dbg & 8)) {
-        constexpr int CH = HD / 8;            // 16-byte pieces per row
+        constexpr int CH = OC / 8;            // 16-byte pieces per (part of a) row
 #pragma unroll
         for (int e = lane; e < 32 * CH; e += 32) {
           const int row = e / CH, ch = e - row * CH;
@@ -797,6 +751,8 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     };
     const long long t_loop = timing ? clock64() : 0;
     long long t_body = 0;
+    // VPB_ATT_DEBUG & 2048 (experiment): start group 1 half a unit late, so that the two groups' exp2 phases (which
+    // share the four MUFU pipes) alternate instead of coinciding
     for (int i = g; i < n_local; i += 2) {
       const long long t_top = timing ? clock64() : 0;
       const int unit = blockIdx.x + i * gridDim.x;
@@ -812,6 +768,7 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       float inv = 0.f;
       const bool tlive = timing && warp_live;      // counters: s_full wait, softmax math, o_full wait, epilogue
       timed_wait(&s_full[g], ph, warp_live ? 0 : 4);
+      if ((p.dbg & 2048) && g == 1 && i == 1) __nanosleep(900);   // (experiment, see above; after the first S is there)
       long long t_mark = tlive ? clock64() : 0;
       tc_fence_after();
       if (warp_live) {
@@ -835,6 +792,11 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
           }
           mx = fmaxf(mx, fmaxf(m0, m1));
         }
+        }
+        if constexpr (RS == 2) {             // the other half of the keys: exchange the partial maxima
+          s_xmax[g][half][r] = mx;
+          asm volatile("bar.sync %0, 64;" ::"r"(xbar) : "memory");
+          mx = fmaxf(mx, s_xmax[g][half ^ 1][r]);
         }
         // pass 2: p = exp2(s * scale*log2e - max'), bf16 pairs written back over columns [16c, 16c + 16) — always
         // behind the columns still to be read
@@ -863,19 +825,20 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
           tmem_st_32x32b_x16(S + 16 * c, pk);
         }
         tmem_st_wait();
-        const float sum = (sum_a.x + sum_b.x) + (sum_a.y + sum_b.y);
+        float sum = (sum_a.x + sum_b.x) + (sum_a.y + sum_b.y);
+        if constexpr (RS == 2) {             // partial row sums (the barrier also orders the reads of s_xmax above
+          s_xsum[g][half][r] = sum;          // before the next unit's writes)
+          asm volatile("bar.sync %0, 64;" ::"r"(xbar) : "memory");
+          const float other = s_xsum[g][half ^ 1][r];
+          sum = half == 0 ? sum + other : other + sum;      // the same association in both threads of the row
+        }
         inv = 1.0f / sum;
-        if constexpr (EPIW) s_inv[g][ph][r] = inv;
-        if (p.lse != nullptr && row_live)
+        if (p.lse != nullptr && row_live && half == 0)
           p.lse[(static_cast<size_t>(crop) * p.heads + head) * T + token] = fmaf(mx, p.scale_log2e, log2f(sum));
       }
       tc_fence_before();            // our tcgen05.ld / st of S_g are complete and ordered before the arrive
       mbar_arrive(&p_full[g]);
       if (tlive) { t_acc[1] += clock64() - t_mark; t_acc[5] += 1; }
-      if constexpr (EPIW) {         // the epilogue warpgroup takes O_g from here
-        if (timing) t_body += clock64() - t_top;
-        continue;
-      }
       flush_pending();              // previous unit's output rows, while P.V of this one runs
 
       // epilogue: O_g / row sum -> bf16, one whole output row (HD * 2 bytes, contiguous) per thread
@@ -883,9 +846,9 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       t_mark = tlive ? clock64() : 0;
       tc_fence_after();
       if (warp_live) {
-        uint32_t o[HD];               // all loads in flight at once, one wait
+        uint32_t o[OC];               // all loads in flight at once, one wait
 #pragma unroll
-        for (int c = 0; c < HD; c += 16) tmem_ld_32x32b_x16(O + c, *reinterpret_cast<uint32_t(*)[16]>(&o[c]));
+        for (int c = 0; c < OC; c += 16) tmem_ld_32x32b_x16(O + c, *reinterpret_cast<uint32_t(*)[16]>(&o[c]));
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&o_free[g]);      // O_g is in registers: the next P.V (or S, when aliased) may overwrite it now
@@ -893,7 +856,7 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
         // instruction (measured: 38 of 115 us). Stage the warp's 32 rows in shared memory and write them back with
         // consecutive lanes on consecutive 16-byte pieces of a row: whole lines per instruction.
 #pragma unroll
-        for (int c = 0; c < HD; c += 8) {
+        for (int c = 0; c < OC; c += 8) {
           uint32_t w4[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -901,7 +864,7 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
           *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 2) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
         }
         __syncwarp();
-        pend_base = p.out + (static_cast<size_t>(crop) * T + pl.q0 + quad * 32) * p.ldo + head * HD;
+        pend_base = p.out + (static_cast<size_t>(crop) * T + pl.q0 + quad * 32) * p.ldo + head * HD + half * OC;
         pend_lo = pl.r_lo;
         pend_hi = pl.r_hi;
       } else {
@@ -913,8 +876,7 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     }
     flush_pending();
     if (timing && threadIdx.x == 32 * W0 + 64) {
-      for (int k = 0; k < 4; ++k)
-        if (!(EPIW && k == 2)) p.dbg_buf[6 + k] = t_acc[k];
+      for (int k = 0; k < 4; ++k) p.dbg_buf[6 + k] = t_acc[k];
       p.dbg_buf[10] = clock64() - t_start;
       p.dbg_buf[11] = n_local;
       p.dbg_buf[12] = t_acc[4];
@@ -930,13 +892,13 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
 
 #undef PP_TIMING_STATE
 
-template <int HD, int T_, bool EPIW>
+template <int HD, int T_, int RS>
 static int launch_attention_pingpong(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& tqb,
                                      const CUtensorMap& tkvb, const AttnParams& p, int max_ctas, cudaStream_t stream) {
   constexpr int smem = PP_QK_DEPTH * (ATT_BM + T_) * att2_row_bytes(HD) + pp_v_depth(HD) * T_ * att2_row_bytes(HD) +
-                       pp_stage_bytes(HD) + 1024;
+                       pp_stage_bytes(HD, RS) + 1024;
   static_assert(smem <= 227 * 1024 - 6 * 1024, "ping-pong attention tiles do not fit shared memory");
-  auto kern = attention_pingpong_kernel<HD, T_, EPIW>;
+  auto kern = attention_pingpong_kernel<HD, T_, RS>;
   static bool configured = false;
   if (!configured) {
     VPB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -948,7 +910,7 @@ static int launch_attention_pingpong(const CUtensorMap& tq, const CUtensorMap& t
   if (grid > units) grid = units;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(pp_threads(EPIW));
+  cfg.blockDim = dim3(pp_threads(RS));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1040,16 +1002,17 @@ int attention_fwd(const void* qkv, void* out, int n, int T, int heads, int hd, f
   if (max_ctas >= 0) {   // max_ctas < 0 selects the per-unit kernel (kept for head_dim > 64 and for A/B tests)
     int rc = 1;
     const bool pingpong = !(p.dbg & 256);     // VPB_ATT_DEBUG & 256: the single-group kernel (P through smem), for A/B
-    // VPB_ATT_DEBUG & 512: a separate epilogue warpgroup drains O_g (A/B; measured slower for head_dim 64 / 80:
-    // 150.4 vs 139.0 us at 512 image passes — the kernel is bound by the two tcgen05.ld passes over the scores,
-    // not by the softmax -> P.V -> epilogue chain)
-    const bool epiw = (p.dbg & 512) != 0;
+    // VPB_ATT_DEBUG & 512: two threads per query row (RS = 2), for A/B. Measured SLOWER (B200, 512 image passes:
+    // head_dim 64 166.1 vs 157.3 us, head_dim 32 211.6 vs 199.3 us): with half the work per thread the softmax phase of a
+    // unit still takes ~3200 cycles — while both groups are in it the four MUFU pipes are saturated (2 x 24576 exp2 per
+    // 3072 cycles at 16 / clk / SM), so more warps only add exchange barriers.
+    const bool split = (p.dbg & 512) != 0;
     if (pingpong && hd == 32 && T == 192)
-      rc = epiw ? launch_attention_pingpong<32, 192, true>(tq, tkv, tq, tkv, p, max_ctas, stream)
-                : launch_attention_pingpong<32, 192, false>(tq, tkv, tq, tkv, p, max_ctas, stream);
+      rc = split ? launch_attention_pingpong<32, 192, 2>(tq, tkv, tq, tkv, p, max_ctas, stream)
+                 : launch_attention_pingpong<32, 192, 1>(tq, tkv, tq, tkv, p, max_ctas, stream);
     if (pingpong && hd == 64 && T == 192)
-      rc = epiw ? launch_attention_pingpong<64, 192, true>(tq, tkv, tq, tkv, p, max_ctas, stream)
-                : launch_attention_pingpong<64, 192, false>(tq, tkv, tq, tkv, p, max_ctas, stream);
+      rc = split ? launch_attention_pingpong<64, 192, 2>(tq, tkv, tq, tkv, p, max_ctas, stream)
+                 : launch_attention_pingpong<64, 192, 1>(tq, tkv, tq, tkv, p, max_ctas, stream);
     // head_dim 80: O_g aliases the consumed half of S_g (2T + 2*80 > 512 TMEM columns), so S(i+2) is issued after the
     // epilogue of unit i has loaded O_g into registers; still 65.6 us vs 85.8 us for the single-group kernel at 128
     // image passes once the output stores were deferred
@@ -1058,8 +1021,7 @@ int attention_fwd(const void* qkv, void* out, int n, int T, int heads, int hd, f
       uint32_t box_qb[3] = {16, ATT_BM, 1}, box_kvb[3] = {16, (uint32_t)T, 1};
       if (make_tma_desc(&tqb, TMA_BF16, qkv, 3, dims, strides, box_qb, TMA_SWIZZLE_32B)) return -1;
       if (make_tma_desc(&tkvb, TMA_BF16, qkv, 3, dims, strides, box_kvb, TMA_SWIZZLE_32B)) return -1;
-      rc = epiw ? launch_attention_pingpong<80, 192, true>(tq, tkv, tqb, tkvb, p, max_ctas, stream)
-                : launch_attention_pingpong<80, 192, false>(tq, tkv, tqb, tkvb, p, max_ctas, stream);
+      rc = launch_attention_pingpong<80, 192, 1>(tq, tkv, tqb, tkvb, p, max_ctas, stream);
     }
     if (rc <= 0) return rc;
     if (hd == 32 && T == 192) rc = launch_attention_persistent<32, 192, 2>(tq, tkv, tq, tkv, p, max_ctas, stream);

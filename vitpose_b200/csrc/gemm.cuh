@@ -225,7 +225,8 @@ __device__ __forceinline__ void ln_row_stats(const GemmParams& p, int m_blk, int
       unsigned long long w = ld_relaxed_gpu_u64(part + j);
       uint32_t spins = 0;
       while ((static_cast<uint32_t>(w >> 32) & 0x80000000u) != tag) {
-        if (++spins > (1u << 24)) __trap();   // a sibling CTA never arrived: fail loudly instead of hanging
+        if (++spins > (1u << 22)) __trap();   // a sibling CTA never arrived: fail loudly instead of hanging
+        __nanosleep(32);                      // 128 threads polling L2 flat out cost power the MMAs need
         w = ld_relaxed_gpu_u64(part + j);
       }
       pm[j] = __uint_as_float(static_cast<uint32_t>(w));
