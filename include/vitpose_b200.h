@@ -224,6 +224,12 @@ int vpb_nchw_f32_to_rows_bf16(const float* in, void* out, int n, int K, int P, i
 int vpb_deconv_gather_x(const void* x, void* out, int n, int h, int w, int cin, void* stream);
 int vpb_deconv_gather_dy(const void* dy, void* out, int n, int h, int w, int cout, void* stream);
 int vpb_deconv_phase_dy(const void* dy, void* out, int n, int h, int w, int cout, void* stream);
+/* ConvTranspose2d weight fp32 [Cin, Cout, 4, 4] (nn.ConvTranspose2d layout, simple_head.py:324-333) -> the packed bf16
+ * operands in one launch: wp [4 phases][Cout][4 taps * Cin] (vpb_weights.deconv_w) and, unless NULL, wd [Cin][16 * Cout]
+ * with column (phase * 4 + tap) * Cout + co (B operand of the input gradient over vpb_deconv_gather_dy);
+ * vpb_deconv_unpack_wgrad maps a packed fp32 weight gradient [4][Cout][4 * Cin] back to [Cin, Cout, 4, 4]. */
+int vpb_deconv_pack_weight(const float* w, void* wp, void* wd, int cin, int cout, void* stream);
+int vpb_deconv_unpack_wgrad(const float* dwp, float* dw, int cin, int cout, void* stream);
 
 /* ---- post-decode evaluation step ----
  * Per-image rescoring + OKS NMS of the top-down COCO datasets (topdown_coco_dataset.py:476-503; oks_iou / oks_nms /

@@ -198,3 +198,21 @@ def test_cast_transpose_multi_matches_per_layer_ops():
         with torch.no_grad():
             for l in layers:
                 l.weight.mul_(1.5).add_(0.01)
+
+
+def test_deconv_weight_pack_kernels_match_torch_formulation():
+    """vpb_deconv_pack_weight / vpb_deconv_unpack_wgrad (one launch each) == engine.pack_deconv_weight,
+    pack_deconv_weight_dgrad and unpack_deconv_weight (the torch slice-copy formulations), bit for bit."""
+    from vitpose_b200.engine import pack_deconv_weight, pack_deconv_weight_dgrad, unpack_deconv_weight
+    g = torch.Generator().manual_seed(5)
+    for cin, cout in ((768, 256), (256, 256), (64, 32)):
+        w = (torch.randn(cin, cout, 4, 4, generator=g) * 0.05).to(_dev())
+        wp, wd = ops.deconv_pack_weight(w)
+        ref = pack_deconv_weight(w)
+        assert torch.equal(wp, ref)
+        assert torch.equal(wd, pack_deconv_weight_dgrad(ref))
+        wp2, none = ops.deconv_pack_weight(w, want_dgrad=False)
+        assert none is None and torch.equal(wp2, ref)
+        dwp = torch.randn(4, cout, 4 * cin, generator=g).to(_dev())
+        out = torch.empty(cin, cout, 4, 4, device=_dev())
+        assert torch.equal(ops.deconv_unpack_wgrad(dwp, out), unpack_deconv_weight(dwp))

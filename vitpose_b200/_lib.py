@@ -80,6 +80,8 @@ _SIGS = {
     'vpb_deconv_gather_x': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'vpb_deconv_gather_dy': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'vpb_deconv_phase_dy': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'vpb_deconv_pack_weight': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'vpb_deconv_unpack_wgrad': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'vpb_warp_affine_normalize': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                           ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p, c_void_p]),
     'vpb_joints_mse_loss': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,

@@ -434,6 +434,13 @@ int vpb_deconv_phase_dy(const void* dy, void* out, int n, int h, int w, int cout
   return deconv_phase_dy(dy, out, n, h, w, cout, as_stream(stream));
 }
 
+int vpb_deconv_pack_weight(const float* w, void* wp, void* wd, int cin, int cout, void* stream) {
+  return deconv_pack_weight(w, wp, wd, cin, cout, as_stream(stream));
+}
+int vpb_deconv_unpack_wgrad(const float* dwp, float* dw, int cin, int cout, void* stream) {
+  return deconv_unpack_wgrad(dwp, dw, cin, cout, as_stream(stream));
+}
+
 int vpb_warp_affine_normalize(const unsigned char* const* src_ptrs, const int32_t* src_hw, const double* inv_mats,
                               int n, int out_h, int out_w, const float* mean3, const float* std3, float* out,
                               void* stream) {

@@ -139,4 +139,9 @@ int oks_nms(const float* kpts, const double* areas, const double* box_scores, co
             int max_group, const double* var, double thr, int use_vis, double vis_thr, int rescore, int soft,
             int max_dets, double* scores_out, int* keep, int* keep_count, cudaStream_t stream);
 
+// ConvTranspose2d weight fp32 [Cin, Cout, 4, 4] -> packed bf16 operands (wp: forward, wd: input gradient, may be null)
+// and packed fp32 weight gradient [4][Cout][4 * Cin] -> [Cin, Cout, 4, 4] (train_bwd.cu)
+int deconv_pack_weight(const float* w, void* wp, void* wd, int cin, int cout, cudaStream_t stream);
+int deconv_unpack_wgrad(const float* dwp, float* dw, int cin, int cout, cudaStream_t stream);
+
 }  // namespace vpb

@@ -672,4 +672,56 @@ int deconv_phase_dy(const void* dy, void* out, int n, int h, int w, int cout, cu
   return 0;
 }
 
+// -------------------------------------------------------------------------------------------------------------
+// ConvTranspose2d weight [Cin, Cout, 4, 4] (fp32 master) <-> the packed layouts of the implicit GEMMs, one launch
+// each (the training step repacks the weights it has just updated every iteration; as 4 x 16 strided torch copies
+// this was the largest group of ATen kernels in the step):
+//   wp  bf16 [4 phases][Cout][4 taps * Cin]  forward B operand (include/vitpose_b200.h, vpb_weights.deconv_w)
+//   wd  bf16 [Cin][16 * Cout], column (phase * 4 + tap) * Cout + co: B operand of the input-gradient GEMM
+//   and back: packed weight gradient fp32 [4][Cout][4 * Cin] -> [Cin, Cout, 4, 4].
+// (phase, tap) <-> (kh, kw): py = 0: taps (ty 0, 1) read kh (1, 3); py = 1: kh (2, 0); same for x.
+// -------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void deconv_k_to_phase_tap(int k, int& par, int& tap) {
+  // kh 0 -> (py 1, ty 1), 1 -> (0, 0), 2 -> (1, 0), 3 -> (0, 1)
+  par = (k == 0 || k == 2) ? 1 : 0;
+  tap = (k == 0 || k == 3) ? 1 : 0;
+}
+__global__ void deconv_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
+                                          __nv_bfloat16* __restrict__ wd, int cin, int cout) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // over [cin, cout, 4, 4]
+  if (idx >= cin * cout * 16) return;
+  const int kw = idx & 3, kh = (idx >> 2) & 3, co = (idx >> 4) % cout, ci = (idx >> 4) / cout;
+  int py, ty, px, tx;
+  deconv_k_to_phase_tap(kh, py, ty);
+  deconv_k_to_phase_tap(kw, px, tx);
+  const int ph = py * 2 + px, t = ty * 2 + tx;
+  const __nv_bfloat16 v = __float2bfloat16_rn(__ldg(w + idx));
+  wp[(static_cast<size_t>(ph) * cout + co) * (4 * cin) + t * cin + ci] = v;
+  if (wd != nullptr) wd[static_cast<size_t>(ci) * (16 * cout) + (ph * 4 + t) * cout + co] = v;
+}
+__global__ void deconv_unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int cin, int cout) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // over [cin, cout, 4, 4]
+  if (idx >= cin * cout * 16) return;
+  const int kw = idx & 3, kh = (idx >> 2) & 3, co = (idx >> 4) % cout, ci = (idx >> 4) / cout;
+  int py, ty, px, tx;
+  deconv_k_to_phase_tap(kh, py, ty);
+  deconv_k_to_phase_tap(kw, px, tx);
+  dw[idx] = __ldg(dwp + (static_cast<size_t>(py * 2 + px) * cout + co) * (4 * cin) + (ty * 2 + tx) * cin + ci);
+}
+int deconv_pack_weight(const float* w, void* wp, void* wd, int cin, int cout, cudaStream_t stream) {
+  VPB_REQUIRE(cin > 0 && cout > 0 && static_cast<long long>(cin) * cout * 16 < (1ll << 31), "deconv_pack_weight: bad shape");
+  const int total = cin * cout * 16;
+  deconv_pack_weight_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(wp),
+                                                                     reinterpret_cast<__nv_bfloat16*>(wd), cin, cout);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int deconv_unpack_wgrad(const float* dwp, float* dw, int cin, int cout, cudaStream_t stream) {
+  VPB_REQUIRE(cin > 0 && cout > 0 && static_cast<long long>(cin) * cout * 16 < (1ll << 31), "deconv_unpack_wgrad: bad shape");
+  const int total = cin * cout * 16;
+  deconv_unpack_wgrad_kernel<<<(total + 255) / 256, 256, 0, stream>>>(dwp, dw, cin, cout);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace vpb

@@ -7,6 +7,7 @@ flip_back + shift + average + argmax + refinement + transform_preds on the devic
 copy is the [N,K,3] result (plus the averaged heatmap when ``return_heatmap=True``); the reference copies
 every heatmap twice and decodes in Python loops (simple_head.py:219,226; top_down_eval.py:598-617).
 """
+import os
 import warnings
 
 import numpy as np
@@ -82,7 +83,7 @@ class TopDown(nn.Module):
     # device->host sync) and, when distributed, one all_reduce per value. Here the values are stacked, averaged over
     # the ranks with ONE all_reduce (NCCL) and read back with ONE copy. ``log_vars_on_device = True`` skips the
     # read-back and leaves 0-dim device tensors (no host sync in the step; not what an mmcv log buffer expects).
-    log_vars_on_device = False
+    log_vars_on_device = os.environ.get('VPB_LOG_ON_DEVICE', '0') == '1'
 
     def _parse_losses(self, losses):
         """mmpose/models/detectors/base.py:37-76: ``loss`` = sum of the entries whose name contains 'loss';

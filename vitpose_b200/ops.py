@@ -342,3 +342,25 @@ def pose_pck_accuracy(output, target, weight, thr=0.05, normalize=None):
     check(lib().vpb_pose_pck_accuracy(ptr(pred), ptr(gt), ptr(w), N, K, n0, n1, float(thr), ptr(acc), ptr(avg),
                                       ptr(cnt), stream_ptr()), 'vpb_pose_pck_accuracy')
     return acc, avg, cnt
+
+
+def deconv_pack_weight(w, want_dgrad=True):
+    """ConvTranspose2d weight fp32 [Cin, Cout, 4, 4] -> (wp bf16 [4, Cout, 4*Cin], wd bf16 [Cin, 16*Cout] or None):
+    the forward and input-gradient operands of the transposed convolution, one launch (engine.pack_deconv_weight /
+    pack_deconv_weight_dgrad are the torch formulations, kept for the one-time inference repack and the tests)."""
+    _need(w, torch.float32, 'w')
+    cin, cout = w.shape[:2]
+    assert tuple(w.shape[2:]) == (4, 4) and w.is_contiguous()
+    wp = torch.empty(4, cout, 4 * cin, device=w.device, dtype=BF16)
+    wd = torch.empty(cin, 16 * cout, device=w.device, dtype=BF16) if want_dgrad else None
+    check(lib().vpb_deconv_pack_weight(ptr(w), ptr(wp), ptr(wd), cin, cout, stream_ptr()), 'vpb_deconv_pack_weight')
+    return wp, wd
+
+
+def deconv_unpack_wgrad(dwp, out):
+    """packed fp32 weight gradient [4, Cout, 4*Cin] -> ``out`` [Cin, Cout, 4, 4] (contiguous fp32)."""
+    _need(dwp, torch.float32, 'dwp'); _need(out, torch.float32, 'out')
+    cin, cout = out.shape[:2]
+    assert dwp.shape == (4, cout, 4 * cin) and out.is_contiguous() and dwp.is_contiguous()
+    check(lib().vpb_deconv_unpack_wgrad(ptr(dwp), ptr(out), cin, cout, stream_ptr()), 'vpb_deconv_unpack_wgrad')
+    return out

@@ -18,7 +18,6 @@ import os
 import torch
 
 from . import _lib, ops
-from .engine import pack_deconv_weight, pack_deconv_weight_dgrad, unpack_deconv_weight
 
 BF16 = torch.bfloat16
 EPI_BIAS, EPI_RESID, EPI_POS, EPI_NCHW = _lib.EPI_BIAS_BF16, _lib.EPI_RESID_F32, _lib.EPI_POS_F32, _lib.EPI_NCHW_F32
@@ -211,7 +210,7 @@ class _NetworkFn(torch.autograd.Function):
         for i in range(2):
             dw = head.deconv_layers[3 * i].weight.detach()
             bn = head.deconv_layers[3 * i + 1]
-            wp_ = pack_deconv_weight(dw)
+            wp_, wd_ = ops.deconv_pack_weight(dw.contiguous())     # forward + input-gradient operands, one launch
             raw = ops.deconv4x4s2_raw(cur, wp_)
             if bn.training:
                 mean, rstd = ops.bn_train_stats(raw, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
@@ -219,7 +218,7 @@ class _NetworkFn(torch.autograd.Function):
             else:
                 mean, rstd = bn.running_mean.detach().clone(), torch.rsqrt(bn.running_var.detach() + bn.eps)
             act = ops.bn_relu_fwd(raw, mean, rstd, bn.weight.detach(), bn.bias.detach())
-            hs.append(dict(x=cur, wp=wp_, raw=raw, mean=mean, rstd=rstd, bn=bn, frozen_stats=not bn.training))
+            hs.append(dict(x=cur, wp=wp_, wd=wd_, raw=raw, mean=mean, rstd=rstd, bn=bn, frozen_stats=not bn.training))
             cur = act
         fl = head.final_layer
         K = fl.weight.shape[0]
@@ -317,10 +316,10 @@ class _NetworkFn(torch.autograd.Function):
             dwp = scratch_zeros(4, cout, wp_.shape[2])
             for ph in range(4):
                 _wgrad(a_t[ph], b_t[ph], dwp[ph])
-            g[f'keypoint_head.deconv_layers.{3 * i}.weight'] = unpack_deconv_weight(
-                dwp, out=zeros(wp_.shape[2] // 4, cout, 4, 4))
+            g[f'keypoint_head.deconv_layers.{3 * i}.weight'] = ops.deconv_unpack_wgrad(
+                dwp, zeros(wp_.shape[2] // 4, cout, 4, 4))
             del a_t, b_t
-            dact = ops.gemm(ops.deconv_gather_dy(draw), pack_deconv_weight_dgrad(wp_), EPI_BIAS)   # [pixels_in, cin]
+            dact = ops.gemm(ops.deconv_gather_dy(draw), hsi['wd'], EPI_BIAS)             # [pixels_in, cin]
         # ---- last_norm, then the blocks in reverse
         exchange()
         dx = scratch_zeros(M, D)
