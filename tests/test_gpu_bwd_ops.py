@@ -203,6 +203,7 @@ def test_cast_transpose_multi_matches_per_layer_ops():
 def test_deconv_weight_pack_kernels_match_torch_formulation():
     """vpb_deconv_pack_weight / vpb_deconv_unpack_wgrad (one launch each) == engine.pack_deconv_weight,
     pack_deconv_weight_dgrad and unpack_deconv_weight (the torch slice-copy formulations), bit for bit."""
+    from vitpose_b200 import ops
     from vitpose_b200.engine import pack_deconv_weight, pack_deconv_weight_dgrad, unpack_deconv_weight
     g = torch.Generator().manual_seed(5)
     for cin, cout in ((768, 256), (256, 256), (64, 32)):

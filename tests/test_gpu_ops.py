@@ -98,7 +98,7 @@ def test_gemm_nchw_heatmap(Kout, C):
 @pytest.mark.parametrize('M,D,K,offset', [
     (192 * 3, 128, 128, 0.0), (192 * 5, 384, 384, 0.5), (192 * 7, 768, 768, 0.0), (192 * 40, 768, 3072, 3.0),
     (192 * 200, 768, 768, 0.5), (192 * 200, 768, 3072, 0.0), (192 * 33, 1024, 1024, 0.0), (192 * 64, 1280, 5120, 1.0),
-    (192, 768, 768, 0.0)])
+    (192, 768, 768, 0.0), (192 * 64, 384, 384, 0.5), (192 * 64, 384, 1536, 1.0)])
 def test_gemm_residual_layernorm_fused(M, D, K, offset):
     """x = x + a @ w^T + bias (fp32, in place) and xn = LayerNorm(x) * gamma + beta from ONE kernel, against the
     two-step fp32 reference; row means up to 3 sigma to exercise the (mean, M2) merge across column tiles."""

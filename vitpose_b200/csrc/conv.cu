@@ -18,7 +18,14 @@
 
 namespace vpb {
 
-constexpr int CV_THREADS = 192;
+// warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: two epilogue warpgroups. The accumulators (384 of the 512 TMEM
+// columns) are single-buffered, so the epilogue of an item is NOT overlapped with the next item's MMAs: the two groups
+// each drain half of the channels of every pixel tile (round 2; one group of four warps before).
+#ifndef VPB_CV_EPI_GROUPS
+#define VPB_CV_EPI_GROUPS 2
+#endif
+constexpr int CV_EPI_GROUPS = VPB_CV_EPI_GROUPS;
+constexpr int CV_THREADS = 64 + 128 * CV_EPI_GROUPS;
 constexpr int CV_SUB = 3;                 // 128-row sub-tiles per super tile
 constexpr int CV_ROWS = CV_SUB * 128;     // 384 pixels
 constexpr int MODE_DECONV = 0;
@@ -57,7 +64,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   __shared__ uint64_t tfull_bar, tempty_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_ss[2][2][BN];                 // [item parity][scale | shift][channel of the n-tile]
-  __shared__ __align__(16) uint8_t s_ostage[4][32 * 64];   // per epilogue warp: 32 pixels x 64 bytes (deconv stores)
+  __shared__ __align__(16) uint8_t s_ostage[4 * CV_EPI_GROUPS][32 * 64];   // per epilogue warp: 32 pixels x 64 bytes
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cin_chunks = p.cin / 64;
@@ -67,7 +74,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tfull_bar, 1);
-    mbar_init(&tempty_bar, 4);
+    mbar_init(&tempty_bar, 4 * CV_EPI_GROUPS);
     fence_mbar_init();
     tma_prefetch_desc(&tm_in);
     tma_prefetch_desc(&tm_w);
@@ -148,6 +155,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   } else {
     const int quad = warp & 3;
     const int etid = threadIdx.x - 64;
+    const int egrp = (warp - 2) >> 2;            // epilogue group: channel chunks egrp, egrp + CV_EPI_GROUPS, ...
     uint32_t acc_ph = 0;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
@@ -159,12 +167,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       // per-channel scale / shift (folded BN) or bias of this n-tile -> smem, double-buffered by item parity
       float* sc = s_ss[it & 1][0];
       float* sh = s_ss[it & 1][1];
-      for (int i = etid; i < BN; i += 128) {
+      for (int i = etid; i < BN; i += 128 * CV_EPI_GROUPS) {
         const int co = nt * BN + i;
         sc[i] = (p.scale != nullptr && co < p.cout) ? __ldg(p.scale + co) : 1.0f;
         sh[i] = (p.shift != nullptr && co < p.cout) ? __ldg(p.shift + co) : 0.0f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * CV_EPI_GROUPS) : "memory");
       mbar_wait(&tfull_bar, acc_ph);
       tc_fence_after();
 #pragma unroll 1
@@ -186,10 +194,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
           long long poff[4];                        // output offsets of the pixels this lane writes back
 #pragma unroll
           for (int j = 0; j < 4; ++j) poff[j] = __shfl_sync(0xffffffffu, my_off, 8 * j + (lane >> 2));
-          uint8_t* stage = s_ostage[quad];
+          uint8_t* stage = s_ostage[warp - 2];
           __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out);
 #pragma unroll 1
-          for (int c = 0; c < BN; c += 32) {
+          for (int c = 32 * egrp; c < BN; c += 32 * CV_EPI_GROUPS) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_row + c, r);
             tmem_ld_wait();
@@ -224,7 +232,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
           }
         } else {
 #pragma unroll 1
-          for (int c = 0; c < BN / 16; ++c) {
+          for (int c = egrp; c < BN / 16; c += CV_EPI_GROUPS) {
             uint32_t r[16];
             tmem_ld_32x32b_x16(t_row + c * 16, r);
             tmem_ld_wait();

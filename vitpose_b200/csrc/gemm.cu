@@ -113,6 +113,14 @@ int gemm_pick_cg(int M, int bn, int epilogue, int K) {
     forced = e ? atoi(e) : 0;
   }
   if (forced == 1) return 1;
+  // 128-wide pair tiles (M = 256 x N = 128 per pair) exist for the fused-LayerNorm epilogues only: ViTPose-S, D = 384
+  // = three 128-column tiles per row block (VPB_GEMM_PAIR128=0: single-CTA tiles as in round 1, A/B)
+  static int pair128 = -1;
+  if (pair128 < 0) {
+    const char* e = getenv("VPB_GEMM_PAIR128");
+    pair128 = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (bn == 128 && pair128 && gemm_epi_ln(epilogue) && !gemm_epi_pos(epilogue) && M >= 1024) return 2;
   if (!(bn == 256 && gemm_epi_staged(epilogue) && M >= 1024)) return 1;
   // measured (B200, M = 49152): qkv 1135 -> 1269, fc1 w/o GELU 1152 -> 1284, fc2 1080 -> 1218 TFLOP/s with pairs;
   // the short-K residual GEMM (attn.proj, K = D) is bound by its fp32 residual traffic and is ~3 % faster unpaired
@@ -179,6 +187,8 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue,
     if (bn == 256 && epilogue == EPI_POSTMA_LN_F32) return launch_gemm_inst<256, EPI_POSTMA_LN_F32, 2>(maps, p, max_ctas, stream);
     if (bn == 256 && epilogue == EPI_RESID_LNS_F32) return launch_gemm_inst<256, EPI_RESID_LNS_F32, 2>(maps, p, max_ctas, stream);
     if (bn == 256 && epilogue == EPI_POSTMA_LNS_F32) return launch_gemm_inst<256, EPI_POSTMA_LNS_F32, 2>(maps, p, max_ctas, stream);
+    if (bn == 128 && epilogue == EPI_RESID_LN_F32) return launch_gemm_inst<128, EPI_RESID_LN_F32, 2>(maps, p, max_ctas, stream);
+    if (bn == 128 && epilogue == EPI_RESID_LNS_F32) return launch_gemm_inst<128, EPI_RESID_LNS_F32, 2>(maps, p, max_ctas, stream);
     set_last_error("gemm: no CTA-pair kernel instance for BN=%d epilogue=%d", bn, epilogue);
     return -2;
   }
@@ -313,6 +323,7 @@ int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue
   // 0.211 ms unsplit, 0.240 ms split at M = 49152)
   const bool short_k = K < 1536;
   int cg = gemm_pick_cg(M, bn, EPI_RESID_LNS_F32, K);
+  if (bn == 128 && epilogue != EPI_RESID_F32) cg = 1;     // (128-wide pair tiles: residual epilogues only)
   const bool split = short_k && (bn <= 128 || cg == 2);
   const int epi = epilogue == EPI_RESID_F32 ? (split ? EPI_RESID_LNS_F32 : EPI_RESID_LN_F32)
                                             : (split ? EPI_POSTMA_LNS_F32 : EPI_POSTMA_LN_F32);
