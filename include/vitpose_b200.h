@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VPB_ABI_VERSION 1
+#define VPB_ABI_VERSION 2
 
 int vpb_abi_version(void);
 const char* vpb_last_error(void);
@@ -65,6 +65,17 @@ typedef struct vpb_block_weights {
   const void* fc2_w;  const float* fc2_b;    /* [D, 4D], [D]   (mlp.fc2)   */
 } vpb_block_weights;
 
+/* Optional per-Block operands of the "folded LayerNorm" forward (vpb_fold_layernorm_linear builds them): the two
+ * Linear layers that follow a LayerNorm (attn.qkv after norm1, mlp.fc1 after norm2, vit.py:138-139) then read the plain
+ * bf16 residual rows and apply the normalisation in their own epilogue,
+ *   LN(x) W^T + b = rstd * (x (gamma o W)^T - mean * s) + c,   s_n = sum_k (gamma o W)[n,k],  c_n = b_n + sum_k beta_k W[n,k],
+ * so that the GEMM in front (attn.proj / mlp.fc2 + residual) finishes each tile in one pass and no longer waits for
+ * its sibling tiles' row statistics. *_wf bf16 [N, D], *_s / *_c fp32 [N]. */
+typedef struct vpb_block_fold {
+  const void* qkv_wf; const float* qkv_s; const float* qkv_c;
+  const void* fc1_wf; const float* fc1_s; const float* fc1_c;
+} vpb_block_fold;
+
 /* Repacked weights (built once by the host side, vitpose_b200/engine.py: PackedWeights):
  *  patch_w  bf16 [D, 768]      = patch_embed.proj.weight.reshape(D, 3*16*16)
  *  pos      fp32 [T, D]        = pos_embed[0, 1:] + pos_embed[0, :1]           (vit.py:320)
@@ -79,6 +90,7 @@ typedef struct vpb_weights {
   const float* last_g; const float* last_b;
   const void* deconv_w[3]; const float* deconv_scale[3]; const float* deconv_shift[3];
   const void* final_w; const float* final_b;
+  const vpb_block_fold* fold;                /* HOST pointer to `depth` structs, or NULL: LayerNorm in the producing GEMM */
 } vpb_weights;
 
 /* Bytes of scratch `vpb_vitpose_forward` needs for `images` crops (count the flipped copies too). */
@@ -162,6 +174,25 @@ int vpb_gemm_bf16_layernorm(const void* A, const void* B, int M, int N, int K, i
                             float* out, const float* aux, int period, const float* gamma, const float* beta, float eps,
                             void* xn, void* scratch, size_t scratch_bytes, const float* row_scale, int rows_per_scale,
                             void* stream);
+/* Folded LayerNorm, the three pieces (see vpb_block_fold):
+ *  vpb_fold_layernorm_linear: W fp32 [N, K], bias [N] or NULL, gamma / beta [K] -> Wf bf16 [N, K], s [N], c [N];
+ *  vpb_gemm_bf16_resid_stats: out = aux + A.B^T + bias like vpb_gemm_bf16_layernorm (same epilogues), but xb receives
+ *    the PLAIN bf16 copy of the updated rows and `stats` one (mean, M2) float pair per row and column tile:
+ *    stats[(row * parts + tile) * 2 + {0, 1}], parts / part_cols from vpb_gemm_stats_layout(N, ...), rows padded to 128
+ *    (vpb_gemm_stats_bytes). Shapes the fused-LayerNorm tiles do not cover (N not a multiple of 192 / 256 / 128 ...)
+ *    return -2;
+ *  vpb_gemm_bf16_lnfold: out[M, N] bf16 = act(LN(x) W^T + b) from A = xb, B = Wf, (s, c), the statistics; epilogue =
+ *    VPB_EPI_BIAS_BF16 or VPB_EPI_GELU_BF16. K must equal parts * part_cols. */
+int vpb_fold_layernorm_linear(const float* W, const float* bias, const float* gamma, const float* beta, int N, int K,
+                              void* Wf, float* s, float* c, void* stream);
+int vpb_gemm_stats_layout(int N, int* parts, int* part_cols);
+size_t vpb_gemm_stats_bytes(int M, int N);
+int vpb_gemm_bf16_resid_stats(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias,
+                              float* out, const float* aux, int period, void* xb, void* stats, size_t stats_bytes,
+                              const float* row_scale, int rows_per_scale, void* stream);
+int vpb_gemm_bf16_lnfold(const void* A, const void* Wf, int M, int N, int K, int epilogue, const float* c,
+                         const float* s, const void* stats, int parts, int part_cols, float eps, void* out, int ldo,
+                         void* stream);
 int vpb_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int M, int D, float eps,
                        void* stream);
 int vpb_im2col_patch16(const float* img, void* patches, int n, int H, int W, int flip, void* stream);

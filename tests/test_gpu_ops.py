@@ -61,6 +61,26 @@ def test_gemm_gelu_bf16():
     _report('gemm+gelu', out, ref, 0.03)
 
 
+def test_gemm_gelu_values_exact_erf():
+    """The epilogue's GELU itself: an identity weight makes the pre-activations the (bf16) inputs, which sweep
+    [-9, 9] densely plus large magnitudes; against fp64 x Phi(x) the error must stay at float rounding level
+    before the bf16 rounding of the output."""
+    from vitpose_b200 import ops, _lib
+    K = 64
+    x = torch.cat([torch.linspace(-9, 9, 128 * K - 256), torch.tensor([0.0, -0.0, 1e-6, -1e-6, 30.0, -30.0, 1e4, -1e4]),
+                   torch.randn(248) * 3]).to(BF16).reshape(-1, K)
+    eye = torch.eye(K).to(BF16)
+    out = ops.gemm(x.to(_dev()), eye.to(_dev()), _lib.EPI_GELU_BF16, bias=torch.zeros(K, device=_dev()))
+    xd = x.double()
+    ref = 0.5 * xd * (1 + torch.erf(xd / math.sqrt(2)))
+    got = out.cpu().double()
+    # half a bf16 ulp of the exact value for the output rounding + 2e-6 for the formula (|error| <= 7e-7) and fp32
+    ulp = 2.0 ** (torch.floor(torch.log2(ref.abs().clamp_min(1e-30))) - 7)
+    tol = 0.5 * ulp + 2e-6
+    assert ((got - ref).abs() <= tol).all(), ((got - ref).abs() / tol).max()
+    assert (got[x.float() >= 30] == x.double()[x.float() >= 30]).all() and (got[x.float() <= -30] == 0).all()
+
+
 def test_gemm_residual_f32_inplace():
     from vitpose_b200 import ops, _lib
     M, N, K = 192 * 5, 768, 768
@@ -133,6 +153,84 @@ def test_gemm_pos_layernorm_fused():
     ref = (a.float() @ b.float().t() + bias).reshape(n, T, D) + pos
     _report('gemm+pos (ln variant)', out.reshape(n, T, D), ref, 2e-3, bf16_out=False)
     _report('fused layernorm', xn, F.layer_norm(out.cpu(), (D,), gamma, beta, 1e-6), 0.04)
+
+
+def test_fold_layernorm_linear():
+    """Wf = bf16(gamma o W), s = row sums of the ROUNDED Wf, c = b + W . beta (vpb_fold_layernorm_linear)."""
+    from vitpose_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    N, K = 2304, 768
+    w, bias = torch.randn(N, K, generator=g) / math.sqrt(K), torch.randn(N, generator=g)
+    gamma, beta = torch.randn(K, generator=g), torch.randn(K, generator=g)
+    wf, s, c = ops.fold_layernorm_linear(w.to(_dev()), bias.to(_dev()), gamma.to(_dev()), beta.to(_dev()))
+    ref_wf = (w * gamma).to(BF16)
+    assert torch.equal(wf.cpu(), ref_wf)
+    assert (s.cpu() - ref_wf.float().sum(1)).abs().max() < 1e-4
+    assert (c.cpu() - (bias + w @ beta)).abs().max() < 1e-4
+
+
+def _fold_check(M, D, K, N2, offset, epilogue, pos_period=0):
+    """producer (fp32 rows + plain bf16 copy + per-tile (mean, M2)) and consumer (LayerNorm applied in the epilogue of
+    the next Linear layer) of the folded LayerNorm, each against fp32 PyTorch on the same operands."""
+    from vitpose_b200 import ops, _lib
+    dev = _dev()
+    g = torch.Generator().manual_seed(M + D + K)
+    a, w = _rand_bf16((M, K), 31).to(dev), _rand_bf16((D, K), 32, 1.0 / math.sqrt(K)).to(dev)
+    bias = torch.randn(D, generator=g).to(dev)
+    if pos_period:
+        aux = torch.randn(pos_period, D, generator=g).to(dev)
+        out, xb, stats = ops.gemm_resid_stats(a, w, _lib.EPI_POS_F32, bias, aux, period=pos_period)
+        ref = (a.float() @ w.float().t() + bias).reshape(-1, pos_period, D) + aux
+        ref = ref.reshape(M, D)
+    else:
+        resid = (torch.randn(M, D, generator=g) * 2 + offset * 2).to(dev)
+        x = resid.clone()
+        out, xb, stats = ops.gemm_resid_stats(a, w, _lib.EPI_RESID_F32, bias, x, out=x)
+        assert out.data_ptr() == x.data_ptr()
+        ref = resid + a.float() @ w.float().t() + bias
+    torch.cuda.synchronize()
+    _report('fold producer rows', out, ref, 2e-3, bf16_out=False)
+    assert torch.equal(xb, out.to(BF16)), 'the bf16 copy must be the rounded fp32 rows'
+    parts, cols = ops.gemm_stats_layout(D)
+    assert parts * cols == D and stats.shape[1] == parts
+    tiles = out.reshape(M, parts, cols)
+    mean = tiles.mean(-1)
+    m2 = ((tiles - mean[..., None]) ** 2).sum(-1)
+    assert (stats[:M, :, 0] - mean).abs().max().item() < 1e-4 * (1 + abs(offset) * 2)
+    assert ((stats[:M, :, 1] - m2).abs() / m2.clamp_min(1.0)).max().item() < 1e-4
+    # consumer
+    w2 = (torch.randn(N2, D, generator=g) / math.sqrt(D)).to(dev)
+    b2 = torch.randn(N2, generator=g).to(dev)
+    gamma, beta = (1 + 0.3 * torch.randn(D, generator=g)).to(dev), (0.3 * torch.randn(D, generator=g)).to(dev)
+    wf, s, c = ops.fold_layernorm_linear(w2, b2, gamma, beta)
+    y = ops.gemm_lnfold(xb, wf, s, c, stats, epilogue=epilogue)
+    torch.cuda.synchronize()
+    # the same information the kernel has: statistics of the fp32 rows, the bf16-rounded rows and folded weight
+    mu, var = out.mean(-1, keepdim=True), out.var(-1, unbiased=False, keepdim=True)
+    rstd = torch.rsqrt(var + 1e-6)
+    ref_y = rstd * (xb.float() @ wf.float().t() - mu * s) + c
+    exact = F.layer_norm(out, (D,), gamma, beta, 1e-6) @ w2.t() + b2
+    if epilogue == _lib.EPI_GELU_BF16:
+        ref_y, exact = F.gelu(ref_y), F.gelu(exact)
+    _report('fold consumer (same operands)', y, ref_y, 0.03)
+    # against the unfolded fp32 evaluation: bf16 rounding of x (instead of LN(x)) scales with |mean| / sigma
+    _report('fold consumer (exact LN)', y, exact, 0.06 * (1 + abs(offset)))
+
+
+@pytest.mark.parametrize('M,D,K,N2,offset', [
+    (192 * 7, 768, 768, 2304, 0.0), (192 * 40, 768, 3072, 3072, 1.0), (192 * 5, 384, 384, 1152, 0.5),
+    (192 * 64, 384, 1536, 1536, 0.0), (192 * 33, 1024, 1024, 3072, 0.0), (192 * 16, 1280, 5120, 3840, 0.5),
+    (192, 768, 768, 768, 0.0), (1000, 768, 768, 2304, 0.0)])
+def test_gemm_folded_layernorm(M, D, K, N2, offset):
+    from vitpose_b200 import _lib
+    _fold_check(M, D, K, N2, offset, _lib.EPI_BIAS_BF16)
+
+
+def test_gemm_folded_layernorm_gelu_and_pos():
+    from vitpose_b200 import _lib
+    _fold_check(192 * 9, 768, 768, 3072, 0.0, _lib.EPI_GELU_BF16)
+    _fold_check(192 * 9, 768, 768, 2304, 0.0, _lib.EPI_BIAS_BF16, pos_period=192)
+    _fold_check(192 * 6, 384, 768, 1152, 0.0, _lib.EPI_BIAS_BF16, pos_period=192)
 
 
 @pytest.mark.parametrize('D', [128, 384, 768, 1024, 1280])

@@ -28,14 +28,15 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f'{name} declared in the header but not exported'
     assert set(declared) == set(_lib.EXPORTED_SYMBOLS)
-    assert _lib.lib().vpb_abi_version() == 1
+    assert _lib.lib().vpb_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
     # field order/size sanity: 13 int32/float fields + int32[3]
     assert ctypes.sizeof(_lib.ModelDesc) == 4 * 15
     assert ctypes.sizeof(_lib.BlockWeights) == 8 * 12
-    assert ctypes.sizeof(_lib.Weights) == 8 * (6 + 9 + 2)
+    assert ctypes.sizeof(_lib.BlockFold) == 8 * 6
+    assert ctypes.sizeof(_lib.Weights) == 8 * (6 + 9 + 2 + 1)
 
 
 def test_workspace_bytes_no_gpu_needed():

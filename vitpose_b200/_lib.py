@@ -29,11 +29,15 @@ class BlockWeights(ctypes.Structure):
                                         'ln2_g', 'ln2_b', 'fc1_w', 'fc1_b', 'fc2_w', 'fc2_b')]
 
 
+class BlockFold(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ('qkv_wf', 'qkv_s', 'qkv_c', 'fc1_wf', 'fc1_s', 'fc1_c')]
+
+
 class Weights(ctypes.Structure):
     _fields_ = [('patch_w', c_void_p), ('patch_b', c_void_p), ('pos', c_void_p),
                 ('blocks', ctypes.POINTER(BlockWeights)), ('last_g', c_void_p), ('last_b', c_void_p),
                 ('deconv_w', c_void_p * 3), ('deconv_scale', c_void_p * 3), ('deconv_shift', c_void_p * 3),
-                ('final_w', c_void_p), ('final_b', c_void_p)]
+                ('final_w', c_void_p), ('final_b', c_void_p), ('fold', ctypes.POINTER(BlockFold))]
 
 
 class VitposeLibError(RuntimeError):
@@ -103,6 +107,14 @@ _SIGS = {
     'vpb_gemm_bf16_layernorm': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                         c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_int,
                                         c_void_p]),
+    'vpb_fold_layernorm_linear': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                          c_void_p, c_void_p]),
+    'vpb_gemm_stats_layout': (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    'vpb_gemm_stats_bytes': (c_size_t, [c_int, c_int]),
+    'vpb_gemm_bf16_resid_stats': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                          c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
+    'vpb_gemm_bf16_lnfold': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_int, c_int, c_float, c_void_p, c_int, c_void_p]),
     'vpb_layernorm_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     'vpb_im2col_patch16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'vpb_attention': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
@@ -130,7 +142,7 @@ def lib():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    if L.vpb_abi_version() != 1:
+    if L.vpb_abi_version() != 2:
         raise VitposeLibError('ABI version mismatch between _lib.py and libvitpose_b200.so')
     _lib = L
     return L

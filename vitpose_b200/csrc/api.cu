@@ -145,10 +145,27 @@ int vpb_vitpose_forward(const vpb_model_desc* desc, const vpb_weights* w, const 
   void* ln_scratch = base + ws.ln_scratch;
   if (int e = gemm_ln_scratch_init(ln_scratch, rows, D, stream)) return e;
   unsigned epoch = 0;
+  // Folded LayerNorm (vpb_block_fold): the residual GEMMs leave plain bf16 rows + per-tile (mean, M2) and qkv / fc1
+  // normalise in their epilogue. The statistics live in the first half of the scratch above (the fused LayerNorm of the
+  // last fc2 — last_norm has no Linear layer behind it to fold into — runs as epoch 1 and uses the second half).
+  // Measured on ViTPose-B (profiles/r02_summary.md §8): proj -21 us, fc2 -6 us per launch, but qkv +17 us and fc1 +22 us
+  // (their epilogues gain an FFMA2 and a shared-memory read per pair of outputs on a power-capped GPU) -> the step is
+  // no faster. Kept behind VPB_LN_FOLD=1 (and only when the caller supplies w->fold).
+  static const bool fold_enabled = [] {
+    const char* e = getenv("VPB_LN_FOLD");
+    return e != nullptr && atoi(e) != 0;
+  }();
+  const int parts = gemm_ln_parts(D), part_cols = gemm_ln_part_cols(D);
+  const bool fold = fold_enabled && w->fold != nullptr && parts > 0 && parts <= 10 && T % 64 == 0 && D % 8 == 0;
+  void* stats = ln_scratch;
+  const LnFoldIn ln_in{stats, nullptr, parts, part_cols, d.ln_eps};
 
   // PatchEmbed (vit.py:159-165) + pos embed (vit.py:320) + blocks[0].norm1
   if (int e = prof_run("im2col", stream, [&] { return im2col_patch16(img, patches, n, d.img_h, d.img_w, flip, stream); })) return e;
   if (int e = prof_run("gemm_patch_ln", stream, [&] {
+        if (fold)
+          return gemm_bf16_ln(patches, w->patch_w, rows, D, 768, EPI_POS_F32, w->patch_b, x, w->pos, T, nullptr, nullptr,
+                              d.ln_eps, xn, nullptr, 0, 0, stream, nullptr, 0, stats);
         return gemm_bf16_ln(patches, w->patch_w, rows, D, 768, EPI_POS_F32, w->patch_b, x, w->pos, T, w->blocks[0].ln1_g,
                             w->blocks[0].ln1_b, d.ln_eps, xn, ln_scratch, ++epoch, 0, stream);
       }))
@@ -158,21 +175,43 @@ int vpb_vitpose_forward(const vpb_model_desc* desc, const vpb_weights* w, const 
   for (int l = 0; l < d.depth; ++l) {
     const vpb_block_weights& b = w->blocks[l];
     // x = x + proj(attn(LN1(x)))            (vit.py:138), then LN2(x) for the MLP
-    if (int e = prof_run("gemm_qkv", stream, [&] { return gemm_bf16(xn, b.qkv_w, rows, 3 * D, D, EPI_BIAS_BF16, b.qkv_b, qkv, 3 * D, nullptr, 0, 0, stream); }))
+    if (int e = prof_run("gemm_qkv", stream, [&] {
+          if (fold) {
+            LnFoldIn in = ln_in;
+            in.s = w->fold[l].qkv_s;
+            return gemm_bf16(xn, w->fold[l].qkv_wf, rows, 3 * D, D, EPI_BIAS_BF16, w->fold[l].qkv_c, qkv, 3 * D, nullptr, 0, 0,
+                             stream, &in);
+          }
+          return gemm_bf16(xn, b.qkv_w, rows, 3 * D, D, EPI_BIAS_BF16, b.qkv_b, qkv, 3 * D, nullptr, 0, 0, stream);
+        }))
       return e;
     if (int e = prof_run("attention", stream, [&] { return attention_fwd(qkv, attn, images, T, d.num_heads, hd, scale, 0, stream); })) return e;
     if (int e = prof_run("gemm_proj_ln", stream, [&] {
+          if (fold)
+            return gemm_bf16_ln(attn, b.proj_w, rows, D, D, EPI_RESID_F32, b.proj_b, x, x, 0, nullptr, nullptr, d.ln_eps, xn,
+                                nullptr, 0, 0, stream, nullptr, 0, stats);
           return gemm_bf16_ln(attn, b.proj_w, rows, D, D, EPI_RESID_F32, b.proj_b, x, x, 0, b.ln2_g, b.ln2_b, d.ln_eps, xn,
                               ln_scratch, ++epoch, 0, stream);
         }))
       return e;
     // x = x + fc2(gelu(fc1(LN2(x))))        (vit.py:139), then the next block's LN1 (or last_norm, vit.py:328)
-    if (int e = prof_run("gemm_fc1", stream, [&] { return gemm_bf16(xn, b.fc1_w, rows, d.mlp_hidden, D, EPI_GELU_BF16, b.fc1_b, hidden, d.mlp_hidden, nullptr,
-                          0, 0, stream); }))
+    if (int e = prof_run("gemm_fc1", stream, [&] {
+          if (fold) {
+            LnFoldIn in = ln_in;
+            in.s = w->fold[l].fc1_s;
+            return gemm_bf16(xn, w->fold[l].fc1_wf, rows, d.mlp_hidden, D, EPI_GELU_BF16, w->fold[l].fc1_c, hidden,
+                             d.mlp_hidden, nullptr, 0, 0, stream, &in);
+          }
+          return gemm_bf16(xn, b.fc1_w, rows, d.mlp_hidden, D, EPI_GELU_BF16, b.fc1_b, hidden, d.mlp_hidden, nullptr, 0, 0,
+                           stream);
+        }))
       return e;
     const float* ng = l + 1 < d.depth ? w->blocks[l + 1].ln1_g : w->last_g;
     const float* nb = l + 1 < d.depth ? w->blocks[l + 1].ln1_b : w->last_b;
     if (int e = prof_run("gemm_fc2_ln", stream, [&] {
+          if (fold && l + 1 < d.depth)
+            return gemm_bf16_ln(hidden, b.fc2_w, rows, D, d.mlp_hidden, EPI_RESID_F32, b.fc2_b, x, x, 0, nullptr, nullptr,
+                                d.ln_eps, xn, nullptr, 0, 0, stream, nullptr, 0, stats);
           return gemm_bf16_ln(hidden, b.fc2_w, rows, D, d.mlp_hidden, EPI_RESID_F32, b.fc2_b, x, x, 0, ng, nb, d.ln_eps, xn,
                               ln_scratch, ++epoch, 0, stream);
         }))
@@ -294,6 +333,33 @@ int vpb_gemm_bf16_layernorm(const void* A, const void* B, int M, int N, int K, i
   if (int e = gemm_ln_scratch_init(scratch, M, N, stream)) return e;
   return gemm_bf16_ln(A, B, M, N, K, epilogue, bias, out, aux, period, gamma, beta, eps, xn, scratch, 1u, 0, stream,
                       row_scale, rows_per_scale);
+}
+int vpb_fold_layernorm_linear(const float* W, const float* bias, const float* gamma, const float* beta, int N, int K,
+                              void* Wf, float* s, float* c, void* stream) {
+  return fold_layernorm_linear(W, bias, gamma, beta, N, K, Wf, s, c, as_stream(stream));
+}
+int vpb_gemm_stats_layout(int N, int* parts, int* part_cols) {
+  VPB_REQUIRE(parts && part_cols, "gemm_stats_layout: null argument");
+  *parts = N > 0 ? gemm_ln_parts(N) : 0;
+  *part_cols = N > 0 ? gemm_ln_part_cols(N) : 0;
+  return *parts > 0 ? 0 : -2;
+}
+size_t vpb_gemm_stats_bytes(int M, int N) { return M > 0 && N > 0 ? gemm_ln_stats_bytes(M, N) : 0; }
+int vpb_gemm_bf16_resid_stats(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias,
+                              float* out, const float* aux, int period, void* xb, void* stats, size_t stats_bytes,
+                              const float* row_scale, int rows_per_scale, void* stream) {
+  VPB_REQUIRE(M > 0 && N > 0, "gemm+stats: bad shape");
+  VPB_REQUIRE(stats != nullptr && gemm_ln_parts(N) > 0 && stats_bytes >= gemm_ln_stats_bytes(M, N),
+              "gemm+stats: statistics buffer too small (%zu < %zu)", stats_bytes, gemm_ln_stats_bytes(M, N));
+  return gemm_bf16_ln(A, B, M, N, K, epilogue, bias, out, aux, period, nullptr, nullptr, 0.f, xb, nullptr, 0, 0,
+                      as_stream(stream), row_scale, rows_per_scale, stats);
+}
+int vpb_gemm_bf16_lnfold(const void* A, const void* Wf, int M, int N, int K, int epilogue, const float* c,
+                         const float* s, const void* stats, int parts, int part_cols, float eps, void* out, int ldo,
+                         void* stream) {
+  VPB_REQUIRE(stats != nullptr && s != nullptr && c != nullptr, "gemm+folded layernorm: null argument");
+  const LnFoldIn in{stats, s, parts, part_cols, eps};
+  return gemm_bf16(A, Wf, M, N, K, epilogue, c, out, ldo, nullptr, 0, 0, as_stream(stream), &in);
 }
 size_t vpb_gemm_layernorm_scratch_bytes(int M, int N) { return M > 0 && N > 0 ? gemm_ln_scratch_bytes(M, N) : 0; }
 int vpb_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int M, int D, float eps,

@@ -407,4 +407,48 @@ int simple_head_gather(const float* z, const float* bias, float* out, int images
   return 0;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Weights of a Linear layer that applies the LayerNorm in front of it in its own epilogue (gemm.cuh, "folded"
+// LayerNorm): Wf = bf16(gamma o W), s_n = sum_k float(Wf[n, k]) (the rounded values the tensor cores multiply by, so that
+// the mean term cancels exactly), c_n = b_n + sum_k beta_k W[n, k]. One CTA per output row; one-time weight repack.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fold_ln_linear_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, int K,
+                                                             __nv_bfloat16* __restrict__ Wf, float* __restrict__ s_out,
+                                                             float* __restrict__ c_out) {
+  const int n = blockIdx.x;
+  const float* w = W + static_cast<size_t>(n) * K;
+  float s = 0.f, c = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float wk = __ldg(w + k);
+    const __nv_bfloat16 wf = __float2bfloat16_rn(wk * __ldg(gamma + k));
+    Wf[static_cast<size_t>(n) * K + k] = wf;
+    s += __bfloat162float(wf);
+    c = fmaf(__ldg(beta + k), wk, c);
+  }
+  __shared__ float red[2][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ss = 0.f, cc = 0.f;
+    for (int i = 0; i < 8; ++i) { ss += red[0][i]; cc += red[1][i]; }
+    s_out[n] = ss;
+    c_out[n] = cc + (bias != nullptr ? bias[n] : 0.f);
+  }
+}
+
+int fold_layernorm_linear(const float* W, const float* bias, const float* gamma, const float* beta, int N, int K,
+                          void* Wf, float* s, float* c, cudaStream_t stream) {
+  VPB_REQUIRE(N > 0 && K > 0 && W && gamma && beta && Wf && s && c, "fold_layernorm_linear: bad argument");
+  fold_ln_linear_kernel<<<N, 256, 0, stream>>>(W, bias, gamma, beta, K, reinterpret_cast<__nv_bfloat16*>(Wf), s, c);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace vpb

@@ -44,7 +44,7 @@ static int launch_gemm_inst(const GemmMaps& maps, const GemmParams& p, int max_c
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  if (gemm_epi_ln(EPI) && gemm_cooperative()) {
+  if (gemm_epi_ln(EPI) && p.ln_fold == 0 && gemm_cooperative()) {
     // The CTAs that own the column tiles of one row block spin on each other's LayerNorm statistics: they must all
     // be resident. A cooperative launch makes the driver guarantee that (it places the whole grid at once, whatever
     // else runs on the device — a second stream, NCCL's CTAs, MPS) or fail the launch loudly, instead of relying on
@@ -233,7 +233,7 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue,
 }
 
 int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, void* out, int ldo,
-              const float* aux, int period, int max_ctas, cudaStream_t stream) {
+              const float* aux, int period, int max_ctas, cudaStream_t stream, const LnFoldIn* ln) {
   VPB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   VPB_REQUIRE(K % 8 == 0, "gemm: K=%d must be a multiple of 8 (16-byte TMA row pitch)", K);
   VPB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
@@ -253,6 +253,17 @@ int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, c
   if (make_gemm_maps(&maps, A, B, M, N, K, K, K, bn, epilogue, out, ldo, aux, cg, period)) return -1;
   GemmParams p{M, N, K, bias, out, ldo, aux, period, 1, nullptr, 1, nullptr, nullptr, nullptr, 0, 0u, 0.0f};
   p.flags = gemm_flags();
+  if (ln != nullptr && ln->stats != nullptr) {     // A = plain bf16 rows of a residual stream, LayerNorm applied here
+    VPB_REQUIRE(epilogue == EPI_BIAS_BF16 || epilogue == EPI_GELU_BF16, "gemm: folded LayerNorm needs a bf16 epilogue");
+    VPB_REQUIRE(ln->s != nullptr && bias != nullptr && ln->parts >= 1 && ln->parts <= 10 && ln->part_cols > 0 &&
+                    ln->parts * ln->part_cols == K,
+                "gemm: folded LayerNorm: bad statistics layout (parts %d x %d columns, K = %d)", ln->parts, ln->part_cols, K);
+    p.ln_stats = reinterpret_cast<const float2*>(ln->stats);
+    p.ln_s = ln->s;
+    p.ln_parts = ln->parts;
+    p.ln_part_cols = ln->part_cols;
+    p.ln_eps = ln->eps;
+  }
   if (epilogue == EPI_ACCUM_F32) {
     VPB_REQUIRE(bias == nullptr && ldo % 4 == 0, "gemm: the accumulating epilogue takes no bias and needs ldo %% 4 == 0");
     // about two waves of CTAs, at least 8 K blocks (512 rows of the contraction) per split, every split non-empty
@@ -276,6 +287,10 @@ static size_t ln_region_words(int M, int N) {     // one 8-byte word per (row, n
   return (static_cast<size_t>(ln_row_blocks(M)) * 128 * n_tiles + 31) / 32 * 32;
 }
 size_t gemm_ln_scratch_bytes(int M, int N) { return 2 * ln_region_words(M, N) * 8; }
+// folded LayerNorm: column tiles per row the producer writes statistics for, their width, and the buffer size
+int gemm_ln_parts(int N) { return ln_bn(N) ? N / ln_bn(N) : 0; }
+int gemm_ln_part_cols(int N) { return ln_bn(N); }
+size_t gemm_ln_stats_bytes(int M, int N) { return static_cast<size_t>(ln_row_blocks(M)) * 128 * gemm_ln_parts(N) * 8; }
 // Launch e uses region e & 1 and expects tag (e >> 1) & 1 in the words its siblings write: region 1 (first used by
 // e = 1, tag 0) starts with all tag bits set, region 0 (first used by e = 2, tag 1) with all tag bits clear.
 int gemm_ln_scratch_init(void* scratch, int M, int N, cudaStream_t stream) {
@@ -288,12 +303,13 @@ int gemm_ln_scratch_init(void* scratch, int M, int N, cudaStream_t stream) {
 int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, float* out,
                  const float* aux, int period, const float* gamma, const float* beta, float eps, void* xn,
                  void* scratch, unsigned epoch, int max_ctas, cudaStream_t stream, const float* row_scale,
-                 int rows_per_scale) {
+                 int rows_per_scale, void* fold_stats) {
   VPB_REQUIRE(row_scale == nullptr || (rows_per_scale > 0 && epilogue == EPI_RESID_F32),
               "gemm+layernorm: row_scale needs rows_per_scale > 0 and the residual epilogue");
   VPB_REQUIRE(epilogue == EPI_RESID_F32 || epilogue == EPI_POS_F32, "gemm+layernorm: epilogue %d has no fused form",
               epilogue);
-  VPB_REQUIRE(gamma && beta && xn && out && aux, "gemm+layernorm: null argument");
+  const bool fold = fold_stats != nullptr;   // xn = plain bf16 copy of the rows + per-tile (mean, M2): see gemm.cuh
+  VPB_REQUIRE((fold || (gamma && beta)) && xn && out && aux, "gemm+layernorm: null argument");
   const int bn = ln_bn(N);
   static int disabled = -1;   // VPB_LN_FUSED=0: GEMM + separate LayerNorm kernel (A/B measurements)
   if (disabled < 0) {
@@ -301,9 +317,14 @@ int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue
     disabled = (e && atoi(e) == 0) ? 1 : 0;
   }
   const bool pos_ok = epilogue != EPI_POS_F32 || (period > 0 && period % 64 == 0);
-  const bool fused = !disabled && bn != 0 && pos_ok && scratch != nullptr && epoch > 0 && K % 8 == 0 && N % 8 == 0 &&
+  const bool fused = (fold || (!disabled && scratch != nullptr && epoch > 0)) && bn != 0 && pos_ok && K % 8 == 0 &&
+                     N % 8 == 0 &&
                      ((reinterpret_cast<uintptr_t>(aux) | reinterpret_cast<uintptr_t>(out) |
-                       reinterpret_cast<uintptr_t>(xn) | reinterpret_cast<uintptr_t>(scratch)) & 15) == 0;
+                       reinterpret_cast<uintptr_t>(xn) | reinterpret_cast<uintptr_t>(fold ? fold_stats : scratch)) & 15) == 0;
+  if (fold && !fused) {
+    set_last_error("gemm + folded layernorm: unsupported shape N=%d K=%d period=%d", N, K, period);
+    return -2;
+  }
   if (!fused && row_scale != nullptr) {
     set_last_error("gemm+layernorm: row_scale is only implemented in the fused kernel (N=%d K=%d)", N, K);
     return -2;
@@ -339,6 +360,10 @@ int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue
                reinterpret_cast<unsigned long long*>(scratch),
                ln_region_words(M, N), epoch, eps};
   p.flags = gemm_flags();
+  if (fold) {
+    p.ln_fold = 1;
+    p.ln_stats_out = reinterpret_cast<float2*>(fold_stats);
+  }
   return launch_gemm(maps, p, bn, epi, cg, max_ctas, stream);
 }
 

@@ -67,6 +67,19 @@ struct GemmParams {
   size_t ln_region;              // words per region
   unsigned ln_epoch;
   float ln_eps;
+  // "Folded" LayerNorm (round 2). The LayerNorm that follows a residual update is an affine map of the row followed
+  // by a Linear layer, so it can be applied AFTER that layer's GEMM:
+  //   LN(x) W^T + b = rstd * (x (gamma o W)^T - mean * s) + c,   s_n = sum_k (gamma o W)[n, k],  c_n = b_n + sum_k beta_k W[n, k]
+  // The producer (EPI_*_LN* with ln_fold != 0) writes the fp32 rows, their plain bf16 copy (the next GEMM's A operand)
+  // and one (mean, M2) pair per row and column tile — single pass, no exchange between CTAs, TMEM released as soon as
+  // the tile is in registers. The consumer (EPI_BIAS_BF16 / EPI_GELU_BF16 with ln_stats != null) merges the pairs of
+  // its rows and applies rstd, mean, s and c (passed as `bias`) in its epilogue.
+  int ln_fold;
+  float2* ln_stats_out;     // producer: [row blocks * 128, n_tiles]
+  const float2* ln_stats;   // consumer: [rows of A (padded to 128), ln_parts]
+  const float* ln_s;        // consumer: [N]
+  int ln_parts;             // consumer: column tiles per row of the producer
+  int ln_part_cols;         //           and their width
   // Pipeline-depth switches (gemm_flags(): VPB_GEMM_FLAGS overrides the default for A/B runs; results identical):
   int flags;
   // optional [32] cycle counters of CTA 0 (VPB_GEMM_DEBUG=1, printed by the next launch), see gemm.cu
@@ -97,6 +110,10 @@ __host__ __device__ constexpr int gemm_threads(int epi) {
   return 64 + 128 * gemm_epi_groups(epi) + (gemm_epi_adds_tile(epi) ? 32 : 0) + (gemm_ln_split(epi) ? 160 : 0);
 }
 constexpr int GEMM_RES_SLOTS = 4;   // upper bound (barrier arrays)
+// Dynamic shared memory a kernel may plan with: the 227 KB opt-in limit minus 3 KB for the static arrays (barriers,
+// bias / folded-LayerNorm columns). The dynamic array is declared __align__(1024) — ptxas pads the static part to the
+// next KB, so the 128B-swizzle tiles need no run-time alignment slack.
+constexpr int GEMM_SMEM_BUDGET = 232448 - 3072;
 constexpr int GEMM_STAGING_BYTES = GEMM_BM * 128;   // one [128 rows x 128 B] TMA-store box
 
 __host__ __device__ constexpr bool gemm_epi_staged(int epi) {
@@ -115,7 +132,7 @@ __host__ __device__ constexpr int gemm_stage_bytes(int bn, int cg = 1) { return 
 __host__ __device__ constexpr int gemm_split_stages(int bn, int cg) { return (cg == 2 && bn == 256) ? VPB_SPLIT_STAGES : 3; }
 __host__ __device__ constexpr int gemm_res_slots(int bn, int epi, int cg) {
   if (!gemm_ln_split(epi)) return gemm_epi_ln(epi) ? 3 : 4;
-  const int n = (230400 - gemm_split_stages(bn, cg) * gemm_stage_bytes(bn, cg) - 4096) / (2 * GEMM_STAGING_BYTES);
+  const int n = (GEMM_SMEM_BUDGET - gemm_split_stages(bn, cg) * gemm_stage_bytes(bn, cg) - 4096) / (2 * GEMM_STAGING_BYTES);
   return n > GEMM_RES_SLOTS ? GEMM_RES_SLOTS : n;
 }
 // shared memory for the epilogue: one staging box per bf16 epilogue group, or the residual ring (+ gamma/beta)
@@ -127,14 +144,13 @@ __host__ __device__ constexpr int gemm_epi_smem(int bn, int epi, int cg) {
                                                (gemm_epi_ln(epi) ? 2048 : 0));
 }
 __host__ __device__ constexpr int gemm_num_stages(int bn, int epi, int cg = 1) {
-  // 227 KB usable, minus 1 KB alignment slack and ~1 KB of static shared memory
   return gemm_ln_split(epi) ? gemm_split_stages(bn, cg)
-         : ((230400 - gemm_epi_smem(bn, epi, cg)) / gemm_stage_bytes(bn, cg)) > 8
+         : ((GEMM_SMEM_BUDGET - gemm_epi_smem(bn, epi, cg)) / gemm_stage_bytes(bn, cg)) > 8
              ? 8
-             : ((230400 - gemm_epi_smem(bn, epi, cg)) / gemm_stage_bytes(bn, cg));
+             : ((GEMM_SMEM_BUDGET - gemm_epi_smem(bn, epi, cg)) / gemm_stage_bytes(bn, cg));
 }
 __host__ __device__ constexpr int gemm_smem_bytes(int bn, int epi, int cg = 1) {
-  return gemm_num_stages(bn, epi, cg) * gemm_stage_bytes(bn, cg) + gemm_epi_smem(bn, epi, cg) + 1024;
+  return gemm_num_stages(bn, epi, cg) * gemm_stage_bytes(bn, cg) + gemm_epi_smem(bn, epi, cg);
 }
 // Decoupled operand rings (CTA pairs, 256-wide tiles): the A tiles (activations, streamed from HBM: ~2 us under load)
 // and the B tiles (weights, L2-resident: a fraction of that) get rings of their own depth in the same shared memory,
@@ -161,26 +177,22 @@ __host__ __device__ constexpr int gemm_a_stages(int bn, int epi, int cg) {
          (GEMM_BM * 128);
 }
 
-// Exact-erf GELU (nn.GELU default) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. float
-// rounding level): erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p z), z >= 0.
-// ~17 issue slots per element instead of ~40 for erff(): the fc1 epilogue must stay under the tile's MMA time.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float e = fast_ex2(-1.4426950408889634f * z * z);
-  const float erf_abs = fmaf(-poly, e, 1.0f);          // erf(|x|/sqrt2) in [0, 1]
-  const float half_x = 0.5f * x;
-  return fmaf(half_x, copysignf(erf_abs, x), half_x);  // 0.5 x (1 + erf(x/sqrt2))
-}
+// Exact-erf GELU (nn.GELU default), gelu(x) = x Phi(x), written as
+//   gelu(x) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt 2),      erfc(a / sqrt 2) ~= exp2(q(a)),
+// q = the degree-5 polynomial below (no constant term; minimax fit of the ABSOLUTE error of gelu over a in [0, 9],
+// tools/fit_gelu.py): |error| <= 7e-7 for every finite input — float rounding level, the same as the Abramowitz &
+// Stegun 7.1.26 form the round-1 kernel used — with ONE MUFU op (ex2) per element instead of two (rcp + ex2) and 13
+// issue slots per PAIR of elements instead of 22: the fc1 epilogue is what the tile's MMA loop waits for.
+// q is strictly decreasing on [0, inf) and -> -inf, so large |x| give erfc = 0 exactly (gelu = max(x, 0)).
+#ifndef VPB_GELU_AS
+#define VPB_GELU_AS 0      // 1: the Abramowitz & Stegun form (A/B measurements)
+#endif
+constexpr float GELU_Q1 = -1.1510006189346313f, GELU_Q2 = -0.4595956802368164f, GELU_Q3 = -0.05214685946702957f,
+                GELU_Q4 = 0.007198837120085955f, GELU_Q5 = -0.000488122837850824f;
 
-// Same formula on two elements at once with Blackwell's packed fp32 pipe (FFMA2/FMUL2/FADD2): the FMA-pipe
-// instruction count per element halves; the two MUFU ops (rcp, ex2) per element stay scalar.
+// two elements at once on Blackwell's packed fp32 pipe (FFMA2 / FMUL2 / FADD2); the MUFU ops stay scalar
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
+#if VPB_GELU_AS
   const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
   const float2 z = __fmul2_rn(ax, make_float2(0.70710678118654752f, 0.70710678118654752f));
   const float2 den = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
@@ -197,6 +209,17 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   const float2 half_x = __fmul2_rn(x, make_float2(0.5f, 0.5f));
   const float2 erf_s = make_float2(copysignf(erf_abs.x, x.x), copysignf(erf_abs.y, x.y));
   return __ffma2_rn(half_x, erf_s, half_x);
+#else
+  const float2 a = make_float2(fabsf(x.x), fabsf(x.y));
+  float2 q = __ffma2_rn(make_float2(GELU_Q5, GELU_Q5), a, make_float2(GELU_Q4, GELU_Q4));
+  q = __ffma2_rn(q, a, make_float2(GELU_Q3, GELU_Q3));
+  q = __ffma2_rn(q, a, make_float2(GELU_Q2, GELU_Q2));
+  q = __ffma2_rn(q, a, make_float2(GELU_Q1, GELU_Q1));
+  q = __fmul2_rn(q, a);
+  const float2 e = make_float2(fast_ex2(q.x), fast_ex2(q.y));            // erfc(|x| / sqrt 2)
+  const float2 t = __fmul2_rn(__fmul2_rn(a, make_float2(-0.5f, -0.5f)), e);
+  return __ffma2_rn(__fadd2_rn(x, a), make_float2(0.5f, 0.5f), t);       // 0.5 (x + |x|) = max(x, 0), exactly
+#endif
 }
 
 // Fused-LayerNorm statistics exchange: one 8-byte word per (row, n-tile) = {mean, M2 | tag << 31}; 8-byte accesses
@@ -284,8 +307,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   static_assert(!STAGED || BN % CHUNK == 0, "staged epilogue needs BN to be a multiple of the chunk width");
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0) __trap();   // (the swizzled TMA boxes rely on it)
   // staging boxes of [128 rows x 128 B]: one per epilogue group (bf16), or the in-place residual ring (fp32)
   uint8_t* s_out = smem + STAGES * STAGE_BYTES;
   constexpr int RING_BYTES = RES_SLOTS * GEMM_STAGING_BYTES;  // per tile group
@@ -301,6 +325,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   __shared__ uint32_t tmem_slot;
   constexpr int BIAS_PER_GROUP = (BN / CHUNK + GROUPS - 1) / GROUPS * CHUNK;   // columns a group's chunks cover
   __shared__ __align__(16) float s_bias[LN_SPLIT ? 2 : GROUPS][STAGED ? BIAS_PER_GROUP : 1];
+  // consumer of a folded LayerNorm: s_n of this group's columns (bf16 epilogues only)
+  __shared__ __align__(16) float s_lns[GROUPS][(STAGED && !gemm_epi_adds_tile(EPI)) ? BIAS_PER_GROUP : 1];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -512,11 +538,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint8_t* ring = s_out + tg * RING_BYTES;
       constexpr int NX = BN / 32, NCH = NX + (LN ? BN / 64 : 0);     // chunks per tile
       const int first_tile = tile0 + tg * tile_step, stride = tile_step * TG;
-      auto load = [&](int tile, int c, uint32_t slot) {
-        if (c >= NX) {                      // bf16 LayerNorm box: the slot only has to be free
+      // Order of a tile's chunks through the ring. Fused LayerNorm: the NX fp32 chunks, then the BN / 64 bf16 boxes
+      // (pass 2). Folded LayerNorm: the bf16 box of 64 columns right after its two fp32 chunks.
+      const bool fold = LN && p.ln_fold != 0;
+      auto seq_is_box = [&](int q) { return LN && (fold ? (q % 3) == 2 : q >= NX); };
+      auto seq_index = [&](int q) { return fold ? ((q % 3) == 2 ? q / 3 : (q / 3) * 2 + (q % 3)) : (q >= NX ? q - NX : q); };
+      auto load = [&](int tile, int q, uint32_t slot) {
+        if (seq_is_box(q)) {                // bf16 box: the slot only has to be free
           mbar_arrive(&res_full[tg][slot]);
           return;
         }
+        const int c = seq_index(q);
         const int m_blk = ((tile / p.ksplit) / n_tiles) * CG + cta_rank;
         const int n_blk = (tile / p.ksplit) % n_tiles;
         mbar_arrive_expect_tx(&res_full[tg][slot], GEMM_STAGING_BYTES);
@@ -552,10 +584,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         twait(&res_ready[tg][slot], (nst / RES_SLOTS) & 1, w_ready);  // the epilogue has finished chunk nst in place
         const int m_blk = ((st_tile / p.ksplit) / n_tiles) * CG + cta_rank;
         const int n_blk = (st_tile / p.ksplit) % n_tiles;
-        if (st_c < NX)
-          tma_store_2d(&tma_out, ring + slot * GEMM_STAGING_BYTES, n_blk * BN + st_c * 32, m_blk * GEMM_BM);
+        if (!seq_is_box(st_c))
+          tma_store_2d(&tma_out, ring + slot * GEMM_STAGING_BYTES, n_blk * BN + seq_index(st_c) * 32, m_blk * GEMM_BM);
         else
-          tma_store_2d(&tma_ln, ring + slot * GEMM_STAGING_BYTES, n_blk * BN + (st_c - NX) * 64, m_blk * GEMM_BM);
+          tma_store_2d(&tma_ln, ring + slot * GEMM_STAGING_BYTES, n_blk * BN + seq_index(st_c) * 64, m_blk * GEMM_BM);
         tma_store_commit();
         if (p.flags & GEMM_FLAG_WAIT0) {    // this store has read its slot (a few hundred cycles): reload it now
           const long long t0 = timing ? clock64() : 0;
@@ -616,14 +648,44 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           for (int i = etid; i < BIAS_PER_GROUP; i += 128) {
             const int col = n_blk * BN + ((i / CHUNK) * GROUPS + cgrp) * CHUNK + (i % CHUNK);
             s_bias[grp][i] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+            if constexpr (!gemm_epi_adds_tile(EPI))
+              s_lns[grp][i] = (p.ln_s != nullptr && col < p.N) ? __ldg(p.ln_s + col) : 0.0f;
           }
           if constexpr (LN) {
+            if (p.ln_fold == 0)     // (the folded form leaves gamma / beta to the consumer's weights)
             for (int i = etid; i < BN; i += 128) {
               s_gamma[i] = __ldg(p.ln_gamma + n_blk * BN + i);
               s_beta[i] = __ldg(p.ln_beta + n_blk * BN + i);
             }
           }
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // constants visible to the whole group
+        }
+        // ---- consumer side of a folded LayerNorm: (mean, M2) pairs of this thread's row of A, merged over the producer's
+        // column tiles. Requested BEFORE the wait for the accumulator so that the L2 round trip hides behind it.
+        float ln_rstd = 1.0f, ln_nmr = 0.0f;
+        const bool ln_in = !gemm_epi_adds_tile(EPI) && p.ln_stats != nullptr;
+        if (ln_in) {
+          const int row = min(m_blk * GEMM_BM + r, p.M - 1);
+          const float2* st = p.ln_stats + static_cast<size_t>(row) * p.ln_parts;
+          float pm[10], pq[10], mu = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 10; ++j)
+            if (j < p.ln_parts) {
+              const float2 w = __ldg(st + j);
+              pm[j] = w.x;
+              pq[j] = w.y;
+              mu += w.x;
+            }
+          mu /= static_cast<float>(p.ln_parts);
+          float var = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 10; ++j)
+            if (j < p.ln_parts) {
+              const float dm = pm[j] - mu;
+              var += pq[j] + static_cast<float>(p.ln_part_cols) * dm * dm;
+            }
+          ln_rstd = rsqrtf(var / static_cast<float>(p.ln_parts * p.ln_part_cols) + p.ln_eps);
+          ln_nmr = -mu * ln_rstd;
         }
         twait(&tfull_bar[acc], acc_phase, w_tfull);
         ++n_epi_tiles;
@@ -634,6 +696,91 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (lane == 0) arrive_tempty(acc);
         }
         if constexpr (LN) {
+          if (p.ln_fold != 0) {
+            // ---- folded LayerNorm: ONE pass. x' = residual + acc + bias goes out as fp32 through the in-place ring
+            // and as bf16 (64-column boxes through the same ring, right after their two fp32 chunks); the row's
+            // (mean, M2) over this tile's columns is left for the consumer GEMM. TMEM is free after the last load.
+            float mean = 0.0f, m2 = 0.0f;
+            uint32_t va[32], vb[32], pk[32];
+            auto fold_chunk = [&](uint32_t(&v)[32], int c, uint32_t* pkh) {
+              const uint32_t buf = chunk_seq % RES_SLOTS;
+              const uint32_t srow = smem_u32(ring) + buf * GEMM_STAGING_BYTES + r * 128;
+              const float4* bias4 = reinterpret_cast<const float4*>(&s_bias[grp][c * 32]);
+              twait(&rfull[buf], (chunk_seq / RES_SLOTS) & 1, w_rfull);
+              float2 s0 = make_float2(0.0f, 0.0f), s1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const uint32_t pu = srow + ((u ^ (r & 7)) * 16);
+                const float4 x = lds_f4(pu);
+                const float4 bb = bias4[u];
+                const float2 lo = __ffma2_rn(rs2,
+                                             __fadd2_rn(make_float2(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1])),
+                                                        make_float2(bb.x, bb.y)),
+                                             make_float2(x.x, x.y));
+                const float2 hi = __ffma2_rn(rs2,
+                                             __fadd2_rn(make_float2(__uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3])),
+                                                        make_float2(bb.z, bb.w)),
+                                             make_float2(x.z, x.w));
+                sts_f4(pu, make_float4(lo.x, lo.y, hi.x, hi.y));
+                v[4 * u + 0] = __float_as_uint(lo.x);
+                v[4 * u + 1] = __float_as_uint(lo.y);
+                v[4 * u + 2] = __float_as_uint(hi.x);
+                v[4 * u + 3] = __float_as_uint(hi.y);
+                pkh[2 * u] = pack_bf16x2(lo.x, lo.y);
+                pkh[2 * u + 1] = pack_bf16x2(hi.x, hi.y);
+                s0 = __fadd2_rn(s0, lo);
+                s1 = __fadd2_rn(s1, hi);
+              }
+              fence_proxy_async_smem();
+              asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+              if (etid == 0) mbar_arrive(&rready[buf]);
+              const float2 ss = __fadd2_rn(s0, s1);
+              const float mc = (ss.x + ss.y) * (1.0f / 32.0f);
+              const float2 nmc = make_float2(-mc, -mc);
+              float2 q0 = make_float2(0.0f, 0.0f), q1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float2 d0 = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), nmc);
+                const float2 d1 = __fadd2_rn(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), nmc);
+                q0 = __ffma2_rn(d0, d0, q0);
+                q1 = __ffma2_rn(d1, d1, q1);
+              }
+              const float2 qq = __fadd2_rn(q0, q1);
+              const float delta = mc - mean;
+              const float wgt = 1.0f / static_cast<float>(c + 1);
+              mean = fmaf(delta, wgt, mean);
+              m2 += (qq.x + qq.y) + delta * delta * (32.0f * static_cast<float>(c) * wgt);
+              ++chunk_seq;
+            };
+            tmem_ld_32x32b_x32(t_row, va);
+#pragma unroll 1
+            for (int c = 0; c < NCHUNK; c += 2) {
+              tmem_ld_wait();
+              tmem_ld_32x32b_x32(t_row + (c + 1) * 32, vb);
+              fold_chunk(va, c, &pk[0]);
+              tmem_ld_wait();
+              if (c + 2 < NCHUNK) {
+                tmem_ld_32x32b_x32(t_row + (c + 2) * 32, va);
+              } else {                              // the whole tile is in registers: hand TMEM back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) arrive_tempty(acc);
+              }
+              fold_chunk(vb, c + 1, &pk[16]);
+              // bf16 copy of the 64 columns just finished (same swizzled box layout as the normalised rows of pass 2)
+              const uint32_t buf = chunk_seq % RES_SLOTS;
+              const uint32_t srow = smem_u32(ring) + buf * GEMM_STAGING_BYTES + r * 128;
+              twait(&rfull[buf], (chunk_seq / RES_SLOTS) & 1, w_bar);
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                sts_u4(srow + ((u ^ (r & 7)) * 16), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+              fence_proxy_async_smem();
+              asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+              if (etid == 0) mbar_arrive(&rready[buf]);
+              ++chunk_seq;
+            }
+            p.ln_stats_out[(static_cast<size_t>(m_blk) * GEMM_BM + r) * n_tiles + n_blk] = make_float2(mean, m2);
+          } else {
           // ---- pass 1: x' = residual + acc + bias. Stored as fp32 through the in-place ring exactly like
           // EPI_RESID_F32, written back into the TMEM accumulator for pass 2, and reduced to a running (mean, M2)
           // of this row over the tile's BN columns (two-pass inside a 32-column chunk, Chan's update across chunks).
@@ -749,7 +896,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
             if (etid == 0) mbar_arrive(&rready[buf]);
           }
+          }
         } else {
+        const float2 ln_r2 = make_float2(ln_rstd, ln_rstd), ln_m2 = make_float2(ln_nmr, ln_nmr);
+        (void)ln_r2; (void)ln_m2;
 #pragma unroll 1
         for (int c = cgrp; c < NCHUNK; c += GROUPS, ++chunk_seq) {
           // staging slot: bf16 epilogues own one box per group; the residual epilogue walks the in-place ring
@@ -786,12 +936,25 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             }
           } else {
             // all the math first, into packed registers (overwriting v) ...
+            if (ln_in) {      // acc * rstd - mean * rstd * s + c   (folded LayerNorm of the A rows; `bias` holds c)
+              const float* lns_c = &s_lns[grp][(c / GROUPS) * CHUNK];
+#pragma unroll
+              for (int j = 0; j < CHUNK / 2; ++j) {
+                const float2 b2 = *reinterpret_cast<const float2*>(bias_c + 2 * j);
+                const float2 s2 = *reinterpret_cast<const float2*>(lns_c + 2 * j);
+                float2 f = __ffma2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), ln_r2,
+                                      __ffma2_rn(ln_m2, s2, b2));
+                if constexpr (EPI == EPI_GELU_BF16) f = gelu_erf2(f);
+                v[j] = pack_bf16x2(f.x, f.y);
+              }
+            } else {
 #pragma unroll
             for (int j = 0; j < CHUNK / 2; ++j) {
               const float2 b2 = *reinterpret_cast<const float2*>(bias_c + 2 * j);
               float2 f = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), b2);
               if constexpr (EPI == EPI_GELU_BF16) f = gelu_erf2(f);
               v[j] = pack_bf16x2(f.x, f.y);
+            }
             }
             // ... then wait until the TMA store that last read this group's staging box has finished reading it
             // (that latency is now hidden behind the math), and write the row

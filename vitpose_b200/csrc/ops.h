@@ -20,8 +20,12 @@ int make_gemm_maps(GemmMaps* maps, const void* A, const void* B, int M, int N, i
                    int epilogue, void* out, int ldo, const float* aux, int cg, int period);
 int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue, int cg, int max_ctas,
                 cudaStream_t stream);
+// Consumer side of a folded LayerNorm (gemm.cuh): A holds the plain bf16 rows of the residual stream, `stats` the
+// (mean, M2) pairs per row and column tile its producer left, `s` [N] the row sums of the gamma-folded weight; the
+// folded bias c goes in as `bias`.
+struct LnFoldIn { const void* stats; const float* s; int parts, part_cols; float eps; };
 int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, void* out, int ldo,
-              const float* aux, int period, int max_ctas, cudaStream_t stream);
+              const float* aux, int period, int max_ctas, cudaStream_t stream, const LnFoldIn* ln = nullptr);
 // out[M, N] (fp32, leading dimension ldo) += At^T . Bt for ROW-MAJOR At [K, M], Bt [K, N]: the weight gradient
 // dW = dY^T X straight from dY and X (MN-major tensor-core operands, K split over CTAs, atomic accumulation)
 int gemm_bf16_atb_accum(const void* At, const void* Bt, int M, int N, int K, float* out, int ldo, int max_ctas,
@@ -36,7 +40,17 @@ int gemm_ln_scratch_init(void* scratch, int M, int N, cudaStream_t stream);
 int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, float* out,
                  const float* aux, int period, const float* gamma, const float* beta, float eps, void* xn,
                  void* scratch, unsigned epoch, int max_ctas, cudaStream_t stream, const float* row_scale = nullptr,
-                 int rows_per_scale = 0);
+                 int rows_per_scale = 0, void* fold_stats = nullptr);
+// fold_stats != null: folded LayerNorm — xn receives the PLAIN bf16 copy of the updated rows and fold_stats
+// (gemm_ln_stats_bytes(M, N) bytes, 16-byte aligned) one (mean, M2) float pair per row and column tile
+// (gemm_ln_parts(N) tiles of gemm_ln_part_cols(N) columns); gamma / beta / scratch / epoch are not used.
+int gemm_ln_parts(int N);
+int gemm_ln_part_cols(int N);
+size_t gemm_ln_stats_bytes(int M, int N);
+// W fp32 [N, K], bias [N] (may be null), gamma / beta [K] -> Wf bf16 [N, K] = gamma o W, s [N] = row sums of the
+// ROUNDED Wf, c [N] = bias + W . beta: the operands of a Linear layer that applies the preceding LayerNorm itself
+int fold_layernorm_linear(const float* W, const float* bias, const float* gamma, const float* beta, int N, int K,
+                          void* Wf, float* s, float* c, cudaStream_t stream);
 
 // ---- elementwise / normalisation (elementwise.cu) ----
 // img fp32 [n,3,H,W] -> patches bf16 [(flip?2n:n) * Hp*Wp, 768]; rows [n*Hp*Wp, 2n*Hp*Wp) hold the

@@ -6,12 +6,13 @@ libvitpose_b200.so.  State-dict keys/layouts are the reference's (SURVEY.md §8b
 unchanged.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BlockWeights, ModelDesc, Weights, check, lib, ptr, stream_ptr
+from ._lib import BlockFold, BlockWeights, ModelDesc, Weights, check, lib, ptr, stream_ptr
 
 BF16 = torch.bfloat16
 
@@ -131,6 +132,26 @@ class PackedWeights:
             bw.fc1_w, bw.fc1_b = ptr(dev_bf16(g(b + 'mlp.fc1.weight'))), ptr(dev_f32(g(b + 'mlp.fc1.bias')))
             bw.fc2_w, bw.fc2_b = ptr(dev_bf16(g(b + 'mlp.fc2.weight'))), ptr(dev_f32(g(b + 'mlp.fc2.bias')))
         w.blocks = ctypes.cast(self.blocks, ctypes.POINTER(BlockWeights))
+        # folded LayerNorm (include/vitpose_b200.h: vpb_block_fold): qkv / fc1 operands that carry norm1 / norm2
+        # (opt-in, VPB_LN_FOLD=1: measured no faster end to end, see profiles/r02_summary.md §8)
+        from .ops import fold_layernorm_linear
+        use_fold = os.environ.get('VPB_LN_FOLD', '0') not in ('', '0')
+        self.fold = (BlockFold * L)()
+        for i in range(L if use_fold else 0):
+            b, fw = f'blocks.{i}.', self.fold[i]
+            for lin, norm, n_out in (('attn.qkv', 'norm1', 3 * D), ('mlp.fc1', 'norm2', desc.mlp_hidden)):
+                bias = sd.get(backbone_prefix + b + lin + '.bias')
+                wf, s, c = fold_layernorm_linear(
+                    g(b + lin + '.weight').detach().to(device=dev, dtype=torch.float32),
+                    dev_f32(bias if bias is not None else torch.zeros(n_out)),
+                    dev_f32(g(b + norm + '.weight')), dev_f32(g(b + norm + '.bias')))
+                self.keep += [wf, s, c]
+                short = lin.split('.')[1]
+                setattr(fw, short + '_wf', ptr(wf))
+                setattr(fw, short + '_s', ptr(s))
+                setattr(fw, short + '_c', ptr(c))
+        if use_fold:
+            w.fold = ctypes.cast(self.fold, ctypes.POINTER(BlockFold))
         if desc.has_last_norm:
             w.last_g, w.last_b = ptr(dev_f32(g('last_norm.weight'))), ptr(dev_f32(g('last_norm.bias')))
         if desc.num_keypoints > 0 and (head_prefix + 'final_layer.weight') in sd:

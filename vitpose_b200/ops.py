@@ -1,5 +1,7 @@
 """Torch-tensor front ends of the C-ABI operators (plumbing only: pointers, shapes, current stream).
 Every function launches hand-written sm_100a kernels from libvitpose_b200.so; nothing here computes."""
+import ctypes
+
 import numpy as np
 import torch
 
@@ -68,6 +70,58 @@ def gemm_layernorm(a, b, epilogue, bias, aux, gamma, beta, eps=1e-6, period=0, o
                                         ptr(gamma), ptr(beta), float(eps), ptr(xn), ptr(scratch), nbytes,
                                         ptr(row_scale), int(rows_per_scale), stream_ptr()), 'vpb_gemm_bf16_layernorm')
     return out, xn
+
+
+def fold_layernorm_linear(w, bias, gamma, beta):
+    """(Wf bf16 [N, K], s [N], c [N]) of a Linear layer that applies the LayerNorm in front of it in its epilogue."""
+    N, K = w.shape
+    w = w.detach().float().contiguous()
+    wf = torch.empty(N, K, device=w.device, dtype=torch.bfloat16)
+    s = torch.empty(N, device=w.device, dtype=torch.float32)
+    c = torch.empty(N, device=w.device, dtype=torch.float32)
+    check(lib().vpb_fold_layernorm_linear(ptr(w), ptr(bias), ptr(gamma), ptr(beta), N, K, ptr(wf), ptr(s), ptr(c),
+                                          stream_ptr()), 'vpb_fold_layernorm_linear')
+    return wf, s, c
+
+
+def gemm_stats_layout(N):
+    """(column tiles per row, columns per tile) of the statistics gemm_resid_stats writes; (0, 0) = unsupported N."""
+    parts, cols = ctypes.c_int(0), ctypes.c_int(0)
+    lib().vpb_gemm_stats_layout(int(N), ctypes.byref(parts), ctypes.byref(cols))
+    return parts.value, cols.value
+
+
+def gemm_resid_stats(a, b, epilogue, bias, aux, period=0, out=None, row_scale=None, rows_per_scale=0, xb=None,
+                     stats=None):
+    """out fp32 = aux + a @ b.T + bias (in place when out is aux), xb = bf16(out), stats = per-tile (mean, M2) pairs:
+    the producer side of a folded LayerNorm. Returns (out, xb, stats [rows padded to 128, parts, 2])."""
+    M, K = a.shape
+    N = b.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    if xb is None:
+        xb = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    nbytes = lib().vpb_gemm_stats_bytes(M, N)
+    parts, _ = gemm_stats_layout(N)
+    if stats is None:
+        stats = torch.empty(max(nbytes, 8) // 8, 2, device=a.device, dtype=torch.float32)
+    check(lib().vpb_gemm_bf16_resid_stats(ptr(a), ptr(b), M, N, K, epilogue, ptr(bias), ptr(out), ptr(aux), period,
+                                          ptr(xb), ptr(stats), nbytes, ptr(row_scale), int(rows_per_scale),
+                                          stream_ptr()), 'vpb_gemm_bf16_resid_stats')
+    return out, xb, stats.view(-1, parts, 2)
+
+
+def gemm_lnfold(xb, wf, s, c, stats, epilogue=None, eps=1e-6, out=None):
+    """bf16 act(LayerNorm(x) @ W.T + b) from the plain bf16 rows, the folded weight and the row statistics."""
+    M, K = xb.shape
+    N = wf.shape[0]
+    parts, cols = stats.shape[1], K // stats.shape[1]
+    if out is None:
+        out = torch.empty(M, N, device=xb.device, dtype=torch.bfloat16)
+    check(lib().vpb_gemm_bf16_lnfold(ptr(xb), ptr(wf), M, N, K, EPI_BIAS_BF16 if epilogue is None else epilogue, ptr(c),
+                                     ptr(s), ptr(stats), parts, cols, float(eps), ptr(out), out.stride(0),
+                                     stream_ptr()), 'vpb_gemm_bf16_lnfold')
+    return out
 
 
 def layernorm(x, gamma, beta, eps=1e-6, out=None):
