@@ -219,6 +219,19 @@ int vpb_cast_f32_bf16(const float* in, void* out, long long n, const float* row_
 /* out[C] += sum over the R rows of in[R,C] (bf16, or fp32 when is_f32): bias / pos-embed gradients */
 int vpb_colsum_accumulate(const void* in, int is_f32, int R, int C, float* out, void* stream);
 /* nn.GELU (exact erf, vit.py:71-76): out = gelu(pre); dpre = dh * gelu'(pre) */
+/* Training-step fusions of the MLP (vit.py:64-73: fc1 -> nn.GELU -> fc2):
+ *  vpb_gemm_bf16_gelu_save: out bf16 [M, ldo] = gelu_erf(A.B^T + bias) AND pre_out bf16 [M, N] = A.B^T + bias (the
+ *    activation the backward pass differentiates; the GELU is evaluated on the fp32 value, before that rounding);
+ *  vpb_gemm_bf16_gelu_bwd:  out bf16 [M, ldo] = (A.B^T) * gelu'(pre[M, N]): A = dY of fc2, B = W2^T, so out = dL/d(pre);
+ *    colsum (optional, fp32 [N]) += column sums of out's fp32 values = fc1's bias gradient;
+ *  vpb_cast_f32_bf16_colsum: vpb_cast_f32_bf16 over [R, C] + colsum[C] += column sums of the rounded output (the bias
+ *    gradient of the layer whose output gradient is being cast). */
+int vpb_gemm_bf16_gelu_save(const void* A, const void* B, int M, int N, int K, const float* bias, void* out, int ldo,
+                            void* pre_out, void* stream);
+int vpb_gemm_bf16_gelu_bwd(const void* A, const void* B, int M, int N, int K, const void* pre, void* out, int ldo,
+                           float* colsum, void* stream);
+int vpb_cast_f32_bf16_colsum(const float* in, void* out, int R, int C, const float* row_scale, int rows_per_scale,
+                             float* colsum, void* stream);
 int vpb_gelu_fwd_bf16(const void* pre, void* out, long long n, void* stream);
 int vpb_gelu_bwd_bf16(const void* pre, const void* dh, void* dpre, long long n, void* stream);
 /* nn.LayerNorm backward (vit.py:125,133,328): x fp32 [M,D] (the saved input), dy bf16 [M,D];

@@ -59,6 +59,49 @@ def test_gelu_fwd_bwd():
     _close('gelu bwd', ops.gelu_bwd(pre, dh), x.grad, 1e-2)
 
 
+def _gelu_grad(x):
+    x = x.double()
+    return 0.5 * (1 + torch.erf(x / math.sqrt(2))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
+
+
+@pytest.mark.parametrize('M,N,K', [(192 * 64, 3072, 768), (1000, 1536, 384), (192 * 3, 256, 64)])
+def test_gemm_gelu_save_and_gelu_bwd(M, N, K):
+    """The MLP fusions of the training step: fc1 + GELU that also stores the pre-activation, and fc2's input gradient
+    with the GELU backward (and fc1's bias gradient) in its epilogue, against fp64 PyTorch on the same operands."""
+    from vitpose_b200 import ops
+    a, w = _rand((M, K), 21), _rand((N, K), 22, 1.0 / math.sqrt(K))
+    bias = _rand((N,), 23, 0.5, dtype=torch.float32)
+    h, pre = ops.gemm_gelu_save(a, w, bias)
+    ref_pre = a.double() @ w.double().t() + bias.double()
+    _close('pre-activation', pre, ref_pre, 1e-2)
+    _close('gelu(pre)', h, F.gelu(ref_pre), 1e-2)
+    # backward: dy [M, D], W2 [D, N] -> W2^T [N, D]
+    D = 256
+    dy, w2t = _rand((M, D), 24), _rand((N, D), 25, 1.0 / math.sqrt(D))
+    db = torch.ones(N, device=_dev())
+    dpre = ops.gemm_gelu_bwd(dy, w2t, pre, db)
+    ref = (dy.double() @ w2t.double().t()) * _gelu_grad(pre)
+    _close('dgelu', dpre, ref, 1e-2)
+    _close('fc1 bias gradient', db, 1 + ref.sum(0), 2e-3)
+    # without the column sums, and against the two-kernel path
+    dpre2 = ops.gemm_gelu_bwd(dy, w2t, pre)
+    assert torch.equal(dpre, dpre2)
+    _close('two-kernel path', dpre, ops.gelu_bwd(pre, ops.gemm(dy, w2t, 0)), 2e-2)
+
+
+@pytest.mark.parametrize('R,C,scaled', [(192 * 64, 768, True), (1000, 384, False), (192 * 5, 1280, True)])
+def test_cast_bf16_colsum(R, C, scaled):
+    from vitpose_b200 import ops
+    x = _rand((R, C), 26, dtype=torch.float32)
+    rps = 192 if scaled else 0
+    scale = (torch.rand(R // 192 + 1, device=_dev()) * 2).contiguous() if scaled else None
+    cs = torch.full((C,), 2.0, device=_dev())
+    out = ops.cast_bf16_colsum(x, cs, scale, rps)
+    ref = ops.cast_bf16(x, scale, rps)
+    assert torch.equal(out, ref)
+    _close('colsum of the rounded rows', cs, 2 + ref.float().sum(0), 2e-4)
+
+
 @pytest.mark.parametrize('D', [128, 768])
 def test_layernorm_bwd(D):
     from vitpose_b200 import ops

@@ -32,11 +32,15 @@ def _cos(a, b):
     return float((a @ b) / (a.norm() * b.norm() + 1e-30))
 
 
-@pytest.mark.parametrize('name,n,depth,drop', [('tiny', 4, 2, 0.0), ('B-classic-17', 3, 2, 0.0),
-                                               ('B-classic-17', 2, 12, 0.0), ('B-classic-17', 6, 3, 0.3)])
-def test_forward_train_backward_vs_oracle(name, n, depth, drop):
-    """drop > 0: stochastic depth with the SAME per-crop masks injected into both implementations."""
+@pytest.mark.parametrize('name,n,depth,drop,fused', [('tiny', 4, 2, 0.0, True), ('B-classic-17', 3, 2, 0.0, True),
+                                                     ('B-classic-17', 2, 12, 0.0, True), ('B-classic-17', 6, 3, 0.3, True),
+                                                     ('B-classic-17', 6, 3, 0.3, False)])
+def test_forward_train_backward_vs_oracle(name, n, depth, drop, fused, monkeypatch):
+    """drop > 0: stochastic depth with the SAME per-crop masks injected into both implementations. fused = the MLP /
+    bias-gradient fusions of the training step (training.FUSE_MLP); the un-fused kernels stay covered by one case."""
     import vitpose_b200 as V
+    from vitpose_b200 import training
+    monkeypatch.setattr(training, 'FUSE_MLP', fused)
     if name == 'tiny':
         cfg = configs.tiny_model_cfg(5)
     else:

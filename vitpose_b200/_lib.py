@@ -107,6 +107,11 @@ _SIGS = {
     'vpb_gemm_bf16_layernorm': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                         c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_int,
                                         c_void_p]),
+    'vpb_gemm_bf16_gelu_save': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                        c_void_p]),
+    'vpb_gemm_bf16_gelu_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                       c_void_p]),
+    'vpb_cast_f32_bf16_colsum': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'vpb_fold_layernorm_linear': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                           c_void_p, c_void_p]),
     'vpb_gemm_stats_layout': (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),

@@ -334,6 +334,20 @@ int vpb_gemm_bf16_layernorm(const void* A, const void* B, int M, int N, int K, i
   return gemm_bf16_ln(A, B, M, N, K, epilogue, bias, out, aux, period, gamma, beta, eps, xn, scratch, 1u, 0, stream,
                       row_scale, rows_per_scale);
 }
+int vpb_gemm_bf16_gelu_save(const void* A, const void* B, int M, int N, int K, const float* bias, void* out, int ldo,
+                            void* pre_out, void* stream) {
+  const GemmTrainAux tr{pre_out, nullptr, nullptr};
+  return gemm_bf16(A, B, M, N, K, EPI_GELU_BF16, bias, out, ldo, nullptr, 0, 0, as_stream(stream), nullptr, &tr);
+}
+int vpb_gemm_bf16_gelu_bwd(const void* A, const void* B, int M, int N, int K, const void* pre, void* out, int ldo,
+                           float* colsum, void* stream) {
+  const GemmTrainAux tr{nullptr, pre, colsum};
+  return gemm_bf16(A, B, M, N, K, EPI_DGELU_BF16, nullptr, out, ldo, nullptr, 0, 0, as_stream(stream), nullptr, &tr);
+}
+int vpb_cast_f32_bf16_colsum(const float* in, void* out, int R, int C, const float* row_scale, int rows_per_scale,
+                             float* colsum, void* stream) {
+  return cast_f32_bf16_colsum(in, out, R, C, row_scale, rows_per_scale, colsum, as_stream(stream));
+}
 int vpb_fold_layernorm_linear(const float* W, const float* bias, const float* gamma, const float* beta, int N, int K,
                               void* Wf, float* s, float* c, void* stream) {
   return fold_layernorm_linear(W, bias, gamma, beta, N, K, Wf, s, c, as_stream(stream));

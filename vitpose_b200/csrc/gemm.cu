@@ -181,6 +181,10 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue,
   if (cg == 2) {
     if (bn == 256 && epilogue == EPI_BIAS_BF16) return launch_gemm_inst<256, EPI_BIAS_BF16, 2>(maps, p, max_ctas, stream);
     if (bn == 256 && epilogue == EPI_GELU_BF16) return launch_gemm_inst<256, EPI_GELU_BF16, 2>(maps, p, max_ctas, stream);
+    if (bn == 256 && epilogue == EPI_BIAS_LNIN_BF16) return launch_gemm_inst<256, EPI_BIAS_LNIN_BF16, 2>(maps, p, max_ctas, stream);
+    if (bn == 256 && epilogue == EPI_GELU_LNIN_BF16) return launch_gemm_inst<256, EPI_GELU_LNIN_BF16, 2>(maps, p, max_ctas, stream);
+    if (bn == 256 && epilogue == EPI_GELU_SAVE_BF16) return launch_gemm_inst<256, EPI_GELU_SAVE_BF16, 2>(maps, p, max_ctas, stream);
+    if (bn == 256 && epilogue == EPI_DGELU_BF16) return launch_gemm_inst<256, EPI_DGELU_BF16, 2>(maps, p, max_ctas, stream);
     if (bn == 256 && epilogue == EPI_RESID_F32) return launch_gemm_inst<256, EPI_RESID_F32, 2>(maps, p, max_ctas, stream);
     if (bn == 256 && epilogue == EPI_POSTMA_F32) return launch_gemm_inst<256, EPI_POSTMA_F32, 2>(maps, p, max_ctas, stream);
     if (bn == 256 && epilogue == EPI_RESID_LN_F32) return launch_gemm_inst<256, EPI_RESID_LN_F32, 2>(maps, p, max_ctas, stream);
@@ -200,6 +204,18 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue,
   VPB_GEMM_CASE(256, EPI_GELU_BF16)
   VPB_GEMM_CASE(128, EPI_GELU_BF16)
   VPB_GEMM_CASE(64, EPI_GELU_BF16)
+  VPB_GEMM_CASE(256, EPI_BIAS_LNIN_BF16)
+  VPB_GEMM_CASE(128, EPI_BIAS_LNIN_BF16)
+  VPB_GEMM_CASE(64, EPI_BIAS_LNIN_BF16)
+  VPB_GEMM_CASE(256, EPI_GELU_LNIN_BF16)
+  VPB_GEMM_CASE(128, EPI_GELU_LNIN_BF16)
+  VPB_GEMM_CASE(64, EPI_GELU_LNIN_BF16)
+  VPB_GEMM_CASE(256, EPI_GELU_SAVE_BF16)
+  VPB_GEMM_CASE(128, EPI_GELU_SAVE_BF16)
+  VPB_GEMM_CASE(64, EPI_GELU_SAVE_BF16)
+  VPB_GEMM_CASE(256, EPI_DGELU_BF16)
+  VPB_GEMM_CASE(128, EPI_DGELU_BF16)
+  VPB_GEMM_CASE(64, EPI_DGELU_BF16)
   VPB_GEMM_CASE(256, EPI_RESID_F32)
   VPB_GEMM_CASE(128, EPI_RESID_F32)
   VPB_GEMM_CASE(64, EPI_RESID_F32)
@@ -233,7 +249,8 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue,
 }
 
 int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, void* out, int ldo,
-              const float* aux, int period, int max_ctas, cudaStream_t stream, const LnFoldIn* ln) {
+              const float* aux, int period, int max_ctas, cudaStream_t stream, const LnFoldIn* ln,
+              const GemmTrainAux* tr) {
   VPB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   VPB_REQUIRE(K % 8 == 0, "gemm: K=%d must be a multiple of 8 (16-byte TMA row pitch)", K);
   VPB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
@@ -263,6 +280,21 @@ int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, c
     p.ln_parts = ln->parts;
     p.ln_part_cols = ln->part_cols;
     p.ln_eps = ln->eps;
+    epilogue = epilogue == EPI_BIAS_BF16 ? EPI_BIAS_LNIN_BF16 : EPI_GELU_LNIN_BF16;    // (same tiles and tensor maps)
+  }
+  if (epilogue == EPI_DGELU_BF16)
+    VPB_REQUIRE(tr != nullptr && tr->pre_in != nullptr && bias == nullptr && N % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(tr->pre_in) & 15) == 0,
+                "gemm: the gelu-backward epilogue needs the saved pre-activation [M, N] (16-byte aligned, N %% 8 == 0) and no bias");
+  if (tr != nullptr) {
+    if (tr->pre_out != nullptr && epilogue == EPI_GELU_BF16) epilogue = EPI_GELU_SAVE_BF16;
+    VPB_REQUIRE(tr->pre_out == nullptr || (epilogue == EPI_GELU_SAVE_BF16 && N % 8 == 0 &&
+                                           (reinterpret_cast<uintptr_t>(tr->pre_out) & 15) == 0),
+                "gemm: a pre-activation output needs the GELU epilogue, N %% 8 == 0 and a 16-byte aligned buffer");
+    VPB_REQUIRE(tr->colsum_out == nullptr || epilogue == EPI_DGELU_BF16, "gemm: column sums come with the gelu-backward epilogue");
+    p.pre_out = tr->pre_out;
+    p.pre_in = tr->pre_in;
+    p.colsum_out = tr->colsum_out;
   }
   if (epilogue == EPI_ACCUM_F32) {
     VPB_REQUIRE(bias == nullptr && ldo % 4 == 0, "gemm: the accumulating epilogue takes no bias and needs ldo %% 4 == 0");
@@ -345,10 +377,10 @@ int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue
   const bool short_k = K < 1536;
   int cg = gemm_pick_cg(M, bn, EPI_RESID_LNS_F32, K);
   if (bn == 128 && epilogue != EPI_RESID_F32) cg = 1;     // (128-wide pair tiles: residual epilogues only)
-  const bool split = short_k && (bn <= 128 || cg == 2);
+  const bool split = !fold && short_k && (bn <= 128 || cg == 2);   // (the folded form: one-group kernels only)
   const int epi = epilogue == EPI_RESID_F32 ? (split ? EPI_RESID_LNS_F32 : EPI_RESID_LN_F32)
                                             : (split ? EPI_POSTMA_LNS_F32 : EPI_POSTMA_LN_F32);
-  if (!split && short_k) cg = 1;     // short-K residual GEMMs are slightly faster unpaired (see gemm_pick_cg)
+  if (!split && short_k && !fold) cg = 1;     // short-K residual GEMMs are slightly faster unpaired (see gemm_pick_cg)
   GemmMaps maps;
   if (make_gemm_maps(&maps, A, B, M, N, K, K, K, bn, epi, out, N, aux, cg, period)) return -1;
   uint64_t dims_o[2] = {(uint64_t)N, (uint64_t)M};

@@ -35,6 +35,16 @@ enum GemmEpilogue {
   // out fp32 [M, ldo] += A.B^T with the K range of every tile split over `ksplit` CTAs that accumulate with vector
   // atomics: weight gradients (small M x N, K = all tokens of the batch) would otherwise occupy a few SMs
   EPI_ACCUM_F32 = 10,
+  // training: out bf16 [M, ldo] = acc * gelu'(pre), pre bf16 [M, N] the saved fc1 pre-activation (the input gradient of
+  // mlp.fc2 with the backward of nn.GELU in its epilogue); optionally colsum[N] += column sums of out (fc1's bias gradient)
+  EPI_DGELU_BF16 = 11,
+  // training forward of mlp.fc1: EPI_GELU_BF16 + the bf16 pre-activation acc + bias stored to pre_out [M, N] (an
+  // instance of its own so that the inference kernel carries none of it)
+  EPI_GELU_SAVE_BF16 = 12,
+  // consumer side of a folded LayerNorm (see GemmParams::ln_stats): EPI_BIAS_BF16 / EPI_GELU_BF16 of LN(A) from the
+  // plain rows A, the producer's row statistics and the folded weight (instances of their own, as above)
+  EPI_BIAS_LNIN_BF16 = 13,
+  EPI_GELU_LNIN_BF16 = 14,
 };
 __host__ __device__ constexpr bool gemm_epi_ln(int epi) { return epi >= EPI_RESID_LN_F32 && epi <= EPI_POSTMA_LNS_F32; }
 __host__ __device__ constexpr bool gemm_epi_pos(int epi) {
@@ -74,6 +84,11 @@ struct GemmParams {
   // and one (mean, M2) pair per row and column tile — single pass, no exchange between CTAs, TMEM released as soon as
   // the tile is in registers. The consumer (EPI_BIAS_BF16 / EPI_GELU_BF16 with ln_stats != null) merges the pairs of
   // its rows and applies rstd, mean, s and c (passed as `bias`) in its epilogue.
+  // training (EPI_GELU_SAVE_BF16): also store the bf16 pre-activation acc + bias [M, N] (row pitch N) for the backward pass
+  void* pre_out;
+  // training (EPI_DGELU_BF16): the saved pre-activation [M, N], and optionally where to add the column sums of out
+  const void* pre_in;
+  float* colsum_out;
   int ln_fold;
   float2* ln_stats_out;     // producer: [row blocks * 128, n_tiles]
   const float2* ln_stats;   // consumer: [rows of A (padded to 128), ln_parts]
@@ -99,7 +114,15 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;   // 64 bf16 = one 128-byte swizzle row
 // bf16 epilogues (bias / GELU) are instruction-heavy: two epilogue warpgroups (8 warps, 2 per scheduler) split
 // the column chunks of a tile; the fp32 residual epilogue is memory-heavy and keeps one warpgroup.
-__host__ __device__ constexpr int gemm_epi_groups(int epi) { return (epi == 0 || epi == 1) ? 2 : 1; }
+__host__ __device__ constexpr bool gemm_epi_bf16(int epi) {
+  return epi == EPI_BIAS_BF16 || epi == EPI_GELU_BF16 || epi == EPI_DGELU_BF16 || epi == EPI_GELU_SAVE_BF16 ||
+         epi == EPI_BIAS_LNIN_BF16 || epi == EPI_GELU_LNIN_BF16;
+}
+__host__ __device__ constexpr bool gemm_epi_ln_in(int epi) { return epi == EPI_BIAS_LNIN_BF16 || epi == EPI_GELU_LNIN_BF16; }
+__host__ __device__ constexpr bool gemm_epi_gelu(int epi) {
+  return epi == EPI_GELU_BF16 || epi == EPI_GELU_SAVE_BF16 || epi == EPI_GELU_LNIN_BF16;
+}
+__host__ __device__ constexpr int gemm_epi_groups(int epi) { return gemm_epi_bf16(epi) ? 2 : 1; }
 // The fp32 residual epilogues add warp 6 (and 11): the ring warp that streams the residual tile through in-place
 // staging slots (loads ahead of the epilogue, stores behind it).
 // The short-K LayerNorm variants run TWO such epilogue warpgroups (warps 2..5 and 7..10), each with its own
@@ -117,7 +140,7 @@ constexpr int GEMM_SMEM_BUDGET = 232448 - 3072;
 constexpr int GEMM_STAGING_BYTES = GEMM_BM * 128;   // one [128 rows x 128 B] TMA-store box
 
 __host__ __device__ constexpr bool gemm_epi_staged(int epi) {
-  return epi == EPI_BIAS_BF16 || epi == EPI_GELU_BF16 || gemm_epi_adds_tile(epi);
+  return gemm_epi_bf16(epi) || gemm_epi_adds_tile(epi);
 }
 __host__ __device__ constexpr int gemm_tmem_cols(int bn) {
   return 2 * bn <= 32 ? 32 : 2 * bn <= 64 ? 64 : 2 * bn <= 128 ? 128 : 2 * bn <= 256 ? 256 : 512;
@@ -220,6 +243,40 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   const float2 t = __fmul2_rn(__fmul2_rn(a, make_float2(-0.5f, -0.5f)), e);
   return __ffma2_rn(__fadd2_rn(x, a), make_float2(0.5f, 0.5f), t);       // 0.5 (x + |x|) = max(x, 0), exactly
 #endif
+}
+
+// d/dx [x Phi(x)] = Phi(x) + x phi(x) on two elements, with the same erfc polynomial as gelu_erf2:
+// Phi(x) = 0.5 + copysign(0.5 - 0.5 erfc(|x| / sqrt 2), x), phi(x) = exp(-x^2 / 2) / sqrt(2 pi).
+__device__ __forceinline__ float2 gelu_erf_grad2(float2 x) {
+  const float2 a = make_float2(fabsf(x.x), fabsf(x.y));
+  float2 q = __ffma2_rn(make_float2(GELU_Q5, GELU_Q5), a, make_float2(GELU_Q4, GELU_Q4));
+  q = __ffma2_rn(q, a, make_float2(GELU_Q3, GELU_Q3));
+  q = __ffma2_rn(q, a, make_float2(GELU_Q2, GELU_Q2));
+  q = __ffma2_rn(q, a, make_float2(GELU_Q1, GELU_Q1));
+  q = __fmul2_rn(q, a);
+  const float2 e = make_float2(fast_ex2(q.x), fast_ex2(q.y));
+  const float2 h = __ffma2_rn(e, make_float2(-0.5f, -0.5f), make_float2(0.5f, 0.5f));      // 0.5 - 0.5 erfc >= 0
+  const float2 cdf = __fadd2_rn(make_float2(copysignf(h.x, x.x), copysignf(h.y, x.y)), make_float2(0.5f, 0.5f));
+  const float2 gq = __fmul2_rn(__fmul2_rn(x, x), make_float2(-0.72134752044448170f, -0.72134752044448170f));
+  const float2 g = make_float2(fast_ex2(gq.x), fast_ex2(gq.y));                              // exp(-x^2 / 2)
+  return __ffma2_rn(__fmul2_rn(x, make_float2(0.3989422804014327f, 0.3989422804014327f)), g, cdf);
+}
+
+// Column sums over the 32 lanes of a warp for 32 columns at once (lane = row, x[c] = this row's value in column c):
+// recursive halving — at step `off` a lane keeps the half of its columns whose bit `off` equals its own lane bit and
+// adds the partner's values for them — 31 shuffles instead of 32 x 5. Returns the sum of column `lane`.
+__device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? x[i] : x[i + off];
+      const float keep = up ? x[i + off] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return x[0];
 }
 
 // Fused-LayerNorm statistics exchange: one 8-byte word per (row, n-tile) = {mean, M2 | tag << 31}; 8-byte accesses
@@ -326,7 +383,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   constexpr int BIAS_PER_GROUP = (BN / CHUNK + GROUPS - 1) / GROUPS * CHUNK;   // columns a group's chunks cover
   __shared__ __align__(16) float s_bias[LN_SPLIT ? 2 : GROUPS][STAGED ? BIAS_PER_GROUP : 1];
   // consumer of a folded LayerNorm: s_n of this group's columns (bf16 epilogues only)
-  __shared__ __align__(16) float s_lns[GROUPS][(STAGED && !gemm_epi_adds_tile(EPI)) ? BIAS_PER_GROUP : 1];
+  __shared__ __align__(16) float s_lns[GROUPS][gemm_epi_ln_in(EPI) ? BIAS_PER_GROUP : 1];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -540,7 +597,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const int first_tile = tile0 + tg * tile_step, stride = tile_step * TG;
       // Order of a tile's chunks through the ring. Fused LayerNorm: the NX fp32 chunks, then the BN / 64 bf16 boxes
       // (pass 2). Folded LayerNorm: the bf16 box of 64 columns right after its two fp32 chunks.
-      const bool fold = LN && p.ln_fold != 0;
+      // (the folded form exists in the one-group variants only: the two-group kernels stay free of its registers)
+      const bool fold = LN && !LN_SPLIT && p.ln_fold != 0;
       auto seq_is_box = [&](int q) { return LN && (fold ? (q % 3) == 2 : q >= NX); };
       auto seq_index = [&](int q) { return fold ? ((q % 3) == 2 ? q / 3 : (q / 3) * 2 + (q % 3)) : (q >= NX ? q - NX : q); };
       auto load = [&](int tile, int q, uint32_t slot) {
@@ -648,11 +706,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           for (int i = etid; i < BIAS_PER_GROUP; i += 128) {
             const int col = n_blk * BN + ((i / CHUNK) * GROUPS + cgrp) * CHUNK + (i % CHUNK);
             s_bias[grp][i] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
-            if constexpr (!gemm_epi_adds_tile(EPI))
-              s_lns[grp][i] = (p.ln_s != nullptr && col < p.N) ? __ldg(p.ln_s + col) : 0.0f;
+            if constexpr (gemm_epi_ln_in(EPI)) s_lns[grp][i] = col < p.N ? __ldg(p.ln_s + col) : 0.0f;
           }
           if constexpr (LN) {
-            if (p.ln_fold == 0)     // (the folded form leaves gamma / beta to the consumer's weights)
+            if (LN_SPLIT || p.ln_fold == 0)     // (the folded form leaves gamma / beta to the consumer's weights)
             for (int i = etid; i < BN; i += 128) {
               s_gamma[i] = __ldg(p.ln_gamma + n_blk * BN + i);
               s_beta[i] = __ldg(p.ln_beta + n_blk * BN + i);
@@ -663,8 +720,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         // ---- consumer side of a folded LayerNorm: (mean, M2) pairs of this thread's row of A, merged over the producer's
         // column tiles. Requested BEFORE the wait for the accumulator so that the L2 round trip hides behind it.
         float ln_rstd = 1.0f, ln_nmr = 0.0f;
-        const bool ln_in = !gemm_epi_adds_tile(EPI) && p.ln_stats != nullptr;
-        if (ln_in) {
+        constexpr bool ln_in = gemm_epi_ln_in(EPI);
+        if constexpr (ln_in) {
           const int row = min(m_blk * GEMM_BM + r, p.M - 1);
           const float2* st = p.ln_stats + static_cast<size_t>(row) * p.ln_parts;
           float pm[10], pq[10], mu = 0.0f;
@@ -696,7 +753,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (lane == 0) arrive_tempty(acc);
         }
         if constexpr (LN) {
-          if (p.ln_fold != 0) {
+          if (!LN_SPLIT && p.ln_fold != 0) {
             // ---- folded LayerNorm: ONE pass. x' = residual + acc + bias goes out as fp32 through the in-place ring
             // and as bf16 (64-column boxes through the same ring, right after their two fp32 chunks); the row's
             // (mean, M2) over this tile's columns is left for the consumer GEMM. TMEM is free after the last load.
@@ -911,6 +968,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           } else {
             tmem_ld_32x32b_x32(t_row + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
           }
+          // training epilogues address global memory directly: this thread's row, this chunk's 64 columns (128 bytes)
+          const int g_row = m_blk * GEMM_BM + r, g_col = n_blk * BN + c * CHUNK;
+          uint4 pre8[EPI == EPI_DGELU_BF16 ? CHUNK / 8 : 1];
+          if constexpr (EPI == EPI_DGELU_BF16) {      // saved pre-activation, requested while the TMEM load is in flight
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.pre_in) +
+                                                              static_cast<size_t>(min(g_row, p.M - 1)) * p.N + g_col);
+#pragma unroll
+            for (int u = 0; u < CHUNK / 8; ++u)
+              pre8[u] = (g_col + 8 * u + 8 <= p.N) ? __ldg(src + u) : make_uint4(0u, 0u, 0u, 0u);
+          }
           tmem_ld_wait();
           if (c + GROUPS >= NCHUNK) {       // this group's last chunk is in registers: hand TMEM back to the MMA warp
             tc_fence_before();
@@ -936,7 +1003,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             }
           } else {
             // all the math first, into packed registers (overwriting v) ...
-            if (ln_in) {      // acc * rstd - mean * rstd * s + c   (folded LayerNorm of the A rows; `bias` holds c)
+            if constexpr (ln_in) {      // acc * rstd - mean * rstd * s + c   (folded LayerNorm of the A rows; `bias` holds c)
               const float* lns_c = &s_lns[grp][(c / GROUPS) * CHUNK];
 #pragma unroll
               for (int j = 0; j < CHUNK / 2; ++j) {
@@ -944,16 +1011,51 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 const float2 s2 = *reinterpret_cast<const float2*>(lns_c + 2 * j);
                 float2 f = __ffma2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), ln_r2,
                                       __ffma2_rn(ln_m2, s2, b2));
-                if constexpr (EPI == EPI_GELU_BF16) f = gelu_erf2(f);
+                if constexpr (gemm_epi_gelu(EPI)) f = gelu_erf2(f);
                 v[j] = pack_bf16x2(f.x, f.y);
               }
-            } else {
+            } else if constexpr (EPI == EPI_DGELU_BF16) {
+              // acc * gelu'(pre); 32 columns at a time so that their fp32 values can be column-summed across the warp
+              const uint32_t* prw = reinterpret_cast<const uint32_t*>(pre8);
 #pragma unroll
-            for (int j = 0; j < CHUNK / 2; ++j) {
-              const float2 b2 = *reinterpret_cast<const float2*>(bias_c + 2 * j);
-              float2 f = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), b2);
-              if constexpr (EPI == EPI_GELU_BF16) f = gelu_erf2(f);
-              v[j] = pack_bf16x2(f.x, f.y);
+              for (int hh = 0; hh < CHUNK / 32; ++hh) {
+                float cs[32];
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
+                  const int j = hh * 16 + jj;
+                  const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&prw[j]));
+                  const float2 f = __fmul2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])),
+                                              gelu_erf_grad2(x));
+                  v[j] = pack_bf16x2(f.x, f.y);
+                  cs[2 * jj] = f.x;
+                  cs[2 * jj + 1] = f.y;
+                }
+                if (p.colsum_out != nullptr) {        // (rows past M hold acc = 0: A is zero-filled there)
+                  const float sum = warp_colsum32(cs, lane);
+                  const int col = g_col + hh * 32 + lane;
+                  if (col < p.N) atomicAdd(p.colsum_out + col, sum);
+                }
+              }
+            } else {
+            const bool save_pre = EPI == EPI_GELU_SAVE_BF16 && g_row < p.M;
+            uint4* pre_dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.pre_out) +
+                                                      static_cast<size_t>(g_row) * p.N + g_col);
+            (void)save_pre; (void)pre_dst;
+#pragma unroll
+            for (int u = 0; u < CHUNK / 8; ++u) {
+              uint32_t pw[4];
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = 4 * u + jj;
+                const float2 b2 = *reinterpret_cast<const float2*>(bias_c + 2 * j);
+                float2 f = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), b2);
+                if constexpr (EPI == EPI_GELU_SAVE_BF16) pw[jj] = pack_bf16x2(f.x, f.y);
+                if constexpr (gemm_epi_gelu(EPI)) f = gelu_erf2(f);
+                v[j] = pack_bf16x2(f.x, f.y);
+              }
+              if constexpr (EPI == EPI_GELU_SAVE_BF16) {   // the pre-activation the backward pass differentiates
+                if (save_pre && g_col + 8 * u + 8 <= p.N) pre_dst[u] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+              }
             }
             }
             // ... then wait until the TMA store that last read this group's staging box has finished reading it

@@ -24,8 +24,13 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue,
 // (mean, M2) pairs per row and column tile its producer left, `s` [N] the row sums of the gamma-folded weight; the
 // folded bias c goes in as `bias`.
 struct LnFoldIn { const void* stats; const float* s; int parts, part_cols; float eps; };
+// Training-step extras of the bf16 epilogues: EPI_GELU_BF16 can also save the bf16 pre-activation (pre_out [M, N]);
+// EPI_DGELU_BF16 (input gradient of mlp.fc2 times gelu'(pre)) reads it back (pre_in) and can add the column sums of
+// its output to colsum_out [N] (fc1's bias gradient).
+struct GemmTrainAux { void* pre_out; const void* pre_in; float* colsum_out; };
 int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, void* out, int ldo,
-              const float* aux, int period, int max_ctas, cudaStream_t stream, const LnFoldIn* ln = nullptr);
+              const float* aux, int period, int max_ctas, cudaStream_t stream, const LnFoldIn* ln = nullptr,
+              const GemmTrainAux* tr = nullptr);
 // out[M, N] (fp32, leading dimension ldo) += At^T . Bt for ROW-MAJOR At [K, M], Bt [K, N]: the weight gradient
 // dW = dY^T X straight from dY and X (MN-major tensor-core operands, K split over CTAs, atomic accumulation)
 int gemm_bf16_atb_accum(const void* At, const void* Bt, int M, int N, int K, float* out, int ldo, int max_ctas,
@@ -116,6 +121,10 @@ int adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_s
 
 // ---- backward pass of the training step (train_bwd.cu, attention_bwd.cu) ----
 int transpose_bf16(const void* in, void* out, int R, int C, int batch, cudaStream_t stream);
+// out bf16 [R, C] = in * row_scale (as cast_f32_bf16) and colsum[C] += column sums of the ROUNDED output: the bias
+// gradient of the Linear layer whose output gradient this is, without a second pass over it
+int cast_f32_bf16_colsum(const float* in, void* out, int R, int C, const float* row_scale, int rows_per_scale,
+                         float* colsum, cudaStream_t stream);
 int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream, const float* row_scale = nullptr,
                   int row_len = 0, int rows_per_scale = 0);
 int colsum_accumulate(const void* in, int is_f32, int R, int C, float* out, cudaStream_t stream);

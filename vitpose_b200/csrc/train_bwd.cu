@@ -82,6 +82,60 @@ int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream, 
   return 0;
 }
 
+// cast + column sums in one pass. Block = 32 x 8 threads: 128 columns (4 per thread), `rows_per_block` rows; the sums
+// are taken over the bf16-ROUNDED values so that they equal colsum_accumulate() of the output.
+__global__ void __launch_bounds__(256) cast_colsum_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                          int R, int C, int rows_per_block,
+                                                          const float* __restrict__ row_scale, int rows_per_scale,
+                                                          float* __restrict__ colsum) {
+  __shared__ float red[8][128];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + 4 * tx;
+  const int r_begin = blockIdx.y * rows_per_block, r_end = min(R, r_begin + rows_per_block);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < C) {
+    for (int r = r_begin + ty; r < r_end; r += 8) {
+      const size_t off = static_cast<size_t>(r) * C + c;
+      float4 v = *reinterpret_cast<const float4*>(in + off);
+      if (row_scale != nullptr) {
+        const float s = __ldg(row_scale + r / rows_per_scale);
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+      }
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      *reinterpret_cast<uint2*>(out + off) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+      const float2 flo = __bfloat1622float2(lo), fhi = __bfloat1622float2(hi);
+      s0 += flo.x; s1 += flo.y; s2 += fhi.x; s3 += fhi.y;
+    }
+  }
+  red[ty][4 * tx] = s0; red[ty][4 * tx + 1] = s1; red[ty][4 * tx + 2] = s2; red[ty][4 * tx + 3] = s3;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    const int cc = blockIdx.x * 128 + threadIdx.x;
+    if (cc < C) atomicAdd(colsum + cc, s);
+  }
+}
+int cast_f32_bf16_colsum(const float* in, void* out, int R, int C, const float* row_scale, int rows_per_scale,
+                         float* colsum, cudaStream_t stream) {
+  VPB_REQUIRE(R > 0 && C > 0 && C % 4 == 0 && in && out && colsum, "cast+colsum: C=%d must be a positive multiple of 4", C);
+  VPB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0,
+              "cast+colsum: unaligned buffers");
+  VPB_REQUIRE(row_scale == nullptr || rows_per_scale > 0, "cast+colsum: row_scale needs rows_per_scale > 0");
+  const int col_blocks = (C + 127) / 128;
+  int row_blocks = (4 * sm_count() + col_blocks - 1) / col_blocks;
+  if (row_blocks < 1) row_blocks = 1;
+  const int rows_per_block = ((R + row_blocks - 1) / row_blocks + 7) / 8 * 8;
+  row_blocks = (R + rows_per_block - 1) / rows_per_block;
+  cast_colsum_kernel<<<dim3(col_blocks, row_blocks), 256, 0, stream>>>(
+      in, reinterpret_cast<__nv_bfloat16*>(out), R, C, rows_per_block, row_scale, rows_per_scale > 0 ? rows_per_scale : 1,
+      colsum);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // -------------------------------------------------------------------------------------------------
 // Column reductions over a row-major [R, C] matrix, accumulated (atomicAdd) into fp32 [C] vectors.
 //   COLSUM_BF16 / COLSUM_F32 : out0 += sum_r a              (bias gradients, pos-embed gradient)

@@ -250,6 +250,41 @@ def cast_bf16(x, row_scale=None, rows_per_scale=0):
     return out
 
 
+def cast_bf16_colsum(x, colsum, row_scale=None, rows_per_scale=0):
+    """cast_bf16 of the 2-D x and colsum[C] (fp32) += column sums of the rounded result, in one pass."""
+    _need(x, torch.float32, 'x'); _need(colsum, torch.float32, 'colsum')
+    R, C = x.shape
+    assert colsum.numel() == C
+    out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    check(lib().vpb_cast_f32_bf16_colsum(ptr(x), ptr(out), R, C, ptr(row_scale), int(rows_per_scale), ptr(colsum),
+                                         stream_ptr()), 'vpb_cast_f32_bf16_colsum')
+    return out
+
+
+def gemm_gelu_save(a, b, bias):
+    """(gelu(a @ b.T + bias), a @ b.T + bias), both bf16: the MLP's first half in the training forward pass."""
+    _need(a, BF16, 'a'); _need(b, BF16, 'b')
+    M, K = a.shape
+    N = b.shape[0]
+    out = torch.empty(M, N, device=a.device, dtype=BF16)
+    pre = torch.empty(M, N, device=a.device, dtype=BF16)
+    check(lib().vpb_gemm_bf16_gelu_save(ptr(a), ptr(b), M, N, K, ptr(bias), ptr(out), N, ptr(pre), stream_ptr()),
+          'vpb_gemm_bf16_gelu_save')
+    return out, pre
+
+
+def gemm_gelu_bwd(dy, wt, pre, colsum=None):
+    """(dy @ wt.T) * gelu'(pre) as bf16 [M, N]; colsum (fp32 [N], optional) += its column sums."""
+    _need(dy, BF16, 'dy'); _need(wt, BF16, 'wt'); _need(pre, BF16, 'pre')
+    M, K = dy.shape
+    N = wt.shape[0]
+    assert pre.shape == (M, N)
+    out = torch.empty(M, N, device=dy.device, dtype=BF16)
+    check(lib().vpb_gemm_bf16_gelu_bwd(ptr(dy), ptr(wt), M, N, K, ptr(pre), ptr(out), N, ptr(colsum), stream_ptr()),
+          'vpb_gemm_bf16_gelu_bwd')
+    return out
+
+
 def colsum_accumulate(x, out):
     """out[C] (fp32) += column sums of x [R, C] (bf16 or fp32)."""
     assert x.is_contiguous() and out.dtype == torch.float32

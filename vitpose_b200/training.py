@@ -98,6 +98,10 @@ class _LinearBank:
         return [_Linear(l, w, wt) for l, (w, wt) in zip(self.layers, self.views)]
 
 
+# VPB_TRAIN_FUSE=0: the un-fused MLP / bias-gradient kernels of round 1 (A/B measurements, parity tests of both paths)
+FUSE_MLP = os.environ.get('VPB_TRAIN_FUSE', '1') != '0'
+
+
 def drop_path_scales(bb, n, device):
     """[(s_attn, s_mlp)] per block: fp32 [n] factors mask / keep_prob of timm's drop_path (per-sample Bernoulli), or
     (None, None) where the branch is always kept. ``bb._drop_path_scales`` (same structure) overrides the random
@@ -196,8 +200,11 @@ class _NetworkFn(torch.autograd.Function):
             s1, s2 = scales[l]
             x_mid, xn2 = ops.gemm_layernorm(attn, w['proj'].w, EPI_RESID, w['proj'].b, x, blk.norm2.weight.detach(),
                                             blk.norm2.bias.detach(), 1e-6, row_scale=s1, rows_per_scale=T)
-            pre = ops.gemm(xn2, w['fc1'].w, EPI_BIAS, bias=w['fc1'].b)
-            h = ops.gelu_fwd(pre)
+            if FUSE_MLP:      # one kernel: h = gelu(pre) for fc2 and the bf16 pre-activation for the backward pass
+                h, pre = ops.gemm_gelu_save(xn2, w['fc1'].w, w['fc1'].b)
+            else:
+                pre = ops.gemm(xn2, w['fc1'].w, EPI_BIAS, bias=w['fc1'].b)
+                h = ops.gelu_fwd(pre)
             nxt = bb.blocks[l + 1].norm1 if l + 1 < depth else bb.last_norm
             x, xn = ops.gemm_layernorm(h, w['fc2'].w, EPI_RESID, w['fc2'].b, x_mid, nxt.weight.detach(),
                                        nxt.bias.detach(), 1e-6, row_scale=s2, rows_per_scale=T)
@@ -330,33 +337,49 @@ class _NetworkFn(torch.autograd.Function):
 
         trainable = {nm for nm, p in _param_list(model) if p.requires_grad}
 
-        def linear_bwd(name, lin, dy_bf16, x_bf16, want_dx=True):
+        def linear_bwd(name, lin, dy_bf16, x_bf16, want_dx=True, dbias=None):
             """gradients of y = x W^T + b given dy: dW, db into g[...]; returns dx (bf16). Frozen tensors
-            (``requires_grad = False``: frozen_stages / freeze_attn / freeze_ffn, vit.py:249-284) are skipped."""
+            (``requires_grad = False``: frozen_stages / freeze_attn / freeze_ffn, vit.py:249-284) are skipped.
+            ``dbias``: the bias gradient if the kernel that produced dy already summed its columns."""
             if name + '.weight' in trainable:
                 dw = zeros(*lin.w.shape)
                 _wgrad(dy_bf16, x_bf16, dw)
                 g[name + '.weight'] = dw
             if name + '.bias' in trainable:
-                dbias = zeros(lin.w.shape[0])
-                ops.colsum_accumulate(dy_bf16, dbias)
+                if dbias is None:
+                    dbias = zeros(lin.w.shape[0])
+                    ops.colsum_accumulate(dy_bf16, dbias)
                 g[name + '.bias'] = dbias
             return ops.gemm(dy_bf16, lin.wt, EPI_BIAS) if want_dx else None
+
+        def branch_grad(dx_f32, scale, bias_name, n_out):
+            """bf16 gradient of a residual branch (dx times the stochastic-depth factor of the crop) and, from the same
+            pass, the bias gradient of the Linear layer that ends the branch (None if that bias is frozen)."""
+            if FUSE_MLP and bias_name in trainable:
+                db = zeros(n_out)
+                return ops.cast_bf16_colsum(dx_f32, db, scale, T), db
+            return ops.cast_bf16(dx_f32, scale, T), None
 
         for l in range(len(bb.blocks) - 1, -1, -1):
             a, w, blk = s['acts'][l], s['blocks'][l], bb.blocks[l]
             pfx = f'backbone.blocks.{l}.'
             # x_out = x_mid + fc2(gelu(fc1(norm2(x_mid))))            (vit.py:139)
-            dyb = ops.cast_bf16(dx, a['s2'], T)                # gradient of the (possibly dropped / rescaled) branch
-            dh = linear_bwd(pfx + 'mlp.fc2', w['fc2'], dyb, a['h'])
-            dpre = ops.gelu_bwd(a['pre'], dh)
-            dxn2 = linear_bwd(pfx + 'mlp.fc1', w['fc1'], dpre, a['xn2'])
+            dyb, db2 = branch_grad(dx, a['s2'], pfx + 'mlp.fc2.bias', D)   # gradient of the (dropped / rescaled) branch
+            if FUSE_MLP:
+                # fc2's input gradient with the GELU backward in its epilogue (+ fc1's bias gradient as column sums)
+                linear_bwd(pfx + 'mlp.fc2', w['fc2'], dyb, a['h'], want_dx=False, dbias=db2)
+                db1 = zeros(w['fc1'].w.shape[0]) if pfx + 'mlp.fc1.bias' in trainable else None
+                dpre = ops.gemm_gelu_bwd(dyb, w['fc2'].wt, a['pre'], db1)
+            else:
+                dh = linear_bwd(pfx + 'mlp.fc2', w['fc2'], dyb, a['h'], dbias=db2)
+                dpre, db1 = ops.gelu_bwd(a['pre'], dh), None
+            dxn2 = linear_bwd(pfx + 'mlp.fc1', w['fc1'], dpre, a['xn2'], dbias=db1)
             dg_, db_ = zeros(D), zeros(D)
             ops.layernorm_bwd(a['x_mid'], blk.norm2.weight.detach(), dxn2, dx, dg_, db_, 1e-6)
             g[pfx + 'norm2.weight'], g[pfx + 'norm2.bias'] = dg_, db_
             # x_mid = x_in + proj(attention(qkv(norm1(x_in))))        (vit.py:138)
-            dyb = ops.cast_bf16(dx, a['s1'], T)
-            dattn = linear_bwd(pfx + 'attn.proj', w['proj'], dyb, a['attn'])
+            dyb, dbp = branch_grad(dx, a['s1'], pfx + 'attn.proj.bias', D)
+            dattn = linear_bwd(pfx + 'attn.proj', w['proj'], dyb, a['attn'], dbias=dbp)
             dqkv = ops.attention_bwd(a['qkv'].view(n, T, 3 * D), a['attn'].view(n, T, D), a['lse'],
                                      dattn.view(n, T, D), heads)
             dxn1 = linear_bwd(pfx + 'attn.qkv', w['qkv'], dqkv.view(M, 3 * D), a['xn1'])
