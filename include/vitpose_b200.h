@@ -174,6 +174,14 @@ int vpb_gemm_bf16_layernorm(const void* A, const void* B, int M, int N, int K, i
                             float* out, const float* aux, int period, const float* gamma, const float* beta, float eps,
                             void* xn, void* scratch, size_t scratch_bytes, const float* row_scale, int rows_per_scale,
                             void* stream);
+/* The same without the two memsets per call: initialise a scratch once (vpb_gemm_layernorm_scratch_init), then pass
+ * epoch = 1, 2, 3, ... to successive launches that use it. All launches on one scratch must have the same (M, N) and be
+ * ordered on one stream; re-initialise before the epoch wraps. (vpb_vitpose_forward does this internally.) */
+int vpb_gemm_layernorm_scratch_init(void* scratch, size_t scratch_bytes, int M, int N, void* stream);
+int vpb_gemm_bf16_layernorm_seq(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias,
+                                float* out, const float* aux, int period, const float* gamma, const float* beta,
+                                float eps, void* xn, void* scratch, size_t scratch_bytes, unsigned epoch,
+                                const float* row_scale, int rows_per_scale, void* stream);
 /* Folded LayerNorm, the three pieces (see vpb_block_fold):
  *  vpb_fold_layernorm_linear: W fp32 [N, K], bias [N] or NULL, gamma / beta [K] -> Wf bf16 [N, K], s [N], c [N];
  *  vpb_gemm_bf16_resid_stats: out = aux + A.B^T + bias like vpb_gemm_bf16_layernorm (same epilogues), but xb receives

@@ -141,6 +141,29 @@ def test_gemm_residual_layernorm_fused(M, D, K, offset):
     _report('fused layernorm', xn, ref_n, 0.04)
 
 
+def test_gemm_layernorm_shared_scratch_epochs():
+    """Successive fused-LayerNorm launches on ONE scratch (ops.LnScratch: initialised once, increasing epochs — the
+    training forward and vpb_vitpose_forward) give exactly what a freshly initialised scratch gives, through several
+    region / tag cycles of the exchange protocol and with different K."""
+    from vitpose_b200 import ops, _lib
+    M, D = 192 * 9, 768
+    g = torch.Generator().manual_seed(3)
+    gamma, beta = torch.randn(D, generator=g).to(_dev()), torch.randn(D, generator=g).to(_dev())
+    bias = torch.randn(D, generator=g).to(_dev())
+    x0 = (torch.randn(M, D, generator=g) * 2).to(_dev())
+    scratch = ops.LnScratch(M, D, _dev())
+    xa, xb = x0.clone(), x0.clone()
+    for i in range(9):
+        K = 768 if i % 2 == 0 else 3072
+        a = _rand_bf16((M, K), 100 + i).to(_dev())
+        w = _rand_bf16((D, K), 200 + i, 1.0 / math.sqrt(K)).to(_dev())
+        _, na = ops.gemm_layernorm(a, w, _lib.EPI_RESID_F32, bias, xa, gamma, beta, out=xa)
+        _, nb = ops.gemm_layernorm(a, w, _lib.EPI_RESID_F32, bias, xb, gamma, beta, out=xb, scratch=scratch)
+        torch.cuda.synchronize()
+        assert torch.equal(xa, xb) and torch.equal(na, nb), f'launch {i} (epoch {scratch.epoch}) differs'
+    assert scratch.epoch == 9
+
+
 def test_gemm_pos_layernorm_fused():
     from vitpose_b200 import ops, _lib
     T, n, D, K = 192, 9, 768, 768

@@ -1,0 +1,5 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+O=gpurun_out/r02_call28
+for f in 1 0; do VPB_TRAIN_FUSE=$f timeout 300 python tools/train_kernel_profile.py 64 5 > $O.kprof_fuse$f.txt 2>&1; head -32 $O.kprof_fuse$f.txt | cut -c1-130; done

@@ -120,6 +120,10 @@ _SIGS = {
                                           c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
     'vpb_gemm_bf16_lnfold': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                      c_int, c_int, c_float, c_void_p, c_int, c_void_p]),
+    'vpb_gemm_layernorm_scratch_init': (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    'vpb_gemm_bf16_layernorm_seq': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                            c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t,
+                                            ctypes.c_uint, c_void_p, c_int, c_void_p]),
     'vpb_layernorm_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     'vpb_im2col_patch16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'vpb_attention': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),

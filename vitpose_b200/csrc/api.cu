@@ -375,6 +375,21 @@ int vpb_gemm_bf16_lnfold(const void* A, const void* Wf, int M, int N, int K, int
   const LnFoldIn in{stats, s, parts, part_cols, eps};
   return gemm_bf16(A, Wf, M, N, K, epilogue, c, out, ldo, nullptr, 0, 0, as_stream(stream), &in);
 }
+int vpb_gemm_layernorm_scratch_init(void* scratch, size_t scratch_bytes, int M, int N, void* stream) {
+  VPB_REQUIRE(M > 0 && N > 0 && scratch != nullptr && scratch_bytes >= gemm_ln_scratch_bytes(M, N),
+              "gemm+layernorm: scratch too small (%zu < %zu)", scratch_bytes, gemm_ln_scratch_bytes(M > 0 ? M : 1, N > 0 ? N : 1));
+  return gemm_ln_scratch_init(scratch, M, N, as_stream(stream));
+}
+int vpb_gemm_bf16_layernorm_seq(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias,
+                                float* out, const float* aux, int period, const float* gamma, const float* beta,
+                                float eps, void* xn, void* scratch, size_t scratch_bytes, unsigned epoch,
+                                const float* row_scale, int rows_per_scale, void* stream) {
+  VPB_REQUIRE(M > 0 && N > 0, "gemm+layernorm: empty problem");
+  VPB_REQUIRE(epoch >= 1u && scratch != nullptr && scratch_bytes >= gemm_ln_scratch_bytes(M, N),
+              "gemm+layernorm: epoch must be >= 1 and the scratch %zu bytes", gemm_ln_scratch_bytes(M, N));
+  return gemm_bf16_ln(A, B, M, N, K, epilogue, bias, out, aux, period, gamma, beta, eps, xn, scratch, epoch, 0,
+                      as_stream(stream), row_scale, rows_per_scale);
+}
 size_t vpb_gemm_layernorm_scratch_bytes(int M, int N) { return M > 0 && N > 0 ? gemm_ln_scratch_bytes(M, N) : 0; }
 int vpb_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int M, int D, float eps,
                        void* stream) {

@@ -248,6 +248,25 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue,
   return -2;
 }
 
+// Split of the contraction for the accumulating epilogue (weight gradients: few output tiles, long K). Every work item
+// (tile, split) goes to one CTA of a persistent grid of `ctas`, so the cost is waves x (K blocks per item + the item's
+// fixed part: pipeline fill and the fp32 atomic epilogue, about 8 K blocks' worth). Picks the split count that
+// minimises it — e.g. fc1's gradient at 64 crops (72 tiles, 192 K blocks): 2 splits = one wave of 144 items instead of
+// the 5 splits = 2.4 -> 3 waves that "about two waves" used to give; at least 8 K blocks per split.
+static int pick_ksplit(int tiles, int k_blocks, int ctas) {
+  int best = 1;
+  long best_cost = -1;
+  for (int s = 1; s <= 32 && s * 8 <= k_blocks; ++s) {
+    const int kb_per = (k_blocks + s - 1) / s;
+    const int splits = (k_blocks + kb_per - 1) / kb_per;
+    if (splits != s) continue;                            // (same item size as a smaller s)
+    const long waves = (static_cast<long>(tiles) * splits + ctas - 1) / ctas;
+    const long cost = waves * (kb_per + 8);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
 int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias, void* out, int ldo,
               const float* aux, int period, int max_ctas, cudaStream_t stream, const LnFoldIn* ln,
               const GemmTrainAux* tr) {
@@ -298,14 +317,8 @@ int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, c
   }
   if (epilogue == EPI_ACCUM_F32) {
     VPB_REQUIRE(bias == nullptr && ldo % 4 == 0, "gemm: the accumulating epilogue takes no bias and needs ldo %% 4 == 0");
-    // about two waves of CTAs, at least 8 K blocks (512 rows of the contraction) per split, every split non-empty
     const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + bn - 1) / bn);
-    const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
-    int want = (2 * sm_count() + tiles - 1) / tiles;
-    if (want > k_blocks / 8) want = k_blocks / 8;
-    if (want < 1) want = 1;
-    const int kb_per = (k_blocks + want - 1) / want;
-    p.ksplit = (k_blocks + kb_per - 1) / kb_per;
+    p.ksplit = pick_ksplit(tiles, (K + GEMM_BK - 1) / GEMM_BK, max_ctas > 0 ? max_ctas : sm_count());
   }
   return launch_gemm(maps, p, bn, epilogue, cg, max_ctas, stream);
 }
@@ -420,12 +433,7 @@ int gemm_bf16_atb_accum(const void* At, const void* Bt, int M, int N, int K, flo
   maps.ln = maps.a;
   GemmParams p{M, N, K, nullptr, out, ldo, nullptr, 0, 1, nullptr, 1, nullptr, nullptr, nullptr, 0, 0u, 0.0f};
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + bn - 1) / bn);
-  const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
-  int want = (2 * sm_count() + tiles - 1) / tiles;
-  if (want > k_blocks / 8) want = k_blocks / 8;
-  if (want < 1) want = 1;
-  const int kb_per = (k_blocks + want - 1) / want;
-  p.ksplit = (k_blocks + kb_per - 1) / kb_per;
+  p.ksplit = pick_ksplit(tiles, (K + GEMM_BK - 1) / GEMM_BK, max_ctas > 0 ? max_ctas : sm_count());
   if (bn == 256) return launch_gemm_inst<256, EPI_ACCUM_F32, 1, 1>(maps, p, max_ctas, stream);
   if (bn == 128) return launch_gemm_inst<128, EPI_ACCUM_F32, 1, 1>(maps, p, max_ctas, stream);
   return launch_gemm_inst<64, EPI_ACCUM_F32, 1, 1>(maps, p, max_ctas, stream);

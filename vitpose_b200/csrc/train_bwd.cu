@@ -352,6 +352,9 @@ int gelu_bwd_bf16(const void* pre, const void* dh, void* dpre, long long n, cuda
 // One warp per row (row in registers, statistics recomputed from the saved fp32 x); dx is ADDED to dx_accum
 // (the gradient already flowing through the residual connection); dgamma / dbeta are accumulated per warp over
 // `rows_per_warp` rows in registers and then added atomically.
+// (Writing the bf16 branch gradient that the next Linear backward needs — cast_f32_bf16_colsum of dx_accum — from this
+// kernel as well was tried in round 2: 70 us per launch against 33 + 9 us for the two kernels at M = 12288; the kernel
+// runs one 8-warp block per SM and every extra dependent step of its row loop is exposed latency. Dropped.)
 // -------------------------------------------------------------------------------------------------
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,

@@ -54,8 +54,31 @@ def gemm_atb_accum(at, bt, out):
     return out
 
 
+class LnScratch:
+    """Statistics-exchange buffer of the fused-LayerNorm GEMMs for one (M, N), initialised once; successive launches on
+    it (same stream) take increasing epochs instead of two memsets each (see include/vitpose_b200.h)."""
+
+    def __init__(self, M, N, device):
+        self.M, self.N = M, N
+        self.nbytes = lib().vpb_gemm_layernorm_scratch_bytes(M, N)
+        self.buf = torch.empty(self.nbytes, device=device, dtype=torch.uint8)
+        self.stream = None
+        self.epoch = 0
+
+    def next_epoch(self):
+        st = stream_ptr()
+        if self.epoch == 0 or self.epoch >= (1 << 30) or st != self.stream:
+            if self.stream is not None and st != self.stream:
+                torch.cuda.synchronize(self.buf.device)          # (the launches on the other stream may still read it)
+            check(lib().vpb_gemm_layernorm_scratch_init(ptr(self.buf), self.nbytes, self.M, self.N, st),
+                  'vpb_gemm_layernorm_scratch_init')
+            self.stream, self.epoch = st, 0
+        self.epoch += 1
+        return self.epoch
+
+
 def gemm_layernorm(a, b, epilogue, bias, aux, gamma, beta, eps=1e-6, period=0, out=None, row_scale=None,
-                   rows_per_scale=0):
+                   rows_per_scale=0, scratch=None):
     """Residual-stream GEMM + the LayerNorm that follows it, one kernel: returns (out fp32 [M,N], xn bf16 [M,N]).
     `out` may be the residual tensor itself (in-place update, as the forward pass does)."""
     _need(a, BF16, 'a'); _need(b, BF16, 'b'); _need(aux, torch.float32, 'aux')
@@ -64,6 +87,13 @@ def gemm_layernorm(a, b, epilogue, bias, aux, gamma, beta, eps=1e-6, period=0, o
     assert b.shape[1] == K and epilogue in (_lib.EPI_RESID_F32, _lib.EPI_POS_F32)
     out = torch.empty(M, N, device=a.device, dtype=torch.float32) if out is None else out
     xn = torch.empty(M, N, device=a.device, dtype=BF16)
+    if scratch is not None:        # an LnScratch the caller keeps across launches: no memsets
+        assert (scratch.M, scratch.N) == (M, N)
+        check(lib().vpb_gemm_bf16_layernorm_seq(ptr(a), ptr(b), M, N, K, epilogue, ptr(bias), ptr(out), ptr(aux), period,
+                                                ptr(gamma), ptr(beta), float(eps), ptr(xn), ptr(scratch.buf),
+                                                scratch.nbytes, scratch.next_epoch(), ptr(row_scale),
+                                                int(rows_per_scale), stream_ptr()), 'vpb_gemm_bf16_layernorm_seq')
+        return out, xn
     nbytes = lib().vpb_gemm_layernorm_scratch_bytes(M, N)
     scratch = torch.empty(nbytes, device=a.device, dtype=torch.uint8)
     check(lib().vpb_gemm_bf16_layernorm(ptr(a), ptr(b), M, N, K, epilogue, ptr(bias), ptr(out), ptr(aux), period,

@@ -188,8 +188,12 @@ class _NetworkFn(torch.autograd.Function):
         scales = drop_path_scales(bb, n, img.device)
         patches = ops.im2col_patch16(img, flip=False)
         b0 = bb.blocks[0]
+        # one statistics-exchange scratch for the 25 fused-LayerNorm GEMMs of a step (kept on the model across steps)
+        lns = getattr(model, '_vpb_ln_scratch', None)
+        if lns is None or (lns.M, lns.N) != (M, D) or lns.buf.device != img.device:
+            lns = model._vpb_ln_scratch = ops.LnScratch(M, D, img.device)
         x, xn = ops.gemm_layernorm(patches, pe.w, EPI_POS, pe.b, pos_tok, b0.norm1.weight.detach(),
-                                   b0.norm1.bias.detach(), 1e-6, period=T)
+                                   b0.norm1.bias.detach(), 1e-6, period=T, scratch=lns)
         acts = []
         for l, blk in enumerate(bb.blocks):
             w = blocks[l]
@@ -199,7 +203,7 @@ class _NetworkFn(torch.autograd.Function):
             attn = attn.view(M, D)
             s1, s2 = scales[l]
             x_mid, xn2 = ops.gemm_layernorm(attn, w['proj'].w, EPI_RESID, w['proj'].b, x, blk.norm2.weight.detach(),
-                                            blk.norm2.bias.detach(), 1e-6, row_scale=s1, rows_per_scale=T)
+                                            blk.norm2.bias.detach(), 1e-6, row_scale=s1, rows_per_scale=T, scratch=lns)
             if FUSE_MLP:      # one kernel: h = gelu(pre) for fc2 and the bf16 pre-activation for the backward pass
                 h, pre = ops.gemm_gelu_save(xn2, w['fc1'].w, w['fc1'].b)
             else:
@@ -207,7 +211,7 @@ class _NetworkFn(torch.autograd.Function):
                 h = ops.gelu_fwd(pre)
             nxt = bb.blocks[l + 1].norm1 if l + 1 < depth else bb.last_norm
             x, xn = ops.gemm_layernorm(h, w['fc2'].w, EPI_RESID, w['fc2'].b, x_mid, nxt.weight.detach(),
-                                       nxt.bias.detach(), 1e-6, row_scale=s2, rows_per_scale=T)
+                                       nxt.bias.detach(), 1e-6, row_scale=s2, rows_per_scale=T, scratch=lns)
             a.update(qkv=qkv, attn=attn, lse=lse, x_mid=x_mid, xn2=xn2, pre=pre, h=h, s1=s1, s2=s2)
             acts.append(a)
         s.update(patches=patches, acts=acts, x_final=x, blocks=blocks, pe=pe)
@@ -330,11 +334,6 @@ class _NetworkFn(torch.autograd.Function):
         # ---- last_norm, then the blocks in reverse
         exchange()
         dx = scratch_zeros(M, D)
-        ln = bb.last_norm
-        dg_, db_ = zeros(D), zeros(D)
-        ops.layernorm_bwd(s['x_final'], ln.weight.detach(), dact, dx, dg_, db_, 1e-6)
-        g['backbone.last_norm.weight'], g['backbone.last_norm.bias'] = dg_, db_
-
         trainable = {nm for nm, p in _param_list(model) if p.requires_grad}
 
         def linear_bwd(name, lin, dy_bf16, x_bf16, want_dx=True, dbias=None):
@@ -352,19 +351,26 @@ class _NetworkFn(torch.autograd.Function):
                 g[name + '.bias'] = dbias
             return ops.gemm(dy_bf16, lin.wt, EPI_BIAS) if want_dx else None
 
-        def branch_grad(dx_f32, scale, bias_name, n_out):
-            """bf16 gradient of a residual branch (dx times the stochastic-depth factor of the crop) and, from the same
-            pass, the bias gradient of the Linear layer that ends the branch (None if that bias is frozen)."""
+        def norm_bwd(pfx, norm, x_saved, dy_bf16, scale, bias_name):
+            """LayerNorm backward into the residual gradient dx (+ dgamma / dbeta into g), then the bf16 output gradient
+            of the residual branch that ends in this stream: dx times the stochastic-depth factor of the crop, and the
+            bias gradient of the branch's last Linear layer (None if frozen; from the cast's own pass when FUSE_MLP)."""
+            dg_, db_ = zeros(D), zeros(D)
+            g[pfx + '.weight'], g[pfx + '.bias'] = dg_, db_
+            ops.layernorm_bwd(x_saved, norm.weight.detach(), dy_bf16, dx, dg_, db_, 1e-6)
             if FUSE_MLP and bias_name in trainable:
-                db = zeros(n_out)
-                return ops.cast_bf16_colsum(dx_f32, db, scale, T), db
-            return ops.cast_bf16(dx_f32, scale, T), None
+                dbias = zeros(D)
+                return ops.cast_bf16_colsum(dx, dbias, scale, T), dbias
+            return ops.cast_bf16(dx, scale, T), None
 
-        for l in range(len(bb.blocks) - 1, -1, -1):
-            a, w, blk = s['acts'][l], s['blocks'][l], bb.blocks[l]
+        L = len(bb.blocks)
+        acts = s['acts']
+        dyb, db2 = norm_bwd('backbone.last_norm', bb.last_norm, s['x_final'], dact, acts[L - 1]['s2'],
+                            f'backbone.blocks.{L - 1}.mlp.fc2.bias')
+        for l in range(L - 1, -1, -1):
+            a, w, blk = acts[l], s['blocks'][l], bb.blocks[l]
             pfx = f'backbone.blocks.{l}.'
-            # x_out = x_mid + fc2(gelu(fc1(norm2(x_mid))))            (vit.py:139)
-            dyb, db2 = branch_grad(dx, a['s2'], pfx + 'mlp.fc2.bias', D)   # gradient of the (dropped / rescaled) branch
+            # x_out = x_mid + fc2(gelu(fc1(norm2(x_mid))))            (vit.py:139); dyb = gradient of that branch
             if FUSE_MLP:
                 # fc2's input gradient with the GELU backward in its epilogue (+ fc1's bias gradient as column sums)
                 linear_bwd(pfx + 'mlp.fc2', w['fc2'], dyb, a['h'], want_dx=False, dbias=db2)
@@ -374,23 +380,21 @@ class _NetworkFn(torch.autograd.Function):
                 dh = linear_bwd(pfx + 'mlp.fc2', w['fc2'], dyb, a['h'], dbias=db2)
                 dpre, db1 = ops.gelu_bwd(a['pre'], dh), None
             dxn2 = linear_bwd(pfx + 'mlp.fc1', w['fc1'], dpre, a['xn2'], dbias=db1)
-            dg_, db_ = zeros(D), zeros(D)
-            ops.layernorm_bwd(a['x_mid'], blk.norm2.weight.detach(), dxn2, dx, dg_, db_, 1e-6)
-            g[pfx + 'norm2.weight'], g[pfx + 'norm2.bias'] = dg_, db_
+            dyb, dbp = norm_bwd(pfx + 'norm2', blk.norm2, a['x_mid'], dxn2, a['s1'], pfx + 'attn.proj.bias')
             # x_mid = x_in + proj(attention(qkv(norm1(x_in))))        (vit.py:138)
-            dyb, dbp = branch_grad(dx, a['s1'], pfx + 'attn.proj.bias', D)
             dattn = linear_bwd(pfx + 'attn.proj', w['proj'], dyb, a['attn'], dbias=dbp)
             dqkv = ops.attention_bwd(a['qkv'].view(n, T, 3 * D), a['attn'].view(n, T, D), a['lse'],
                                      dattn.view(n, T, D), heads)
             dxn1 = linear_bwd(pfx + 'attn.qkv', w['qkv'], dqkv.view(M, 3 * D), a['xn1'])
-            dg_, db_ = zeros(D), zeros(D)
-            ops.layernorm_bwd(a['x_in'], blk.norm1.weight.detach(), dxn1, dx, dg_, db_, 1e-6)
-            g[pfx + 'norm1.weight'], g[pfx + 'norm1.bias'] = dg_, db_
-            s['acts'][l] = None                               # activations of this block are dead
+            if l > 0:
+                dyb, db2 = norm_bwd(pfx + 'norm1', blk.norm1, a['x_in'], dxn1, acts[l - 1]['s2'],
+                                    f'backbone.blocks.{l - 1}.mlp.fc2.bias')
+            else:       # the stream below block 0 is the patch embedding (no stochastic depth)
+                dyb, db2 = norm_bwd(pfx + 'norm1', blk.norm1, a['x_in'], dxn1, None, 'backbone.patch_embed.proj.bias')
+            acts[l] = None                                    # activations of this block are dead
             exchange()
         # ---- patch embed (vit.py:159-165) + pos embed (vit.py:320)
-        dyb = ops.cast_bf16(dx)
-        linear_bwd('backbone.patch_embed.proj', s['pe'], dyb, s['patches'], want_dx=False)
+        linear_bwd('backbone.patch_embed.proj', s['pe'], dyb, s['patches'], want_dx=False, dbias=db2)
         if 'backbone.patch_embed.proj.weight' in g:
             g['backbone.patch_embed.proj.weight'] = g['backbone.patch_embed.proj.weight'].view(
                 bb.patch_embed.proj.weight.shape)
