@@ -34,7 +34,8 @@ def _cos(a, b):
 
 @pytest.mark.parametrize('name,n,depth,drop,fused', [('tiny', 4, 2, 0.0, True), ('B-classic-17', 3, 2, 0.0, True),
                                                      ('B-classic-17', 2, 12, 0.0, True), ('B-classic-17', 6, 3, 0.3, True),
-                                                     ('B-classic-17', 6, 3, 0.3, False)])
+                                                     ('B-classic-17', 6, 3, 0.3, False),
+                                                     ('L-classic-17', 2, 2, 0.0, True)])
 def test_forward_train_backward_vs_oracle(name, n, depth, drop, fused, monkeypatch):
     """drop > 0: stochastic depth with the SAME per-crop masks injected into both implementations. fused = the MLP /
     bias-gradient fusions of the training step (training.FUSE_MLP); the un-fused kernels stay covered by one case."""
@@ -43,6 +44,10 @@ def test_forward_train_backward_vs_oracle(name, n, depth, drop, fused, monkeypat
     monkeypatch.setattr(training, 'FUSE_MLP', fused)
     if name == 'tiny':
         cfg = configs.tiny_model_cfg(5)
+    elif name == 'L-classic-17':      # ViTPose-L with the classic decoder (the reference trains it: logs/vitpose-l.log.json)
+        cfg = configs.baseline_model_cfg('B-classic-17')
+        cfg['backbone'].update(embed_dim=1024, num_heads=16)
+        cfg['keypoint_head'].update(in_channels=1024)
     else:
         cfg = configs.baseline_model_cfg(name)
     cfg['backbone'].update(depth=depth, drop_path_rate=0.0)

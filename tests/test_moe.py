@@ -126,6 +126,15 @@ def test_topdown_moe_mixed_batch_vs_oracle():
     ref2 = VT.forward_test(sd, img, metas, ocfg, return_heatmap=True)
     assert np.abs(r2['output_heatmap'] - ref2['output_heatmap']).max() < 1e-2
     assert np.abs(ref2['output_heatmap'] - ref['output_heatmap']).max() > 10 * err
+    # the three per-dataset engines share every backbone tensor except mlp.fc2 (one backbone + 3 x fc2 in HBM)
+    engines = [model.backbone.engine(model.keypoint_head, d) for d in range(3)]
+    base = engines[0].weights if engines[0].weights.shared_bytes == 0 else engines[1].weights
+    others = [e.weights for e in engines if e.weights is not base]
+    total = sum(t.numel() * t.element_size() for t in base.by_id.values())
+    for w in others:
+        assert w.shared_bytes > 0.5 * total, (w.shared_bytes, total)
+        n_private = sum(1 for i in w.by_id if w.by_id[i].data_ptr() != base.by_id[i].data_ptr())
+        assert n_private <= 4 * len(model.backbone.blocks), n_private      # fc2 weight + bias (+ unkeyed small ones)
     feats = model.backbone(img.cuda(), torch.tensor([1, 0, 2, 1, 0]))
     f_ref = VT.vit_features(sd, img, 2, 2, dataset_source=torch.tensor([1, 0, 2, 1, 0]))
     assert (feats.cpu() - f_ref).abs().max() < 0.05 * max(1.0, float(f_ref.abs().max()))

@@ -70,7 +70,12 @@ class ViTMoE(ViT):
             if head is not None:
                 sd.update({'keypoint_head.' + k: v for k, v in head.state_dict().items()})
                 head_cfg = head.cfg_dict()
-            cached = (key, VitPoseEngine(self._cfg, head_cfg, sd, device=dev))
+            # The per-dataset networks differ in mlp.fc2 only (vit_moe.py:107-111: the expert owns the last
+            # part_features output columns): every other repacked tensor is shared with an engine already built for
+            # another dataset at the same weights version, so num_expert engines cost one backbone + num_expert x fc2.
+            donor = next((e for k, e in self._engines.values() if k[1:] == key[1:] and e.device == dev), None)
+            cached = (key, VitPoseEngine(self._cfg, head_cfg, sd, device=dev, share_weights_from=donor,
+                                         private_keys=('.mlp.fc2.',)))
             self._engines[dataset_idx] = cached
         return cached[1]
 

@@ -97,23 +97,41 @@ def fold_bn(g, b, mean, var, eps=1e-5):
 class PackedWeights:
     """Device buffers + the ctypes vpb_weights struct that points at them."""
 
-    def __init__(self, state_dict, desc, device, backbone_prefix='backbone.', head_prefix='keypoint_head.'):
+    def __init__(self, state_dict, desc, device, backbone_prefix='backbone.', head_prefix='keypoint_head.',
+                 share=None, private=()):
+        """``share``: another PackedWeights built from the same module at the same weights version; every repacked
+        tensor is taken from it instead of being converted again, except those made from state-dict keys that contain
+        one of the ``private`` substrings (ViTPose+: only mlp.fc2 differs between the per-dataset networks)."""
         sd = state_dict
         dev = device
         D, L = desc.embed_dim, desc.depth
         self.keep = []          # owns every tensor the struct points to
+        self.by_id = {}         # conversion order -> device tensor (what a later `share=` reuses)
+        self.shared_bytes = 0
+        pending = [None]        # state-dict key of the tensor being converted (set by g / h below)
+
+        def convert(t, make):
+            idx, key = len(self.by_id), pending[0]
+            pending[0] = None
+            if share is not None and key is not None and not any(p in key for p in private) and idx in share.by_id:
+                out = share.by_id[idx]
+                self.shared_bytes += out.numel() * out.element_size()
+            else:
+                out = make(t)
+            self.by_id[idx] = out
+            self.keep.append(out)
+            return out
 
         def dev_f32(t):
-            t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
-            self.keep.append(t)
-            return t
+            return convert(t, lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous())
 
         def dev_bf16(t):
-            t = t.detach().to(device=dev, dtype=torch.float32).to(BF16).contiguous()
-            self.keep.append(t)
-            return t
+            return convert(t, lambda t: t.detach().to(device=dev, dtype=torch.float32).to(BF16).contiguous())
 
-        g = lambda k: sd[backbone_prefix + k]
+        def g(k):
+            pending[0] = backbone_prefix + k
+            return sd[backbone_prefix + k]
+
         w = Weights()
         self.patch_w = dev_bf16(g('patch_embed.proj.weight').reshape(D, -1))
         w.patch_w = ptr(self.patch_w)
@@ -185,12 +203,15 @@ DECODE_MODES = {'none': _lib.DECODE_NONE, 'default': _lib.DECODE_DEFAULT, 'unbia
 class VitPoseEngine:
     """Runs backbone + head + decode for batches of crops on one GPU."""
 
-    def __init__(self, backbone_cfg, head_cfg, state_dict, device='cuda', max_batch=64):
+    def __init__(self, backbone_cfg, head_cfg, state_dict, device='cuda', max_batch=64, share_weights_from=None,
+                 private_keys=()):
         _lib.require_cuda()
         lib()
         self.device = torch.device(device)
         self.desc = model_desc_from_cfg(backbone_cfg, head_cfg)
-        self.weights = PackedWeights(state_dict, self.desc, self.device)
+        self.weights = PackedWeights(state_dict, self.desc, self.device,
+                                     share=None if share_weights_from is None else share_weights_from.weights,
+                                     private=private_keys)
         self._ws = None
         self._ws_images = 0
         self.max_batch = max_batch
