@@ -373,19 +373,30 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int row = row0; row < min(M, row0 + rows_per_warp); ++row) {
+  // Two rows in flight: the loads of row r + 1 (x, dy and the dx_accum row it updates) are issued before row r is
+  // processed, so the three shuffle reductions of a row hide the next row's memory latency (one 8-warp block per SM
+  // cannot hide it by occupancy: 33 -> see profiles/r02_summary.md per launch at M = 12288).
+  struct Row { float4 v[NV]; uint2 d[NV]; float4 a[NV]; };
+  auto load_row = [&](Row& r, int row) {
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
     const uint2* dr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(row) * D);
-    float4 v[NV], d[NV];
+    const float4* o = reinterpret_cast<const float4*>(dx_accum + static_cast<size_t>(row) * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      r.v[i] = xr[i * 32 + lane];
+      r.d[i] = dr[i * 32 + lane];
+      r.a[i] = o[i * 32 + lane];
+    }
+  };
+  auto process_row = [&](Row& r, int row) {
+    float4 d[NV];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      v[i] = xr[i * 32 + lane];
-      const uint2 raw = dr[i * 32 + lane];
-      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.d[i].x));
+      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.d[i].y));
       d[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      s += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -393,8 +404,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      float4& v = r.v[i];
+      v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
+      q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
@@ -402,13 +414,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;        // xhat
+      float4& v = r.v[i];
+      v.x *= rstd; v.y *= rstd; v.z *= rstd; v.w *= rstd;        // xhat
       db[i].x += d[i].x; db[i].y += d[i].y; db[i].z += d[i].z; db[i].w += d[i].w;
-      dg[i].x = fmaf(d[i].x, v[i].x, dg[i].x); dg[i].y = fmaf(d[i].y, v[i].y, dg[i].y);
-      dg[i].z = fmaf(d[i].z, v[i].z, dg[i].z); dg[i].w = fmaf(d[i].w, v[i].w, dg[i].w);
+      dg[i].x = fmaf(d[i].x, v.x, dg[i].x); dg[i].y = fmaf(d[i].y, v.y, dg[i].y);
+      dg[i].z = fmaf(d[i].z, v.z, dg[i].z); dg[i].w = fmaf(d[i].w, v.w, dg[i].w);
       d[i].x *= gm[i].x; d[i].y *= gm[i].y; d[i].z *= gm[i].z; d[i].w *= gm[i].w;   // g = dy * gamma
       c1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
-      c2 += (d[i].x * v[i].x + d[i].y * v[i].y) + (d[i].z * v[i].z + d[i].w * v[i].w);
+      c2 += (d[i].x * v.x + d[i].y * v.y) + (d[i].z * v.z + d[i].w * v.w);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -420,12 +433,32 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     float4* o = reinterpret_cast<float4*>(dx_accum + static_cast<size_t>(row) * D);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      float4 a = o[i * 32 + lane];
-      a.x += rstd * (d[i].x - c1 - v[i].x * c2);
-      a.y += rstd * (d[i].y - c1 - v[i].y * c2);
-      a.z += rstd * (d[i].z - c1 - v[i].z * c2);
-      a.w += rstd * (d[i].w - c1 - v[i].w * c2);
+      float4 a = r.a[i];
+      const float4& v = r.v[i];
+      a.x += rstd * (d[i].x - c1 - v.x * c2);
+      a.y += rstd * (d[i].y - c1 - v.y * c2);
+      a.z += rstd * (d[i].z - c1 - v.z * c2);
+      a.w += rstd * (d[i].w - c1 - v.w * c2);
       o[i * 32 + lane] = a;
+    }
+  };
+  const int row_end = min(M, row0 + rows_per_warp);
+  if constexpr (NV <= 6) {
+    Row ra, rb;
+    if (row0 < row_end) load_row(ra, row0);
+    for (int row = row0; row < row_end; row += 2) {
+      if (row + 1 < row_end) load_row(rb, row + 1);
+      process_row(ra, row);
+      if (row + 1 < row_end) {
+        if (row + 2 < row_end) load_row(ra, row + 2);
+        process_row(rb, row + 1);
+      }
+    }
+  } else {          // D = 1024 / 1280: two rows do not fit the register file (372 / 744 bytes of spills): one at a time
+    Row ra;
+    for (int row = row0; row < row_end; ++row) {
+      load_row(ra, row);
+      process_row(ra, row);
     }
   }
   // block-level reduction of the per-warp dgamma / dbeta partials, then one atomic per column per block
