@@ -311,6 +311,13 @@ int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, c
                                            (reinterpret_cast<uintptr_t>(tr->pre_out) & 15) == 0),
                 "gemm: a pre-activation output needs the GELU epilogue, N %% 8 == 0 and a 16-byte aligned buffer");
     VPB_REQUIRE(tr->colsum_out == nullptr || epilogue == EPI_DGELU_BF16, "gemm: column sums come with the gelu-backward epilogue");
+    if (tr->pre_out != nullptr || tr->pre_in != nullptr) {     // [M, N] bf16, same boxes as the output
+      uint64_t dims_o[2] = {(uint64_t)N, (uint64_t)M};
+      uint64_t str_o[1] = {(uint64_t)N * 2};
+      uint32_t box_o[2] = {64u, GEMM_BM};
+      void* pre = tr->pre_out != nullptr ? tr->pre_out : const_cast<void*>(tr->pre_in);
+      if (make_tma_desc(&maps.aux, TMA_BF16, pre, 2, dims_o, str_o, box_o, TMA_SWIZZLE_128B)) return -1;
+    }
     p.pre_out = tr->pre_out;
     p.pre_in = tr->pre_in;
     p.colsum_out = tr->colsum_out;

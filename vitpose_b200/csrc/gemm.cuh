@@ -84,7 +84,7 @@ struct GemmParams {
   // and one (mean, M2) pair per row and column tile — single pass, no exchange between CTAs, TMEM released as soon as
   // the tile is in registers. The consumer (EPI_BIAS_BF16 / EPI_GELU_BF16 with ln_stats != null) merges the pairs of
   // its rows and applies rstd, mean, s and c (passed as `bias`) in its epilogue.
-  // training (EPI_GELU_SAVE_BF16): also store the bf16 pre-activation acc + bias [M, N] (row pitch N) for the backward pass
+  // training (EPI_GELU_SAVE_BF16): the bf16 pre-activation acc + bias [M, N] is stored too (through the aux tensor map)
   void* pre_out;
   // training (EPI_DGELU_BF16): the saved pre-activation [M, N], and optionally where to add the column sums of out
   const void* pre_in;
@@ -162,7 +162,7 @@ __host__ __device__ constexpr int gemm_res_slots(int bn, int epi, int cg) {
 __host__ __device__ constexpr int gemm_epi_smem(int bn, int epi, int cg) {
   return !gemm_epi_staged(epi) ? 0
          : !gemm_epi_adds_tile(epi)
-             ? 2 * GEMM_STAGING_BYTES
+             ? ((epi == EPI_GELU_SAVE_BF16 || epi == EPI_DGELU_BF16) ? 4 : 2) * GEMM_STAGING_BYTES
              : (gemm_ln_split(epi) ? 2 : 1) * (gemm_res_slots(bn, epi, cg) * GEMM_STAGING_BYTES +
                                                (gemm_epi_ln(epi) ? 2048 : 0));
 }
@@ -686,6 +686,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint32_t chunk_seq = 0;                // running chunk counter of this group: staging buffer = chunk_seq & 1
     int const_n_blk = -1;                  // n-tile whose bias / gamma / beta columns are in shared memory
     long long w_tfull = 0, w_rfull = 0, w_sib = 0, w_bar = 0, n_epi_tiles = 0;
+    // EPI_DGELU_BF16: the saved pre-activation of a chunk ([128 rows x 64 columns] bf16) arrives by TMA in the group's
+    // second staging box (2 + grp), one chunk ahead: requested by the group's first thread as soon as all its threads
+    // have read the previous one, on the (otherwise unused) barrier res_full[grp][0].
+    uint32_t pre_phase = 0;
+    auto request_pre = [&](int tile_, int c_) {
+      const int mb = ((tile_ / p.ksplit) / n_tiles) * CG + cta_rank, nb = (tile_ / p.ksplit) % n_tiles;
+      mbar_arrive_expect_tx(&res_full[grp][0], GEMM_STAGING_BYTES);
+      tma_load_2d(s_out + (2 + grp) * GEMM_STAGING_BYTES, &tma_aux, &res_full[grp][0], nb * BN + c_ * 64, mb * GEMM_BM);
+    };
+    if constexpr (EPI == EPI_DGELU_BF16) {
+      if (etid == 0 && tile0 < num_tiles && cgrp < BN / 64) request_pre(tile0, cgrp);
+    }
     for (int tile = tile0 + (LN_SPLIT ? grp : 0) * tile_step; tile < num_tiles; tile += tile_step * TG) {
       const int m_blk = ((tile / p.ksplit) / n_tiles) * CG + cta_rank;
       const int n_blk = (tile / p.ksplit) % n_tiles;
@@ -971,12 +983,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           // training epilogues address global memory directly: this thread's row, this chunk's 64 columns (128 bytes)
           const int g_row = m_blk * GEMM_BM + r, g_col = n_blk * BN + c * CHUNK;
           uint4 pre8[EPI == EPI_DGELU_BF16 ? CHUNK / 8 : 1];
-          if constexpr (EPI == EPI_DGELU_BF16) {      // saved pre-activation, requested while the TMEM load is in flight
-            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.pre_in) +
-                                                              static_cast<size_t>(min(g_row, p.M - 1)) * p.N + g_col);
+          if constexpr (EPI == EPI_DGELU_BF16) {      // this thread's row of the pre-activation box (zero past M / N)
+            mbar_wait(&res_full[grp][0], pre_phase);
+            pre_phase ^= 1u;
+            const uint32_t prow = smem_u32(s_out) + (2 + grp) * GEMM_STAGING_BYTES + r * 128;
 #pragma unroll
-            for (int u = 0; u < CHUNK / 8; ++u)
-              pre8[u] = (g_col + 8 * u + 8 <= p.N) ? __ldg(src + u) : make_uint4(0u, 0u, 0u, 0u);
+            for (int u = 0; u < CHUNK / 8; ++u) pre8[u] = lds_u4(prow + ((u ^ (r & 7)) * 16));
           }
           tmem_ld_wait();
           if (c + GROUPS >= NCHUNK) {       // this group's last chunk is in registers: hand TMEM back to the MMA warp
@@ -1036,32 +1048,50 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                   if (col < p.N) atomicAdd(p.colsum_out + col, sum);
                 }
               }
-            } else {
-            const bool save_pre = EPI == EPI_GELU_SAVE_BF16 && g_row < p.M;
-            uint4* pre_dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.pre_out) +
-                                                      static_cast<size_t>(g_row) * p.N + g_col);
-            (void)save_pre; (void)pre_dst;
+            } else if constexpr (EPI == EPI_GELU_SAVE_BF16) {
+              // training forward of fc1: the pre-activation the backward pass differentiates goes out through a second
+              // staging box per group (boxes 2 + grp) and its own TMA store, then the activation as usual
+              uint32_t pw[CHUNK / 2];
 #pragma unroll
-            for (int u = 0; u < CHUNK / 8; ++u) {
-              uint32_t pw[4];
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const int j = 4 * u + jj;
+              for (int j = 0; j < CHUNK / 2; ++j) {
                 const float2 b2 = *reinterpret_cast<const float2*>(bias_c + 2 * j);
-                float2 f = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), b2);
-                if constexpr (EPI == EPI_GELU_SAVE_BF16) pw[jj] = pack_bf16x2(f.x, f.y);
-                if constexpr (gemm_epi_gelu(EPI)) f = gelu_erf2(f);
+                const float2 f = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), b2);
+                pw[j] = pack_bf16x2(f.x, f.y);
+              }
+              if (etid == 0) tma_store_wait_read<0>();       // both boxes of this group: their last stores have read them
+              asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+              const uint32_t prow = smem_u32(ring) + (2 + grp) * GEMM_STAGING_BYTES + r * 128;
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                sts_u4(prow + ((u ^ (r & 7)) * 16), pw[4 * u], pw[4 * u + 1], pw[4 * u + 2], pw[4 * u + 3]);
+#pragma unroll
+              for (int j = 0; j < CHUNK / 2; ++j) {
+                const float2 b2 = *reinterpret_cast<const float2*>(bias_c + 2 * j);
+                const float2 f = gelu_erf2(
+                    __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), b2));
                 v[j] = pack_bf16x2(f.x, f.y);
               }
-              if constexpr (EPI == EPI_GELU_SAVE_BF16) {   // the pre-activation the backward pass differentiates
-                if (save_pre && g_col + 8 * u + 8 <= p.N) pre_dst[u] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-              }
+            } else {
+#pragma unroll
+            for (int j = 0; j < CHUNK / 2; ++j) {
+              const float2 b2 = *reinterpret_cast<const float2*>(bias_c + 2 * j);
+              float2 f = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), b2);
+              if constexpr (gemm_epi_gelu(EPI)) f = gelu_erf2(f);
+              v[j] = pack_bf16x2(f.x, f.y);
             }
             }
             // ... then wait until the TMA store that last read this group's staging box has finished reading it
             // (that latency is now hidden behind the math), and write the row
-            if (etid == 0) tma_store_wait_read<0>();
-            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if constexpr (EPI != EPI_GELU_SAVE_BF16) {
+              if (etid == 0) tma_store_wait_read<0>();
+              asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            }
+            if constexpr (EPI == EPI_DGELU_BF16) {     // every thread of the group has its pre-activation row: next box
+              if (etid == 0) {
+                if (c + GROUPS < NCHUNK) request_pre(tile, c + GROUPS);
+                else if (tile + tile_step * TG < num_tiles) request_pre(tile + tile_step * TG, cgrp);
+              }
+            }
 #pragma unroll
             for (int u = 0; u < 8; ++u)
               sts_u4(srow + ((u ^ (r & 7)) * 16), v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
@@ -1073,6 +1103,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               mbar_arrive(&rready[buf]);                   // the ring warp stores the slot and recycles it
             } else {
               tma_store_2d(&tma_out, ring + buf * GEMM_STAGING_BYTES, n_blk * BN + c * CHUNK, m_blk * GEMM_BM);
+              if constexpr (EPI == EPI_GELU_SAVE_BF16)
+                tma_store_2d(&tma_aux, ring + (2 + grp) * GEMM_STAGING_BYTES, n_blk * BN + c * CHUNK, m_blk * GEMM_BM);
               tma_store_commit();
             }
           }
