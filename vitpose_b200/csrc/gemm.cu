@@ -120,7 +120,7 @@ int gemm_pick_cg(int M, int bn, int epilogue, int K) {
     const char* e = getenv("VPB_GEMM_PAIR128");
     pair128 = (e && atoi(e) == 0) ? 0 : 1;
   }
-  if (bn == 128 && pair128 && gemm_epi_ln(epilogue) && !gemm_epi_pos(epilogue) && M >= 1024) return 2;
+  if ((bn == 128 || bn == 192) && pair128 && gemm_epi_ln(epilogue) && !gemm_epi_pos(epilogue) && M >= 1024) return 2;
   if (!(bn == 256 && gemm_epi_staged(epilogue) && M >= 1024)) return 1;
   // measured (B200, M = 49152): qkv 1135 -> 1269, fc1 w/o GELU 1152 -> 1284, fc2 1080 -> 1218 TFLOP/s with pairs;
   // the short-K residual GEMM (attn.proj, K = D) is bound by its fp32 residual traffic and is ~3 % faster unpaired
@@ -191,6 +191,8 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue,
     if (bn == 256 && epilogue == EPI_POSTMA_LN_F32) return launch_gemm_inst<256, EPI_POSTMA_LN_F32, 2>(maps, p, max_ctas, stream);
     if (bn == 256 && epilogue == EPI_RESID_LNS_F32) return launch_gemm_inst<256, EPI_RESID_LNS_F32, 2>(maps, p, max_ctas, stream);
     if (bn == 256 && epilogue == EPI_POSTMA_LNS_F32) return launch_gemm_inst<256, EPI_POSTMA_LNS_F32, 2>(maps, p, max_ctas, stream);
+    if (bn == 192 && epilogue == EPI_RESID_LN_F32) return launch_gemm_inst<192, EPI_RESID_LN_F32, 2>(maps, p, max_ctas, stream);
+    if (bn == 192 && epilogue == EPI_RESID_LNS_F32) return launch_gemm_inst<192, EPI_RESID_LNS_F32, 2>(maps, p, max_ctas, stream);
     if (bn == 128 && epilogue == EPI_RESID_LN_F32) return launch_gemm_inst<128, EPI_RESID_LN_F32, 2>(maps, p, max_ctas, stream);
     if (bn == 128 && epilogue == EPI_RESID_LNS_F32) return launch_gemm_inst<128, EPI_RESID_LNS_F32, 2>(maps, p, max_ctas, stream);
     set_last_error("gemm: no CTA-pair kernel instance for BN=%d epilogue=%d", bn, epilogue);
@@ -223,15 +225,19 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int epilogue,
   VPB_GEMM_CASE(128, EPI_POSTMA_F32)
   VPB_GEMM_CASE(64, EPI_POSTMA_F32)
   VPB_GEMM_CASE(256, EPI_RESID_LN_F32)
+  VPB_GEMM_CASE(192, EPI_RESID_LN_F32)
   VPB_GEMM_CASE(128, EPI_RESID_LN_F32)
   VPB_GEMM_CASE(64, EPI_RESID_LN_F32)
   VPB_GEMM_CASE(256, EPI_POSTMA_LN_F32)
+  VPB_GEMM_CASE(192, EPI_POSTMA_LN_F32)
   VPB_GEMM_CASE(128, EPI_POSTMA_LN_F32)
   VPB_GEMM_CASE(64, EPI_POSTMA_LN_F32)
   VPB_GEMM_CASE(256, EPI_RESID_LNS_F32)
+  VPB_GEMM_CASE(192, EPI_RESID_LNS_F32)
   VPB_GEMM_CASE(128, EPI_RESID_LNS_F32)
   VPB_GEMM_CASE(64, EPI_RESID_LNS_F32)
   VPB_GEMM_CASE(256, EPI_POSTMA_LNS_F32)
+  VPB_GEMM_CASE(192, EPI_POSTMA_LNS_F32)
   VPB_GEMM_CASE(128, EPI_POSTMA_LNS_F32)
   VPB_GEMM_CASE(64, EPI_POSTMA_LNS_F32)
   VPB_GEMM_CASE(256, EPI_ACCUM_F32)
@@ -332,7 +338,18 @@ int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, c
 
 // ---- residual GEMM + fused LayerNorm ------------------------------------------------------------------------
 static int ln_row_blocks(int M) { return (M + 255) / 256 * 2; }          // 128-row blocks, padded to CTA pairs
-static int ln_bn(int N) { return N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 0)); }
+// column tile of the fused-LayerNorm GEMMs: the widest of 256 / 192 / 128 / 64 that divides N (ViTPose-S, N = 384: two
+// 192-wide tiles — 22 % fewer operand bytes per FLOP than three 128-wide ones; VPB_LN_BN192=0: the round-1 choice)
+static int ln_bn(int N) {
+  static int use192 = -1;
+  if (use192 < 0) {
+    const char* e = getenv("VPB_LN_BN192");
+    use192 = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (N % 256 == 0) return 256;
+  if (use192 && N % 192 == 0) return 192;
+  return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 0);
+}
 static size_t ln_region_words(int M, int N) {     // one 8-byte word per (row, n-tile), region padded to 256 bytes
   const int bn = ln_bn(N) >= 128 ? 128 : 64;      // room for the narrowest tiles a variant may pick
   const size_t n_tiles = (N + bn - 1) / bn;
@@ -396,8 +413,8 @@ int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue
   // 0.211 ms unsplit, 0.240 ms split at M = 49152)
   const bool short_k = K < 1536;
   int cg = gemm_pick_cg(M, bn, EPI_RESID_LNS_F32, K);
-  if (bn == 128 && epilogue != EPI_RESID_F32) cg = 1;     // (128-wide pair tiles: residual epilogues only)
-  const bool split = !fold && short_k && (bn <= 128 || cg == 2);   // (the folded form: one-group kernels only)
+  if (bn <= 192 && epilogue != EPI_RESID_F32) cg = 1;     // (128 / 192-wide pair tiles: residual epilogues only)
+  const bool split = !fold && short_k && (bn <= 192 || cg == 2);   // (the folded form: one-group kernels only)
   const int epi = epilogue == EPI_RESID_F32 ? (split ? EPI_RESID_LNS_F32 : EPI_RESID_LN_F32)
                                             : (split ? EPI_POSTMA_LNS_F32 : EPI_POSTMA_LN_F32);
   if (!split && short_k && !fold) cg = 1;     // short-K residual GEMMs are slightly faster unpaired (see gemm_pick_cg)
