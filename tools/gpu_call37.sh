@@ -1,0 +1,14 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+O=gpurun_out/r02_call37
+timeout 1500 python -m pytest tests -q -m gpu > $O.tests.txt 2>&1; echo "tests rc=$?" >> $O.tests.txt
+python -c "import __graft_entry__ as g; g.smoke()" > $O.smoke.txt 2>&1; echo "smoke rc=$?" >> $O.smoke.txt
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29537 bench.py --gpus 2 --steps 10 --warmup 3 > $O.bench2.json 2> $O.bench2.err
+grep -E "passed|failed|rc=|FAILED|Error" $O.tests.txt | tail; cat $O.smoke.txt | tail -3
+python - <<PY
+import json
+d=json.loads(open('$O.bench2.json').read().strip().splitlines()[-1])
+print('bench2', round(d['value']), d['ms_per_step'], round(d['e2e']['value']))
+for k,v in d.get('configs',{}).items(): print(' ',k, round(v['value']), round(v['ms_per_step'],2), round(v['e2e']['value']))
+PY
