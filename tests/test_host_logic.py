@@ -28,7 +28,8 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f'{name} declared in the header but not exported'
     assert set(declared) == set(_lib.EXPORTED_SYMBOLS)
-    assert _lib.lib().vpb_abi_version() == 2
+    assert _lib.lib().vpb_abi_version() == _lib.ABI_VERSION
+    assert f'#define VPB_ABI_VERSION {_lib.ABI_VERSION}' in header
 
 
 def test_struct_layout_matches_header():
