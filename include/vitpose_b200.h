@@ -227,6 +227,19 @@ int vpb_cast_f32_bf16(const float* in, void* out, long long n, const float* row_
 /* out[C] += sum over the R rows of in[R,C] (bf16, or fp32 when is_f32): bias / pos-embed gradients */
 int vpb_colsum_accumulate(const void* in, int is_f32, int R, int C, float* out, void* stream);
 /* nn.GELU (exact erf, vit.py:71-76): out = gelu(pre); dpre = dh * gelu'(pre) */
+/* Simple decoder (topdown_heatmap_simple_head.py:132-139 with num_deconv_layers = 0: ReLU -> bilinear x f ->
+ * Conv2d 3x3) in its un-materialised form, as vpb_vitpose_forward runs it, and its backward:
+ *   r = vpb_relu_bf16(tokens);  z fp32 [images, 9K, h*w] = vpb_gemm_bf16(r, W9 [9K, D] (row k*9 + ky*3 + kx),
+ *   VPB_EPI_NCHW_F32, period h*w);  heatmaps = vpb_simple_head_gather(z, bias)  (bilinear gather of the nine tap maps);
+ *   backward: dz bf16 [images*h*w, ldz] (token-major, column k*9+t, ldz >= 9K; pad columns are NOT written) =
+ *   vpb_simple_head_gather_bwd(dheatmaps); then two GEMMs on dz (input / weight gradient of the tap GEMM) and
+ *   vpb_relu_bwd_bf16(r, dr) = dr where r > 0. */
+int vpb_relu_bf16(const void* in, void* out, long long n, void* stream);
+int vpb_relu_bwd_bf16(const void* y, const void* dy, void* dx, long long n, void* stream);
+int vpb_simple_head_gather(const float* z, const float* bias, float* out, int images, int K, int h, int w, int factor,
+                           void* stream);
+int vpb_simple_head_gather_bwd(const float* dout, void* dz, int ldz, int images, int K, int h, int w, int factor,
+                               void* stream);
 /* Training-step fusions of the MLP (vit.py:64-73: fc1 -> nn.GELU -> fc2):
  *  vpb_gemm_bf16_gelu_save: out bf16 [M, ldo] = gelu_erf(A.B^T + bias) AND pre_out bf16 [M, N] = A.B^T + bias (the
  *    activation the backward pass differentiates; the GELU is evaluated on the fp32 value, before that rounding);

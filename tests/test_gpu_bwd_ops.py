@@ -119,6 +119,39 @@ def test_layernorm_bwd(D):
     _close('ln dbeta', db, br.grad, 2e-3)
 
 
+@pytest.mark.parametrize('n,K,h,w,f', [(3, 17, 16, 12, 4), (2, 5, 8, 6, 2)])
+def test_simple_head_gather_and_its_backward(n, K, h, w, f):
+    """The un-materialised simple decoder (bilinear x f of the nine tap maps + their shifted sum) and its transpose,
+    against F.interpolate + autograd (topdown_heatmap_simple_head.py:132-139,197-202 after the 1x1-tap split)."""
+    from vitpose_b200 import ops
+    g = torch.Generator().manual_seed(n * 100 + K)
+    z = torch.randn(n, K * 9, h * w, generator=g).to(_dev()).requires_grad_(True)
+    bias = torch.randn(K, generator=g).to(_dev())
+    H, W = h * f, w * f
+    up = F.interpolate(z.view(n, K * 9, h, w), scale_factor=f, mode='bilinear', align_corners=False).view(n, K, 9, H, W)
+    pad = F.pad(up, (1, 1, 1, 1))
+    ref = sum(pad[:, :, ky * 3 + kx, ky:ky + H, kx:kx + W] for ky in range(3) for kx in range(3)) + bias.view(1, K, 1, 1)
+    out = ops.simple_head_gather(z.detach().contiguous(), bias, K, h, w, f)
+    _close('gather', out, ref.detach(), 1e-5)
+    dout = torch.randn(n, K, H, W, generator=g).to(_dev())
+    ref.backward(dout)
+    ldz = (9 * K + 7) // 8 * 8
+    dz = ops.simple_head_gather_bwd(dout, h, w, f, ldz)                       # [n*h*w, ldz] bf16, column k*9+t
+    ref_dz = z.grad.view(n, K * 9, h * w).permute(0, 2, 1).reshape(n * h * w, K * 9)
+    _close('gather backward', dz[:, :9 * K], ref_dz, 1e-2)
+    assert (dz[:, 9 * K:] == 0).all()
+
+
+def test_relu_and_relu_bwd():
+    from vitpose_b200 import ops
+    x = _rand((192 * 3, 768), 51)
+    x.view(-1)[:16] = torch.tensor([0.0, -0.0, 1e-30, -1e-30] * 4, device=_dev()).to(BF16)
+    y = ops.relu(x)
+    assert torch.equal(y, torch.relu(x))
+    dy = _rand((192 * 3, 768), 52)
+    assert torch.equal(ops.relu_bwd(y, dy), torch.where(y > 0, dy, torch.zeros_like(dy)))
+
+
 @pytest.mark.parametrize('n,heads', [(2, 2), (3, 12)])
 def test_attention_bwd(n, heads):
     from vitpose_b200 import ops

@@ -35,7 +35,8 @@ def _cos(a, b):
 @pytest.mark.parametrize('name,n,depth,drop,fused', [('tiny', 4, 2, 0.0, True), ('B-classic-17', 3, 2, 0.0, True),
                                                      ('B-classic-17', 2, 12, 0.0, True), ('B-classic-17', 6, 3, 0.3, True),
                                                      ('B-classic-17', 6, 3, 0.3, False),
-                                                     ('L-classic-17', 2, 2, 0.0, True)])
+                                                     ('L-classic-17', 2, 2, 0.0, True),
+                                                     ('B-simple-17', 3, 2, 0.0, True)])
 def test_forward_train_backward_vs_oracle(name, n, depth, drop, fused, monkeypatch):
     """drop > 0: stochastic depth with the SAME per-crop masks injected into both implementations. fused = the MLP /
     bias-gradient fusions of the training step (training.FUSE_MLP); the un-fused kernels stay covered by one case."""
@@ -48,8 +49,13 @@ def test_forward_train_backward_vs_oracle(name, n, depth, drop, fused, monkeypat
         cfg = configs.baseline_model_cfg('B-classic-17')
         cfg['backbone'].update(embed_dim=1024, num_heads=16)
         cfg['keypoint_head'].update(in_channels=1024)
+    elif name == 'B-simple-17':       # the simple decoder (ReLU -> bilinear x4 -> 3x3 conv; logs/vitpose-*-simple.log.json)
+        cfg = configs.baseline_model_cfg('L-simple-17')
+        cfg['backbone'].update(embed_dim=768, num_heads=12)
+        cfg['keypoint_head'].update(in_channels=768)
     else:
         cfg = configs.baseline_model_cfg(name)
+    simple = cfg['keypoint_head'].get('num_deconv_layers', 3) == 0
     cfg['backbone'].update(depth=depth, drop_path_rate=0.0)
     K = cfg['keypoint_head']['out_channels']
     sd = synthetic.scaled_init_state_dict(cfg, 7)
@@ -79,7 +85,7 @@ def test_forward_train_backward_vs_oracle(name, n, depth, drop, fused, monkeypat
     torch.cuda.synchronize()
     assert abs(loss.item() - loss_ref.item()) <= 2e-2 * abs(loss_ref.item()), (loss.item(), loss_ref.item())
     # BatchNorm running statistics were updated as nn.BatchNorm2d(train) does
-    for i in (1, 4):
+    for i in (() if simple else (1, 4)):
         for b in ('running_mean', 'running_var'):
             k = f'keypoint_head.deconv_layers.{i}.{b}'
             assert _rel(model.state_dict()[k].cpu(), ref_sd[k]) < 2e-2, k
@@ -92,8 +98,10 @@ def test_forward_train_backward_vs_oracle(name, n, depth, drop, fused, monkeypat
             continue
         worst[nm] = (_rel(gr, rf), _cos(gr, rf))
     # Upstream of the first ReLU everything is a linear function of bf16-rounded operands: tight.
-    for nm in ('keypoint_head.final_layer.weight', 'keypoint_head.final_layer.bias',
-               'keypoint_head.deconv_layers.4.weight', 'keypoint_head.deconv_layers.4.bias'):
+    tight = ('keypoint_head.final_layer.weight', 'keypoint_head.final_layer.bias')
+    if not simple:
+        tight += ('keypoint_head.deconv_layers.4.weight', 'keypoint_head.deconv_layers.4.bias')
+    for nm in tight:
         assert worst[nm][0] < 0.02, (nm, worst[nm])
     # Below a ReLU the comparison is statistical: the GPU path keeps the conv outputs in bf16, so ~0.4 % of the
     # BatchNorm+ReLU units that sit within rounding distance of zero take the other branch than in the fp32 oracle,

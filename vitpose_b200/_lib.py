@@ -108,6 +108,10 @@ _SIGS = {
     'vpb_gemm_bf16_layernorm': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                         c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_int,
                                         c_void_p]),
+    'vpb_relu_bf16': (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p]),
+    'vpb_relu_bwd_bf16': (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p]),
+    'vpb_simple_head_gather': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'vpb_simple_head_gather_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'vpb_gemm_bf16_gelu_save': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                         c_void_p]),
     'vpb_gemm_bf16_gelu_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,

@@ -334,6 +334,18 @@ int vpb_gemm_bf16_layernorm(const void* A, const void* B, int M, int N, int K, i
   return gemm_bf16_ln(A, B, M, N, K, epilogue, bias, out, aux, period, gamma, beta, eps, xn, scratch, 1u, 0, stream,
                       row_scale, rows_per_scale);
 }
+int vpb_relu_bf16(const void* in, void* out, long long n, void* stream) { return relu_bf16(in, out, n, as_stream(stream)); }
+int vpb_relu_bwd_bf16(const void* y, const void* dy, void* dx, long long n, void* stream) {
+  return relu_bwd_bf16(y, dy, dx, n, as_stream(stream));
+}
+int vpb_simple_head_gather(const float* z, const float* bias, float* out, int images, int K, int h, int w, int factor,
+                           void* stream) {
+  return simple_head_gather(z, bias, out, images, K, h, w, factor, as_stream(stream));
+}
+int vpb_simple_head_gather_bwd(const float* dout, void* dz, int ldz, int images, int K, int h, int w, int factor,
+                               void* stream) {
+  return simple_head_gather_bwd(dout, dz, ldz, images, K, h, w, factor, as_stream(stream));
+}
 int vpb_gemm_bf16_gelu_save(const void* A, const void* B, int M, int N, int K, const float* bias, void* out, int ldo,
                             void* pre_out, void* stream) {
   const GemmTrainAux tr{pre_out, nullptr, nullptr};

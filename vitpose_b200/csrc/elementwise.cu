@@ -408,6 +408,106 @@ int simple_head_gather(const float* z, const float* bias, float* out, int images
 }
 
 // -------------------------------------------------------------------------------------------------
+// Backward of simple_head_gather (training of the simple decoder): dout fp32 [images, K, h*f, w*f] ->
+// dz bf16 [images * h * w, ldz] (TOKEN-major rows, column k * 9 + t: the A operand of the tap GEMM's input- and
+// weight-gradient GEMMs). out = sum_t shift_t(bilinear(z_t)), so dz_t = bilinear^T(shift_t^T(dout)), and the transposed
+// interpolation is separable like the forward one: first along y into shared memory (v[t][i][xx]), then along x.
+// One CTA per (image, keypoint); every (t, i, xx) / (t, i, j) element looks at the <= 3 f source rows / columns whose
+// interpolation touches it, with the same index / weight formulas as the forward kernel.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) simple_head_gather_bwd_kernel(const float* __restrict__ dout,
+                                                                      __nv_bfloat16* __restrict__ dz, int ldz, int K,
+                                                                      int h, int w, int f) {
+  extern __shared__ float s_dyn[];
+  const int img = blockIdx.x / K, k = blockIdx.x % K;
+  const int T = h * w, H = h * f, W = w * f;
+  float* s_d = s_dyn;                           // [H][W]
+  float* s_v = s_d + H * W;                     // [9][h][W]
+  const float* src = dout + (static_cast<size_t>(img) * K + k) * H * W;
+  for (int i = threadIdx.x; i < H * W; i += blockDim.x) s_d[i] = __ldg(src + i);
+  __syncthreads();
+  const float inv = 1.0f / f;
+  auto src_index = [&](int o, int n_src, int& i0, int& i1, float& l) {   // as the forward kernel (align_corners=False)
+    float s = (o + 0.5f) * inv - 0.5f;
+    s = s < 0.f ? 0.f : s;
+    i0 = static_cast<int>(s);
+    i1 = i0 + (i0 < n_src - 1 ? 1 : 0);
+    l = s - i0;
+  };
+  for (int e = threadIdx.x; e < 9 * h * W; e += blockDim.x) {
+    const int xx = e % W, i = (e / W) % h, t = e / (W * h);
+    const int ky = t / 3, kx = t % 3;
+    const int Xo = xx - kx + 1;                 // output column whose tap t reads upsampled column xx
+    float acc = 0.f;
+    if (Xo >= 0 && Xo < W) {
+      const int lo = max(0, f * (i - 1)), hi = min(H - 1, f * (i + 2));
+      for (int yy = lo; yy <= hi; ++yy) {
+        int y0, y1;
+        float ly;
+        src_index(yy, h, y0, y1, ly);
+        const float wgt = (y0 == i ? 1.f - ly : 0.f) + (y1 == i ? ly : 0.f);
+        const int Yo = yy - ky + 1;
+        if (wgt != 0.f && Yo >= 0 && Yo < H) acc = fmaf(wgt, s_d[Yo * W + Xo], acc);
+      }
+    }
+    s_v[e] = acc;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 9 * T; e += blockDim.x) {
+    const int j = e % w, i = (e / w) % h, t = e / T;
+    const float* row = s_v + (t * h + i) * W;
+    float acc = 0.f;
+    const int lo = max(0, f * (j - 1)), hi = min(W - 1, f * (j + 2));
+    for (int xx = lo; xx <= hi; ++xx) {
+      int x0, x1;
+      float lx;
+      src_index(xx, w, x0, x1, lx);
+      const float wgt = (x0 == j ? 1.f - lx : 0.f) + (x1 == j ? lx : 0.f);
+      acc = fmaf(wgt, row[xx], acc);
+    }
+    dz[(static_cast<size_t>(img) * T + i * w + j) * ldz + k * 9 + t] = __float2bfloat16_rn(acc);
+  }
+}
+
+int simple_head_gather_bwd(const float* dout, void* dz, int ldz, int images, int K, int h, int w, int factor,
+                           cudaStream_t stream) {
+  VPB_REQUIRE(images > 0 && K > 0 && factor >= 1 && ldz >= 9 * K, "simple_head_gather_bwd: bad shape (ldz %d < 9 K)", ldz);
+  const size_t smem = (static_cast<size_t>(h) * factor * w * factor + static_cast<size_t>(9) * h * w * factor) * sizeof(float);
+  VPB_REQUIRE(smem <= 48 * 1024, "simple_head_gather_bwd: token grid %d x %d (x%d) too large", h, w, factor);
+  simple_head_gather_bwd_kernel<<<static_cast<unsigned>(images) * K, 256, smem, stream>>>(
+      dout, reinterpret_cast<__nv_bfloat16*>(dz), ldz, K, h, w, factor);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// dx = dy where y > 0 else 0 (y = relu(x) as the forward pass stored it), 8 bf16 per thread
+__global__ void relu_bwd_bf16_kernel(const uint4* __restrict__ y, const uint4* __restrict__ dy, uint4* __restrict__ dx,
+                                     long long n_vec) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_vec) return;
+  const uint4 a = __ldg(y + i);
+  uint4 d = __ldg(dy + i);
+  const uint32_t* aw = &a.x;
+  uint32_t* dw = &d.x;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {       // bf16 > 0: sign bit clear and not (+)zero
+    const uint32_t lo = aw[j] & 0xffffu, hi = aw[j] >> 16;
+    const uint32_t mlo = (lo != 0u && (lo & 0x8000u) == 0u) ? 0xffffu : 0u;
+    const uint32_t mhi = (hi != 0u && (hi & 0x8000u) == 0u) ? 0xffff0000u : 0u;
+    dw[j] &= (mlo | mhi);
+  }
+  dx[i] = d;
+}
+int relu_bwd_bf16(const void* y, const void* dy, void* dx, long long n, cudaStream_t stream) {
+  VPB_REQUIRE(n > 0 && n % 8 == 0, "relu_bwd_bf16: element count %lld must be a positive multiple of 8", n);
+  const long long n_vec = n / 8;
+  relu_bwd_bf16_kernel<<<static_cast<unsigned>((n_vec + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(dx), n_vec);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
 // Weights of a Linear layer that applies the LayerNorm in front of it in its own epilogue (gemm.cuh, "folded"
 // LayerNorm): Wf = bf16(gamma o W), s_n = sum_k float(Wf[n, k]) (the rounded values the tensor cores multiply by, so that
 // the mean term cancels exactly), c_n = b_n + sum_k beta_k W[n, k]. One CTA per output row; one-time weight repack.

@@ -73,6 +73,9 @@ int relu_upsample_bilinear_nhwc(const void* in, void* out, int n, int h, int w, 
 // Simple decoder without the upsampled map (see elementwise.cu): relu on the bf16 features, then — after the tap GEMM
 // z = relu(x) . W9^T (fp32 [images, 9K, h*w]) — the bilinear gather of the nine tap maps + bias -> fp32 NCHW heatmaps
 int relu_bf16(const void* in, void* out, long long n, cudaStream_t stream);
+int relu_bwd_bf16(const void* y, const void* dy, void* dx, long long n, cudaStream_t stream);
+int simple_head_gather_bwd(const float* dout, void* dz, int ldz, int images, int K, int h, int w, int factor,
+                           cudaStream_t stream);
 int simple_head_gather(const float* z, const float* bias, float* out, int images, int K, int h, int w, int factor,
                        cudaStream_t stream);
 

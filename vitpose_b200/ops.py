@@ -280,6 +280,41 @@ def cast_bf16(x, row_scale=None, rows_per_scale=0):
     return out
 
 
+def relu(x):
+    _need(x, BF16, 'x')
+    out = torch.empty_like(x)
+    check(lib().vpb_relu_bf16(ptr(x), ptr(out), x.numel(), stream_ptr()), 'vpb_relu_bf16')
+    return out
+
+
+def relu_bwd(y, dy):
+    """dy where y > 0 else 0 (y = relu output)."""
+    _need(y, BF16, 'y'); _need(dy, BF16, 'dy')
+    out = torch.empty_like(dy)
+    check(lib().vpb_relu_bwd_bf16(ptr(y), ptr(dy), ptr(out), y.numel(), stream_ptr()), 'vpb_relu_bwd_bf16')
+    return out
+
+
+def simple_head_gather(z, bias, K, h, w, factor):
+    """z fp32 [images, 9K, h*w] (tap maps) -> heatmaps fp32 [images, K, h*factor, w*factor]."""
+    _need(z, torch.float32, 'z')
+    images = z.shape[0]
+    out = torch.empty(images, K, h * factor, w * factor, device=z.device, dtype=torch.float32)
+    check(lib().vpb_simple_head_gather(ptr(z), ptr(bias), ptr(out), images, K, h, w, factor, stream_ptr()),
+          'vpb_simple_head_gather')
+    return out
+
+
+def simple_head_gather_bwd(dout, h, w, factor, ldz):
+    """dheatmaps fp32 [images, K, H, W] -> dz bf16 [images*h*w, ldz] (token-major, column k*9+t; pad columns zero)."""
+    _need(dout, torch.float32, 'dout')
+    images, K = dout.shape[:2]
+    dz = torch.zeros(images * h * w, ldz, device=dout.device, dtype=BF16)
+    check(lib().vpb_simple_head_gather_bwd(ptr(dout), ptr(dz), ldz, images, K, h, w, factor, stream_ptr()),
+          'vpb_simple_head_gather_bwd')
+    return dz
+
+
 def cast_bf16_colsum(x, colsum, row_scale=None, rows_per_scale=0):
     """cast_bf16 of the 2-D x and colsum[C] (fp32) += column sums of the rounded result, in one pass."""
     _need(x, torch.float32, 'x'); _need(colsum, torch.float32, 'colsum')

@@ -159,8 +159,11 @@ class _NetworkFn(torch.autograd.Function):
         bb, head = model.backbone, model.keypoint_head
         if not img.is_cuda:
             raise _lib.VitposeLibError('forward_train needs CUDA tensors (vitpose_b200 has no CPU path)')
-        if head.num_deconv_layers != 2 or head.final_conv_kernel != 1:
-            raise NotImplementedError('the training step is built for the classic decoder (2 deconv layers, 1x1 conv)')
+        classic = head.num_deconv_layers == 2 and head.final_conv_kernel == 1
+        simple = head.num_deconv_layers == 0 and head.final_conv_kernel == 3 and int(getattr(head, 'upsample', 0)) > 1
+        if not (classic or simple):
+            raise NotImplementedError('the training step is built for the classic decoder (2 deconv layers, 1x1 conv) '
+                                      'and the simple decoder (upsample + 3x3 conv)')
         img = img.contiguous().float()
         n = img.shape[0]
         D, heads, depth = bb.embed_dim, bb.num_heads, bb.depth
@@ -215,6 +218,19 @@ class _NetworkFn(torch.autograd.Function):
             a.update(qkv=qkv, attn=attn, lse=lse, x_mid=x_mid, xn2=xn2, pre=pre, h=h, s1=s1, s2=s2)
             acts.append(a)
         s.update(patches=patches, acts=acts, x_final=x, blocks=blocks, pe=pe)
+        if simple:
+            # ---- simple decoder (simple_head.py:132-139,197-202: ReLU -> bilinear x f -> Conv2d 3x3) without the
+            # upsampled map: the 3x3 conv on the token grid as nine 1x1 convs (one GEMM with 9K columns), then a
+            # bilinear gather of the nine tap maps (as vpb_vitpose_forward, csrc/api.cu)
+            fl = head.final_layer
+            K, f = fl.weight.shape[0], int(head.upsample)
+            r = ops.relu(xn)
+            w9 = ops.cast_bf16(fl.weight.detach().permute(0, 2, 3, 1).reshape(K * 9, D).contiguous())
+            z = ops.gemm(r, w9, EPI_NCHW, period=T)                                  # [n, 9K, T] fp32
+            hm = ops.simple_head_gather(z, fl.bias.detach().float().contiguous(), K, hp, wp, f)
+            s.update(simple=True, relu=r, w9=w9, K=K, f=f, n=n, T=T, M=M, D=D, heads=heads, hw=(hp, wp))
+            ctx.s, ctx.model, ctx.names = s, model, [nm for nm, _ in _param_list(model)]
+            return hm
         # ---- head (simple_head.py:197-202), BatchNorm2d in training mode
         feat = xn.view(n, hp, wp, D)
         cur, hs = feat, []
@@ -244,7 +260,8 @@ class _NetworkFn(torch.autograd.Function):
     def backward(ctx, dhm):
         s, model = ctx.s, ctx.model
         bb, head = model.backbone, model.keypoint_head
-        n, T, M, D, heads, K, P = s['n'], s['T'], s['M'], s['D'], s['heads'], s['K'], s['P']
+        n, T, M, D, heads, K = s['n'], s['T'], s['M'], s['D'], s['heads'], s['K']
+        P = s.get('P')
         dev = dhm.device
         g = {}                                           # parameter name -> fp32 gradient
 
@@ -296,41 +313,62 @@ class _NetworkFn(torch.autograd.Function):
                 pending.append(dist.all_reduce(seg, op=op, group=group, async_op=True))
             sent[0] = used[0]
 
-        # ---- final 1x1 conv: rows = pixels, columns = keypoints (zero padded to a multiple of 8)
-        Kp = (K + 7) // 8 * 8
-        dy = ops.nchw_to_rows(dhm.contiguous().float().view(n, K, P), Kp)                # [n*P, Kp]
-        act = s['act_last'].view(n * P, -1)
-        C = act.shape[1]
-        dwf = zeros(Kp, C)
-        _wgrad(dy, act, dwf)
-        dbf = zeros(Kp)
-        ops.colsum_accumulate(dy, dbf)
-        g['keypoint_head.final_layer.weight'] = dwf[:K].reshape(K, C, 1, 1)
-        g['keypoint_head.final_layer.bias'] = dbf[:K]
-        wf_pad = torch.zeros(Kp, C, device=dev, dtype=BF16)
-        wf_pad[:K] = s['wf']
-        dact = ops.gemm(dy, ops.transpose(wf_pad), EPI_BIAS)                             # [n*P, C]
-        # ---- [ConvTranspose2d -> BatchNorm2d(train) -> ReLU] x 2, last to first
-        for i in (1, 0):
-            hsi = s['head'][i]
-            bn, raw, xin, wp_ = hsi['bn'], hsi['raw'], hsi['x'], hsi['wp']
-            cout = raw.shape[-1]
-            dgam, dbet = zeros(cout), zeros(cout)
-            if hsi['frozen_stats']:
-                raise NotImplementedError('BatchNorm in eval mode inside forward_train is not implemented')
-            draw = ops.bn_relu_bwd(raw, dact.view(raw.shape), hsi['mean'], hsi['rstd'], bn.weight.detach(),
-                                   bn.bias.detach(), dgam, dbet)
-            g[f'keypoint_head.deconv_layers.{3 * i + 1}.weight'] = dgam
-            g[f'keypoint_head.deconv_layers.{3 * i + 1}.bias'] = dbet
-            a_t = ops.deconv_phase_dy(draw)                                             # [4, pixels, cout]
-            b_t = ops.deconv_gather_x(xin)                                               # [4, pixels, 4*cin]
-            dwp = scratch_zeros(4, cout, wp_.shape[2])
-            for ph in range(4):
-                _wgrad(a_t[ph], b_t[ph], dwp[ph])
-            g[f'keypoint_head.deconv_layers.{3 * i}.weight'] = ops.deconv_unpack_wgrad(
-                dwp, zeros(wp_.shape[2] // 4, cout, 4, 4))
-            del a_t, b_t
-            dact = ops.gemm(ops.deconv_gather_dy(draw), hsi['wd'], EPI_BIAS)             # [pixels_in, cin]
+        if s.get('simple'):
+            # ---- simple decoder: bias, then the transposed gather, then the tap GEMM's weight / input gradients
+            hp, wp = s['hw']
+            f = s['f']
+            P_out = hp * f * wp * f
+            dhm32 = dhm.contiguous().float()
+            Kp = (K + 7) // 8 * 8
+            dbf = zeros(Kp)
+            ops.colsum_accumulate(ops.nchw_to_rows(dhm32.view(n, K, P_out), Kp), dbf)
+            g['keypoint_head.final_layer.bias'] = dbf[:K]
+            Kp9 = (9 * K + 7) // 8 * 8
+            dz = ops.simple_head_gather_bwd(dhm32, hp, wp, f, Kp9)                       # [M, Kp9], column k*9+t
+            dw9 = scratch_zeros(Kp9, D)
+            _wgrad(dz, s['relu'], dw9)
+            dwf = zeros(K, D, 3, 3)
+            dwf.copy_(dw9[:9 * K].view(K, 3, 3, D).permute(0, 3, 1, 2))
+            g['keypoint_head.final_layer.weight'] = dwf
+            w9_pad = torch.zeros(Kp9, D, device=dev, dtype=BF16)
+            w9_pad[:9 * K] = s['w9']
+            dact = ops.relu_bwd(s['relu'], ops.gemm(dz, ops.transpose(w9_pad), EPI_BIAS))   # [M, D]
+        else:
+            # ---- final 1x1 conv: rows = pixels, columns = keypoints (zero padded to a multiple of 8)
+            Kp = (K + 7) // 8 * 8
+            dy = ops.nchw_to_rows(dhm.contiguous().float().view(n, K, P), Kp)                # [n*P, Kp]
+            act = s['act_last'].view(n * P, -1)
+            C = act.shape[1]
+            dwf = zeros(Kp, C)
+            _wgrad(dy, act, dwf)
+            dbf = zeros(Kp)
+            ops.colsum_accumulate(dy, dbf)
+            g['keypoint_head.final_layer.weight'] = dwf[:K].reshape(K, C, 1, 1)
+            g['keypoint_head.final_layer.bias'] = dbf[:K]
+            wf_pad = torch.zeros(Kp, C, device=dev, dtype=BF16)
+            wf_pad[:K] = s['wf']
+            dact = ops.gemm(dy, ops.transpose(wf_pad), EPI_BIAS)                             # [n*P, C]
+            # ---- [ConvTranspose2d -> BatchNorm2d(train) -> ReLU] x 2, last to first
+            for i in (1, 0):
+                hsi = s['head'][i]
+                bn, raw, xin, wp_ = hsi['bn'], hsi['raw'], hsi['x'], hsi['wp']
+                cout = raw.shape[-1]
+                dgam, dbet = zeros(cout), zeros(cout)
+                if hsi['frozen_stats']:
+                    raise NotImplementedError('BatchNorm in eval mode inside forward_train is not implemented')
+                draw = ops.bn_relu_bwd(raw, dact.view(raw.shape), hsi['mean'], hsi['rstd'], bn.weight.detach(),
+                                       bn.bias.detach(), dgam, dbet)
+                g[f'keypoint_head.deconv_layers.{3 * i + 1}.weight'] = dgam
+                g[f'keypoint_head.deconv_layers.{3 * i + 1}.bias'] = dbet
+                a_t = ops.deconv_phase_dy(draw)                                             # [4, pixels, cout]
+                b_t = ops.deconv_gather_x(xin)                                               # [4, pixels, 4*cin]
+                dwp = scratch_zeros(4, cout, wp_.shape[2])
+                for ph in range(4):
+                    _wgrad(a_t[ph], b_t[ph], dwp[ph])
+                g[f'keypoint_head.deconv_layers.{3 * i}.weight'] = ops.deconv_unpack_wgrad(
+                    dwp, zeros(wp_.shape[2] // 4, cout, 4, 4))
+                del a_t, b_t
+                dact = ops.gemm(ops.deconv_gather_dy(draw), hsi['wd'], EPI_BIAS)             # [pixels_in, cin]
         # ---- last_norm, then the blocks in reverse
         exchange()
         dx = scratch_zeros(M, D)
