@@ -280,6 +280,11 @@ int vpb_bn_relu_fwd(const void* raw, void* act, const float* mean, const float* 
 int vpb_bn_relu_bwd(const void* raw, const void* dact, void* draw, const float* mean, const float* rstd,
                     const float* gamma, const float* beta, float* dgamma, float* dbeta, float* scratch /* 6*C floats */,
                     long long rows, int C, void* stream);
+/* the same for a BatchNorm2d in EVAL mode inside forward_train (mean / rstd = the running statistics): no batch-mean
+ * correction terms in draw; dgamma / dbeta as above */
+int vpb_bn_relu_bwd_eval(const void* raw, const void* dact, void* draw, const float* mean, const float* rstd,
+                         const float* gamma, const float* beta, float* dgamma, float* dbeta, float* scratch,
+                         long long rows, int C, void* stream);
 /* dL/dheatmaps fp32 [n,K,P] -> bf16 rows [n*P, Kp] (zero padded to Kp >= K): operand of the final conv's GEMMs */
 int vpb_nchw_f32_to_rows_bf16(const float* in, void* out, int n, int K, int P, int Kp, void* stream);
 /* Operand gathers for the backward of the 4-phase transposed convolution (layouts in csrc/train_bwd.cu):

@@ -220,6 +220,19 @@ def test_bn_train_relu_fwd_bwd():
     _close('bn dgamma', dg, g.grad, 5e-3)
     _close('bn dbeta', db, b.grad, 5e-3)
     _close('bn+relu bwd', draw, x.grad.permute(0, 2, 3, 1), 2e-2)
+    # BatchNorm2d.eval() inside forward_train: running statistics, no batch-mean terms in the input gradient
+    rm2, rv2 = _rand((C,), 20, 0.3, torch.float32), _rand((C,), 21, 0.2, torch.float32).abs() + 0.5
+    x2 = raw.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    g2, b2 = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y2 = F.relu(F.batch_norm(x2, rm2, rv2, g2, b2, False, 0.1, 1e-5))
+    y2.backward(dact.float().permute(0, 3, 1, 2))
+    rstd2 = torch.rsqrt(rv2 + 1e-5)
+    _close('bn(eval)+relu fwd', ops.bn_relu_fwd(raw, rm2, rstd2, gamma, beta), y2.detach().permute(0, 2, 3, 1), 1e-2)
+    dg2, db2 = torch.zeros(C, device=_dev()), torch.zeros(C, device=_dev())
+    draw2 = ops.bn_relu_bwd(raw, dact, rm2, rstd2, gamma, beta, dg2, db2, eval_mode=True)
+    _close('bn(eval) dgamma', dg2, g2.grad, 5e-3)
+    _close('bn(eval) dbeta', db2, b2.grad, 5e-3)
+    _close('bn(eval)+relu bwd', draw2, x2.grad.permute(0, 2, 3, 1), 2e-2)
 
 
 @pytest.mark.parametrize('n,h,w,cin,cout', [(2, 16, 12, 128, 64), (3, 32, 24, 256, 256)])

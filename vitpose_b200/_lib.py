@@ -81,6 +81,8 @@ _SIGS = {
                                 c_void_p]),
     'vpb_bn_relu_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]),
+    'vpb_bn_relu_bwd_eval': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]),
     'vpb_nchw_f32_to_rows_bf16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'vpb_deconv_gather_x': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'vpb_deconv_gather_dy': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -528,6 +528,22 @@ int vpb_bn_relu_bwd(const void* raw, const void* dact, void* draw, const float* 
     return e;
   return bn_relu_bwd(raw, dact, draw, mean, rstd, gamma, beta, sums, sums + C, rows, C, stream);
 }
+// BatchNorm2d in EVAL mode (running statistics passed as mean / rstd) + ReLU: the statistics do not depend on the
+// batch, so draw = gamma * rstd * dy' without the two batch-mean correction terms; dgamma / dbeta as in training mode
+int vpb_bn_relu_bwd_eval(const void* raw, const void* dact, void* draw, const float* mean, const float* rstd,
+                         const float* gamma, const float* beta, float* dgamma, float* dbeta, float* scratch,
+                         long long rows, int C, void* stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  VPB_REQUIRE(rows > 0 && rows < (1ll << 31), "bn_relu_bwd: bad shape");
+  VPB_REQUIRE(scratch != nullptr && (reinterpret_cast<uintptr_t>(scratch) & 7) == 0, "bn_relu_bwd: scratch (6*C floats, 8-byte aligned)");
+  double* acc = reinterpret_cast<double*>(scratch);
+  float* sums = scratch + 4 * C;
+  if (int e = bn_relu_bwd_reduce(raw, dact, mean, rstd, gamma, beta, static_cast<int>(rows), C, acc, sums, dbeta, dgamma,
+                                 stream))
+    return e;
+  VPB_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
+  return bn_relu_bwd(raw, dact, draw, mean, rstd, gamma, beta, sums, sums + C, rows, C, stream);
+}
 int vpb_nchw_f32_to_rows_bf16(const float* in, void* out, int n, int K, int P, int Kp, void* stream) {
   return nchw_f32_to_rows_bf16(in, out, n, K, P, Kp, as_stream(stream));
 }

@@ -438,11 +438,13 @@ def bn_relu_fwd(raw, mean, rstd, gamma, beta):
     return act
 
 
-def bn_relu_bwd(raw, dact, mean, rstd, gamma, beta, dgamma, dbeta):
+def bn_relu_bwd(raw, dact, mean, rstd, gamma, beta, dgamma, dbeta, eval_mode=False):
+    """eval_mode: mean / rstd are running statistics (BatchNorm2d.eval() inside forward_train)."""
     C = raw.shape[-1]
     draw = torch.empty_like(raw)
     scratch = torch.empty(6 * C, device=raw.device)
-    check(lib().vpb_bn_relu_bwd(ptr(raw), ptr(dact), ptr(draw), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta),
+    fn = lib().vpb_bn_relu_bwd_eval if eval_mode else lib().vpb_bn_relu_bwd
+    check(fn(ptr(raw), ptr(dact), ptr(draw), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta),
                                 ptr(dgamma), ptr(dbeta), ptr(scratch), raw.numel() // C, C, stream_ptr()),
           'vpb_bn_relu_bwd')
     return draw

@@ -354,10 +354,8 @@ class _NetworkFn(torch.autograd.Function):
                 bn, raw, xin, wp_ = hsi['bn'], hsi['raw'], hsi['x'], hsi['wp']
                 cout = raw.shape[-1]
                 dgam, dbet = zeros(cout), zeros(cout)
-                if hsi['frozen_stats']:
-                    raise NotImplementedError('BatchNorm in eval mode inside forward_train is not implemented')
                 draw = ops.bn_relu_bwd(raw, dact.view(raw.shape), hsi['mean'], hsi['rstd'], bn.weight.detach(),
-                                       bn.bias.detach(), dgam, dbet)
+                                       bn.bias.detach(), dgam, dbet, eval_mode=hsi['frozen_stats'])
                 g[f'keypoint_head.deconv_layers.{3 * i + 1}.weight'] = dgam
                 g[f'keypoint_head.deconv_layers.{3 * i + 1}.bias'] = dbet
                 a_t = ops.deconv_phase_dy(draw)                                             # [4, pixels, cout]
