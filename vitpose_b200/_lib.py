@@ -196,7 +196,14 @@ def ptr(t):
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the current device (every kernel of the library is launched on it).
+    The raw accessor avoids building a torch.cuda.Stream object per launch (~5 us each, 270 launches per training step)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
