@@ -28,7 +28,15 @@ static int launch_gemm_inst(const GemmMaps& maps, const GemmParams& p, int max_c
     // the n-tiles of a row block exchange LayerNorm statistics: keep them on CTAs that run in the same step of the
     // persistent loop (grid a whole number of row blocks), and every CTA must be resident (spin-wait on siblings)
     VPB_REQUIRE(cap >= n_tiles * CG, "gemm+layernorm: needs at least %d resident CTAs", n_tiles * CG);
-    cap -= cap % (n_tiles * CG);
+    // When that rounding would idle >= 5 % of the SMs (ViTPose-H: five column tiles x CTA pairs -> 140 of 148) keep every
+    // SM busy instead: a row block whose tiles straddle the end of a step then has its early tiles wait up to one tile
+    // period for the late ones (no cycle: statistics are published before the wait, and the cooperative launch keeps
+    // every CTA resident). Measured (profiles/r02_summary.md §12): H proj + LN 219 -> 212 us, fc2 + LN 520 -> 509 us;
+    // B (144 of 148 SMs) unchanged, so it keeps the rounded grid. VPB_LN_FULLGRID=0 / 1 forces either.
+    static const int full_grid = [] { const char* e = getenv("VPB_LN_FULLGRID"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+    const int rem = cap % (n_tiles * CG);
+    const bool keep_all = (full_grid == 1 || (full_grid == -1 && rem * 20 >= cap)) && p.ln_fold == 0 && gemm_cooperative();
+    if (!keep_all) cap -= rem;
   }
   if (grid > cap) grid = cap;
   GemmParams pd = p;
