@@ -123,10 +123,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           }
         }
         umma_commit(&bar_mma);
-        if (t == 0) {                 // the next S overwrites columns the threads are done with only after bar_ds; the
-          mbar_wait(&bar_mma, 0);     // P / dS tiles are rewritten by the threads after they have seen bar_mma
-          tc_fence_after();
-        }
+        // The next tile's S is issued right away: its TMEM columns are free since bar_ds (every thread has read dP), the
+        // tensor pipe runs it behind the MMAs above, and the threads rewrite the P / dS tiles only after bar_mma — so
+        // S of tile 1 is ready while the threads still drain dQ of tile 0.
       }
     }
   } else {
