@@ -266,6 +266,9 @@ int vpb_attention_lse(const void* qkv, void* out, float* lse, int n, int T, int 
                       void* stream);
 int vpb_attention_bwd(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, int n, int T,
                       int heads, int head_dim, float scale, void* stream);
+/* the same, and dbias fp32 [3*heads*head_dim] += the column sums of dqkv over all tokens (attn.qkv's bias gradient) */
+int vpb_attention_bwd_bias(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, float* dbias,
+                           int n, int T, int heads, int head_dim, float scale, void* stream);
 /* ConvTranspose2d(k4,s2,p1,bias=False) without BatchNorm / ReLU (training forward; ones / zeros: fp32 [cout]) */
 int vpb_deconv4x4s2_raw(const void* in, const void* wphase, void* out, int n, int h, int w, int cin, int cout,
                         const float* ones, const float* zeros, void* stream);

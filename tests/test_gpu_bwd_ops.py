@@ -169,7 +169,10 @@ def test_attention_bwd(n, heads):
     _close('attention fwd', out, o.detach(), 2e-2)
     s_ref = ((q * hd ** -0.5) @ k.transpose(-2, -1)).detach()
     _close('attention lse', lse, torch.logsumexp(s_ref, -1) * 1.4426950408889634, 1e-3)
-    dqkv = ops.attention_bwd(qkv, out, lse, dout, heads)
+    dbias = torch.full((3 * D,), 0.5, device=_dev())
+    dqkv = ops.attention_bwd(qkv, out, lse, dout, heads, dbias=dbias)
+    assert torch.equal(dqkv, ops.attention_bwd(qkv, out, lse, dout, heads))
+    _close('qkv bias gradient', dbias, 0.5 + dqkv.float().sum((0, 1)), 5e-3)
     g = x.grad.reshape(n, T, 3, D)
     d = dqkv.reshape(n, T, 3, D)
     for i, nm in enumerate('qkv'):

@@ -73,6 +73,8 @@ _SIGS = {
     'vpb_attention_lse': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     'vpb_attention_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   c_float, c_void_p]),
+    'vpb_attention_bwd_bias': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                       c_int, c_float, c_void_p]),
     'vpb_deconv4x4s2_raw': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                     c_void_p, c_void_p]),
     'vpb_bn_train_stats': (c_int, [c_void_p, ctypes.c_longlong, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,

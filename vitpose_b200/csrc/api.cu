@@ -497,6 +497,10 @@ int vpb_attention_bwd(const void* qkv, const void* out, const float* lse, const 
                       int heads, int head_dim, float scale, void* stream) {
   return attention_bwd(qkv, out, lse, dout, dqkv, n, T, heads, head_dim, scale, as_stream(stream));
 }
+int vpb_attention_bwd_bias(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, float* dbias,
+                           int n, int T, int heads, int head_dim, float scale, void* stream) {
+  return attention_bwd(qkv, out, lse, dout, dqkv, n, T, heads, head_dim, scale, as_stream(stream), dbias);
+}
 int vpb_deconv4x4s2_raw(const void* in, const void* wphase, void* out, int n, int h, int w, int cin, int cout,
                         const float* ones, const float* zeros, void* stream) {
   return deconv4x4s2_affine(in, wphase, ones, zeros, out, n, h, w, cin, cout, 0, 0, as_stream(stream));

@@ -34,6 +34,7 @@ struct AttnBwdParams {
   const __nv_bfloat16* O;     // [n, T, heads*64] forward output
   const float* lse;           // [n, heads, T] log2-sum-exp of the scaled scores, written by the forward kernel
   __nv_bfloat16* dqkv;        // [n, T, 3*heads*64]
+  float* dbias;               // optional [3*heads*64]: += column sums of dqkv over all tokens (attn.qkv's bias gradient)
 };
 
 __global__ void __launch_bounds__(AB_THREADS, 1)
@@ -219,6 +220,13 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_dq + lane_off + half * 32, v);
         tmem_ld_wait();
+        if (p.dbias != nullptr) {       // bias gradient of attn.qkv: column sums over the live rows of this warp
+          float cs[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) cs[j] = valid ? __uint_as_float(v[j]) : 0.f;
+          const float sum = warp_colsum32(cs, lane);
+          atomicAdd(p.dbias + head * AB_HD + half * 32 + lane, sum);
+        }
         uint8_t* stage = s_q + (warp - 1) * 2048;
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -252,6 +260,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         uint32_t v[32];
         tmem_ld_32x32b_x32(base + c, v);
         tmem_ld_wait();
+        if (p.dbias != nullptr) {
+          const bool key_ok = m * 128 + quad * 32 + lane < AB_T;
+          float cs[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) cs[j] = key_ok ? __uint_as_float(v[j]) : 0.f;
+          const float sum = warp_colsum32(cs, lane);
+          atomicAdd(p.dbias + (1 + half) * ld_o + head * AB_HD + c + lane, sum);
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           *reinterpret_cast<uint4*>(stage + lane * 144 + c * 2 + u * 16) =
@@ -279,7 +295,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 }
 
 int attention_bwd(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, int n, int T,
-                  int heads, int hd, float scale, cudaStream_t stream) {
+                  int heads, int hd, float scale, cudaStream_t stream, float* dbias) {
   VPB_REQUIRE(n > 0 && heads > 0 && lse != nullptr, "attention_bwd: empty problem / missing log-sum-exp");
   VPB_REQUIRE(T == AB_T && hd == AB_HD, "attention_bwd: built for T=%d, head_dim=%d (got T=%d, head_dim=%d)", AB_T,
               AB_HD, T, hd);
@@ -298,6 +314,7 @@ int attention_bwd(const void* qkv, const void* out, const float* lse, const void
   p.O = reinterpret_cast<const __nv_bfloat16*>(out);
   p.lse = lse;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  p.dbias = dbias;
   static bool configured = false;
   if (!configured) {
     VPB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));

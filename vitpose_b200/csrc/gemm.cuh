@@ -262,23 +262,6 @@ __device__ __forceinline__ float2 gelu_erf_grad2(float2 x) {
   return __ffma2_rn(__fmul2_rn(x, make_float2(0.3989422804014327f, 0.3989422804014327f)), g, cdf);
 }
 
-// Column sums over the 32 lanes of a warp for 32 columns at once (lane = row, x[c] = this row's value in column c):
-// recursive halving — at step `off` a lane keeps the half of its columns whose bit `off` equals its own lane bit and
-// adds the partner's values for them — 31 shuffles instead of 32 x 5. Returns the sum of column `lane`.
-__device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = up ? x[i] : x[i + off];
-      const float keep = up ? x[i + off] : x[i];
-      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return x[0];
-}
-
 // Fused-LayerNorm statistics exchange: one 8-byte word per (row, n-tile) = {mean, M2 | tag << 31}; 8-byte accesses
 // are single-copy atomic, so the word carries its own validity (the tag of this launch) — no fence, flag or barrier.
 __device__ __forceinline__ void ln_publish_stats(const GemmParams& p, int m_blk, int r, int n_tiles, int n_blk,

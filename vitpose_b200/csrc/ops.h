@@ -149,8 +149,9 @@ int nchw_f32_to_rows_bf16(const float* in, void* out, int n, int K, int P, int K
 int deconv_gather_x(const void* x, void* out, int n, int h, int w, int cin, cudaStream_t stream);
 int deconv_gather_dy(const void* dy, void* out, int n, int h, int w, int cout, cudaStream_t stream);
 int deconv_phase_dy(const void* dy, void* out, int n, int h, int w, int cout, cudaStream_t stream);
+// dbias (optional, fp32 [3*heads*hd]) += column sums of dqkv (fp32 values, before the bf16 rounding): attn.qkv's bias gradient
 int attention_bwd(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, int n, int T,
-                  int heads, int hd, float scale, cudaStream_t stream);
+                  int heads, int hd, float scale, cudaStream_t stream, float* dbias = nullptr);
 
 int adamw_multi(const vpb_tensor_entry* entries, const int* chunk_start, int n, int total_chunks, float beta1,
                 float beta2, float eps, float* sq_norm, float max_norm, cudaStream_t stream);

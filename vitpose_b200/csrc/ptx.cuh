@@ -382,4 +382,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Column sums over the 32 lanes of a warp for 32 columns at once (lane = row, x[c] = this row's value in column c):
+// recursive halving — at step `off` a lane keeps the half of its columns whose bit `off` equals its own lane bit and
+// adds the partner's values for them — 31 shuffles instead of 32 x 5. Returns the sum of column `lane`.
+__device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? x[i] : x[i + off];
+      const float keep = up ? x[i + off] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return x[0];
+}
+
 }  // namespace vpb

@@ -393,15 +393,22 @@ def attention_with_lse(qkv, heads, scale=None):
     return out, lse
 
 
-def attention_bwd(qkv, out, lse, dout, heads, scale=None):
-    """qkv bf16 [n,T,3*heads*hd], out / dout bf16 [n,T,heads*hd], lse fp32 [n,heads,T] -> dqkv bf16 [n,T,3*heads*hd]."""
+def attention_bwd(qkv, out, lse, dout, heads, scale=None, dbias=None):
+    """qkv bf16 [n,T,3*heads*hd], out / dout bf16 [n,T,heads*hd], lse fp32 [n,heads,T] -> dqkv bf16 [n,T,3*heads*hd];
+    dbias (fp32 [3*heads*hd], optional) += column sums of dqkv over all tokens (attn.qkv's bias gradient)."""
     _need(qkv, BF16, 'qkv'); _need(out, BF16, 'out'); _need(dout, BF16, 'dout'); _need(lse, torch.float32, 'lse')
     n, T, three = qkv.shape
     hd = three // 3 // heads
     scale = hd ** -0.5 if scale is None else scale
     dqkv = torch.empty_like(qkv)
-    check(lib().vpb_attention_bwd(ptr(qkv), ptr(out), ptr(lse), ptr(dout), ptr(dqkv), n, T, heads, hd, float(scale),
-                                  stream_ptr()), 'vpb_attention_bwd')
+    if dbias is not None:
+        _need(dbias, torch.float32, 'dbias')
+        assert dbias.numel() == three
+        check(lib().vpb_attention_bwd_bias(ptr(qkv), ptr(out), ptr(lse), ptr(dout), ptr(dqkv), ptr(dbias), n, T, heads,
+                                           hd, float(scale), stream_ptr()), 'vpb_attention_bwd_bias')
+    else:
+        check(lib().vpb_attention_bwd(ptr(qkv), ptr(out), ptr(lse), ptr(dout), ptr(dqkv), n, T, heads, hd, float(scale),
+                                      stream_ptr()), 'vpb_attention_bwd')
     return dqkv
 
 

@@ -425,9 +425,10 @@ class _NetworkFn(torch.autograd.Function):
             dyb, dbp = norm_bwd(pfx + 'norm2', blk.norm2, a['x_mid'], dxn2, a['s1'], pfx + 'attn.proj.bias')
             # x_mid = x_in + proj(attention(qkv(norm1(x_in))))        (vit.py:138)
             dattn = linear_bwd(pfx + 'attn.proj', w['proj'], dyb, a['attn'], dbias=dbp)
+            dbq = zeros(3 * D) if FUSE_MLP and pfx + 'attn.qkv.bias' in trainable else None    # summed by the kernel
             dqkv = ops.attention_bwd(a['qkv'].view(n, T, 3 * D), a['attn'].view(n, T, D), a['lse'],
-                                     dattn.view(n, T, D), heads)
-            dxn1 = linear_bwd(pfx + 'attn.qkv', w['qkv'], dqkv.view(M, 3 * D), a['xn1'])
+                                     dattn.view(n, T, D), heads, dbias=dbq)
+            dxn1 = linear_bwd(pfx + 'attn.qkv', w['qkv'], dqkv.view(M, 3 * D), a['xn1'], dbias=dbq)
             if l > 0:
                 dyb, db2 = norm_bwd(pfx + 'norm1', blk.norm1, a['x_in'], dxn1, acts[l - 1]['s2'],
                                     f'backbone.blocks.{l - 1}.mlp.fc2.bias')
