@@ -464,8 +464,13 @@ int gemm_bf16_atb_accum(const void* At, const void* Bt, int M, int N, int K, flo
   maps.aux = maps.a;
   maps.ln = maps.a;
   GemmParams p{M, N, K, nullptr, out, ldo, nullptr, 0, 1, nullptr, 1, nullptr, nullptr, nullptr, 0, 0u, 0.0f};
-  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + bn - 1) / bn);
-  p.ksplit = pick_ksplit(tiles, (K + GEMM_BK - 1) / GEMM_BK, max_ctas > 0 ? max_ctas : sm_count());
+  // CTA pairs (256 x 256 tiles, each CTA stages its 128 A columns and half of the B chunk) when the output has whole
+  // pair tiles: the Linear layers of the backbone (VPB_WGRAD_PAIR=0: single-CTA tiles, A/B)
+  static const bool pair_ok = [] { const char* e = getenv("VPB_WGRAD_PAIR"); return !(e && atoi(e) == 0); }();
+  const int cg = (pair_ok && bn == 256 && M % 256 == 0 && N % 256 == 0) ? 2 : 1;
+  const int tiles = ((M + GEMM_BM * cg - 1) / (GEMM_BM * cg)) * ((N + bn - 1) / bn);
+  p.ksplit = pick_ksplit(tiles, (K + GEMM_BK - 1) / GEMM_BK, (max_ctas > 0 ? max_ctas : sm_count()) / cg);
+  if (cg == 2) return launch_gemm_inst<256, EPI_ACCUM_F32, 2, 1>(maps, p, max_ctas, stream);
   if (bn == 256) return launch_gemm_inst<256, EPI_ACCUM_F32, 1, 1>(maps, p, max_ctas, stream);
   if (bn == 128) return launch_gemm_inst<128, EPI_ACCUM_F32, 1, 1>(maps, p, max_ctas, stream);
   return launch_gemm_inst<64, EPI_ACCUM_F32, 1, 1>(maps, p, max_ctas, stream);

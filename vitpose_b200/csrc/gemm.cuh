@@ -332,7 +332,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   constexpr int TMEM_COLS = gemm_tmem_cols(BN);
   constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM * CG, BN, OPM, OPM);
   static_assert(CG == 1 || (CG == 2 && BN % 32 == 0), "CTA pairs split the B tile in two halves");
-  static_assert(OPM == 0 || (CG == 1 && BN % 64 == 0), "MN-major operands: single-CTA tiles, 64-column chunks");
+  static_assert(OPM == 0 || (BN % (64 * CG) == 0), "MN-major operands: 64-column chunks (per CTA of a pair)");
   constexpr int OPM_CHUNK = GEMM_BK * 128;      // [64 k-rows][64 columns] bf16
   constexpr bool STAGED = gemm_epi_staged(EPI);
   constexpr int CHUNK = (gemm_epi_adds_tile(EPI)) ? 32 : 64;     // columns per 128-byte staging row
@@ -484,8 +484,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             // both CTAs' bytes are credited to the LEADER's barrier, which the MMA issuer waits on
             const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            if constexpr (OPM == 1) {     // [64 k-rows][64 columns] chunks: this CTA's 128 A columns, its half of B's
+#pragma unroll
+              for (int c = 0; c < GEMM_BM / 64; ++c)
+                tma_load_2d_pair(sa + c * OPM_CHUNK, &tma_a, leader_full, m_blk * GEMM_BM + c * 64, kb * GEMM_BK);
+#pragma unroll
+              for (int c = 0; c < BN / 2 / 64; ++c)
+                tma_load_2d_pair(sb + c * OPM_CHUNK, &tma_b, leader_full, n_blk * BN + cta_rank * (BN / 2) + c * 64,
+                                 kb * GEMM_BK);
+            } else {
             tma_load_2d_pair(sa, &tma_a, leader_full, kb * GEMM_BK, m_blk * GEMM_BM);
             tma_load_2d_pair(sb, &tma_b, leader_full, kb * GEMM_BK, n_blk * BN + cta_rank * (BN / 2));
+            }
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
             if constexpr (OPM == 1) {
@@ -543,7 +553,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
-            if constexpr (CG == 2)
+            if constexpr (CG == 2 && OPM == 1)
+              umma_bf16_ss_pair(d_tmem, umma_desc_mn_sw128(a_addr + k * 2048, OPM_CHUNK),
+                                umma_desc_mn_sw128(b_addr + k * 2048, OPM_CHUNK), IDESC, (kb > kb0 || k != 0) ? 1u : 0u);
+            else if constexpr (CG == 2)
               umma_bf16_ss_pair(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), IDESC,
                                 (kb > kb0 || k != 0) ? 1u : 0u);
             else if constexpr (OPM == 1)     // 16 k-rows = 2048 B per step; 64-column chunks OPM_CHUNK apart
