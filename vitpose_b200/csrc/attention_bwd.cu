@@ -135,15 +135,18 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     const int r = quad * 32 + lane;                 // row inside a tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     constexpr int KH = AB_T / 2;                    // 96 keys per thread
+    // delta = <dO_row, O_row> and the forward log-sum-exp of this thread's row in BOTH query tiles, requested up front:
+    // the global-memory latency (16 x 16-byte loads per tile; 20 % of the kernel's stall samples when they sat at the
+    // top of each tile) hides behind the TMA loads of Q / K / V / dO. Both halves of a row compute it: no exchange.
+    float delta_t[2] = {0.f, 0.f}, lse_t[2] = {0.f, 0.f};
+#pragma unroll
     for (int t = 0; t < 2; ++t) {
       const int token = t * 128 + r;
-      const bool valid = token < AB_T;
-      // delta = <dO_row, O_row> (both halves compute it: 256 bytes per thread, no exchange needed)
-      float delta = 0.f, lse = 0.f;
-      if (valid) {
+      if (token < AB_T) {
         const size_t off = (static_cast<size_t>(crop) * AB_T + token) * ld_o + head * AB_HD;
         const uint4* a = reinterpret_cast<const uint4*>(p.dO + off);
         const uint4* b = reinterpret_cast<const uint4*>(p.O + off);
+        float d = 0.f;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const uint4 x = __ldg(a + u), y = __ldg(b + u);
@@ -152,11 +155,17 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           for (int j = 0; j < 4; ++j) {
             const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[j]));
             const float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[j]));
-            delta = fmaf(fx.x, fy.x, fmaf(fx.y, fy.y, delta));
+            d = fmaf(fx.x, fy.x, fmaf(fx.y, fy.y, d));
           }
         }
-        lse = __ldg(p.lse + (static_cast<size_t>(crop) * p.heads + head) * AB_T + token);
+        delta_t[t] = d;
+        lse_t[t] = __ldg(p.lse + (static_cast<size_t>(crop) * p.heads + head) * AB_T + token);
       }
+    }
+    for (int t = 0; t < 2; ++t) {
+      const int token = t * 128 + r;
+      const bool valid = token < AB_T;
+      const float delta = t == 0 ? delta_t[0] : delta_t[1], lse = t == 0 ? lse_t[0] : lse_t[1];
       mbar_wait(&bar_s, t);
       tc_fence_after();
       // P = exp2(s * scale * log2e - lse), one pass over this thread's 96 keys
