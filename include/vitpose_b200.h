@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VPB_ABI_VERSION 2
+#define VPB_ABI_VERSION 3
 
 int vpb_abi_version(void);
 const char* vpb_last_error(void);
@@ -76,6 +76,19 @@ typedef struct vpb_block_fold {
   const void* fc1_wf; const float* fc1_s; const float* fc1_c;
 } vpb_block_fold;
 
+/* ViTPose+ (ViTMoE, vit_moe.py:78-115): the per-dataset experts own the last part_features output columns of mlp.fc2,
+ * every other weight is shared. A batch whose crops are sorted by dataset runs in ONE pass: all kernels on the whole
+ * batch except mlp.fc2 (+ residual + the following LayerNorm), which is launched once per run of images with that
+ * run's weight. image_begin counts images of the batch the forward call sees (2n of them with flip: the n originals, then
+ * the n flipped copies — so a dataset that owns crops [a, b) owns the runs [a, b) and [n + a, n + b)). */
+#define VPB_MOE_MAX_RUNS 64
+typedef struct vpb_moe_runs {
+  int32_t num_runs;                 /* 1 .. VPB_MOE_MAX_RUNS */
+  const int32_t* image_begin;       /* HOST [num_runs + 1], increasing, image_begin[0] = 0, last = number of images */
+  const void* const* fc2_w;         /* HOST [num_runs * depth]: bf16 [D, hidden] of run r, block l at [r * depth + l] */
+  const float* const* fc2_b;        /* HOST [num_runs * depth]: fp32 [D] */
+} vpb_moe_runs;
+
 /* Repacked weights (built once by the host side, vitpose_b200/engine.py: PackedWeights):
  *  patch_w  bf16 [D, 768]      = patch_embed.proj.weight.reshape(D, 3*16*16)
  *  pos      fp32 [T, D]        = pos_embed[0, 1:] + pos_embed[0, :1]           (vit.py:320)
@@ -91,6 +104,7 @@ typedef struct vpb_weights {
   const void* deconv_w[3]; const float* deconv_scale[3]; const float* deconv_shift[3];
   const void* final_w; const float* final_b;
   const vpb_block_fold* fold;                /* HOST pointer to `depth` structs, or NULL: LayerNorm in the producing GEMM */
+  const vpb_moe_runs* moe;                   /* HOST pointer or NULL: blocks[l].fc2_* for every image */
 } vpb_weights;
 
 /* Bytes of scratch `vpb_vitpose_forward` needs for `images` crops (count the flipped copies too). */

@@ -37,7 +37,8 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.ModelDesc) == 4 * 15
     assert ctypes.sizeof(_lib.BlockWeights) == 8 * 12
     assert ctypes.sizeof(_lib.BlockFold) == 8 * 6
-    assert ctypes.sizeof(_lib.Weights) == 8 * (6 + 9 + 2 + 1)
+    assert ctypes.sizeof(_lib.MoeRuns) == 8 * 4
+    assert ctypes.sizeof(_lib.Weights) == 8 * (6 + 9 + 2 + 1 + 1)
 
 
 def test_workspace_bytes_no_gpu_needed():

@@ -119,6 +119,24 @@ def test_topdown_moe_mixed_batch_vs_oracle():
     assert err < 1e-2 and err < 0.1 * std, f'heatmap err {err:.4g}, std {std:.4g}'
     assert r['bbox_ids'] == ref['bbox_ids'] and r['image_paths'] == ref['image_paths']
     np.testing.assert_allclose(r['boxes'], ref['boxes'], rtol=1e-6)
+    # the mixed batch ran in ONE forward pass: the engine of dataset 0 with every dataset's mlp.fc2 attached (vpb_moe_runs)
+    eng = model.backbone.moe_engine(model.keypoint_head)
+    assert sorted(eng.experts) == [0, 1, 2] and getattr(eng, '_moe_runs', None) is None
+    order, runs = model.backbone.dataset_runs([1, 0, 2, 1, 0])
+    assert order == [1, 4, 0, 3, 2] and runs == [(0, 2), (1, 2), (2, 1)]
+    from vitpose_b200 import _lib
+    L = _lib.lib()
+    c0 = L.vpb_launch_count()
+    model(img=img.cuda(), img_metas=metas, return_loss=False)
+    per_mixed = L.vpb_launch_count() - c0
+    for m in metas:
+        m['dataset_idx'] = 1
+    c0 = L.vpb_launch_count()
+    model(img=img.cuda(), img_metas=metas, return_loss=False)
+    per_single = L.vpb_launch_count() - c0
+    assert per_mixed == per_single, (per_mixed, per_single)     # same kernel sequence: one pass, not one per dataset
+    for m, d in zip(metas, [1, 0, 2, 1, 0]):
+        m['dataset_idx'] = d
     # a homogeneous batch goes through the single-engine path; the experts must actually matter
     for m in metas:
         m['dataset_idx'] = 2

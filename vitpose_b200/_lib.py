@@ -13,7 +13,7 @@ c_void_p, c_int, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_flo
 
 EPI_BIAS_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_POS_F32, EPI_NCHW_F32 = range(5)
 EPI_ACCUM_F32 = 10
-ABI_VERSION = 2          # VPB_ABI_VERSION of include/vitpose_b200.h this module was written against
+ABI_VERSION = 3          # VPB_ABI_VERSION of include/vitpose_b200.h this module was written against
 DECODE_NONE, DECODE_DEFAULT, DECODE_UNBIASED, DECODE_UDP_DARK = range(4)
 
 
@@ -34,11 +34,21 @@ class BlockFold(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ('qkv_wf', 'qkv_s', 'qkv_c', 'fc1_wf', 'fc1_s', 'fc1_c')]
 
 
+class MoeRuns(ctypes.Structure):
+    """vpb_moe_runs: runs of images (sorted by dataset) with their own mlp.fc2 weights (ViTPose+)."""
+    _fields_ = [('num_runs', ctypes.c_int32), ('image_begin', ctypes.POINTER(ctypes.c_int32)),
+                ('fc2_w', ctypes.POINTER(c_void_p)), ('fc2_b', ctypes.POINTER(c_void_p))]
+
+
+MOE_MAX_RUNS = 64
+
+
 class Weights(ctypes.Structure):
     _fields_ = [('patch_w', c_void_p), ('patch_b', c_void_p), ('pos', c_void_p),
                 ('blocks', ctypes.POINTER(BlockWeights)), ('last_g', c_void_p), ('last_b', c_void_p),
                 ('deconv_w', c_void_p * 3), ('deconv_scale', c_void_p * 3), ('deconv_shift', c_void_p * 3),
-                ('final_w', c_void_p), ('final_b', c_void_p), ('fold', ctypes.POINTER(BlockFold))]
+                ('final_w', c_void_p), ('final_b', c_void_p), ('fold', ctypes.POINTER(BlockFold)),
+                ('moe', ctypes.POINTER(MoeRuns))]
 
 
 class VitposeLibError(RuntimeError):

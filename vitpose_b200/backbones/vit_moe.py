@@ -79,22 +79,60 @@ class ViTMoE(ViT):
             self._engines[dataset_idx] = cached
         return cached[1]
 
+    def moe_engine(self, head=None):
+        """ONE engine for batches that mix datasets: the packed network of dataset 0 plus every dataset's mlp.fc2
+        (cat(fc2, experts[d]), vit_moe.py:107-111) on the device; ``VitPoseEngine.set_moe_runs`` then selects the fc2
+        per run of crops inside a single forward pass (include/vitpose_b200.h: vpb_moe_runs)."""
+        eng = self.engine(head, 0)
+        key = (self._weights_version(), None if head is None else head._weights_version())
+        if getattr(eng, '_experts_key', None) != key:
+            dev, sd = eng.device, self.state_dict()
+            experts = {}
+            for d in range(self.num_expert):
+                ws_, bs_ = [], []
+                for i in range(len(self.blocks)):
+                    pre = f'blocks.{i}.mlp.'
+                    w = torch.cat([sd[pre + 'fc2.weight'], sd[pre + f'experts.{d}.weight']], dim=0)
+                    b = torch.cat([sd[pre + 'fc2.bias'], sd[pre + f'experts.{d}.bias']], dim=0)
+                    ws_.append(w.detach().to(device=dev, dtype=torch.float32).to(torch.bfloat16).contiguous())
+                    bs_.append(b.detach().to(device=dev, dtype=torch.float32).contiguous())
+                experts[d] = (ws_, bs_)
+            eng.set_experts(experts)
+            eng._experts_key = key
+        return eng
+
+    @staticmethod
+    def dataset_runs(src):
+        """(order, runs): a stable permutation that sorts the crops by dataset index and the [(dataset, count)] runs."""
+        src = [int(v) for v in src]
+        order = sorted(range(len(src)), key=lambda i: src[i])
+        runs = []
+        for i in order:
+            if runs and runs[-1][0] == src[i]:
+                runs[-1][1] += 1
+            else:
+                runs.append([src[i], 1])
+        return order, [(d, c) for d, c in runs]
+
     def forward_features(self, x, dataset_source=None):
-        """[N,3,H,W] -> [N,D,Hp,Wp]; ``dataset_source`` int tensor [N] (default: dataset 0 for every crop)."""
+        """[N,3,H,W] -> [N,D,Hp,Wp]; ``dataset_source`` int tensor [N] (default: dataset 0 for every crop). Mixed batches
+        run in one pass: crops sorted by dataset, one mlp.fc2 launch per run."""
         from .. import ops
         n = x.shape[0]
-        src = torch.zeros(n, dtype=torch.long) if dataset_source is None else dataset_source.detach().cpu().long()
-        out = None
-        for d in sorted(set(src.tolist())):
-            idx = torch.nonzero(src == d).flatten().to(x.device)
-            eng = self.engine(None, d)
-            _, tokens = eng.forward_heatmaps(x.index_select(0, idx).float(), flip=False, want_features=True,
+        src = [0] * n if dataset_source is None else dataset_source.detach().cpu().long().tolist()
+        order, runs = self.dataset_runs(src)
+        eng = self.moe_engine(None)
+        perm = torch.tensor(order, device=x.device)
+        eng.set_moe_runs(runs)
+        try:
+            _, tokens = eng.forward_heatmaps(x.index_select(0, perm).float(), flip=False, want_features=True,
                                              want_heatmaps=False)
-            hp, wp = eng.tokens_hw
-            f = ops.tokens_to_nchw(tokens, hp, wp)
-            if out is None:
-                out = torch.empty(n, *f.shape[1:], device=f.device, dtype=f.dtype)
-            out.index_copy_(0, idx, f)
+        finally:
+            eng.set_moe_runs(None)
+        hp, wp = eng.tokens_hw
+        f = ops.tokens_to_nchw(tokens, hp, wp)
+        out = torch.empty_like(f)
+        out.index_copy_(0, perm, f)
         return out
 
     def forward(self, x, dataset_source=None):

@@ -46,7 +46,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
   // offsets in bytes
-  size_t patches, x, xn, qkv, attn, hidden, head_a, head_b, ln_scratch, total;
+  size_t patches, x, xn, qkv, attn, hidden, head_a, head_b, ln_scratch, moe_scratch, total;
 };
 
 Workspace plan_workspace(const vpb_model_desc& d, int images) {
@@ -81,7 +81,10 @@ Workspace plan_workspace(const vpb_model_desc& d, int images) {
   w.head_a = take(a);
   w.head_b = take(b);
   // per-row LayerNorm partial statistics + arrival counters of the residual GEMMs with the fused LayerNorm
+  // (+ one small slice per ViTPose+ run: each run's fc2 launch exchanges statistics in a scratch of its own)
   w.ln_scratch = take(gemm_ln_scratch_bytes(static_cast<int>(rows), static_cast<int>(D)));
+  w.moe_scratch = take(gemm_ln_scratch_bytes(static_cast<int>(rows), static_cast<int>(D)) +
+                       VPB_MOE_MAX_RUNS * (gemm_ln_scratch_bytes(256, static_cast<int>(D)) + 1024));
   w.total = off;
   return w;
 }
@@ -156,7 +159,29 @@ int vpb_vitpose_forward(const vpb_model_desc* desc, const vpb_weights* w, const 
     return e != nullptr && atoi(e) != 0;
   }();
   const int parts = gemm_ln_parts(D), part_cols = gemm_ln_part_cols(D);
-  const bool fold = fold_enabled && w->fold != nullptr && parts > 0 && parts <= 10 && T % 64 == 0 && D % 8 == 0;
+  // ---- ViTPose+ runs (vpb_moe_runs): row ranges with their own fc2 weights and their own statistics scratch
+  const vpb_moe_runs* moe = w->moe;
+  struct MoeRun { int row0, rows; void* scratch; };
+  MoeRun runs[VPB_MOE_MAX_RUNS];
+  int n_runs = 0;
+  if (moe != nullptr) {
+    VPB_REQUIRE(moe->num_runs >= 1 && moe->num_runs <= VPB_MOE_MAX_RUNS && moe->image_begin && moe->fc2_w && moe->fc2_b,
+                "forward: bad vpb_moe_runs (num_runs %d)", moe->num_runs);
+    VPB_REQUIRE(moe->image_begin[0] == 0 && moe->image_begin[moe->num_runs] == images,
+                "forward: vpb_moe_runs must cover the %d images of the batch exactly", images);
+    uint8_t* sp = base + ws.moe_scratch;
+    for (int r = 0; r < moe->num_runs; ++r) {
+      const int i0 = moe->image_begin[r], i1 = moe->image_begin[r + 1];
+      VPB_REQUIRE(i1 > i0, "forward: vpb_moe_runs: run %d is empty", r);
+      runs[r] = MoeRun{i0 * T, (i1 - i0) * T, sp};
+      if (int e = gemm_ln_scratch_init(sp, runs[r].rows, D, stream)) return e;
+      sp += (gemm_ln_scratch_bytes(runs[r].rows, D) + 1023) / 1024 * 1024;
+    }
+    n_runs = moe->num_runs;
+  }
+  unsigned moe_epoch = 0;
+  const bool fold = fold_enabled && w->fold != nullptr && moe == nullptr && parts > 0 && parts <= 10 && T % 64 == 0 &&
+                    D % 8 == 0;
   void* stats = ln_scratch;
   const LnFoldIn ln_in{stats, nullptr, parts, part_cols, d.ln_eps};
 
@@ -209,6 +234,20 @@ int vpb_vitpose_forward(const vpb_model_desc* desc, const vpb_weights* w, const 
     const float* ng = l + 1 < d.depth ? w->blocks[l + 1].ln1_g : w->last_g;
     const float* nb = l + 1 < d.depth ? w->blocks[l + 1].ln1_b : w->last_b;
     if (int e = prof_run("gemm_fc2_ln", stream, [&] {
+          if (n_runs > 0) {      // ViTPose+: one launch per run of images, each with its dataset's fc2
+            ++moe_epoch;
+            for (int r = 0; r < n_runs; ++r) {
+              const size_t r0 = static_cast<size_t>(runs[r].row0);
+              const uint8_t* a = static_cast<const uint8_t*>(hidden) + r0 * d.mlp_hidden * 2;
+              float* xr = x + r0 * D;
+              void* xnr = static_cast<uint8_t*>(xn) + r0 * D * 2;
+              if (int e2 = gemm_bf16_ln(a, moe->fc2_w[r * d.depth + l], runs[r].rows, D, d.mlp_hidden, EPI_RESID_F32,
+                                        moe->fc2_b[r * d.depth + l], xr, xr, 0, ng, nb, d.ln_eps, xnr, runs[r].scratch,
+                                        moe_epoch, 0, stream))
+                return e2;
+            }
+            return 0;
+          }
           if (fold && l + 1 < d.depth)
             return gemm_bf16_ln(hidden, b.fc2_w, rows, D, d.mlp_hidden, EPI_RESID_F32, b.fc2_b, x, x, 0, nullptr, nullptr,
                                 d.ln_eps, xn, nullptr, 0, 0, stream, nullptr, 0, stats);

@@ -36,8 +36,8 @@ class TopDownMoE(TopDown):
 
     @torch.no_grad()
     def forward_test(self, img, img_metas, return_heatmap=False, **kwargs):
-        """top_down_moe.py:205-244. Crops are grouped by dataset index; each group runs through the engine packed
-        with that dataset's effective FFN weights, and the groups' results are put back in batch order."""
+        """top_down_moe.py:205-244. A batch of one dataset runs through the engine packed with that dataset's effective
+        FFN weights; a mixed batch runs in one pass with the crops sorted by dataset (see below)."""
         assert img.size(0) == len(img_metas)
         if img.size(0) > 1:
             assert 'bbox_id' in img_metas[0]
@@ -46,32 +46,38 @@ class TopDownMoE(TopDown):
         if len(groups) == 1:
             self._dataset_idx = groups[0]
             return TopDown.forward_test(self, img, img_metas, return_heatmap=return_heatmap, **kwargs)
-        merged = None
+        # Mixed batch: ONE forward pass. Crops are sorted by dataset; every kernel runs on the whole batch except
+        # mlp.fc2 (+ residual + LayerNorm), launched once per run of crops with that dataset's expert columns
+        # (vpb_moe_runs); the results go back in batch order.
+        order, runs = self.backbone.dataset_runs(src)
+        eng = self.backbone.moe_engine(self.keypoint_head if self.with_keypoint else None)
+        dev = eng.device
+        perm = torch.tensor(order)
+        metas_p = [img_metas[i] for i in order]
+        # the reference flips the WHOLE batch back with img_metas[0]['flip_pairs'] (top_down_moe.py:229-232)
+        if 'flip_pairs' in img_metas[0]:
+            metas_p[0] = dict(metas_p[0], flip_pairs=img_metas[0]['flip_pairs'])
+        img_p = img.index_select(0, perm.to(img.device)).to(dev, non_blocking=True)     # (one call: no host chunking)
+        eng.set_moe_runs(runs)
+        self._use_moe_engine = True
+        try:
+            r = TopDown.forward_test(self, img_p, metas_p, return_heatmap=return_heatmap, **kwargs)
+        finally:
+            self._use_moe_engine = False
+            eng.set_moe_runs(None)
         n = len(img_metas)
-        for d in groups:
-            idx = np.nonzero(src == d)[0]
-            self._dataset_idx = d
-            sel = torch.from_numpy(idx).to(img.device)
-            # the reference flips the WHOLE batch back with img_metas[0]['flip_pairs'] (top_down_moe.py:229-232)
-            metas_d = [img_metas[i] for i in idx]
-            if 'flip_pairs' in img_metas[0]:
-                metas_d[0] = dict(metas_d[0], flip_pairs=img_metas[0]['flip_pairs'])
-            r = TopDown.forward_test(self, img.index_select(0, sel), metas_d, return_heatmap=return_heatmap, **kwargs)
-            if merged is None:
-                merged = dict(preds=np.zeros((n,) + r['preds'].shape[1:], r['preds'].dtype),
-                              boxes=np.zeros((n,) + r['boxes'].shape[1:], r['boxes'].dtype),
-                              image_paths=[None] * n, bbox_ids=[None] * n if r['bbox_ids'] is not None else None,
-                              output_heatmap=None if r['output_heatmap'] is None else
-                              np.zeros((n,) + r['output_heatmap'].shape[1:], r['output_heatmap'].dtype))
-            merged['preds'][idx], merged['boxes'][idx] = r['preds'], r['boxes']
-            for j, i in enumerate(idx):
-                merged['image_paths'][i] = r['image_paths'][j]
-                if merged['bbox_ids'] is not None:
-                    merged['bbox_ids'][i] = r['bbox_ids'][j]
-            if merged['output_heatmap'] is not None:
-                merged['output_heatmap'][idx] = r['output_heatmap']
-        return merged
+        inv = np.empty(n, dtype=np.int64)
+        inv[np.asarray(order)] = np.arange(n)
+        out = dict(r)
+        out['preds'], out['boxes'] = r['preds'][inv], r['boxes'][inv]
+        out['image_paths'] = [r['image_paths'][j] for j in inv]
+        out['bbox_ids'] = None if r['bbox_ids'] is None else [r['bbox_ids'][j] for j in inv]
+        if r.get('output_heatmap') is not None:
+            out['output_heatmap'] = r['output_heatmap'][inv]
+        return out
 
     def _engine(self):
-        return self.backbone.engine(self.keypoint_head if self.with_keypoint else None,
-                                    getattr(self, '_dataset_idx', 0))
+        head = self.keypoint_head if self.with_keypoint else None
+        if getattr(self, '_use_moe_engine', False):
+            return self.backbone.moe_engine(head)
+        return self.backbone.engine(head, getattr(self, '_dataset_idx', 0))

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BlockFold, BlockWeights, ModelDesc, Weights, check, lib, ptr, stream_ptr
+from ._lib import BlockFold, BlockWeights, ModelDesc, MoeRuns, Weights, check, lib, ptr, stream_ptr
 
 BF16 = torch.bfloat16
 
@@ -217,6 +217,54 @@ class VitPoseEngine:
         self.max_batch = max_batch
 
     # ---- workspace ------------------------------------------------------------------------------
+    # ---- ViTPose+ (vpb_moe_runs): crops sorted by dataset, one mlp.fc2 launch per run ------------------
+    def set_experts(self, experts):
+        """experts: {dataset_idx: ([bf16 fc2 weight per block], [fp32 fc2 bias per block])} device tensors (kept here)."""
+        self.experts = experts
+
+    def set_moe_runs(self, runs):
+        """runs: [(dataset_idx, number of crops), ...] covering, in order, the crops of the NEXT forward calls (None:
+        back to the packed weights for every crop)."""
+        self._moe_runs = runs
+
+    def _moe_struct(self, n, flip):
+        """ctypes vpb_moe_runs for a batch of n crops (+ their flipped copies) and the arrays it points to."""
+        runs = getattr(self, '_moe_runs', None)
+        if not runs:
+            return None, None
+        assert sum(c for _, c in runs) == n, 'the runs must cover the batch'
+        passes = 2 if flip else 1
+        R, depth = len(runs) * passes, self.desc.depth
+        if R > _lib.MOE_MAX_RUNS:
+            raise ValueError(f'{R} runs of datasets in one batch (max {_lib.MOE_MAX_RUNS}): sort the crops by dataset_idx')
+        begin = (ctypes.c_int32 * (R + 1))()
+        wp = (ctypes.c_void_p * (R * depth))()
+        bp = (ctypes.c_void_p * (R * depth))()
+        pos = 0
+        for r, (d, c) in enumerate(list(runs) * passes):
+            begin[r] = pos
+            pos += c
+            ws_, bs_ = self.experts[int(d)]
+            for l in range(depth):
+                wp[r * depth + l] = ws_[l].data_ptr()
+                bp[r * depth + l] = bs_[l].data_ptr()
+        begin[R] = pos
+        mr = MoeRuns(R, ctypes.cast(begin, ctypes.POINTER(ctypes.c_int32)), ctypes.cast(wp, ctypes.POINTER(ctypes.c_void_p)),
+                     ctypes.cast(bp, ctypes.POINTER(ctypes.c_void_p)))
+        return mr, (begin, wp, bp)
+
+    def _forward_call(self, img, n, flip, ws_ptr, ws_bytes, out_main, out_flip, feat):
+        mr, keep = self._moe_struct(n, flip)
+        w = self.weights.struct
+        w.moe = ctypes.pointer(mr) if mr is not None else None
+        try:
+            check(lib().vpb_vitpose_forward(ctypes.byref(self.desc), ctypes.byref(w), ptr(img), n, int(flip), ws_ptr,
+                                            ws_bytes, ptr(out_main), ptr(out_flip), ptr(feat), stream_ptr()),
+                  'vpb_vitpose_forward')
+        finally:
+            w.moe = None
+        del keep
+
     def _workspace(self, images):
         if self._ws is None or images > self._ws_images:
             nbytes = lib().vpb_workspace_bytes(ctypes.byref(self.desc), images)
@@ -261,9 +309,7 @@ class VitPoseEngine:
                 raise ValueError(f'heatmap buffer must be contiguous float32 {want}, got {tuple(t.shape)} {t.dtype}')
         images = 2 * n if flip else n
         ws_ptr, ws_bytes = self._workspace(images)
-        check(lib().vpb_vitpose_forward(ctypes.byref(self.desc), ctypes.byref(self.weights.struct), ptr(img), n,
-                                        int(flip), ws_ptr, ws_bytes, ptr(out_main), ptr(out_flip) if flip else None,
-                                        None, stream_ptr()), 'vpb_vitpose_forward')
+        self._forward_call(img, n, flip, ws_ptr, ws_bytes, out_main, out_flip if flip else None, None)
 
     def forward_heatmaps(self, img, flip=False, want_features=False, want_heatmaps=True):
         """img fp32 CUDA [n,3,H,W] -> raw heatmaps fp32 [(2n|n), K, H/4, W/4] (+ bf16 token features)."""
@@ -278,9 +324,7 @@ class VitPoseEngine:
         hp, wp = self.tokens_hw
         feat = (torch.empty(images, hp * wp, self.desc.embed_dim, device=self.device, dtype=BF16)
                 if want_features else None)
-        check(lib().vpb_vitpose_forward(ctypes.byref(self.desc), ctypes.byref(self.weights.struct), ptr(img), n,
-                                        int(flip), ws_ptr, ws_bytes, ptr(hm), None, ptr(feat), stream_ptr()),
-              'vpb_vitpose_forward')
+        self._forward_call(img, n, flip, ws_ptr, ws_bytes, hm, None, feat)
         return hm, feat
 
     # ---- decode -------------------------------------------------------------------------------------
