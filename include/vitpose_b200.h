@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VPB_ABI_VERSION 3
+#define VPB_ABI_VERSION 4
 
 int vpb_abi_version(void);
 const char* vpb_last_error(void);
@@ -172,6 +172,11 @@ int vpb_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogu
  * gradient dW[N_out,K_in] += dY[tokens,N_out]^T . X[tokens,K_in] straight from dY and X — both tiles are consumed as
  * MN-major tensor-core operands (no transposed copies), the contraction over the tokens is split over CTAs. */
 int vpb_gemm_bf16_atb_accum(const void* At, const void* Bt, int M, int N, int K, float* out, int ldo, void* stream);
+/* The same with explicit row pitches lda >= M, ldb >= N (elements, multiples of 8): At / Bt are column slices of wider
+ * row-major matrices. ViTPose+ (MoEMlp, mmpose/models/backbones/vit_moe.py:97-115): the shared fc2 owns the first
+ * D - part_features columns of the FFN output gradient, the expert of a crop's dataset the last part_features. */
+int vpb_gemm_bf16_atb_accum_ld(const void* At, int lda, const void* Bt, int ldb, int M, int N, int K, float* out,
+                               int ldo, void* stream);
 /* Residual-stream GEMM with the following LayerNorm fused into its epilogue:
  *   out fp32 [M,N] = (epilogue == VPB_EPI_RESID_F32 ? aux[M,N] : aux[row % period, N]) + A.B^T + bias
  *   xn  bf16 [M,N] = LayerNorm(out row, eps) * gamma + beta

@@ -228,3 +228,19 @@ def build_reference_topdown(model_cfg):
     m = ref.TopDown(**cfg)
     m.eval()
     return m
+
+
+def build_reference_topdown_moe(model_cfg):
+    """The reference's ViTPose+ detector (mmpose/models/detectors/top_down_moe.py:15-92) over its ViTMoE backbone
+    (mmpose/models/backbones/vit_moe.py), from a ``model=`` block with ``associate_keypoint_head``."""
+    import copy
+    load_reference()
+    if 'mmpose.models.backbones.vit_moe' not in sys.modules:
+        _load('mmpose.models.backbones.vit_moe', 'mmpose/models/backbones/vit_moe.py')
+    if 'mmpose.models.detectors.top_down_moe' not in sys.modules:
+        _load('mmpose.models.detectors.top_down_moe', 'mmpose/models/detectors/top_down_moe.py')
+    cfg = copy.deepcopy(model_cfg)
+    cfg.pop('type', None)
+    cfg.pop('pretrained', None)
+    cfg.setdefault('train_cfg', dict())
+    return sys.modules['mmpose.models.detectors.top_down_moe'].TopDownMoE(**cfg)

@@ -98,6 +98,125 @@ def test_moe_state_dict_keys_equal_reference():
     assert torch.allclose(f_ref, f_or, atol=1e-5)
 
 
+def _train_batch(n, K, seed, src):
+    g = torch.Generator().manual_seed(seed)
+    ys, xs = torch.meshgrid(torch.arange(64.), torch.arange(48.), indexing='ij')
+    cx = torch.rand(n, K, generator=g) * 47
+    cy = torch.rand(n, K, generator=g) * 63
+    t = torch.exp(-((xs - cx[..., None, None]) ** 2 + (ys - cy[..., None, None]) ** 2) / 8.0).contiguous()
+    w = (torch.rand(n, K, 1, generator=g) > 0.2).float()
+    return synthetic.synthetic_crops(n, seed), t, w, [dict(dataset_idx=int(d)) for d in src]
+
+
+def _moe_train_cfg(depth=2):
+    """every head with the keypoint count of the batch's targets (the reference's get_loss needs that, mse_loss.py:30)"""
+    cfg = _moe_cfg(depth=depth)
+    cfg['associate_keypoint_head'] = [dict(cfg['keypoint_head']), dict(cfg['keypoint_head'])]
+    return cfg
+
+
+@pytest.mark.reference
+def test_moe_training_oracle_equals_live_reference():
+    """Pins oracle.train_loss_and_grads_moe: the unmodified reference TopDownMoE.forward_train + _parse_losses'
+    loss + backward() on the same weights and a batch that mixes datasets 0 and 2 (dataset 1 absent)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip('reference tree not mounted')
+    cfg = _moe_train_cfg()
+    ref = ref_loader.build_reference_topdown_moe(cfg)
+    _randomise(ref, 3)
+    ref.train()
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    src = [2, 0, 0, 2, 2]
+    img, target, tw, metas = _train_batch(5, 5, 3, src)
+    losses = ref.forward_train(img, target, tw, metas)
+    loss, log_vars = ref._parse_losses(losses)
+    loss.backward()
+    o_losses, _, g = VT.train_loss_and_grads_moe(sd, img, target, tw, cfg, torch.tensor(src))
+    assert set(o_losses) == {k for k in losses if 'loss' in k} == {'main_stream_loss', '1_loss', '2_loss'}
+    for k, v in o_losses.items():
+        assert abs(float(v) - float(losses[k])) <= 1e-6 * max(1.0, abs(float(v))), k
+    assert float(o_losses['1_loss']) == 0.0
+    for nm, p in ref.named_parameters():
+        assert nm in g, nm
+        if p.grad is None:
+            assert g[nm] is None or float(g[nm].abs().max()) == 0.0, nm
+            continue
+        assert torch.allclose(p.grad, g[nm], rtol=1e-4, atol=1e-7), nm
+    # the absent dataset's expert still gets a (zero) gradient: the dense masked form of vit_moe.py:107-111
+    assert float(g['backbone.blocks.0.mlp.experts.1.weight'].abs().max()) == 0.0
+    for k, v in sd.items():      # BatchNorm running statistics of every head were updated identically
+        if 'running_' in k:
+            assert torch.allclose(v, ref.state_dict()[k], rtol=1e-5, atol=1e-7), k
+
+
+def _rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('src,fused', [([2, 0, 0, 2, 1, 2], True), ([2, 0, 0, 2, 2], True), ([1, 1, 1], True),
+                                       ([0, 2, 1, 0], False)])
+def test_topdown_moe_forward_train_backward_vs_oracle(src, fused, monkeypatch):
+    """TopDownMoE.forward_train -> sum of the losses -> backward() on the B200 path against torch.autograd over the fp32
+    oracle (pinned to the live reference above): mixed batches in arbitrary order, an absent dataset (its expert and
+    head get zero / no gradient), a homogeneous batch. Tolerances as in tests/test_gpu_train_step.py."""
+    import vitpose_b200 as V
+    from vitpose_b200 import training
+    monkeypatch.setattr(training, 'FUSE_MLP', fused)
+    cfg = _moe_train_cfg()
+    model = V.build_posenet(cfg)
+    _randomise(model, 5)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    n = len(src)
+    img, target, tw, metas = _train_batch(n, 5, 5, src)
+    ref_sd = {k: v.clone() for k, v in sd.items()}
+    l_ref, hm_ref, g_ref = VT.train_loss_and_grads_moe(ref_sd, img, target, tw, cfg, torch.tensor(src))
+    model = model.cuda().train()
+    out = model.train_step(dict(img=img.cuda(), target=target.cuda(), target_weight=tw.cuda(), img_metas=metas))
+    assert set(out['log_vars']) == {'main_stream_loss', 'main_stream_acc', '1_loss', '1_acc', '2_loss', '2_acc', 'loss'}
+    out['loss'].backward()
+    torch.cuda.synchronize()
+    for k, v in l_ref.items():
+        assert abs(out['log_vars'][k] - float(v)) <= 2e-2 * abs(float(v)) + 1e-12, (k, out['log_vars'][k], float(v))
+    assert abs(out['loss'].item() - float(sum(l_ref.values()))) <= 2e-2 * float(sum(l_ref.values()))
+    present = set(src)
+    worst = {}
+    for nm, p in model.named_parameters():
+        rf = g_ref[nm]
+        if p.grad is None:          # only a head whose loss is identically zero may lack a gradient
+            assert rf is None or float(rf.abs().max()) == 0.0, nm
+            continue
+        gr = p.grad.cpu()
+        assert gr.shape == rf.shape and torch.isfinite(gr).all(), nm
+        if rf.norm() < 1e-12:
+            assert float(gr.abs().max()) <= 1e-12, (nm, float(gr.abs().max()))
+            continue
+        worst[nm] = (_rel(gr, rf), _cos(gr, rf))
+    for e in range(3):              # every expert has a gradient tensor; absent datasets' are exactly zero
+        for l in range(2):
+            gw = dict(model.named_parameters())[f'backbone.blocks.{l}.mlp.experts.{e}.weight'].grad
+            assert gw is not None
+            assert (float(gw.abs().max()) > 0) == (e in present), (e, l)
+    bad = {k: v for k, v in worst.items() if v[0] > 0.15 or v[1] < 0.99}
+    top = sorted(worst.items(), key=lambda kv: -kv[1][0])[:5]
+    assert not bad, f'gradient mismatch (rel err, cosine): {bad}; worst five: {top}'
+    names = [nm for nm, p in model.named_parameters() if p.grad is not None]
+    flat = torch.cat([dict(model.named_parameters())[nm].grad.flatten().cpu() for nm in names])
+    flat_ref = torch.cat([g_ref[nm].flatten() for nm in names])
+    assert _cos(flat, flat_ref) > 0.998 and abs(float(flat.norm() / flat_ref.norm()) - 1) < 0.02
+    # BatchNorm running statistics of every head that ran
+    for k in ref_sd:
+        if 'running_' in k:
+            assert _rel(model.state_dict()[k].cpu(), ref_sd[k]) < 2e-2, k
+
+
 @pytest.mark.gpu
 def test_topdown_moe_mixed_batch_vs_oracle():
     import vitpose_b200 as V

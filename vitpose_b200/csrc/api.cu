@@ -361,6 +361,10 @@ int vpb_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogu
 int vpb_gemm_bf16_atb_accum(const void* At, const void* Bt, int M, int N, int K, float* out, int ldo, void* stream) {
   return gemm_bf16_atb_accum(At, Bt, M, N, K, out, ldo, 0, as_stream(stream));
 }
+int vpb_gemm_bf16_atb_accum_ld(const void* At, int lda, const void* Bt, int ldb, int M, int N, int K, float* out,
+                               int ldo, void* stream) {
+  return gemm_bf16_atb_accum_ld(At, lda, Bt, ldb, M, N, K, out, ldo, 0, as_stream(stream));
+}
 int vpb_gemm_bf16_layernorm(const void* A, const void* B, int M, int N, int K, int epilogue, const float* bias,
                             float* out, const float* aux, int period, const float* gamma, const float* beta, float eps,
                             void* xn, void* scratch, size_t scratch_bytes, const float* row_scale, int rows_per_scale,

@@ -451,18 +451,27 @@ int gemm_bf16_ln(const void* A, const void* B, int M, int N, int K, int epilogue
 // ---- out[M, N] += At^T . Bt for row-major At [K, M], Bt [K, N] (weight gradients) ------------------------------
 int gemm_bf16_atb_accum(const void* At, const void* Bt, int M, int N, int K, float* out, int ldo, int max_ctas,
                         cudaStream_t stream) {
+  return gemm_bf16_atb_accum_ld(At, M, Bt, N, M, N, K, out, ldo, max_ctas, stream);
+}
+
+// the same with explicit row pitches (elements): At / Bt may be column slices of wider row-major matrices — the
+// gradient of a Linear layer whose output columns are a slice of dY (ViTPose+ experts, vit_moe.py:107-111)
+int gemm_bf16_atb_accum_ld(const void* At, int lda, const void* Bt, int ldb, int M, int N, int K, float* out, int ldo,
+                           int max_ctas, cudaStream_t stream) {
   VPB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-  VPB_REQUIRE(M % 8 == 0 && N % 8 == 0, "gemm(At, Bt): M=%d and N=%d must be multiples of 8 (16-byte row pitch)", M, N);
+  VPB_REQUIRE(M % 8 == 0 && N % 8 == 0 && lda >= M && ldb >= N && lda % 8 == 0 && ldb % 8 == 0,
+              "gemm(At, Bt): M=%d, N=%d and the row pitches %d / %d must be multiples of 8 (16-byte row pitch)", M, N,
+              lda, ldb);
   VPB_REQUIRE(((reinterpret_cast<uintptr_t>(At) | reinterpret_cast<uintptr_t>(Bt) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
                   ldo % 4 == 0, "gemm(At, Bt): operands / out must be 16-byte aligned, ldo %% 4 == 0");
   const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
   GemmMaps maps;
   uint64_t dims_a[2] = {(uint64_t)M, (uint64_t)K};
-  uint64_t str_a[1] = {(uint64_t)M * 2};
+  uint64_t str_a[1] = {(uint64_t)lda * 2};
   uint32_t box[2] = {64u, (uint32_t)GEMM_BK};
   if (make_tma_desc(&maps.a, TMA_BF16, At, 2, dims_a, str_a, box, TMA_SWIZZLE_128B)) return -1;
   uint64_t dims_b[2] = {(uint64_t)N, (uint64_t)K};
-  uint64_t str_b[1] = {(uint64_t)N * 2};
+  uint64_t str_b[1] = {(uint64_t)ldb * 2};
   if (make_tma_desc(&maps.b, TMA_BF16, Bt, 2, dims_b, str_b, box, TMA_SWIZZLE_128B)) return -1;
   maps.out = maps.a;
   maps.aux = maps.a;

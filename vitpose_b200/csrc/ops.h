@@ -35,6 +35,8 @@ int gemm_bf16(const void* A, const void* B, int M, int N, int K, int epilogue, c
 // dW = dY^T X straight from dY and X (MN-major tensor-core operands, K split over CTAs, atomic accumulation)
 int gemm_bf16_atb_accum(const void* At, const void* Bt, int M, int N, int K, float* out, int ldo, int max_ctas,
                         cudaStream_t stream);
+int gemm_bf16_atb_accum_ld(const void* At, int lda, const void* Bt, int ldb, int M, int N, int K, float* out, int ldo,
+                           int max_ctas, cudaStream_t stream);
 // Residual / patch-embed GEMM (epilogue EPI_RESID_F32 or EPI_POS_F32, out fp32 [M, N]) that also writes
 // xn = LayerNorm(out) * gamma + beta as bf16 [M, N] from the same kernel. `scratch` (gemm_ln_scratch_bytes(M, N)
 // bytes, 16-byte aligned) holds the per-row partial statistics the column tiles exchange; gemm_ln_scratch_init

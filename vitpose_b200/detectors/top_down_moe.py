@@ -32,7 +32,40 @@ class TopDownMoE(TopDown):
             h.init_weights()
 
     def forward_train(self, img, target, target_weight, img_metas=None, **kwargs):
-        raise NotImplementedError('multi-dataset ViTPose+ training is outside the B200 path (inference only)')
+        """top_down_moe.py:166-203: the backbone with each crop's expert, then EVERY head on the whole batch; head i's
+        loss / accuracy see only the crops of dataset i (targets and target weights of the others multiplied by 0).
+        Here the crops are first sorted by dataset (losses and accuracies are means over the batch: the order does
+        not matter), so that mlp.fc2 and its gradients run once per run of crops; backbone + all heads are one autograd
+        node (vitpose_b200/training.py) and ``loss.backward()`` fills every parameter's ``.grad`` — every expert
+        gets one (zero when its dataset is absent from the batch), as the reference's dense masked form does."""
+        from ..training import network_heatmaps_train
+        src = [int(m['dataset_idx']) for m in img_metas]
+        assert len(src) == img.size(0)
+        order, runs = self.backbone.dataset_runs(src)
+        if order != list(range(len(src))):
+            perm = torch.tensor(order, device=img.device)
+            img = img.index_select(0, perm)
+            target = target.index_select(0, perm.to(target.device))
+            target_weight = target_weight.index_select(0, perm.to(target_weight.device))
+        img_sources = torch.tensor([src[i] for i in order], device=target.device)
+        self._vpb_dataset_runs = runs
+        try:
+            outputs = network_heatmaps_train(self, img)
+        finally:
+            self._vpb_dataset_runs = None
+        if not isinstance(outputs, tuple):
+            outputs = (outputs,)
+        losses = dict()
+        heads = [self.keypoint_head, *self.associate_keypoint_heads]
+        for idx, (head, output) in enumerate(zip(heads, outputs)):
+            select = (img_sources == idx)
+            target_select = target * select.view(-1, 1, 1, 1)
+            target_weight_select = target_weight * select.view(-1, 1, 1)
+            loss = head.get_loss(output, target_select, target_weight_select)['heatmap_loss']
+            acc = head.get_accuracy(output, target_select, target_weight_select)['acc_pose']
+            losses['main_stream_loss' if idx == 0 else f'{idx}_loss'] = loss
+            losses['main_stream_acc' if idx == 0 else f'{idx}_acc'] = acc
+        return losses
 
     @torch.no_grad()
     def forward_test(self, img, img_metas, return_heatmap=False, **kwargs):

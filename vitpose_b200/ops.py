@@ -44,13 +44,21 @@ def gemm(a, b, epilogue, bias=None, out=None, aux=None, period=0, max_ctas=0):
 
 
 def gemm_atb_accum(at, bt, out):
-    """out [M,N] fp32 += at^T @ bt for row-major bf16 at [K,M], bt [K,N] (weight gradient from dY and X)."""
+    """out [M,N] fp32 += at^T @ bt for row-major bf16 at [K,M], bt [K,N] (weight gradient from dY and X). at / bt may
+    be column slices of wider row-major matrices (unit column stride, any row pitch that is a multiple of 8)."""
     _need(at, BF16, 'at'); _need(bt, BF16, 'bt'); _need(out, torch.float32, 'out')
     K, M = at.shape
     N = bt.shape[1]
     assert bt.shape[0] == K and out.shape == (M, N)
-    check(lib().vpb_gemm_bf16_atb_accum(ptr(at), ptr(bt), M, N, K, ptr(out), out.stride(0), stream_ptr()),
-          'vpb_gemm_bf16_atb_accum')
+    if at.is_contiguous() and bt.is_contiguous():
+        check(lib().vpb_gemm_bf16_atb_accum(ptr(at), ptr(bt), M, N, K, ptr(out), out.stride(0), stream_ptr()),
+              'vpb_gemm_bf16_atb_accum')
+        return out
+    assert at.stride(1) == 1 and bt.stride(1) == 1, 'operands need unit column stride'
+    if not (at.is_cuda and bt.is_cuda):
+        raise _lib.VitposeLibError('the vitpose_b200 kernels need CUDA tensors (no CPU fallback)')
+    check(lib().vpb_gemm_bf16_atb_accum_ld(at.data_ptr(), at.stride(0), bt.data_ptr(), bt.stride(0), M, N, K, ptr(out),
+                                           out.stride(0), stream_ptr()), 'vpb_gemm_bf16_atb_accum_ld')
     return out
 
 
@@ -78,7 +86,7 @@ class LnScratch:
 
 
 def gemm_layernorm(a, b, epilogue, bias, aux, gamma, beta, eps=1e-6, period=0, out=None, row_scale=None,
-                   rows_per_scale=0, scratch=None):
+                   rows_per_scale=0, scratch=None, xn=None):
     """Residual-stream GEMM + the LayerNorm that follows it, one kernel: returns (out fp32 [M,N], xn bf16 [M,N]).
     `out` may be the residual tensor itself (in-place update, as the forward pass does)."""
     _need(a, BF16, 'a'); _need(b, BF16, 'b'); _need(aux, torch.float32, 'aux')
@@ -86,7 +94,8 @@ def gemm_layernorm(a, b, epilogue, bias, aux, gamma, beta, eps=1e-6, period=0, o
     N = b.shape[0]
     assert b.shape[1] == K and epilogue in (_lib.EPI_RESID_F32, _lib.EPI_POS_F32)
     out = torch.empty(M, N, device=a.device, dtype=torch.float32) if out is None else out
-    xn = torch.empty(M, N, device=a.device, dtype=BF16)
+    xn = torch.empty(M, N, device=a.device, dtype=BF16) if xn is None else xn
+    assert xn.shape == (M, N) and xn.is_contiguous() and out.is_contiguous()
     if scratch is not None:        # an LnScratch the caller keeps across launches: no memsets
         assert (scratch.M, scratch.N) == (M, N)
         check(lib().vpb_gemm_bf16_layernorm_seq(ptr(a), ptr(b), M, N, K, epilogue, ptr(bias), ptr(out), ptr(aux), period,
@@ -338,13 +347,14 @@ def gemm_gelu_save(a, b, bias):
     return out, pre
 
 
-def gemm_gelu_bwd(dy, wt, pre, colsum=None):
+def gemm_gelu_bwd(dy, wt, pre, colsum=None, out=None):
     """(dy @ wt.T) * gelu'(pre) as bf16 [M, N]; colsum (fp32 [N], optional) += its column sums."""
     _need(dy, BF16, 'dy'); _need(wt, BF16, 'wt'); _need(pre, BF16, 'pre')
     M, K = dy.shape
     N = wt.shape[0]
-    assert pre.shape == (M, N)
-    out = torch.empty(M, N, device=dy.device, dtype=BF16)
+    assert pre.shape == (M, N) and pre.is_contiguous() and dy.is_contiguous()
+    out = torch.empty(M, N, device=dy.device, dtype=BF16) if out is None else out
+    assert out.shape == (M, N) and out.is_contiguous()
     check(lib().vpb_gemm_bf16_gelu_bwd(ptr(dy), ptr(wt), M, N, K, ptr(pre), ptr(out), N, ptr(colsum), stream_ptr()),
           'vpb_gemm_bf16_gelu_bwd')
     return out

@@ -157,6 +157,130 @@ def _param_list(model):
     return cached
 
 
+def _heads_of(model):
+    """[(parameter-name prefix, head)]: the keypoint head, then TopDownMoE's associate heads (top_down_moe.py:75-89)."""
+    out = [('keypoint_head.', model.keypoint_head)]
+    for i, h in enumerate(getattr(model, 'associate_keypoint_heads', None) or ()):
+        out.append((f'associate_keypoint_heads.{i}.', h))
+    return out
+
+
+def _head_kind(head):
+    classic = head.num_deconv_layers == 2 and head.final_conv_kernel == 1
+    simple = head.num_deconv_layers == 0 and head.final_conv_kernel == 3 and int(getattr(head, 'upsample', 0)) > 1
+    if not (classic or simple):
+        raise NotImplementedError('the training step is built for the classic decoder (2 deconv layers, 1x1 conv) '
+                                  'and the simple decoder (upsample + 3x3 conv)')
+    return 'simple' if simple else 'classic'
+
+
+def _run_scratch(model, M, D, device):
+    """statistics-exchange scratch of the fused-LayerNorm GEMMs for a run of M token rows (ViTPose+ batches)."""
+    cache = model.__dict__.setdefault('_vpb_ln_scratch_runs', {})
+    sc = cache.get((M, D))
+    if sc is None or sc.buf.device != device:
+        sc = cache[(M, D)] = ops.LnScratch(M, D, device)
+    return sc
+
+
+def _head_forward(head, xn, n, hp, wp, D, T):
+    """TopdownHeatmapSimpleHead.forward (simple_head.py:197-202) on the normalised tokens xn bf16 [n * T, D], keeping
+    what the backward pass needs. Returns (heatmaps fp32 [n, K, H, W], saved)."""
+    if _head_kind(head) == 'simple':
+        # ---- simple decoder (simple_head.py:132-139,197-202: ReLU -> bilinear x f -> Conv2d 3x3) without the
+        # upsampled map: the 3x3 conv on the token grid as nine 1x1 convs (one GEMM with 9K columns), then a
+        # bilinear gather of the nine tap maps (as vpb_vitpose_forward, csrc/api.cu)
+        fl = head.final_layer
+        K, f = fl.weight.shape[0], int(head.upsample)
+        r = ops.relu(xn)
+        w9 = ops.cast_bf16(fl.weight.detach().permute(0, 2, 3, 1).reshape(K * 9, D).contiguous())
+        z = ops.gemm(r, w9, EPI_NCHW, period=T)                                  # [n, 9K, T] fp32
+        hm = ops.simple_head_gather(z, fl.bias.detach().float().contiguous(), K, hp, wp, f)
+        return hm, dict(simple=True, relu=r, w9=w9, K=K, f=f)
+    # ---- classic decoder, BatchNorm2d in training mode (simple_head.py:324-333)
+    cur, hs = xn.view(n, hp, wp, D), []
+    for i in range(2):
+        dw = head.deconv_layers[3 * i].weight.detach()
+        bn = head.deconv_layers[3 * i + 1]
+        wp_, wd_ = ops.deconv_pack_weight(dw.contiguous())     # forward + input-gradient operands, one launch
+        raw = ops.deconv4x4s2_raw(cur, wp_)
+        if bn.training:
+            mean, rstd = ops.bn_train_stats(raw, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
+            bn.num_batches_tracked += 1
+        else:
+            mean, rstd = bn.running_mean.detach().clone(), torch.rsqrt(bn.running_var.detach() + bn.eps)
+        act = ops.bn_relu_fwd(raw, mean, rstd, bn.weight.detach(), bn.bias.detach())
+        hs.append(dict(x=cur, wp=wp_, wd=wd_, raw=raw, mean=mean, rstd=rstd, bn=bn, frozen_stats=not bn.training))
+        cur = act
+    fl = head.final_layer
+    K = fl.weight.shape[0]
+    wf = ops.cast_bf16(fl.weight.detach().reshape(K, -1).contiguous())
+    P = cur.shape[1] * cur.shape[2]
+    hm = ops.gemm(cur.view(n * P, -1), wf, EPI_NCHW, bias=fl.bias.detach(), period=P)
+    return hm.view(n, K, cur.shape[1], cur.shape[2]), dict(simple=False, head=hs, act_last=cur, wf=wf, K=K, P=P)
+
+
+def _head_backward(pfx, head, sv, dhm, s, g, zeros, scratch_zeros):
+    """Backward of _head_forward: parameter gradients into g[pfx + ...], returns the gradient of xn (bf16 [M, D])."""
+    n, T, D = s['n'], s['T'], s['D']
+    K = sv['K']
+    dev = dhm.device
+    if sv['simple']:
+        # ---- simple decoder: bias, then the transposed gather, then the tap GEMM's weight / input gradients
+        hp, wp = s['hw']
+        f = sv['f']
+        P_out = hp * f * wp * f
+        dhm32 = dhm.contiguous().float()
+        Kp = (K + 7) // 8 * 8
+        dbf = zeros(Kp)
+        ops.colsum_accumulate(ops.nchw_to_rows(dhm32.view(n, K, P_out), Kp), dbf)
+        g[pfx + 'final_layer.bias'] = dbf[:K]
+        Kp9 = (9 * K + 7) // 8 * 8
+        dz = ops.simple_head_gather_bwd(dhm32, hp, wp, f, Kp9)                       # [M, Kp9], column k*9+t
+        dw9 = scratch_zeros(Kp9, D)
+        _wgrad(dz, sv['relu'], dw9)
+        dwf = zeros(K, D, 3, 3)
+        dwf.copy_(dw9[:9 * K].view(K, 3, 3, D).permute(0, 3, 1, 2))
+        g[pfx + 'final_layer.weight'] = dwf
+        w9_pad = torch.zeros(Kp9, D, device=dev, dtype=BF16)
+        w9_pad[:9 * K] = sv['w9']
+        return ops.relu_bwd(sv['relu'], ops.gemm(dz, ops.transpose(w9_pad), EPI_BIAS))   # [M, D]
+    # ---- final 1x1 conv: rows = pixels, columns = keypoints (zero padded to a multiple of 8)
+    P = sv['P']
+    Kp = (K + 7) // 8 * 8
+    dy = ops.nchw_to_rows(dhm.contiguous().float().view(n, K, P), Kp)                # [n*P, Kp]
+    act = sv['act_last'].view(n * P, -1)
+    C = act.shape[1]
+    dwf = zeros(Kp, C)
+    _wgrad(dy, act, dwf)
+    dbf = zeros(Kp)
+    ops.colsum_accumulate(dy, dbf)
+    g[pfx + 'final_layer.weight'] = dwf[:K].reshape(K, C, 1, 1)
+    g[pfx + 'final_layer.bias'] = dbf[:K]
+    wf_pad = torch.zeros(Kp, C, device=dev, dtype=BF16)
+    wf_pad[:K] = sv['wf']
+    dact = ops.gemm(dy, ops.transpose(wf_pad), EPI_BIAS)                             # [n*P, C]
+    # ---- [ConvTranspose2d -> BatchNorm2d(train) -> ReLU] x 2, last to first
+    for i in (1, 0):
+        hsi = sv['head'][i]
+        bn, raw, xin, wp_ = hsi['bn'], hsi['raw'], hsi['x'], hsi['wp']
+        cout = raw.shape[-1]
+        dgam, dbet = zeros(cout), zeros(cout)
+        draw = ops.bn_relu_bwd(raw, dact.view(raw.shape), hsi['mean'], hsi['rstd'], bn.weight.detach(),
+                               bn.bias.detach(), dgam, dbet, eval_mode=hsi['frozen_stats'])
+        g[pfx + f'deconv_layers.{3 * i + 1}.weight'] = dgam
+        g[pfx + f'deconv_layers.{3 * i + 1}.bias'] = dbet
+        a_t = ops.deconv_phase_dy(draw)                                             # [4, pixels, cout]
+        b_t = ops.deconv_gather_x(xin)                                               # [4, pixels, 4*cin]
+        dwp = scratch_zeros(4, cout, wp_.shape[2])
+        for ph in range(4):
+            _wgrad(a_t[ph], b_t[ph], dwp[ph])
+        g[pfx + f'deconv_layers.{3 * i}.weight'] = ops.deconv_unpack_wgrad(dwp, zeros(wp_.shape[2] // 4, cout, 4, 4))
+        del a_t, b_t
+        dact = ops.gemm(ops.deconv_gather_dy(draw), hsi['wd'], EPI_BIAS)             # [pixels_in, cin]
+    return dact.view(-1, D)
+
+
 class _NetworkFn(torch.autograd.Function):
     """img [N,3,H,W] fp32 (+ every parameter of backbone and head) -> heatmaps [N,K,H/4,W/4] fp32."""
 
@@ -165,11 +289,8 @@ class _NetworkFn(torch.autograd.Function):
         bb, head = model.backbone, model.keypoint_head
         if not img.is_cuda:
             raise _lib.VitposeLibError('forward_train needs CUDA tensors (vitpose_b200 has no CPU path)')
-        classic = head.num_deconv_layers == 2 and head.final_conv_kernel == 1
-        simple = head.num_deconv_layers == 0 and head.final_conv_kernel == 3 and int(getattr(head, 'upsample', 0)) > 1
-        if not (classic or simple):
-            raise NotImplementedError('the training step is built for the classic decoder (2 deconv layers, 1x1 conv) '
-                                      'and the simple decoder (upsample + 3x3 conv)')
+        for _, head_i in _heads_of(model):
+            _head_kind(head_i)
         img = img.contiguous().float()
         n = img.shape[0]
         D, heads, depth = bb.embed_dim, bb.num_heads, bb.depth
@@ -178,8 +299,18 @@ class _NetworkFn(torch.autograd.Function):
         s = {}                                           # saved activations / operands for the backward pass
         # ---- operands from the current fp32 master parameters
         bank = getattr(model, '_vpb_linear_bank', None)
+        # ViTPose+ (ViTMoE, vit_moe.py:77-115): the FFN output of a crop is cat(fc2(h), experts[dataset](h)). The crops
+        # arrive sorted by dataset (TopDownMoE.forward_train); `runs` = [(dataset, crops)] in batch order.
+        E = len(bb.blocks[0].mlp.experts) if hasattr(bb.blocks[0].mlp, 'experts') else 0
+        runs = getattr(model, '_vpb_dataset_runs', None) or [(0, n)]
+        if E == 0:
+            runs = [(0, n)]
+        elif sum(c for _, c in runs) != n or any(not 0 <= d < E for d, _ in runs):
+            raise IndexError(f'dataset runs {runs} do not describe a batch of {n} crops over {E} experts')
+        per_blk = 4 + E
         layers = [bb.patch_embed.proj] + [m for blk in bb.blocks
-                                          for m in (blk.attn.qkv, blk.attn.proj, blk.mlp.fc1, blk.mlp.fc2)]
+                                          for m in (blk.attn.qkv, blk.attn.proj, blk.mlp.fc1, blk.mlp.fc2,
+                                                    *(blk.mlp.experts if E else ()))]
         if bank is None or bank.layers != layers or bank.arena.device != img.device:
             bank = _LinearBank(layers)
             model._vpb_linear_bank = bank
@@ -189,8 +320,15 @@ class _NetworkFn(torch.autograd.Function):
         pos_tok = (pos[0, 1:] + pos[0, :1]).contiguous()
         blocks = []
         for i in range(len(bb.blocks)):
-            q, pr, f1, f2 = lins[1 + 4 * i:5 + 4 * i]
-            blocks.append(dict(qkv=q, proj=pr, fc1=f1, fc2=f2))
+            q, pr, f1, f2 = lins[1 + per_blk * i:5 + per_blk * i]
+            w = dict(qkv=q, proj=pr, fc1=f1, fc2=f2)
+            if E:
+                # the effective fc2 of dataset d (tools/model_split.py:36-40): rows / bias of fc2, then of experts[d]
+                ex = lins[5 + per_blk * i:5 + per_blk * i + E]
+                w['experts'] = ex
+                w['cat'] = {d: (torch.cat([f2.w, ex[d].w], 0), torch.cat([f2.wt, ex[d].wt], 1),
+                                torch.cat([f2.b, ex[d].b], 0)) for d in sorted({d for d, _ in runs})}
+            blocks.append(w)
         # ---- ViT (vit.py:313-332). Stochastic depth (DropPath, vit.py:48-56,132,138-139,233): block i drops the
         # whole residual branch of a crop with probability linspace(0, drop_path_rate, depth)[i]; the surviving
         # branches are divided by keep_prob. The per-crop factor goes into the residual GEMM epilogue.
@@ -219,56 +357,44 @@ class _NetworkFn(torch.autograd.Function):
                 pre = ops.gemm(xn2, w['fc1'].w, EPI_BIAS, bias=w['fc1'].b)
                 h = ops.gelu_fwd(pre)
             nxt = bb.blocks[l + 1].norm1 if l + 1 < depth else bb.last_norm
-            x, xn = ops.gemm_layernorm(h, w['fc2'].w, EPI_RESID, w['fc2'].b, x_mid, nxt.weight.detach(),
-                                       nxt.bias.detach(), 1e-6, row_scale=s2, rows_per_scale=T, scratch=lns)
+            if E:
+                # one launch per run of crops with that dataset's effective fc2 (as vpb_moe_runs does in inference)
+                x = torch.empty(M, D, device=img.device, dtype=torch.float32)
+                xn = torch.empty(M, D, device=img.device, dtype=BF16)
+                c0 = 0
+                for d, cnt in runs:
+                    r0, r1 = c0 * T, (c0 + cnt) * T
+                    wc, _, bc = w['cat'][d]
+                    ops.gemm_layernorm(h[r0:r1], wc, EPI_RESID, bc, x_mid[r0:r1], nxt.weight.detach(),
+                                       nxt.bias.detach(), 1e-6, row_scale=None if s2 is None else s2[c0:c0 + cnt],
+                                       rows_per_scale=T, scratch=_run_scratch(model, r1 - r0, D, img.device),
+                                       out=x[r0:r1], xn=xn[r0:r1])
+                    c0 += cnt
+            else:
+                x, xn = ops.gemm_layernorm(h, w['fc2'].w, EPI_RESID, w['fc2'].b, x_mid, nxt.weight.detach(),
+                                           nxt.bias.detach(), 1e-6, row_scale=s2, rows_per_scale=T, scratch=lns)
             a.update(qkv=qkv, attn=attn, lse=lse, x_mid=x_mid, xn2=xn2, pre=pre, h=h, s1=s1, s2=s2)
             acts.append(a)
-        s.update(patches=patches, acts=acts, x_final=x, blocks=blocks, pe=pe)
-        if simple:
-            # ---- simple decoder (simple_head.py:132-139,197-202: ReLU -> bilinear x f -> Conv2d 3x3) without the
-            # upsampled map: the 3x3 conv on the token grid as nine 1x1 convs (one GEMM with 9K columns), then a
-            # bilinear gather of the nine tap maps (as vpb_vitpose_forward, csrc/api.cu)
-            fl = head.final_layer
-            K, f = fl.weight.shape[0], int(head.upsample)
-            r = ops.relu(xn)
-            w9 = ops.cast_bf16(fl.weight.detach().permute(0, 2, 3, 1).reshape(K * 9, D).contiguous())
-            z = ops.gemm(r, w9, EPI_NCHW, period=T)                                  # [n, 9K, T] fp32
-            hm = ops.simple_head_gather(z, fl.bias.detach().float().contiguous(), K, hp, wp, f)
-            s.update(simple=True, relu=r, w9=w9, K=K, f=f, n=n, T=T, M=M, D=D, heads=heads, hw=(hp, wp))
-            ctx.s, ctx.model, ctx.names = s, model, [nm for nm, _ in _param_list(model)]
-            return hm
-        # ---- head (simple_head.py:197-202), BatchNorm2d in training mode
-        feat = xn.view(n, hp, wp, D)
-        cur, hs = feat, []
-        for i in range(2):
-            dw = head.deconv_layers[3 * i].weight.detach()
-            bn = head.deconv_layers[3 * i + 1]
-            wp_, wd_ = ops.deconv_pack_weight(dw.contiguous())     # forward + input-gradient operands, one launch
-            raw = ops.deconv4x4s2_raw(cur, wp_)
-            if bn.training:
-                mean, rstd = ops.bn_train_stats(raw, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
-                bn.num_batches_tracked += 1
-            else:
-                mean, rstd = bn.running_mean.detach().clone(), torch.rsqrt(bn.running_var.detach() + bn.eps)
-            act = ops.bn_relu_fwd(raw, mean, rstd, bn.weight.detach(), bn.bias.detach())
-            hs.append(dict(x=cur, wp=wp_, wd=wd_, raw=raw, mean=mean, rstd=rstd, bn=bn, frozen_stats=not bn.training))
-            cur = act
-        fl = head.final_layer
-        K = fl.weight.shape[0]
-        wf = ops.cast_bf16(fl.weight.detach().reshape(K, -1).contiguous())
-        P = cur.shape[1] * cur.shape[2]
-        hm = ops.gemm(cur.view(n * P, -1), wf, EPI_NCHW, bias=fl.bias.detach(), period=P)
-        s.update(head=hs, act_last=cur, wf=wf, K=K, P=P, n=n, T=T, M=M, D=D, heads=heads, hw=(hp, wp))
+        s.update(patches=patches, acts=acts, x_final=x, blocks=blocks, pe=pe, runs=runs, E=E,
+                 n=n, T=T, M=M, D=D, heads=heads, hw=(hp, wp))
+        # ---- keypoint heads: TopDown has one; TopDownMoE runs the main head and every associate head on the whole
+        # batch (top_down_moe.py:180-201) and returns one heatmap tensor per head
+        outs, saved = [], []
+        for _, head_i in _heads_of(model):
+            hm, sv = _head_forward(head_i, xn, n, hp, wp, D, T)
+            outs.append(hm)
+            saved.append(sv)
+        s['head_saved'] = saved
         ctx.s, ctx.model, ctx.names = s, model, [nm for nm, _ in _param_list(model)]
-        return hm.view(n, K, cur.shape[1], cur.shape[2])
+        return outs[0] if len(outs) == 1 else tuple(outs)
 
     @staticmethod
-    def backward(ctx, dhm):
+    def backward(ctx, *dhms):
         s, model = ctx.s, ctx.model
-        bb, head = model.backbone, model.keypoint_head
-        n, T, M, D, heads, K = s['n'], s['T'], s['M'], s['D'], s['heads'], s['K']
-        P = s.get('P')
-        dev = dhm.device
+        bb = model.backbone
+        n, T, M, D, heads = s['n'], s['T'], s['M'], s['D'], s['heads']
+        runs, E = s['runs'], s['E']
+        dev = next(d for d in dhms if d is not None).device
         g = {}                                           # parameter name -> fp32 gradient
 
         # Every parameter gradient lives in ONE zero-initialised arena, in the order the backward pass produces
@@ -319,60 +445,19 @@ class _NetworkFn(torch.autograd.Function):
                 pending.append(dist.all_reduce(seg, op=op, group=group, async_op=True))
             sent[0] = used[0]
 
-        if s.get('simple'):
-            # ---- simple decoder: bias, then the transposed gather, then the tap GEMM's weight / input gradients
-            hp, wp = s['hw']
-            f = s['f']
-            P_out = hp * f * wp * f
-            dhm32 = dhm.contiguous().float()
-            Kp = (K + 7) // 8 * 8
-            dbf = zeros(Kp)
-            ops.colsum_accumulate(ops.nchw_to_rows(dhm32.view(n, K, P_out), Kp), dbf)
-            g['keypoint_head.final_layer.bias'] = dbf[:K]
-            Kp9 = (9 * K + 7) // 8 * 8
-            dz = ops.simple_head_gather_bwd(dhm32, hp, wp, f, Kp9)                       # [M, Kp9], column k*9+t
-            dw9 = scratch_zeros(Kp9, D)
-            _wgrad(dz, s['relu'], dw9)
-            dwf = zeros(K, D, 3, 3)
-            dwf.copy_(dw9[:9 * K].view(K, 3, 3, D).permute(0, 3, 1, 2))
-            g['keypoint_head.final_layer.weight'] = dwf
-            w9_pad = torch.zeros(Kp9, D, device=dev, dtype=BF16)
-            w9_pad[:9 * K] = s['w9']
-            dact = ops.relu_bwd(s['relu'], ops.gemm(dz, ops.transpose(w9_pad), EPI_BIAS))   # [M, D]
-        else:
-            # ---- final 1x1 conv: rows = pixels, columns = keypoints (zero padded to a multiple of 8)
-            Kp = (K + 7) // 8 * 8
-            dy = ops.nchw_to_rows(dhm.contiguous().float().view(n, K, P), Kp)                # [n*P, Kp]
-            act = s['act_last'].view(n * P, -1)
-            C = act.shape[1]
-            dwf = zeros(Kp, C)
-            _wgrad(dy, act, dwf)
-            dbf = zeros(Kp)
-            ops.colsum_accumulate(dy, dbf)
-            g['keypoint_head.final_layer.weight'] = dwf[:K].reshape(K, C, 1, 1)
-            g['keypoint_head.final_layer.bias'] = dbf[:K]
-            wf_pad = torch.zeros(Kp, C, device=dev, dtype=BF16)
-            wf_pad[:K] = s['wf']
-            dact = ops.gemm(dy, ops.transpose(wf_pad), EPI_BIAS)                             # [n*P, C]
-            # ---- [ConvTranspose2d -> BatchNorm2d(train) -> ReLU] x 2, last to first
-            for i in (1, 0):
-                hsi = s['head'][i]
-                bn, raw, xin, wp_ = hsi['bn'], hsi['raw'], hsi['x'], hsi['wp']
-                cout = raw.shape[-1]
-                dgam, dbet = zeros(cout), zeros(cout)
-                draw = ops.bn_relu_bwd(raw, dact.view(raw.shape), hsi['mean'], hsi['rstd'], bn.weight.detach(),
-                                       bn.bias.detach(), dgam, dbet, eval_mode=hsi['frozen_stats'])
-                g[f'keypoint_head.deconv_layers.{3 * i + 1}.weight'] = dgam
-                g[f'keypoint_head.deconv_layers.{3 * i + 1}.bias'] = dbet
-                a_t = ops.deconv_phase_dy(draw)                                             # [4, pixels, cout]
-                b_t = ops.deconv_gather_x(xin)                                               # [4, pixels, 4*cin]
-                dwp = scratch_zeros(4, cout, wp_.shape[2])
-                for ph in range(4):
-                    _wgrad(a_t[ph], b_t[ph], dwp[ph])
-                g[f'keypoint_head.deconv_layers.{3 * i}.weight'] = ops.deconv_unpack_wgrad(
-                    dwp, zeros(wp_.shape[2] // 4, cout, 4, 4))
-                del a_t, b_t
-                dact = ops.gemm(ops.deconv_gather_dy(draw), hsi['wd'], EPI_BIAS)             # [pixels_in, cin]
+        # ---- keypoint heads, each back to the gradient of the backbone features (bf16 [M, D]); a head whose output
+        # took no part in the loss gets no gradient (its parameters' .grad stay None, as with autograd)
+        dact = None
+        for (pfx, head_i), sv, dhm in zip(_heads_of(model), s['head_saved'], dhms):
+            if dhm is None:
+                continue
+            d_i = _head_backward(pfx, head_i, sv, dhm, s, g, zeros, scratch_zeros)
+            if dact is None:
+                dact = d_i
+            else:                        # several heads: summed in fp32, rounded once
+                dact = (dact.float() if dact.dtype == BF16 else dact).add_(d_i.float())
+        if dact.dtype != BF16:
+            dact = dact.to(BF16)
         # ---- last_norm, then the blocks in reverse
         exchange()
         dx = scratch_zeros(M, D)
@@ -405,6 +490,58 @@ class _NetworkFn(torch.autograd.Function):
                 return ops.cast_bf16_colsum(dx, dbias, scale, T), dbias
             return ops.cast_bf16(dx, scale, T), None
 
+        def moe_fc2_bwd(pfx, w, dyb, a, db2):
+            """Backward of MoEMlp's second half (vit_moe.py:97-115): the shared fc2 owns the first D - part columns of
+            the branch gradient dyb on every token, experts[d] the last `part` columns on the tokens of dataset d;
+            every expert gets a gradient (zero if its dataset is not in the batch), as the reference's dense masked
+            form does "to support ddp training". Returns (gradient of fc1's pre-activation, fc1's bias gradient)."""
+            part = w['experts'][0].w.shape[0]
+            Ds, H4 = D - part, w['fc2'].w.shape[1]
+            h, pre = a['h'], a['pre']
+            if pfx + 'fc2.weight' in trainable:
+                dw = zeros(Ds, H4)
+                _wgrad(dyb[:, :Ds], h, dw)
+                g[pfx + 'fc2.weight'] = dw
+            if pfx + 'fc2.bias' in trainable:
+                if db2 is None:
+                    db2 = zeros(D)
+                    ops.colsum_accumulate(dyb, db2)
+                g[pfx + 'fc2.bias'] = db2[:Ds]
+            spans, c0 = [], 0
+            for d, cnt in runs:
+                spans.append((d, c0 * T, (c0 + cnt) * T))
+                c0 += cnt
+            for e in range(E):
+                want_w, want_b = pfx + f'experts.{e}.weight' in trainable, pfx + f'experts.{e}.bias' in trainable
+                dwe = zeros(part, H4) if want_w else None
+                dbe = zeros(part) if want_b else None
+                for d, r0, r1 in spans:
+                    if d != e:
+                        continue
+                    if want_w:
+                        _wgrad(dyb[r0:r1, Ds:], h[r0:r1], dwe)
+                    if want_b:
+                        if len(spans) == 1 and db2 is not None:
+                            dbe.copy_(db2[Ds:])
+                        else:
+                            tmp = scratch_zeros(D)
+                            ops.colsum_accumulate(dyb[r0:r1], tmp)
+                            dbe.add_(tmp[Ds:])
+                if want_w:
+                    g[pfx + f'experts.{e}.weight'] = dwe
+                if want_b:
+                    g[pfx + f'experts.{e}.bias'] = dbe
+            # input gradient through the effective fc2 of each run's dataset (+ GELU', + fc1's bias gradient)
+            db1 = zeros(H4) if FUSE_MLP and pfx + 'fc1.bias' in trainable else None
+            dpre = torch.empty(M, H4, device=dev, dtype=BF16)
+            for d, r0, r1 in spans:
+                wct = w['cat'][d][1]
+                if FUSE_MLP:
+                    ops.gemm_gelu_bwd(dyb[r0:r1], wct, pre[r0:r1], db1, out=dpre[r0:r1])
+                else:
+                    dpre[r0:r1] = ops.gelu_bwd(pre[r0:r1], ops.gemm(dyb[r0:r1], wct, EPI_BIAS))
+            return dpre, db1
+
         L = len(bb.blocks)
         acts = s['acts']
         dyb, db2 = norm_bwd('backbone.last_norm', bb.last_norm, s['x_final'], dact, acts[L - 1]['s2'],
@@ -413,7 +550,9 @@ class _NetworkFn(torch.autograd.Function):
             a, w, blk = acts[l], s['blocks'][l], bb.blocks[l]
             pfx = f'backbone.blocks.{l}.'
             # x_out = x_mid + fc2(gelu(fc1(norm2(x_mid))))            (vit.py:139); dyb = gradient of that branch
-            if FUSE_MLP:
+            if E:
+                dpre, db1 = moe_fc2_bwd(pfx + 'mlp.', w, dyb, a, db2)
+            elif FUSE_MLP:
                 # fc2's input gradient with the GELU backward in its epilogue (+ fc1's bias gradient as column sums)
                 linear_bwd(pfx + 'mlp.fc2', w['fc2'], dyb, a['h'], want_dx=False, dbias=db2)
                 db1 = zeros(w['fc1'].w.shape[0]) if pfx + 'mlp.fc1.bias' in trainable else None
