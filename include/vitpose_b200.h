@@ -280,7 +280,7 @@ int vpb_layernorm_bwd(const float* x, const float* gamma, const void* dy, float*
                       float* dbeta, int M, int D, float eps, void* stream);
 /* Attention.forward (vit.py:99-115) that also returns lse fp32 [n, heads, T] = log2 sum_j exp2(s_ij * scale * log2 e),
  * and its backward: qkv [n,T,3*heads*hd], out [n,T,heads*hd] and lse saved by the forward pass, dout = dL/dout ->
- * dqkv [n,T,3*heads*hd]. Backward: T = 192, head_dim = 64 (ViTPose-B, the training configuration). */
+ * dqkv [n,T,3*heads*hd]. Backward: T = 192, head_dim 32 / 64 / 80 (ViTPose-S / -B, -L / -H). */
 int vpb_attention_lse(const void* qkv, void* out, float* lse, int n, int T, int heads, int head_dim, float scale,
                       void* stream);
 int vpb_attention_bwd(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, int n, int T,

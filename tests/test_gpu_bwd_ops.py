@@ -152,10 +152,11 @@ def test_relu_and_relu_bwd():
     assert torch.equal(ops.relu_bwd(y, dy), torch.where(y > 0, dy, torch.zeros_like(dy)))
 
 
-@pytest.mark.parametrize('n,heads', [(2, 2), (3, 12)])
-def test_attention_bwd(n, heads):
+@pytest.mark.parametrize('n,heads,hd', [(2, 2, 64), (3, 12, 64), (2, 3, 32), (3, 12, 32), (2, 2, 80), (2, 16, 80)])
+def test_attention_bwd(n, heads, hd):
+    """head_dim 32 / 64 / 80 = ViTPose-S / -B, -L / -H (vit.py:99-115 under autograd)"""
     from vitpose_b200 import ops
-    T, hd = 192, 64
+    T = 192
     D = heads * hd
     qkv = _rand((n, T, 3 * D), 11, 1.0)
     dout = _rand((n, T, D), 12, 1.0)

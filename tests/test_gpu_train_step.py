@@ -36,6 +36,8 @@ def _cos(a, b):
                                                      ('B-classic-17', 2, 12, 0.0, True), ('B-classic-17', 6, 3, 0.3, True),
                                                      ('B-classic-17', 6, 3, 0.3, False),
                                                      ('L-classic-17', 2, 2, 0.0, True),
+                                                     ('S-classic-17', 3, 2, 0.0, True),
+                                                     ('H-classic-17', 2, 2, 0.0, True),
                                                      ('B-simple-17', 3, 2, 0.0, True)])
 def test_forward_train_backward_vs_oracle(name, n, depth, drop, fused, monkeypatch):
     """drop > 0: stochastic depth with the SAME per-crop masks injected into both implementations. fused = the MLP /
@@ -49,6 +51,14 @@ def test_forward_train_backward_vs_oracle(name, n, depth, drop, fused, monkeypat
         cfg = configs.baseline_model_cfg('B-classic-17')
         cfg['backbone'].update(embed_dim=1024, num_heads=16)
         cfg['keypoint_head'].update(in_channels=1024)
+    elif name == 'S-classic-17':      # ViTPose-S: D = 384, head_dim 32
+        cfg = configs.baseline_model_cfg('B-classic-17')
+        cfg['backbone'].update(embed_dim=384, num_heads=12)
+        cfg['keypoint_head'].update(in_channels=384)
+    elif name == 'H-classic-17':      # ViTPose-H: D = 1280, head_dim 80 (logs/vitpose-h.log.json)
+        cfg = configs.baseline_model_cfg('B-classic-17')
+        cfg['backbone'].update(embed_dim=1280, num_heads=16)
+        cfg['keypoint_head'].update(in_channels=1280)
     elif name == 'B-simple-17':       # the simple decoder (ReLU -> bilinear x4 -> 3x3 conv; logs/vitpose-*-simple.log.json)
         cfg = configs.baseline_model_cfg('L-simple-17')
         cfg['backbone'].update(embed_dim=768, num_heads=12)

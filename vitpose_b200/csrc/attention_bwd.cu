@@ -1,9 +1,10 @@
 // Backward of the fused multi-head self-attention (Attention.forward, mmpose/models/backbones/vit.py:99-115) for the
-// training-step configuration (ViTPose-B: T = 192 tokens, head_dim 64).
+// training-step configurations (T = 192 tokens; head_dim 32 / 64 / 80 = ViTPose-S / -B, -L / -H).
 //   S = (Q K^T) * scale, P = softmax(S), O = P V            (forward, attention.cu)
 //   dV = P^T dO,  dP = dO V^T,  dS = P o (dP - delta),  delta_i = sum_d dO_id O_id,
 //   dQ = scale * dS K,  dK = scale * dS^T Q
-// One CTA per (crop, head). Q, K, V, dO of the head are TMA-loaded once as 128B-swizzled [192 x 64] tiles; the
+// One CTA per (crop, head). Q, K, V, dO of the head are TMA-loaded once as 128B-swizzled [192 x 64] tiles (plus a
+// 16-column SWIZZLE_32B tile each for head_dim 80; TMEM column numbers below are those of head_dim <= 64); the
 // query rows are processed in two 128-row tiles (the second is half empty). Per tile:
 //   tcgen05.mma S  = Q_t K^T       -> TMEM [0,192)   ; 256 threads ((query row, half of the keys) each) form
 //                                                       P = exp2(S * scale * log2e - lse) with the forward pass's
@@ -21,40 +22,108 @@
 namespace vpb {
 
 constexpr int AB_T = 192;
-constexpr int AB_HD = 64;
 constexpr int AB_THREADS = 288;                     // warp 0: TMA + MMA issue; warps 1..8: (row, column half) per thread
-constexpr int AB_TILE = AB_T * 128;                 // [192 rows][128 B]
+constexpr int AB_TILE = AB_T * 128;                 // SWIZZLE_128B box: [192 rows][128 B] = 64 columns
+constexpr int AB_BOXB = AB_T * 32;                  // SWIZZLE_32B box: [192 rows][32 B] = the 16-column remainder of head_dim 80
 constexpr int AB_CHUNK = 128 * 128;                 // [128 rows][64 keys] bf16
-constexpr int AB_SMEM = 4 * AB_TILE + 3 * AB_CHUNK + 4 * AB_CHUNK + 1024;   // Q K V dO | dS | P + one chunk of slack
+
+// head_dim 32 / 64: one 64-column box per operand (head_dim 32 uses its first 32 columns; the rest belongs to the next
+// head and never enters an MMA). head_dim 80 (ViTPose-H): 64 columns + a 16-column SWIZZLE_32B box, as in the forward
+// kernel (attention.cu); every MMA over the head dimension is then one N = 64 / K-step-4 piece plus one N = 16 / K = 16
+// piece. Shared memory: P | dS | Q K V dO (| their 16-column boxes) | slack. M = 128 reads of the second query / key tile
+// run past their 192-row tile into whatever follows (P -> dS, dS -> Q, dO -> slack): garbage rows land in TMEM lanes
+// that are never read.
+template <int HD>
+struct AttnBwdCfg {
+  static constexpr bool WIDE = HD > 64;
+  static constexpr int HDM = WIDE ? 64 : HD;                        // columns of the 128-byte box the MMAs use
+  static constexpr int SLACK = WIDE ? 2048 : 8192;                  // rows 192..255 of the last operand tile
+  static constexpr int SMEM = 6 * AB_CHUNK + 4 * AB_TILE + (WIDE ? 4 * AB_BOXB : 0) + SLACK + 1024;
+  // TMEM columns: S / dP [0,192). head_dim <= 64: dQ [192,256), dK [256,384), dV [384,512). head_dim 80: dK 2 x 80 and
+  // dV 2 x 80 fill the rest, so dQ takes the S columns once dP has been consumed and the next tile's S waits for it.
+  static constexpr int COL_DQ = WIDE ? 0 : 192;
+  static constexpr int COL_DK = WIDE ? 192 : 256;
+  static constexpr int COL_DV = WIDE ? 192 + 2 * HD : 384;
+  static constexpr int QC = HD / 2;                                 // dQ columns per thread
+  static constexpr int Q_PIECES = QC * 2 / 16;                      // 16-byte pieces of a thread's dQ row
+  static constexpr int Q_PITCH = (Q_PIECES | 1) * 16;               // odd number of 16-byte units: conflict-free
+  static constexpr int K_PIECES = HD * 2 / 16;                      // 16-byte pieces of a dK / dV row
+  static constexpr int K_PITCH = HD * 2 + 16;
+  static_assert(HD == 32 || HD == 64 || HD == 80, "attention backward handles head_dim 32 / 64 / 80");
+  static_assert(COL_DV + 2 * HD <= 512 && 8 * 32 * Q_PITCH <= 3 * AB_CHUNK && 8 * 32 * K_PITCH <= 4 * AB_TILE, "budget");
+};
 
 struct AttnBwdParams {
   int n, heads;
   float scale, scale_log2e;
-  const __nv_bfloat16* dO;    // [n, T, heads*64]
-  const __nv_bfloat16* O;     // [n, T, heads*64] forward output
+  const __nv_bfloat16* dO;    // [n, T, heads*hd]
+  const __nv_bfloat16* O;     // [n, T, heads*hd] forward output
   const float* lse;           // [n, heads, T] log2-sum-exp of the scaled scores, written by the forward kernel
-  __nv_bfloat16* dqkv;        // [n, T, 3*heads*64]
-  float* dbias;               // optional [3*heads*64]: += column sums of dqkv over all tokens (attn.qkv's bias gradient)
+  __nv_bfloat16* dqkv;        // [n, T, 3*heads*hd]
+  float* dbias;               // optional [3*heads*hd]: += column sums of dqkv over all tokens (attn.qkv's bias gradient)
 };
 
+// fp32 columns [0, N) of this thread's TMEM lane, N a multiple of 8
+template <int N>
+__device__ __forceinline__ void tmem_ld_row(uint32_t taddr, float (&out)[N]) {
+  static_assert(N % 8 == 0, "pieces of 8 columns");
+#pragma unroll
+  for (int c = 0; c + 16 <= N; c += 16) {
+    uint32_t v[16];
+    tmem_ld_32x32b_x16(taddr + c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) out[c + j] = __uint_as_float(v[j]);
+  }
+  if constexpr (N % 16 != 0) {
+    uint32_t v[8];
+    tmem_ld_32x32b_x8(taddr + (N - 8), v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[N - 8 + j] = __uint_as_float(v[j]);
+  }
+}
+
+// dst[j] += sum over the warp's live rows of x[j], j < N (lane = row)
+template <int N>
+__device__ __forceinline__ void warp_colsum_atomic(const float (&x)[N], bool live, int lane, float* dst) {
+#pragma unroll
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float cs[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) cs[j] = (live && c0 + j < N) ? x[c0 + j < N ? c0 + j : 0] : 0.f;
+    const float sum = warp_colsum32(cs, lane);
+    if (c0 + lane < N) atomicAdd(dst + c0 + lane, sum);
+  }
+}
+
+template <int HD>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                     const __grid_constant__ CUtensorMap tm_qkvb, const __grid_constant__ CUtensorMap tm_dob,
                      const AttnBwdParams p) {
+  using C = AttnBwdCfg<HD>;
+  constexpr bool WIDE = C::WIDE;
+  constexpr int HDM = C::HDM;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_q = smem;
+  uint8_t* s_p = smem;                              // 3 chunks of [128 q][64 keys]
+  uint8_t* s_ds = s_p + 3 * AB_CHUNK;               // 3 chunks
+  uint8_t* s_q = s_ds + 3 * AB_CHUNK;
   uint8_t* s_k = s_q + AB_TILE;
   uint8_t* s_v = s_k + AB_TILE;
   uint8_t* s_do = s_v + AB_TILE;
-  uint8_t* s_ds = s_do + AB_TILE;                   // 3 chunks of [128 q][64 keys]
-  uint8_t* s_p = s_ds + 3 * AB_CHUNK;               // 3 chunks (+ 1 chunk of slack read by the M=128 key tile 1)
-  __shared__ uint64_t bar_load, bar_s, bar_sdone, bar_dp, bar_ds, bar_mma;
+  uint8_t* s_qb = s_do + AB_TILE;                   // head_dim 80: columns [64, 80) of Q, K, V, dO
+  uint8_t* s_kb = s_qb + AB_BOXB;
+  uint8_t* s_vb = s_kb + AB_BOXB;
+  uint8_t* s_dob = s_vb + AB_BOXB;
+  __shared__ uint64_t bar_load, bar_s, bar_sdone, bar_dp, bar_ds, bar_mma, bar_dq;
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.x % p.heads;
   const int crop = blockIdx.x / p.heads;
-  const int ld_o = p.heads * AB_HD, ld_qkv = 3 * ld_o;
+  const int ld_o = p.heads * HD, ld_qkv = 3 * ld_o;
 
   if (threadIdx.x == 0) {
     mbar_init(&bar_load, 1);
@@ -63,70 +132,97 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     mbar_init(&bar_dp, 1);
     mbar_init(&bar_ds, 256);
     mbar_init(&bar_mma, 1);
+    mbar_init(&bar_dq, 256);
     fence_mbar_init();
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
+    if constexpr (WIDE) {
+      tma_prefetch_desc(&tm_qkvb);
+      tma_prefetch_desc(&tm_dob);
+    }
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_s = tmem_slot;                // S / dP
-  const uint32_t tmem_dq = tmem_s + 192;
-  const uint32_t tmem_dk = tmem_s + 256;            // two key tiles x 64 columns
-  const uint32_t tmem_dv = tmem_s + 384;
+  const uint32_t tmem_dq = tmem_s + C::COL_DQ;
+  const uint32_t tmem_dk = tmem_s + C::COL_DK;      // two key tiles x HD columns
+  const uint32_t tmem_dv = tmem_s + C::COL_DV;
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(&bar_load, 4 * AB_TILE);
-      tma_load_3d(s_q, &tm_qkv, &bar_load, head * AB_HD, 0, crop);
-      tma_load_3d(s_k, &tm_qkv, &bar_load, ld_o + head * AB_HD, 0, crop);
-      tma_load_3d(s_v, &tm_qkv, &bar_load, 2 * ld_o + head * AB_HD, 0, crop);
-      tma_load_3d(s_do, &tm_do, &bar_load, head * AB_HD, 0, crop);
+      mbar_arrive_expect_tx(&bar_load, 4 * AB_TILE + (WIDE ? 4 * AB_BOXB : 0));
+      tma_load_3d(s_q, &tm_qkv, &bar_load, head * HD, 0, crop);
+      tma_load_3d(s_k, &tm_qkv, &bar_load, ld_o + head * HD, 0, crop);
+      tma_load_3d(s_v, &tm_qkv, &bar_load, 2 * ld_o + head * HD, 0, crop);
+      tma_load_3d(s_do, &tm_do, &bar_load, head * HD, 0, crop);
+      if constexpr (WIDE) {
+        tma_load_3d(s_qb, &tm_qkvb, &bar_load, head * HD + 64, 0, crop);
+        tma_load_3d(s_kb, &tm_qkvb, &bar_load, ld_o + head * HD + 64, 0, crop);
+        tma_load_3d(s_vb, &tm_qkvb, &bar_load, 2 * ld_o + head * HD + 64, 0, crop);
+        tma_load_3d(s_dob, &tm_dob, &bar_load, head * HD + 64, 0, crop);
+      }
       mbar_wait(&bar_load, 0);
       tc_fence_after();
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, AB_T);            // K-major A and B
-      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, AB_HD, 0, 1);    // B (K) MN-major
-      constexpr uint32_t idesc_t = umma_idesc_bf16(128, AB_HD, 1, 1);     // A (P^T / dS^T) and B MN-major
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, HDM, 0, 1);      // B (K) MN-major
+      constexpr uint32_t idesc_dq16 = umma_idesc_bf16(128, 16, 0, 1);
+      constexpr uint32_t idesc_t = umma_idesc_bf16(128, HDM, 1, 1);       // A (P^T / dS^T) and B MN-major
+      constexpr uint32_t idesc_t16 = umma_idesc_bf16(128, 16, 1, 1);
       for (int t = 0; t < 2; ++t) {
         const uint32_t q_t = smem_u32(s_q) + t * AB_CHUNK, do_t = smem_u32(s_do) + t * AB_CHUNK;
+        const uint32_t qb_t = smem_u32(s_qb) + t * 128 * 32, dob_t = smem_u32(s_dob) + t * 128 * 32;
+        if constexpr (WIDE) {
+          if (t == 1) {                 // dQ of tile 0 sits in the S columns until every thread has loaded it
+            mbar_wait(&bar_dq, 0);
+            tc_fence_after();
+          }
+        }
         // S = Q_t K^T
 #pragma unroll
-        for (int ks = 0; ks < AB_HD / 16; ++ks)
+        for (int ks = 0; ks < HDM / 16; ++ks)
           umma_bf16_ss(tmem_s, umma_desc_k_sw128(q_t + ks * 32), umma_desc_k_sw128(smem_u32(s_k) + ks * 32), idesc_s,
                        ks != 0);
+        if constexpr (WIDE) umma_bf16_ss(tmem_s, umma_desc_k_sw32(qb_t), umma_desc_k_sw32(smem_u32(s_kb)), idesc_s, 1u);
         umma_commit(&bar_s);
         // dP = dO_t V^T into the same columns once every thread has consumed S
         mbar_wait(&bar_sdone, t);
         tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < AB_HD / 16; ++ks)
+        for (int ks = 0; ks < HDM / 16; ++ks)
           umma_bf16_ss(tmem_s, umma_desc_k_sw128(do_t + ks * 32), umma_desc_k_sw128(smem_u32(s_v) + ks * 32), idesc_s,
                        ks != 0);
+        if constexpr (WIDE) umma_bf16_ss(tmem_s, umma_desc_k_sw32(dob_t), umma_desc_k_sw32(smem_u32(s_vb)), idesc_s, 1u);
         umma_commit(&bar_dp);
         mbar_wait(&bar_ds, t);
         tc_fence_after();
         // dQ_t = dS K (contraction over the 192 keys)
-        for (int ks = 0; ks < AB_T / 16; ++ks)
-          umma_bf16_ss(tmem_dq, umma_desc_k_sw128(smem_u32(s_ds) + (ks / 4) * AB_CHUNK + (ks % 4) * 32),
-                       umma_desc_mn_sw128(smem_u32(s_k) + ks * 2048, AB_TILE), idesc_dq, ks != 0);
+        for (int ks = 0; ks < AB_T / 16; ++ks) {
+          const uint64_t a = umma_desc_k_sw128(smem_u32(s_ds) + (ks / 4) * AB_CHUNK + (ks % 4) * 32);
+          umma_bf16_ss(tmem_dq, a, umma_desc_mn_sw128(smem_u32(s_k) + ks * 2048, AB_TILE), idesc_dq, ks != 0);
+          if constexpr (WIDE)
+            umma_bf16_ss(tmem_dq + 64, a, umma_desc_mn_sw32(smem_u32(s_kb) + ks * 512), idesc_dq16, ks != 0);
+        }
         // dK += dS^T Q_t, dV += P^T dO_t (contraction over the valid queries of this tile)
         const int nks = t == 0 ? 8 : (AB_T - 128) / 16;
         for (int m = 0; m < 2; ++m) {
           for (int ks = 0; ks < nks; ++ks) {
             const uint32_t acc = (t | ks) != 0 ? 1u : 0u;
-            umma_bf16_ss(tmem_dk + m * AB_HD,
-                         umma_desc_mn_sw128(smem_u32(s_ds) + 2 * m * AB_CHUNK + ks * 2048, AB_CHUNK),
-                         umma_desc_mn_sw128(q_t + ks * 2048, AB_TILE), idesc_t, acc);
-            umma_bf16_ss(tmem_dv + m * AB_HD,
-                         umma_desc_mn_sw128(smem_u32(s_p) + 2 * m * AB_CHUNK + ks * 2048, AB_CHUNK),
-                         umma_desc_mn_sw128(do_t + ks * 2048, AB_TILE), idesc_t, acc);
+            const uint64_t a_ds = umma_desc_mn_sw128(smem_u32(s_ds) + 2 * m * AB_CHUNK + ks * 2048, AB_CHUNK);
+            const uint64_t a_p = umma_desc_mn_sw128(smem_u32(s_p) + 2 * m * AB_CHUNK + ks * 2048, AB_CHUNK);
+            umma_bf16_ss(tmem_dk + m * HD, a_ds, umma_desc_mn_sw128(q_t + ks * 2048, AB_TILE), idesc_t, acc);
+            umma_bf16_ss(tmem_dv + m * HD, a_p, umma_desc_mn_sw128(do_t + ks * 2048, AB_TILE), idesc_t, acc);
+            if constexpr (WIDE) {
+              umma_bf16_ss(tmem_dk + m * HD + 64, a_ds, umma_desc_mn_sw32(qb_t + ks * 512), idesc_t16, acc);
+              umma_bf16_ss(tmem_dv + m * HD + 64, a_p, umma_desc_mn_sw32(dob_t + ks * 512), idesc_t16, acc);
+            }
           }
         }
         umma_commit(&bar_mma);
-        // The next tile's S is issued right away: its TMEM columns are free since bar_ds (every thread has read dP), the
-        // tensor pipe runs it behind the MMAs above, and the threads rewrite the P / dS tiles only after bar_mma — so
-        // S of tile 1 is ready while the threads still drain dQ of tile 0.
+        // head_dim <= 64: the next tile's S is issued right away: its TMEM columns are free since bar_ds (every thread
+        // has read dP), the tensor pipe runs it behind the MMAs above, and the threads rewrite the P / dS tiles only
+        // after bar_mma — so S of tile 1 is ready while the threads still drain dQ of tile 0.
       }
     }
   } else {
@@ -136,19 +232,19 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     constexpr int KH = AB_T / 2;                    // 96 keys per thread
     // delta = <dO_row, O_row> and the forward log-sum-exp of this thread's row in BOTH query tiles, requested up front:
-    // the global-memory latency (16 x 16-byte loads per tile; 20 % of the kernel's stall samples when they sat at the
-    // top of each tile) hides behind the TMA loads of Q / K / V / dO. Both halves of a row compute it: no exchange.
+    // the global-memory latency (16-byte loads; 20 % of the kernel's stall samples when they sat at the top of each
+    // tile) hides behind the TMA loads of Q / K / V / dO. Both halves of a row compute it: no exchange.
     float delta_t[2] = {0.f, 0.f}, lse_t[2] = {0.f, 0.f};
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       const int token = t * 128 + r;
       if (token < AB_T) {
-        const size_t off = (static_cast<size_t>(crop) * AB_T + token) * ld_o + head * AB_HD;
+        const size_t off = (static_cast<size_t>(crop) * AB_T + token) * ld_o + head * HD;
         const uint4* a = reinterpret_cast<const uint4*>(p.dO + off);
         const uint4* b = reinterpret_cast<const uint4*>(p.O + off);
         float d = 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < HD / 8; ++u) {
           const uint4 x = __ldg(a + u), y = __ldg(b + u);
           const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
@@ -221,79 +317,67 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       mbar_arrive(&bar_ds);
       mbar_wait(&bar_mma, t);
       tc_fence_after();
-      // dQ rows of this tile: 32 of the 64 columns per thread. A row-per-thread global store would touch 32 lines
-      // with 16 bytes each per instruction, so the warp stages its 32 x 64-byte block in shared memory (the Q rows
-      // of tile 0, dead once bar_mma(0) has completed; 16-byte pieces XOR-swizzled: conflict-free both ways) and
-      // writes it back with four lanes per row.
+      // dQ rows of this tile: half of the head's columns per thread. A row-per-thread global store would touch 32 lines
+      // with 16 bytes each per instruction, so the warp stages its 32-row block in shared memory (the dS tile: dead
+      // from bar_mma(t) until every thread has arrived at bar_sdone(t + 1), which this one does only after the copy;
+      // row pitch an odd number of 16-byte units: conflict-free both ways) and writes whole row pieces back.
       {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_dq + lane_off + half * 32, v);
-        tmem_ld_wait();
-        if (p.dbias != nullptr) {       // bias gradient of attn.qkv: column sums over the live rows of this warp
-          float cs[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) cs[j] = valid ? __uint_as_float(v[j]) : 0.f;
-          const float sum = warp_colsum32(cs, lane);
-          atomicAdd(p.dbias + head * AB_HD + half * 32 + lane, sum);
+        float v[C::QC];
+        tmem_ld_row<C::QC>(tmem_dq + lane_off + half * C::QC, v);
+        if constexpr (WIDE) {           // the S columns are free for the next tile's scores
+          tc_fence_before();
+          mbar_arrive(&bar_dq);
         }
-        uint8_t* stage = s_q + (warp - 1) * 2048;
+        if (p.dbias != nullptr)         // bias gradient of attn.qkv: column sums over the live rows of this warp
+          warp_colsum_atomic<C::QC>(v, valid, lane, p.dbias + head * HD + half * C::QC);
+        uint8_t* stage = s_ds + (warp - 1) * (32 * C::Q_PITCH);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          *reinterpret_cast<uint4*>(stage + lane * 64 + ((u ^ ((lane >> 1) & 3)) * 16)) =
-              make_uint4(pack_bf16x2(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
-                         pack_bf16x2(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
-                         pack_bf16x2(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
-                         pack_bf16x2(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
+        for (int u = 0; u < C::Q_PIECES; ++u)
+          *reinterpret_cast<uint4*>(stage + lane * C::Q_PITCH + u * 16) =
+              make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                         pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
         __syncwarp();
         __nv_bfloat16* obase = p.dqkv + (static_cast<size_t>(crop) * AB_T + t * 128 + quad * 32) * ld_qkv +
-                               head * AB_HD + half * 32;
+                               head * HD + half * C::QC;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int row = 8 * j + (lane >> 2), ch = lane & 3;
+        for (int j = 0; j < C::Q_PIECES; ++j) {
+          const int idx = j * 32 + lane, row = idx / C::Q_PIECES, ch = idx % C::Q_PIECES;
           if (t * 128 + quad * 32 + row < AB_T)
             *reinterpret_cast<uint4*>(obase + static_cast<size_t>(row) * ld_qkv + ch * 8) =
-                *reinterpret_cast<const uint4*>(stage + row * 64 + ((ch ^ ((row >> 1) & 3)) * 16));
+                *reinterpret_cast<const uint4*>(stage + row * C::Q_PITCH + ch * 16);
         }
         __syncwarp();
       }
       tc_fence_before();
     }
     // dK / dV rows (keys): key tile m, lane r <-> key m*128 + r; half 0 stores dK, half 1 stores dV. Every operand tile
-    // is dead by now (all MMAs have completed): the warp stages its 32 x 128-byte block in the K/V/dO area (row pitch
-    // 144 bytes) and stores whole 128-byte lines, eight lanes per row.
+    // is dead by now (all MMAs have completed): the warp stages its 32-row block in the Q/K/V/dO area and stores whole
+    // rows, HD / 8 lanes per row.
     for (int m = 0; m < 2; ++m) {
-      const uint32_t base = (half == 0 ? tmem_dk : tmem_dv) + m * AB_HD + lane_off;
-      uint8_t* stage = s_k + (warp - 1) * (32 * 144);
+      const uint32_t base = (half == 0 ? tmem_dk : tmem_dv) + m * HD + lane_off;
+      uint8_t* stage = s_q + (warp - 1) * (32 * C::K_PITCH);
+      const bool key_ok = m * 128 + quad * 32 + lane < AB_T;
 #pragma unroll
-      for (int c = 0; c < AB_HD; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(base + c, v);
-        tmem_ld_wait();
-        if (p.dbias != nullptr) {
-          const bool key_ok = m * 128 + quad * 32 + lane < AB_T;
-          float cs[32];
+      for (int c = 0; c < HD; c += 16) {
+        float v[16];
+        tmem_ld_row<16>(base + c, v);
+        if (p.dbias != nullptr)
+          warp_colsum_atomic<16>(v, key_ok, lane, p.dbias + (1 + half) * ld_o + head * HD + c);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) cs[j] = key_ok ? __uint_as_float(v[j]) : 0.f;
-          const float sum = warp_colsum32(cs, lane);
-          atomicAdd(p.dbias + (1 + half) * ld_o + head * AB_HD + c + lane, sum);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          *reinterpret_cast<uint4*>(stage + lane * 144 + c * 2 + u * 16) =
-              make_uint4(pack_bf16x2(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
-                         pack_bf16x2(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
-                         pack_bf16x2(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
-                         pack_bf16x2(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
+        for (int u = 0; u < 2; ++u)
+          *reinterpret_cast<uint4*>(stage + lane * C::K_PITCH + c * 2 + u * 16) =
+              make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                         pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
       }
       __syncwarp();
       __nv_bfloat16* obase = p.dqkv + (static_cast<size_t>(crop) * AB_T + m * 128 + quad * 32) * ld_qkv +
-                             (1 + half) * ld_o + head * AB_HD;
+                             (1 + half) * ld_o + head * HD;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int row = 4 * j + (lane >> 3), ch = lane & 7;
+      for (int j = 0; j < C::K_PIECES; ++j) {
+        const int idx = j * 32 + lane, row = idx / C::K_PIECES, ch = idx % C::K_PIECES;
         if (m * 128 + quad * 32 + row < AB_T)
           *reinterpret_cast<uint4*>(obase + static_cast<size_t>(row) * ld_qkv + ch * 8) =
-              *reinterpret_cast<const uint4*>(stage + row * 144 + ch * 16);
+              *reinterpret_cast<const uint4*>(stage + row * C::K_PITCH + ch * 16);
       }
       __syncwarp();
     }
@@ -303,13 +387,27 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   if (warp == 0) tmem_dealloc(tmem_s, 512);
 }
 
+template <int HD>
+static int launch_attention_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tqb,
+                                const CUtensorMap& tdob, const AttnBwdParams& p, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    VPB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        AttnBwdCfg<HD>::SMEM));
+    configured = true;
+  }
+  attention_bwd_kernel<HD><<<p.n * p.heads, AB_THREADS, AttnBwdCfg<HD>::SMEM, stream>>>(tq, tdo, tqb, tdob, p);
+  VPB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int attention_bwd(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, int n, int T,
                   int heads, int hd, float scale, cudaStream_t stream, float* dbias) {
   VPB_REQUIRE(n > 0 && heads > 0 && lse != nullptr, "attention_bwd: empty problem / missing log-sum-exp");
-  VPB_REQUIRE(T == AB_T && hd == AB_HD, "attention_bwd: built for T=%d, head_dim=%d (got T=%d, head_dim=%d)", AB_T,
-              AB_HD, T, hd);
+  VPB_REQUIRE(T == AB_T && (hd == 32 || hd == 64 || hd == 80),
+              "attention_bwd: built for T=%d, head_dim 32 / 64 / 80 (got T=%d, head_dim=%d)", AB_T, T, hd);
   const int ld_o = heads * hd, ld = 3 * ld_o;
-  CUtensorMap tq, tdo;
+  CUtensorMap tq, tdo, tqb, tdob;
   uint64_t dims[3] = {(uint64_t)ld, (uint64_t)T, (uint64_t)n};
   uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)T * ld * 2};
   uint32_t box[3] = {64, (uint32_t)T, 1};
@@ -317,6 +415,13 @@ int attention_bwd(const void* qkv, const void* out, const float* lse, const void
   uint64_t dims_o[3] = {(uint64_t)ld_o, (uint64_t)T, (uint64_t)n};
   uint64_t strides_o[2] = {(uint64_t)ld_o * 2, (uint64_t)T * ld_o * 2};
   if (make_tma_desc(&tdo, TMA_BF16, dout, 3, dims_o, strides_o, box, TMA_SWIZZLE_128B)) return -1;
+  tqb = tq;
+  tdob = tdo;
+  if (hd > 64) {      // the 16-column remainder of each operand
+    uint32_t box_b[3] = {16, (uint32_t)T, 1};
+    if (make_tma_desc(&tqb, TMA_BF16, qkv, 3, dims, strides, box_b, TMA_SWIZZLE_32B)) return -1;
+    if (make_tma_desc(&tdob, TMA_BF16, dout, 3, dims_o, strides_o, box_b, TMA_SWIZZLE_32B)) return -1;
+  }
   AttnBwdParams p;
   p.n = n; p.heads = heads; p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
   p.dO = reinterpret_cast<const __nv_bfloat16*>(dout);
@@ -324,14 +429,9 @@ int attention_bwd(const void* qkv, const void* out, const float* lse, const void
   p.lse = lse;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   p.dbias = dbias;
-  static bool configured = false;
-  if (!configured) {
-    VPB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
-    configured = true;
-  }
-  attention_bwd_kernel<<<n * heads, AB_THREADS, AB_SMEM, stream>>>(tq, tdo, p);
-  VPB_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  if (hd == 32) return launch_attention_bwd<32>(tq, tdo, tqb, tdob, p, stream);
+  if (hd == 64) return launch_attention_bwd<64>(tq, tdo, tqb, tdob, p, stream);
+  return launch_attention_bwd<80>(tq, tdo, tqb, tdob, p, stream);
 }
 
 }  // namespace vpb
