@@ -15,6 +15,9 @@
 //                                                 (transposed) straight from where the threads wrote them
 // Nothing of size T x T ever touches HBM. Every MMA is M = 128: rows past the sequence end compute garbage from
 // whatever follows the tile in shared memory, land in TMEM lanes that are never read, and never enter a contraction.
+#include <cstdio>
+#include <type_traits>
+#include <cstdlib>
 #include "host_util.h"
 #include "ops.h"
 #include "ptx.cuh"
@@ -61,6 +64,8 @@ struct AttnBwdParams {
   const float* lse;           // [n, heads, T] log2-sum-exp of the scaled scores, written by the forward kernel
   __nv_bfloat16* dqkv;        // [n, T, 3*heads*hd]
   float* dbias;               // optional [3*heads*hd]: += column sums of dqkv over all tokens (attn.qkv's bias gradient)
+  long long* dbg;             // VPB_ATTBWD_DEBUG=<cta>: clock64 stamps of that CTA (thread 0: [0,16), thread 32: [16,32))
+  int dbg_cta;
 };
 
 // fp32 columns [0, N) of this thread's TMEM lane, N a multiple of 8
@@ -97,10 +102,17 @@ __device__ __forceinline__ void warp_colsum_atomic(const float (&x)[N], bool liv
   }
 }
 
+#define AB_STAMP(slot)                                                                  \
+  do {                                                                                  \
+    if (p.dbg != nullptr && blockIdx.x == p.dbg_cta && (threadIdx.x == 0 || threadIdx.x == 32)) \
+      p.dbg[(threadIdx.x == 0 ? 0 : 16) + (slot)] = clock64();                          \
+  } while (0)
+
 template <int HD>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                     const __grid_constant__ CUtensorMap tm_qkvb, const __grid_constant__ CUtensorMap tm_dob,
+                     const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_qkvb,
+                     const __grid_constant__ CUtensorMap tm_dob, const __grid_constant__ CUtensorMap tm_ob,
                      const AttnBwdParams p) {
   using C = AttnBwdCfg<HD>;
   constexpr bool WIDE = C::WIDE;
@@ -124,6 +136,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   const int head = blockIdx.x % p.heads;
   const int crop = blockIdx.x / p.heads;
   const int ld_o = p.heads * HD, ld_qkv = 3 * ld_o;
+  AB_STAMP(0);
 
   if (threadIdx.x == 0) {
     mbar_init(&bar_load, 1);
@@ -136,9 +149,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     fence_mbar_init();
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_o);
     if constexpr (WIDE) {
       tma_prefetch_desc(&tm_qkvb);
       tma_prefetch_desc(&tm_dob);
+      tma_prefetch_desc(&tm_ob);
     }
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -152,12 +167,15 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(&bar_load, 4 * AB_TILE + (WIDE ? 4 * AB_BOXB : 0));
+      // the forward output O goes where P will be written: it is only needed for delta = <dO_row, O_row> at the start
+      mbar_arrive_expect_tx(&bar_load, 5 * AB_TILE + (WIDE ? 5 * AB_BOXB : 0));
       tma_load_3d(s_q, &tm_qkv, &bar_load, head * HD, 0, crop);
       tma_load_3d(s_k, &tm_qkv, &bar_load, ld_o + head * HD, 0, crop);
       tma_load_3d(s_v, &tm_qkv, &bar_load, 2 * ld_o + head * HD, 0, crop);
       tma_load_3d(s_do, &tm_do, &bar_load, head * HD, 0, crop);
+      tma_load_3d(s_p, &tm_o, &bar_load, head * HD, 0, crop);
       if constexpr (WIDE) {
+        tma_load_3d(s_p + AB_TILE, &tm_ob, &bar_load, head * HD + 64, 0, crop);
         tma_load_3d(s_qb, &tm_qkvb, &bar_load, head * HD + 64, 0, crop);
         tma_load_3d(s_kb, &tm_qkvb, &bar_load, ld_o + head * HD + 64, 0, crop);
         tma_load_3d(s_vb, &tm_qkvb, &bar_load, 2 * ld_o + head * HD + 64, 0, crop);
@@ -165,19 +183,19 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       }
       mbar_wait(&bar_load, 0);
       tc_fence_after();
+      AB_STAMP(1);
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, AB_T);            // K-major A and B
       constexpr uint32_t idesc_dq = umma_idesc_bf16(128, HDM, 0, 1);      // B (K) MN-major
       constexpr uint32_t idesc_dq16 = umma_idesc_bf16(128, 16, 0, 1);
       constexpr uint32_t idesc_t = umma_idesc_bf16(128, HDM, 1, 1);       // A (P^T / dS^T) and B MN-major
       constexpr uint32_t idesc_t16 = umma_idesc_bf16(128, 16, 1, 1);
-      for (int t = 0; t < 2; ++t) {
+      auto issue_tile = [&](auto tc) {
+        constexpr int t = decltype(tc)::value;
         const uint32_t q_t = smem_u32(s_q) + t * AB_CHUNK, do_t = smem_u32(s_do) + t * AB_CHUNK;
         const uint32_t qb_t = smem_u32(s_qb) + t * 128 * 32, dob_t = smem_u32(s_dob) + t * 128 * 32;
-        if constexpr (WIDE) {
-          if (t == 1) {                 // dQ of tile 0 sits in the S columns until every thread has loaded it
-            mbar_wait(&bar_dq, 0);
-            tc_fence_after();
-          }
+        if constexpr (WIDE && t == 1) {   // dQ of tile 0 sits in the S columns until every thread has loaded it
+          mbar_wait(&bar_dq, 0);
+          tc_fence_after();
         }
         // S = Q_t K^T
 #pragma unroll
@@ -189,41 +207,57 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         // dP = dO_t V^T into the same columns once every thread has consumed S
         mbar_wait(&bar_sdone, t);
         tc_fence_after();
+        AB_STAMP(2 + 4 * t);
 #pragma unroll
         for (int ks = 0; ks < HDM / 16; ++ks)
           umma_bf16_ss(tmem_s, umma_desc_k_sw128(do_t + ks * 32), umma_desc_k_sw128(smem_u32(s_v) + ks * 32), idesc_s,
                        ks != 0);
         if constexpr (WIDE) umma_bf16_ss(tmem_s, umma_desc_k_sw32(dob_t), umma_desc_k_sw32(smem_u32(s_vb)), idesc_s, 1u);
         umma_commit(&bar_dp);
+        // dV += P^T dO_t needs only P: it runs on the tensor pipe while the threads form dS
+        constexpr int nks = t == 0 ? 8 : (AB_T - 128) / 16;     // the valid queries of this tile
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+#pragma unroll
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint32_t acc = (t | ks) != 0 ? 1u : 0u;
+            const uint64_t a_p = umma_desc_mn_sw128(smem_u32(s_p) + 2 * m * AB_CHUNK + ks * 2048, AB_CHUNK);
+            umma_bf16_ss(tmem_dv + m * HD, a_p, umma_desc_mn_sw128(do_t + ks * 2048, AB_TILE), idesc_t, acc);
+            if constexpr (WIDE)
+              umma_bf16_ss(tmem_dv + m * HD + 64, a_p, umma_desc_mn_sw32(dob_t + ks * 512), idesc_t16, acc);
+          }
+        }
         mbar_wait(&bar_ds, t);
         tc_fence_after();
+        AB_STAMP(3 + 4 * t);
         // dQ_t = dS K (contraction over the 192 keys)
+#pragma unroll
         for (int ks = 0; ks < AB_T / 16; ++ks) {
           const uint64_t a = umma_desc_k_sw128(smem_u32(s_ds) + (ks / 4) * AB_CHUNK + (ks % 4) * 32);
           umma_bf16_ss(tmem_dq, a, umma_desc_mn_sw128(smem_u32(s_k) + ks * 2048, AB_TILE), idesc_dq, ks != 0);
           if constexpr (WIDE)
             umma_bf16_ss(tmem_dq + 64, a, umma_desc_mn_sw32(smem_u32(s_kb) + ks * 512), idesc_dq16, ks != 0);
         }
-        // dK += dS^T Q_t, dV += P^T dO_t (contraction over the valid queries of this tile)
-        const int nks = t == 0 ? 8 : (AB_T - 128) / 16;
+        // dK += dS^T Q_t (contraction over the valid queries of this tile)
+#pragma unroll
         for (int m = 0; m < 2; ++m) {
+#pragma unroll
           for (int ks = 0; ks < nks; ++ks) {
             const uint32_t acc = (t | ks) != 0 ? 1u : 0u;
             const uint64_t a_ds = umma_desc_mn_sw128(smem_u32(s_ds) + 2 * m * AB_CHUNK + ks * 2048, AB_CHUNK);
-            const uint64_t a_p = umma_desc_mn_sw128(smem_u32(s_p) + 2 * m * AB_CHUNK + ks * 2048, AB_CHUNK);
             umma_bf16_ss(tmem_dk + m * HD, a_ds, umma_desc_mn_sw128(q_t + ks * 2048, AB_TILE), idesc_t, acc);
-            umma_bf16_ss(tmem_dv + m * HD, a_p, umma_desc_mn_sw128(do_t + ks * 2048, AB_TILE), idesc_t, acc);
-            if constexpr (WIDE) {
+            if constexpr (WIDE)
               umma_bf16_ss(tmem_dk + m * HD + 64, a_ds, umma_desc_mn_sw32(qb_t + ks * 512), idesc_t16, acc);
-              umma_bf16_ss(tmem_dv + m * HD + 64, a_p, umma_desc_mn_sw32(dob_t + ks * 512), idesc_t16, acc);
-            }
           }
         }
         umma_commit(&bar_mma);
+        AB_STAMP(4 + 4 * t);
         // head_dim <= 64: the next tile's S is issued right away: its TMEM columns are free since bar_ds (every thread
         // has read dP), the tensor pipe runs it behind the MMAs above, and the threads rewrite the P / dS tiles only
         // after bar_mma — so S of tile 1 is ready while the threads still drain dQ of tile 0.
-      }
+      };
+      issue_tile(std::integral_constant<int, 0>{});
+      issue_tile(std::integral_constant<int, 1>{});
     }
   } else {
     const int quad = warp & 3;
@@ -231,21 +265,23 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     const int r = quad * 32 + lane;                 // row inside a tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     constexpr int KH = AB_T / 2;                    // 96 keys per thread
-    // delta = <dO_row, O_row> and the forward log-sum-exp of this thread's row in BOTH query tiles, requested up front:
-    // the global-memory latency (16-byte loads; 20 % of the kernel's stall samples when they sat at the top of each
-    // tile) hides behind the TMA loads of Q / K / V / dO. Both halves of a row compute it: no exchange.
+    // delta = <dO_row, O_row> of this thread's row in BOTH query tiles from the TMA-loaded tiles (O sits in the P area;
+    // both tiles carry the same swizzle, so the 16-byte pieces pair up by position), the forward log-sum-exp from
+    // global memory, requested before the wait. Both halves of a row compute it: no exchange. (Loading the rows with
+    // 16-byte global loads instead cost ~5000 cycles per CTA after the operands had already landed.)
     float delta_t[2] = {0.f, 0.f}, lse_t[2] = {0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+      if (t * 128 + r < AB_T)
+        lse_t[t] = __ldg(p.lse + (static_cast<size_t>(crop) * p.heads + head) * AB_T + t * 128 + r);
+    mbar_wait(&bar_load, 0);
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       const int token = t * 128 + r;
       if (token < AB_T) {
-        const size_t off = (static_cast<size_t>(crop) * AB_T + token) * ld_o + head * HD;
-        const uint4* a = reinterpret_cast<const uint4*>(p.dO + off);
-        const uint4* b = reinterpret_cast<const uint4*>(p.O + off);
         float d = 0.f;
-#pragma unroll
-        for (int u = 0; u < HD / 8; ++u) {
-          const uint4 x = __ldg(a + u), y = __ldg(b + u);
+        auto dot16 = [&](const uint8_t* a, const uint8_t* b) {
+          const uint4 x = *reinterpret_cast<const uint4*>(a), y = *reinterpret_cast<const uint4*>(b);
           const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -253,27 +289,41 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
             const float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[j]));
             d = fmaf(fx.x, fy.x, fmaf(fx.y, fy.y, d));
           }
+        };
+#pragma unroll
+        for (int u = 0; u < HDM / 8; ++u) {
+          const int off = token * 128 + ((u ^ (token & 7)) * 16);
+          dot16(s_do + off, s_p + off);
+        }
+        if constexpr (WIDE) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) dot16(s_dob + token * 32 + u * 16, s_p + AB_TILE + token * 32 + u * 16);
         }
         delta_t[t] = d;
-        lse_t[t] = __ldg(p.lse + (static_cast<size_t>(crop) * p.heads + head) * AB_T + token);
       }
     }
+    asm volatile("bar.sync 1, 256;" ::: "memory");     // every row of O has been read: the P area may be written
     for (int t = 0; t < 2; ++t) {
       const int token = t * 128 + r;
       const bool valid = token < AB_T;
       const float delta = t == 0 ? delta_t[0] : delta_t[1], lse = t == 0 ? lse_t[0] : lse_t[1];
+      AB_STAMP(1 + 6 * t);
       mbar_wait(&bar_s, t);
       tc_fence_after();
+      AB_STAMP(2 + 6 * t);
+      // Warps whose 32 rows all lie past the sequence end (second tile, rows 64..127) skip the arithmetic: P / dS rows of
+      // dead queries never enter a contraction (dK / dV contract over the live queries only, dQ rows are per query).
+      const bool warp_live = t * 128 + quad * 32 < AB_T;
       // P = exp2(s * scale * log2e - lse), one pass over this thread's 96 keys
-      for (int c = half * KH; c < (half + 1) * KH; c += 32) {
+      for (int c = half * KH; warp_live && c < (half + 1) * KH; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_s + lane_off + c, v);
         tmem_ld_wait();
         uint32_t packed[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          const float e0 = valid ? exp2f(fmaf(__uint_as_float(v[j]), p.scale_log2e, -lse)) : 0.f;
-          const float e1 = valid ? exp2f(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, -lse)) : 0.f;
+          const float e0 = fast_ex2(fmaf(__uint_as_float(v[j]), p.scale_log2e, -lse));
+          const float e1 = fast_ex2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, -lse));
           packed[j / 2] = pack_bf16x2(e0, e1);
         }
         const uint32_t row = smem_u32(s_p) + (c / 64) * AB_CHUNK + r * 128;
@@ -283,11 +333,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           sts_u4(row + (((u0 + u) ^ (r & 7)) * 16), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
       }
       tc_fence_before();               // all tcgen05.ld of S done before dP overwrites the columns
+      fence_proxy_async_smem();        // P (generic-proxy writes) visible to the tensor core: dV += P^T dO starts now
       mbar_arrive(&bar_sdone);
+      AB_STAMP(3 + 6 * t);
       mbar_wait(&bar_dp, t);
       tc_fence_after();
+      AB_STAMP(4 + 6 * t);
       // dS = scale * P o (dP - delta)
-      for (int c = half * KH; c < (half + 1) * KH; c += 32) {
+      for (int c = half * KH; warp_live && c < (half + 1) * KH; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_s + lane_off + c, v);
         tmem_ld_wait();
@@ -307,16 +360,18 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
             const float2 pp = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pw[j]));
             const float d0 = pp.x * (__uint_as_float(v[8 * u + 2 * j]) - delta) * p.scale;
             const float d1 = pp.y * (__uint_as_float(v[8 * u + 2 * j + 1]) - delta) * p.scale;
-            o[j] = valid ? pack_bf16x2(d0, d1) : 0u;
+            o[j] = pack_bf16x2(d0, d1);
           }
           sts_u4(drow + so, o[0], o[1], o[2], o[3]);
         }
       }
       tc_fence_before();
-      fence_proxy_async_smem();         // P and dS (generic-proxy writes) visible to the tensor core
+      fence_proxy_async_smem();         // dS (generic-proxy writes) visible to the tensor core
       mbar_arrive(&bar_ds);
+      AB_STAMP(5 + 6 * t);
       mbar_wait(&bar_mma, t);
       tc_fence_after();
+      AB_STAMP(6 + 6 * t);
       // dQ rows of this tile: half of the head's columns per thread. A row-per-thread global store would touch 32 lines
       // with 16 bytes each per instruction, so the warp stages its 32-row block in shared memory (the dS tile: dead
       // from bar_mma(t) until every thread has arrived at bar_sdone(t + 1), which this one does only after the copy;
@@ -350,6 +405,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       }
       tc_fence_before();
     }
+    AB_STAMP(13);
     // dK / dV rows (keys): key tile m, lane r <-> key m*128 + r; half 0 stores dK, half 1 stores dV. Every operand tile
     // is dead by now (all MMAs have completed): the warp stages its 32-row block in the Q/K/V/dO area and stores whole
     // rows, HD / 8 lanes per row.
@@ -382,21 +438,24 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       __syncwarp();
     }
   }
+  AB_STAMP(14);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_s, 512);
+  AB_STAMP(15);
 }
 
 template <int HD>
-static int launch_attention_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tqb,
-                                const CUtensorMap& tdob, const AttnBwdParams& p, cudaStream_t stream) {
+static int launch_attention_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& to,
+                                const CUtensorMap& tqb, const CUtensorMap& tdob, const CUtensorMap& tob,
+                                const AttnBwdParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     VPB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         AttnBwdCfg<HD>::SMEM));
     configured = true;
   }
-  attention_bwd_kernel<HD><<<p.n * p.heads, AB_THREADS, AttnBwdCfg<HD>::SMEM, stream>>>(tq, tdo, tqb, tdob, p);
+  attention_bwd_kernel<HD><<<p.n * p.heads, AB_THREADS, AttnBwdCfg<HD>::SMEM, stream>>>(tq, tdo, to, tqb, tdob, tob, p);
   VPB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -407,7 +466,7 @@ int attention_bwd(const void* qkv, const void* out, const float* lse, const void
   VPB_REQUIRE(T == AB_T && (hd == 32 || hd == 64 || hd == 80),
               "attention_bwd: built for T=%d, head_dim 32 / 64 / 80 (got T=%d, head_dim=%d)", AB_T, T, hd);
   const int ld_o = heads * hd, ld = 3 * ld_o;
-  CUtensorMap tq, tdo, tqb, tdob;
+  CUtensorMap tq, tdo, to, tqb, tdob, tob;
   uint64_t dims[3] = {(uint64_t)ld, (uint64_t)T, (uint64_t)n};
   uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)T * ld * 2};
   uint32_t box[3] = {64, (uint32_t)T, 1};
@@ -415,12 +474,15 @@ int attention_bwd(const void* qkv, const void* out, const float* lse, const void
   uint64_t dims_o[3] = {(uint64_t)ld_o, (uint64_t)T, (uint64_t)n};
   uint64_t strides_o[2] = {(uint64_t)ld_o * 2, (uint64_t)T * ld_o * 2};
   if (make_tma_desc(&tdo, TMA_BF16, dout, 3, dims_o, strides_o, box, TMA_SWIZZLE_128B)) return -1;
+  if (make_tma_desc(&to, TMA_BF16, out, 3, dims_o, strides_o, box, TMA_SWIZZLE_128B)) return -1;
   tqb = tq;
   tdob = tdo;
+  tob = to;
   if (hd > 64) {      // the 16-column remainder of each operand
     uint32_t box_b[3] = {16, (uint32_t)T, 1};
     if (make_tma_desc(&tqb, TMA_BF16, qkv, 3, dims, strides, box_b, TMA_SWIZZLE_32B)) return -1;
     if (make_tma_desc(&tdob, TMA_BF16, dout, 3, dims_o, strides_o, box_b, TMA_SWIZZLE_32B)) return -1;
+    if (make_tma_desc(&tob, TMA_BF16, out, 3, dims_o, strides_o, box_b, TMA_SWIZZLE_32B)) return -1;
   }
   AttnBwdParams p;
   p.n = n; p.heads = heads; p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
@@ -429,9 +491,31 @@ int attention_bwd(const void* qkv, const void* out, const float* lse, const void
   p.lse = lse;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   p.dbias = dbias;
-  if (hd == 32) return launch_attention_bwd<32>(tq, tdo, tqb, tdob, p, stream);
-  if (hd == 64) return launch_attention_bwd<64>(tq, tdo, tqb, tdob, p, stream);
-  return launch_attention_bwd<80>(tq, tdo, tqb, tdob, p, stream);
+  p.dbg = nullptr;
+  p.dbg_cta = 0;
+  {
+    static const bool debug = getenv("VPB_ATTBWD_DEBUG") != nullptr;
+    if (debug) p.dbg_cta = atoi(getenv("VPB_ATTBWD_DEBUG"));
+    static long long* buf = nullptr;
+    if (debug) {
+      if (buf == nullptr) VPB_CHECK_CUDA(cudaMallocManaged(&buf, 32 * sizeof(long long)));
+      else {      // stamps of the previous launch
+        cudaStreamSynchronize(stream);
+        const long long t0 = buf[0];
+        fprintf(stderr, "attention_bwd stamped CTA cycles | issuer: loaded %lld, t0: S consumed %lld dS ready %lld MMAs issued %lld, "
+                        "t1: %lld %lld %lld, end %lld | thread 32: t0 wait-S %lld..%lld P done %lld dP ready %lld dS done %lld "
+                        "MMAs done %lld, t1 %lld..%lld %lld %lld %lld %lld, dQ drained %lld, dK/dV stored %lld, exit %lld\n",
+                buf[1] - t0, buf[2] - t0, buf[3] - t0, buf[4] - t0, buf[6] - t0, buf[7] - t0, buf[8] - t0, buf[15] - t0,
+                buf[17] - t0, buf[18] - t0, buf[19] - t0, buf[20] - t0, buf[21] - t0, buf[22] - t0, buf[23] - t0,
+                buf[24] - t0, buf[25] - t0, buf[26] - t0, buf[27] - t0, buf[28] - t0, buf[29] - t0, buf[30] - t0,
+                buf[31] - t0);
+      }
+      p.dbg = buf;
+    }
+  }
+  if (hd == 32) return launch_attention_bwd<32>(tq, tdo, to, tqb, tdob, tob, p, stream);
+  if (hd == 64) return launch_attention_bwd<64>(tq, tdo, to, tqb, tdob, tob, p, stream);
+  return launch_attention_bwd<80>(tq, tdo, to, tqb, tdob, tob, p, stream);
 }
 
 }  // namespace vpb
