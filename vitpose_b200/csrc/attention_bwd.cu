@@ -66,6 +66,7 @@ struct AttnBwdParams {
   float* dbias;               // optional [3*heads*hd]: += column sums of dqkv over all tokens (attn.qkv's bias gradient)
   long long* dbg;             // VPB_ATTBWD_DEBUG=<cta>: clock64 stamps of that CTA (thread 0: [0,16), thread 32: [16,32))
   int dbg_cta;
+  int prefetch;               // > 0: block b prefetches the tiles of block b + prefetch into L2
 };
 
 // fp32 columns [0, N) of this thread's TMEM lane, N a multiple of 8
@@ -89,16 +90,26 @@ __device__ __forceinline__ void tmem_ld_row(uint32_t taddr, float (&out)[N]) {
   }
 }
 
-// dst[j] += sum over the warp's live rows of x[j], j < N (lane = row)
-template <int N>
-__device__ __forceinline__ void warp_colsum_atomic(const float (&x)[N], bool live, int lane, float* dst) {
+// dst[c] += sum over the first `rows` rows of a staged bf16 block [32 rows x NCOLS] (row pitch PITCH bytes), c < NCOLS:
+// lane j owns the 32-bit words j, j + 32, ... of every row (two columns each; consecutive lanes read consecutive
+// words: conflict-free). The sums are those of the bf16 values the kernel stores, i.e. exactly the column sums of dqkv.
+// (A shuffle tree over the fp32 registers cost ~2.5x the instructions: 9 of 104 us per launch.)
+template <int NCOLS, int PITCH>
+__device__ __forceinline__ void staged_colsum_atomic(const uint8_t* stage, int rows, int lane, float* dst) {
+  constexpr int NW = NCOLS / 2;
 #pragma unroll
-  for (int c0 = 0; c0 < N; c0 += 32) {
-    float cs[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) cs[j] = (live && c0 + j < N) ? x[c0 + j < N ? c0 + j : 0] : 0.f;
-    const float sum = warp_colsum32(cs, lane);
-    if (c0 + lane < N) atomicAdd(dst + c0 + lane, sum);
+  for (int w0 = 0; w0 < NW; w0 += 32) {
+    const int w = w0 + lane;
+    if (w < NW) {
+      float s0 = 0.f, s1 = 0.f;
+      for (int i = 0; i < rows; ++i) {
+        const uint32_t x = *reinterpret_cast<const uint32_t*>(stage + i * PITCH + w * 4);
+        s0 += __uint_as_float(x << 16);
+        s1 += __uint_as_float(x & 0xffff0000u);
+      }
+      atomicAdd(dst + 2 * w, s0);
+      atomicAdd(dst + 2 * w + 1, s1);
+    }
   }
 }
 
@@ -129,8 +140,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   uint8_t* s_kb = s_qb + AB_BOXB;
   uint8_t* s_vb = s_kb + AB_BOXB;
   uint8_t* s_dob = s_vb + AB_BOXB;
-  __shared__ uint64_t bar_load, bar_s, bar_sdone, bar_dp, bar_ds, bar_mma, bar_dq;
+  __shared__ uint64_t bar_load, bar_s, bar_sdone, bar_dp, bar_ds, bar_mma, bar_dq, bar_dqr;
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_delta[2][2][128];              // [tile][half][row]: partial <dO_row, O_row>
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.x % p.heads;
@@ -146,6 +158,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     mbar_init(&bar_ds, 256);
     mbar_init(&bar_mma, 1);
     mbar_init(&bar_dq, 256);
+    mbar_init(&bar_dqr, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
@@ -167,19 +180,36 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
-      // the forward output O goes where P will be written: it is only needed for delta = <dO_row, O_row> at the start
+      // the forward output O goes where dS will be written: it is only needed for delta = <dO_row, O_row>, which the
+      // threads form while they wait for the first dP
       mbar_arrive_expect_tx(&bar_load, 5 * AB_TILE + (WIDE ? 5 * AB_BOXB : 0));
       tma_load_3d(s_q, &tm_qkv, &bar_load, head * HD, 0, crop);
       tma_load_3d(s_k, &tm_qkv, &bar_load, ld_o + head * HD, 0, crop);
       tma_load_3d(s_v, &tm_qkv, &bar_load, 2 * ld_o + head * HD, 0, crop);
       tma_load_3d(s_do, &tm_do, &bar_load, head * HD, 0, crop);
-      tma_load_3d(s_p, &tm_o, &bar_load, head * HD, 0, crop);
+      tma_load_3d(s_ds, &tm_o, &bar_load, head * HD, 0, crop);
       if constexpr (WIDE) {
-        tma_load_3d(s_p + AB_TILE, &tm_ob, &bar_load, head * HD + 64, 0, crop);
+        tma_load_3d(s_ds + AB_TILE, &tm_ob, &bar_load, head * HD + 64, 0, crop);
         tma_load_3d(s_qb, &tm_qkvb, &bar_load, head * HD + 64, 0, crop);
         tma_load_3d(s_kb, &tm_qkvb, &bar_load, ld_o + head * HD + 64, 0, crop);
         tma_load_3d(s_vb, &tm_qkvb, &bar_load, 2 * ld_o + head * HD + 64, 0, crop);
         tma_load_3d(s_dob, &tm_dob, &bar_load, head * HD + 64, 0, crop);
+      }
+      // the tiles of the CTA that will follow on some SM one wave later: L2 hits instead of HBM latency at its start
+      if (const int nxt = blockIdx.x + p.prefetch; p.prefetch > 0 && nxt < p.n * p.heads) {
+        const int h2 = nxt % p.heads, c2 = nxt / p.heads;
+        tma_prefetch_l2_3d(&tm_qkv, h2 * HD, 0, c2);
+        tma_prefetch_l2_3d(&tm_qkv, ld_o + h2 * HD, 0, c2);
+        tma_prefetch_l2_3d(&tm_qkv, 2 * ld_o + h2 * HD, 0, c2);
+        tma_prefetch_l2_3d(&tm_do, h2 * HD, 0, c2);
+        tma_prefetch_l2_3d(&tm_o, h2 * HD, 0, c2);
+        if constexpr (WIDE) {
+          tma_prefetch_l2_3d(&tm_qkvb, h2 * HD + 64, 0, c2);
+          tma_prefetch_l2_3d(&tm_qkvb, ld_o + h2 * HD + 64, 0, c2);
+          tma_prefetch_l2_3d(&tm_qkvb, 2 * ld_o + h2 * HD + 64, 0, c2);
+          tma_prefetch_l2_3d(&tm_dob, h2 * HD + 64, 0, c2);
+          tma_prefetch_l2_3d(&tm_ob, h2 * HD + 64, 0, c2);
+        }
       }
       mbar_wait(&bar_load, 0);
       tc_fence_after();
@@ -238,7 +268,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           if constexpr (WIDE)
             umma_bf16_ss(tmem_dq + 64, a, umma_desc_mn_sw32(smem_u32(s_kb) + ks * 512), idesc_dq16, ks != 0);
         }
-        // dK += dS^T Q_t (contraction over the valid queries of this tile)
+        umma_commit(&bar_dqr);          // dQ (and every MMA before it: dV) complete -> the threads drain dQ ...
+        // ... while dK += dS^T Q_t runs (contraction over the valid queries of this tile)
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
 #pragma unroll
@@ -253,8 +284,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         umma_commit(&bar_mma);
         AB_STAMP(4 + 4 * t);
         // head_dim <= 64: the next tile's S is issued right away: its TMEM columns are free since bar_ds (every thread
-        // has read dP), the tensor pipe runs it behind the MMAs above, and the threads rewrite the P / dS tiles only
-        // after bar_mma — so S of tile 1 is ready while the threads still drain dQ of tile 0.
+        // has read dP) and the tensor pipe runs it behind the MMAs above. The threads rewrite P after bar_dqr (dV has
+        // consumed it) and dS after bar_mma (dK has consumed it).
       };
       issue_tile(std::integral_constant<int, 0>{});
       issue_tile(std::integral_constant<int, 1>{});
@@ -265,48 +296,49 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     const int r = quad * 32 + lane;                 // row inside a tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     constexpr int KH = AB_T / 2;                    // 96 keys per thread
-    // delta = <dO_row, O_row> of this thread's row in BOTH query tiles from the TMA-loaded tiles (O sits in the P area;
-    // both tiles carry the same swizzle, so the 16-byte pieces pair up by position), the forward log-sum-exp from
-    // global memory, requested before the wait. Both halves of a row compute it: no exchange. (Loading the rows with
-    // 16-byte global loads instead cost ~5000 cycles per CTA after the operands had already landed.)
+    // The forward log-sum-exp of this thread's row in BOTH query tiles, requested up front. delta = <dO_row, O_row> is
+    // formed from the TMA-loaded tiles while the first dP is in flight (O sits in the dS area; both tiles carry the same
+    // swizzle, so the 16-byte pieces pair up by position). (Loading the
+    // rows with 16-byte global loads instead cost ~5000 cycles per CTA after the operands had already landed.)
     float delta_t[2] = {0.f, 0.f}, lse_t[2] = {0.f, 0.f};
 #pragma unroll
     for (int t = 0; t < 2; ++t)
       if (t * 128 + r < AB_T)
         lse_t[t] = __ldg(p.lse + (static_cast<size_t>(crop) * p.heads + head) * AB_T + t * 128 + r);
-    mbar_wait(&bar_load, 0);
+    auto form_delta = [&]() {
+      mbar_wait(&bar_load, 0);         // completed long ago: orders this thread's reads behind the TMA writes
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int token = t * 128 + r;
-      if (token < AB_T) {
-        float d = 0.f;
-        auto dot16 = [&](const uint8_t* a, const uint8_t* b) {
-          const uint4 x = *reinterpret_cast<const uint4*>(a), y = *reinterpret_cast<const uint4*>(b);
-          const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+      for (int t = 0; t < 2; ++t) {
+        const int token = t * 128 + r;
+        if (token < AB_T) {
+          float d = 0.f;
+          auto dot16 = [&](const uint8_t* a, const uint8_t* b) {
+            const uint4 x = *reinterpret_cast<const uint4*>(a), y = *reinterpret_cast<const uint4*>(b);
+            const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[j]));
-            const float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[j]));
-            d = fmaf(fx.x, fy.x, fmaf(fx.y, fy.y, d));
+            for (int j = 0; j < 4; ++j) {
+              const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[j]));
+              const float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[j]));
+              d = fmaf(fx.x, fy.x, fmaf(fx.y, fy.y, d));
+            }
+          };
+          // each half takes half of the row's 16-byte pieces; the partial sums meet in shared memory
+#pragma unroll
+          for (int u = half * (HDM / 16); u < (half + 1) * (HDM / 16); ++u) {
+            const int off = token * 128 + ((u ^ (token & 7)) * 16);
+            dot16(s_do + off, s_ds + off);
           }
-        };
-#pragma unroll
-        for (int u = 0; u < HDM / 8; ++u) {
-          const int off = token * 128 + ((u ^ (token & 7)) * 16);
-          dot16(s_do + off, s_p + off);
+          if constexpr (WIDE) dot16(s_dob + token * 32 + half * 16, s_ds + AB_TILE + token * 32 + half * 16);
+          s_delta[t][half][r] = d;
         }
-        if constexpr (WIDE) {
-#pragma unroll
-          for (int u = 0; u < 2; ++u) dot16(s_dob + token * 32 + u * 16, s_p + AB_TILE + token * 32 + u * 16);
-        }
-        delta_t[t] = d;
       }
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");     // every row of O has been read: the P area may be written
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // every row of O has been read: the dS area may be written
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        if (t * 128 + r < AB_T) delta_t[t] = s_delta[t][0][r] + s_delta[t][1][r];
+    };
     for (int t = 0; t < 2; ++t) {
-      const int token = t * 128 + r;
-      const bool valid = token < AB_T;
-      const float delta = t == 0 ? delta_t[0] : delta_t[1], lse = t == 0 ? lse_t[0] : lse_t[1];
+      const float lse = t == 0 ? lse_t[0] : lse_t[1];
       AB_STAMP(1 + 6 * t);
       mbar_wait(&bar_s, t);
       tc_fence_after();
@@ -336,6 +368,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       fence_proxy_async_smem();        // P (generic-proxy writes) visible to the tensor core: dV += P^T dO starts now
       mbar_arrive(&bar_sdone);
       AB_STAMP(3 + 6 * t);
+      if (t == 0) form_delta();
+      else mbar_wait(&bar_mma, 0);     // dK of tile 0 has consumed the dS tile
+      const float delta = t == 0 ? delta_t[0] : delta_t[1];
       mbar_wait(&bar_dp, t);
       tc_fence_after();
       AB_STAMP(4 + 6 * t);
@@ -369,13 +404,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       fence_proxy_async_smem();         // dS (generic-proxy writes) visible to the tensor core
       mbar_arrive(&bar_ds);
       AB_STAMP(5 + 6 * t);
-      mbar_wait(&bar_mma, t);
+      mbar_wait(&bar_dqr, t);
       tc_fence_after();
       AB_STAMP(6 + 6 * t);
       // dQ rows of this tile: half of the head's columns per thread. A row-per-thread global store would touch 32 lines
-      // with 16 bytes each per instruction, so the warp stages its 32-row block in shared memory (the dS tile: dead
-      // from bar_mma(t) until every thread has arrived at bar_sdone(t + 1), which this one does only after the copy;
-      // row pitch an odd number of 16-byte units: conflict-free both ways) and writes whole row pieces back.
+      // with 16 bytes each per instruction, so the warp stages its 32-row block in shared memory and writes whole row
+      // pieces back. The block lives in the part of the P tile only this warp writes (its 32 rows of key chunk 0 /
+      // chunk 2 for the two halves; dV has consumed P: bar_dqr), so no other warp's next P can touch it; row pitch an
+      // odd number of 16-byte units: conflict-free both ways.
       {
         float v[C::QC];
         tmem_ld_row<C::QC>(tmem_dq + lane_off + half * C::QC, v);
@@ -383,15 +419,17 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           tc_fence_before();
           mbar_arrive(&bar_dq);
         }
-        if (p.dbias != nullptr)         // bias gradient of attn.qkv: column sums over the live rows of this warp
-          warp_colsum_atomic<C::QC>(v, valid, lane, p.dbias + head * HD + half * C::QC);
-        uint8_t* stage = s_ds + (warp - 1) * (32 * C::Q_PITCH);
+        uint8_t* stage = s_p + 2 * half * AB_CHUNK + quad * 32 * 128;
+        static_assert(32 * C::Q_PITCH <= 32 * 128, "the staging block fits the warp's own rows of one key chunk");
 #pragma unroll
         for (int u = 0; u < C::Q_PIECES; ++u)
           *reinterpret_cast<uint4*>(stage + lane * C::Q_PITCH + u * 16) =
               make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
                          pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
         __syncwarp();
+        const int live_rows = min(32, max(0, AB_T - (t * 128 + quad * 32)));
+        if (p.dbias != nullptr)         // bias gradient of attn.qkv: column sums over the live rows of this warp
+          staged_colsum_atomic<C::QC, C::Q_PITCH>(stage, live_rows, lane, p.dbias + head * HD + half * C::QC);
         __nv_bfloat16* obase = p.dqkv + (static_cast<size_t>(crop) * AB_T + t * 128 + quad * 32) * ld_qkv +
                                head * HD + half * C::QC;
 #pragma unroll
@@ -405,6 +443,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       }
       tc_fence_before();
     }
+    mbar_wait(&bar_mma, 1);
+    tc_fence_after();
     AB_STAMP(13);
     // dK / dV rows (keys): key tile m, lane r <-> key m*128 + r; half 0 stores dK, half 1 stores dV. Every operand tile
     // is dead by now (all MMAs have completed): the warp stages its 32-row block in the Q/K/V/dO area and stores whole
@@ -412,20 +452,23 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     for (int m = 0; m < 2; ++m) {
       const uint32_t base = (half == 0 ? tmem_dk : tmem_dv) + m * HD + lane_off;
       uint8_t* stage = s_q + (warp - 1) * (32 * C::K_PITCH);
-      const bool key_ok = m * 128 + quad * 32 + lane < AB_T;
+      auto piece = [&](auto nc, int c) {
+        constexpr int NC = decltype(nc)::value;
+        float v[NC];
+        tmem_ld_row<NC>(base + c, v);
 #pragma unroll
-      for (int c = 0; c < HD; c += 16) {
-        float v[16];
-        tmem_ld_row<16>(base + c, v);
-        if (p.dbias != nullptr)
-          warp_colsum_atomic<16>(v, key_ok, lane, p.dbias + (1 + half) * ld_o + head * HD + c);
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < NC / 8; ++u)
           *reinterpret_cast<uint4*>(stage + lane * C::K_PITCH + c * 2 + u * 16) =
               make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
                          pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
-      }
+      };
+#pragma unroll
+      for (int c = 0; c + 32 <= HD; c += 32) piece(std::integral_constant<int, 32>{}, c);
+      if constexpr (HD % 32 != 0) piece(std::integral_constant<int, 16>{}, HD - 16);
       __syncwarp();
+      if (p.dbias != nullptr)
+        staged_colsum_atomic<HD, C::K_PITCH>(stage, min(32, max(0, AB_T - (m * 128 + quad * 32))), lane,
+                                             p.dbias + (1 + half) * ld_o + head * HD);
       __nv_bfloat16* obase = p.dqkv + (static_cast<size_t>(crop) * AB_T + m * 128 + quad * 32) * ld_qkv +
                              (1 + half) * ld_o + head * HD;
 #pragma unroll
@@ -493,6 +536,10 @@ int attention_bwd(const void* qkv, const void* out, const float* lse, const void
   p.dbias = dbias;
   p.dbg = nullptr;
   p.dbg_cta = 0;
+  {
+    static const int pf = getenv("VPB_ATTBWD_PREFETCH") ? atoi(getenv("VPB_ATTBWD_PREFETCH")) : sm_count();
+    p.prefetch = pf;
+  }
   {
     static const bool debug = getenv("VPB_ATTBWD_DEBUG") != nullptr;
     if (debug) p.dbg_cta = atoi(getenv("VPB_ATTBWD_DEBUG"));
