@@ -73,21 +73,13 @@ struct AttnBwdParams {
 template <int N>
 __device__ __forceinline__ void tmem_ld_row(uint32_t taddr, float (&out)[N]) {
   static_assert(N % 8 == 0, "pieces of 8 columns");
+  uint32_t v[N];                        // every load in flight, one wait
 #pragma unroll
-  for (int c = 0; c + 16 <= N; c += 16) {
-    uint32_t v[16];
-    tmem_ld_32x32b_x16(taddr + c, v);
-    tmem_ld_wait();
+  for (int c = 0; c + 16 <= N; c += 16) tmem_ld_32x32b_x16(taddr + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+  if constexpr (N % 16 != 0) tmem_ld_32x32b_x8(taddr + (N - 8), *reinterpret_cast<uint32_t(*)[8]>(&v[N - 8]));
+  tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) out[c + j] = __uint_as_float(v[j]);
-  }
-  if constexpr (N % 16 != 0) {
-    uint32_t v[8];
-    tmem_ld_32x32b_x8(taddr + (N - 8), v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) out[N - 8 + j] = __uint_as_float(v[j]);
-  }
+  for (int j = 0; j < N; ++j) out[j] = __uint_as_float(v[j]);
 }
 
 // dst[c] += sum over the first `rows` rows of a staged bf16 block [32 rows x NCOLS] (row pitch PITCH bytes), c < NCOLS:
@@ -101,12 +93,20 @@ __device__ __forceinline__ void staged_colsum_atomic(const uint8_t* stage, int r
   for (int w0 = 0; w0 < NW; w0 += 32) {
     const int w = w0 + lane;
     if (w < NW) {
-      float s0 = 0.f, s1 = 0.f;
-      for (int i = 0; i < rows; ++i) {
-        const uint32_t x = *reinterpret_cast<const uint32_t*>(stage + i * PITCH + w * 4);
+      // rows is warp-uniform but not known at compile time: fixed trip count with predicated loads, so that the loads
+      // of a batch are in flight together (a `rows`-bounded loop ran as 32 dependent load -> add steps)
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const uint32_t x = i < rows ? *reinterpret_cast<const uint32_t*>(stage + i * PITCH + w * 4) : 0u;
+        const uint32_t y = i + 1 < rows ? *reinterpret_cast<const uint32_t*>(stage + (i + 1) * PITCH + w * 4) : 0u;
         s0 += __uint_as_float(x << 16);
         s1 += __uint_as_float(x & 0xffff0000u);
+        s2 += __uint_as_float(y << 16);
+        s3 += __uint_as_float(y & 0xffff0000u);
       }
+      s0 += s2;
+      s1 += s3;
       atomicAdd(dst + 2 * w, s0);
       atomicAdd(dst + 2 * w + 1, s1);
     }
@@ -119,6 +119,7 @@ __device__ __forceinline__ void staged_colsum_atomic(const uint8_t* stage, int r
       p.dbg[(threadIdx.x == 0 ? 0 : 16) + (slot)] = clock64();                          \
   } while (0)
 
+// 9 warps: one sub-partition holds three of them, so 16384 / (3 * 32) = 170 registers per thread is the ceiling
 template <int HD>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
@@ -219,6 +220,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       constexpr uint32_t idesc_dq16 = umma_idesc_bf16(128, 16, 0, 1);
       constexpr uint32_t idesc_t = umma_idesc_bf16(128, HDM, 1, 1);       // A (P^T / dS^T) and B MN-major
       constexpr uint32_t idesc_t16 = umma_idesc_bf16(128, 16, 1, 1);
+      auto issue_s = [&](uint32_t q_t, uint32_t qb_t) {        // S = Q_t K^T
+#pragma unroll
+        for (int ks = 0; ks < HDM / 16; ++ks)
+          umma_bf16_ss(tmem_s, umma_desc_k_sw128(q_t + ks * 32), umma_desc_k_sw128(smem_u32(s_k) + ks * 32), idesc_s,
+                       ks != 0);
+        if constexpr (WIDE) umma_bf16_ss(tmem_s, umma_desc_k_sw32(qb_t), umma_desc_k_sw32(smem_u32(s_kb)), idesc_s, 1u);
+        umma_commit(&bar_s);
+      };
       auto issue_tile = [&](auto tc) {
         constexpr int t = decltype(tc)::value;
         const uint32_t q_t = smem_u32(s_q) + t * AB_CHUNK, do_t = smem_u32(s_do) + t * AB_CHUNK;
@@ -227,13 +236,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           mbar_wait(&bar_dq, 0);
           tc_fence_after();
         }
-        // S = Q_t K^T
-#pragma unroll
-        for (int ks = 0; ks < HDM / 16; ++ks)
-          umma_bf16_ss(tmem_s, umma_desc_k_sw128(q_t + ks * 32), umma_desc_k_sw128(smem_u32(s_k) + ks * 32), idesc_s,
-                       ks != 0);
-        if constexpr (WIDE) umma_bf16_ss(tmem_s, umma_desc_k_sw32(qb_t), umma_desc_k_sw32(smem_u32(s_kb)), idesc_s, 1u);
-        umma_commit(&bar_s);
+        if constexpr (WIDE || t == 0) issue_s(q_t, qb_t);
         // dP = dO_t V^T into the same columns once every thread has consumed S
         mbar_wait(&bar_sdone, t);
         tc_fence_after();
@@ -260,6 +263,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         mbar_wait(&bar_ds, t);
         tc_fence_after();
         AB_STAMP(3 + 4 * t);
+        // head_dim <= 64: the next tile's S goes first — its TMEM columns are free (every thread has read dP) and the
+        // threads start on its P while dQ / dK of this tile are still running; dQ of tile 0 is drained later, behind
+        // the wait for dP of tile 1. (head_dim 80: dQ occupies the S columns, the order stays S after dQ.)
+        if constexpr (!WIDE && t == 0) issue_s(smem_u32(s_q) + AB_CHUNK, 0u);
         // dQ_t = dS K (contraction over the 192 keys)
 #pragma unroll
         for (int ks = 0; ks < AB_T / 16; ++ks) {
@@ -283,9 +290,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         }
         umma_commit(&bar_mma);
         AB_STAMP(4 + 4 * t);
-        // head_dim <= 64: the next tile's S is issued right away: its TMEM columns are free since bar_ds (every thread
-        // has read dP) and the tensor pipe runs it behind the MMAs above. The threads rewrite P after bar_dqr (dV has
-        // consumed it) and dS after bar_mma (dK has consumed it).
+        // The threads rewrite P once dV has consumed it (bar_s of the next tile / bar_dqr: both commits follow the dV
+        // MMAs) and dS after bar_mma (dK has consumed it).
       };
       issue_tile(std::integral_constant<int, 0>{});
       issue_tile(std::integral_constant<int, 1>{});
@@ -337,6 +343,40 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       for (int t = 0; t < 2; ++t)
         if (t * 128 + r < AB_T) delta_t[t] = s_delta[t][0][r] + s_delta[t][1][r];
     };
+    // dQ rows of a tile: half of the head's columns per thread. A row-per-thread global store would touch 32 lines with
+    // 16 bytes each per instruction, so the warp stages its 32-row block in shared memory and writes whole row pieces
+    // back. The block lives in the part of the P (or dS) tile only this warp writes (its 32 rows of key chunk 0 / chunk
+    // 2 for the two halves), so no other warp's next P / dS can touch it; row pitch an odd number of 16-byte units:
+    // conflict-free both ways.
+    auto drain_dq = [&](int t, uint8_t* area) {
+      float v[C::QC];
+      tmem_ld_row<C::QC>(tmem_dq + lane_off + half * C::QC, v);
+      if constexpr (WIDE) {             // the S columns are free for the next tile's scores
+        tc_fence_before();
+        mbar_arrive(&bar_dq);
+      }
+      uint8_t* stage = area + 2 * half * AB_CHUNK + quad * 32 * 128;
+      static_assert(32 * C::Q_PITCH <= 32 * 128, "the staging block fits the warp's own rows of one key chunk");
+#pragma unroll
+      for (int u = 0; u < C::Q_PIECES; ++u)
+        *reinterpret_cast<uint4*>(stage + lane * C::Q_PITCH + u * 16) =
+            make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                       pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+      __syncwarp();
+      const int live_rows = min(32, max(0, AB_T - (t * 128 + quad * 32)));
+      if (p.dbias != nullptr)           // bias gradient of attn.qkv: column sums over the live rows of this warp
+        staged_colsum_atomic<C::QC, C::Q_PITCH>(stage, live_rows, lane, p.dbias + head * HD + half * C::QC);
+      __nv_bfloat16* obase = p.dqkv + (static_cast<size_t>(crop) * AB_T + t * 128 + quad * 32) * ld_qkv +
+                             head * HD + half * C::QC;
+#pragma unroll
+      for (int j = 0; j < C::Q_PIECES; ++j) {
+        const int idx = j * 32 + lane, row = idx / C::Q_PIECES, ch = idx % C::Q_PIECES;
+        if (t * 128 + quad * 32 + row < AB_T)
+          *reinterpret_cast<uint4*>(obase + static_cast<size_t>(row) * ld_qkv + ch * 8) =
+              *reinterpret_cast<const uint4*>(stage + row * C::Q_PITCH + ch * 16);
+      }
+      __syncwarp();
+    };
     for (int t = 0; t < 2; ++t) {
       const float lse = t == 0 ? lse_t[0] : lse_t[1];
       AB_STAMP(1 + 6 * t);
@@ -368,8 +408,16 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       fence_proxy_async_smem();        // P (generic-proxy writes) visible to the tensor core: dV += P^T dO starts now
       mbar_arrive(&bar_sdone);
       AB_STAMP(3 + 6 * t);
-      if (t == 0) form_delta();
-      else mbar_wait(&bar_mma, 0);     // dK of tile 0 has consumed the dS tile
+      if (t == 0) {
+        form_delta();
+      } else {
+        mbar_wait(&bar_mma, 0);        // dK of tile 0 has consumed the dS tile (and dQ of tile 0 is complete)
+        if constexpr (!WIDE) {         // head_dim <= 64: dQ of tile 0 is drained here, behind the wait for dP of tile 1
+          tc_fence_after();
+          drain_dq(0, s_ds);
+          tc_fence_before();
+        }
+      }
       const float delta = t == 0 ? delta_t[0] : delta_t[1];
       mbar_wait(&bar_dp, t);
       tc_fence_after();
@@ -404,42 +452,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       fence_proxy_async_smem();         // dS (generic-proxy writes) visible to the tensor core
       mbar_arrive(&bar_ds);
       AB_STAMP(5 + 6 * t);
-      mbar_wait(&bar_dqr, t);
-      tc_fence_after();
-      AB_STAMP(6 + 6 * t);
-      // dQ rows of this tile: half of the head's columns per thread. A row-per-thread global store would touch 32 lines
-      // with 16 bytes each per instruction, so the warp stages its 32-row block in shared memory and writes whole row
-      // pieces back. The block lives in the part of the P tile only this warp writes (its 32 rows of key chunk 0 /
-      // chunk 2 for the two halves; dV has consumed P: bar_dqr), so no other warp's next P can touch it; row pitch an
-      // odd number of 16-byte units: conflict-free both ways.
-      {
-        float v[C::QC];
-        tmem_ld_row<C::QC>(tmem_dq + lane_off + half * C::QC, v);
-        if constexpr (WIDE) {           // the S columns are free for the next tile's scores
-          tc_fence_before();
-          mbar_arrive(&bar_dq);
-        }
-        uint8_t* stage = s_p + 2 * half * AB_CHUNK + quad * 32 * 128;
-        static_assert(32 * C::Q_PITCH <= 32 * 128, "the staging block fits the warp's own rows of one key chunk");
-#pragma unroll
-        for (int u = 0; u < C::Q_PIECES; ++u)
-          *reinterpret_cast<uint4*>(stage + lane * C::Q_PITCH + u * 16) =
-              make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
-                         pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
-        __syncwarp();
-        const int live_rows = min(32, max(0, AB_T - (t * 128 + quad * 32)));
-        if (p.dbias != nullptr)         // bias gradient of attn.qkv: column sums over the live rows of this warp
-          staged_colsum_atomic<C::QC, C::Q_PITCH>(stage, live_rows, lane, p.dbias + head * HD + half * C::QC);
-        __nv_bfloat16* obase = p.dqkv + (static_cast<size_t>(crop) * AB_T + t * 128 + quad * 32) * ld_qkv +
-                               head * HD + half * C::QC;
-#pragma unroll
-        for (int j = 0; j < C::Q_PIECES; ++j) {
-          const int idx = j * 32 + lane, row = idx / C::Q_PIECES, ch = idx % C::Q_PIECES;
-          if (t * 128 + quad * 32 + row < AB_T)
-            *reinterpret_cast<uint4*>(obase + static_cast<size_t>(row) * ld_qkv + ch * 8) =
-                *reinterpret_cast<const uint4*>(stage + row * C::Q_PITCH + ch * 16);
-        }
-        __syncwarp();
+      if (WIDE || t == 1) {
+        mbar_wait(&bar_dqr, t);
+        tc_fence_after();
+        AB_STAMP(6 + 6 * t);
+        drain_dq(t, s_p);               // dV of this tile has consumed P (bar_dqr)
       }
       tc_fence_before();
     }
