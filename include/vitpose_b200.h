@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VPB_ABI_VERSION 4
+#define VPB_ABI_VERSION 5
 
 int vpb_abi_version(void);
 const char* vpb_last_error(void);
@@ -394,7 +394,7 @@ int vpb_adamw_multi(const vpb_tensor_entry* entries, const int32_t* chunk_start,
  * bf16(src) and wt[cols, rows] = bf16(src)^T (round to nearest even). Replaces, per layer, the implicit fp32 -> bf16
  * weight use of nn.Linear in the reference's autograd graph (mmpose/models/backbones/vit.py:79-85, 100-121: attn.qkv /
  * attn.proj / mlp.fc1 / mlp.fc2; patch_embed.proj :143-165 as a [D, 3*16*16] matrix). `entries` and `tile_start`
- * ([n + 1] prefix sums of ceil(rows/32) * ceil(cols/32)) live in device memory. */
+ * ([n + 1] prefix sums of ceil(rows/64) * ceil(cols/64)) live in device memory. */
 typedef struct vpb_cast_entry {
   const float* src; void* w; void* wt; int32_t rows; int32_t cols;
 } vpb_cast_entry;

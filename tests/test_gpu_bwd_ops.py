@@ -268,14 +268,14 @@ def test_deconv_fwd_bwd(n, h, w, cin, cout):
 
 def test_cast_transpose_multi_matches_per_layer_ops():
     """One launch for the bf16 W / W^T copies of many layers == cast_bf16 + transpose per layer, bit for bit
-    (ragged shapes exercise partial 32 x 32 tiles)."""
+    (ragged / odd shapes exercise partial 64 x 64 tiles and the element-wise path)."""
     import torch.nn as nn
     from vitpose_b200 import ops
     from vitpose_b200.training import _LinearBank
     torch.manual_seed(0)
     dev = torch.device('cuda:0')
     layers = [nn.Linear(45, 70), nn.Linear(768, 96), nn.Linear(33, 31, bias=False), nn.Conv2d(3, 40, 16, 16),
-              nn.Linear(64, 2304)]
+              nn.Linear(64, 2304), nn.Linear(130, 66)]
     layers = [l.to(dev) for l in layers]
     bank = _LinearBank(layers)
     for rep in range(2):                       # second pass: weights updated in place, table reused

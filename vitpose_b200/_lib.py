@@ -13,7 +13,7 @@ c_void_p, c_int, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_flo
 
 EPI_BIAS_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_POS_F32, EPI_NCHW_F32 = range(5)
 EPI_ACCUM_F32 = 10
-ABI_VERSION = 4          # VPB_ABI_VERSION of include/vitpose_b200.h this module was written against
+ABI_VERSION = 5          # VPB_ABI_VERSION of include/vitpose_b200.h this module was written against
 DECODE_NONE, DECODE_DEFAULT, DECODE_UNBIASED, DECODE_UDP_DARK = range(4)
 
 

@@ -81,7 +81,7 @@ class _LinearBank:
             if not l.weight.is_contiguous() or l.weight.dtype != torch.float32:
                 raise _lib.VitposeLibError('training expects contiguous fp32 master weights')
             table[i] = (l.weight.data_ptr(), w.data_ptr(), wt.data_ptr(), r, c)
-            starts[i + 1] = starts[i] + ((r + 31) // 32) * ((c + 31) // 32)
+            starts[i + 1] = starts[i] + ((r + 63) // 64) * ((c + 63) // 64)
         dev = self.arena.device
         self._table = torch.from_numpy(table.view(np.uint8)).to(dev)
         self._starts = torch.from_numpy(starts).to(dev)
