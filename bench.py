@@ -503,10 +503,10 @@ def main():
         # DRAM bytes of one fc1 launch: NOT measured by this run — read from the committed ncu --set full capture of
         # this same command (B workload, 256 crops), see traffic_source
         traffic, traffic_source = None, None
-        tpath = os.path.join(ROOT, 'profiles', 'r01_fc1_traffic.json')
+        tpath = os.path.join(ROOT, 'profiles', 'r02_fc1_traffic.json')
         if args.workload == 'B-classic-17' and n == 256 and os.path.exists(tpath):
             traffic = json.load(open(tpath))['traffic_bytes']
-            traffic_source = ('constant from profiles/r01_fc1_traffic.json (ncu --set full capture of the fc1 launch '
+            traffic_source = ('constant from profiles/r02_fc1_traffic.json (ncu --set full capture of the fc1 launch '
                               'of `bench.py`, dram__bytes_read.sum + dram__bytes_write.sum); not re-measured live')
         roofline = dict(bound='tensor', kernel='gemm_bf16_tn_kernel<256,GELU> (mlp.fc1)', achieved=achieved,
                         peak=pk['tf_sustained'], unit='TFLOP/s', frac=achieved / pk['tf_sustained'], traffic=traffic,
