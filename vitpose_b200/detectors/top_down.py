@@ -28,7 +28,10 @@ class TopDown(nn.Module):
                  loss_pose=None):
         super().__init__()
         self.fp16_enabled = False
-        self.host_chunk = 64          # crops per H2D chunk when forward_test is fed host tensors
+        # crops in the first H2D chunk when forward_test is fed host tensors (VPB_HOST_CHUNK: A/B switch)
+        self.host_chunk = int(os.environ.get('VPB_HOST_CHUNK', '32'))
+        # optional schedule of leading chunk sizes, the rest goes as one batch (VPB_HOST_CHUNKS=16,48: A/B switch)
+        self.host_chunks = [int(v) for v in os.environ.get('VPB_HOST_CHUNKS', '').split(',') if v]
         self._copy_stream = None
         self.backbone = builder.build_backbone(backbone)
         self.train_cfg = train_cfg
@@ -152,19 +155,21 @@ class TopDown(nn.Module):
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(dev)
             staged = []
-            # two chunks: a first one of `host_chunk` crops starts the GPU after a ~0.7 ms copy, and the copy of all
-            # the remaining crops (PCIe: ~2 ms per 192 crops) hides behind its ~5 ms of compute; the rest then runs
-            # as one large batch (few, full-size GEMM launches). Measured against a 32/64/128/... schedule: 3 % faster.
-            lo, size = 0, max(1, chunk)
+            # two chunks: a first one of `host_chunk` crops starts the GPU after a ~0.35 ms copy, and the copy of all
+            # the remaining crops (PCIe: ~2.4 ms per 224 crops) hides behind its ~2.7 ms of compute; the rest then runs
+            # as one large batch (few, full-size GEMM launches). Measured (256 crops + flips, end-to-end minus
+            # device-resident ms per step, same box): first chunk 64: 0.82 / 1.14, 48: 0.71, 32: 0.47-0.63, 24: 0.71;
+            # three chunks 16,48,rest: 0.75-0.92; 8,24,64,rest: 2.0 (profiles/r02_summary.md section 15).
+            sizes = list(self.host_chunks) if self.host_chunks else [max(1, chunk)]
+            lo = 0
             while lo < n:
-                size = min(size, n - lo)
+                size = min(sizes.pop(0) if sizes else n - lo, n - lo)
                 with torch.cuda.stream(self._copy_stream):
                     d = img[lo:lo + size].to(dev, non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(self._copy_stream)
                 staged.append((lo, d, ev))
                 lo += size
-                size = n - lo
             for lo, d, ev in staged:
                 main_stream.wait_event(ev)
                 d.record_stream(main_stream)
