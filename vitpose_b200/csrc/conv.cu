@@ -12,6 +12,7 @@
 // NHWC input fetched at the tap's (dx, dy) offset — out-of-image coordinates are zero-filled by TMA, which is
 // exactly the conv padding. A box holds 384 pixels = three 128-row UMMA tiles that share one weight tile, so
 // every weight byte staged in shared memory feeds 3x the math.
+#include <cstdlib>
 #include "host_util.h"
 #include "ops.h"
 #include "ptx.cuh"
@@ -33,9 +34,9 @@ constexpr int MODE_CONV3 = 1;
 
 struct ConvParams {
   int n, h, w, cin, cout;
-  int w_box, h_box, n_box;       // w_box == w
-  int tiles_y;                   // h / h_box
-  int super_tiles;               // ceil(n / n_box) * tiles_y
+  int w_box, h_box, n_box;       // pixels of an item = w_box * h_box * n_box (w_box divides w)
+  int tiles_x, tiles_y;          // w / w_box, h / h_box
+  int super_tiles;               // ceil(n / n_box) * tiles_y * tiles_x
   int n_tiles;                   // ceil(cout / BN)
   const float* scale;            // [cout] (deconv: folded BN scale)
   const float* shift;            // [cout] (deconv: folded BN shift; conv3: bias)
@@ -43,19 +44,23 @@ struct ConvParams {
   void* out;
 };
 
-template <int BN, int MODE>
+// SUB = 128-row sub-tiles per item. <128 channels, 3 sub-tiles> moves (48 + 16) KB of operands per 768 MMA cycles;
+// <256 channels, 2 sub-tiles> (the whole Cout = 256 of the ViTPose decoders in one tile: the activation box is
+// fetched once instead of once per 128-channel tile) moves (32 + 32) KB per 1024 cycles: 25 % fewer L2 -> SM bytes per
+// MMA cycle, which is what bounds this kernel. 256 pixels are a strip w_box x h_box x n_box of the image (w_box < w).
+template <int BN, int MODE, int SUB = CV_SUB>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
                   const ConvParams p) {
-  constexpr int A_BYTES = CV_ROWS * 128;
+  constexpr int A_BYTES = SUB * 128 * 128;
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int STAGES = (196608 / STAGE_BYTES) > 6 ? 6 : (196608 / STAGE_BYTES);
-  constexpr int TMEM_COLS = CV_SUB * BN <= 128 ? 128 : (CV_SUB * BN <= 256 ? 256 : 512);
+  constexpr int TMEM_COLS = SUB * BN <= 128 ? 128 : (SUB * BN <= 256 ? 256 : 512);
   constexpr uint32_t IDESC = umma_idesc_bf16(128, BN);
   constexpr int NTAPS = MODE == MODE_DECONV ? 4 : 9;
   constexpr int NPHASE = MODE == MODE_DECONV ? 4 : 1;
-  static_assert(CV_SUB * BN <= 512, "accumulators must fit TMEM");
+  static_assert(SUB * BN <= 512, "accumulators must fit TMEM");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -102,8 +107,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int st, phase, nt;
         decode_item(item, st, phase, nt);
-        const int n0 = (st / p.tiles_y) * p.n_box;
-        const int y0 = (st % p.tiles_y) * p.h_box;
+        const int x0 = (st % p.tiles_x) * p.w_box;
+        const int n0 = (st / p.tiles_x / p.tiles_y) * p.n_box;
+        const int y0 = (st / p.tiles_x % p.tiles_y) * p.h_box;
         const int py = phase >> 1, px = phase & 1;
         for (int ks = 0; ks < k_steps; ++ks) {
           const int tap = ks / cin_chunks, cc = ks - tap * cin_chunks;
@@ -119,7 +125,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
           mbar_wait(&empty_bar[stage], ph ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_4d(sa, &tm_in, &full_bar[stage], cc * 64, dx, y0 + dy, n0);
+          tma_load_4d(sa, &tm_in, &full_bar[stage], cc * 64, x0 + dx, y0 + dy, n0);
           tma_load_2d(sa + A_BYTES, &tm_w, &full_bar[stage], tap * p.cin + cc * 64, phase * p.cout + nt * BN);
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
@@ -138,7 +144,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
-          for (int sub = 0; sub < CV_SUB; ++sub) {
+          for (int sub = 0; sub < SUB; ++sub) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               umma_bf16_ss(tmem_base + sub * BN, umma_desc_k_sw128(a_addr + sub * (128 * 128) + k * 32),
@@ -161,8 +167,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       int st, phase, nt;
       decode_item(item, st, phase, nt);
-      const int n0 = (st / p.tiles_y) * p.n_box;
-      const int y0 = (st % p.tiles_y) * p.h_box;
+      const int x0 = (st % p.tiles_x) * p.w_box;
+      const int n0 = (st / p.tiles_x / p.tiles_y) * p.n_box;
+      const int y0 = (st / p.tiles_x % p.tiles_y) * p.h_box;
       const int py = phase >> 1, px = phase & 1;
       // per-channel scale / shift (folded BN) or bias of this n-tile -> smem, double-buffered by item parity
       float* sc = s_ss[it & 1][0];
@@ -176,9 +183,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       mbar_wait(&tfull_bar, acc_ph);
       tc_fence_after();
 #pragma unroll 1
-      for (int sub = 0; sub < CV_SUB; ++sub) {
+      for (int sub = 0; sub < SUB; ++sub) {
         const int pr = sub * 128 + quad * 32 + lane;            // pixel row inside the box (x fastest)
-        const int xx = pr % p.w_box;
+        const int xx = x0 + pr % p.w_box;
         const int yy = (pr / p.w_box) % p.h_box;
         const int nn = pr / (p.w_box * p.h_box);
         const int img = n0 + nn, iy = y0 + yy;
@@ -269,27 +276,32 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-static int pick_boxes(int n, int h, int w, ConvParams& p) {
-  p.w_box = w;
-  if (w > 256 || CV_ROWS % w != 0) return -1;
-  const int rows = CV_ROWS / w;                 // image rows per super tile if a tile stays inside one image
-  if (rows <= h && h % rows == 0) {
+static int pick_boxes(int n, int h, int w, ConvParams& p, int box_rows = CV_ROWS) {
+  // the widest strip of image columns whose pixels fill whole image rows of the box: w_box divides w and box_rows
+  p.w_box = 0;
+  for (int wb = w; wb >= 1; --wb)
+    if (w % wb == 0 && box_rows % wb == 0 && wb <= 256) {
+      const int rows = box_rows / wb;             // image rows per item if an item stays inside one image
+      if ((rows <= h && h % rows == 0) || rows % h == 0) { p.w_box = wb; break; }
+    }
+  if (p.w_box == 0) return -1;
+  const int rows = box_rows / p.w_box;
+  if (rows <= h) {
     p.h_box = rows; p.n_box = 1;
-  } else if (rows % h == 0) {
-    p.h_box = h; p.n_box = rows / h;
   } else {
-    return -1;
+    p.h_box = h; p.n_box = rows / h;
   }
   if (p.h_box > 256 || p.n_box > 256) return -1;
+  p.tiles_x = w / p.w_box;
   p.tiles_y = h / p.h_box;
-  p.super_tiles = ((n + p.n_box - 1) / p.n_box) * p.tiles_y;
+  p.super_tiles = ((n + p.n_box - 1) / p.n_box) * p.tiles_y * p.tiles_x;
   return 0;
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, int SUB = CV_SUB>
 static int launch_conv(const void* in, const void* wts, ConvParams& p, int k_total, int w_rows, int max_ctas,
                        cudaStream_t stream) {
-  constexpr int STAGE_BYTES = CV_ROWS * 128 + BN * 128;
+  constexpr int STAGE_BYTES = SUB * 128 * 128 + BN * 128;
   constexpr int STAGES = (196608 / STAGE_BYTES) > 6 ? 6 : (196608 / STAGE_BYTES);
   constexpr int smem = STAGES * STAGE_BYTES + 1024;
   CUtensorMap tin, tw;
@@ -302,7 +314,7 @@ static int launch_conv(const void* in, const void* wts, ConvParams& p, int k_tot
   uint32_t wb[2] = {64, (uint32_t)BN};
   if (make_tma_desc(&tw, TMA_BF16, wts, 2, wd, ws, wb, TMA_SWIZZLE_128B)) return -1;
   p.n_tiles = (p.cout + BN - 1) / BN;
-  auto kern = conv_igemm_kernel<BN, MODE>;
+  auto kern = conv_igemm_kernel<BN, MODE, SUB>;
   static bool configured = false;
   if (!configured) {
     VPB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -335,6 +347,11 @@ int deconv4x4s2_affine(const void* in, const void* wphase, const float* scale, c
   ConvParams p{};
   p.n = n; p.h = h; p.w = w; p.cin = cin; p.cout = cout; p.scale = scale; p.shift = shift; p.out = out;
   p.floor = relu ? 0.f : -INFINITY;
+  // Cout = 256 (every ViTPose decoder): one 256-channel tile over 256-pixel strips (VPB_DECONV_WIDE=0: the 128-channel
+  // tiles over 384 pixels, for A/B)
+  static const bool wide = getenv("VPB_DECONV_WIDE") == nullptr || atoi(getenv("VPB_DECONV_WIDE")) != 0;
+  if (wide && cout % 256 == 0 && pick_boxes(n, h, w, p, 256) == 0)
+    return launch_conv<256, MODE_DECONV, 2>(in, wphase, p, 4 * cin, 4 * cout, max_ctas, stream);
   VPB_REQUIRE(pick_boxes(n, h, w, p) == 0, "deconv: %dx%d input does not tile into 384-pixel TMA boxes", h, w);
   if (cout % 128 == 0 || cout > 64) return launch_conv<128, MODE_DECONV>(in, wphase, p, 4 * cin, 4 * cout, max_ctas, stream);
   return launch_conv<64, MODE_DECONV>(in, wphase, p, 4 * cin, 4 * cout, max_ctas, stream);
