@@ -161,9 +161,10 @@ def _cos(a, b):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('src,fused', [([2, 0, 0, 2, 1, 2], True), ([2, 0, 0, 2, 2], True), ([1, 1, 1], True),
-                                       ([0, 2, 1, 0], False)])
-def test_topdown_moe_forward_train_backward_vs_oracle(src, fused, monkeypatch):
+@pytest.mark.parametrize('src,fused,drop', [([2, 0, 0, 2, 1, 2], True, 0.0), ([2, 0, 0, 2, 2], True, 0.0),
+                                            ([1, 1, 1], True, 0.0), ([0, 2, 1, 0], False, 0.0),
+                                            ([2, 0, 1, 2, 1, 0, 0, 2], True, 0.4)])
+def test_topdown_moe_forward_train_backward_vs_oracle(src, fused, drop, monkeypatch):
     """TopDownMoE.forward_train -> sum of the losses -> backward() on the B200 path against torch.autograd over the fp32
     oracle (pinned to the live reference above): mixed batches in arbitrary order, an absent dataset (its expert and
     head get zero / no gradient), a homogeneous batch. Tolerances as in tests/test_gpu_train_step.py."""
@@ -177,8 +178,24 @@ def test_topdown_moe_forward_train_backward_vs_oracle(src, fused, monkeypatch):
     n = len(src)
     img, target, tw, metas = _train_batch(n, 5, 5, src)
     ref_sd = {k: v.clone() for k, v in sd.items()}
-    l_ref, hm_ref, g_ref = VT.train_loss_and_grads_moe(ref_sd, img, target, tw, cfg, torch.tensor(src))
+    scales = None
+    if drop > 0:            # stochastic depth: the SAME per-crop factors in both implementations (batch order)
+        gen = torch.Generator().manual_seed(13)
+        scales = []
+        for p_drop in torch.linspace(0, drop, 2).tolist():
+            keep = 1.0 - p_drop
+            scales.append(tuple(torch.floor(keep + torch.rand(n, generator=gen)) / keep for _ in range(2)))
+        assert any((s_ == 0).any() for pair in scales for s_ in pair), 'the masks must drop something'
+    l_ref, hm_ref, g_ref = VT.train_loss_and_grads_moe(ref_sd, img, target, tw, cfg, torch.tensor(src),
+                                                       drop_scales=scales)
     model = model.cuda().train()
+    if scales is not None:
+        # forward_train sorts the crops by dataset: the injected factors follow the crops
+        order, _ = model.backbone.dataset_runs(src)
+        perm = torch.tensor(order)
+        model.backbone.drop_path_rate = drop
+        model.backbone._drop_path_scales = [tuple(s_[perm].float().cuda().contiguous() for s_ in pair)
+                                            for pair in scales]
     out = model.train_step(dict(img=img.cuda(), target=target.cuda(), target_weight=tw.cuda(), img_metas=metas))
     assert set(out['log_vars']) == {'main_stream_loss', 'main_stream_acc', '1_loss', '1_acc', '2_loss', '2_acc', 'loss'}
     out['loss'].backward()
@@ -203,7 +220,10 @@ def test_topdown_moe_forward_train_backward_vs_oracle(src, fused, monkeypatch):
         for l in range(2):
             gw = dict(model.named_parameters())[f'backbone.blocks.{l}.mlp.experts.{e}.weight'].grad
             assert gw is not None
-            assert (float(gw.abs().max()) > 0) == (e in present), (e, l)
+            live = float(g_ref[f'backbone.blocks.{l}.mlp.experts.{e}.weight'].abs().max()) > 0
+            assert (float(gw.abs().max()) > 0) == live, (e, l)
+            if drop == 0:
+                assert live == (e in present), (e, l)
     bad = {k: v for k, v in worst.items() if v[0] > 0.15 or v[1] < 0.99}
     top = sorted(worst.items(), key=lambda kv: -kv[1][0])[:5]
     assert not bad, f'gradient mismatch (rel err, cosine): {bad}; worst five: {top}'
