@@ -29,11 +29,15 @@ class TopDown(nn.Module):
         super().__init__()
         self.fp16_enabled = False
         # crops in the first H2D chunk when forward_test is fed host tensors (VPB_HOST_CHUNK: A/B switch)
-        self.host_chunk = int(os.environ.get('VPB_HOST_CHUNK', '32'))
+        self.host_chunk = int(os.environ.get('VPB_HOST_CHUNK', '0'))      # 0: chosen from the backbone width below
         # optional schedule of leading chunk sizes, the rest goes as one batch (VPB_HOST_CHUNKS=16,48: A/B switch)
         self.host_chunks = [int(v) for v in os.environ.get('VPB_HOST_CHUNKS', '').split(',') if v]
         self._copy_stream = None
         self.backbone = builder.build_backbone(backbone)
+        if self.host_chunk <= 0:
+            # the first chunk must compute for as long as the copy of the rest takes (~10.7 us per crop over PCIe):
+            # ViTPose-S needs ~37 us per crop (with flip) -> 64 crops of 256, ViTPose-B 84 us -> 32 (measured), L / H less
+            self.host_chunk = 64 if int(getattr(self.backbone, 'embed_dim', 768)) < 768 else 32
         self.train_cfg = train_cfg
         self.test_cfg = test_cfg if test_cfg is not None else {}
         if neck is not None:
