@@ -3,16 +3,23 @@
 //   S = (Q K^T) * scale, P = softmax(S), O = P V            (forward, attention.cu)
 //   dV = P^T dO,  dP = dO V^T,  dS = P o (dP - delta),  delta_i = sum_d dO_id O_id,
 //   dQ = scale * dS K,  dK = scale * dS^T Q
-// One CTA per (crop, head). Q, K, V, dO of the head are TMA-loaded once as 128B-swizzled [192 x 64] tiles (plus a
-// 16-column SWIZZLE_32B tile each for head_dim 80; TMEM column numbers below are those of head_dim <= 64); the
-// query rows are processed in two 128-row tiles (the second is half empty). Per tile:
+// One CTA per (crop, head). Q, K, V, dO and O of the head are TMA-loaded once as 128B-swizzled [192 x 64] tiles (plus
+// a 16-column SWIZZLE_32B tile each for head_dim 80; TMEM column numbers below are those of head_dim <= 64); O lands
+// in the dS area and is only read for delta. The query rows are processed in two 128-row tiles (the second is half
+// empty). Per tile t, in issue order:
 //   tcgen05.mma S  = Q_t K^T       -> TMEM [0,192)   ; 256 threads ((query row, half of the keys) each) form
 //                                                       P = exp2(S * scale * log2e - lse) with the forward pass's
 //                                                       log-sum-exp in ONE pass and write it (bf16) to smem
-//   tcgen05.mma dP = dO_t V^T      -> same TMEM columns; the threads form dS = scale * P o (dP - delta) (bf16, smem)
-//   tcgen05.mma dQ_t = dS K        -> TMEM [192,256)  (K consumed as an MN-major operand)
-//   tcgen05.mma dK += dS^T Q_t, dV += P^T dO_t -> TMEM [256,512): A operands are the P / dS tiles read MN-major
+//   tcgen05.mma dP = dO_t V^T      -> same TMEM columns; meanwhile (tile 0) the threads form delta from the dO / O tiles
+//   tcgen05.mma dV += P^T dO_t     -> TMEM [384,512)  (needs only P: runs while the threads form dS)
+//                                                       dS = scale * P o (dP - delta) (bf16, smem)
+//   tcgen05.mma S of tile t + 1    (head_dim <= 64: its columns are free once dP has been read)
+//   tcgen05.mma dQ_t = dS K        -> TMEM [192,256)  (K consumed as an MN-major operand), committed on its own:
+//                                                       drained while dK runs (tile 0: behind the wait for dP of tile 1)
+//   tcgen05.mma dK += dS^T Q_t     -> TMEM [256,384): the A operands of dK / dV are the dS / P tiles read MN-major
 //                                                 (transposed) straight from where the threads wrote them
+// The bias gradient of attn.qkv (column sums of dQ / dK / dV) is taken from the staged bf16 output blocks. Block b
+// prefetches the tiles of block b + #SMs into L2. VPB_ATTBWD_DEBUG=<cta>: clock64 stamps of every phase of that CTA.
 // Nothing of size T x T ever touches HBM. Every MMA is M = 128: rows past the sequence end compute garbage from
 // whatever follows the tile in shared memory, land in TMEM lanes that are never read, and never enter a contraction.
 #include <cstdio>
