@@ -671,42 +671,55 @@ __device__ __forceinline__ int deconv_shift(int parity, int tap) { return tap ==
 
 // IdxT = unsigned when every index fits 32 bits (always, at the sizes of the training step): 64-bit divisions by
 // run-time values cost ~100 instructions each and made these copy kernels instruction-bound.
+// One thread = one (input pixel, 8-channel group): the pixel's coordinates are decoded once, its 3 x 3 neighbourhood is
+// read once (9 loads) and written to the 16 (phase, tap) slots that use it (one thread per 16-byte OUTPUT element with
+// six run-time divisions each ran at 2.8 TB/s).
 template <typename IdxT>
 __global__ void deconv_gather_x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int h, int w, int cin8,
                                        long long pixels_, long long total) {
-  const IdxT idx = static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const IdxT idx = static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x;      // over pixels * cin8
   if (static_cast<long long>(idx) >= total) return;
   const IdxT pixels = static_cast<IdxT>(pixels_);
   const int c8 = static_cast<int>(idx % cin8);
-  IdxT rest = idx / cin8;
-  const int t = static_cast<int>(rest % 4);
-  rest /= 4;
-  const IdxT pix = rest % pixels;
-  const int ph = static_cast<int>(rest / pixels);
+  const IdxT pix = idx / cin8;
   const int j = static_cast<int>(pix % w), i = static_cast<int>((pix / w) % h);
   const IdxT im = pix / (static_cast<IdxT>(w) * h);
-  const int ii = i + deconv_shift(ph >> 1, t >> 1), jj = j + deconv_shift(ph & 1, t & 1);
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (ii >= 0 && ii < h && jj >= 0 && jj < w) v = x[((im * h + ii) * w + jj) * cin8 + c8];
-  out[idx] = v;
+  uint4 nb[3][3];                               // nb[dy + 1][dx + 1]
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int ii = i + dy, jj = j + dx;
+      nb[dy + 1][dx + 1] = (ii >= 0 && ii < h && jj >= 0 && jj < w) ? x[((im * h + ii) * w + jj) * cin8 + c8]
+                                                                  : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+  for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int dy = deconv_shift(ph >> 1, t >> 1), dx = deconv_shift(ph & 1, t & 1);
+      out[((static_cast<IdxT>(ph) * pixels + pix) * 4 + t) * cin8 + c8] = nb[dy + 1][dx + 1];
+    }
 }
+// One thread = one (input pixel, 8-channel group) and its 16 (phase, tap) sources: one row of 16 * Cout per pixel.
 template <typename IdxT>
 __global__ void deconv_gather_dy_kernel(const uint4* __restrict__ dy, uint4* __restrict__ out, int h, int w, int cout8,
                                         long long total) {
-  const IdxT idx = static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const IdxT idx = static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x;      // over pixels * cout8
   if (static_cast<long long>(idx) >= total) return;
   const int c8 = static_cast<int>(idx % cout8);
-  IdxT rest = idx / cout8;
-  const int pt = static_cast<int>(rest % 16);
-  const IdxT pix = rest / 16;
-  const int ph = pt >> 2, t = pt & 3;
+  const IdxT pix = idx / cout8;
   const int j = static_cast<int>(pix % w), i = static_cast<int>((pix / w) % h);
   const IdxT im = pix / (static_cast<IdxT>(w) * h);
-  const int ii = i - deconv_shift(ph >> 1, t >> 1), jj = j - deconv_shift(ph & 1, t & 1);
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (ii >= 0 && ii < h && jj >= 0 && jj < w)
-    v = dy[((im * 2 * h + 2 * ii + (ph >> 1)) * 2 * w + 2 * jj + (ph & 1)) * cout8 + c8];
-  out[idx] = v;
+#pragma unroll
+  for (int pt = 0; pt < 16; ++pt) {
+    const int ph = pt >> 2, t = pt & 3;
+    const int ii = i - deconv_shift(ph >> 1, t >> 1), jj = j - deconv_shift(ph & 1, t & 1);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (ii >= 0 && ii < h && jj >= 0 && jj < w)
+      v = dy[((im * 2 * h + 2 * ii + (ph >> 1)) * 2 * w + 2 * jj + (ph & 1)) * cout8 + c8];
+    out[(pix * 16 + pt) * cout8 + c8] = v;
+  }
 }
 template <typename IdxT>
 __global__ void deconv_phase_dy_kernel(const uint4* __restrict__ dy, uint4* __restrict__ out, int h, int w, int cout8,
@@ -724,9 +737,9 @@ __global__ void deconv_phase_dy_kernel(const uint4* __restrict__ dy, uint4* __re
 }
 int deconv_gather_x(const void* x, void* out, int n, int h, int w, int cin, cudaStream_t stream) {
   VPB_REQUIRE(n > 0 && h > 0 && w > 0 && cin % 8 == 0, "deconv_gather_x: bad shape");
-  const long long pixels = static_cast<long long>(n) * h * w, total = 4 * pixels * 4 * (cin / 8);
+  const long long pixels = static_cast<long long>(n) * h * w, total = pixels * (cin / 8);      // threads
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
-  if (total + 256 < (1ll << 31))           // the source index is < total / 16, the padded grid stays below 2^32
+  if (16 * total + 256 < (1ll << 31))      // the largest output index is < 16 * total
     deconv_gather_x_kernel<unsigned><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
                                                                reinterpret_cast<uint4*>(out), h, w, cin / 8, pixels, total);
   else
@@ -737,9 +750,9 @@ int deconv_gather_x(const void* x, void* out, int n, int h, int w, int cin, cuda
 }
 int deconv_gather_dy(const void* dy, void* out, int n, int h, int w, int cout, cudaStream_t stream) {
   VPB_REQUIRE(n > 0 && h > 0 && w > 0 && cout % 8 == 0, "deconv_gather_dy: bad shape");
-  const long long total = static_cast<long long>(n) * h * w * 16 * (cout / 8);
+  const long long total = static_cast<long long>(n) * h * w * (cout / 8);                        // threads
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
-  if (total + 256 < (1ll << 31))           // the source index is < total / 4
+  if (16 * total + 256 < (1ll << 31))      // the largest output index is < 16 * total, source indices < 4 * total
     deconv_gather_dy_kernel<unsigned><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(dy),
                                                                 reinterpret_cast<uint4*>(out), h, w, cout / 8, total);
   else
