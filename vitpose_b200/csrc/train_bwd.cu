@@ -494,9 +494,10 @@ int layernorm_bwd(const float* x, const float* gamma, const void* dy, float* dx_
                   int M, int D, float eps, cudaStream_t stream) {
   VPB_REQUIRE(M > 0 && D > 0 && D % 128 == 0, "layernorm_bwd: D=%d must be a multiple of 128", D);
   const int warps = 8;
-  // two blocks per SM: enough warps to stream at HBM speed, few enough blocks that the parameter-gradient atomics
-  // (one per column per block) stay negligible
-  int rows_per_warp = (M + 2 * sm_count() * warps - 1) / (2 * sm_count() * warps);
+  // One wave of blocks: the kernel keeps two rows in flight per warp in registers (255 per thread), so ONE 8-warp block
+  // is resident per SM; sizing the grid for two per SM ran 256 blocks as 148 + 108 (12 row times per warp instead of
+  // 11 at 12288 rows). Few blocks also keep the parameter-gradient atomics (one per column per block) negligible.
+  int rows_per_warp = (M + sm_count() * warps - 1) / (sm_count() * warps);
   if (rows_per_warp < 1) rows_per_warp = 1;
   const int total_warps = (M + rows_per_warp - 1) / rows_per_warp;
   dim3 grid((total_warps + warps - 1) / warps), block(warps * 32);
