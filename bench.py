@@ -248,8 +248,6 @@ def measure_inference(ctx, workload, n, steps, warmup, profile=False, e2e_steps=
     # ---- timed region (device-resident inputs) -------------------------------------------------------
     L = _lib.lib()
     launches0 = L.vpb_launch_count()
-    if profile:
-        L.vpb_profile_enable(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ctx.barrier()
     m0 = ctx.sampler.mark()
@@ -260,11 +258,27 @@ def measure_inference(ctx, workload, n, steps, warmup, profile=False, e2e_steps=
     ctx.barrier()
     m1 = ctx.sampler.mark()
     ms = ev0.elapsed_time(ev1) / steps
-    records = _lib.profile_records() if profile else []
-    if profile:
-        L.vpb_profile_enable(0)
     launches = L.vpb_launch_count() - launches0
     clocks = ctx.sampler.region(m0, m1) if rank == 0 else None
+    # ---- per-kernel durations: the SAME K steps once more, right away, with a CUDA-event pair around every launch ----
+    # (on the launching stream, vpb_profile_enable). Recording the events inside the timed region above cost 0.3-0.6 ms
+    # per step — an event between two launches takes the programmatic-dependent-launch overlap away (same-box A/B,
+    # tools/profile_overhead.py: 20.61 / 20.96 ms without, 21.20 / 21.26 ms with) — so `value` is timed without them and
+    # the roofline / step shares come from this second pass, whose own step time is reported next to them (it can be
+    # lower or higher than the timed one: the power-capped SM clock drifts by a few percent between the two passes).
+    records, ms_events = [], None
+    if profile:
+        L.vpb_profile_enable(1)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.barrier()
+        p0.record()
+        for i in range(steps):
+            device_step(i)
+        p1.record()
+        ctx.barrier()
+        ms_events = p0.elapsed_time(p1) / steps
+        records = _lib.profile_records()
+        L.vpb_profile_enable(0)
 
     # ---- end to end through the reference-facing API: pinned host crops -> host keypoints ----------------
     e2e_steps = e2e_steps or steps
@@ -281,7 +295,7 @@ def measure_inference(ctx, workload, n, steps, warmup, profile=False, e2e_steps=
     total = n * world
     out = dict(workload=workload, crops_per_gpu=n, global_crops=total, ms=ms, e2e_ms=e2e_ms,
                value=total / (ms / 1e3), e2e_value=total / (e2e_ms / 1e3), clocks=clocks, launches=int(launches),
-               records=records, mode=mode, cfg=cfg, sd=sd, K=K,
+               records=records, ms_events=ms_events, mode=mode, cfg=cfg, sd=sd, K=K,
                h2d=int(host[0].numel() * 4 + n * 16), d2h=int(n * K * 3 * 4))
     del model, eng, dev_img, host
     torch.cuda.empty_cache()
@@ -498,7 +512,7 @@ def main():
         achieved = flops[dom] / dom_ms / 1e9
         tgemm_ms = sum(float(np.sum(by_tag[k])) for k in flops) / args.steps
         tgemm_tf = sum(flops[k] * len(by_tag[k]) for k in flops) / args.steps / tgemm_ms / 1e9
-        shares = {k: round(float(np.sum(v)) / args.steps / r['ms'], 4) for k, v in by_tag.items()}
+        shares = {k: round(float(np.sum(v)) / args.steps / r['ms_events'], 4) for k, v in by_tag.items()}
         per_launch_ms = {k: round(float(np.mean(v)), 4) for k, v in by_tag.items()}
         # DRAM bytes of one fc1 launch: NOT measured by this run — read from the committed ncu --set full capture of
         # this same command (B workload, 256 crops), see traffic_source
@@ -515,7 +529,11 @@ def main():
                         frac_of_burst=achieved / pk['tf_burst'],
                         transformer_gemms_tflops=tgemm_tf, transformer_gemms_frac=tgemm_tf / pk['tf_sustained'],
                         transformer_gemms_frac_of_burst=tgemm_tf / pk['tf_burst'],
-                        step_share_by_kernel=shares, ms_per_launch=per_launch_ms)
+                        step_share_by_kernel=shares, ms_per_launch=per_launch_ms,
+                        kernel_timing=('CUDA-event pair around every launch on the launching stream, recorded in a '
+                                       'second pass of the same %d steps right after the timed region (events inside '
+                                       'it cost 0.3-0.6 ms per step: no launch overlap across an event)' % args.steps),
+                        ms_per_step_with_events=r['ms_events'])
         line = inference_record(r, world, pk, args.steps, args.warmup, 'weak')
         line['vs_baseline'] = None
         line['roofline'] = roofline
