@@ -329,3 +329,19 @@ def test_moe_loads_plain_vit_checkpoint(tmp_path):
     # freeze_ffn also freezes the expert FFNs that replace the plain ones
     frozen = V.build_backbone(dict(cfg['backbone'], freeze_ffn=True))
     assert not any(p.requires_grad for n, p in frozen.named_parameters() if '.mlp.' in n)
+
+
+def test_moe_forward_train_has_no_cpu_path_and_host_chunk_follows_width():
+    """The product path fails loudly without CUDA tensors (no CPU fallback); the first H2D chunk of forward_test is
+    chosen from the backbone width (64 crops below D = 768, 32 otherwise)."""
+    import vitpose_b200 as V
+    from vitpose_b200 import _lib
+    cfg = _moe_train_cfg()
+    model = V.build_posenet(cfg).train()
+    img, target, tw, metas = _train_batch(3, 5, 1, [1, 0, 2])
+    with pytest.raises(_lib.VitposeLibError):
+        model(img=img, target=target, target_weight=tw, img_metas=metas, return_loss=True)
+    assert model._vpb_dataset_runs is None                       # reset even when the step fails
+    assert model.host_chunk == 64                                # tiny config: D = 128
+    b = V.build_posenet(configs.baseline_model_cfg('B-classic-17'))
+    assert b.host_chunk == 32 and b.host_chunks == []
